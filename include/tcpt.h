@@ -1,0 +1,147 @@
+/* tcpt.h — C ABI of the B200-native path-integration backend (libtcpt.so / libtcpt.a, nvcc sm_100a).
+ *
+ * Drop-in boundary for toy-cpu-pathtracing's per-pixel path-integration hot path.  The reference has NO FFI at this seam;
+ * the seam is the generic Rust trait
+ *     pub trait Renderer { fn render<S: Sampler>(&mut self, p: UVec2) -> Self::Color }      renderer/src/renderer.rs:93-98
+ * driven one pixel at a time by RendererImage::render (renderer/src/renderer.rs:120-134).  A GPU backend replaces the
+ * whole-frame loop, so the entry points below are what a `GpuRendererImage::render` would bind (see INTEGRATION.md for the
+ * Rust `extern "C"` block and `flatten.rs`).  Everything is POD: plain pointers and sizes, caller-owned host buffers unless a
+ * parameter says "device"; the context owns all device memory.  Every function returns 0 on success or a negative
+ * TCPT_ERR_* code and never unwinds across the boundary (the reference panics instead: renderer/src/main.rs:61,91,138,235).
+ * There is no CPU fallback: every entry point that computes anything fails with TCPT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef TCPT_H
+#define TCPT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tcpt_ctx tcpt_ctx;
+
+enum {
+    TCPT_OK = 0,
+    TCPT_ERR_INVALID = -1, /* bad argument / call order */
+    TCPT_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+    TCPT_ERR_LIMIT = -3,   /* scene exceeds a compiled limit (BVH depth, lights) */
+    TCPT_ERR_NOMEM = -4
+};
+
+/* ---- enumerations mirrored from the reference CLI (renderer/src/main.rs:20-53) */
+enum { TCPT_INTEGRATOR_PT = 0, TCPT_INTEGRATOR_NEE = 1, TCPT_INTEGRATOR_MIS = 2 }; /* SrgbRendererPt / Nee / Mis */
+enum { TCPT_SAMPLER_RANDOM = 0, TCPT_SAMPLER_SOBOL = 1 };                          /* RandomSampler / ZSobolSampler */
+
+/* ---- material description (scene/src/material/impls/*.rs constructors) */
+enum {
+    TCPT_MAT_LAMBERT = 0,       /* LambertMaterial::new(albedo, normal)                         lambert_material.rs:15-31 */
+    TCPT_MAT_EMISSIVE = 1,      /* EmissiveMaterial::new(radiance, intensity)                   emissive_material.rs:15-37 */
+    TCPT_MAT_PLASTIC = 2,       /* PlasticMaterial::new(eta, color, normal, thin, roughness)    plastic_material.rs:17-52 */
+    TCPT_MAT_SIMPLE_PBR = 3,    /* SimplePbrMaterial::new(base, metallic, roughness, normal, ior) simple_pbr_material.rs:38-53 */
+    TCPT_MAT_CLEARCOAT_PBR = 4  /* SimpleClearcoatPbrMaterial::new(...)                          simple_pbr_clearcoat_material.rs:17-73 */
+};
+/* SpectrumParameter (material/parameter.rs:13-21) over the Spectrum kinds that reach the hot path */
+enum {
+    TCPT_SPEC_CONSTANT = 0,        /* ConstantSpectrum::new(value[0]) */
+    TCPT_SPEC_RGB_ALBEDO_SRGB = 1, /* RgbAlbedoSpectrum::<ColorSrgb>::new(value)        (gamma-encoded sRGB colour) */
+    TCPT_SPEC_RGB_ALBEDO_LINEAR = 2, /* RgbAlbedoSpectrum::<ColorSrgbLinear>::new(value) */
+    TCPT_SPEC_D65 = 3,             /* presets::cie_illum_d6500() */
+    TCPT_SPEC_TEXTURE_SRGB = 4     /* SpectrumParameter::texture(RgbTexture::load_srgb, SpectrumType::Albedo) */
+};
+typedef struct { int32_t kind; float value[3]; int32_t texture; } tcpt_spectrum_param;
+typedef struct { int32_t kind; /* 0 constant, 1 gray8 FloatTexture */ float value; int32_t texture; int32_t gamma_corrected; } tcpt_float_param;
+typedef struct { int32_t texture; /* -1 = NormalParameter::none() */ int32_t flip_y; } tcpt_normal_param;
+typedef struct {
+    int32_t type;
+    tcpt_spectrum_param color;   /* albedo | radiance | plastic colour | base colour */
+    tcpt_float_param intensity;  /* emissive */
+    tcpt_normal_param normal;
+    float eta;                   /* plastic */
+    int32_t thin_surface;        /* plastic */
+    tcpt_float_param roughness, metallic, ior;
+    tcpt_float_param coat_ior, coat_roughness, coat_thickness;
+    tcpt_spectrum_param coat_tint;
+} tcpt_material_desc;
+
+/* ---- render parameters = RendererArgs + Camera + SrgbRenderer*::new arguments
+ *      (renderer/src/renderer.rs:84-90, camera.rs:26-48, pt_renderer.rs:92-101) */
+typedef struct {
+    uint32_t width, height, spp, seed, max_depth;
+    int32_t integrator, sampler;
+    float exposure, fov_deg;
+    float cam_pos[3], cam_dir[3], cam_up[3]; /* Camera::set_look_to arguments (normalised again inside, like the reference) */
+    /* sharding: this call renders image rows y with y % row_stride == row_offset and sample indices [spp_begin, spp_end)
+     * (0,0 = all rows / all samples).  Tile(row) sharding keeps the per-pixel sample order => bitwise equal to one GPU. */
+    uint32_t row_offset, row_stride;
+    uint32_t spp_begin, spp_end;
+    uint32_t max_slots;                      /* wavefront size in paths (0 = default 4 Mi) */
+} tcpt_render_params;
+
+typedef struct {
+    uint64_t paths;          /* (pixel, sample) iterations of base_renderer.rs:160 */
+    uint64_t closest_rays;   /* Scene::intersect calls   (scene.rs:80) */
+    uint64_t shadow_rays;    /* Scene::intersect_p calls (scene.rs:93) */
+    uint64_t box_tests, tri_tests; /* only counted when tcpt_set_option(ctx,"count_tests",1) */
+    uint64_t kernel_launches;
+    double render_ms;        /* device time of the last tcpt_render* (CUDA events) */
+    double trace_closest_ms, trace_shadow_ms, shade_ms, generate_ms, film_ms; /* per stage, when option "stage_timing" = 1 */
+    uint32_t passes, max_bvh_depth;
+} tcpt_stats;
+
+/* ---- context */
+int tcpt_create(int device_id, tcpt_ctx** out);
+void tcpt_destroy(tcpt_ctx* ctx);
+const char* tcpt_last_error(const tcpt_ctx* ctx);
+int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
+/* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65: spectrum/src/presets.rs);
+ * rgb2spec = rgb_to_spec table, 64 z-nodes + [3][64][64][64][3] f32 (spectrum/src/rgb_sigmoid_polynomial.rs:35-84) */
+int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_floats);
+
+/* ---- host scene construction: replaces scene::Scene::{load_obj, create_primitive, build} (scene/src/scene.rs:54-76).
+ * Meshes are passed as the arrays TriangleMesh::load_obj holds after tobj (geometry/impls/triangle_mesh.rs:141-180). */
+int tcpt_scene_clear(tcpt_ctx* ctx);
+int tcpt_scene_add_mesh(tcpt_ctx* ctx, const float* positions, const float* normals, const float* uvs /*nullable*/, int n_vertices,
+                        const uint32_t* indices, int n_triangles);               /* returns geometry index */
+int tcpt_scene_add_texture(tcpt_ctx* ctx, const uint8_t* data, uint32_t width, uint32_t height, uint32_t channels /*1|3*/);
+int tcpt_scene_add_material(tcpt_ctx* ctx, const tcpt_material_desc* desc);
+int tcpt_scene_add_primitive(tcpt_ctx* ctx, int geometry, int material, const float local_to_world[16] /*column major*/);
+int tcpt_scene_add_env_light(tcpt_ctx* ctx, float intensity, const float* rgb /*h*w*3*/, uint32_t width, uint32_t height,
+                             const float local_to_world[16]);                    /* EnvironmentLight::new environment_light.rs:34-84 */
+/* Scene::build(&camera): bakes world_to_render = translate(-cam_pos), builds BLAS/TLAS with the reference's exact SAH topology,
+ * flattens to the device layout and uploads (scene.rs:64-76, bvh.rs:92-295). */
+int tcpt_scene_build(tcpt_ctx* ctx, const float cam_pos[3]);
+
+/* ---- the hot path: replaces RendererImage::<SrgbRenderer{Pt,Nee,Mis}>::render::<S>() (renderer/src/renderer.rs:120-134).
+ * out_acc  : host, width*height*3 f32, the Sensor accumulators (sum over samples of exposed linear-sRGB; sensor.rs:76-77)
+ * out_srgb : host, optional, width*height*3 f32 after /spp, clip, Reinhard, sRGB OETF (sensor.rs:81-88) — what `pixels` holds */
+int tcpt_render(tcpt_ctx* ctx, const tcpt_render_params* params, float* out_acc, float* out_srgb);
+/* same, accumulating into a DEVICE buffer (width*height*3 f32) for multi-GPU film reduction; stream = cudaStream_t or NULL */
+int tcpt_render_device(tcpt_ctx* ctx, const tcpt_render_params* params, void* dev_acc, void* stream);
+/* Sensor::to_rgb on a device accumulator (after the NCCL reduce): dev_srgb = OETF(Reinhard(max(acc/spp,0))) */
+int tcpt_finalize_device(tcpt_ctx* ctx, const void* dev_acc, uint32_t width, uint32_t height, uint32_t spp, void* dev_srgb, void* stream);
+int tcpt_get_stats(const tcpt_ctx* ctx, tcpt_stats* out);
+
+/* ---- single stages, exposed for parity tests and the traversal micro-benchmark */
+/* rays: n x {o[3], d[3], tmax}; out: n x {prim, tri, t bits, b0 bits, b1 bits, b2 bits} (prim -1 = miss; any_hit: out[0] = 0|1) */
+int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* out_hit);
+/* device-resident variant used by the micro-benchmark: dev_rays (n x 8 f32: o,tmax,d,pad), dev_hits (n x 8 x 4 B) */
+int tcpt_trace_device(tcpt_ctx* ctx, const void* dev_rays, int n, int any_hit, void* dev_hits, void* stream);
+int tcpt_sampler_stream(tcpt_ctx* ctx, int sampler, uint32_t spp, uint32_t width, uint32_t height, uint32_t seed, uint32_t px,
+                        uint32_t py, uint32_t sample_index, const int32_t* kinds /*1 = get_1d, 2 = get_2d*/, int n, float* out);
+/* RGB contribution of individual (pixel, sample) paths = what Sensor::add_sample adds for that sample */
+int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uint32_t* pixels_xy, const uint32_t* sample_indices,
+                      int n, float* out_rgb);
+
+/* ---- host-side introspection for bit-exactness tests (BVH topology, table indexing, load-time tangents) */
+/* which = -1: TLAS, else geometry index.  Records of 8 x u32 in the REFERENCE's flattened order (bvh.rs:234-295):
+ * {kind 0 inner|1 leaf|2 item, value = second_offset|item_count|item, min.xyz bits, max.xyz bits}.  Returns the node count. */
+int tcpt_get_bvh(tcpt_ctx* ctx, int which, uint32_t* out, int max_nodes);
+int tcpt_build_bvh_boxes(const float* boxes /*n x {min[3],max[3]}*/, int n, uint32_t* out, int max_nodes); /* builder alone, no device */
+int tcpt_rgb_to_coeffs(tcpt_ctx* ctx, const float rgb[3], int gamma_encoded, float coeffs[3], int32_t index[4] /*m,zi,yi,xi*/);
+int tcpt_get_mesh_tangents(tcpt_ctx* ctx, int geometry, float* out, int max_triangles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCPT_H */

@@ -1,0 +1,377 @@
+// Device-side common definitions: math helpers, device scene view, path-state SoA, samplers, spectra.
+// Compiled with --fmad=false: the parity-critical arithmetic (slab test, watertight triangle test, instance transforms,
+// Sobol float conversion, table indexing) must round exactly like the reference's unfused f32 operations
+// (last bullet).  Shading arithmetic shares the flag in this round (measured cost: see DESIGN.md).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tcpt_flat.h"
+
+namespace tcpt {
+
+#define TCPT_PI 3.14159265358979323846f
+#define TCPT_FLT_MAX 3.402823466e+38f
+#define TCPT_INF __int_as_float(0x7f800000)
+
+// ---------------------------------------------------------------- float3 helpers (component order as in glam's scalar Vec3)
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+__device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ float3 normalize(float3 a) { return a * (1.0f / length(a)); }
+__device__ __forceinline__ float comp(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// Rust f32::max/min ignore a NaN operand; CUDA fmaxf/fminf have the same rule
+__device__ __forceinline__ float rmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float rmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float signum(float x) { return isnan(x) ? x : (signbit(x) ? -1.0f : 1.0f); }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ uint32_t f2u_sat(float x) { return __float2uint_rz(x); }  // saturating, NaN -> 0, like Rust `as u32`
+
+// 3x4 affine stored as four columns of xyz (tcpt_flat_primitive::l2r / r2l)
+__device__ __forceinline__ float3 xf_point(const float* __restrict__ m, float3 p) {
+    return f3(((m[0] * p.x + m[3] * p.y) + m[6] * p.z) + m[9], ((m[1] * p.x + m[4] * p.y) + m[7] * p.z) + m[10],
+              ((m[2] * p.x + m[5] * p.y) + m[8] * p.z) + m[11]);
+}
+__device__ __forceinline__ float3 xf_vector(const float* __restrict__ m, float3 v) {
+    return f3((m[0] * v.x + m[3] * v.y) + m[6] * v.z, (m[1] * v.x + m[4] * v.y) + m[7] * v.z, (m[2] * v.x + m[5] * v.y) + m[8] * v.z);
+}
+// Transform * Normal = transpose(inverse(M)) * n, re-normalised: pass the INVERSE matrix (math/src/transform.rs:44-51)
+__device__ __forceinline__ float3 xf_normal_by_inverse(const float* __restrict__ inv, float3 n) {
+    float3 r = f3((inv[0] * n.x + inv[1] * n.y) + inv[2] * n.z, (inv[3] * n.x + inv[4] * n.y) + inv[5] * n.z, (inv[6] * n.x + inv[7] * n.y) + inv[8] * n.z);
+    return normalize(r);
+}
+
+// ---------------------------------------------------------------- 4-lane spectra (spectrum/src/sampled_spectrum.rs)
+struct S4 { float v[4]; };
+__device__ __forceinline__ S4 s4(float c) { S4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = c; return r; }
+__device__ __forceinline__ S4 s4(float4 a) { S4 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; return r; }
+__device__ __forceinline__ float4 to_f4(const S4& a) { return make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+#define S4_BINOP(op)                                                                                                   \
+    __device__ __forceinline__ S4 operator op(const S4& a, const S4& b) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] op b.v[i]; return r; }
+S4_BINOP(+) S4_BINOP(-) S4_BINOP(*)
+__device__ __forceinline__ S4 operator*(const S4& a, float s) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] * s; return r; }
+__device__ __forceinline__ S4 operator*(float s, const S4& a) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = s * a.v[i]; return r; }
+// division by zero yields zero (sampled_spectrum.rs:59-83)
+__device__ __forceinline__ S4 operator/(const S4& a, float s) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = s == 0.0f ? 0.0f : a.v[i] / s; return r; }
+__device__ __forceinline__ S4 operator/(const S4& a, const S4& b) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = b.v[i] == 0.0f ? 0.0f : a.v[i] / b.v[i]; return r; }
+__device__ __forceinline__ float s4_max(const S4& a) { return rmax(rmax(rmax(rmax(-TCPT_INF, a.v[0]), a.v[1]), a.v[2]), a.v[3]); }
+__device__ __forceinline__ float s4_avg(const S4& a) { return ((((0.0f + a.v[0]) + a.v[1]) + a.v[2]) + a.v[3]) / 4.0f; }
+__device__ __forceinline__ bool s4_is_constant(const S4& a) { return a.v[1] == a.v[0] && a.v[2] == a.v[0] && a.v[3] == a.v[0]; }
+
+// ---------------------------------------------------------------- device scene view
+struct DTexture { const uint8_t* data; uint32_t w, h, channels, pad; };
+struct DEnv {
+    const float* data; const float* marginal; const float* conditional;
+    float intensity, total_weight; uint32_t w, h; tcpt_flat_spectrum integrated; int32_t primitive;
+};
+struct DScene {
+    const float4* nodes;            // 2 x float4 per node
+    uint32_t tlas_node_count;
+    const int32_t* tlas_items;
+    const float4* tri_verts;        // 3 x float4 per slot
+    const float* positions; const float* normals; const float* uvs; const uint32_t* indices; const float* tangents;
+    const tcpt_flat_geometry* geometries;
+    const tcpt_flat_primitive* primitives; uint32_t n_primitives;
+    const tcpt_flat_material* materials;
+    const DTexture* textures;
+    const float* area_list; const float* area_table;
+    int32_t light_list[TCPT_MAX_LIGHTS]; uint32_t n_lights;
+    const DEnv* envs; uint32_t n_envs;
+    const float4* cmf;              // 470 x {x_bar, y_bar, z_bar, d65}  (spectrum/src/presets.rs tables, densely resampled)
+    const float* z_nodes; const float* rgb2spec;
+    float xyz_to_rgb[9];            // column major (color/src/gamut.rs:43-69)
+};
+
+struct DCamera { float3 s, u, nf; float scale, aspect; uint32_t width, height; };
+
+struct DRender {
+    uint32_t width, height, spp, seed, max_depth;
+    int32_t integrator, sampler;
+    float exposure;
+    uint32_t log2_spp, n_base4_digits;  // ZSobolSampler::new (z_sobol_sampler.rs:179-196)
+    // pass geometry: slot = s_local * n_pix + p_local; pixel p_local -> row rows[p_local / width]
+    uint32_t n_pix, s_begin, s_count, row_offset, row_stride, row_first, n_rows;
+};
+
+// Path state: structure of arrays of 16-byte records, one per path slot.
+struct DState {
+    float4* thr; float4* con; float4* f_prev; float4* misc;  // misc = {pdf_prev, lambda0, bits(dim), bits(flags)}
+    float4* prev_pos;
+    float4* ray_o; float4* ray_d;                            // o.xyz,tmax | d.xyz,-
+    float4* hit0; int4* hit1;                                // {t,b0,b1,b2} | {prim,tri,-,-}
+    float4* sh_o; float4* sh_d; float4* pending;             // shadow ray + pending NEE contribution
+    uint32_t* q_ext[2]; uint32_t* q_sh;
+    uint32_t* counters;                                      // [0],[1] = ext queue sizes (ping-pong), [2] = shadow queue size
+    unsigned long long* stats;                               // [0] closest rays [1] shadow rays [2] box tests [3] tri tests
+};
+
+enum : uint32_t { FLAG_SPEC_PREV = 1u, FLAG_LAMBDA_TERMINATED = 2u };
+
+// ---------------------------------------------------------------- samplers
+__constant__ uint32_t c_sobol_dim1[52];  // SOBOL_MATRICES_32[52..104) (dimension 1); dimension 0 is the bit reversal
+
+struct DSampler {
+    uint32_t kind, seed, log2_spp, nb4, morton, dim, key;
+
+    __device__ __forceinline__ static uint32_t part1by1(uint32_t x) {  // left_shift2 of a 32-bit value truncated to u32 (z_sobol_sampler.rs:54-65)
+        x &= 0x0000ffffu;
+        x = (x ^ (x << 8)) & 0x00ff00ffu;
+        x = (x ^ (x << 4)) & 0x0f0f0f0fu;
+        x = (x ^ (x << 2)) & 0x33333333u;
+        x = (x ^ (x << 1)) & 0x55555555u;
+        return x;
+    }
+    __device__ __forceinline__ static uint64_t mix_bits(uint64_t v) {
+        v ^= v >> 31; v *= 0x7fb5d329728ea185ull; v ^= v >> 27; v *= 0x81dadef4bc2dd44dull; v ^= v >> 33;
+        return v;
+    }
+    __device__ __forceinline__ static uint64_t hash(uint32_t dimension, uint32_t seed) {  // MurmurHash64A (z_sobol_sampler.rs:76-99)
+        const uint64_t M = 0xc6a4a7935bd1e995ull;
+        uint64_t h = 8ull * M;
+        uint64_t k = (uint64_t)dimension | ((uint64_t)seed << 32);
+        k *= M; k ^= k >> 47; k *= M;
+        h ^= k; h *= M;
+        h ^= h >> 47; h *= M; h ^= h >> 47;
+        return h;
+    }
+    __device__ __forceinline__ static uint32_t owen(uint32_t v, uint32_t seed) {  // FastOwenScrambler (z_sobol_sampler.rs:3-29)
+        v = __brev(v);
+        v ^= v * 0x3d20adeau; v += seed; v *= (seed >> 16) | 1u; v ^= v * 0x05526c56u; v ^= v * 0x53a22864u;
+        return __brev(v);
+    }
+    __device__ __forceinline__ static uint32_t pcg_hash2(uint32_t key, uint32_t ctr) {
+        uint32_t x = key * 747796405u + ctr * 2891336453u + 0x9e3779b9u;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        uint32_t w = ((x >> ((x >> 28u) + 4u)) ^ x) * 277803737u;
+        return (w >> 22u) ^ w;
+    }
+    __device__ __forceinline__ static float unit_float(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
+    __device__ __forceinline__ static float to_unit(uint32_t v) { return fminf((float)v * 2.3283064365386963e-10f, 0.99999994f); }
+
+    __device__ void start(uint32_t px, uint32_t py, uint32_t sample_index) {
+        dim = 0;
+        // encode_morton2 computes in u64 then truncates to u32: only the low 16 bits of x and y survive (z_sobol_sampler.rs:54-66)
+        morton = (((part1by1(py) << 1) | part1by1(px)) << log2_spp) | sample_index;
+        key = (px * 0x9e3779b9u) ^ (py * 0x85ebca6bu) ^ (sample_index * 0xc2b2ae35u) ^ seed;
+    }
+
+    // ZSobolSampler::get_sample_index (z_sobol_sampler.rs:101-156)
+    __device__ uint64_t sample_index() const {
+        // PERMUTATIONS[24][4] packed 2 bits per digit, 8 bits per permutation
+        const uint64_t P0 = 0x6c9cd8b4786ce1e4ull >> 0, P1 = 0, P2 = 0;
+        (void)P0; (void)P1; (void)P2;
+        uint64_t sidx = 0;
+        const bool pow2 = (log2_spp & 1u) == 1u;
+        const int last_digit = pow2 ? 1 : 0;
+        const uint64_t dk = 0x55555555ull * (uint64_t)dim;
+        for (int i = (int)nb4 - 1; i >= last_digit; --i) {
+            const int digit_shift = 2 * i - (pow2 ? 1 : 0);
+            uint32_t digit = (uint32_t)(((uint64_t)morton >> digit_shift) & 3ull);
+            const uint64_t higher = (digit_shift + 2) >= 64 ? 0ull : ((uint64_t)morton >> (digit_shift + 2));
+            const uint32_t p = (uint32_t)((mix_bits(higher ^ dk) >> 24) % 24ull);
+            digit = perm_digit(p, digit);
+            sidx |= (uint64_t)digit << digit_shift;
+        }
+        if (pow2) {
+            // quirk: the reference ANDs with the loop variable, which is 0 here (pbrt-v4 has `& 1`)
+            const uint64_t digit = 0ull;
+            sidx |= digit ^ (mix_bits(((uint64_t)morton >> 1) ^ dk) & 1ull);
+        }
+        return sidx;
+    }
+    __device__ __forceinline__ static uint32_t perm_digit(uint32_t p, uint32_t digit) {
+        // rows of PERMUTATIONS (z_sobol_sampler.rs:102-127), digit d stored at bits [2d, 2d+2)
+        const uint32_t T[24] = {0xE4, 0xB4, 0xD8, 0x78, 0x6C, 0x9C, 0xE1, 0xB1, 0xC9, 0x39, 0x2D, 0x8D,
+                                0xC6, 0x36, 0xD2, 0x72, 0x4E, 0x1E, 0x27, 0x87, 0x1B, 0x4B, 0x63, 0x93};
+        return (T[p] >> (2u * digit)) & 3u;
+    }
+    __device__ __forceinline__ static uint32_t sobol_dim1(uint64_t a) {
+        uint32_t v = 0;
+        for (int i = 0; a != 0; a >>= 1, ++i)
+            if (a & 1ull) v ^= c_sobol_dim1[i];
+        return v;
+    }
+
+    __device__ float get_1d() {
+        if (kind == TCPT_SAMPLER_SOBOL) {
+            const uint64_t a = sample_index();
+            dim += 1;
+            const uint64_t h = hash(dim, seed);
+            return to_unit(owen(__brev((uint32_t)a), (uint32_t)h));  // Sobol matrix 0 = identity on reversed bits; rows >= 32 are zero
+        }
+        return unit_float(pcg_hash2(key, dim++));
+    }
+    __device__ float2 get_2d() {
+        if (kind == TCPT_SAMPLER_SOBOL) {
+            const uint64_t a = sample_index();
+            dim += 2;
+            const uint64_t h = hash(dim, seed);
+            float2 r;
+            r.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+            r.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+            return r;
+        }
+        float2 r;
+        r.x = unit_float(pcg_hash2(key, dim++));
+        r.y = unit_float(pcg_hash2(key, dim++));
+        return r;
+    }
+};
+
+// independent stream standing in for rand::rng() inside shading (generalized_schlick.rs:901): keyed by (path, depth, call site)
+struct DAuxRng {
+    uint32_t key, ctr;
+    __device__ __forceinline__ float next() { return DSampler::unit_float(DSampler::pcg_hash2(key, ctr++)); }
+};
+__device__ __forceinline__ DAuxRng aux_rng(uint32_t path_key, uint32_t depth, uint32_t site) {
+    DAuxRng r; r.key = path_key ^ 0x5bd1e995u ^ ((depth * 4u + site) * 0x27d4eb2fu); r.ctr = 0; return r;
+}
+
+// ---------------------------------------------------------------- wavelengths and spectra
+struct DWavelengths { float lambda[4]; float pdf[4]; };
+__device__ __forceinline__ DWavelengths wavelengths_uniform(float lambda0, bool terminated) {  // sampled_spectrum.rs:318-336 with lambda[0] given
+    DWavelengths w;
+    w.lambda[0] = lambda0;
+    const float delta = (830.0f - 360.0f) / 4.0f;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        float l = w.lambda[i - 1] + delta;
+        if (l >= 830.0f) l = 360.0f + (l - 830.0f);
+        w.lambda[i] = l;
+    }
+    const float p = 1.0f / (830.0f - 360.0f);
+    w.pdf[0] = terminated ? p / 4.0f : p;
+    w.pdf[1] = w.pdf[2] = w.pdf[3] = terminated ? 0.0f : p;
+    return w;
+}
+__device__ __forceinline__ float srgb_to_linear(float c) { return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
+__device__ __forceinline__ float linear_to_srgb(float c) { return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f; }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float4 cmf_at(const DScene& sc, float lambda) {  // DenselySampledSpectrum::value for x,y,z,D65 at once
+    if (!(lambda >= 360.0f && lambda <= 830.0f)) return make_float4(0, 0, 0, 0);
+    uint32_t i = f2u_sat(floorf(lambda - 360.0f));
+    return i < 470u ? __ldg(&sc.cmf[i]) : make_float4(0, 0, 0, 0);
+}
+
+// RgbToSpectrumTable::get (rgb_sigmoid_polynomial.rs:87-155), sRGB-gamma typed colour
+__device__ inline void rgb_to_coeffs(const DScene& sc, float3 rgb_in, float cs[3]) {
+    float rgb[3] = {srgb_to_linear(rgb_in.x), srgb_to_linear(rgb_in.y), srgb_to_linear(rgb_in.z)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb[k] = rgb[k] > 0.0f ? rgb[k] : 0.0f;
+    // (component > 1 panics in the reference; u8/255 texels and half-scaled illuminant colours never exceed 1)
+    if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) { cs[0] = 0.0f; cs[1] = 0.0f; cs[2] = logf(rgb[0] / (1.0f - rgb[0])); return; }
+    int m = 0;
+    { float best = rgb[0]; if (rgb[1] > best) { best = rgb[1]; m = 1; } if (rgb[2] > best) m = 2; }
+    const float z = rgb[m];
+    const float x = rgb[(m + 1) % 3] * (64.0f - 1.0f) / z;
+    const float y = rgb[(m + 2) % 3] * (64.0f - 1.0f) / z;
+    const uint32_t xi = min(f2u_sat(x), 62u), yi = min(f2u_sat(y), 62u);
+    uint32_t zi = 62;
+    for (uint32_t i = 0; i <= 62; ++i) if (__ldg(&sc.z_nodes[i + 1]) > z) { zi = i; break; }
+    const float z0 = __ldg(&sc.z_nodes[zi]), z1 = __ldg(&sc.z_nodes[zi + 1]);
+    const float dx = x - (float)xi, dy = y - (float)yi, dz = (z - z0) / (z1 - z0);
+    const float* base = sc.rgb2spec + ((((size_t)m * 64 + zi) * 64 + yi) * 64 + xi) * 3;
+    const size_t sx = 3, sy = 64 * 3, sz = 64 * 64 * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float c000 = __ldg(base + i), c100 = __ldg(base + sx + i), c010 = __ldg(base + sy + i), c110 = __ldg(base + sy + sx + i);
+        const float c001 = __ldg(base + sz + i), c101 = __ldg(base + sz + sx + i), c011 = __ldg(base + sz + sy + i), c111 = __ldg(base + sz + sy + sx + i);
+        const float a0 = c000 + (c100 - c000) * dx, a1 = c010 + (c110 - c010) * dx;
+        const float b0 = c001 + (c101 - c001) * dx, b1 = c011 + (c111 - c011) * dx;
+        const float a = a0 + (a1 - a0) * dy, b = b0 + (b1 - b0) * dy;
+        cs[i] = a + (b - a) * dz;
+    }
+}
+
+// a resolved Spectrum (SpectrumTrait object) on the device
+struct DSpectrum { int kind; float c[3]; float scale; };  // 0 const 1 sigmoid 2 sigmoid*scale*D65 3 D65
+__device__ __forceinline__ float spectrum_value(const DScene& sc, const DSpectrum& s, float lambda) {
+    if (s.kind == 0) return s.c[0];
+    if (s.kind == 3) return cmf_at(sc, lambda).w;
+    const float t = (lambda - 360.0f) / (830.0f - 360.0f);
+    const float sg = sigmoidf(t * t * s.c[0] + t * s.c[1] + s.c[2]);
+    if (s.kind == 1) return sg;
+    return s.scale * sg * cmf_at(sc, lambda).w;
+}
+__device__ __forceinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl, bool terminated) {
+    S4 r = s4(0.0f);
+    r.v[0] = spectrum_value(sc, s, wl.lambda[0]);
+    if (terminated) return r;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) r.v[i] = spectrum_value(sc, s, wl.lambda[i]);
+    return r;
+}
+// RgbIlluminantSpectrum::<ColorSrgb>::new (rgb_illuminant_spectrum.rs:27-40)
+__device__ __forceinline__ DSpectrum illuminant_from_rgb(const DScene& sc, float3 rgb) {
+    DSpectrum s; s.kind = 2;
+    const float mx = rmax(rgb.x, rmax(rgb.y, rgb.z));
+    s.scale = 2.0f * mx;
+    rgb_to_coeffs(sc, rgb / s.scale, s.c);
+    return s;
+}
+
+// ---------------------------------------------------------------- textures (scene/src/texture/sampler.rs)
+__device__ __forceinline__ float fract_rs(float x) { return x - truncf(x); }
+struct Taps { uint32_t x0, y0, x1, y1; float fx, fy; };
+__device__ __forceinline__ Taps bilinear_taps(uint32_t w, uint32_t h, float2 uv) {
+    const float u = fabsf(fract_rs(uv.x)), v = 1.0f - fabsf(fract_rs(uv.y));
+    const float x = u * ((float)w - 1.0f), y = v * ((float)h - 1.0f);
+    Taps t;
+    t.x0 = f2u_sat(floorf(x)); t.y0 = f2u_sat(floorf(y));
+    t.x1 = min(t.x0 + 1u, w - 1u); t.y1 = min(t.y0 + 1u, h - 1u);
+    t.fx = x - (float)t.x0; t.fy = y - (float)t.y0;
+    return t;
+}
+__device__ __forceinline__ float lerp2d(float p00, float p10, float p01, float p11, float fx, float fy) {
+    const float top = p00 * (1.0f - fx) + p10 * fx, bottom = p01 * (1.0f - fx) + p11 * fx;
+    return top * (1.0f - fy) + bottom * fy;
+}
+__device__ inline float3 tex_rgb(const DTexture& t, float2 uv) {
+    const Taps k = bilinear_taps(t.w, t.h, uv);
+    const uint8_t* a = t.data + ((size_t)k.y0 * t.w + k.x0) * 3; const uint8_t* b = t.data + ((size_t)k.y0 * t.w + k.x1) * 3;
+    const uint8_t* c = t.data + ((size_t)k.y1 * t.w + k.x0) * 3; const uint8_t* d = t.data + ((size_t)k.y1 * t.w + k.x1) * 3;
+    float o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+        o[ch] = lerp2d((float)__ldg(a + ch) / 255.0f, (float)__ldg(b + ch) / 255.0f, (float)__ldg(c + ch) / 255.0f, (float)__ldg(d + ch) / 255.0f, k.fx, k.fy);
+    return f3(o[0], o[1], o[2]);
+}
+__device__ inline float tex_gray(const DTexture& t, float2 uv) {
+    const Taps k = bilinear_taps(t.w, t.h, uv);
+    return lerp2d((float)__ldg(t.data + (size_t)k.y0 * t.w + k.x0) / 255.0f, (float)__ldg(t.data + (size_t)k.y0 * t.w + k.x1) / 255.0f,
+                  (float)__ldg(t.data + (size_t)k.y1 * t.w + k.x0) / 255.0f, (float)__ldg(t.data + (size_t)k.y1 * t.w + k.x1) / 255.0f, k.fx, k.fy);
+}
+
+__device__ __forceinline__ DSpectrum param_spectrum(const DScene& sc, const tcpt_flat_spectrum& p, float2 uv) {
+    DSpectrum s;
+    if (p.kind == 4) { s.kind = 1; s.scale = 1.0f; rgb_to_coeffs(sc, tex_rgb(sc.textures[p.texture], uv), s.c); return s; }  // rgb_texture.rs:48-66
+    s.kind = p.kind; s.c[0] = p.c[0]; s.c[1] = p.c[1]; s.c[2] = p.c[2]; s.scale = p.scale;
+    return s;
+}
+__device__ __forceinline__ float param_float(const DScene& sc, const tcpt_flat_float& p, float2 uv) {
+    if (!p.is_texture) return p.value;
+    const float v = tex_gray(sc.textures[p.texture], uv);
+    return p.gamma_corrected ? srgb_to_linear(v) : v;  // float_texture.rs:45-52
+}
+
+// warp-aggregated queue append: every lane of the warp must call it (pred = false for lanes with nothing to push)
+__device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool pred) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+}  // namespace tcpt
