@@ -33,7 +33,7 @@ enum {
 enum { TCPT_INTEGRATOR_PT = 0, TCPT_INTEGRATOR_NEE = 1, TCPT_INTEGRATOR_MIS = 2 }; /* SrgbRendererPt / Nee / Mis */
 enum { TCPT_SAMPLER_RANDOM = 0, TCPT_SAMPLER_SOBOL = 1 };                          /* RandomSampler / ZSobolSampler */
 
-/* ---- material description (scene/src/material/impls/*.rs constructors) */
+/* ---- material description (scene/src/material/impls/ constructors) */
 enum {
     TCPT_MAT_LAMBERT = 0,       /* LambertMaterial::new(albedo, normal)                         lambert_material.rs:15-31 */
     TCPT_MAT_EMISSIVE = 1,      /* EmissiveMaterial::new(radiance, intensity)                   emissive_material.rs:15-37 */
@@ -89,7 +89,9 @@ typedef struct {
     uint32_t passes, max_bvh_depth;
 } tcpt_stats;
 
-/* ---- context */
+/* ---- context.  tcpt_create returns TCPT_ERR_CUDA when no sm_100 device is usable; *out is then still a context on which only
+ * the HOST-side functions work (scene construction, tcpt_get_bvh, tcpt_rgb_to_coeffs, tcpt_get_mesh_tangents, tcpt_last_error):
+ * tcpt_set_tables and tcpt_scene_build do their host half and then report TCPT_ERR_CUDA.  Nothing is ever rendered on the CPU. */
 int tcpt_create(int device_id, tcpt_ctx** out);
 void tcpt_destroy(tcpt_ctx* ctx);
 const char* tcpt_last_error(const tcpt_ctx* ctx);
@@ -125,7 +127,8 @@ int tcpt_get_stats(const tcpt_ctx* ctx, tcpt_stats* out);
 /* ---- single stages, exposed for parity tests and the traversal micro-benchmark */
 /* rays: n x {o[3], d[3], tmax}; out: n x {prim, tri, t bits, b0 bits, b1 bits, b2 bits} (prim -1 = miss; any_hit: out[0] = 0|1) */
 int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* out_hit);
-/* device-resident variant used by the micro-benchmark: dev_rays (n x 8 f32: o,tmax,d,pad), dev_hits (n x 8 x 4 B) */
+/* device-resident variant used by the micro-benchmark (SoA, fully coalesced):
+ * dev_rays = n x float4 {o.xyz, tmax} followed by n x float4 {d.xyz, -}; dev_hits = n x float4 {t,b0,b1,b2} followed by n x uint2 {prim,tri} */
 int tcpt_trace_device(tcpt_ctx* ctx, const void* dev_rays, int n, int any_hit, void* dev_hits, void* stream);
 int tcpt_sampler_stream(tcpt_ctx* ctx, int sampler, uint32_t spp, uint32_t width, uint32_t height, uint32_t seed, uint32_t px,
                         uint32_t py, uint32_t sample_index, const int32_t* kinds /*1 = get_1d, 2 = get_2d*/, int n, float* out);

@@ -4,13 +4,20 @@
  * builder in csrc/host_scene.cpp which stands in for it here) produces one tcpt_flat_scene and hands it to
  * tcpt_upload_flat_scene(); everything device-side reads only these arrays.
  *
- * BVH nodes (TLAS and all BLAS, concatenated) are 32-byte records fetched as two 16-byte loads:
- *     lo = {min.x, min.y, min.z, bits(a)}     hi = {max.x, max.y, max.z, bits(b)}
- *     inner: b == 0, a = index of the SECOND child (first child = this + 1)         [scene/src/bvh.rs:259-266 second_offset]
- *     leaf : b = item_count (> 0), a = first item slot                               [scene/src/bvh.rs:271-286]
- * Node indices are relative to the BVH's node_base and enumerate inner/leaf nodes in the reference's pre-order (item records
- * removed), so "later leaf in DFS order" == larger node index; item slots enumerate leaf items in the same order.
- * BLAS items are stored pre-gathered: tri_verts[3*slot+k] = {p_k.xyz, bits(k==0 ? triangle_index : k==1 ? degenerate_flag : 0)}.
+ * BVH nodes (TLAS and all BLAS, concatenated) are 64-byte CHILD-PAIR records fetched as four 16-byte loads.  One record per
+ * inner node of the reference tree, holding the boxes of BOTH children, so one fetch decides both slab tests:
+ *     q0 = {lo0.xyz, bits(ref0)}   q1 = {hi0.xyz, bits(cnt0)}   q2 = {lo1.xyz, bits(ref1)}   q3 = {hi1.xyz, bits(cnt1)}
+ *     child k inner : cnt_k == 0, ref_k = index of the child's own pair record (relative to the BVH's node_base)
+ *     child k leaf  : cnt_k  > 0 = item_count, ref_k = first item slot (relative to slot_base)   [scene/src/bvh.rs:271-286]
+ *     child k absent: cnt_k == 0, ref_k = 0xffffffff
+ * Record 0 of every BVH is an entry record {child0 = the root (inner or leaf) with the ROOT box, child1 = absent}, so the root
+ * box is tested like the reference does (bvh.rs:362).  Records are emitted in the reference's pre-order of inner nodes
+ * (bvh.rs:234-295 with leaf/item records removed); item slots enumerate leaf items in the reference's leaf order, so
+ * "later leaf in DFS order" == larger first-slot.  The tree SHAPE, every box and every per-leaf item order are the
+ * reference's; only the storage differs (tcpt_get_bvh() returns the reference's own flattened order for comparison).
+ * BLAS items are stored pre-gathered: tri_verts[3*slot+k] = {p_k.xyz, bits(w_k)} with w_0 = triangle index,
+ * w_1 = degenerate flag (|e1 x e2|^2 == 0, math/src/ray.rs:50-57), w_2 = first slot of the leaf holding this slot.
+ * TLAS items: tlas_items[2*slot] = primitive index, tlas_items[2*slot+1] = first slot of the leaf holding this slot.
  */
 #ifndef TCPT_FLAT_H
 #define TCPT_FLAT_H
@@ -23,9 +30,9 @@ extern "C" {
 #endif
 
 #define TCPT_MAX_LIGHTS 16
-#define TCPT_TRAVERSAL_STACK 96
+#define TCPT_TRAVERSAL_STACK 64
 
-typedef struct { float lo[4]; float hi[4]; } tcpt_bvh_node;
+typedef struct { float q[16]; } tcpt_bvh_node; /* 4 x float4, see above */
 
 typedef struct {
     uint32_t node_base, node_count;   /* into bvh_nodes */
@@ -76,7 +83,7 @@ typedef struct {
 typedef struct {
     const tcpt_bvh_node* bvh_nodes; uint64_t n_bvh_nodes;
     uint32_t tlas_node_count;               /* TLAS occupies bvh_nodes[0 .. tlas_node_count) */
-    const int32_t* tlas_items; uint32_t n_tlas_items; /* primitive index per TLAS item slot */
+    const int32_t* tlas_items; uint32_t n_tlas_items; /* 2 x int32 per TLAS item slot: {primitive, leaf_first_slot} */
     const float* tri_verts; uint64_t n_tri_slots;     /* 12 floats per slot */
     const float* positions; const float* normals; const float* uvs; uint64_t n_vertices; /* 3,3,2 floats per vertex */
     const uint32_t* indices; uint64_t n_triangles;
@@ -90,7 +97,7 @@ typedef struct {
     const int32_t* light_list; uint32_t n_lights;   /* primitive indices, LightSamplerFactory order (light_sampler.rs:168-187) */
     const tcpt_flat_env* envs; uint32_t n_envs;
     const float* env_floats; uint64_t n_env_floats;
-    uint32_t max_bvh_depth;                 /* TLAS depth + deepest BLAS depth, must be < TCPT_TRAVERSAL_STACK */
+    uint32_t max_bvh_depth;                 /* TLAS depth + largest TLAS leaf + deepest BLAS depth, must be < TCPT_TRAVERSAL_STACK */
 } tcpt_flat_scene;
 
 /* copies everything to the device owned by ctx; replaces any previously uploaded scene */

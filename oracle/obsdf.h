@@ -405,13 +405,13 @@ struct GeneralizedSchlickBsdf {
         return vis / jac;
     }
     // 64-sample stochastic estimate driven by an independent RNG stream (generalized_schlick.rs:893-918)
-    SampledSpectrum directional_albedo(Vec3 wo, SamplerBase& rng) const {
+    SampledSpectrum directional_albedo(Vec3 wo, AuxRng rng) const {
         SampledSpectrum sum = SampledSpectrum::zero();
         for (int i = 0; i < 64; ++i) {
-            float uc = u32_to_unit_float(rng.aux_u32());
+            float uc = rng.next();
             Vec2 uv;
-            uv.x = u32_to_unit_float(rng.aux_u32());
-            uv.y = u32_to_unit_float(rng.aux_u32());
+            uv.x = rng.next();
+            uv.y = rng.next();
             BsdfSample s;
             if (sample(wo, uv, uc, &s)) {
                 float ci = std::fabs(s.wi.z);
@@ -450,7 +450,8 @@ struct Material {
 struct MaterialContext {
     const Tables* T;
     const std::vector<Texture>* textures;
-    SamplerBase* rng;  // aux stream for directional_albedo
+    uint32_t aux_base = 0;  // aux streams for directional_albedo: one per (path, bounce, call site)
+    uint32_t depth = 0;
 };
 
 inline Spectrum sample_spectrum_param(const MaterialContext& c, const SpectrumParam& p, Vec2 uv) {
@@ -609,7 +610,7 @@ inline MaterialSample material_sample(const MaterialContext& c, const Material& 
             ClearcoatParams cp = load_coat(c, m, sp.uv, wl);
             if (cp.thickness <= 0.0f) return b.sample(wo_nm, uc, uv, fr.from_nm);
             GeneralizedSchlickBsdf coat = cp.bsdf();
-            float fc = coat.directional_albedo(wo_nm, *c.rng).average();
+            float fc = coat.directional_albedo(wo_nm, aux_rng(c.aux_base, c.depth, 0)).average();
             if (uc < fc) {
                 float uc2 = uc / fc;
                 BsdfSample s;
@@ -650,7 +651,7 @@ inline SampledSpectrum material_evaluate(const MaterialContext& c, const Materia
             ClearcoatParams cp = load_coat(c, m, sp.uv, wl);
             if (cp.thickness <= 0.0f) return b.evaluate(wo_nm, wi_nm);
             GeneralizedSchlickBsdf coat = cp.bsdf();
-            float fc = coat.directional_albedo(wo_nm, *c.rng).average();
+            float fc = coat.directional_albedo(wo_nm, aux_rng(c.aux_base, c.depth, 1)).average();
             SampledSpectrum coat_f = coat.evaluate(wo_nm, wi_nm);
             SampledSpectrum sub_f = b.evaluate(wo_nm, wi_nm);
             SampledSpectrum att = coat_attenuation(cp.tint, cp.thickness, wo_nm.z) * coat_attenuation(cp.tint, cp.thickness, wi_nm.z);
@@ -679,7 +680,7 @@ inline float material_pdf(const MaterialContext& c, const Material& m, const Sam
             ClearcoatParams cp = load_coat(c, m, sp.uv, wl);
             if (cp.thickness <= 0.0f) return b.pdf(wo_nm, wi_nm);
             GeneralizedSchlickBsdf coat = cp.bsdf();
-            float fc = coat.directional_albedo(wo_nm, *c.rng).average();
+            float fc = coat.directional_albedo(wo_nm, aux_rng(c.aux_base, c.depth, 2)).average();
             return coat.pdf(wo_nm, wi_nm) * fc + b.pdf(wo_nm, wi_nm) * (1.0f - fc);
         }
         default: return 0.0f;

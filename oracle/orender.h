@@ -167,8 +167,8 @@ struct PathTracer {
     // BaseSrgbRenderer::render, one (pixel, sample_index) path (base_renderer.rs:160-276); returns the RGB the sensor would add
     Vec3 trace_path(SamplerBase& smp, uint32_t px, uint32_t py, uint32_t sample_index, RayStats* st) const {
         const Tables& T = scene.T;
-        MaterialContext mc{&T, &scene.textures, &smp};
         smp.start_pixel_sample(px, py, sample_index);
+        MaterialContext mc{&T, &scene.textures, smp.aux_base(), 0};
         SampledSpectrum throughput = SampledSpectrum::one();
         SampledSpectrum contribution = SampledSpectrum::zero();
         float u = smp.get_1d();
@@ -189,6 +189,7 @@ struct PathTracer {
         for (uint32_t depth = 1; depth <= rp.max_depth; ++depth) {
             const Material& mat = scene.materials[hit.si.material];
             if (mat.type == MAT_EMISSIVE) break;  // no BSDF (base_renderer.rs:199-202)
+            mc.depth = depth;
             Mat4 r2t = shading_transform(hit.si);
             Vec3 wo = transform_vector3(r2t, hit.wo);
             TangentShadingPoint tsp;

@@ -38,15 +38,17 @@ struct SamplerBase {
     virtual float get_1d() = 0;
     virtual Vec2 get_2d() = 0;
     Vec2 get_2d_pixel() { return get_2d(); }
-    // independent stream used where the reference calls rand::rng() inside shading (generalized_schlick.rs:901)
-    virtual uint32_t aux_u32() = 0;
+    // key of the independent streams used where the reference calls rand::rng() inside shading (generalized_schlick.rs:901);
+    // the reference's ThreadRng is OS-seeded, so any fixed stream is an equally valid stand-in.  One stream per
+    // (path, bounce, call site), defined identically in the device code (csrc/dcommon.cuh aux_rng).
+    virtual uint32_t aux_base() const = 0;
 };
 
 // z_sobol_sampler.rs:33-235
 struct ZSobolSampler : SamplerBase {
     const uint32_t* matrices;  // 2 x 52 words (sobol_matrices.rs:7, dims 0 and 1)
     uint32_t dimension = 0, seed = 0, log2_spp = 0, n_base4_digits = 0, morton_index = 0;
-    uint32_t aux_key = 0, aux_ctr = 0;
+    uint32_t aux_key = 0;
 
     static uint32_t log2_int(uint32_t v) { return v == 0 ? 0 : 31 - (uint32_t)__builtin_clz(v); }
     static uint32_t round_up_pow2(uint32_t v) { return v <= 1 ? 1u : 1u << (32 - __builtin_clz(v - 1)); }
@@ -97,7 +99,6 @@ struct ZSobolSampler : SamplerBase {
         // u32 shift silently drops high bits; Rust `<<` on u32 with shift < 32 wraps the value bits out
         morton_index = (encode_morton2(px, py) << log2_spp) | sample_index;
         aux_key = (px * 0x9e3779b9u) ^ (py * 0x85ebca6bu) ^ (sample_index * 0xc2b2ae35u) ^ seed ^ 0x5bd1e995u;
-        aux_ctr = 0;
     }
 
     uint64_t get_sample_index() const {
@@ -155,7 +156,7 @@ struct ZSobolSampler : SamplerBase {
         r.y = sobol_sample(idx, 1, (uint32_t)(bits >> 32));
         return r;
     }
-    uint32_t aux_u32() override;
+    uint32_t aux_base() const override { return aux_key; }
 };
 
 // Counter RNG shared by definition with the device code ("pcg4d"-style hash of (key, counter)); stands in for
@@ -174,16 +175,19 @@ inline uint32_t pcg_hash2(uint32_t key, uint32_t ctr) {
 // rand 0.9 StandardUniform for f32: 24 random bits * 2^-24
 inline float u32_to_unit_float(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 
-inline uint32_t ZSobolSampler::aux_u32() { return pcg_hash2(aux_key, aux_ctr++); }
+struct AuxRng {
+    uint32_t key, ctr;
+    float next() { return u32_to_unit_float(pcg_hash2(key, ctr++)); }
+};
+inline AuxRng aux_rng(uint32_t aux_base, uint32_t depth, uint32_t site) { return AuxRng{aux_base ^ ((depth * 4u + site) * 0x27d4eb2fu), 0u}; }
 
 struct RandomSampler : SamplerBase {
-    uint32_t seed, key = 0, ctr = 0, aux_key = 0, aux_ctr = 0;
+    uint32_t seed, key = 0, ctr = 0, aux_key = 0;
     explicit RandomSampler(uint32_t seed_) : seed(seed_) {}
     void start_pixel_sample(uint32_t px, uint32_t py, uint32_t sample_index) override {
         key = (px * 0x9e3779b9u) ^ (py * 0x85ebca6bu) ^ (sample_index * 0xc2b2ae35u) ^ seed;
         ctr = 0;
         aux_key = key ^ 0x5bd1e995u;
-        aux_ctr = 0;
     }
     float get_1d() override { return u32_to_unit_float(pcg_hash2(key, ctr++)); }
     Vec2 get_2d() override {
@@ -192,7 +196,7 @@ struct RandomSampler : SamplerBase {
         r.y = get_1d();
         return r;
     }
-    uint32_t aux_u32() override { return pcg_hash2(aux_key, aux_ctr++); }
+    uint32_t aux_base() const override { return aux_key; }
 };
 
 }  // namespace orc

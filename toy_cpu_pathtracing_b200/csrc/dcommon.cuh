@@ -1,7 +1,7 @@
-// Device-side common definitions: math helpers, device scene view, path-state SoA, samplers, spectra.
+// Device-side common definitions: math helpers, device scene view, wavefront buffers, samplers, spectra, textures.
 // Compiled with --fmad=false: the parity-critical arithmetic (slab test, watertight triangle test, instance transforms,
 // Sobol float conversion, table indexing) must round exactly like the reference's unfused f32 operations
-// (last bullet).  Shading arithmetic shares the flag in this round (measured cost: see DESIGN.md).
+// (last bullet).  Shading arithmetic shares the flag (measured cost: see DESIGN.md).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,6 +24,7 @@ __device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a
 __device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
 __device__ __forceinline__ float3 cross(float3 a, float3 b) { return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+__device__ __forceinline__ float length_squared(float3 a) { return dot(a, a); }
 __device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
 __device__ __forceinline__ float3 normalize(float3 a) { return a * (1.0f / length(a)); }
 __device__ __forceinline__ float comp(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
@@ -48,6 +49,28 @@ __device__ __forceinline__ float3 xf_normal_by_inverse(const float* __restrict__
     return normalize(r);
 }
 
+// 3x3 linear part of the tangent-frame transforms (column major: c0, c1, c2).  The reference builds a glam Mat4 from three
+// columns and calls Mat4::inverse (math/src/transform.rs:186-203, 216-244); with last row/column (0,0,0,1) the cofactor scheme
+// reduces to the expressions below term by term (the vanished terms are exact zeros), so the values match the 4x4 inverse.
+struct M3 { float3 c0, c1, c2; };
+__device__ __forceinline__ M3 m3_inverse(const M3& s) {
+    const float m00 = s.c0.x, m01 = s.c0.y, m02 = s.c0.z, m10 = s.c1.x, m11 = s.c1.y, m12 = s.c1.z, m20 = s.c2.x, m21 = s.c2.y, m22 = s.c2.z;
+    M3 r;
+    r.c0 = f3(m11 * m22 - m12 * m21, -(m01 * m22 - m02 * m21), m01 * m12 - m02 * m11);
+    r.c1 = f3(-(m10 * m22 - m12 * m20), m00 * m22 - m02 * m20, -(m00 * m12 - m02 * m10));
+    r.c2 = f3(m10 * m21 - m11 * m20, -(m00 * m21 - m01 * m20), m00 * m11 - m01 * m10);
+    const float det = (m00 * r.c0.x + m01 * r.c1.x) + m02 * r.c2.x;
+    const float rcp = 1.0f / det;
+    r.c0 = r.c0 * rcp; r.c1 = r.c1 * rcp; r.c2 = r.c2 * rcp;
+    return r;
+}
+__device__ __forceinline__ float3 m3_vector(const M3& m, float3 v) { return (m.c0 * v.x + m.c1 * v.y) + m.c2 * v.z; }
+// Transform * Normal with the per-call inverse().transpose() (math/src/transform.rs:44-51): pass inverse(M)
+__device__ __forceinline__ float3 m3_normal_by_inverse(const M3& inv, float3 n) {
+    return normalize(f3((inv.c0.x * n.x + inv.c0.y * n.y) + inv.c0.z * n.z, (inv.c1.x * n.x + inv.c1.y * n.y) + inv.c1.z * n.z,
+                        (inv.c2.x * n.x + inv.c2.y * n.y) + inv.c2.z * n.z));
+}
+
 // ---------------------------------------------------------------- 4-lane spectra (spectrum/src/sampled_spectrum.rs)
 struct S4 { float v[4]; };
 __device__ __forceinline__ S4 s4(float c) { S4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = c; return r; }
@@ -64,6 +87,8 @@ __device__ __forceinline__ S4 operator/(const S4& a, const S4& b) { S4 r; _Pragm
 __device__ __forceinline__ float s4_max(const S4& a) { return rmax(rmax(rmax(rmax(-TCPT_INF, a.v[0]), a.v[1]), a.v[2]), a.v[3]); }
 __device__ __forceinline__ float s4_avg(const S4& a) { return ((((0.0f + a.v[0]) + a.v[1]) + a.v[2]) + a.v[3]) / 4.0f; }
 __device__ __forceinline__ bool s4_is_constant(const S4& a) { return a.v[1] == a.v[0] && a.v[2] == a.v[0] && a.v[3] == a.v[0]; }
+__device__ __forceinline__ S4 s4_sqrt(const S4& a) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = sqrtf(a.v[i]); return r; }
+__device__ __forceinline__ S4 s4_clamp(const S4& a, float lo, float hi) { S4 r; _Pragma("unroll") for (int i = 0; i < 4; ++i) r.v[i] = clampf(a.v[i], lo, hi); return r; }
 
 // ---------------------------------------------------------------- device scene view
 struct DTexture { const uint8_t* data; uint32_t w, h, channels, pad; };
@@ -72,9 +97,8 @@ struct DEnv {
     float intensity, total_weight; uint32_t w, h; tcpt_flat_spectrum integrated; int32_t primitive;
 };
 struct DScene {
-    const float4* nodes;            // 2 x float4 per node
-    uint32_t tlas_node_count;
-    const int32_t* tlas_items;
+    const float4* nodes;            // 4 x float4 per child-pair record (include/tcpt_flat.h)
+    const int2* tlas_items;         // {primitive, leaf_first_slot}
     const float4* tri_verts;        // 3 x float4 per slot
     const float* positions; const float* normals; const float* uvs; const uint32_t* indices; const float* tangents;
     const tcpt_flat_geometry* geometries;
@@ -89,30 +113,32 @@ struct DScene {
     float xyz_to_rgb[9];            // column major (color/src/gamut.rs:43-69)
 };
 
-struct DCamera { float3 s, u, nf; float scale, aspect; uint32_t width, height; };
+struct DCamera { float3 s, u, nf; float scale, aspect; };
 
 struct DRender {
     uint32_t width, height, spp, seed, max_depth;
     int32_t integrator, sampler;
     float exposure;
     uint32_t log2_spp, n_base4_digits;  // ZSobolSampler::new (z_sobol_sampler.rs:179-196)
-    // pass geometry: slot = s_local * n_pix + p_local; pixel p_local -> row rows[p_local / width]
-    uint32_t n_pix, s_begin, s_count, row_offset, row_stride, row_first, n_rows;
+    // pass geometry: slot = s_local * n_pix + p_local ; owned pixel index = pix_begin + p_local ;
+    // owned pixel k -> x = k % width, y = row_offset + (k / width) * row_stride ; sample_index = s_begin + s_local
+    uint32_t n_pix, pix_begin, s_begin, s_count, row_offset, row_stride;
 };
 
-// Path state: structure of arrays of 16-byte records, one per path slot.
+// Wavefront buffers.  Path state is a structure of arrays of 16-byte records indexed by path slot; ray queues, hit records
+// and shadow queues are indexed by QUEUE POSITION so every stage reads and writes them fully coalesced.
 struct DState {
-    float4* thr; float4* con; float4* f_prev; float4* misc;  // misc = {pdf_prev, lambda0, bits(dim), bits(flags)}
-    float4* prev_pos;
-    float4* ray_o; float4* ray_d;                            // o.xyz,tmax | d.xyz,-
-    float4* hit0; int4* hit1;                                // {t,b0,b1,b2} | {prim,tri,-,-}
-    float4* sh_o; float4* sh_d; float4* pending;             // shadow ray + pending NEE contribution
-    uint32_t* q_ext[2]; uint32_t* q_sh;
-    uint32_t* counters;                                      // [0],[1] = ext queue sizes (ping-pong), [2] = shadow queue size
-    unsigned long long* stats;                               // [0] closest rays [1] shadow rays [2] box tests [3] tri tests
+    float4* thr; float4* con; float4* fprev; float4* misc;  // misc = {pdf_prev, lambda0, bits(dim), bits(flags | depth << 8)}
+    float4* ppos;                                           // previous path vertex (MIS light pdf needs it)
+    float4* rgb;                                            // per-path sensor contribution, reduced per pixel by k_film
+    float4* ext_o[2]; float4* ext_d[2];                     // {o.xyz, tmax} | {d.xyz, bits(slot)}   (ping-pong)
+    float4* hit0; uint2* hit1;                              // {t, b0, b1, b2} | {prim, tri}
+    float4* sh_o; float4* sh_d; float4* sh_c;               // shadow ray + pending NEE contribution (sh_d.w = slot | finalize << 31)
+    uint32_t* counters;                                     // [0],[1] extension queue sizes (ping-pong), [2] shadow queue size
+    unsigned long long* stats;                              // [0] closest rays [1] shadow rays [2] box tests [3] tri tests [4] paths
 };
 
-enum : uint32_t { FLAG_SPEC_PREV = 1u, FLAG_LAMBDA_TERMINATED = 2u };
+enum : uint32_t { FLAG_SPEC_PREV = 1u, FLAG_LAMBDA_TERMINATED = 2u, FLAG_SAMPLED_PREV = 4u };
 
 // ---------------------------------------------------------------- samplers
 __constant__ uint32_t c_sobol_dim1[52];  // SOBOL_MATRICES_32[52..104) (dimension 1); dimension 0 is the bit reversal
@@ -155,42 +181,40 @@ struct DSampler {
     __device__ __forceinline__ static float unit_float(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
     __device__ __forceinline__ static float to_unit(uint32_t v) { return fminf((float)v * 2.3283064365386963e-10f, 0.99999994f); }
 
-    __device__ void start(uint32_t px, uint32_t py, uint32_t sample_index) {
+    __device__ __forceinline__ void start(uint32_t px, uint32_t py, uint32_t sample_index) {
         dim = 0;
         // encode_morton2 computes in u64 then truncates to u32: only the low 16 bits of x and y survive (z_sobol_sampler.rs:54-66)
         morton = (((part1by1(py) << 1) | part1by1(px)) << log2_spp) | sample_index;
         key = (px * 0x9e3779b9u) ^ (py * 0x85ebca6bu) ^ (sample_index * 0xc2b2ae35u) ^ seed;
     }
 
-    // ZSobolSampler::get_sample_index (z_sobol_sampler.rs:101-156)
-    __device__ uint64_t sample_index() const {
-        // PERMUTATIONS[24][4] packed 2 bits per digit, 8 bits per permutation
-        const uint64_t P0 = 0x6c9cd8b4786ce1e4ull >> 0, P1 = 0, P2 = 0;
-        (void)P0; (void)P1; (void)P2;
-        uint64_t sidx = 0;
-        const bool pow2 = (log2_spp & 1u) == 1u;
-        const int last_digit = pow2 ? 1 : 0;
-        const uint64_t dk = 0x55555555ull * (uint64_t)dim;
-        for (int i = (int)nb4 - 1; i >= last_digit; --i) {
-            const int digit_shift = 2 * i - (pow2 ? 1 : 0);
-            uint32_t digit = (uint32_t)(((uint64_t)morton >> digit_shift) & 3ull);
-            const uint64_t higher = (digit_shift + 2) >= 64 ? 0ull : ((uint64_t)morton >> (digit_shift + 2));
-            const uint32_t p = (uint32_t)((mix_bits(higher ^ dk) >> 24) % 24ull);
-            digit = perm_digit(p, digit);
-            sidx |= (uint64_t)digit << digit_shift;
-        }
-        if (pow2) {
-            // quirk: the reference ANDs with the loop variable, which is 0 here (pbrt-v4 has `& 1`)
-            const uint64_t digit = 0ull;
-            sidx |= digit ^ (mix_bits(((uint64_t)morton >> 1) ^ dk) & 1ull);
-        }
-        return sidx;
-    }
     __device__ __forceinline__ static uint32_t perm_digit(uint32_t p, uint32_t digit) {
         // rows of PERMUTATIONS (z_sobol_sampler.rs:102-127), digit d stored at bits [2d, 2d+2)
         const uint32_t T[24] = {0xE4, 0xB4, 0xD8, 0x78, 0x6C, 0x9C, 0xE1, 0xB1, 0xC9, 0x39, 0x2D, 0x8D,
                                 0xC6, 0x36, 0xD2, 0x72, 0x4E, 0x1E, 0x27, 0x87, 0x1B, 0x4B, 0x63, 0x93};
         return (T[p] >> (2u * digit)) & 3u;
+    }
+    // ZSobolSampler::get_sample_index (z_sobol_sampler.rs:101-156)
+    __device__ uint64_t sample_index() const {
+        uint64_t sidx = 0;
+        const bool pow2 = (log2_spp & 1u) == 1u;
+        const int last_digit = pow2 ? 1 : 0;
+        const uint64_t dk = 0x55555555ull * (uint64_t)dim;
+        int i = (int)nb4 - 1;
+        for (; i >= last_digit; --i) {
+            const int digit_shift = 2 * i - (pow2 ? 1 : 0);
+            uint32_t digit = (uint32_t)(((uint64_t)morton >> digit_shift) & 3ull);
+            const uint64_t higher = (uint64_t)morton >> (digit_shift + 2);
+            const uint32_t p = (uint32_t)((mix_bits(higher ^ dk) >> 24) % 24ull);
+            digit = perm_digit(p, digit);
+            sidx |= (uint64_t)digit << digit_shift;
+        }
+        if (pow2) {
+            // quirk: the reference ANDs with the loop variable (0 after the loop whenever n_base4_digits >= 1); pbrt-v4 has `& 1`
+            const uint64_t digit = (uint64_t)morton & (uint64_t)(int64_t)i;
+            sidx |= digit ^ (mix_bits(((uint64_t)morton >> 1) ^ dk) & 1ull);
+        }
+        return sidx;
     }
     __device__ __forceinline__ static uint32_t sobol_dim1(uint64_t a) {
         uint32_t v = 0;
@@ -209,23 +233,23 @@ struct DSampler {
         return unit_float(pcg_hash2(key, dim++));
     }
     __device__ float2 get_2d() {
+        float2 r;
         if (kind == TCPT_SAMPLER_SOBOL) {
             const uint64_t a = sample_index();
             dim += 2;
             const uint64_t h = hash(dim, seed);
-            float2 r;
             r.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
             r.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
             return r;
         }
-        float2 r;
         r.x = unit_float(pcg_hash2(key, dim++));
         r.y = unit_float(pcg_hash2(key, dim++));
         return r;
     }
 };
 
-// independent stream standing in for rand::rng() inside shading (generalized_schlick.rs:901): keyed by (path, depth, call site)
+// Independent stream standing in for rand::rng() inside shading (generalized_schlick.rs:901, an OS-seeded ThreadRng in the
+// reference, so only its distribution can be reproduced): keyed by (path, bounce, call site), shared by definition with the oracle.
 struct DAuxRng {
     uint32_t key, ctr;
     __device__ __forceinline__ float next() { return DSampler::unit_float(DSampler::pcg_hash2(key, ctr++)); }
@@ -235,7 +259,7 @@ __device__ __forceinline__ DAuxRng aux_rng(uint32_t path_key, uint32_t depth, ui
 }
 
 // ---------------------------------------------------------------- wavelengths and spectra
-struct DWavelengths { float lambda[4]; float pdf[4]; };
+struct DWavelengths { float lambda[4]; float pdf[4]; bool terminated; };
 __device__ __forceinline__ DWavelengths wavelengths_uniform(float lambda0, bool terminated) {  // sampled_spectrum.rs:318-336 with lambda[0] given
     DWavelengths w;
     w.lambda[0] = lambda0;
@@ -249,6 +273,7 @@ __device__ __forceinline__ DWavelengths wavelengths_uniform(float lambda0, bool 
     const float p = 1.0f / (830.0f - 360.0f);
     w.pdf[0] = terminated ? p / 4.0f : p;
     w.pdf[1] = w.pdf[2] = w.pdf[3] = terminated ? 0.0f : p;
+    w.terminated = terminated;
     return w;
 }
 __device__ __forceinline__ float srgb_to_linear(float c) { return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
@@ -270,12 +295,17 @@ __device__ inline void rgb_to_coeffs(const DScene& sc, float3 rgb_in, float cs[3
     if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) { cs[0] = 0.0f; cs[1] = 0.0f; cs[2] = logf(rgb[0] / (1.0f - rgb[0])); return; }
     int m = 0;
     { float best = rgb[0]; if (rgb[1] > best) { best = rgb[1]; m = 1; } if (rgb[2] > best) m = 2; }
-    const float z = rgb[m];
-    const float x = rgb[(m + 1) % 3] * (64.0f - 1.0f) / z;
-    const float y = rgb[(m + 2) % 3] * (64.0f - 1.0f) / z;
+    const float z = m == 0 ? rgb[0] : (m == 1 ? rgb[1] : rgb[2]);
+    const float xr = m == 0 ? rgb[1] : (m == 1 ? rgb[2] : rgb[0]);
+    const float yr = m == 0 ? rgb[2] : (m == 1 ? rgb[0] : rgb[1]);
+    const float x = xr * (64.0f - 1.0f) / z;
+    const float y = yr * (64.0f - 1.0f) / z;
     const uint32_t xi = min(f2u_sat(x), 62u), yi = min(f2u_sat(y), 62u);
-    uint32_t zi = 62;
-    for (uint32_t i = 0; i <= 62; ++i) if (__ldg(&sc.z_nodes[i + 1]) > z) { zi = i; break; }
+    // zi = first i with z_nodes[i+1] > z, else 62 (rgb_sigmoid_polynomial.rs:124-126); the nodes are increasing, so a
+    // binary search over the same predicate returns the same index
+    uint32_t lo = 0, hi = 62;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&sc.z_nodes[mid + 1]) > z) hi = mid; else lo = mid + 1; }
+    const uint32_t zi = lo;
     const float z0 = __ldg(&sc.z_nodes[zi]), z1 = __ldg(&sc.z_nodes[zi + 1]);
     const float dx = x - (float)xi, dy = y - (float)yi, dz = (z - z0) / (z1 - z0);
     const float* base = sc.rgb2spec + ((((size_t)m * 64 + zi) * 64 + yi) * 64 + xi) * 3;
@@ -301,13 +331,16 @@ __device__ __forceinline__ float spectrum_value(const DScene& sc, const DSpectru
     if (s.kind == 1) return sg;
     return s.scale * sg * cmf_at(sc, lambda).w;
 }
-__device__ __forceinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl, bool terminated) {
+__device__ __forceinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl) {
     S4 r = s4(0.0f);
     r.v[0] = spectrum_value(sc, s, wl.lambda[0]);
-    if (terminated) return r;
+    if (wl.terminated) return r;
 #pragma unroll
     for (int i = 1; i < 4; ++i) r.v[i] = spectrum_value(sc, s, wl.lambda[i]);
     return r;
+}
+__device__ __forceinline__ DSpectrum spectrum_from_flat(const tcpt_flat_spectrum& p) {
+    DSpectrum s; s.kind = p.kind; s.c[0] = p.c[0]; s.c[1] = p.c[1]; s.c[2] = p.c[2]; s.scale = p.scale; return s;
 }
 // RgbIlluminantSpectrum::<ColorSrgb>::new (rgb_illuminant_spectrum.rs:27-40)
 __device__ __forceinline__ DSpectrum illuminant_from_rgb(const DScene& sc, float3 rgb) {
@@ -353,8 +386,7 @@ __device__ inline float tex_gray(const DTexture& t, float2 uv) {
 __device__ __forceinline__ DSpectrum param_spectrum(const DScene& sc, const tcpt_flat_spectrum& p, float2 uv) {
     DSpectrum s;
     if (p.kind == 4) { s.kind = 1; s.scale = 1.0f; rgb_to_coeffs(sc, tex_rgb(sc.textures[p.texture], uv), s.c); return s; }  // rgb_texture.rs:48-66
-    s.kind = p.kind; s.c[0] = p.c[0]; s.c[1] = p.c[1]; s.c[2] = p.c[2]; s.scale = p.scale;
-    return s;
+    return spectrum_from_flat(p);
 }
 __device__ __forceinline__ float param_float(const DScene& sc, const tcpt_flat_float& p, float2 uv) {
     if (!p.is_texture) return p.value;

@@ -1,0 +1,728 @@
+// Device shading: hit reconstruction, BSDFs and materials, light sampling, sensor.  One path vertex per thread.
+// Follows (file:line in /root/reference):
+//   hit reconstruction   math/src/ray.rs:161-175, scene/src/geometry/impls/triangle_mesh.rs:79-96, scene/src/primitive/bvh.rs:96-108
+//   material helpers     scene/src/material/common.rs:7-139
+//   Lambert              scene/src/material/bsdf/lambert.rs:11-120, impls/lambert_material.rs:42-179
+//   Dielectric/Plastic   scene/src/material/bsdf/dielectric.rs:167-645, impls/plastic_material.rs:122-264
+//   GeneralizedSchlick   scene/src/material/bsdf/generalized_schlick.rs:92-918 (ScatterMode::R, the only mode the materials use)
+//   SimplePbr/Clearcoat  impls/simple_pbr_material.rs:78-537, impls/simple_pbr_clearcoat_material.rs:88-845
+//   lights               scene/src/light_sampler.rs:17-220, primitive/impls/emissive_triangle_mesh.rs:166-353,
+//                        primitive/impls/environment_light.rs:86-351, scene/src/scene.rs:107-231
+//   sensor               renderer/src/sensor.rs:41-88
+// Convention of the reference kept everywhere: every BSDF value `f` already contains the cosine |wi.z|.
+#pragma once
+#include "dcommon.cuh"
+
+namespace tcpt {
+
+enum : int { ST_DIFFUSE = 0, ST_SPECULAR_REFLECTION = 1, ST_SPECULAR_TRANSMISSION = 2, ST_GLOSSY_REFLECTION = 3, ST_GLOSSY_TRANSMISSION = 4 };
+
+struct BsdfSample { S4 f; float3 wi; float pdf; int type; };
+struct MatSample {
+    S4 f; float3 wi; float pdf; int type; bool sampled;
+    __device__ __forceinline__ bool is_specular() const { return type == ST_SPECULAR_REFLECTION || type == ST_SPECULAR_TRANSMISSION; }
+};
+__device__ __forceinline__ MatSample mat_fail() { MatSample m; m.f = s4(0.0f); m.wi = f3(0, 0, 1); m.pdf = 0.0f; m.type = ST_DIFFUSE; m.sampled = false; return m; }
+__device__ __forceinline__ MatSample mat_ok(const S4& f, float3 wi, float pdf, int type) { MatSample m; m.f = f; m.wi = wi; m.pdf = pdf; m.type = type; m.sampled = true; return m; }
+
+// ---------------------------------------------------------------- surface interaction in Render space
+struct DSurface {
+    float3 position, normal, shading_normal, tangent, wo;
+    float2 uv;
+    int material, prim;
+    uint32_t tri;
+};
+
+__device__ __forceinline__ float3 orthogonalize(float3 n, float3 v) { const float pm = dot(n, v); return normalize(v - n * pm); }
+__device__ __forceinline__ float3 generate_tangent(float3 n) { return orthogonalize(n, fabsf(n.x) > 0.999f ? f3(0, 1, 0) : f3(1, 0, 0)); }
+
+__device__ inline void reconstruct_hit(const DScene& sc, int prim, uint32_t tri, float b0, float b1, float b2, float3 ray_d, DSurface& s) {
+    const tcpt_flat_primitive& P = sc.primitives[prim];
+    const tcpt_flat_geometry& G = sc.geometries[P.geometry];
+    const uint32_t* idx = sc.indices + 3 * ((size_t)G.index_base + tri);
+    const uint32_t i0 = __ldg(idx) + G.vertex_base, i1 = __ldg(idx + 1) + G.vertex_base, i2 = __ldg(idx + 2) + G.vertex_base;
+    const float* pp = sc.positions; const float* nn = sc.normals;
+    const float3 p0 = f3(__ldg(pp + 3 * (size_t)i0), __ldg(pp + 3 * (size_t)i0 + 1), __ldg(pp + 3 * (size_t)i0 + 2));
+    const float3 p1 = f3(__ldg(pp + 3 * (size_t)i1), __ldg(pp + 3 * (size_t)i1 + 1), __ldg(pp + 3 * (size_t)i1 + 2));
+    const float3 p2 = f3(__ldg(pp + 3 * (size_t)i2), __ldg(pp + 3 * (size_t)i2 + 1), __ldg(pp + 3 * (size_t)i2 + 2));
+    const float3 n0 = f3(__ldg(nn + 3 * (size_t)i0), __ldg(nn + 3 * (size_t)i0 + 1), __ldg(nn + 3 * (size_t)i0 + 2));
+    const float3 n1 = f3(__ldg(nn + 3 * (size_t)i1), __ldg(nn + 3 * (size_t)i1 + 1), __ldg(nn + 3 * (size_t)i1 + 2));
+    const float3 n2 = f3(__ldg(nn + 3 * (size_t)i2), __ldg(nn + 3 * (size_t)i2 + 1), __ldg(nn + 3 * (size_t)i2 + 2));
+    const float3 pos_l = (p0 * b0 + p1 * b1) + p2 * b2;                      // ray.rs:161-165
+    const float3 ng_l = normalize(normalize(cross(p1 - p0, p2 - p0)));       // ray.rs:168-174 (.normalize().to_normal())
+    const float3 ns_l = normalize((n0 * b0 + n1 * b1) + n2 * b2);            // triangle_mesh.rs:79-83
+    float3 tan_l;
+    if (G.has_uv) {
+        const float* uu = sc.uvs;
+        const float2 a = make_float2(__ldg(uu + 2 * (size_t)i0), __ldg(uu + 2 * (size_t)i0 + 1));
+        const float2 b = make_float2(__ldg(uu + 2 * (size_t)i1), __ldg(uu + 2 * (size_t)i1 + 1));
+        const float2 c = make_float2(__ldg(uu + 2 * (size_t)i2), __ldg(uu + 2 * (size_t)i2 + 1));
+        s.uv = make_float2((a.x * b0 + b.x * b1) + c.x * b2, (a.y * b0 + b.y * b1) + c.y * b2);
+        const float* tt = sc.tangents + 3 * ((size_t)G.tangent_base + tri);
+        tan_l = orthogonalize(ns_l, f3(__ldg(tt), __ldg(tt + 1), __ldg(tt + 2)));
+    } else {
+        s.uv = make_float2(0.0f, 0.0f);
+        tan_l = generate_tangent(ns_l);
+    }
+    // Transform * Intersection (primitive/bvh.rs:96-108, scene/src/samples.rs:129-141)
+    const float3 d_l = xf_vector(P.r2l, ray_d);
+    s.position = xf_point(P.l2r, pos_l);
+    s.normal = xf_normal_by_inverse(P.r2l, ng_l);
+    s.shading_normal = xf_normal_by_inverse(P.r2l, ns_l);
+    s.tangent = xf_vector(P.l2r, tan_l);
+    s.wo = xf_vector(P.l2r, -d_l);
+    s.material = P.material; s.prim = prim; s.tri = tri;
+}
+
+// Transform::from_shading_normal_tangent (math/src/transform.rs:186-203): returns render->tangent and its inverse
+__device__ __forceinline__ void shading_frame(const DSurface& s, M3& r2t, M3& t2r) {
+    const float3 n = normalize(s.shading_normal);
+    const float3 b = normalize(cross(normalize(n), s.tangent));
+    const float3 t = normalize(cross(b, n));
+    M3 m; m.c0 = t; m.c1 = b; m.c2 = n;
+    r2t = m3_inverse(m);
+    t2r = m3_inverse(r2t);
+}
+
+// ---------------------------------------------------------------- material/common.rs
+__device__ __forceinline__ float cos2_theta(float3 w) { return w.z * w.z; }
+__device__ __forceinline__ float tan2_theta(float3 w) { const float c2 = cos2_theta(w); return c2 == 0.0f ? TCPT_INF : (1.0f - c2) / c2; }
+__device__ __forceinline__ float cos_phi(float3 w) { const float st = sqrtf(rmax(1.0f - cos2_theta(w), 0.0f)); return st == 0.0f ? 1.0f : clampf(w.x / st, -1.0f, 1.0f); }
+__device__ __forceinline__ float sin_phi(float3 w) { const float st = sqrtf(rmax(1.0f - cos2_theta(w), 0.0f)); return st == 0.0f ? 0.0f : clampf(w.y / st, -1.0f, 1.0f); }
+__device__ __forceinline__ bool half_vector(float3 wo, float3 wi, float3* wm) { const float3 m = wo + wi; if (length_squared(m) == 0.0f) return false; *wm = normalize(m); return true; }
+__device__ __forceinline__ float3 reflect(float3 wo, float3 n) { return n * (2.0f * dot(wo, n)) - wo; }
+__device__ __forceinline__ bool same_hemisphere(float3 a, float3 b) { return a.z * b.z > 0.0f; }
+__device__ __forceinline__ float pow2(float x) { return x * x; }
+__device__ __forceinline__ float pow6(float x) { const float x2 = x * x; const float x4 = x2 * x2; return x4 * x2; }
+__device__ __forceinline__ float2 sample_uniform_disk_polar(float2 u) { const float r = sqrtf(u.x); const float th = 2.0f * TCPT_PI * u.y; return make_float2(r * cosf(th), r * sinf(th)); }
+__device__ inline S4 fresnel_dielectric(float cos_theta_i, const S4& eta) {
+    cos_theta_i = clampf(cos_theta_i, 0.0f, 1.0f);
+    const float sin2_theta_i = 1.0f - cos_theta_i * cos_theta_i;
+    const S4 sin2_t = s4(sin2_theta_i) / (eta * eta);
+    const S4 cos_t = s4_sqrt(s4_clamp(s4(1.0f) - sin2_t, 0.0f, 1.0f));
+    const S4 ci = s4(cos_theta_i);
+    const S4 r_parl = (eta * ci - cos_t) / (eta * ci + cos_t);
+    const S4 r_perp = (ci - eta * cos_t) / (ci + eta * cos_t);
+    return (r_parl * r_parl + r_perp * r_perp) * 0.5f;
+}
+__device__ inline bool refract(float3 wi, float3 n, float eta, float3* wt) {
+    const float cos_theta_i = dot(n, wi);
+    const float sin2_theta_i = rmax(1.0f - cos_theta_i * cos_theta_i, 0.0f);
+    const float sin2_theta_t = sin2_theta_i / (eta * eta);
+    if (sin2_theta_t >= 1.0f) return false;
+    const float cos_theta_t = sqrtf(rmax(1.0f - sin2_theta_t, 0.0f));
+    const float3 t = (-wi) / eta + n * (cos_theta_i / eta - cos_theta_t);
+    if (length_squared(t) < 1e-12f) return false;
+    *wt = normalize(t);
+    return true;
+}
+
+// ---------------------------------------------------------------- Trowbridge-Reitz helpers (dielectric.rs:22-120 == generalized_schlick.rs:96-190)
+struct Ggx {
+    float ax, ay;
+    __device__ __forceinline__ bool effectively_smooth() const { return rmax(ax, ay) < 1e-3f; }
+    __device__ float D(float3 wm) const {
+        const float t2 = tan2_theta(wm);
+        if (!isfinite(t2)) return 0.0f;
+        const float cos4 = pow2(cos2_theta(wm));
+        const float e = t2 * (pow2(cos_phi(wm)) / pow2(ax) + pow2(sin_phi(wm)) / pow2(ay));
+        return 1.0f / (TCPT_PI * ax * ay * cos4 * pow2(1.0f + e));
+    }
+    __device__ float lambda(float3 w) const {
+        const float t2 = tan2_theta(w);
+        if (isinf(t2)) return 0.0f;
+        const float a2 = pow2(cos_phi(w) * ax) + pow2(sin_phi(w) * ay);
+        return (sqrtf(1.0f + a2 * t2) - 1.0f) / 2.0f;
+    }
+    __device__ float G1(float3 w) const { return 1.0f / (1.0f + lambda(w)); }
+    __device__ float G(float3 wo, float3 wi) const { return 1.0f / (1.0f + lambda(wo) + lambda(wi)); }
+    __device__ float Dvis(float3 w, float3 wm) const {
+        const float c = fabsf(w.z);
+        if (c == 0.0f) return 0.0f;
+        return G1(w) / c * D(wm) * fabsf(dot(w, wm));
+    }
+    __device__ float3 sample_wm(float3 w, float2 u) const {
+        float3 wh = normalize(f3(ax * w.x, ay * w.y, w.z));
+        if (wh.z < 0.0f) wh = -wh;
+        const float3 t1 = wh.z < 0.99999f ? normalize(cross(f3(0, 0, 1), wh)) : f3(1, 0, 0);
+        const float3 t2 = cross(wh, t1);
+        const float2 p = sample_uniform_disk_polar(u);
+        const float h = sqrtf(rmax(1.0f - p.x * p.x, 0.0f));
+        const float lf = (1.0f + wh.z) / 2.0f;
+        const float py = h * (1.0f - lf) + p.y * lf;
+        const float pz = sqrtf(rmax(1.0f - p.x * p.x - py * py, 0.0f));
+        const float3 nh = (t1 * p.x + t2 * py) + wh * pz;
+        return normalize(f3(ax * nh.x, ay * nh.y, rmax(1e-6f, nh.z)));
+    }
+};
+
+__device__ inline bool generalized_half_vector(float3 wo, float3 wi, float eta, float3* out) {
+    const float co = wo.z, ci = wi.z;
+    const bool refl = ci * co > 0.0f;
+    const float etap = !refl ? (co > 0.0f ? eta : 1.0f / eta) : 1.0f;
+    float3 wm = wi * etap + wo;
+    if (ci == 0.0f || co == 0.0f || length_squared(wm) == 0.0f) return false;
+    wm = normalize(wm);
+    if (wm.z < 0.0f) wm = -wm;
+    if (dot(wm, wi) * ci < 0.0f || dot(wm, wo) * co < 0.0f) return false;
+    *out = wm;
+    return true;
+}
+
+// ---------------------------------------------------------------- bsdf/lambert.rs
+__device__ inline bool lambert_sample(const S4& albedo, float3 wo, float2 uv, BsdfSample* out) {
+    const float wo_cos = wo.z;
+    if (wo_cos == 0.0f) return false;
+    const float r = sqrtf(uv.x), th = 2.0f * TCPT_PI * uv.y;
+    float3 wi = f3(r * cosf(th), r * sinf(th), sqrtf(1.0f - uv.x));
+    if (wo_cos < 0.0f) wi.z = -wi.z;
+    const float wi_cos = wi.z;
+    if (wi_cos == 0.0f) return false;
+    if (signum(wo_cos) != signum(wi_cos)) return false;
+    out->f = albedo * fabsf(wi_cos) / TCPT_PI;
+    out->pdf = fabsf(wi_cos) / TCPT_PI;
+    out->wi = wi;
+    out->type = ST_DIFFUSE;
+    return true;
+}
+__device__ __forceinline__ bool lambert_ok(float3 wo, float3 wi) { return !(wo.z == 0.0f || wi.z == 0.0f) && signum(wo.z) == signum(wi.z); }
+__device__ __forceinline__ S4 lambert_eval(const S4& albedo, float3 wo, float3 wi) { return lambert_ok(wo, wi) ? albedo * fabsf(wi.z) / TCPT_PI : s4(0.0f); }
+__device__ __forceinline__ float lambert_pdf(float3 wo, float3 wi) { return lambert_ok(wo, wi) ? fabsf(wi.z) / TCPT_PI : 0.0f; }
+
+// ---------------------------------------------------------------- bsdf/dielectric.rs
+struct Dielectric {
+    S4 eta; bool entering, thin; Ggx g;
+    __device__ __forceinline__ S4 eta_spectrum() const { return (thin || entering) ? eta : s4(1.0f) / eta; }
+    __device__ __forceinline__ static void thin_coeffs(float fresnel, float* pr, float* pt) {
+        float r = fresnel; const float t = 1.0f - r, r2 = r * r;
+        r = r2 > 1.0f ? 1.0f : r + (t * t * r) / (1.0f - r2);
+        *pr = r; *pt = t;
+    }
+    __device__ bool sample_specular(float3 wo, float ux, DWavelengths& wl, BsdfSample* out) const {
+        const float wo_cos = wo.z;
+        const float3 n = entering ? f3(0, 0, 1) : f3(0, 0, -1);
+        const S4 es = eta_spectrum();
+        const float etap = es.v[0];
+        const S4 fresnel = fresnel_dielectric(fabsf(wo_cos), es);
+        float pr, pt;
+        if (thin) thin_coeffs(s4_avg(fresnel), &pr, &pt);
+        else { pr = s4_avg(fresnel); pt = 1.0f - pr; }
+        if (ux < pr / (pr + pt)) {
+            if (fabsf(wo_cos) < 1e-6f) return false;
+            out->f = fresnel; out->wi = f3(-wo.x, -wo.y, wo.z); out->pdf = pr / (pr + pt); out->type = ST_SPECULAR_REFLECTION;
+            return true;
+        }
+        if (thin) {
+            const float3 wi = f3(-wo.x, -wo.y, -wo.z);
+            if (wi.z == 0.0f) return false;
+            out->f = s4(1.0f) - fresnel; out->wi = wi; out->pdf = pt / (pr + pt); out->type = ST_SPECULAR_TRANSMISSION;
+            return true;
+        }
+        if (!s4_is_constant(eta) && !wl.terminated) wl = wavelengths_uniform(wl.lambda[0], true);
+        float3 wt;
+        if (!refract(wo, n, etap, &wt)) return false;
+        if (wt.z == 0.0f) return false;
+        out->f = (s4(1.0f) - fresnel) / pow2(etap); out->wi = wt; out->pdf = pt / (pr + pt); out->type = ST_SPECULAR_TRANSMISSION;
+        return true;
+    }
+    __device__ bool mf_reflection(float3 wo, float3 wm, const S4& fresnel, float prob, BsdfSample* out) const {
+        const float3 wi = reflect(wo, wm);
+        if (!same_hemisphere(wo, wi)) return false;
+        const float cd = fabsf(dot(wo, wm));
+        if (cd < 1e-6f) return false;
+        out->pdf = g.Dvis(wo, wm) / (4.0f * cd) * prob;
+        const float d = g.D(wm), gg = g.G(wo, wi);
+        // quirk: an extra |wi.z| here that evaluate() does not have (dielectric.rs:318 vs :589)
+        out->f = fresnel * d * gg * fabsf(wi.z) / (4.0f * fabsf(wo.z));
+        out->wi = wi; out->type = ST_GLOSSY_REFLECTION;
+        return true;
+    }
+    __device__ bool mf_transmission(float3 wo, float3 wm, const S4& tr, float prob, float etap, BsdfSample* out) const {
+        const float3 wmr = entering ? wm : -wm;
+        float3 wi;
+        if (!refract(wo, wmr, etap, &wi)) return false;
+        if (same_hemisphere(wo, wi) || fabsf(wi.z) == 0.0f) return false;
+        const float denom = pow2(dot(wi, wm) + dot(wo, wm) / etap);
+        const float dwm_dwi = fabsf(dot(wi, wm)) / denom;
+        out->pdf = g.Dvis(wo, wm) * dwm_dwi * prob;
+        const float d = g.D(wm), gg = g.G(wo, wi);
+        out->f = tr * d * gg * fabsf(dot(wi, wm)) * fabsf(dot(wo, wm)) / (denom * fabsf(wo.z) * etap * etap);
+        out->wi = wi; out->type = ST_GLOSSY_TRANSMISSION;
+        return true;
+    }
+    __device__ bool sample(float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) const {
+        if (wo.z == 0.0f) return false;
+        if (g.effectively_smooth()) return sample_specular(wo, uc, wl, out);  // selector = uc (dielectric.rs:180)
+        const float3 wm = g.sample_wm(wo, uv);
+        const S4 es = eta_spectrum();
+        const float eta_scalar = es.v[0];
+        const S4 fresnel = fresnel_dielectric(fabsf(dot(wo, wm)), es);
+        const float pr = s4_avg(fresnel), pt = 1.0f - pr;
+        if (thin) {
+            float tpr, tpt;
+            thin_coeffs(s4_avg(fresnel), &tpr, &tpt);
+            if (uc < tpr / (tpr + tpt)) return mf_reflection(wo, wm, fresnel, tpr / (tpr + tpt), out);
+            out->f = s4(1.0f) - fresnel; out->wi = f3(-wo.x, -wo.y, -wo.z); out->pdf = tpt / (tpr + tpt); out->type = ST_GLOSSY_TRANSMISSION;
+            return true;
+        } else if (uc < pr / (pr + pt)) {
+            return mf_reflection(wo, wm, fresnel, pr / (pr + pt), out);
+        }
+        if (!s4_is_constant(eta) && !wl.terminated) wl = wavelengths_uniform(wl.lambda[0], true);
+        return mf_transmission(wo, wm, s4(1.0f) - fresnel, pt / (pr + pt), eta_scalar, out);
+    }
+    __device__ S4 evaluate(float3 wo, float3 wi) const {
+        if (g.effectively_smooth()) return s4(0.0f);
+        const S4 es = eta_spectrum();
+        const float eta_scalar = es.v[0];
+        float3 wm;
+        if (!generalized_half_vector(wo, wi, eta_scalar, &wm)) return s4(0.0f);
+        const S4 fresnel = fresnel_dielectric(fabsf(dot(wo, wm)), es);
+        const bool refl = wi.z * wo.z > 0.0f;
+        const float d = g.D(wm), gg = g.G(wo, wi);
+        if (refl) return fresnel * d * gg / (4.0f * fabsf(wo.z));
+        const float denom = pow2(dot(wi, wm) + dot(wo, wm) / eta_scalar);
+        return (s4(1.0f) - fresnel) * d * gg * fabsf(dot(wi, wm)) * fabsf(dot(wo, wm)) / (denom * fabsf(wo.z) * eta_scalar * eta_scalar);
+    }
+    __device__ float pdf(float3 wo, float3 wi) const {
+        if (g.effectively_smooth()) return 0.0f;
+        const S4 es = eta_spectrum();
+        const float eta_scalar = es.v[0];
+        float3 wm;
+        if (!generalized_half_vector(wo, wi, eta_scalar, &wm)) return 0.0f;
+        const S4 fresnel = fresnel_dielectric(fabsf(dot(wo, wm)), es);
+        const float pr = s4_avg(fresnel), pt = 1.0f - pr;
+        const bool refl = wi.z * wo.z > 0.0f;
+        if (refl) return g.Dvis(wo, wm) / (4.0f * fabsf(dot(wo, wm))) * pr / (pr + pt);
+        if (thin) return pt / (pr + pt);
+        const float denom = pow2(dot(wi, wm) + dot(wo, wm) / eta_scalar);
+        const float dwm_dwi = fabsf(dot(wi, wm)) / denom;
+        return g.Dvis(wo, wm) * dwm_dwi * pt / (pr + pt);
+    }
+};
+__device__ __forceinline__ Dielectric make_dielectric(float eta, bool entering, bool thin, float alpha) {
+    Dielectric d; d.eta = s4(eta == 0.0f ? 1.0f : eta); d.entering = entering; d.thin = thin; d.g.ax = alpha; d.g.ay = alpha; return d;
+}
+
+// ---------------------------------------------------------------- bsdf/generalized_schlick.rs (ScatterMode::R)
+// The materials only ever build it with r90 = 1, exponent = 5, tint = 1 (simple_pbr_material.rs:290-520,
+// simple_pbr_clearcoat_material.rs:171-188, 580-829); the Lazanyi term is kept because (1 - tint) = 0 must still multiply through.
+struct Schlick {
+    S4 r0; Ggx g;
+    __device__ S4 fresnel_at(float cos_theta) const {
+        cos_theta = clampf(cos_theta, 0.0f, 1.0f);
+        const float omc = 1.0f - cos_theta;
+        const float COS_MAX = 1.0f / 7.0f;
+        const float OM_COS_MAX = 1.0f - COS_MAX;
+        const S4 r90 = s4(1.0f), tint = s4(1.0f);
+        const S4 base = r0 + (r90 - r0) * powf(omc, 5.0f);
+        const S4 at_max = r0 + (r90 - r0) * powf(OM_COS_MAX, 5.0f);
+        const S4 a = at_max * (s4(1.0f) - tint) / (COS_MAX * pow6(OM_COS_MAX));
+        const S4 laz = a * cos_theta * pow6(omc);
+        return base - laz;
+    }
+    __device__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
+        if (wo.z == 0.0f) return false;
+        if (g.effectively_smooth()) {
+            const float3 wi = f3(-wo.x, -wo.y, wo.z);
+            if (wi.z == 0.0f) return false;
+            out->f = fresnel_at(fabsf(wo.z)); out->wi = wi; out->pdf = 1.0f; out->type = ST_SPECULAR_REFLECTION;
+            return true;
+        }
+        const float3 wm = g.sample_wm(wo, uv);
+        const S4 fr = fresnel_at(fabsf(dot(wo, wm)));
+        const float3 wi = reflect(wo, wm);
+        if (!same_hemisphere(wo, wi)) return false;
+        const float cd = fabsf(dot(wo, wm));
+        if (cd < 1e-6f) return false;
+        const float pdf = g.Dvis(wo, wm) / (4.0f * cd) * 1.0f;
+        const float d = g.D(wm), gg = g.G(wo, wi);
+        const float ci = fabsf(wi.z), co = fabsf(wo.z);
+        if (ci == 0.0f || co == 0.0f) return false;
+        out->f = fr * d * gg / (4.0f * co); out->wi = wi; out->pdf = pdf; out->type = ST_GLOSSY_REFLECTION;
+        return true;
+    }
+    __device__ S4 evaluate(float3 wo, float3 wi) const {
+        if (g.effectively_smooth()) return s4(0.0f);
+        const float co = fabsf(wo.z), ci = fabsf(wi.z);
+        if (co == 0.0f || ci == 0.0f) return s4(0.0f);
+        if (!same_hemisphere(wo, wi)) return s4(0.0f);
+        float3 wm;
+        if (!half_vector(wo, wi, &wm)) return s4(0.0f);
+        const S4 fr = fresnel_at(fabsf(dot(wo, wm)));
+        const float d = g.D(wm), gg = g.G(wo, wi);
+        return fr * d * gg / (4.0f * co);
+    }
+    __device__ float pdf(float3 wo, float3 wi) const {
+        if (g.effectively_smooth()) return 0.0f;
+        if (!same_hemisphere(wo, wi)) return 0.0f;
+        float3 wm;
+        if (!half_vector(wo, wi, &wm)) return 0.0f;
+        const float vis = g.Dvis(wo, wm);
+        const float jac = 4.0f * fabsf(dot(wo, wm));
+        if (jac == 0.0f) return 0.0f;
+        return vis / jac;
+    }
+    // 64-sample stochastic estimate (generalized_schlick.rs:893-918); `f` already holds a cosine, reproduced as is
+    __device__ S4 directional_albedo(float3 wo, DAuxRng rng) const {
+        S4 sum = s4(0.0f);
+        for (int i = 0; i < 64; ++i) {
+            rng.next();  // uc (unused by the R-mode sampler, but drawn by the reference)
+            float2 uv; uv.x = rng.next(); uv.y = rng.next();
+            BsdfSample s;
+            if (sample(wo, uv, &s)) {
+                const float ci = fabsf(s.wi.z);
+                if (ci > 0.0f && s.pdf > 0.0f) sum = sum + s.f * ci / s.pdf;
+            }
+        }
+        return sum / 64.0f;
+    }
+};
+__device__ __forceinline__ float r0_of(float ior) { const float r = (ior - 1.0f) / (ior + 1.0f); return r * r; }
+__device__ __forceinline__ Schlick make_schlick(const S4& r0, float alpha) { Schlick s; s.r0 = r0; s.g.ax = alpha; s.g.ay = alpha; return s; }
+
+// ---------------------------------------------------------------- SimplePbr (simple_pbr_material.rs:274-537 == simple_pbr_clearcoat_material.rs:540-845)
+struct PbrBase {
+    S4 base_color; float metallic, roughness, ior;
+    __device__ MatSample sample_metallic(float alpha, float3 wo, float2 uv, const M3& from_nm) const {
+        BsdfSample s;
+        if (!make_schlick(base_color, alpha).sample(wo, uv, &s)) return mat_fail();
+        return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
+    }
+    __device__ MatSample sample_dielectric(float alpha, float3 wo, float uc, float2 uv, const M3& from_nm) const {
+        const Schlick gs = make_schlick(s4(r0_of(ior)), alpha);
+        const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
+        BsdfSample s;
+        if (uc < fresnel) {
+            if (!gs.sample(wo, uv, &s)) return mat_fail();
+            return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf * fresnel, s.type);
+        }
+        if (!lambert_sample(base_color, wo, uv, &s)) return mat_fail();
+        return mat_ok(s.f * (1.0f - fresnel), m3_vector(from_nm, s.wi), s.pdf * (1.0f - fresnel), s.type);
+    }
+    __device__ MatSample sample(float3 wo, float uc, float2 uv, const M3& from_nm) const {
+        const float alpha = roughness * roughness;
+        if (metallic >= 1.0f) return sample_metallic(alpha, wo, uv, from_nm);
+        if (metallic <= 0.0f) return sample_dielectric(alpha, wo, uc, uv, from_nm);
+        if (uc <= metallic) return sample_metallic(alpha, wo, uv, from_nm);
+        return sample_dielectric(alpha, wo, (uc - metallic) / (1.0f - metallic), uv, from_nm);
+    }
+    __device__ S4 eval_dielectric(float alpha, float3 wo, float3 wi) const {
+        const Schlick gs = make_schlick(s4(r0_of(ior)), alpha);
+        const S4 direct = gs.evaluate(wo, wi);
+        const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
+        return direct + (1.0f - fresnel) * lambert_eval(base_color, wo, wi);
+    }
+    __device__ S4 evaluate(float3 wo, float3 wi) const {
+        const float alpha = roughness * roughness;
+        if (metallic >= 1.0f) return make_schlick(base_color, alpha).evaluate(wo, wi);
+        if (metallic <= 0.0f) return eval_dielectric(alpha, wo, wi);
+        return make_schlick(base_color, alpha).evaluate(wo, wi) * metallic + eval_dielectric(alpha, wo, wi) * (1.0f - metallic);
+    }
+    __device__ float pdf_dielectric(float alpha, float3 wo, float3 wi) const {
+        const Schlick gs = make_schlick(s4(r0_of(ior)), alpha);
+        const float direct = gs.pdf(wo, wi);
+        const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
+        return fresnel * direct + (1.0f - fresnel) * lambert_pdf(wo, wi);
+    }
+    __device__ float pdf(float3 wo, float3 wi) const {
+        const float alpha = roughness * roughness;
+        if (metallic >= 1.0f) return make_schlick(s4(1.0f), alpha).pdf(wo, wi);
+        if (metallic <= 0.0f) return pdf_dielectric(alpha, wo, wi);
+        return make_schlick(s4(1.0f), alpha).pdf(wo, wi) * metallic + pdf_dielectric(alpha, wo, wi) * (1.0f - metallic);
+    }
+};
+
+// Beer-Lambert coat attenuation (simple_pbr_clearcoat_material.rs:88-107)
+__device__ inline S4 coat_attenuation(const S4& tint, float thickness, float cos_theta) {
+    S4 r;
+    const float thickness_m = thickness * 0.001f;
+    const float l = thickness_m / rmax(cos_theta, 1e-4f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float log_tint = logf(rmax(tint.v[i], 1e-10f));
+        const float sigma = (-1.0f * log_tint) / 0.001f;
+        r.v[i] = expf((-1.0f * sigma) * l);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------- materials (BsdfSurfaceMaterial::{sample,evaluate,pdf}, material/traits.rs:29-83)
+struct MatCtx {
+    const DScene* sc;
+    uint32_t path_key, depth;  // aux RNG keying
+};
+
+__device__ inline float3 param_normal(const DScene& sc, const tcpt_flat_material& m, float2 uv) {  // normal_texture.rs:40-66
+    if (m.normal_texture < 0) return normalize(f3(0, 0, 1));
+    const float3 rgb = tex_rgb(sc.textures[m.normal_texture], uv);
+    float x = rgb.x * 2.0f - 1.0f, y = rgb.y * 2.0f - 1.0f, z = rgb.z * 2.0f - 1.0f;
+    if (m.normal_flip_y) y = -y;
+    const float len = sqrtf(x * x + y * y + z * z);
+    if (len > 0.0f) return normalize(f3(x / len, y / len, z / len));
+    return normalize(f3(0, 0, 1));
+}
+// Transform::from_normal_map (math/src/transform.rs:216-244)
+__device__ inline void normal_map_frame(float3 nm, M3& to_nm, M3& from_nm) {
+    const float3 z = normalize(nm);
+    const float3 cand = fabsf(dot(z, f3(1, 0, 0))) < 0.9f ? f3(1, 0, 0) : f3(0, 1, 0);
+    const float3 x = normalize(cand - dot(z, cand) * z);
+    const float3 y = normalize(cross(z, x));
+    M3 m; m.c0 = x; m.c1 = y; m.c2 = z;
+    to_nm = m3_inverse(m);
+    from_nm = m3_inverse(to_nm);
+}
+__device__ __forceinline__ PbrBase load_pbr(const DScene& sc, const tcpt_flat_material& m, float2 uv, const DWavelengths& wl) {
+    PbrBase b;
+    b.base_color = spectrum_sample(sc, param_spectrum(sc, m.color, uv), wl);
+    b.metallic = param_float(sc, m.metallic, uv);
+    b.roughness = param_float(sc, m.roughness, uv);
+    b.ior = param_float(sc, m.ior, uv);
+    return b;
+}
+struct Coat { float ior, roughness, thickness; S4 tint; };
+__device__ __forceinline__ Coat load_coat(const DScene& sc, const tcpt_flat_material& m, float2 uv, const DWavelengths& wl) {
+    Coat c;
+    c.ior = param_float(sc, m.coat_ior, uv);
+    c.roughness = param_float(sc, m.coat_roughness, uv);
+    c.tint = spectrum_sample(sc, param_spectrum(sc, m.coat_tint, uv), wl);
+    c.thickness = param_float(sc, m.coat_thickness, uv);
+    return c;
+}
+__device__ __forceinline__ Schlick coat_bsdf(const Coat& c) { return make_schlick(s4(r0_of(c.ior)), c.roughness * c.roughness); }
+
+// `ng_t` = geometric normal in the tangent frame, `sp_uv` = surface uv
+__device__ inline MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
+    const DScene& sc = *c.sc;
+    M3 to_nm, from_nm;
+    normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
+    const float3 wo_nm = m3_vector(to_nm, wo);
+    switch (m.type) {
+        case TCPT_MAT_LAMBERT: {  // lambert_material.rs:42-97
+            const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
+            BsdfSample s;
+            if (!lambert_sample(albedo, wo_nm, uv, &s)) return mat_fail();
+            const float3 wi_sh = m3_vector(from_nm, s.wi);
+            if (signum(dot(ng_t, wi_sh)) != signum(dot(ng_t, wo))) return mat_fail();
+            return mat_ok(s.f, wi_sh, s.pdf, s.type);
+        }
+        case TCPT_MAT_PLASTIC: {  // plastic_material.rs:122-187 (roughness passed unsquared as alpha)
+            const float rough = param_float(sc, m.roughness, sp_uv);
+            const Dielectric d = make_dielectric(m.eta, dot(ng_t, wo) > 0.0f, m.thin_surface != 0, rough);
+            BsdfSample s;
+            if (!d.sample(wo_nm, uv, uc, wl, &s)) return mat_fail();
+            if (dot(s.wi, wo_nm) < 0.0f) s.f = s.f * spectrum_sample(sc, param_spectrum(sc, m.color, uv), wl);  // quirk: filter looked up at the RANDOM uv (:167)
+            return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
+        }
+        case TCPT_MAT_SIMPLE_PBR: return load_pbr(sc, m, sp_uv, wl).sample(wo_nm, uc, uv, from_nm);
+        case TCPT_MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:121-250
+            const PbrBase b = load_pbr(sc, m, sp_uv, wl);
+            const Coat cp = load_coat(sc, m, sp_uv, wl);
+            if (cp.thickness <= 0.0f) return b.sample(wo_nm, uc, uv, from_nm);
+            const Schlick coat = coat_bsdf(cp);
+            const float fc = s4_avg(coat.directional_albedo(wo_nm, aux_rng(c.path_key, c.depth, 0)));
+            if (uc < fc) {
+                BsdfSample s;
+                if (!coat.sample(wo_nm, uv, &s)) return mat_fail();
+                return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf * fc, s.type);
+            }
+            const float uc2 = (uc - fc) / (1.0f - fc);
+            MatSample sub = b.sample(wo_nm, uc2, uv, from_nm);
+            if (!sub.sampled) return sub;
+            const S4 att = coat_attenuation(cp.tint, cp.thickness, wo_nm.z) * coat_attenuation(cp.tint, cp.thickness, sub.wi.z);
+            return mat_ok(sub.f * att, sub.wi, sub.pdf * (1.0f - fc), sub.type);
+        }
+        default: return mat_fail();
+    }
+}
+
+// evaluate() and pdf() of the same (wo, wi) pair, as the NEE helpers call them back to back (common.rs:142-158)
+__device__ inline void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
+                                         bool want_pdf, S4* f_out, float* pdf_out) {
+    const DScene& sc = *c.sc;
+    M3 to_nm, from_nm;
+    normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
+    const float3 wo_nm = m3_vector(to_nm, wo), wi_nm = m3_vector(to_nm, wi);
+    *pdf_out = 0.0f;
+    switch (m.type) {
+        case TCPT_MAT_LAMBERT: {  // lambert_material.rs:99-170
+            if (signum(dot(ng_t, wi)) != signum(dot(ng_t, wo))) { *f_out = s4(0.0f); return; }
+            const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
+            *f_out = lambert_eval(albedo, wo_nm, wi_nm);
+            if (want_pdf) *pdf_out = lambert_pdf(wo_nm, wi_nm);
+            return;
+        }
+        case TCPT_MAT_PLASTIC: {  // plastic_material.rs:189-264
+            const float rough = param_float(sc, m.roughness, sp_uv);
+            const Dielectric d = make_dielectric(m.eta, dot(ng_t, wo) > 0.0f, m.thin_surface != 0, rough);
+            S4 f = d.evaluate(wo_nm, wi_nm);
+            if (dot(wi_nm, wo_nm) < 0.0f) f = f * spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
+            *f_out = f;
+            if (want_pdf) *pdf_out = d.pdf(wo_nm, wi_nm);
+            return;
+        }
+        case TCPT_MAT_SIMPLE_PBR: {
+            const PbrBase b = load_pbr(sc, m, sp_uv, wl);
+            *f_out = b.evaluate(wo_nm, wi_nm);
+            if (want_pdf) *pdf_out = b.pdf(wo_nm, wi_nm);
+            return;
+        }
+        case TCPT_MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:252-433: evaluate and pdf each draw their OWN albedo estimate
+            const PbrBase b = load_pbr(sc, m, sp_uv, wl);
+            const Coat cp = load_coat(sc, m, sp_uv, wl);
+            if (cp.thickness <= 0.0f) { *f_out = b.evaluate(wo_nm, wi_nm); if (want_pdf) *pdf_out = b.pdf(wo_nm, wi_nm); return; }
+            const Schlick coat = coat_bsdf(cp);
+            const float fc = s4_avg(coat.directional_albedo(wo_nm, aux_rng(c.path_key, c.depth, 1)));
+            const S4 att = coat_attenuation(cp.tint, cp.thickness, wo_nm.z) * coat_attenuation(cp.tint, cp.thickness, wi_nm.z);
+            *f_out = coat.evaluate(wo_nm, wi_nm) * fc + b.evaluate(wo_nm, wi_nm) * att * (1.0f - fc);
+            if (want_pdf) {
+                const float fc2 = s4_avg(coat.directional_albedo(wo_nm, aux_rng(c.path_key, c.depth, 2)));
+                *pdf_out = coat.pdf(wo_nm, wi_nm) * fc2 + b.pdf(wo_nm, wi_nm) * (1.0f - fc2);
+            }
+            return;
+        }
+        default: *f_out = s4(0.0f); return;
+    }
+}
+
+// ---------------------------------------------------------------- lights
+// emissive_material.rs:48-80 (UniformEdf: two-sided, direction independent)
+__device__ __forceinline__ S4 emissive_radiance(const DScene& sc, const tcpt_flat_material& m, float2 uv, const DWavelengths& wl) {
+    const S4 r = spectrum_sample(sc, param_spectrum(sc, m.color, uv), wl);
+    return r * param_float(sc, m.intensity, uv);
+}
+
+struct LightTable { float w[TCPT_MAX_LIGHTS]; float sum; };
+// LightSamplerFactory::create (light_sampler.rs:190-220): phi(lambda).average() per light
+__device__ inline void light_table(const DScene& sc, const DWavelengths& wl, LightTable& lt) {
+    lt.sum = 0.0f;
+    for (uint32_t i = 0; i < sc.n_lights; ++i) {
+        const tcpt_flat_primitive& P = sc.primitives[sc.light_list[i]];
+        S4 phi;
+        if (P.kind == 1) phi = emissive_radiance(sc, sc.materials[P.material], make_float2(0.5f, 0.5f), wl) * P.area_sum;  // emissive_triangle_mesh.rs:166-173
+        else { const DEnv& e = sc.envs[P.env]; phi = e.intensity * spectrum_sample(sc, spectrum_from_flat(e.integrated), wl); }  // environment_light.rs:299-301
+        lt.w[i] = s4_avg(phi);
+        lt.sum += lt.w[i];
+    }
+}
+// LightSampler::sample_light (light_sampler.rs:26-44): linear scan of the normalised running sum
+__device__ inline int sample_light(const DScene& sc, const LightTable& lt, float u, float* prob) {
+    if (sc.n_lights == 0 || lt.sum == 0.0f) return -1;
+    float cum = 0.0f;
+    for (uint32_t i = 0; i < sc.n_lights; ++i) {
+        cum += lt.w[i];
+        if (u < cum / lt.sum) { *prob = lt.w[i] / lt.sum; return (int)i; }
+    }
+    *prob = lt.w[sc.n_lights - 1] / lt.sum;
+    return (int)sc.n_lights - 1;
+}
+
+// environment_light.rs:102-116
+__device__ __forceinline__ void direction_to_spherical(float3 d, float* theta, float* phi) {
+    *theta = clampf(acosf(d.y), 0.0f, TCPT_PI);
+    float p = atan2f(d.z, d.x);
+    if (p < 0.0f) p += 2.0f * TCPT_PI;
+    *phi = p;
+}
+__device__ inline float3 env_texel_bilinear(const DEnv& e, float u, float v) {  // environment_light.rs:124-160
+    u = clampf(u, 0.0f, 1.0f); v = clampf(v, 0.0f, 1.0f);
+    const float x = u * (float)(e.w - 1), y = v * (float)(e.h - 1);
+    const uint32_t x0 = f2u_sat(floorf(x)), y0 = f2u_sat(floorf(y));
+    const uint32_t x1 = min(x0 + 1u, e.w - 1u), y1 = min(y0 + 1u, e.h - 1u);
+    const float fx = x - (float)x0, fy = y - (float)y0;
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float p00 = __ldg(e.data + ((size_t)y0 * e.w + x0) * 3 + c), p10 = __ldg(e.data + ((size_t)y0 * e.w + x1) * 3 + c);
+        const float p01 = __ldg(e.data + ((size_t)y1 * e.w + x0) * 3 + c), p11 = __ldg(e.data + ((size_t)y1 * e.w + x1) * 3 + c);
+        const float a = p00 * (1.0f - fx) + p10 * fx, b = p01 * (1.0f - fx) + p11 * fx;
+        o[c] = a * (1.0f - fy) + b * fy;
+    }
+    return f3(o[0], o[1], o[2]);
+}
+__device__ inline float env_direction_pdf(const DScene& sc, const tcpt_flat_primitive& P, float3 dir) {  // environment_light.rs:234-259
+    const DEnv& e = sc.envs[P.env];
+    if (e.total_weight <= 0.0f) return 0.0f;
+    float theta, phi;
+    direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
+    const float u = phi / (2.0f * TCPT_PI), v = theta / TCPT_PI;
+    const uint32_t x = min(f2u_sat(floorf(u * (float)e.w)), e.w - 1u), y = min(f2u_sat(floorf(v * (float)e.h)), e.h - 1u);
+    const float* px = e.data + ((size_t)y * e.w + x) * 3;
+    const float lum = 0.299f * __ldg(px) + 0.587f * __ldg(px + 1) + 0.114f * __ldg(px + 2);
+    const float sin_theta = rmax(sinf(theta), 1e-8f);
+    const float pdf_texture = lum * sin_theta / e.total_weight;
+    const float jac = (float)e.w * (float)e.h / (2.0f * TCPT_PI * TCPT_PI * sin_theta);
+    return pdf_texture * jac;
+}
+__device__ inline S4 env_direction_radiance(const DScene& sc, const tcpt_flat_primitive& P, float3 dir, const DWavelengths& wl) {  // environment_light.rs:304-316
+    const DEnv& e = sc.envs[P.env];
+    float theta, phi;
+    direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
+    const float3 rgb = env_texel_bilinear(e, phi / (2.0f * TCPT_PI), theta / TCPT_PI);
+    return spectrum_sample(sc, illuminant_from_rgb(sc, rgb), wl) * e.intensity;
+}
+// Scene::evaluate_infinite_light_radiance (scene.rs:213-231)
+__device__ inline S4 scene_env_radiance(const DScene& sc, float3 dir, const DWavelengths& wl) {
+    S4 tot = s4(0.0f);
+    for (uint32_t i = 0; i < sc.n_envs; ++i) tot = tot + env_direction_radiance(sc, sc.primitives[sc.envs[i].primitive], dir, wl);
+    return tot;
+}
+// Scene::pdf_infinite_light_sample (scene.rs:184-210) with LightSampler::probability_infinite_light (light_sampler.rs:121-158)
+__device__ inline float scene_env_pdf(const DScene& sc, const LightTable& lt, float3 dir) {
+    if (sc.n_lights == 0 || lt.sum == 0.0f) return 0.0f;
+    float inf_sum = 0.0f;
+    for (uint32_t i = 0; i < sc.n_lights; ++i) if (sc.primitives[sc.light_list[i]].kind == 2) inf_sum += lt.w[i];
+    if (inf_sum == 0.0f) return 0.0f;
+    float tot = 0.0f;
+    for (uint32_t i = 0; i < sc.n_lights; ++i) {
+        const tcpt_flat_primitive& P = sc.primitives[sc.light_list[i]];
+        if (P.kind == 2) tot += (lt.w[i] / inf_sum) * env_direction_pdf(sc, P, dir);
+    }
+    return tot;
+}
+// Rust slice::binary_search_by(partial_cmp) then clamp (environment_light.rs:218-223)
+__device__ inline uint32_t sample_from_cdf(const float* cdf, uint32_t n, float u) {
+    uint32_t size = n, base = 0;
+    while (size > 1) {
+        const uint32_t half = size / 2, mid = base + half;
+        if (!(__ldg(cdf + mid) > u)) base = mid;
+        size -= half;
+    }
+    const float c = __ldg(cdf + base);
+    if (c == u) return base;
+    return min(base + (c < u ? 1u : 0u), n - 1u);
+}
+
+// Scene::pdf_light_sample (scene.rs:156-181) for a BSDF-sampled hit on an emissive mesh
+__device__ inline float scene_pdf_light_sample(const DScene& sc, const LightTable& lt, float3 shading_pos, const DSurface& hit) {
+    const tcpt_flat_primitive& P = sc.primitives[hit.prim];
+    if (P.kind != 1) return 0.0f;
+    float probability = 0.0f;
+    if (sc.n_lights != 0 && lt.sum != 0.0f && P.light_index >= 0) probability = lt.w[P.light_index] / lt.sum;
+    const float* table = sc.area_table + P.area_base;
+    const float tri_prob = hit.tri == 0 ? __ldg(table) : __ldg(table + hit.tri) - __ldg(table + hit.tri - 1);
+    const float pdf_area = 1.0f / __ldg(sc.area_list + P.area_base + hit.tri) * tri_prob;  // emissive_triangle_mesh.rs:331-353
+    const float3 dv = shading_pos - hit.position;
+    const float distance = length(dv);
+    const float3 wo = -normalize(dv);
+    const float pdf_dir = pdf_area * (distance * distance) / fabsf(dot(hit.normal, wo));
+    return probability * pdf_dir;
+}
+
+// ---------------------------------------------------------------- sensor (renderer/src/sensor.rs:41-78)
+__device__ inline float3 sensor_rgb(const DScene& sc, const DWavelengths& wl, const S4& s, float exposure) {
+    const int count = wl.terminated ? 1 : 4;
+    float x = 0.0f, y = 0.0f, z = 0.0f;
+    for (int k = 0; k < count; ++k) {
+        uint32_t i = f2u_sat(floorf(wl.lambda[k] - 360.0f));
+        if (i == 470u) i = 0u;
+        const float a = s.v[k] / wl.pdf[k];
+        const float nc = a / 4.0f;
+        const float4 cm = cmf_at(sc, 360.0f + (float)i);
+        x += nc * cm.x; y += nc * cm.y; z += nc * cm.z;
+    }
+    const float* m = sc.xyz_to_rgb;
+    const float3 rgb = f3((m[0] * x + m[3] * y) + m[6] * z, (m[1] * x + m[4] * y) + m[7] * z, (m[2] * x + m[5] * y) + m[8] * z);
+    return rgb * exposure;
+}
+
+}  // namespace tcpt

@@ -1,16 +1,17 @@
 // Two-level BVH traversal on the device (software; B200 has no RT cores).
 //
 // Reproduces the RESULT of the reference's exhaustive recursive traversal (/root/reference/scene/src/bvh.rs:344-520) with an
-// ordered, t-shrinking, stack-based walk:
+// ordered, t-shrinking, stack-based walk over 64-byte child-pair records (include/tcpt_flat.h):
 //   * slab test = math/src/bounds.rs:27-55, same operations in the same order (sub, mul, compare-selects; no FMA);
 //   * triangle test = math/src/ray.rs:44-158 (watertight shear, f64 fallback when an edge function is 0, conservative t > delta_t);
 //   * instance transform = primitive/impls/triangle_mesh.rs:97 (ray parameter t preserved, direction not re-normalised);
 //   * the reference never shrinks t_max and keeps candidates by  Node: ties -> second child,  Leaf: ties -> earlier item
 //     (bvh.rs:384-388, 413-420).  That is the total order  (t, later leaf first, earlier item first)  applied per level
 //     (TLAS, then BLAS), so any visiting order that sees every candidate the winner competes with gives the same hit.
-//     Boxes are culled against  t_best * (1 + 2^-10) + 2^-10  instead of t_best: the slab interval of a box and the
-//     watertight t of a triangle inside it are rounded independently, so the margin keeps every box that could still hold an
-//     equal-or-smaller t (the triangle test itself always runs with the caller's t_max, like the reference).
+//     Every box on the path to a candidate is tested with the reference's own slab arithmetic, so the candidate set is a
+//     subset of the reference's; boxes are additionally culled against  t_best * (1 + 2^-10) + 2^-10  instead of t_best:
+//     the slab interval of a box and the watertight t of a triangle inside it are rounded independently, so the margin keeps
+//     every box that could still hold an equal-or-smaller t (the triangle test itself always runs with the caller's t_max).
 #pragma once
 #include "dcommon.cuh"
 
@@ -22,21 +23,21 @@ struct DHit {
     uint32_t tri;  // triangle index within the geometry
 };
 
-struct RayXform {  // per-space ray constants for the watertight test (math/src/ray.rs:63-78)
-    float3 o, d, inv_d;
-    int kx, ky, kz;
+struct RayXform {  // per-space ray constants for the slab and watertight tests (math/src/ray.rs:63-78)
+    float3 o, inv_d;
+    int kz;
     float sx, sy, sz;
 };
 
 __device__ __forceinline__ void ray_setup(RayXform& r, float3 o, float3 d) {
-    r.o = o; r.d = d;
+    r.o = o;
     r.inv_d = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // bvh.rs:433
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     int kz = 0; float m = ax;
     if (ay > m) { m = ay; kz = 1; }
     if (az > m) { kz = 2; }
-    r.kz = kz; r.kx = (kz + 1) % 3; r.ky = (r.kx + 1) % 3;
-    const float dx = comp(d, r.kx), dy = comp(d, r.ky), dz = comp(d, r.kz);
+    r.kz = kz;
+    const float dx = kz == 0 ? d.y : (kz == 1 ? d.z : d.x), dy = kz == 0 ? d.z : (kz == 1 ? d.x : d.y), dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
     r.sx = -dx / dz; r.sy = -dy / dz; r.sz = 1.0f / dz;
 }
 
@@ -65,10 +66,13 @@ __device__ __forceinline__ bool slab_test(const float4 lo, const float4 hi, cons
 // math::intersect_triangle up to the accept decision; returns true and t/barycentrics on a hit
 __device__ __forceinline__ bool tri_test(const float4 v0, const float4 v1, const float4 v2, const RayXform& r, float t_max, float* t_out, float* b0, float* b1, float* b2) {
     if (__float_as_uint(v1.w) != 0u) return false;  // degenerate (|e1 x e2|^2 == 0), decided on the host
-    const float3 a = f3(v0.x - r.o.x, v0.y - r.o.y, v0.z - r.o.z), b = f3(v1.x - r.o.x, v1.y - r.o.y, v1.z - r.o.z), c = f3(v2.x - r.o.x, v2.y - r.o.y, v2.z - r.o.z);
-    float p0x = comp(a, r.kx), p0y = comp(a, r.ky), p0z = comp(a, r.kz);
-    float p1x = comp(b, r.kx), p1y = comp(b, r.ky), p1z = comp(b, r.kz);
-    float p2x = comp(c, r.kx), p2y = comp(c, r.ky), p2z = comp(c, r.kz);
+    const float ax = v0.x - r.o.x, ay = v0.y - r.o.y, az = v0.z - r.o.z;
+    const float bx = v1.x - r.o.x, by = v1.y - r.o.y, bz = v1.z - r.o.z;
+    const float cx = v2.x - r.o.x, cy = v2.y - r.o.y, cz = v2.z - r.o.z;
+    float p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z;
+    if (r.kz == 0) { p0x = ay; p0y = az; p0z = ax; p1x = by; p1y = bz; p1z = bx; p2x = cy; p2y = cz; p2z = cx; }
+    else if (r.kz == 1) { p0x = az; p0y = ax; p0z = ay; p1x = bz; p1y = bx; p1z = by; p2x = cz; p2y = cx; p2z = cy; }
+    else { p0x = ax; p0y = ay; p0z = az; p1x = bx; p1y = by; p1z = bz; p2x = cx; p2y = cy; p2z = cz; }
     p0x += r.sx * p0z; p0y += r.sy * p0z;
     p1x += r.sx * p1z; p1y += r.sy * p1z;
     p2x += r.sx * p2z; p2y += r.sy * p2z;
@@ -107,182 +111,100 @@ __device__ __forceinline__ bool tri_test(const float4 v0, const float4 v1, const
 
 __device__ __forceinline__ float cull_limit(float t_best) { return t_best * 1.0009765625f + 0.0009765625f; }
 
-#define TCPT_STACK_SENTINEL 0xffffffffu
+#define TCPT_TLAS_ITEM_BIT 0x80000000u
+#define TCPT_ABSENT 0xffffffffu
 
-// Closest hit.  COUNT adds box/triangle test counters (algorithmic work B, T of SURVEY.md section 8d).
-template <bool COUNT>
-__device__ inline DHit trace_closest(const DScene& sc, float3 o, float3 d, float t_max, uint32_t* n_box, uint32_t* n_tri) {
+// Closest hit (Scene::intersect, scene.rs:80-90).  COUNT adds box/triangle test counters (work figures B, T of SURVEY.md 8d).
+// ANY = Scene::intersect_p (scene.rs:93-103): order independent, returns at the first accepted triangle (prim = 0 on hit).
+template <bool ANY, bool COUNT>
+__device__ inline DHit trace_ray(const DScene& sc, float3 o, float3 d, float t_max, uint32_t* n_box, uint32_t* n_tri) {
     DHit best; best.prim = -1; best.t = t_max; best.b0 = best.b1 = best.b2 = 0.0f; best.tri = 0;
-    // tie-break state of the current best: TLAS leaf, position of the primitive inside that leaf, BLAS leaf
-    uint32_t best_tleaf = 0, best_titem = 0, best_bleaf = 0;
+    // tie-break state of the current best: TLAS (leaf first slot, slot) and BLAS (leaf first slot, slot)
+    uint32_t best_tleaf = 0, best_tslot = 0, best_bleaf = 0, best_bslot = 0;
     float limit = t_max;  // box-culling bound (t_max until the first hit)
 
     RayXform rw; ray_setup(rw, o, d);
     RayXform rl = rw;
     uint32_t stack[TCPT_TRAVERSAL_STACK];
     int sp = 0;
-    // TLAS root
-    {
-        const float4 lo = __ldg(&sc.nodes[0]), hi = __ldg(&sc.nodes[1]);
-        float te; if (COUNT) (*n_box)++;
-        if (!slab_test(lo, hi, rw, limit, &te)) return best;
-    }
-    uint32_t node = 0;           // current node (absolute index into sc.nodes/2)
-    bool in_blas = false;
-    uint32_t blas_base = 0, slot_base = 0;
-    int cur_prim = -1; uint32_t cur_tleaf = 0, cur_titem = 0;
-    // pending TLAS leaf iteration state
-    uint32_t tl_first = 0, tl_count = 0, tl_next = 0;
+    int blas_sp = -1;            // stack height at BLAS entry; -1 = traversing the TLAS
+    uint32_t node_base = 0, slot_base = 0;
+    int cur_prim = -1; uint32_t cur_tleaf = 0, cur_tslot = 0;
+    uint32_t node = 0;           // absolute record index
 
     for (;;) {
-        const float4 nlo = __ldg(&sc.nodes[2 * (size_t)node]), nhi = __ldg(&sc.nodes[2 * (size_t)node + 1]);
-        const uint32_t a = __float_as_uint(nlo.w), cnt = __float_as_uint(nhi.w);
-        bool pop = false;
-        if (cnt == 0) {
-            // inner: test both children, descend into the nearer, push the farther
-            const uint32_t base = in_blas ? blas_base : 0u;
-            const uint32_t c0 = node + 1, c1 = base + a;
-            const float4 lo0 = __ldg(&sc.nodes[2 * (size_t)c0]), hi0 = __ldg(&sc.nodes[2 * (size_t)c0 + 1]);
-            const float4 lo1 = __ldg(&sc.nodes[2 * (size_t)c1]), hi1 = __ldg(&sc.nodes[2 * (size_t)c1 + 1]);
-            float t0e, t1e;
-            const RayXform& r = in_blas ? rl : rw;
-            const bool h0 = slab_test(lo0, hi0, r, limit, &t0e);
-            const bool h1 = slab_test(lo1, hi1, r, limit, &t1e);
-            if (COUNT) (*n_box) += 2;
-            if (h0 && h1) {
-                if (t1e < t0e) { stack[sp++] = c0; node = c1; } else { stack[sp++] = c1; node = c0; }
-            } else if (h0) node = c0;
-            else if (h1) node = c1;
-            else pop = true;
-        } else if (!in_blas) {
-            // TLAS leaf: iterate its primitives one at a time (each may open a BLAS)
-            tl_first = a; tl_count = cnt; tl_next = 0; cur_tleaf = node;
-            pop = true;  // falls into the TLAS-leaf continuation below
-            stack[sp++] = TCPT_STACK_SENTINEL;  // marker: resume TLAS leaf iteration
-        } else {
-            // BLAS leaf: test triangles in order
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const size_t s = 3 * (size_t)(slot_base + a + i);
-                const float4 v0 = __ldg(&sc.tri_verts[s]), v1 = __ldg(&sc.tri_verts[s + 1]), v2 = __ldg(&sc.tri_verts[s + 2]);
-                float t, b0, b1, b2;
-                if (COUNT) (*n_tri)++;
-                if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) {
-                    // total order: smaller t; then (TLAS) later leaf, earlier primitive slot; then (BLAS) later leaf, earlier item
-                    bool take;
-                    if (best.prim < 0) take = true;
-                    else if (t != best.t) take = t < best.t;
-                    else if (cur_tleaf != best_tleaf) take = cur_tleaf > best_tleaf;
-                    else if (cur_titem != best_titem) take = cur_titem < best_titem;
-                    else if (node != best_bleaf) take = node > best_bleaf;
-                    else take = false;  // same leaf: earlier item already recorded
-                    if (take) {
-                        best.t = t; best.b0 = b0; best.b1 = b1; best.b2 = b2; best.prim = cur_prim; best.tri = __float_as_uint(v0.w);
-                        best_tleaf = cur_tleaf; best_titem = cur_titem; best_bleaf = node;
-                        limit = fminf(t_max, cull_limit(t));
+        const float4* rec = sc.nodes + 4 * (size_t)node;
+        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+        const bool in_blas = blas_sp >= 0;
+        const RayXform& r = in_blas ? rl : rw;
+        const uint32_t ref0 = __float_as_uint(q0.w), cnt0 = __float_as_uint(q1.w), ref1 = __float_as_uint(q2.w), cnt1 = __float_as_uint(q3.w);
+        float te0, te1;
+        bool h0 = slab_test(q0, q1, r, limit, &te0);
+        bool h1 = (ref1 != TCPT_ABSENT) && slab_test(q2, q3, r, limit, &te1);
+        if (COUNT) (*n_box) += (ref1 != TCPT_ABSENT) ? 2u : 1u;
+
+        // leaves are handled as soon as they are reached
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const bool hk = k == 0 ? h0 : h1;
+            const uint32_t cnt = k == 0 ? cnt0 : cnt1, first = k == 0 ? ref0 : ref1;
+            if (!hk || cnt == 0) continue;
+            if (in_blas) {
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    const size_t s = 3 * (size_t)(slot_base + first + i);
+                    const float4 v0 = __ldg(&sc.tri_verts[s]), v1 = __ldg(&sc.tri_verts[s + 1]), v2 = __ldg(&sc.tri_verts[s + 2]);
+                    float t, b0, b1, b2;
+                    if (COUNT) (*n_tri)++;
+                    if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) {
+                        if (ANY) { best.prim = 0; best.t = t; return best; }
+                        // total order: smaller t; then (TLAS) later leaf, earlier slot; then (BLAS) later leaf, earlier slot
+                        const uint32_t bslot = first + i;
+                        bool take;
+                        if (best.prim < 0) take = true;
+                        else if (t != best.t) take = t < best.t;
+                        else if (cur_tleaf != best_tleaf) take = cur_tleaf > best_tleaf;
+                        else if (cur_tslot != best_tslot) take = cur_tslot < best_tslot;
+                        else if (first != best_bleaf) take = first > best_bleaf;
+                        else take = bslot < best_bslot;
+                        if (take) {
+                            best.t = t; best.b0 = b0; best.b1 = b1; best.b2 = b2; best.prim = cur_prim; best.tri = __float_as_uint(v0.w);
+                            best_tleaf = cur_tleaf; best_tslot = cur_tslot; best_bleaf = first; best_bslot = bslot;
+                            limit = fminf(t_max, cull_limit(t));
+                        }
                     }
                 }
+            } else {
+                // TLAS leaf: queue its primitives (each opens a BLAS when popped)
+                for (uint32_t i = 0; i < cnt; ++i) stack[sp++] = TCPT_TLAS_ITEM_BIT | (first + cnt - 1u - i);
             }
-            pop = true;
         }
-        while (pop) {
+        const bool i0 = h0 && cnt0 == 0, i1 = h1 && cnt1 == 0;
+        if (i0 && i1) {
+            const uint32_t c0 = node_base + ref0, c1 = node_base + ref1;
+            if (te1 < te0) { stack[sp++] = c0; node = c1; } else { stack[sp++] = c1; node = c0; }
+            continue;
+        }
+        if (i0) { node = node_base + ref0; continue; }
+        if (i1) { node = node_base + ref1; continue; }
+        // pop
+        for (;;) {
+            if (sp == blas_sp) { blas_sp = -1; node_base = 0; }  // this BLAS is exhausted: back in the TLAS
             if (sp == 0) return best;
             const uint32_t top = stack[--sp];
-            if (top == TCPT_STACK_SENTINEL) {
-                // continue the TLAS leaf: open the next primitive's BLAS, or finish the leaf
-                in_blas = false;
-                if (tl_next < tl_count) {
-                    cur_titem = tl_next;
-                    cur_prim = __ldg(&sc.tlas_items[tl_first + tl_next]);
-                    tl_next++;
-                    const tcpt_flat_primitive& P = sc.primitives[cur_prim];
-                    const tcpt_flat_geometry& G = sc.geometries[P.geometry];
-                    if (P.identity) rl = rw;
-                    else ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
-                    blas_base = G.node_base; slot_base = G.slot_base;
-                    stack[sp++] = TCPT_STACK_SENTINEL;
-                    // BLAS root box with the caller's semantics
-                    const float4 lo = __ldg(&sc.nodes[2 * (size_t)blas_base]), hi = __ldg(&sc.nodes[2 * (size_t)blas_base + 1]);
-                    float te; if (COUNT) (*n_box)++;
-                    if (slab_test(lo, hi, rl, limit, &te)) { in_blas = true; node = blas_base; pop = false; }
-                } else {
-                    // the sentinel pushed for this leaf is consumed; restore the enclosing TLAS leaf state is not needed:
-                    // TLAS leaves never nest
-                }
-            } else {
-                // the culling bound may have shrunk since this node was pushed: re-test lazily by just visiting it
-                node = top; pop = false;
+            if (top & TCPT_TLAS_ITEM_BIT) {
+                const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
+                const int2 item = __ldg(&sc.tlas_items[tslot]);
+                cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
+                const tcpt_flat_primitive& P = sc.primitives[cur_prim];
+                const tcpt_flat_geometry& G = sc.geometries[P.geometry];
+                ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
+                node_base = G.node_base; slot_base = G.slot_base;
+                blas_sp = sp;
+                node = node_base;  // entry record: tests the BLAS root box
+                break;
             }
-        }
-    }
-}
-
-// Any hit (Scene::intersect_p, scene.rs:93-103): order independent, returns at the first accepted triangle
-template <bool COUNT>
-__device__ inline bool trace_any(const DScene& sc, float3 o, float3 d, float t_max, uint32_t* n_box, uint32_t* n_tri) {
-    RayXform rw; ray_setup(rw, o, d);
-    RayXform rl = rw;
-    uint32_t stack[TCPT_TRAVERSAL_STACK];
-    int sp = 0;
-    {
-        const float4 lo = __ldg(&sc.nodes[0]), hi = __ldg(&sc.nodes[1]);
-        float te; if (COUNT) (*n_box)++;
-        if (!slab_test(lo, hi, rw, t_max, &te)) return false;
-    }
-    uint32_t node = 0;
-    bool in_blas = false;
-    uint32_t blas_base = 0, slot_base = 0;
-    uint32_t tl_first = 0, tl_count = 0, tl_next = 0;
-    for (;;) {
-        const float4 nlo = __ldg(&sc.nodes[2 * (size_t)node]), nhi = __ldg(&sc.nodes[2 * (size_t)node + 1]);
-        const uint32_t a = __float_as_uint(nlo.w), cnt = __float_as_uint(nhi.w);
-        bool pop = false;
-        if (cnt == 0) {
-            const uint32_t base = in_blas ? blas_base : 0u;
-            const uint32_t c0 = node + 1, c1 = base + a;
-            const float4 lo0 = __ldg(&sc.nodes[2 * (size_t)c0]), hi0 = __ldg(&sc.nodes[2 * (size_t)c0 + 1]);
-            const float4 lo1 = __ldg(&sc.nodes[2 * (size_t)c1]), hi1 = __ldg(&sc.nodes[2 * (size_t)c1 + 1]);
-            float t0e, t1e;
-            const RayXform& r = in_blas ? rl : rw;
-            const bool h0 = slab_test(lo0, hi0, r, t_max, &t0e);
-            const bool h1 = slab_test(lo1, hi1, r, t_max, &t1e);
-            if (COUNT) (*n_box) += 2;
-            if (h0 && h1) { stack[sp++] = c1; node = c0; }
-            else if (h0) node = c0;
-            else if (h1) node = c1;
-            else pop = true;
-        } else if (!in_blas) {
-            tl_first = a; tl_count = cnt; tl_next = 0;
-            pop = true;
-            stack[sp++] = TCPT_STACK_SENTINEL;
-        } else {
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const size_t s = 3 * (size_t)(slot_base + a + i);
-                const float4 v0 = __ldg(&sc.tri_verts[s]), v1 = __ldg(&sc.tri_verts[s + 1]), v2 = __ldg(&sc.tri_verts[s + 2]);
-                float t, b0, b1, b2;
-                if (COUNT) (*n_tri)++;
-                if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) return true;
-            }
-            pop = true;
-        }
-        while (pop) {
-            if (sp == 0) return false;
-            const uint32_t top = stack[--sp];
-            if (top == TCPT_STACK_SENTINEL) {
-                in_blas = false;
-                if (tl_next < tl_count) {
-                    const int prim = __ldg(&sc.tlas_items[tl_first + tl_next]);
-                    tl_next++;
-                    const tcpt_flat_primitive& P = sc.primitives[prim];
-                    const tcpt_flat_geometry& G = sc.geometries[P.geometry];
-                    if (P.identity) rl = rw;
-                    else ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
-                    blas_base = G.node_base; slot_base = G.slot_base;
-                    stack[sp++] = TCPT_STACK_SENTINEL;
-                    const float4 lo = __ldg(&sc.nodes[2 * (size_t)blas_base]), hi = __ldg(&sc.nodes[2 * (size_t)blas_base + 1]);
-                    float te; if (COUNT) (*n_box)++;
-                    if (slab_test(lo, hi, rl, t_max, &te)) { in_blas = true; node = blas_base; pop = false; }
-                }
-            } else { node = top; pop = false; }
+            node = top;
+            break;
         }
     }
 }

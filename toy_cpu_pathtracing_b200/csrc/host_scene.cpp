@@ -220,16 +220,46 @@ int HostScene::add_env_light(float intensity, const float* rgb, uint32_t w, uint
     return (int)primitives.size() - 1;
 }
 
-static void put_nodes(const BuiltBvh& b, std::vector<tcpt_bvh_node>& out) {
-    for (const BuildNode& n : b.nodes) {
-        tcpt_bvh_node d;
-        d.lo[0] = n.box.lo.x; d.lo[1] = n.box.lo.y; d.lo[2] = n.box.lo.z;
-        d.hi[0] = n.box.hi.x; d.hi[1] = n.box.hi.y; d.hi[2] = n.box.hi.z;
-        uint32_t a = n.count ? n.first_item : n.second, c = n.count;
-        std::memcpy(&d.lo[3], &a, 4);
-        std::memcpy(&d.hi[3], &c, 4);
-        out.push_back(d);
+// Convert the reference-order tree (pre-order inner/leaf records) into the device's child-pair records (include/tcpt_flat.h).
+// Returns the number of records appended; *max_leaf receives the largest leaf item count.
+static uint32_t put_nodes(const BuiltBvh& b, std::vector<tcpt_bvh_node>& out, uint32_t* max_leaf) {
+    const size_t base = out.size();
+    auto set_child = [&](size_t rec, int k, const Box* box, uint32_t ref, uint32_t cnt) {
+        float* q = out[rec].q + 8 * k;
+        const float inf = INFINITY;
+        q[0] = box ? box->lo.x : inf; q[1] = box ? box->lo.y : inf; q[2] = box ? box->lo.z : inf;
+        q[4] = box ? box->hi.x : -inf; q[5] = box ? box->hi.y : -inf; q[6] = box ? box->hi.z : -inf;
+        std::memcpy(&q[3], &ref, 4);
+        std::memcpy(&q[7], &cnt, 4);
+    };
+    *max_leaf = 0;
+    for (const BuildNode& n : b.nodes) if (n.count > *max_leaf) *max_leaf = n.count;
+    // iterative pre-order over inner nodes; rec_of[i] = record index (relative) of inner node i
+    out.push_back(tcpt_bvh_node{});
+    set_child(base, 1, nullptr, 0xffffffffu, 0);
+    if (b.nodes.empty()) { set_child(base, 0, nullptr, 0xffffffffu, 0); return 1; }
+    struct Todo { uint32_t node; size_t parent_rec; int slot; };
+    std::vector<Todo> stack;
+    stack.push_back(Todo{0, base, 0});
+    while (!stack.empty()) {
+        const Todo t = stack.back(); stack.pop_back();
+        const BuildNode& n = b.nodes[t.node];
+        if (n.count) { set_child(t.parent_rec, t.slot, &n.box, n.first_item, n.count); continue; }
+        const size_t rec = out.size();
+        out.push_back(tcpt_bvh_node{});
+        set_child(t.parent_rec, t.slot, &n.box, (uint32_t)(rec - base), 0);
+        // child0 subtree is emitted first (pre-order): push child1 then child0
+        stack.push_back(Todo{n.second, rec, 1});
+        stack.push_back(Todo{t.node + 1, rec, 0});
     }
+    return (uint32_t)(out.size() - base);
+}
+
+// first slot of the leaf that owns each item slot
+static std::vector<uint32_t> leaf_first_of_slots(const BuiltBvh& b) {
+    std::vector<uint32_t> r(b.items.size(), 0);
+    for (const BuildNode& n : b.nodes) for (uint32_t j = 0; j < n.count; ++j) r[n.first_item + j] = n.first_item;
+    return r;
 }
 
 int HostScene::build(const float cam_pos[3], FlatStorage& S) {
@@ -265,8 +295,12 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     if (tb.empty()) { error = "build: no geometry primitives"; return TCPT_ERR_INVALID; }
     tlas = SahBuilder(tb).build();
 
-    put_nodes(tlas, S.nodes);
-    for (uint32_t it : tlas.items) S.tlas_items.push_back(tlas_prims[it]);
+    uint32_t tlas_max_leaf = 0;
+    put_nodes(tlas, S.nodes, &tlas_max_leaf);
+    {
+        const std::vector<uint32_t> lf = leaf_first_of_slots(tlas);
+        for (size_t k = 0; k < tlas.items.size(); ++k) { S.tlas_items.push_back(tlas_prims[tlas.items[k]]); S.tlas_items.push_back((int32_t)lf[k]); }
+    }
     const uint32_t tlas_nodes = (uint32_t)S.nodes.size();
 
     uint32_t deepest = 0;
@@ -275,17 +309,20 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         const HostMesh& m = meshes[g];
         if (!m.built) continue;
         tcpt_flat_geometry fg{};
-        fg.node_base = (uint32_t)S.nodes.size(); fg.node_count = (uint32_t)m.bvh.nodes.size();
+        fg.node_base = (uint32_t)S.nodes.size();
         fg.slot_base = (uint32_t)(S.tri_verts.size() / 12); fg.tri_count = (uint32_t)(m.indices.size() / 3);
         fg.vertex_base = (uint32_t)(S.positions.size() / 3); fg.index_base = (uint32_t)(S.indices.size() / 3);
         fg.tangent_base = (uint32_t)(S.tangents.size() / 3); fg.has_uv = m.uvs.empty() ? 0 : 1;
-        put_nodes(m.bvh, S.nodes);
-        for (uint32_t tri : m.bvh.items) {
+        uint32_t blas_max_leaf = 0;
+        fg.node_count = put_nodes(m.bvh, S.nodes, &blas_max_leaf);
+        const std::vector<uint32_t> lf = leaf_first_of_slots(m.bvh);
+        for (size_t slot = 0; slot < m.bvh.items.size(); ++slot) {
+            const uint32_t tri = m.bvh.items[slot];
             V3 p[3] = {m.positions[m.indices[3 * tri]], m.positions[m.indices[3 * tri + 1]], m.positions[m.indices[3 * tri + 2]]};
             V3 n = cross3(sub(p[1], p[0]), sub(p[2], p[0]));
             uint32_t degenerate = dot3(n, n) == 0.0f ? 1u : 0u;  // math/src/ray.rs:50-57, decided once on the host with the same arithmetic
             for (int k = 0; k < 3; ++k) {
-                float w; uint32_t bits = k == 0 ? tri : (k == 1 ? degenerate : 0u);
+                float w; uint32_t bits = k == 0 ? tri : (k == 1 ? degenerate : lf[slot]);
                 std::memcpy(&w, &bits, 4);
                 S.tri_verts.insert(S.tri_verts.end(), {p[k].x, p[k].y, p[k].z, w});
             }
@@ -343,7 +380,7 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
 
     tcpt_flat_scene& v = S.view;
     v.bvh_nodes = S.nodes.data(); v.n_bvh_nodes = S.nodes.size(); v.tlas_node_count = tlas_nodes;
-    v.tlas_items = S.tlas_items.data(); v.n_tlas_items = (uint32_t)S.tlas_items.size();
+    v.tlas_items = S.tlas_items.data(); v.n_tlas_items = (uint32_t)(S.tlas_items.size() / 2);
     v.tri_verts = S.tri_verts.data(); v.n_tri_slots = S.tri_verts.size() / 12;
     v.positions = S.positions.data(); v.normals = S.normals.data(); v.uvs = S.uvs.data(); v.n_vertices = S.positions.size() / 3;
     v.indices = S.indices.data(); v.n_triangles = S.indices.size() / 3; v.tangents = S.tangents.data();
@@ -356,7 +393,7 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     v.light_list = S.light_list.data(); v.n_lights = (uint32_t)S.light_list.size();
     v.envs = S.envs.data(); v.n_envs = (uint32_t)S.envs.size();
     v.env_floats = S.env_floats.data(); v.n_env_floats = S.env_floats.size();
-    v.max_bvh_depth = tlas.depth + deepest;
+    v.max_bvh_depth = tlas.depth + tlas_max_leaf + deepest;
     if (v.max_bvh_depth + 2 >= TCPT_TRAVERSAL_STACK) { error = "build: BVH deeper than the traversal stack"; return TCPT_ERR_LIMIT; }
     return TCPT_OK;
 }

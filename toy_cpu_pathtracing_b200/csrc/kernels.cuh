@@ -1,0 +1,396 @@
+// The wavefront kernels of the path-integration hot path (sm_100a).  One frame =
+//   for each pass (a block of pixels x a block of sample indices that fits the path-slot budget):
+//     k_generate                      camera rays + sampler dimensions 0..2          base_renderer.rs:160-177
+//     for bounce = 0 .. max_depth:
+//       k_trace_closest               Scene::intersect over the extension-ray queue  scene.rs:80-90
+//       k_shade                       everything between two intersect calls          base_renderer.rs:178-272
+//       k_trace_shadow                Scene::intersect_p + visible-branch add         scene.rs:93-103, common.rs:134-170
+//     k_film                          per-pixel in-order sum of the pass's samples    sensor.rs:76-77
+//   k_finalize                        /spp, clip, Reinhard, sRGB OETF                 sensor.rs:81-88
+// Queues are sized on the device (no host round trip inside a frame); every kernel is a grid-stride loop over a queue
+// whose length it reads from `counters`.
+#pragma once
+#include "dshade.cuh"
+#include "dtraverse.cuh"
+
+namespace tcpt {
+
+struct PathList { const uint32_t* xy; const uint32_t* sample; };  // explicit (pixel, sample) lists for tcpt_path_samples
+
+__device__ __forceinline__ void path_coords(const DRender& R, const PathList& L, uint32_t slot, uint32_t* px, uint32_t* py, uint32_t* si) {
+    if (L.xy) { *px = __ldg(L.xy + 2 * (size_t)slot); *py = __ldg(L.xy + 2 * (size_t)slot + 1); *si = __ldg(L.sample + slot); return; }
+    const uint32_t s_local = slot / R.n_pix, p_local = slot - s_local * R.n_pix;
+    const uint32_t k = R.pix_begin + p_local;
+    const uint32_t row = k / R.width;
+    *px = k - row * R.width;
+    *py = R.row_offset + row * R.row_stride;
+    *si = R.s_begin + s_local;
+}
+
+__device__ __forceinline__ DSampler make_sampler(const DRender& R, uint32_t px, uint32_t py, uint32_t si) {
+    DSampler s;
+    s.kind = (uint32_t)R.sampler; s.seed = R.seed; s.log2_spp = R.log2_spp; s.nb4 = R.n_base4_digits;
+    s.start(px, py, si);
+    return s;
+}
+
+// ---------------------------------------------------------------- K0 generate
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DCamera cam,
+                                                   const __grid_constant__ DState st, const __grid_constant__ PathList L, uint32_t n_slots) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += stride) {
+        uint32_t px, py, si;
+        path_coords(R, L, slot, &px, &py, &si);
+        DSampler smp = make_sampler(R, px, py, si);
+        const float u = smp.get_1d();
+        const float lambda0 = 360.0f + u * (830.0f - 360.0f);  // SampledWavelengths::new_uniform (sampled_spectrum.rs:318-336)
+        const float2 uv = smp.get_2d();
+        // BoxFilter::sample + Camera::sample_ray / generate_ray (filter.rs:24-30, camera.rs:51-81)
+        const float fx = uv.x * 1.0f - 1.0f * 0.5f, fy = uv.y * 1.0f - 1.0f * 0.5f;
+        const float x = (float)px + fx + 0.5f, y = (float)py + fy + 0.5f;
+        const float dir_x = (2.0f * x / (float)R.width - 1.0f) * cam.aspect * cam.scale;
+        const float dir_y = (1.0f - 2.0f * y / (float)R.height) * cam.scale;
+        const float3 rd = normalize(f3(dir_x, dir_y, -1.0f));
+        const float3 d = normalize((cam.s * rd.x + cam.u * rd.y) + cam.nf * rd.z);
+        const float3 o = f3(0.0f, 0.0f, 0.0f) + d * 1e-5f;  // move_forward(1e-5) (base_renderer.rs:177)
+        st.ext_o[0][slot] = make_float4(o.x, o.y, o.z, TCPT_FLT_MAX);
+        st.ext_d[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
+        st.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        st.con[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(smp.dim), __uint_as_float(0u));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0; atomicAdd(&st.stats[4], (unsigned long long)n_slots); }
+}
+
+// ---------------------------------------------------------------- K1 closest hit
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
+                                                        float4* __restrict__ hit0, uint2* __restrict__ hit1, const __grid_constant__ DState st, int cur) {
+    const uint32_t n = st.counters[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // the queues this bounce's k_shade appends to were last read one bounce ago (stream order): reset them here
+        st.counters[cur ^ 1] = 0; st.counters[2] = 0;
+        atomicAdd(&st.stats[0], (unsigned long long)n);
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t nb = 0, nt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o = q_o[i], d = q_d[i];
+        const DHit h = trace_ray<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
+        hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
+        hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
+    }
+    if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
+}
+
+// ---------------------------------------------------------------- K3/K4 shadow rays + visible-branch accumulation
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_shadow(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st) {
+    const uint32_t n = st.counters[2];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st.stats[1], (unsigned long long)n);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t nb = 0, nt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o = st.sh_o[i], d = st.sh_d[i];
+        const DHit h = trace_ray<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
+        const uint32_t tag = __float_as_uint(d.w);
+        const uint32_t slot = tag & 0x7fffffffu;
+        const bool visible = h.prim < 0, last = (tag & 0x80000000u) != 0;
+        if (!visible && !last) continue;
+        S4 con = s4(st.con[slot]);
+        if (visible) {
+            con = con + s4(st.sh_c[i]);
+            st.con[slot] = to_f4(con);
+        }
+        if (last) {  // the path ended at this vertex (failed BSDF sample): hand its radiance to the sensor
+            const float4 misc = st.misc[slot];
+            const DWavelengths wl = wavelengths_uniform(misc.y, (__float_as_uint(misc.w) & FLAG_LAMBDA_TERMINATED) != 0);
+            const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
+            st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+        }
+    }
+    if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
+}
+
+// ---------------------------------------------------------------- K2 shade
+struct ShadeOut {
+    bool push_ext, push_sh;
+    float4 eo, ed, so, sd, sc;
+};
+
+__device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DState& st, const PathList& L, uint32_t stage,
+                                    float3 ray_d, uint32_t slot, const float4 h0, const uint2 h1, ShadeOut& out) {
+    out.push_ext = false; out.push_sh = false;
+    const float4 misc = st.misc[slot];
+    float pdf_prev = misc.x;
+    const float lambda0 = misc.y;
+    uint32_t flags = __float_as_uint(misc.w);
+    DWavelengths wl = wavelengths_uniform(lambda0, (flags & FLAG_LAMBDA_TERMINATED) != 0);
+    uint32_t px, py, si;
+    path_coords(R, L, slot, &px, &py, &si);
+    DSampler smp = make_sampler(R, px, py, si);
+    smp.dim = __float_as_uint(misc.z);
+    S4 thr = s4(st.thr[slot]), con = s4(st.con[slot]);
+    const int integrator = R.integrator;
+    const bool miss = (int)h1.x < 0;
+
+    auto finish = [&]() {
+        const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
+        st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+    };
+
+    if (miss) {
+        if (sc.n_envs != 0) {
+            if (stage == 0) {
+                con = con + thr * scene_env_radiance(sc, ray_d, wl);  // base_renderer.rs:180-186
+            } else if (integrator != TCPT_INTEGRATOR_NEE) {
+                const S4 fprev = s4(st.fprev[slot]);
+                const S4 radiance = scene_env_radiance(sc, ray_d, wl);
+                if (integrator == TCPT_INTEGRATOR_PT) {
+                    con = con + thr * fprev * radiance / pdf_prev;  // pt_renderer.rs:80-81
+                } else {
+                    LightTable lt; light_table(sc, wl, lt);
+                    const float light_pdf = scene_env_pdf(sc, lt, ray_d);
+                    const float a = pdf_prev, b = light_pdf;
+                    const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
+                    const float tf = 1.0f / pdf_prev;
+                    con = con + thr * fprev * radiance * tf * w;  // mis_renderer.rs:228-229
+                }
+            }
+        }
+        finish();
+        return;
+    }
+
+    DSurface hit;
+    reconstruct_hit(sc, (int)h1.x, h1.y, h0.y, h0.z, h0.w, ray_d, hit);
+    const tcpt_flat_material& mat = sc.materials[hit.material];
+    const bool emissive = mat.type == TCPT_MAT_EMISSIVE;
+
+    if (stage == 0) {
+        if (emissive) con = con + thr * emissive_radiance(sc, mat, hit.uv, wl);  // base_renderer.rs:190-194
+    } else {
+        // second half of the previous bounce: calculate_bsdf_contribution, throughput update, Russian roulette
+        const S4 fprev = s4(st.fprev[slot]);
+        const float tf = 1.0f / pdf_prev;
+        S4 next_emissive = s4(0.0f);
+        if (emissive) next_emissive = fprev * emissive_radiance(sc, mat, hit.uv, wl) * tf;  // base_renderer.rs:125-131
+        const S4 modifier = fprev * tf;
+        const bool spec_prev = (flags & FLAG_SPEC_PREV) != 0;
+        if (integrator == TCPT_INTEGRATOR_PT) {
+            con = con + thr * next_emissive;                                  // pt_renderer.rs:41-43
+        } else if (integrator == TCPT_INTEGRATOR_NEE) {
+            if (spec_prev) con = con + thr * next_emissive;                   // nee_renderer.rs:139-147
+        } else {
+            if (spec_prev) con = con + thr * next_emissive;                   // mis_renderer.rs:160-163
+            else {
+                LightTable lt; light_table(sc, wl, lt);
+                const float4 pp = st.ppos[slot];
+                const float pdf_light = scene_pdf_light_sample(sc, lt, f3(pp.x, pp.y, pp.z), hit);
+                const float a = pdf_prev, b = pdf_light;
+                const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
+                con = con + thr * next_emissive * w;                          // mis_renderer.rs:164-179
+            }
+        }
+        thr = thr * modifier;
+        const float p_rr = s4_max(thr);                                       // base_renderer.rs:76-92
+        if (!(p_rr >= 1.0f)) {
+            const float ur = smp.get_1d();
+            if (ur < p_rr) { if (p_rr != 0.0f) { thr.v[0] /= p_rr; thr.v[1] /= p_rr; thr.v[2] /= p_rr; thr.v[3] /= p_rr; } }
+            else { finish(); return; }
+        }
+    }
+    if (stage >= R.max_depth || emissive) { finish(); return; }  // depth loop bound (:197) / emitters have no BSDF (:199-202)
+
+    // ---- one bounce (base_renderer.rs:199-237)
+    M3 r2t, t2r;
+    shading_frame(hit, r2t, t2r);
+    const float3 wo = m3_vector(r2t, hit.wo);
+    const float3 ng_t = m3_normal_by_inverse(t2r, hit.normal);  // Transform * Normal = inverse(r2t)^T n, normalised
+    MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
+    const float uc = smp.get_1d();
+    const float2 uv = smp.get_2d();
+    const MatSample ms = material_sample(mc, mat, uc, uv, wl, wo, ng_t, hit.uv);
+
+    if (!ms.is_specular() && integrator != TCPT_INTEGRATOR_PT) {
+        // next event estimation (nee_renderer.rs:18-102, mis_renderer.rs:21-123)
+        const bool with_mis = integrator == TCPT_INTEGRATOR_MIS;
+        LightTable lt; light_table(sc, wl, lt);
+        const float u = smp.get_1d();
+        float p_light = 0.0f;
+        const int li = sample_light(sc, lt, u, &p_light);
+        if (li >= 0) {
+            const float s = smp.get_1d();
+            const float2 luv = smp.get_2d();
+            const int lprim = sc.light_list[li];
+            const tcpt_flat_primitive& LP = sc.primitives[lprim];
+            float3 sh_dir; float sh_tmax; S4 pending;
+            if (LP.kind == 2) {
+                // EnvironmentLight::sample_infinite_light (environment_light.rs:326-350) + evaluate_infinite_light{,_with_mis} (common.rs:174-241)
+                const DEnv& e = sc.envs[LP.env];
+                const uint32_t yy = sample_from_cdf(e.marginal, e.h, luv.x);
+                const uint32_t xx = sample_from_cdf(e.conditional + (size_t)yy * e.w, e.w, luv.y);
+                const float eu = ((float)xx + 0.5f) / (float)e.w, ev = ((float)yy + 0.5f) / (float)e.h;
+                const float theta = ev * TCPT_PI, phi = eu * 2.0f * TCPT_PI;
+                const float3 wl_local = f3(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));
+                const float3 wi_r = xf_vector(LP.l2r, wl_local);
+                const float pdf_dir = env_direction_pdf(sc, LP, wi_r);
+                const S4 radiance = env_direction_radiance(sc, LP, wi_r, wl);
+                const float3 wi = m3_vector(r2t, wi_r);
+                S4 f; float bpdf;
+                material_eval_pdf(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
+                const float w = with_mis ? ((pdf_dir == 0.0f && bpdf == 0.0f) ? 0.0f : pdf_dir / (pdf_dir + bpdf)) : 1.0f;
+                const S4 c = f * radiance / (pdf_dir * p_light);
+                pending = with_mis ? thr * c * w : thr * c;
+                sh_dir = wi_r; sh_tmax = TCPT_FLT_MAX;
+            } else {
+                // EmissiveTriangleMesh::sample_radiance (emissive_triangle_mesh.rs:176-309) + evaluate_area_light{,_with_mis} (common.rs:82-171)
+                const tcpt_flat_geometry& G = sc.geometries[LP.geometry];
+                const float* table = sc.area_table + LP.area_base;
+                uint32_t index = 0;
+                for (uint32_t i = 0; i < G.tri_count; ++i) if (s < __ldg(table + i)) { index = i; break; }
+                float b0, b1;
+                if (luv.x < luv.y) { b0 = luv.x / 2.0f; b1 = luv.y - b0; } else { b1 = luv.y / 2.0f; b0 = luv.x - b1; }
+                const float b2 = 1.0f - b0 - b1;
+                const uint32_t* idx = sc.indices + 3 * ((size_t)G.index_base + index);
+                const uint32_t i0 = __ldg(idx) + G.vertex_base, i1 = __ldg(idx + 1) + G.vertex_base, i2 = __ldg(idx + 2) + G.vertex_base;
+                const float* pp = sc.positions;
+                const float3 p0 = xf_point(LP.l2r, f3(__ldg(pp + 3 * (size_t)i0), __ldg(pp + 3 * (size_t)i0 + 1), __ldg(pp + 3 * (size_t)i0 + 2)));
+                const float3 p1 = xf_point(LP.l2r, f3(__ldg(pp + 3 * (size_t)i1), __ldg(pp + 3 * (size_t)i1 + 1), __ldg(pp + 3 * (size_t)i1 + 2)));
+                const float3 p2 = xf_point(LP.l2r, f3(__ldg(pp + 3 * (size_t)i2), __ldg(pp + 3 * (size_t)i2 + 1), __ldg(pp + 3 * (size_t)i2 + 2)));
+                const float3 lpos = (p0 * b0 + p1 * b1) + p2 * b2;
+                const float3 lnormal = normalize(normalize(cross(p1 - p0, p2 - p0)));
+                float2 tuv = make_float2(0.0f, 0.0f);
+                if (G.has_uv) {
+                    const float* uu = sc.uvs;
+                    tuv.x = (__ldg(uu + 2 * (size_t)i0) * b0 + __ldg(uu + 2 * (size_t)i1) * b1) + __ldg(uu + 2 * (size_t)i2) * b2;
+                    tuv.y = (__ldg(uu + 2 * (size_t)i0 + 1) * b0 + __ldg(uu + 2 * (size_t)i1 + 1) * b1) + __ldg(uu + 2 * (size_t)i2 + 1) * b2;
+                }
+                const float3 dv = lpos - hit.position;
+                const float3 wi_r = normalize(dv);
+                const S4 radiance = emissive_radiance(sc, sc.materials[LP.material], tuv, wl);
+                const float pdf_area = 1.0f / LP.area_sum;
+                const float distance = length(dv);
+                const float pdf_dir = pdf_area * (distance * distance) / rmax(fabsf(dot(lnormal, -wi_r)), 1e-8f);
+                const float3 wi = m3_vector(r2t, wi_r);
+                S4 f; float bpdf;
+                material_eval_pdf(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
+                const float distance2 = length_squared(dv);
+                const float3 ln_t = m3_normal_by_inverse(t2r, lnormal);
+                const float cos_light = fabsf(dot(ln_t, -wi));
+                const float g = cos_light / distance2;
+                const float w = with_mis ? ((pdf_dir == 0.0f && bpdf == 0.0f) ? 0.0f : pdf_dir / (pdf_dir + bpdf)) : 1.0f;
+                const S4 c = f * radiance * g / (pdf_area * p_light);
+                pending = with_mis ? thr * c * w : thr * c;
+                sh_dir = wi_r; sh_tmax = distance - 2.0f * 1e-4f;
+            }
+            const float3 so = hit.position + sh_dir * 1e-4f;  // move_forward(1e-4), no normal offset (common.rs:12,134-140)
+            out.push_sh = true;
+            out.so = make_float4(so.x, so.y, so.z, sh_tmax);
+            out.sd = make_float4(sh_dir.x, sh_dir.y, sh_dir.z, __uint_as_float(slot));
+            out.sc = to_f4(pending);
+        }
+    }
+
+    if (!ms.sampled) {
+        // process_bsdf_sampling returned None: the path ends here (base_renderer.rs:240-253 adds nothing for a failed sample)
+        st.con[slot] = to_f4(con);
+        if (out.push_sh) {
+            out.sd.w = __uint_as_float(slot | 0x80000000u);
+            st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(smp.dim), __uint_as_float(wl.terminated ? FLAG_LAMBDA_TERMINATED : 0u));
+        } else finish();
+        return;
+    }
+    // spawn the extension ray (base_renderer.rs:111-121)
+    const float3 wi_render = m3_vector(t2r, ms.wi);
+    const float sign = dot(hit.normal, wi_render) < 0.0f ? -1.0f : 1.0f;
+    const float3 origin = hit.position + (sign * hit.normal) * 1e-5f;
+    const float3 o2 = origin + wi_render * 1e-5f;
+    out.push_ext = true;
+    out.eo = make_float4(o2.x, o2.y, o2.z, TCPT_FLT_MAX);
+    out.ed = make_float4(wi_render.x, wi_render.y, wi_render.z, __uint_as_float(slot));
+    st.thr[slot] = to_f4(thr);
+    st.con[slot] = to_f4(con);
+    st.fprev[slot] = to_f4(ms.f);
+    st.ppos[slot] = make_float4(hit.position.x, hit.position.y, hit.position.z, 0.0f);
+    flags = (ms.is_specular() ? FLAG_SPEC_PREV : 0u) | (wl.terminated ? FLAG_LAMBDA_TERMINATED : 0u);
+    st.misc[slot] = make_float4(ms.pdf, lambda0, __uint_as_float(smp.dim), __uint_as_float(flags));
+}
+
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st,
+                                                const __grid_constant__ PathList L, int cur, uint32_t stage) {
+    const uint32_t n = st.counters[cur];
+    const float4* __restrict__ q_d = st.ext_d[cur];
+    float4* __restrict__ n_o = st.ext_o[cur ^ 1];
+    float4* __restrict__ n_d = st.ext_d[cur ^ 1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        ShadeOut out; out.push_ext = false; out.push_sh = false;
+        if (i < n) {
+            const float4 d = q_d[i];
+            shade_vertex(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+        }
+        const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
+        if (out.push_ext) { n_o[pe] = out.eo; n_d[pe] = out.ed; }
+        const uint32_t ps = warp_push(&st.counters[2], out.push_sh);
+        if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
+    }
+}
+
+// ---------------------------------------------------------------- K5 film: acc[pixel] += rgb of samples s_begin .. s_begin + s_count, in order
+__global__ void __launch_bounds__(256) k_film(const __grid_constant__ DRender R, const float4* __restrict__ rgb, float* __restrict__ acc) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < R.n_pix; p += stride) {
+        const uint32_t k = R.pix_begin + p;
+        const uint32_t row = k / R.width;
+        const uint32_t px = k - row * R.width, py = R.row_offset + row * R.row_stride;
+        float* a = acc + 3 * ((size_t)py * R.width + px);
+        float r = a[0], g = a[1], b = a[2];
+        for (uint32_t s = 0; s < R.s_count; ++s) {
+            const float4 v = rgb[(size_t)s * R.n_pix + p];
+            r += v.x; g += v.y; b += v.z;
+        }
+        a[0] = r; a[1] = g; a[2] = b;
+    }
+}
+
+// Sensor::to_rgb (sensor.rs:81-88) + ReinhardToneMap (tone_map.rs:20-28) + sRGB OETF (color/src/eotf.rs:53-61)
+__global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ acc, float* __restrict__ out, uint32_t n_values, float spp) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_values; i += stride) {
+        float c = acc[i] / spp;
+        c = c > 0.0f ? c : 0.0f;  // Vec3::max(ZERO)
+        c = c / (1.0f + c);
+        out[i] = linear_to_srgb(c);
+    }
+}
+
+// ---------------------------------------------------------------- single-stage probes for parity tests and the traversal micro-benchmark
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
+                                                     int any_hit, float4* __restrict__ hit0, uint2* __restrict__ hit1, unsigned long long* stats) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t nb = 0, nt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o = q_o[i], d = q_d[i];
+        DHit h;
+        if (any_hit) h = trace_ray<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
+        else h = trace_ray<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
+        hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
+        hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
+    }
+    if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)nb); atomicAdd(&stats[3], (unsigned long long)nt); }
+}
+
+__global__ void k_sampler_stream(const __grid_constant__ DRender R, uint32_t px, uint32_t py, uint32_t si, const int32_t* kinds, int n, float* out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    DSampler smp = make_sampler(R, px, py, si);
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+        if (kinds[i] == 1) out[k++] = smp.get_1d();
+        else { const float2 v = smp.get_2d(); out[k++] = v.x; out[k++] = v.y; }
+    }
+}
+
+}  // namespace tcpt

@@ -1,0 +1,621 @@
+// libtcpt: context, device memory, frame orchestration and the C ABI of include/tcpt.h / include/tcpt_flat.h.
+// Product code.  There is no CPU fallback: without a usable sm_100 device every computing entry point fails with TCPT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tcpt.h"
+#include "../../include/tcpt_flat.h"
+#include "host_scene.h"
+#include "kernels.cuh"
+
+using namespace tcpt;
+
+namespace {
+
+struct DeviceBuffers {  // one flattened scene on the device
+    std::vector<void*> allocs;
+    DScene view{};
+    uint32_t max_bvh_depth = 0;
+    bool valid = false;
+};
+
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8; };
+
+}  // namespace
+
+struct tcpt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    HostScene host;
+    FlatStorage flat;
+    DeviceBuffers dev;
+    // tables on the device
+    float4* d_cmf = nullptr; float* d_rgb2spec = nullptr;  // d_rgb2spec = 64 z nodes + table
+    float xyz_to_rgb[9];
+    // wavefront buffers
+    DState st{};
+    uint32_t st_capacity = 0;
+    std::vector<void*> st_allocs;
+    unsigned long long* d_stats = nullptr;
+    uint32_t* d_counters = nullptr;
+    Options opt;
+    tcpt_stats stats{};
+    int sm_count = 148;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(tcpt_ctx* c, int code, const std::string& msg) { if (c) c->error = msg; return code; }
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(ctx, TCPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+int upload(tcpt_ctx* ctx, DeviceBuffers& db, const T* src, size_t n, const T** dst) {
+    *dst = nullptr;
+    void* p = nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    CU(cudaMalloc(&p, bytes));
+    db.allocs.push_back(p);
+    if (n) CU(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return TCPT_OK;
+}
+
+void free_scene(DeviceBuffers& db) {
+    for (void* p : db.allocs) cudaFree(p);
+    db.allocs.clear();
+    db.valid = false;
+}
+
+// color/src/gamut.rs:29-69 with glam's Mat3 arithmetic (column major), evaluated on the host like the reference does
+void srgb_xyz_to_rgb(float out[9]) {
+    struct V { float x, y, z; };
+    auto xy = [](float x, float y) { return y == 0.0f ? V{0, 0, 0} : V{x * 1.0f / y, 1.0f, (1.0f - x - y) * 1.0f / y}; };
+    auto cross = [](V a, V b) { return V{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; };
+    auto dot = [](V a, V b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); };
+    auto scale = [](V a, float s) { return V{a.x * s, a.y * s, a.z * s}; };
+    auto add = [](V a, V b) { return V{a.x + b.x, a.y + b.y, a.z + b.z}; };
+    struct M { V c0, c1, c2; };
+    auto mulv = [&](const M& m, V v) { return add(add(scale(m.c0, v.x), scale(m.c1, v.y)), scale(m.c2, v.z)); };
+    auto inv = [&](const M& m) {
+        V t0 = cross(m.c1, m.c2), t1 = cross(m.c2, m.c0), t2 = cross(m.c0, m.c1);
+        float id = 1.0f / dot(m.c2, t2);
+        V a = scale(t0, id), b = scale(t1, id), c = scale(t2, id);
+        return M{V{a.x, b.x, c.x}, V{a.y, b.y, c.y}, V{a.z, b.z, c.z}};
+    };
+    const M rgb{xy(0.6400f, 0.3300f), xy(0.3000f, 0.6000f), xy(0.1500f, 0.0600f)};
+    const V w = xy(0.3127f, 0.3290f);
+    const V c = mulv(inv(rgb), w);
+    const M diag{V{c.x, 0, 0}, V{0, c.y, 0}, V{0, 0, c.z}};
+    const M m{mulv(rgb, diag.c0), mulv(rgb, diag.c1), mulv(rgb, diag.c2)};
+    const M r = inv(m);
+    const float v[9] = {r.c0.x, r.c0.y, r.c0.z, r.c1.x, r.c1.y, r.c1.z, r.c2.x, r.c2.y, r.c2.z};
+    std::memcpy(out, v, sizeof v);
+}
+
+int ensure_state(tcpt_ctx* ctx, uint32_t capacity) {
+    if (ctx->st_capacity >= capacity) return TCPT_OK;
+    for (void* p : ctx->st_allocs) cudaFree(p);
+    ctx->st_allocs.clear();
+    ctx->st_capacity = 0;
+    auto alloc = [&](size_t bytes, void** out) -> int {
+        CU(cudaMalloc(out, bytes));
+        ctx->st_allocs.push_back(*out);
+        return TCPT_OK;
+    };
+    DState& s = ctx->st;
+    const size_t n = capacity;
+    float4** f4s[] = {&s.thr, &s.con, &s.fprev, &s.misc, &s.ppos, &s.rgb, &s.ext_o[0], &s.ext_o[1], &s.ext_d[0], &s.ext_d[1], &s.hit0, &s.sh_o, &s.sh_d, &s.sh_c};
+    for (float4** p : f4s) { int r = alloc(n * sizeof(float4), (void**)p); if (r) return r; }
+    { int r = alloc(n * sizeof(uint2), (void**)&s.hit1); if (r) return r; }
+    s.counters = ctx->d_counters;
+    s.stats = ctx->d_stats;
+    ctx->st_capacity = capacity;
+    return TCPT_OK;
+}
+
+int grid_for(const tcpt_ctx* ctx, uint64_t n, int block) {
+    const uint64_t want = (n + block - 1) / block;
+    const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)ctx->opt.blocks_per_sm;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+uint32_t log2_int(uint32_t v) { return v == 0 ? 0 : 31 - (uint32_t)__builtin_clz(v); }
+uint32_t round_up_pow2(uint32_t v) { return v <= 1 ? 1u : 1u << (32 - __builtin_clz(v - 1)); }
+
+int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera& cam) {
+    if (!p || p->width == 0 || p->height == 0 || p->spp == 0) return fail(ctx, TCPT_ERR_INVALID, "render: width, height and spp must be positive");
+    if (p->integrator < 0 || p->integrator > 2 || p->sampler < 0 || p->sampler > 1) return fail(ctx, TCPT_ERR_INVALID, "render: unknown integrator or sampler");
+    if (!ctx->dev.valid) return fail(ctx, TCPT_ERR_INVALID, "render: no scene uploaded (call tcpt_scene_build or tcpt_upload_flat_scene)");
+    std::memset(&R, 0, sizeof R);
+    R.width = p->width; R.height = p->height; R.spp = p->spp; R.seed = p->seed; R.max_depth = p->max_depth;
+    R.integrator = p->integrator; R.sampler = p->sampler; R.exposure = p->exposure;
+    // ZSobolSampler::new (z_sobol_sampler.rs:179-196)
+    R.log2_spp = log2_int(p->spp);
+    const uint32_t res = round_up_pow2(p->width > p->height ? p->width : p->height);
+    R.n_base4_digits = log2_int(res) + (R.log2_spp + 1) / 2;
+    R.row_offset = p->row_stride ? p->row_offset : 0;
+    R.row_stride = p->row_stride ? p->row_stride : 1;
+    // Camera::set_look_to + generate_ray constants (camera.rs:39-65); glam Mat3::look_to_rh columns s, u, -f after the transpose
+    auto nrm = [](const float v[3], float o[3]) { float l = std::sqrt((v[0] * v[0]) + (v[1] * v[1]) + (v[2] * v[2])); float r = 1.0f / l; o[0] = v[0] * r; o[1] = v[1] * r; o[2] = v[2] * r; };
+    float f[3], up[3], s[3], u[3];
+    nrm(p->cam_dir, f); nrm(p->cam_up, up);
+    float sx[3] = {f[1] * up[2] - up[1] * f[2], f[2] * up[0] - up[2] * f[0], f[0] * up[1] - up[0] * f[1]};
+    nrm(sx, s);
+    u[0] = s[1] * f[2] - f[1] * s[2]; u[1] = s[2] * f[0] - f[2] * s[0]; u[2] = s[0] * f[1] - f[0] * s[1];
+    cam.s = make_float3(s[0], s[1], s[2]); cam.u = make_float3(u[0], u[1], u[2]); cam.nf = make_float3(-f[0], -f[1], -f[2]);
+    const float fov_rad = p->fov_deg * (3.14159265358979323846f / 180.0f);  // f32::to_radians
+    cam.scale = std::tan(fov_rad / 2.0f);
+    cam.aspect = (float)p->width / (float)p->height;
+    return TCPT_OK;
+}
+
+struct StageTimer {
+    tcpt_ctx* ctx; bool on; cudaEvent_t a, b; double* acc;
+    StageTimer(tcpt_ctx* c, double* target) : ctx(c), on(c->opt.stage_timing != 0), a(nullptr), b(nullptr), acc(target) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b); *acc += ms;
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+// one pass = generate + (max_depth + 1) x {closest, shade, shadow} (+ film when acc != nullptr)
+int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList& L, uint32_t n_slots, float* dev_acc, cudaStream_t stream) {
+    const DScene& sc = ctx->dev.view;
+    const DState& st = ctx->st;
+    const bool count = ctx->opt.count_tests != 0;
+    {
+        StageTimer t(ctx, &ctx->stats.generate_ms);
+        k_generate<<<grid_for(ctx, n_slots, 256), 256, 0, stream>>>(sc, R, cam, st, L, n_slots);
+        ctx->stats.kernel_launches++;
+    }
+    const int g128 = grid_for(ctx, n_slots, 128);
+    for (uint32_t stage = 0; stage <= R.max_depth; ++stage) {
+        const int cur = (int)(stage & 1u);
+        {
+            StageTimer t(ctx, &ctx->stats.trace_closest_ms);
+            if (count) k_trace_closest<true><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
+            else k_trace_closest<false><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
+        }
+        {
+            StageTimer t(ctx, &ctx->stats.shade_ms);
+            k_shade<<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+        }
+        ctx->stats.kernel_launches += 2;
+        if (R.integrator != TCPT_INTEGRATOR_PT && stage < R.max_depth) {
+            StageTimer t(ctx, &ctx->stats.trace_shadow_ms);
+            if (count) k_trace_shadow<true><<<g128, 128, 0, stream>>>(sc, R, st);
+            else k_trace_shadow<false><<<g128, 128, 0, stream>>>(sc, R, st);
+            ctx->stats.kernel_launches++;
+        }
+    }
+    if (dev_acc) {
+        StageTimer t(ctx, &ctx->stats.film_ms);
+        k_film<<<grid_for(ctx, R.n_pix, 256), 256, 0, stream>>>(R, st.rgb, dev_acc);
+        ctx->stats.kernel_launches++;
+    }
+    ctx->stats.passes++;
+    CU(cudaGetLastError());
+    return TCPT_OK;
+}
+
+int fetch_stats(tcpt_ctx* ctx) {
+    unsigned long long h[8];
+    CU(cudaMemcpy(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    ctx->stats.closest_rays = h[0]; ctx->stats.shadow_rays = h[1]; ctx->stats.box_tests = h[2]; ctx->stats.tri_tests = h[3]; ctx->stats.paths = h[4];
+    return TCPT_OK;
+}
+
+void reset_stats(tcpt_ctx* ctx) {
+    cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    ctx->stats = tcpt_stats{};
+    ctx->stats.max_bvh_depth = ctx->dev.max_bvh_depth;
+}
+
+int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cudaStream_t stream) {
+    DRender R; DCamera cam;
+    int rc = make_render(ctx, p, R, cam);
+    if (rc) return rc;
+    if (R.row_offset >= R.row_stride) return fail(ctx, TCPT_ERR_INVALID, "render: row_offset must be < row_stride");
+    const uint32_t s0 = (p->spp_begin == 0 && p->spp_end == 0) ? 0 : p->spp_begin;
+    const uint32_t s1 = (p->spp_begin == 0 && p->spp_end == 0) ? p->spp : p->spp_end;
+    if (s1 > p->spp || s0 > s1) return fail(ctx, TCPT_ERR_INVALID, "render: bad sample range");
+    const uint32_t rows = R.row_offset < p->height ? (p->height - R.row_offset + R.row_stride - 1) / R.row_stride : 0;
+    const uint64_t owned = (uint64_t)rows * p->width;
+    if (owned == 0 || s0 == s1) return TCPT_OK;
+    const uint64_t budget = p->max_slots ? p->max_slots : (4u << 20);
+    const uint32_t np = (uint32_t)(owned < budget ? owned : budget);
+    uint32_t sc_per_pass = (uint32_t)(budget / np);
+    if (sc_per_pass < 1) sc_per_pass = 1;
+    if (sc_per_pass > s1 - s0) sc_per_pass = s1 - s0;
+    rc = ensure_state(ctx, (uint32_t)((uint64_t)np * sc_per_pass));
+    if (rc) return rc;
+    PathList none{nullptr, nullptr};
+    for (uint64_t pb = 0; pb < owned; pb += np) {
+        const uint32_t n_pix = (uint32_t)((owned - pb) < np ? (owned - pb) : np);
+        for (uint32_t sb = s0; sb < s1; sb += sc_per_pass) {
+            DRender Rp = R;
+            Rp.n_pix = n_pix; Rp.pix_begin = (uint32_t)pb; Rp.s_begin = sb; Rp.s_count = (s1 - sb) < sc_per_pass ? (s1 - sb) : sc_per_pass;
+            rc = run_pass(ctx, Rp, cam, none, n_pix * Rp.s_count, dev_acc, stream);
+            if (rc) return rc;
+        }
+    }
+    return TCPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tcpt_create(int device_id, tcpt_ctx** out) {
+    if (!out) return TCPT_ERR_INVALID;
+    *out = nullptr;
+    tcpt_ctx* ctx = new tcpt_ctx();
+    ctx->device = device_id;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    auto bail = [&](const std::string& m) { ctx->error = m; *out = ctx; return TCPT_ERR_CUDA; };  // ctx is returned so the message can be read; destroy it
+    if (e != cudaSuccess || n <= 0) return bail(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return bail("device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if (prop.major != 10) return bail("libtcpt is built for sm_100a only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaMalloc((void**)&ctx->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(cudaGetErrorString(e));
+    cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_counters, 0, 16 * sizeof(uint32_t));
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    srgb_xyz_to_rgb(ctx->xyz_to_rgb);
+    *out = ctx;
+    return TCPT_OK;
+}
+
+void tcpt_destroy(tcpt_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->stream) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    free_scene(ctx->dev);
+    for (void* p : ctx->st_allocs) cudaFree(p);
+    if (ctx->d_cmf) cudaFree(ctx->d_cmf);
+    if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* tcpt_last_error(const tcpt_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return TCPT_ERR_INVALID;
+    const std::string n(name);
+    if (n == "count_tests") ctx->opt.count_tests = value;
+    else if (n == "stage_timing") ctx->opt.stage_timing = value;
+    else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
+    else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
+    else return fail(ctx, TCPT_ERR_INVALID, "unknown option " + n);
+    return TCPT_OK;
+}
+
+int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_floats) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    if (!std_tables || std_len != 8 + 104 * 4 + 4 * 470 * 4 || std::memcmp(std_tables, "TCPTSTD1", 8) != 0) return fail(ctx, TCPT_ERR_INVALID, "set_tables: bad std_tables blob");
+    if (!rgb2spec || rgb2spec_floats != 64 + (size_t)3 * 64 * 64 * 64 * 3) return fail(ctx, TCPT_ERR_INVALID, "set_tables: bad rgb2spec table size");
+    HostTables& T = ctx->host.tables;
+    const uint8_t* p = (const uint8_t*)std_tables + 8;
+    std::memcpy(T.sobol, p, 104 * 4); p += 104 * 4;
+    const float* f = (const float*)p;
+    T.cie_x.assign(f, f + 470); T.cie_y.assign(f + 470, f + 940); T.cie_z.assign(f + 940, f + 1410); T.d65.assign(f + 1410, f + 1880);
+    T.rgb2spec.assign(rgb2spec, rgb2spec + rgb2spec_floats);
+    T.set = true;
+    // Sobol matrix 0 must be the bit-reversal identity (the device uses __brev for dimension 0) and its rows >= 32 zero
+    for (int i = 0; i < 52; ++i) if (T.sobol[i] != (i < 32 ? (0x80000000u >> i) : 0u)) return fail(ctx, TCPT_ERR_INVALID, "set_tables: Sobol matrix 0 is not the identity");
+    // host tables are usable from here on (material resolution, tcpt_rgb_to_coeffs); the device copies need the GPU
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyToSymbol(c_sobol_dim1, T.sobol + 52, 52 * 4));
+    std::vector<float> cmf(470 * 4);
+    for (int i = 0; i < 470; ++i) { cmf[4 * i] = T.cie_x[i]; cmf[4 * i + 1] = T.cie_y[i]; cmf[4 * i + 2] = T.cie_z[i]; cmf[4 * i + 3] = T.d65[i]; }
+    if (!ctx->d_cmf) CU(cudaMalloc((void**)&ctx->d_cmf, 470 * sizeof(float4)));
+    CU(cudaMemcpy(ctx->d_cmf, cmf.data(), 470 * sizeof(float4), cudaMemcpyHostToDevice));
+    if (!ctx->d_rgb2spec) CU(cudaMalloc((void**)&ctx->d_rgb2spec, rgb2spec_floats * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_rgb2spec, rgb2spec, rgb2spec_floats * sizeof(float), cudaMemcpyHostToDevice));
+    return TCPT_OK;
+}
+
+int tcpt_scene_clear(tcpt_ctx* ctx) { if (!ctx) return TCPT_ERR_INVALID; ctx->host.clear(); return TCPT_OK; }
+int tcpt_scene_add_mesh(tcpt_ctx* ctx, const float* positions, const float* normals, const float* uvs, int n_vertices, const uint32_t* indices, int n_triangles) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    int r = ctx->host.add_mesh(positions, normals, uvs, n_vertices, indices, n_triangles);
+    if (r < 0) ctx->error = ctx->host.error;
+    return r;
+}
+int tcpt_scene_add_texture(tcpt_ctx* ctx, const uint8_t* data, uint32_t width, uint32_t height, uint32_t channels) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    int r = ctx->host.add_texture(data, width, height, channels);
+    if (r < 0) ctx->error = ctx->host.error;
+    return r;
+}
+int tcpt_scene_add_material(tcpt_ctx* ctx, const tcpt_material_desc* desc) {
+    if (!ctx || !desc) return TCPT_ERR_INVALID;
+    int r = ctx->host.add_material(*desc);
+    if (r < 0) ctx->error = ctx->host.error;
+    return r;
+}
+int tcpt_scene_add_primitive(tcpt_ctx* ctx, int geometry, int material, const float local_to_world[16]) {
+    if (!ctx || !local_to_world) return TCPT_ERR_INVALID;
+    int r = ctx->host.add_primitive(geometry, material, local_to_world);
+    if (r < 0) ctx->error = ctx->host.error;
+    return r;
+}
+int tcpt_scene_add_env_light(tcpt_ctx* ctx, float intensity, const float* rgb, uint32_t width, uint32_t height, const float local_to_world[16]) {
+    if (!ctx || !local_to_world) return TCPT_ERR_INVALID;
+    int r = ctx->host.add_env_light(intensity, rgb, width, height, local_to_world);
+    if (r < 0) ctx->error = ctx->host.error;
+    return r;
+}
+
+int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
+    if (!ctx || !s) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    if (!ctx->d_cmf) return fail(ctx, TCPT_ERR_INVALID, "upload: call tcpt_set_tables first");
+    if (s->n_lights > TCPT_MAX_LIGHTS) return fail(ctx, TCPT_ERR_LIMIT, "upload: too many lights");
+    if (s->max_bvh_depth + 2 >= TCPT_TRAVERSAL_STACK) return fail(ctx, TCPT_ERR_LIMIT, "upload: BVH deeper than the traversal stack");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx->dev);
+    DeviceBuffers& db = ctx->dev;
+    DScene& v = db.view;
+    std::memset(&v, 0, sizeof v);
+    int rc;
+#define UP(expr) if ((rc = (expr)) != TCPT_OK) return rc
+    const tcpt_bvh_node* nodes; UP(upload(ctx, db, s->bvh_nodes, s->n_bvh_nodes, &nodes)); v.nodes = (const float4*)nodes;
+    const int32_t* items; UP(upload(ctx, db, s->tlas_items, (size_t)s->n_tlas_items * 2, &items)); v.tlas_items = (const int2*)items;
+    const float* tv; UP(upload(ctx, db, s->tri_verts, s->n_tri_slots * 12, &tv)); v.tri_verts = (const float4*)tv;
+    UP(upload(ctx, db, s->positions, s->n_vertices * 3, &v.positions));
+    UP(upload(ctx, db, s->normals, s->n_vertices * 3, &v.normals));
+    UP(upload(ctx, db, s->uvs, s->n_vertices * 2, &v.uvs));
+    UP(upload(ctx, db, s->indices, s->n_triangles * 3, &v.indices));
+    UP(upload(ctx, db, s->tangents, s->n_triangles * 3, &v.tangents));
+    UP(upload(ctx, db, s->geometries, s->n_geometries, &v.geometries));
+    UP(upload(ctx, db, s->primitives, s->n_primitives, &v.primitives)); v.n_primitives = s->n_primitives;
+    UP(upload(ctx, db, s->materials, s->n_materials, &v.materials));
+    const uint8_t* tex_bytes; UP(upload(ctx, db, s->texture_bytes, s->n_texture_bytes, &tex_bytes));
+    std::vector<DTexture> dt(s->n_textures);
+    for (uint32_t i = 0; i < s->n_textures; ++i) dt[i] = DTexture{tex_bytes + s->textures[i].offset, s->textures[i].width, s->textures[i].height, s->textures[i].channels, 0};
+    UP(upload(ctx, db, dt.data(), dt.size(), &v.textures));
+    UP(upload(ctx, db, s->area_list, s->n_area, &v.area_list));
+    UP(upload(ctx, db, s->area_table, s->n_area, &v.area_table));
+    for (uint32_t i = 0; i < s->n_lights; ++i) v.light_list[i] = s->light_list[i];
+    v.n_lights = s->n_lights;
+    const float* envf; UP(upload(ctx, db, s->env_floats, s->n_env_floats, &envf));
+    std::vector<DEnv> de(s->n_envs);
+    for (uint32_t i = 0; i < s->n_envs; ++i) {
+        const tcpt_flat_env& e = s->envs[i];
+        de[i] = DEnv{envf + e.data_offset, envf + e.marginal_offset, envf + e.conditional_offset, e.intensity, e.total_weight, e.width, e.height, e.integrated, e.primitive};
+    }
+    UP(upload(ctx, db, de.data(), de.size(), &v.envs)); v.n_envs = s->n_envs;
+#undef UP
+    v.cmf = ctx->d_cmf; v.z_nodes = ctx->d_rgb2spec; v.rgb2spec = ctx->d_rgb2spec + 64;
+    std::memcpy(v.xyz_to_rgb, ctx->xyz_to_rgb, sizeof v.xyz_to_rgb);
+    db.max_bvh_depth = s->max_bvh_depth;
+    db.valid = true;
+    return TCPT_OK;
+}
+
+int tcpt_scene_build(tcpt_ctx* ctx, const float cam_pos[3]) {
+    if (!ctx || !cam_pos) return TCPT_ERR_INVALID;
+    int r = ctx->host.build(cam_pos, ctx->flat);
+    if (r != TCPT_OK) { ctx->error = ctx->host.error; return r; }
+    return tcpt_upload_flat_scene(ctx, &ctx->flat.view);
+}
+
+int tcpt_render_device(tcpt_ctx* ctx, const tcpt_render_params* params, void* dev_acc, void* stream) {
+    if (!ctx || !dev_acc) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    reset_stats(ctx);
+    if (s != ctx->stream) CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, s));
+    int rc = render_into(ctx, params, (float*)dev_acc, s);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev1, s));
+    CU(cudaEventSynchronize(ctx->ev1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.render_ms = ms;
+    return fetch_stats(ctx);
+}
+
+int tcpt_finalize_device(tcpt_ctx* ctx, const void* dev_acc, uint32_t width, uint32_t height, uint32_t spp, void* dev_srgb, void* stream) {
+    if (!ctx || !dev_acc || !dev_srgb || spp == 0) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t n = width * height * 3;
+    k_finalize<<<grid_for(ctx, n, 256), 256, 0, s>>>((const float*)dev_acc, (float*)dev_srgb, n, (float)spp);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    return TCPT_OK;
+}
+
+int tcpt_render(tcpt_ctx* ctx, const tcpt_render_params* params, float* out_acc, float* out_srgb) {
+    if (!ctx || !params || (!out_acc && !out_srgb)) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)params->width * params->height * 3;
+    float* d_acc = nullptr; float* d_srgb = nullptr;
+    CU(cudaMalloc((void**)&d_acc, n * sizeof(float)));
+    cudaError_t e = cudaMemsetAsync(d_acc, 0, n * sizeof(float), ctx->stream);
+    int rc = e == cudaSuccess ? tcpt_render_device(ctx, params, d_acc, nullptr) : fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == TCPT_OK && out_acc) { e = cudaMemcpy(out_acc, d_acc, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc == TCPT_OK && out_srgb) {
+        e = cudaMalloc((void**)&d_srgb, n * sizeof(float));
+        if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
+        else {
+            rc = tcpt_finalize_device(ctx, d_acc, params->width, params->height, params->spp, d_srgb, nullptr);
+            if (rc == TCPT_OK) { e = cudaMemcpy(out_srgb, d_srgb, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+        }
+    }
+    if (d_acc) cudaFree(d_acc);
+    if (d_srgb) cudaFree(d_srgb);
+    return rc;
+}
+
+int tcpt_get_stats(const tcpt_ctx* ctx, tcpt_stats* out) {
+    if (!ctx || !out) return TCPT_ERR_INVALID;
+    *out = ctx->stats;
+    return TCPT_OK;
+}
+
+int tcpt_trace_device(tcpt_ctx* ctx, const void* dev_rays, int n, int any_hit, void* dev_hits, void* stream) {
+    if (!ctx || !dev_rays || !dev_hits || n < 0) return TCPT_ERR_INVALID;
+    if (!ctx->dev.valid) return fail(ctx, TCPT_ERR_INVALID, "trace: no scene uploaded");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (n == 0) return TCPT_OK;
+    // dev_rays: n x {o.xyz, tmax} followed by n x {d.xyz, -}; dev_hits: n x float4 {t,b0,b1,b2} followed by n x uint2 {prim, tri}
+    const float4* q_o = (const float4*)dev_rays; const float4* q_d = q_o + n;
+    float4* h0 = (float4*)dev_hits; uint2* h1 = (uint2*)(h0 + n);
+    const int grid = grid_for(ctx, (uint64_t)n, 128);
+    if (ctx->opt.count_tests) k_trace_rays<true><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, ctx->d_stats);
+    else k_trace_rays<false><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, nullptr);
+    CU(cudaGetLastError());
+    return TCPT_OK;
+}
+
+int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* out_hit) {
+    if (!ctx || !rays || !out_hit || n < 0) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    if (!ctx->dev.valid) return fail(ctx, TCPT_ERR_INVALID, "trace: no scene uploaded");
+    if (n == 0) return TCPT_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float> packed((size_t)n * 8);
+    for (int i = 0; i < n; ++i) {
+        const float* r = rays + 7 * (size_t)i;
+        float* o = &packed[4 * (size_t)i]; float* d = &packed[4 * ((size_t)n + i)];
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[6]; d[0] = r[3]; d[1] = r[4]; d[2] = r[5]; d[3] = 0.0f;
+    }
+    void* d_rays = nullptr; void* d_hits = nullptr;
+    CU(cudaMalloc(&d_rays, packed.size() * 4));
+    cudaError_t e = cudaMalloc(&d_hits, (size_t)n * 24);
+    if (e != cudaSuccess) { cudaFree(d_rays); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    reset_stats(ctx);
+    cudaMemcpyAsync(d_rays, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = tcpt_trace_device(ctx, d_rays, n, any_hit, d_hits, nullptr);
+    std::vector<uint8_t> hits((size_t)n * 24);
+    if (rc == TCPT_OK) { e = cudaMemcpyAsync(hits.data(), d_hits, hits.size(), cudaMemcpyDeviceToHost, ctx->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaFree(d_rays); cudaFree(d_hits);
+    if (rc) return rc;
+    const float* h0 = (const float*)hits.data(); const uint32_t* h1 = (const uint32_t*)(hits.data() + (size_t)n * 16);
+    for (int i = 0; i < n; ++i) {
+        int32_t* o = out_hit + 6 * (size_t)i;
+        const int32_t prim = (int32_t)h1[2 * (size_t)i];
+        if (any_hit) { o[0] = prim >= 0 ? 1 : 0; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
+        else if (prim < 0) { o[0] = -1; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
+        else { o[0] = prim; o[1] = (int32_t)h1[2 * (size_t)i + 1]; std::memcpy(&o[2], &h0[4 * (size_t)i], 16); }
+    }
+    return fetch_stats(ctx);
+}
+
+int tcpt_sampler_stream(tcpt_ctx* ctx, int sampler, uint32_t spp, uint32_t width, uint32_t height, uint32_t seed, uint32_t px, uint32_t py,
+                        uint32_t sample_index, const int32_t* kinds, int n, float* out) {
+    if (!ctx || !kinds || !out || n <= 0) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    if (!ctx->d_cmf) return fail(ctx, TCPT_ERR_INVALID, "sampler_stream: call tcpt_set_tables first");
+    CU(cudaSetDevice(ctx->device));
+    DRender R; std::memset(&R, 0, sizeof R);
+    R.width = width; R.height = height; R.spp = spp; R.seed = seed; R.sampler = sampler;
+    R.log2_spp = log2_int(spp);
+    R.n_base4_digits = log2_int(round_up_pow2(width > height ? width : height)) + (R.log2_spp + 1) / 2;
+    int total = 0;
+    for (int i = 0; i < n; ++i) total += kinds[i] == 1 ? 1 : 2;
+    int32_t* d_k = nullptr; float* d_o = nullptr;
+    CU(cudaMalloc((void**)&d_k, n * 4));
+    cudaError_t e = cudaMalloc((void**)&d_o, total * 4);
+    if (e != cudaSuccess) { cudaFree(d_k); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_k, kinds, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    k_sampler_stream<<<1, 32, 0, ctx->stream>>>(R, px, py, sample_index, d_k, n, d_o);
+    e = cudaMemcpyAsync(out, d_o, total * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_k); cudaFree(d_o);
+    if (e != cudaSuccess) return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
+    return total;
+}
+
+int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uint32_t* pixels_xy, const uint32_t* sample_indices, int n, float* out_rgb) {
+    if (!ctx || !params || !pixels_xy || !sample_indices || !out_rgb || n <= 0) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    DRender R; DCamera cam;
+    int rc = make_render(ctx, params, R, cam);
+    if (rc) return rc;
+    rc = ensure_state(ctx, (uint32_t)n);
+    if (rc) return rc;
+    uint32_t* d_xy = nullptr; uint32_t* d_s = nullptr;
+    CU(cudaMalloc((void**)&d_xy, (size_t)n * 8));
+    cudaError_t e = cudaMalloc((void**)&d_s, (size_t)n * 4);
+    if (e != cudaSuccess) { cudaFree(d_xy); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_xy, pixels_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_s, sample_indices, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    reset_stats(ctx);
+    R.n_pix = (uint32_t)n; R.s_count = 1;
+    PathList L{d_xy, d_s};
+    rc = run_pass(ctx, R, cam, L, (uint32_t)n, nullptr, ctx->stream);
+    std::vector<float> rgb((size_t)n * 4);
+    if (rc == TCPT_OK) {
+        e = cudaMemcpyAsync(rgb.data(), ctx->st.rgb, rgb.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_xy); cudaFree(d_s);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) { out_rgb[3 * (size_t)i] = rgb[4 * (size_t)i]; out_rgb[3 * (size_t)i + 1] = rgb[4 * (size_t)i + 1]; out_rgb[3 * (size_t)i + 2] = rgb[4 * (size_t)i + 2]; }
+    return fetch_stats(ctx);
+}
+
+int tcpt_get_bvh(tcpt_ctx* ctx, int which, uint32_t* out, int max_nodes) {
+    if (!ctx || (!out && max_nodes > 0)) return TCPT_ERR_INVALID;
+    return ctx->host.dump_bvh(which, out, max_nodes);
+}
+
+int tcpt_build_bvh_boxes(const float* boxes, int n, uint32_t* out, int max_nodes) {
+    if (!boxes || n <= 0) return TCPT_ERR_INVALID;
+    std::vector<Box> ib(n);
+    for (int i = 0; i < n; ++i) ib[i] = Box{{boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]}, {boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]}};
+    BuiltBvh b = SahBuilder(ib).build();
+    return HostScene::dump_built(b, out, max_nodes);
+}
+
+int tcpt_rgb_to_coeffs(tcpt_ctx* ctx, const float rgb[3], int gamma_encoded, float coeffs[3], int32_t index[4]) {
+    if (!ctx || !rgb || !coeffs) return TCPT_ERR_INVALID;
+    return ctx->host.rgb_to_coeffs(rgb, gamma_encoded != 0, coeffs, index) ? TCPT_OK : fail(ctx, TCPT_ERR_INVALID, "rgb_to_coeffs: tables not set or component > 1");
+}
+
+int tcpt_get_mesh_tangents(tcpt_ctx* ctx, int geometry, float* out, int max_triangles) {
+    if (!ctx || geometry < 0 || geometry >= (int)ctx->host.meshes.size()) return TCPT_ERR_INVALID;
+    const HostMesh& m = ctx->host.meshes[geometry];
+    const int n = (int)m.tangents.size();
+    for (int i = 0; i < n && i < max_triangles; ++i) { out[3 * i] = m.tangents[i].x; out[3 * i + 1] = m.tangents[i].y; out[3 * i + 2] = m.tangents[i].z; }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+"""The config scenes of BASELINE.json, restated from the reference's scene builders with stand-in assets.
+
+Materials, transforms, lights and cameras are the reference's (renderer/src/scene/scene_{3,10,17,19}.rs); every mesh,
+texture and HDRI it loads is a git-LFS stub in the checkout, so geometry and images come from the
+deterministic generators in assets.py (Cornell walls = axis-aligned quads spanning x,z in [-2.5,2.5], y in [0,5]).
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from . import assets
+from .scene import (ColorSrgb, ColorSrgbLinear, ConstantSpectrum, CreatePrimitiveDesc, EmissiveMaterial, FloatParameter, FloatTexture,
+                    LambertMaterial, NormalParameter, NormalTexture, PlasticMaterial, RgbAlbedoSpectrum, RgbTexture, SimpleClearcoatPbrMaterial,
+                    SimplePbrMaterial, SpectrumParameter, SpectrumType, Transform, presets)
+
+GP = CreatePrimitiveDesc.GeometryPrimitive
+
+
+@functools.lru_cache(maxsize=None)
+def _asset(name: str):
+    if name == "bunny":
+        return assets.blob(center=(-0.8, 1.0, 0.4), radius=1.0, nu=50, nv=50)
+    if name == "dragon":
+        return assets.knot(scale=0.12, nu=250, nv=40)
+    if name == "box":
+        return assets.box((0.5, 0.0, -1.7), (1.9, 2.8, -0.3), rot_y_deg=-18.0)
+    if name == "light":
+        return assets.box((-0.75, 4.90, -0.75), (0.75, 4.99, 0.75))
+    h = 2.5
+    if name == "hidari":   # left wall, faces +x
+        return assets.quad((-h, 0, h), (-h, 0, -h), (-h, 5, -h), (-h, 5, h), (1, 0, 0))
+    if name == "migi":     # right wall, faces -x
+        return assets.quad((h, 0, -h), (h, 0, h), (h, 5, h), (h, 5, -h), (-1, 0, 0))
+    if name == "yuka":     # floor, faces +y
+        return assets.quad((-h, 0, h), (h, 0, h), (h, 0, -h), (-h, 0, -h), (0, 1, 0))
+    if name == "oku":      # back wall, faces +z
+        return assets.quad((-h, 0, -h), (h, 0, -h), (h, 5, -h), (-h, 5, -h), (0, 0, 1))
+    if name == "tenjou":   # ceiling, faces -y
+        return assets.quad((-h, 5, -h), (h, 5, -h), (h, 5, h), (-h, 5, h), (0, -1, 0))
+    if name == "bunny_basecolor":
+        return assets.base_color_texture(1024, seed=0)
+    if name == "bunny_normal":
+        return assets.normal_texture(1024, seed=10)
+    if name == "dragon_basecolor":
+        return assets.base_color_texture(1024, seed=3)
+    if name == "dragon_normal":
+        return assets.normal_texture(1024, seed=13)
+    if name == "dragon_metallic":
+        return assets.gray_texture(1024, seed=20, threshold=0.5)
+    if name == "dragon_roughness":
+        return assets.gray_texture(1024, seed=21, lo=0.15, hi=0.85)
+    if name == "sky":
+        return assets.sky_hdri(1024, 512)
+    raise KeyError(name)
+
+
+def _grey(v=0.8):
+    return SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(v, v, v)))
+
+
+def _lambert(r, g, b):
+    return LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(r, g, b))), NormalParameter.none())
+
+
+def _cornell_rest(scene, with_box=True):
+    """box, hidari, migi, yuka, oku, tenjou, light: identical in scenes 3, 10 and 17 (scene_3.rs:33-108)."""
+    if with_box:
+        scene.create_primitive(GP(scene.load_obj(_asset("box")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("hidari")), _lambert(0.9, 0.0, 0.0), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("migi")), _lambert(0.0, 0.9, 0.0), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("yuka")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("oku")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("tenjou")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("light")),
+                              EmissiveMaterial.new(SpectrumParameter.constant(presets.cie_illum_d6500()), FloatParameter.constant(10.0)), Transform.identity()))
+
+
+def _cornell_camera(camera):
+    d = np.array([0.0, -0.9, -3.2], dtype=np.float32)
+    camera.set_look_to((0.0, 3.15221, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
+def load_scene_3(scene, camera):
+    """Cornell box with a textured, normal-mapped Lambert bunny (scene_3.rs:13-115)."""
+    tex = RgbTexture.load_srgb(_asset("bunny_basecolor"))
+    nrm = NormalTexture.load(_asset("bunny_normal"), False)
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")),
+                              LambertMaterial.new(SpectrumParameter.texture(tex, SpectrumType.Albedo), NormalParameter.texture(nrm)), Transform.identity()))
+    _cornell_rest(scene)
+    _cornell_camera(camera)
+
+
+def load_scene_10(scene, camera):
+    """Same box; the bunny is thin-film plastic, eta 1.8, roughness 0 (scene_10.rs:13-112)."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")),
+                              PlasticMaterial.new(1.8, SpectrumParameter.Constant(ConstantSpectrum(1.0)), NormalParameter.none(), True, FloatParameter.constant(0.0)),
+                              Transform.identity()))
+    _cornell_rest(scene)
+    d = np.array([0.0, -1.0, -3.0], dtype=np.float32)
+    camera.set_look_to((0.0, 3.5, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
+def _clearcoat(coat_roughness):
+    tint = SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(0.7, 0.8, 1.0)))
+    return SimpleClearcoatPbrMaterial.new(_grey(0.8), FloatParameter.constant(1.0), FloatParameter.constant(0.7), NormalParameter.none(), FloatParameter.constant(1.5),
+                                          FloatParameter.constant(1.5), FloatParameter.constant(coat_roughness), tint, FloatParameter.constant(0.8))
+
+
+def load_scene_17(scene, camera, coat=True):
+    """Clearcoat-PBR dragon in the Cornell box (scene_17.rs:13-155).  coat=False swaps in the uncoated SimplePbr substrate
+    (BASELINE.json config 3 'no-coat'; the reference has no such toggle, only pictures/scene17.no-coat.mis.png)."""
+    mat = _clearcoat(0.75) if coat else SimplePbrMaterial.new(_grey(0.8), FloatParameter.constant(1.0), FloatParameter.constant(0.7), NormalParameter.none(), FloatParameter.constant(1.5))
+    xf = Transform.identity().rotate_y(120.0).scale((2.5, 2.5, 2.5)).translate((0.0, 0.0, 0.5))
+    scene.create_primitive(GP(scene.load_obj(_asset("dragon")), mat, xf))
+    _cornell_rest(scene)
+    _cornell_camera(camera)
+
+
+def load_scene_19(scene, camera):
+    """Floor + three instances of one dragon mesh (textured SimplePbr, smooth clearcoat, blue plastic) under an environment light (scene_19.rs:17-153)."""
+    scene.create_primitive(GP(scene.load_obj(_asset("yuka")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    dragon = scene.load_obj(_asset("dragon"))
+    pbr = SimplePbrMaterial.new(SpectrumParameter.texture(RgbTexture.load_srgb(_asset("dragon_basecolor")), SpectrumType.Albedo),
+                                FloatParameter.texture(FloatTexture.load(_asset("dragon_metallic"), False)),
+                                FloatParameter.texture(FloatTexture.load(_asset("dragon_roughness"), False)),
+                                NormalParameter.texture(NormalTexture.load(_asset("dragon_normal"), False)), FloatParameter.constant(1.5))
+    scene.create_primitive(GP(dragon, pbr, Transform.identity()))
+    scene.create_primitive(GP(dragon, _clearcoat(0.01), Transform.identity().translate((0.5, 0.0, 0.5))))
+    plastic = PlasticMaterial.new(1.5, SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(0.4, 0.9, 1.0))), NormalParameter.none(), False, FloatParameter.constant(0.0))
+    scene.create_primitive(GP(dragon, plastic, Transform.identity().translate((-0.5, 0.0, -0.5))))
+    scene.create_primitive(CreatePrimitiveDesc.EnvironmentLightPrimitive(1.0, _asset("sky"), Transform.identity()))
+    d = np.array([1.5, -0.4, -2.5], dtype=np.float32)
+    camera.set_look_to((-1.5, 0.8, 2.5), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
+def load_soup(scene, camera, n_triangles: int, seed: int = 42):
+    """BASELINE.json config 5: synthetic triangle soup lit by a small emissive quad; camera at (0,0,3) looking at the origin."""
+    scene.create_primitive(GP(scene.load_obj(assets.triangle_soup(n_triangles, seed)), _lambert(0.7, 0.7, 0.7), Transform.identity()))
+    light = assets.quad((-0.5, 1.6, -0.5), (0.5, 1.6, -0.5), (0.5, 1.6, 0.5), (-0.5, 1.6, 0.5), (0, -1, 0))
+    scene.create_primitive(GP(scene.load_obj(light), EmissiveMaterial.new(SpectrumParameter.constant(presets.cie_illum_d6500()), FloatParameter.constant(10.0)), Transform.identity()))
+    camera.set_look_to((0.0, 0.0, 3.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
+
+
+SCENES = {3: load_scene_3, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
+
+
+def load_scene(scene_id, scene, camera, **kw):
+    """The `match args.scene` of renderer/src/main.rs:70-92 for the scenes in scope."""
+    if scene_id not in SCENES:
+        raise ValueError(f"scene {scene_id} is outside the B200 hot-path scope (available: {sorted(SCENES)})")
+    SCENES[scene_id](scene, camera, **kw)
