@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py — throughput of the path-integration hot path on B200 (Mrays/s, with Mpaths/s beside it).
+
+Workload (BASELINE.json configs[3], the configuration the metric's 1/2/4/8-GPU numbers are quoted on): scene 19 (floor + three
+dragon instances: textured SimplePbr, smooth clearcoat, plastic; environment light) at 3840x2160, MIS integrator, Z-Sobol
+sampler, max_depth 16, as a 4096-spp frame.  One STEP = one pass of the hot path over one batch = `--spp-per-step` sample
+indices of every pixel of the frame per GPU (default 4 -> 33.2 M paths per GPU per step), including the film kernel and, at
+N > 1, the NCCL reduce of the film accumulators.  Ranks render disjoint sample-index ranges of the same frame (spp-pass
+sharding), so per-GPU work is fixed as N grows: "scaling": "weak".  configs[0..2] are parity-test cases (tests/), not bench lines.
+
+  value    whole-job Mrays/s, film accumulators resident in HBM (tcpt_render_device), CUDA events on the launching stream
+  e2e      the same metric through the reference-facing call RendererImage.render() -> tcpt_render() with HOST buffers:
+           per step the render parameters go host->device and the tone-mapped sRGB frame comes device->host
+  roofline dominant kernel k_trace_closest; see DESIGN.md "Measurement" for the byte/flop definitions
+  cpu_baseline / --impl reference: the CPU restatement of the reference algorithm (oracle, kind "port": the Rust reference
+           cannot be compiled in this image) on all host threads, on a bounded window of the same frame
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "scene19_4k": dict(scene=19, width=3840, height=2160, frame_spp=4096, integrator="mis", sampler="sobol"),
+    "scene17_1080p": dict(scene=17, width=1920, height=1080, frame_spp=1024, integrator="mis", sampler="sobol"),
+    "scene3_test": dict(scene=3, width=200, height=150, frame_spp=512, integrator="mis", sampler="sobol"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="scene19_4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--max-slots", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- shared setup
+def build_scene(wl, device, require_gpu=True):
+    import toy_cpu_pathtracing_b200 as tp
+    from toy_cpu_pathtracing_b200 import scenes
+    scene = tp.Scene(device=device, require_gpu=require_gpu)
+    cam = tp.Camera(45.0, wl["width"], wl["height"])
+    scenes.load_scene(wl["scene"], scene, cam)
+    return tp, scene, cam
+
+
+def cpu_window(wl, seconds, paths_per_second_guess=2.0e5):
+    """A centred pixel window of the SAME frame sized for about `seconds` of CPU work (4 sample indices per pixel, more when the
+    whole frame is too small to fill the time)."""
+    want_paths = max(2000.0, seconds * paths_per_second_guess)
+    spp = 4
+    side = int(max(8, min(wl["height"], wl["width"], (want_paths / spp) ** 0.5)))
+    if side * side * spp < 0.7 * want_paths:
+        spp = int(min(wl["frame_spp"], max(4, want_paths / (side * side))))
+    x0, y0 = (wl["width"] - side) // 2, (wl["height"] - side) // 2
+    return (x0, y0, x0 + side, y0 + side), spp
+
+
+def run_cpu(wl, scene_desc, cam, seconds, threads=0):
+    """The reference algorithm on the host cores (oracle port, reference-faithful mode: exhaustive traversal without t-shrinking,
+    per-call instance-matrix inverses), on a bounded window of the bench frame.  Returns (Mrays/s, Mpaths/s, info)."""
+    from toy_cpu_pathtracing_b200 import capi
+    from oracle import oracle
+    std, tab = capi.load_tables()
+    osc = oracle.scene_from_description(scene_desc, cam.position, std, tab, faithful=True, literal_build=False)
+    # calibrate on a small window, then size the real sample
+    win, spp = cpu_window(wl, 0.5)
+    p = osc.params(wl["width"], wl["height"], wl["frame_spp"], wl["integrator"], wl["sampler"], cam, threads=threads, window=win)
+    p.spp = wl["frame_spp"]
+    _, _, st = _oracle_window(osc, p, spp)
+    rate = st["paths"] / max(st["seconds"], 1e-6)
+    win, spp = cpu_window(wl, seconds, rate)
+    p = osc.params(wl["width"], wl["height"], wl["frame_spp"], wl["integrator"], wl["sampler"], cam, threads=threads, window=win)
+    _, _, st = _oracle_window(osc, p, spp)
+    rays = st["closest_rays"] + st["shadow_rays"]
+    ncores = threads if threads > 0 else (os.cpu_count() or 1)
+    info = {"cores": ncores, "sample": f"{win[2] - win[0]}x{win[3] - win[1]} px window of the {wl['width']}x{wl['height']} frame, sample indices 0..{spp - 1} of {wl['frame_spp']}, "
+                                       f"{st['paths']} paths in {st['seconds']:.2f} s", "seconds": st["seconds"], "paths": st["paths"], "rays": rays}
+    return rays / st["seconds"] / 1e6, st["paths"] / st["seconds"] / 1e6, info
+
+
+def _oracle_window(osc, p, spp_used):
+    """Render sample indices 0..spp_used-1 of the frame's Sobol sequence (the sampler is configured for the full frame spp)."""
+    # the oracle's render loop runs `spp` samples per pixel; the Sobol sampler must still see the frame's spp: orc_render uses
+    # p.spp for both, so a window render at reduced spp uses sampler parameters of the reduced spp.  Throughput is independent
+    # of which low-discrepancy points are drawn, so the sample renders `spp_used` samples with the sampler sized for them.
+    p.spp = spp_used
+    return osc.render(p)
+
+
+# ---------------------------------------------------------------- reference arm
+def main_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    _, scene, cam = build_scene(wl, 0, require_gpu=False)
+    scene.desc  # description only; nothing is built on a GPU in this arm
+    vals, paths = [], []
+    info = None
+    per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        mr, mp, info = run_cpu(wl, scene.desc, cam, per_step)
+        if i >= args.warmup:
+            vals.append((info["rays"], info["seconds"]))
+            paths.append(info["paths"])
+    tot_r = sum(v[0] for v in vals); tot_s = sum(v[1] for v in vals)
+    value = tot_r / tot_s / 1e6
+    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, wl), "mpaths_per_s": sum(paths) / tot_s / 1e6,
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, wl):
+    return {"workload": f"scene{wl['scene']} {wl['width']}x{wl['height']} {wl['integrator']}+{wl['sampler']} max_depth 16, {wl['frame_spp']}-spp frame, "
+                        f"{args.spp_per_step} sample indices of every pixel per GPU per step (BASELINE.json configs[3])",
+            "paths_per_gpu_per_step": wl["width"] * wl["height"] * args.spp_per_step, "sharding": "spp-pass", "collective": "one NCCL reduce of the film accumulators per step",
+            "cache": "working set (path state + ray queues, about 1 GB per GPU) exceeds the 126 MB L2; no explicit flush", "assets": "procedural stand-ins (reference assets are LFS stubs)"}
+
+
+# ---------------------------------------------------------------- GPU arm
+def main_gpu(args, wl):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from toy_cpu_pathtracing_b200 import capi
+    from toy_cpu_pathtracing_b200.multi_gpu import reduce_film, shard_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    tp, scene, cam = build_scene(wl, local)
+    t0 = time.time(); scene.build(cam); build_s = time.time() - t0
+    ctx = scene.ctx
+    W, H, S = wl["width"], wl["height"], args.spp_per_step
+    renderer = tp.RENDERERS[wl["integrator"]](tp.RendererArgs((W, H), wl["frame_spp"], scene, cam, seed=0))
+    image = tp.RendererImage(W, H, renderer)
+    acc = torch.zeros((H, W, 3), dtype=torch.float32, device=f"cuda:{local}")
+    frame = torch.zeros_like(acc) if rank == 0 else None
+    stream = torch.cuda.current_stream()
+
+    def step(k, timing=False):
+        # step k of the job: `world * S` fresh sample indices of the frame, rank r takes its S of them (spp-pass sharding)
+        lo = (k * world * S) % wl["frame_spp"]
+        sh = shard_plan(rank, world, "spp", wl["frame_spp"], lo, min(lo + world * S, wl["frame_spp"]))
+        p = renderer.params(wl["sampler"], max_slots=args.max_slots, **sh.as_kwargs())
+        acc.zero_()
+        ctx.check(ctx.lib.tcpt_render_device(ctx.handle, C.byref(p), C.c_void_p(acc.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        st = ctx.stats()
+        reduce_film(acc, dst=0)
+        if rank == 0:
+            frame.add_(acc)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    ctx.set_option("stage_timing", 1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = {"rays": 0, "paths": 0, "closest": 0, "shadow": 0, "launches": 0, "closest_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "gen_ms": 0.0, "film_ms": 0.0, "passes": 0}
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for k in range(args.steps):
+            st = step(args.warmup + k)
+            tot["rays"] += st["closest_rays"] + st["shadow_rays"]; tot["paths"] += st["paths"]; tot["closest"] += st["closest_rays"]; tot["shadow"] += st["shadow_rays"]
+            tot["launches"] += st["kernel_launches"]; tot["closest_ms"] += st["trace_closest_ms"]; tot["shade_ms"] += st["shade_ms"]; tot["shadow_ms"] += st["trace_shadow_ms"]
+            tot["gen_ms"] += st["generate_ms"]; tot["film_ms"] += st["film_ms"]; tot["passes"] += st["passes"]
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    ctx.set_option("stage_timing", 0)
+    t = torch.tensor([ms, float(tot["rays"]), float(tot["paths"]), float(tot["launches"])], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_max, rays_all, paths_all, launches_all = tmax[0].item(), tsum[1].item(), tsum[2].item(), tsum[3].item()
+    else:
+        ms_max, rays_all, paths_all, launches_all = ms, float(tot["rays"]), float(tot["paths"]), float(tot["launches"])
+    value = rays_all / (ms_max * 1e-3) / 1e6
+
+    # ---- e2e through the reference-facing API with host buffers (every rank renders its share; rank 0 reports the sum / max time)
+    pix = np.zeros((H, W, 3), dtype=np.float32)
+    def e2e_step(k):
+        lo = (k * world * S) % wl["frame_spp"]
+        sh = shard_plan(rank, world, "spp", wl["frame_spp"], lo, min(lo + world * S, wl["frame_spp"]))
+        p = renderer.params(wl["sampler"], max_slots=args.max_slots, **sh.as_kwargs())
+        ctx.check(ctx.lib.tcpt_render(ctx.handle, C.byref(p), None, capi.as_ptr(pix, C.c_float)))
+        st = ctx.stats()
+        return st["closest_rays"] + st["shadow_rays"]
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter(); e2e_rays = 0
+    n_e2e = max(2, min(args.steps, 4))
+    for k in range(n_e2e):
+        e2e_rays += e2e_step(args.warmup + k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_rays = tm[0].item(), ts[1].item()
+    e2e_value = e2e_rays / e2e_s / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_trace_closest): one extra counted step OUTSIDE the timed region gives B and T per ray
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    ctx.set_option("count_tests", 1)
+    p = renderer.params(wl["sampler"], max_slots=args.max_slots, spp_begin=0, spp_end=1)
+    acc.zero_()
+    ctx.check(ctx.lib.tcpt_render_device(ctx.handle, C.byref(p), C.c_void_p(acc.data_ptr()), C.c_void_p(stream.cuda_stream)))
+    cs = ctx.stats()
+    ctx.set_option("count_tests", 0)
+    rays_c = max(1, cs["closest_rays"] + cs["shadow_rays"])
+    box_per_ray, tri_per_ray = cs["box_tests"] / rays_c, cs["tri_tests"] / rays_c
+    n_closest_launches = max(1, tot["passes"] * 17)
+    closest_s = tot["closest_ms"] * 1e-3
+    bytes_per_ray = 48.0  # 32 B ray read + 16 B hit write (compulsory wavefront traffic; the BVH is L2 resident)
+    achieved = bytes_per_ray * tot["closest"] / closest_s / 1e9 if closest_s > 0 else 0.0
+    clk_s = clk.summary()
+    sm_mhz = clk_s["sm_mhz"] or 1965
+    flops_per_ray = 18.0 * box_per_ray + 64.0 * tri_per_ray + 60.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    trace_s = (tot["closest_ms"] + tot["shadow_ms"]) * 1e-3
+    fp32_ach = flops_per_ray * tot["rays"] / trace_s / 1e12 if trace_s > 0 else 0.0
+    stage_sum = tot["closest_ms"] + tot["shade_ms"] + tot["shadow_ms"] + tot["gen_ms"] + tot["film_ms"]
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl),
+        "mpaths_per_s": paths_all / (ms_max * 1e-3) / 1e6, "rays_per_path": rays_all / max(1.0, paths_all),
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.RenderParams), "d2h_bytes_per_step": int(pix.nbytes), "steps": n_e2e,
+                "call": "RendererImage.render -> tcpt_render(params, host sRGB frame out)"},
+        "gpu_launches": int(launches_all),
+        "clocks": clk_s,
+        "roofline": {"kernel": "k_trace_closest", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "rays_per_launch": tot["closest"] / n_closest_launches,
+                     "avg_launch_ms": tot["closest_ms"] / n_closest_launches, "share_of_step": tot["closest_ms"] / stage_sum if stage_sum else None,
+                     "note": "BVH+textures are L2 resident: the path is FP32-issue/latency bound, see roofline_fp32"},
+        "roofline_fp32": {"kernels": "k_trace_closest + k_trace_shadow", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
+                          "flops_per_ray": flops_per_ray, "box_tests_per_ray": box_per_ray, "tri_tests_per_ray": tri_per_ray, "sm_mhz": sm_mhz,
+                          "definition": "18*B + 64*T + 60 flops per ray (SURVEY.md 8d); peak = 148 SM x 128 lanes x 2 x f_SM"},
+        "stage_ms_per_step": {k: tot[k] / args.steps for k in ("gen_ms", "closest_ms", "shade_ms", "shadow_ms", "film_ms")},
+        "scene_build_s": build_s,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            mr, mp, info = run_cpu(wl, scene.desc, cam, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": info["cores"], "kind": "port", "sample": info["sample"], "mpaths_per_s": mp}
+        except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return main_reference(args, wl)
+    return main_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,81 @@
+"""Size-independent properties of the GPU path at the configs' full sizes, plus the reference's own cross-integrator test."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_run_to_run_bitwise_reproducible(bundle_factory):
+    b = bundle_factory(3, 200, 150)
+    a = b.image("mis", 64).render("sobol").accumulators.copy()
+    c = b.image("mis", 64).render("sobol").accumulators.copy()
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
+def test_pass_tiling_does_not_change_the_film(bundle_factory):
+    """The film kernel adds each pixel's samples in sample order, so the slot budget (how many passes a frame takes) must not
+    change a single bit."""
+    b = bundle_factory(3, 200, 150)
+    full = b.image("mis", 64).render("sobol").accumulators.copy()
+    tiled = b.image("mis", 64).render("sobol", max_slots=50000).accumulators.copy()   # 30 000 px -> 1 sample per pass, 64 passes
+    tiny = b.image("mis", 64).render("sobol", max_slots=7777).accumulators.copy()     # pixel chunks smaller than the frame
+    assert np.array_equal(full.view(np.uint32), tiled.view(np.uint32))
+    assert np.array_equal(full.view(np.uint32), tiny.view(np.uint32))
+
+
+def test_row_shards_sum_bitwise_to_the_full_frame(bundle_factory):
+    """Tile (row-interleaved) sharding: each pixel is rendered entirely by one shard; the others hold exact zeros."""
+    b = bundle_factory(10, 200, 150)
+    full = b.image("nee", 32).render("sobol").accumulators.copy()
+    for world in (2, 3, 8):
+        parts = [b.image("nee", 32).render("sobol", row_offset=r, row_stride=world).accumulators.copy() for r in range(world)]
+        for r, p in enumerate(parts):
+            mask = np.ones(150, bool); mask[r::world] = False
+            assert not p[mask].any()
+        assert np.array_equal(sum(parts).view(np.uint32), full.view(np.uint32))
+
+
+def test_spp_shards_sum_to_the_full_frame(bundle_factory):
+    """Sample-range sharding: the same samples, per-pixel sums re-associated across shards."""
+    b = bundle_factory(3, 200, 150)
+    full = b.image("mis", 64).render("sobol").accumulators
+    parts = sum(b.image("mis", 64).render("sobol", spp_begin=s, spp_end=s + 16).accumulators.astype(np.float64) for s in range(0, 64, 16))
+    assert np.abs(parts - full).max() <= 1e-4 * max(1.0, np.abs(full).max())
+
+
+def test_full_size_config1_counts_and_energy(bundle_factory):
+    """BASELINE.json configs[0] at full size (scene 3, MIS + Sobol, 200x150x512): 15.36 M paths, every one accounted for, a
+    finite film, and the duplicated Sobol pairs of odd log2(spp) (Appendix A q15-i) visible as pairwise-equal path samples."""
+    b = bundle_factory(3, 200, 150)
+    img = b.image("mis", 512).render("sobol")
+    assert img.stats["paths"] == 200 * 150 * 512
+    assert img.stats["closest_rays"] > img.stats["paths"] and img.stats["shadow_rays"] > 0
+    assert np.isfinite(img.accumulators).all() and (img.pixels >= 0).all() and (img.pixels <= 1).all()
+    xy = np.array([[50, 60]] * 8, dtype=np.uint32)
+    si = np.array([0, 1, 2, 3, 100, 101, 510, 511], dtype=np.uint32)
+    s = b.image("mis", 512).path_samples("sobol", xy, si)
+    assert np.array_equal(s[0::2], s[1::2])
+
+
+def linearise_gamma22(img):
+    return np.power(np.clip(img, 0, 1).astype(np.float64), 2.2)
+
+
+def median3(img):
+    pad = np.pad(img, ((1, 1), (1, 1), (0, 0)), mode="edge")
+    stack = np.stack([pad[dy:dy + img.shape[0], dx:dx + img.shape[1]] for dy in range(3) for dx in range(3)], 0)
+    return np.median(stack, 0)
+
+
+@pytest.mark.parametrize("scene_id", [3])
+def test_cross_integrator_consistency_like_the_reference(bundle_factory, scene_id):
+    """renderer/tests/renderer_consistency_test.rs:319-353: pt vs nee and pt vs mis, random sampler, 2048 spp, 200x150, u8
+    images, 3x3 median, RMSE in gamma-2.2-linearised space <= 0.013."""
+    b = bundle_factory(scene_id, 200, 150)
+    imgs = {}
+    for integ in ("pt", "nee", "mis"):
+        u8 = b.image(integ, 2048).render("random").to_u8()
+        imgs[integ] = linearise_gamma22(median3(u8.astype(np.float64)) / 255.0)
+    for other in ("nee", "mis"):
+        rmse = np.sqrt(np.mean((imgs["pt"] - imgs[other]) ** 2))
+        assert rmse <= 0.013, f"pt vs {other}: RMSE {rmse:.4f}"

@@ -189,10 +189,18 @@ struct DSampler {
     }
 
     __device__ __forceinline__ static uint32_t perm_digit(uint32_t p, uint32_t digit) {
-        // rows of PERMUTATIONS (z_sobol_sampler.rs:102-127), digit d stored at bits [2d, 2d+2)
-        const uint32_t T[24] = {0xE4, 0xB4, 0xD8, 0x78, 0x6C, 0x9C, 0xE1, 0xB1, 0xC9, 0x39, 0x2D, 0x8D,
-                                0xC6, 0x36, 0xD2, 0x72, 0x4E, 0x1E, 0x27, 0x87, 0x1B, 0x4B, 0x63, 0x93};
-        return (T[p] >> (2u * digit)) & 3u;
+        // rows of PERMUTATIONS (z_sobol_sampler.rs:102-127): one byte per row, digit d stored at bits [2d, 2d+2); four rows per
+        // word, selected with predicated moves so the table lives in registers (a local array would be a divergent LDC/LDL)
+        const uint32_t w0 = 0x78D8B4E4u, w1 = 0xB1E19C6Cu, w2 = 0x8D2D39C9u, w3 = 0x72D236C6u, w4 = 0x87271E4Eu, w5 = 0x93634B1Bu;
+        const uint32_t q = p >> 2;
+        uint32_t w = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : (q == 3 ? w3 : (q == 4 ? w4 : w5))));
+        return (w >> (8u * (p & 3u) + 2u * digit)) & 3u;
+    }
+    // (v >> 24) % 24 of a 64-bit hash with 32-bit arithmetic: v' = hi * 2^32 + lo with hi < 2^8 and 2^32 mod 24 = 16
+    __device__ __forceinline__ static uint32_t perm_index(uint64_t mixed) {
+        const uint64_t v = mixed >> 24;
+        const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+        return (hi * 16u + lo % 24u) % 24u;
     }
     // ZSobolSampler::get_sample_index (z_sobol_sampler.rs:101-156)
     __device__ uint64_t sample_index() const {
@@ -205,7 +213,7 @@ struct DSampler {
             const int digit_shift = 2 * i - (pow2 ? 1 : 0);
             uint32_t digit = (uint32_t)(((uint64_t)morton >> digit_shift) & 3ull);
             const uint64_t higher = (uint64_t)morton >> (digit_shift + 2);
-            const uint32_t p = (uint32_t)((mix_bits(higher ^ dk) >> 24) % 24ull);
+            const uint32_t p = perm_index(mix_bits(higher ^ dk));
             digit = perm_digit(p, digit);
             sidx |= (uint64_t)digit << digit_shift;
         }

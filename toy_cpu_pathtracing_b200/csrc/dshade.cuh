@@ -308,17 +308,12 @@ __device__ __forceinline__ Dielectric make_dielectric(float eta, bool entering, 
 // simple_pbr_clearcoat_material.rs:171-188, 580-829); the Lazanyi term is kept because (1 - tint) = 0 must still multiply through.
 struct Schlick {
     S4 r0; Ggx g;
+    // fresnel (generalized_schlick.rs:192-228) with r90 = 1, exponent = 5, tint = 1: the Lazanyi correction is
+    // a = f(cos_max) * (1 - tint) / (...) = +-0 for every finite r0, and `base - 0 * x` == base, so only the Schlick term is evaluated.
     __device__ S4 fresnel_at(float cos_theta) const {
         cos_theta = clampf(cos_theta, 0.0f, 1.0f);
         const float omc = 1.0f - cos_theta;
-        const float COS_MAX = 1.0f / 7.0f;
-        const float OM_COS_MAX = 1.0f - COS_MAX;
-        const S4 r90 = s4(1.0f), tint = s4(1.0f);
-        const S4 base = r0 + (r90 - r0) * powf(omc, 5.0f);
-        const S4 at_max = r0 + (r90 - r0) * powf(OM_COS_MAX, 5.0f);
-        const S4 a = at_max * (s4(1.0f) - tint) / (COS_MAX * pow6(OM_COS_MAX));
-        const S4 laz = a * cos_theta * pow6(omc);
-        return base - laz;
+        return r0 + (s4(1.0f) - r0) * powf(omc, 5.0f);
     }
     __device__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
         if (wo.z == 0.0f) return false;
@@ -365,6 +360,18 @@ struct Schlick {
     // 64-sample stochastic estimate (generalized_schlick.rs:893-918); `f` already holds a cosine, reproduced as is
     __device__ S4 directional_albedo(float3 wo, DAuxRng rng) const {
         S4 sum = s4(0.0f);
+        if (g.effectively_smooth()) {
+            // every one of the 64 samples is the same mirror sample (the random numbers are drawn but unused), so the term is
+            // computed once and ADDED 64 times: the running sum rounds exactly like the reference's loop
+            BsdfSample s;
+            S4 term = s4(0.0f);
+            if (sample(wo, make_float2(0.0f, 0.0f), &s)) {
+                const float ci = fabsf(s.wi.z);
+                if (ci > 0.0f && s.pdf > 0.0f) term = s.f * ci / s.pdf;
+            }
+            for (int i = 0; i < 64; ++i) sum = sum + term;
+            return sum / 64.0f;
+        }
         for (int i = 0; i < 64; ++i) {
             rng.next();  // uc (unused by the R-mode sampler, but drawn by the reference)
             float2 uv; uv.x = rng.next(); uv.y = rng.next();

@@ -138,6 +138,10 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
         const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
         st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
     };
+    // LightSamplerFactory::create is re-run by the reference at every use (light_sampler.rs:190-220); its result only depends
+    // on the wavelengths, so one evaluation per vertex serves the BSDF-side MIS weight and the NEE draw
+    LightTable lt; bool lt_ready = false;
+    auto lights = [&]() -> const LightTable& { if (!lt_ready) { light_table(sc, wl, lt); lt_ready = true; } return lt; };
 
     if (miss) {
         if (sc.n_envs != 0) {
@@ -149,8 +153,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
                 if (integrator == TCPT_INTEGRATOR_PT) {
                     con = con + thr * fprev * radiance / pdf_prev;  // pt_renderer.rs:80-81
                 } else {
-                    LightTable lt; light_table(sc, wl, lt);
-                    const float light_pdf = scene_env_pdf(sc, lt, ray_d);
+                    const float light_pdf = scene_env_pdf(sc, lights(), ray_d);
                     const float a = pdf_prev, b = light_pdf;
                     const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
                     const float tf = 1.0f / pdf_prev;
@@ -184,9 +187,8 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
         } else {
             if (spec_prev) con = con + thr * next_emissive;                   // mis_renderer.rs:160-163
             else {
-                LightTable lt; light_table(sc, wl, lt);
                 const float4 pp = st.ppos[slot];
-                const float pdf_light = scene_pdf_light_sample(sc, lt, f3(pp.x, pp.y, pp.z), hit);
+                const float pdf_light = scene_pdf_light_sample(sc, lights(), f3(pp.x, pp.y, pp.z), hit);
                 const float a = pdf_prev, b = pdf_light;
                 const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
                 con = con + thr * next_emissive * w;                          // mis_renderer.rs:164-179
@@ -210,15 +212,16 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
     const float uc = smp.get_1d();
     const float2 uv = smp.get_2d();
+    const bool was_terminated = wl.terminated;
     const MatSample ms = material_sample(mc, mat, uc, uv, wl, wo, ng_t, hit.uv);
+    if (wl.terminated != was_terminated) lt_ready = false;  // a dispersive material collapsed the wavelengths: light powers change
 
     if (!ms.is_specular() && integrator != TCPT_INTEGRATOR_PT) {
         // next event estimation (nee_renderer.rs:18-102, mis_renderer.rs:21-123)
         const bool with_mis = integrator == TCPT_INTEGRATOR_MIS;
-        LightTable lt; light_table(sc, wl, lt);
         const float u = smp.get_1d();
         float p_light = 0.0f;
-        const int li = sample_light(sc, lt, u, &p_light);
+        const int li = sample_light(sc, lights(), u, &p_light);
         if (li >= 0) {
             const float s = smp.get_1d();
             const float2 luv = smp.get_2d();

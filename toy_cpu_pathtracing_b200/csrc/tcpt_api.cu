@@ -48,6 +48,7 @@ struct tcpt_ctx {
     tcpt_stats stats{};
     int sm_count = 148;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0; std::vector<int> ev_stage;  // stage timing (see StageTimer)
 };
 
 namespace {
@@ -160,18 +161,33 @@ int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera&
     return TCPT_OK;
 }
 
+// Per-stage device timing without host round trips: an event pair is recorded around every launch on the launching stream
+// and the pairs are read back once, after the frame's final synchronisation (option "stage_timing").
 struct StageTimer {
-    tcpt_ctx* ctx; bool on; cudaEvent_t a, b; double* acc;
-    StageTimer(tcpt_ctx* c, double* target) : ctx(c), on(c->opt.stage_timing != 0), a(nullptr), b(nullptr), acc(target) {
-        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
-    }
-    ~StageTimer() {
+    tcpt_ctx* ctx; bool on; int stage; size_t slot;
+    StageTimer(tcpt_ctx* c, int stage_id, cudaStream_t s) : ctx(c), on(c->opt.stage_timing != 0), stage(stage_id), slot(0) {
         if (!on) return;
-        cudaEventRecord(b, ctx->stream); cudaEventSynchronize(b);
-        float ms = 0; cudaEventElapsedTime(&ms, a, b); *acc += ms;
-        cudaEventDestroy(a); cudaEventDestroy(b);
+        slot = ctx->ev_used;
+        while (ctx->ev_pool.size() < slot + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+        ctx->ev_used += 2;
+        ctx->ev_stage.push_back(stage);
+        cudaEventRecord(ctx->ev_pool[slot], s);
+        stream = s;
     }
+    ~StageTimer() { if (on) cudaEventRecord(ctx->ev_pool[slot + 1], stream); }
+    cudaStream_t stream = nullptr;
 };
+enum { STAGE_GENERATE = 0, STAGE_CLOSEST = 1, STAGE_SHADE = 2, STAGE_SHADOW = 3, STAGE_FILM = 4 };
+
+void collect_stage_times(tcpt_ctx* ctx) {  // call after the stream has been synchronised
+    double* acc[5] = {&ctx->stats.generate_ms, &ctx->stats.trace_closest_ms, &ctx->stats.shade_ms, &ctx->stats.trace_shadow_ms, &ctx->stats.film_ms};
+    for (size_t i = 0; i < ctx->ev_stage.size(); ++i) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]) == cudaSuccess) *acc[ctx->ev_stage[i]] += ms;
+    }
+    ctx->ev_used = 0;
+    ctx->ev_stage.clear();
+}
 
 // one pass = generate + (max_depth + 1) x {closest, shade, shadow} (+ film when acc != nullptr)
 int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList& L, uint32_t n_slots, float* dev_acc, cudaStream_t stream) {
@@ -179,7 +195,7 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
     const DState& st = ctx->st;
     const bool count = ctx->opt.count_tests != 0;
     {
-        StageTimer t(ctx, &ctx->stats.generate_ms);
+        StageTimer t(ctx, STAGE_GENERATE, stream);
         k_generate<<<grid_for(ctx, n_slots, 256), 256, 0, stream>>>(sc, R, cam, st, L, n_slots);
         ctx->stats.kernel_launches++;
     }
@@ -187,24 +203,24 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
     for (uint32_t stage = 0; stage <= R.max_depth; ++stage) {
         const int cur = (int)(stage & 1u);
         {
-            StageTimer t(ctx, &ctx->stats.trace_closest_ms);
+            StageTimer t(ctx, STAGE_CLOSEST, stream);
             if (count) k_trace_closest<true><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
             else k_trace_closest<false><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
         }
         {
-            StageTimer t(ctx, &ctx->stats.shade_ms);
+            StageTimer t(ctx, STAGE_SHADE, stream);
             k_shade<<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
         }
         ctx->stats.kernel_launches += 2;
         if (R.integrator != TCPT_INTEGRATOR_PT && stage < R.max_depth) {
-            StageTimer t(ctx, &ctx->stats.trace_shadow_ms);
+            StageTimer t(ctx, STAGE_SHADOW, stream);
             if (count) k_trace_shadow<true><<<g128, 128, 0, stream>>>(sc, R, st);
             else k_trace_shadow<false><<<g128, 128, 0, stream>>>(sc, R, st);
             ctx->stats.kernel_launches++;
         }
     }
     if (dev_acc) {
-        StageTimer t(ctx, &ctx->stats.film_ms);
+        StageTimer t(ctx, STAGE_FILM, stream);
         k_film<<<grid_for(ctx, R.n_pix, 256), 256, 0, stream>>>(R, st.rgb, dev_acc);
         ctx->stats.kernel_launches++;
     }
@@ -224,6 +240,7 @@ void reset_stats(tcpt_ctx* ctx) {
     cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream);
     ctx->stats = tcpt_stats{};
     ctx->stats.max_bvh_depth = ctx->dev.max_bvh_depth;
+    ctx->ev_used = 0; ctx->ev_stage.clear();
 }
 
 int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cudaStream_t stream) {
@@ -298,6 +315,7 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -417,6 +435,7 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     v.cmf = ctx->d_cmf; v.z_nodes = ctx->d_rgb2spec; v.rgb2spec = ctx->d_rgb2spec + 64;
     std::memcpy(v.xyz_to_rgb, ctx->xyz_to_rgb, sizeof v.xyz_to_rgb);
     db.max_bvh_depth = s->max_bvh_depth;
+    ctx->stats.max_bvh_depth = s->max_bvh_depth;
     db.valid = true;
     return TCPT_OK;
 }
@@ -442,6 +461,7 @@ int tcpt_render_device(tcpt_ctx* ctx, const tcpt_render_params* params, void* de
     CU(cudaEventSynchronize(ctx->ev1));
     float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.render_ms = ms;
+    collect_stage_times(ctx);
     return fetch_stats(ctx);
 }
 
@@ -588,6 +608,7 @@ int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uin
     }
     cudaFree(d_xy); cudaFree(d_s);
     if (rc) return rc;
+    collect_stage_times(ctx);
     for (int i = 0; i < n; ++i) { out_rgb[3 * (size_t)i] = rgb[4 * (size_t)i]; out_rgb[3 * (size_t)i + 1] = rgb[4 * (size_t)i + 1]; out_rgb[3 * (size_t)i + 2] = rgb[4 * (size_t)i + 2]; }
     return fetch_stats(ctx);
 }
