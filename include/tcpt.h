@@ -75,7 +75,7 @@ typedef struct {
      * (0,0 = all rows / all samples).  Tile(row) sharding keeps the per-pixel sample order => bitwise equal to one GPU. */
     uint32_t row_offset, row_stride;
     uint32_t spp_begin, spp_end;
-    uint32_t max_slots;                      /* wavefront size in paths (0 = default 4 Mi) */
+    uint32_t max_slots;                      /* wavefront size in paths (0 = default 32 Mi, about 272 B of device memory each) */
 } tcpt_render_params;
 
 typedef struct {

@@ -134,7 +134,9 @@ struct DState {
     float4* ext_o[2]; float4* ext_d[2];                     // {o.xyz, tmax} | {d.xyz, bits(slot)}   (ping-pong)
     float4* hit0; uint2* hit1;                              // {t, b0, b1, b2} | {prim, tri}
     float4* sh_o; float4* sh_d; float4* sh_c;               // shadow ray + pending NEE contribution (sh_d.w = slot | finalize << 31)
-    uint32_t* counters;                                     // [0],[1] extension queue sizes (ping-pong), [2] shadow queue size
+    uint32_t* order; uint32_t capacity;                     // TCPT_N_BUCKETS x capacity queue positions, bucketed by shading work
+    uint32_t* counters;                                     // [0],[1] extension queue sizes (ping-pong), [2] shadow queue size,
+                                                            // [4..10), [12..18) bucket sizes of even / odd bounces
     unsigned long long* stats;                              // [0] closest rays [1] shadow rays [2] box tests [3] tri tests [4] paths
 };
 
@@ -203,7 +205,7 @@ struct DSampler {
         return (hi * 16u + lo % 24u) % 24u;
     }
     // ZSobolSampler::get_sample_index (z_sobol_sampler.rs:101-156)
-    __device__ uint64_t sample_index() const {
+    __device__ __noinline__ uint64_t sample_index() const {
         uint64_t sidx = 0;
         const bool pow2 = (log2_spp & 1u) == 1u;
         const int last_digit = pow2 ? 1 : 0;
@@ -231,7 +233,7 @@ struct DSampler {
         return v;
     }
 
-    __device__ float get_1d() {
+    __device__ __noinline__ float get_1d() {
         if (kind == TCPT_SAMPLER_SOBOL) {
             const uint64_t a = sample_index();
             dim += 1;
@@ -240,7 +242,7 @@ struct DSampler {
         }
         return unit_float(pcg_hash2(key, dim++));
     }
-    __device__ float2 get_2d() {
+    __device__ __noinline__ float2 get_2d() {
         float2 r;
         if (kind == TCPT_SAMPLER_SOBOL) {
             const uint64_t a = sample_index();
@@ -295,7 +297,7 @@ __device__ __forceinline__ float4 cmf_at(const DScene& sc, float lambda) {  // D
 }
 
 // RgbToSpectrumTable::get (rgb_sigmoid_polynomial.rs:87-155), sRGB-gamma typed colour
-__device__ inline void rgb_to_coeffs(const DScene& sc, float3 rgb_in, float cs[3]) {
+__device__ __noinline__ void rgb_to_coeffs(const DScene& sc, float3 rgb_in, float cs[3]) {
     float rgb[3] = {srgb_to_linear(rgb_in.x), srgb_to_linear(rgb_in.y), srgb_to_linear(rgb_in.z)};
 #pragma unroll
     for (int k = 0; k < 3; ++k) rgb[k] = rgb[k] > 0.0f ? rgb[k] : 0.0f;
@@ -339,7 +341,7 @@ __device__ __forceinline__ float spectrum_value(const DScene& sc, const DSpectru
     if (s.kind == 1) return sg;
     return s.scale * sg * cmf_at(sc, lambda).w;
 }
-__device__ __forceinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl) {
+__device__ __noinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl) {
     S4 r = s4(0.0f);
     r.v[0] = spectrum_value(sc, s, wl.lambda[0]);
     if (wl.terminated) return r;
@@ -375,7 +377,7 @@ __device__ __forceinline__ float lerp2d(float p00, float p10, float p01, float p
     const float top = p00 * (1.0f - fx) + p10 * fx, bottom = p01 * (1.0f - fx) + p11 * fx;
     return top * (1.0f - fy) + bottom * fy;
 }
-__device__ inline float3 tex_rgb(const DTexture& t, float2 uv) {
+__device__ __noinline__ float3 tex_rgb(const DTexture& t, float2 uv) {
     const Taps k = bilinear_taps(t.w, t.h, uv);
     const uint8_t* a = t.data + ((size_t)k.y0 * t.w + k.x0) * 3; const uint8_t* b = t.data + ((size_t)k.y0 * t.w + k.x1) * 3;
     const uint8_t* c = t.data + ((size_t)k.y1 * t.w + k.x0) * 3; const uint8_t* d = t.data + ((size_t)k.y1 * t.w + k.x1) * 3;
@@ -385,7 +387,7 @@ __device__ inline float3 tex_rgb(const DTexture& t, float2 uv) {
         o[ch] = lerp2d((float)__ldg(a + ch) / 255.0f, (float)__ldg(b + ch) / 255.0f, (float)__ldg(c + ch) / 255.0f, (float)__ldg(d + ch) / 255.0f, k.fx, k.fy);
     return f3(o[0], o[1], o[2]);
 }
-__device__ inline float tex_gray(const DTexture& t, float2 uv) {
+__device__ __noinline__ float tex_gray(const DTexture& t, float2 uv) {
     const Taps k = bilinear_taps(t.w, t.h, uv);
     return lerp2d((float)__ldg(t.data + (size_t)k.y0 * t.w + k.x0) / 255.0f, (float)__ldg(t.data + (size_t)k.y0 * t.w + k.x1) / 255.0f,
                   (float)__ldg(t.data + (size_t)k.y1 * t.w + k.x0) / 255.0f, (float)__ldg(t.data + (size_t)k.y1 * t.w + k.x1) / 255.0f, k.fx, k.fy);

@@ -36,7 +36,7 @@ struct DSurface {
 __device__ __forceinline__ float3 orthogonalize(float3 n, float3 v) { const float pm = dot(n, v); return normalize(v - n * pm); }
 __device__ __forceinline__ float3 generate_tangent(float3 n) { return orthogonalize(n, fabsf(n.x) > 0.999f ? f3(0, 1, 0) : f3(1, 0, 0)); }
 
-__device__ inline void reconstruct_hit(const DScene& sc, int prim, uint32_t tri, float b0, float b1, float b2, float3 ray_d, DSurface& s) {
+__device__ __noinline__ void reconstruct_hit(const DScene& sc, int prim, uint32_t tri, float b0, float b1, float b2, float3 ray_d, DSurface& s) {
     const tcpt_flat_primitive& P = sc.primitives[prim];
     const tcpt_flat_geometry& G = sc.geometries[P.geometry];
     const uint32_t* idx = sc.indices + 3 * ((size_t)G.index_base + tri);
@@ -95,7 +95,7 @@ __device__ __forceinline__ bool same_hemisphere(float3 a, float3 b) { return a.z
 __device__ __forceinline__ float pow2(float x) { return x * x; }
 __device__ __forceinline__ float pow6(float x) { const float x2 = x * x; const float x4 = x2 * x2; return x4 * x2; }
 __device__ __forceinline__ float2 sample_uniform_disk_polar(float2 u) { const float r = sqrtf(u.x); const float th = 2.0f * TCPT_PI * u.y; return make_float2(r * cosf(th), r * sinf(th)); }
-__device__ inline S4 fresnel_dielectric(float cos_theta_i, const S4& eta) {
+__device__ __noinline__ S4 fresnel_dielectric(float cos_theta_i, const S4& eta) {
     cos_theta_i = clampf(cos_theta_i, 0.0f, 1.0f);
     const float sin2_theta_i = 1.0f - cos_theta_i * cos_theta_i;
     const S4 sin2_t = s4(sin2_theta_i) / (eta * eta);
@@ -121,14 +121,14 @@ __device__ inline bool refract(float3 wi, float3 n, float eta, float3* wt) {
 struct Ggx {
     float ax, ay;
     __device__ __forceinline__ bool effectively_smooth() const { return rmax(ax, ay) < 1e-3f; }
-    __device__ float D(float3 wm) const {
+    __device__ __noinline__ float D(float3 wm) const {
         const float t2 = tan2_theta(wm);
         if (!isfinite(t2)) return 0.0f;
         const float cos4 = pow2(cos2_theta(wm));
         const float e = t2 * (pow2(cos_phi(wm)) / pow2(ax) + pow2(sin_phi(wm)) / pow2(ay));
         return 1.0f / (TCPT_PI * ax * ay * cos4 * pow2(1.0f + e));
     }
-    __device__ float lambda(float3 w) const {
+    __device__ __noinline__ float lambda(float3 w) const {
         const float t2 = tan2_theta(w);
         if (isinf(t2)) return 0.0f;
         const float a2 = pow2(cos_phi(w) * ax) + pow2(sin_phi(w) * ay);
@@ -141,7 +141,7 @@ struct Ggx {
         if (c == 0.0f) return 0.0f;
         return G1(w) / c * D(wm) * fabsf(dot(w, wm));
     }
-    __device__ float3 sample_wm(float3 w, float2 u) const {
+    __device__ __noinline__ float3 sample_wm(float3 w, float2 u) const {
         float3 wh = normalize(f3(ax * w.x, ay * w.y, w.z));
         if (wh.z < 0.0f) wh = -wh;
         const float3 t1 = wh.z < 0.99999f ? normalize(cross(f3(0, 0, 1), wh)) : f3(1, 0, 0);
@@ -170,7 +170,7 @@ __device__ inline bool generalized_half_vector(float3 wo, float3 wi, float eta, 
 }
 
 // ---------------------------------------------------------------- bsdf/lambert.rs
-__device__ inline bool lambert_sample(const S4& albedo, float3 wo, float2 uv, BsdfSample* out) {
+__device__ __noinline__ bool lambert_sample(const S4& albedo, float3 wo, float2 uv, BsdfSample* out) {
     const float wo_cos = wo.z;
     if (wo_cos == 0.0f) return false;
     const float r = sqrtf(uv.x), th = 2.0f * TCPT_PI * uv.y;
@@ -250,7 +250,7 @@ struct Dielectric {
         out->wi = wi; out->type = ST_GLOSSY_TRANSMISSION;
         return true;
     }
-    __device__ bool sample(float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) const {
+    __device__ __noinline__ bool sample(float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) const {
         if (wo.z == 0.0f) return false;
         if (g.effectively_smooth()) return sample_specular(wo, uc, wl, out);  // selector = uc (dielectric.rs:180)
         const float3 wm = g.sample_wm(wo, uv);
@@ -270,7 +270,7 @@ struct Dielectric {
         if (!s4_is_constant(eta) && !wl.terminated) wl = wavelengths_uniform(wl.lambda[0], true);
         return mf_transmission(wo, wm, s4(1.0f) - fresnel, pt / (pr + pt), eta_scalar, out);
     }
-    __device__ S4 evaluate(float3 wo, float3 wi) const {
+    __device__ __noinline__ S4 evaluate(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return s4(0.0f);
         const S4 es = eta_spectrum();
         const float eta_scalar = es.v[0];
@@ -283,7 +283,7 @@ struct Dielectric {
         const float denom = pow2(dot(wi, wm) + dot(wo, wm) / eta_scalar);
         return (s4(1.0f) - fresnel) * d * gg * fabsf(dot(wi, wm)) * fabsf(dot(wo, wm)) / (denom * fabsf(wo.z) * eta_scalar * eta_scalar);
     }
-    __device__ float pdf(float3 wo, float3 wi) const {
+    __device__ __noinline__ float pdf(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return 0.0f;
         const S4 es = eta_spectrum();
         const float eta_scalar = es.v[0];
@@ -315,7 +315,7 @@ struct Schlick {
         const float omc = 1.0f - cos_theta;
         return r0 + (s4(1.0f) - r0) * powf(omc, 5.0f);
     }
-    __device__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
+    __device__ __noinline__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
         if (wo.z == 0.0f) return false;
         if (g.effectively_smooth()) {
             const float3 wi = f3(-wo.x, -wo.y, wo.z);
@@ -336,7 +336,7 @@ struct Schlick {
         out->f = fr * d * gg / (4.0f * co); out->wi = wi; out->pdf = pdf; out->type = ST_GLOSSY_REFLECTION;
         return true;
     }
-    __device__ S4 evaluate(float3 wo, float3 wi) const {
+    __device__ __noinline__ S4 evaluate(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return s4(0.0f);
         const float co = fabsf(wo.z), ci = fabsf(wi.z);
         if (co == 0.0f || ci == 0.0f) return s4(0.0f);
@@ -347,7 +347,7 @@ struct Schlick {
         const float d = g.D(wm), gg = g.G(wo, wi);
         return fr * d * gg / (4.0f * co);
     }
-    __device__ float pdf(float3 wo, float3 wi) const {
+    __device__ __noinline__ float pdf(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return 0.0f;
         if (!same_hemisphere(wo, wi)) return 0.0f;
         float3 wm;
@@ -358,7 +358,7 @@ struct Schlick {
         return vis / jac;
     }
     // 64-sample stochastic estimate (generalized_schlick.rs:893-918); `f` already holds a cosine, reproduced as is
-    __device__ S4 directional_albedo(float3 wo, DAuxRng rng) const {
+    __device__ __noinline__ S4 directional_albedo(float3 wo, DAuxRng rng) const {
         S4 sum = s4(0.0f);
         if (g.effectively_smooth()) {
             // every one of the 64 samples is the same mirror sample (the random numbers are drawn but unused), so the term is
@@ -406,7 +406,7 @@ struct PbrBase {
         if (!lambert_sample(base_color, wo, uv, &s)) return mat_fail();
         return mat_ok(s.f * (1.0f - fresnel), m3_vector(from_nm, s.wi), s.pdf * (1.0f - fresnel), s.type);
     }
-    __device__ MatSample sample(float3 wo, float uc, float2 uv, const M3& from_nm) const {
+    __device__ __noinline__ MatSample sample(float3 wo, float uc, float2 uv, const M3& from_nm) const {
         const float alpha = roughness * roughness;
         if (metallic >= 1.0f) return sample_metallic(alpha, wo, uv, from_nm);
         if (metallic <= 0.0f) return sample_dielectric(alpha, wo, uc, uv, from_nm);
@@ -419,7 +419,7 @@ struct PbrBase {
         const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
         return direct + (1.0f - fresnel) * lambert_eval(base_color, wo, wi);
     }
-    __device__ S4 evaluate(float3 wo, float3 wi) const {
+    __device__ __noinline__ S4 evaluate(float3 wo, float3 wi) const {
         const float alpha = roughness * roughness;
         if (metallic >= 1.0f) return make_schlick(base_color, alpha).evaluate(wo, wi);
         if (metallic <= 0.0f) return eval_dielectric(alpha, wo, wi);
@@ -431,7 +431,7 @@ struct PbrBase {
         const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
         return fresnel * direct + (1.0f - fresnel) * lambert_pdf(wo, wi);
     }
-    __device__ float pdf(float3 wo, float3 wi) const {
+    __device__ __noinline__ float pdf(float3 wo, float3 wi) const {
         const float alpha = roughness * roughness;
         if (metallic >= 1.0f) return make_schlick(s4(1.0f), alpha).pdf(wo, wi);
         if (metallic <= 0.0f) return pdf_dielectric(alpha, wo, wi);
@@ -440,7 +440,7 @@ struct PbrBase {
 };
 
 // Beer-Lambert coat attenuation (simple_pbr_clearcoat_material.rs:88-107)
-__device__ inline S4 coat_attenuation(const S4& tint, float thickness, float cos_theta) {
+__device__ __noinline__ S4 coat_attenuation(const S4& tint, float thickness, float cos_theta) {
     S4 r;
     const float thickness_m = thickness * 0.001f;
     const float l = thickness_m / rmax(cos_theta, 1e-4f);
@@ -459,7 +459,7 @@ struct MatCtx {
     uint32_t path_key, depth;  // aux RNG keying
 };
 
-__device__ inline float3 param_normal(const DScene& sc, const tcpt_flat_material& m, float2 uv) {  // normal_texture.rs:40-66
+__device__ __noinline__ float3 param_normal(const DScene& sc, const tcpt_flat_material& m, float2 uv) {  // normal_texture.rs:40-66
     if (m.normal_texture < 0) return normalize(f3(0, 0, 1));
     const float3 rgb = tex_rgb(sc.textures[m.normal_texture], uv);
     float x = rgb.x * 2.0f - 1.0f, y = rgb.y * 2.0f - 1.0f, z = rgb.z * 2.0f - 1.0f;
@@ -469,7 +469,7 @@ __device__ inline float3 param_normal(const DScene& sc, const tcpt_flat_material
     return normalize(f3(0, 0, 1));
 }
 // Transform::from_normal_map (math/src/transform.rs:216-244)
-__device__ inline void normal_map_frame(float3 nm, M3& to_nm, M3& from_nm) {
+__device__ __noinline__ void normal_map_frame(float3 nm, M3& to_nm, M3& from_nm) {
     const float3 z = normalize(nm);
     const float3 cand = fabsf(dot(z, f3(1, 0, 0))) < 0.9f ? f3(1, 0, 0) : f3(0, 1, 0);
     const float3 x = normalize(cand - dot(z, cand) * z);
@@ -498,7 +498,7 @@ __device__ __forceinline__ Coat load_coat(const DScene& sc, const tcpt_flat_mate
 __device__ __forceinline__ Schlick coat_bsdf(const Coat& c) { return make_schlick(s4(r0_of(c.ior)), c.roughness * c.roughness); }
 
 // `ng_t` = geometric normal in the tangent frame, `sp_uv` = surface uv
-__device__ inline MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
+__device__ __noinline__ MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
     const DScene& sc = *c.sc;
     M3 to_nm, from_nm;
     normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
@@ -543,7 +543,7 @@ __device__ inline MatSample material_sample(const MatCtx& c, const tcpt_flat_mat
 }
 
 // evaluate() and pdf() of the same (wo, wi) pair, as the NEE helpers call them back to back (common.rs:142-158)
-__device__ inline void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
+__device__ __noinline__ void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
                                          bool want_pdf, S4* f_out, float* pdf_out) {
     const DScene& sc = *c.sc;
     M3 to_nm, from_nm;
@@ -600,7 +600,7 @@ __device__ __forceinline__ S4 emissive_radiance(const DScene& sc, const tcpt_fla
 
 struct LightTable { float w[TCPT_MAX_LIGHTS]; float sum; };
 // LightSamplerFactory::create (light_sampler.rs:190-220): phi(lambda).average() per light
-__device__ inline void light_table(const DScene& sc, const DWavelengths& wl, LightTable& lt) {
+__device__ __noinline__ void light_table(const DScene& sc, const DWavelengths& wl, LightTable& lt) {
     lt.sum = 0.0f;
     for (uint32_t i = 0; i < sc.n_lights; ++i) {
         const tcpt_flat_primitive& P = sc.primitives[sc.light_list[i]];
@@ -646,7 +646,7 @@ __device__ inline float3 env_texel_bilinear(const DEnv& e, float u, float v) {  
     }
     return f3(o[0], o[1], o[2]);
 }
-__device__ inline float env_direction_pdf(const DScene& sc, const tcpt_flat_primitive& P, float3 dir) {  // environment_light.rs:234-259
+__device__ __noinline__ float env_direction_pdf(const DScene& sc, const tcpt_flat_primitive& P, float3 dir) {  // environment_light.rs:234-259
     const DEnv& e = sc.envs[P.env];
     if (e.total_weight <= 0.0f) return 0.0f;
     float theta, phi;
@@ -660,7 +660,7 @@ __device__ inline float env_direction_pdf(const DScene& sc, const tcpt_flat_prim
     const float jac = (float)e.w * (float)e.h / (2.0f * TCPT_PI * TCPT_PI * sin_theta);
     return pdf_texture * jac;
 }
-__device__ inline S4 env_direction_radiance(const DScene& sc, const tcpt_flat_primitive& P, float3 dir, const DWavelengths& wl) {  // environment_light.rs:304-316
+__device__ __noinline__ S4 env_direction_radiance(const DScene& sc, const tcpt_flat_primitive& P, float3 dir, const DWavelengths& wl) {  // environment_light.rs:304-316
     const DEnv& e = sc.envs[P.env];
     float theta, phi;
     direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
@@ -687,7 +687,7 @@ __device__ inline float scene_env_pdf(const DScene& sc, const LightTable& lt, fl
     return tot;
 }
 // Rust slice::binary_search_by(partial_cmp) then clamp (environment_light.rs:218-223)
-__device__ inline uint32_t sample_from_cdf(const float* cdf, uint32_t n, float u) {
+__device__ __noinline__ uint32_t sample_from_cdf(const float* cdf, uint32_t n, float u) {
     uint32_t size = n, base = 0;
     while (size > 1) {
         const uint32_t half = size / 2, mid = base + half;
@@ -700,7 +700,7 @@ __device__ inline uint32_t sample_from_cdf(const float* cdf, uint32_t n, float u
 }
 
 // Scene::pdf_light_sample (scene.rs:156-181) for a BSDF-sampled hit on an emissive mesh
-__device__ inline float scene_pdf_light_sample(const DScene& sc, const LightTable& lt, float3 shading_pos, const DSurface& hit) {
+__device__ __noinline__ float scene_pdf_light_sample(const DScene& sc, const LightTable& lt, float3 shading_pos, const DSurface& hit) {
     const tcpt_flat_primitive& P = sc.primitives[hit.prim];
     if (P.kind != 1) return 0.0f;
     float probability = 0.0f;
@@ -716,7 +716,7 @@ __device__ inline float scene_pdf_light_sample(const DScene& sc, const LightTabl
 }
 
 // ---------------------------------------------------------------- sensor (renderer/src/sensor.rs:41-78)
-__device__ inline float3 sensor_rgb(const DScene& sc, const DWavelengths& wl, const S4& s, float exposure) {
+__device__ __noinline__ float3 sensor_rgb(const DScene& sc, const DWavelengths& wl, const S4& s, float exposure) {
     const int count = wl.terminated ? 1 : 4;
     float x = 0.0f, y = 0.0f, z = 0.0f;
     for (int k = 0; k < count; ++k) {

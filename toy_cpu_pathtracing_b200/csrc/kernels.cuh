@@ -59,17 +59,37 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         st.con[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(smp.dim), __uint_as_float(0u));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0; atomicAdd(&st.stats[4], (unsigned long long)n_slots); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0;
+        for (int b = 0; b < 16; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
+        atomicAdd(&st.stats[4], (unsigned long long)n_slots);
+    }
 }
 
 // ---------------------------------------------------------------- K1 closest hit
+// Besides the hit record, every ray is filed into a BUCKET by what k_shade will have to do with it (miss / material type of
+// the hit), so that k_shade's warps run one material's code instead of serialising up to six branches (ncu on the first
+// version: 8.6 of 32 lanes active in the bounce-1 shade launch).  Filing = one warp-aggregated atomic per distinct bucket.
+#define TCPT_N_BUCKETS 6
+#ifndef TCPT_SHADE_MIN_BLOCKS
+#define TCPT_SHADE_MIN_BLOCKS 4
+#endif
+// shading order: heaviest code first so the tail of the launch is made of cheap vertices
+__device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim) {
+    if (prim < 0) return 5u;                                     // miss: environment lookup only
+    const int t = sc.materials[sc.primitives[prim].material].type;
+    return t == TCPT_MAT_CLEARCOAT_PBR ? 0u : t == TCPT_MAT_SIMPLE_PBR ? 1u : t == TCPT_MAT_PLASTIC ? 2u : t == TCPT_MAT_LAMBERT ? 3u : 4u;
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                         float4* __restrict__ hit0, uint2* __restrict__ hit1, const __grid_constant__ DState st, int cur) {
     const uint32_t n = st.counters[cur];
+    uint32_t* bcount = st.counters + 4 + 8 * cur;  // this bounce's bucket sizes (zeroed one bounce ago)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // the queues this bounce's k_shade appends to were last read one bounce ago (stream order): reset them here
         st.counters[cur ^ 1] = 0; st.counters[2] = 0;
+        for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + 8 * (cur ^ 1) + b] = 0;
         atomicAdd(&st.stats[0], (unsigned long long)n);
     }
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -79,6 +99,15 @@ __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ D
         const DHit h = trace_ray<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
         hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
         hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
+        const uint32_t b = bucket_of(sc, h.prim);
+        const uint32_t act = __activemask();
+        const uint32_t peers = __match_any_sync(act, b);
+        const uint32_t lane = threadIdx.x & 31u;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        st.order[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
     }
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
@@ -320,7 +349,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     st.misc[slot] = make_float4(ms.pdf, lambda0, __uint_as_float(smp.dim), __uint_as_float(flags));
 }
 
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st,
+__global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st,
                                                 const __grid_constant__ PathList L, int cur, uint32_t stage) {
     const uint32_t n = st.counters[cur];
     const float4* __restrict__ q_d = st.ext_d[cur];
@@ -328,9 +357,18 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
     float4* __restrict__ n_d = st.ext_d[cur ^ 1];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    // bucket b occupies sorted positions [off[b], off[b+1]) (sizes written by this bounce's k_trace_closest)
+    uint32_t off[TCPT_N_BUCKETS + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int b = 0; b < TCPT_N_BUCKETS; ++b) off[b + 1] = off[b] + st.counters[4 + 8 * cur + b];
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
         ShadeOut out; out.push_ext = false; out.push_sh = false;
-        if (i < n) {
+        if (p < n) {
+            uint32_t b = 0;
+#pragma unroll
+            for (int k = 1; k < TCPT_N_BUCKETS; ++k) b += (p >= off[k]) ? 1u : 0u;
+            const uint32_t i = st.order[(size_t)b * st.capacity + (p - off[b])];
             const float4 d = q_d[i];
             shade_vertex(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
         }

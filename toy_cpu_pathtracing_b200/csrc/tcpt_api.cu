@@ -119,6 +119,8 @@ int ensure_state(tcpt_ctx* ctx, uint32_t capacity) {
     float4** f4s[] = {&s.thr, &s.con, &s.fprev, &s.misc, &s.ppos, &s.rgb, &s.ext_o[0], &s.ext_o[1], &s.ext_d[0], &s.ext_d[1], &s.hit0, &s.sh_o, &s.sh_d, &s.sh_c};
     for (float4** p : f4s) { int r = alloc(n * sizeof(float4), (void**)p); if (r) return r; }
     { int r = alloc(n * sizeof(uint2), (void**)&s.hit1); if (r) return r; }
+    { int r = alloc(n * sizeof(uint32_t) * TCPT_N_BUCKETS, (void**)&s.order); if (r) return r; }
+    s.capacity = capacity;
     s.counters = ctx->d_counters;
     s.stats = ctx->d_stats;
     ctx->st_capacity = capacity;
@@ -254,7 +256,7 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     const uint32_t rows = R.row_offset < p->height ? (p->height - R.row_offset + R.row_stride - 1) / R.row_stride : 0;
     const uint64_t owned = (uint64_t)rows * p->width;
     if (owned == 0 || s0 == s1) return TCPT_OK;
-    const uint64_t budget = p->max_slots ? p->max_slots : (4u << 20);
+    const uint64_t budget = p->max_slots ? p->max_slots : (32u << 20);  // 33.5 M path slots (about 9 GB of wavefront buffers)
     const uint32_t np = (uint32_t)(owned < budget ? owned : budget);
     uint32_t sc_per_pass = (uint32_t)(budget / np);
     if (sc_per_pass < 1) sc_per_pass = 1;
@@ -295,9 +297,9 @@ int tcpt_create(int device_id, tcpt_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaMalloc((void**)&ctx->d_stats, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(cudaGetErrorString(e));
-    if ((e = cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(uint32_t))) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaMalloc((void**)&ctx->d_counters, 32 * sizeof(uint32_t))) != cudaSuccess) return bail(cudaGetErrorString(e));
     cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long));
-    cudaMemset(ctx->d_counters, 0, 16 * sizeof(uint32_t));
+    cudaMemset(ctx->d_counters, 0, 32 * sizeof(uint32_t));
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     srgb_xyz_to_rgb(ctx->xyz_to_rgb);
     *out = ctx;
