@@ -114,33 +114,40 @@ __device__ __forceinline__ float cull_limit(float t_best) { return t_best * 1.00
 #define TCPT_TLAS_ITEM_BIT 0x80000000u
 #define TCPT_ABSENT 0xffffffffu
 
-// Closest hit (Scene::intersect, scene.rs:80-90).  COUNT adds box/triangle test counters (work figures B, T of SURVEY.md 8d).
-// ANY = Scene::intersect_p (scene.rs:93-103): order independent, returns at the first accepted triangle (prim = 0 on hit).
-template <bool ANY, bool COUNT>
-__device__ inline DHit trace_ray(const DScene& sc, float3 o, float3 d, float t_max, uint32_t* n_box, uint32_t* n_tri) {
-    DHit best; best.prim = -1; best.t = t_max; best.b0 = best.b1 = best.b2 = 0.0f; best.tri = 0;
-    // tie-break state of the current best: TLAS (leaf first slot, slot) and BLAS (leaf first slot, slot)
-    uint32_t best_tleaf = 0, best_tslot = 0, best_bleaf = 0, best_bslot = 0;
-    float limit = t_max;  // box-culling bound (t_max until the first hit)
+// One ray in flight.  The walk is written as an explicit state machine (init / step) so that a warp can keep all 32 lanes
+// busy: a lane whose ray is finished picks up the next ray of the queue instead of idling until the slowest ray of the warp
+// is done (persistent threads with dynamic fetch; ncu on the first, one-ray-per-thread version: 4.2 of 32 lanes active on
+// bounce rays because per-ray work is heavy-tailed).
+struct Traversal {
+    float3 o, d;                 // the ray in Render space
+    float t_max, limit;          // caller's t_max; box-culling bound (t_max until the first hit)
+    RayXform rw, rl;             // Render-space and current BLAS-space ray constants
+    DHit best;
+    uint32_t best_tleaf, best_tslot, best_bleaf, best_bslot;  // tie-break keys of `best`: TLAS (leaf first slot, slot), BLAS (same)
+    int sp, blas_sp;             // stack height; stack height at BLAS entry (-1 = traversing the TLAS)
+    uint32_t node_base, slot_base, node;
+    int cur_prim; uint32_t cur_tleaf, cur_tslot;
 
-    RayXform rw; ray_setup(rw, o, d);
-    RayXform rl = rw;
-    uint32_t stack[TCPT_TRAVERSAL_STACK];
-    int sp = 0;
-    int blas_sp = -1;            // stack height at BLAS entry; -1 = traversing the TLAS
-    uint32_t node_base = 0, slot_base = 0;
-    int cur_prim = -1; uint32_t cur_tleaf = 0, cur_tslot = 0;
-    uint32_t node = 0;           // absolute record index
+    __device__ __forceinline__ void init(float3 o_, float3 d_, float t_max_) {
+        o = o_; d = d_; t_max = t_max_; limit = t_max_;
+        best.prim = -1; best.t = t_max_; best.b0 = best.b1 = best.b2 = 0.0f; best.tri = 0;
+        best_tleaf = best_tslot = best_bleaf = best_bslot = 0;
+        ray_setup(rw, o, d); rl = rw;
+        sp = 0; blas_sp = -1; node_base = 0; slot_base = 0; node = 0; cur_prim = -1; cur_tleaf = cur_tslot = 0;
+    }
 
-    for (;;) {
+    // Visits one child-pair record (both slab tests, any leaf children, descend or pop).  Returns true when the ray is finished.
+    // ANY = Scene::intersect_p (scene.rs:93-103): order independent, finished at the first accepted triangle (best.prim = 0).
+    template <bool ANY, bool COUNT>
+    __device__ __forceinline__ bool step(const DScene& sc, uint32_t* stack, uint32_t* n_box, uint32_t* n_tri) {
         const float4* rec = sc.nodes + 4 * (size_t)node;
         const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
         const bool in_blas = blas_sp >= 0;
         const RayXform& r = in_blas ? rl : rw;
         const uint32_t ref0 = __float_as_uint(q0.w), cnt0 = __float_as_uint(q1.w), ref1 = __float_as_uint(q2.w), cnt1 = __float_as_uint(q3.w);
         float te0, te1;
-        bool h0 = slab_test(q0, q1, r, limit, &te0);
-        bool h1 = (ref1 != TCPT_ABSENT) && slab_test(q2, q3, r, limit, &te1);
+        const bool h0 = slab_test(q0, q1, r, limit, &te0);
+        const bool h1 = (ref1 != TCPT_ABSENT) && slab_test(q2, q3, r, limit, &te1);
         if (COUNT) (*n_box) += (ref1 != TCPT_ABSENT) ? 2u : 1u;
 
         // leaves are handled as soon as they are reached
@@ -156,7 +163,7 @@ __device__ inline DHit trace_ray(const DScene& sc, float3 o, float3 d, float t_m
                     float t, b0, b1, b2;
                     if (COUNT) (*n_tri)++;
                     if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) {
-                        if (ANY) { best.prim = 0; best.t = t; return best; }
+                        if (ANY) { best.prim = 0; best.t = t; return true; }
                         // total order: smaller t; then (TLAS) later leaf, earlier slot; then (BLAS) later leaf, earlier slot
                         const uint32_t bslot = first + i;
                         bool take;
@@ -182,30 +189,72 @@ __device__ inline DHit trace_ray(const DScene& sc, float3 o, float3 d, float t_m
         if (i0 && i1) {
             const uint32_t c0 = node_base + ref0, c1 = node_base + ref1;
             if (te1 < te0) { stack[sp++] = c0; node = c1; } else { stack[sp++] = c1; node = c0; }
-            continue;
+            return false;
         }
-        if (i0) { node = node_base + ref0; continue; }
-        if (i1) { node = node_base + ref1; continue; }
+        if (i0) { node = node_base + ref0; return false; }
+        if (i1) { node = node_base + ref1; return false; }
         // pop
-        for (;;) {
-            if (sp == blas_sp) { blas_sp = -1; node_base = 0; }  // this BLAS is exhausted: back in the TLAS
-            if (sp == 0) return best;
-            const uint32_t top = stack[--sp];
-            if (top & TCPT_TLAS_ITEM_BIT) {
-                const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
-                const int2 item = __ldg(&sc.tlas_items[tslot]);
-                cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
-                const tcpt_flat_primitive& P = sc.primitives[cur_prim];
-                const tcpt_flat_geometry& G = sc.geometries[P.geometry];
-                ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
-                node_base = G.node_base; slot_base = G.slot_base;
-                blas_sp = sp;
-                node = node_base;  // entry record: tests the BLAS root box
-                break;
-            }
+        if (sp == blas_sp) { blas_sp = -1; node_base = 0; }  // this BLAS is exhausted: back in the TLAS
+        if (sp == 0) return true;
+        const uint32_t top = stack[--sp];
+        if (top & TCPT_TLAS_ITEM_BIT) {
+            const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
+            const int2 item = __ldg(&sc.tlas_items[tslot]);
+            cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
+            const tcpt_flat_primitive& P = sc.primitives[cur_prim];
+            const tcpt_flat_geometry& G = sc.geometries[P.geometry];
+            ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
+            node_base = G.node_base; slot_base = G.slot_base;
+            blas_sp = sp;
+            node = node_base;  // entry record: tests the BLAS root box
+        } else {
             node = top;
-            break;
         }
+        return false;
+    }
+};
+
+#ifndef TCPT_REFILL_IDLE_LANES
+#define TCPT_REFILL_IDLE_LANES 8   // a warp fetches new rays once this many of its lanes are idle
+#endif
+
+// Traces the rays of a queue with persistent warps.  `work` is a global counter zeroed before the launch; `done(i, hit)` is
+// called by the lane that finished ray i.  Every warp of the grid must call this with all 32 lanes.
+template <bool ANY, bool COUNT, class Done>
+__device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
+                                            uint32_t* work, uint32_t* n_box, uint32_t* n_tri, Done&& done) {
+    const uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t stack[TCPT_TRAVERSAL_STACK];
+    Traversal T;
+    uint32_t ray = NONE;
+    bool exhausted = false;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(FULL, ray == NONE);
+        if (idle != 0u && !exhausted) {
+            const uint32_t n_idle = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work, n_idle);
+            base = __shfl_sync(FULL, base, 0);
+            if (ray == NONE) {
+                const uint32_t mine = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (mine < n) {
+                    const float4 o = q_o[mine], d = q_d[mine];
+                    T.init(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
+                    ray = mine;
+                }
+            }
+            exhausted = base + n_idle >= n;
+        }
+        if (__ballot_sync(FULL, ray != NONE) == 0u) break;  // nothing in flight and nothing left to fetch
+        const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;
+        uint32_t n_idle_now;
+        do {
+            if (ray != NONE) {
+                if (T.template step<ANY, COUNT>(sc, stack, n_box, n_tri)) { done(ray, T.best); ray = NONE; }
+            }
+            n_idle_now = (uint32_t)__popc(__ballot_sync(FULL, ray == NONE));
+        } while (n_idle_now < stop_at);
     }
 }
 

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0;
         for (int b = 0; b < 16; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
+        st.counters[24] = 0; st.counters[25] = 0;             // work counters of the persistent trace kernels
         atomicAdd(&st.stats[4], (unsigned long long)n_slots);
     }
 }
@@ -81,6 +82,8 @@ __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim) {
     return t == TCPT_MAT_CLEARCOAT_PBR ? 0u : t == TCPT_MAT_SIMPLE_PBR ? 1u : t == TCPT_MAT_PLASTIC ? 2u : t == TCPT_MAT_LAMBERT ? 3u : 4u;
 }
 
+// work counters of the persistent trace kernels: counters[24] closest, counters[25] shadow.  Each is zeroed by an earlier kernel
+// of the same bounce (stream order): k_generate / k_shade zero [24] for the next k_trace_closest, k_trace_closest zeroes [25].
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                         float4* __restrict__ hit0, uint2* __restrict__ hit1, const __grid_constant__ DState st, int cur) {
@@ -88,27 +91,23 @@ __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ D
     uint32_t* bcount = st.counters + 4 + 8 * cur;  // this bounce's bucket sizes (zeroed one bounce ago)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // the queues this bounce's k_shade appends to were last read one bounce ago (stream order): reset them here
-        st.counters[cur ^ 1] = 0; st.counters[2] = 0;
+        st.counters[cur ^ 1] = 0; st.counters[2] = 0; st.counters[25] = 0;
         for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + 8 * (cur ^ 1) + b] = 0;
         atomicAdd(&st.stats[0], (unsigned long long)n);
     }
-    const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t nb = 0, nt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 o = q_o[i], d = q_d[i];
-        const DHit h = trace_ray<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
+    trace_queue<false, COUNT>(sc, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) {
         hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
         hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
         const uint32_t b = bucket_of(sc, h.prim);
-        const uint32_t act = __activemask();
-        const uint32_t peers = __match_any_sync(act, b);
+        const uint32_t peers = __match_any_sync(__activemask(), b);
         const uint32_t lane = threadIdx.x & 31u;
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
         st.order[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
-    }
+    });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -117,15 +116,12 @@ template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_shadow(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st) {
     const uint32_t n = st.counters[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st.stats[1], (unsigned long long)n);
-    const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t nb = 0, nt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 o = st.sh_o[i], d = st.sh_d[i];
-        const DHit h = trace_ray<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
-        const uint32_t tag = __float_as_uint(d.w);
+    trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) {
+        const uint32_t tag = __float_as_uint(st.sh_d[i].w);
         const uint32_t slot = tag & 0x7fffffffu;
         const bool visible = h.prim < 0, last = (tag & 0x80000000u) != 0;
-        if (!visible && !last) continue;
+        if (!visible && !last) return;
         S4 con = s4(st.con[slot]);
         if (visible) {
             con = con + s4(st.sh_c[i]);
@@ -137,7 +133,7 @@ __global__ void __launch_bounds__(128) k_trace_shadow(const __grid_constant__ DS
             const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
             st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
         }
-    }
+    });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -352,6 +348,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
 __global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st,
                                                 const __grid_constant__ PathList L, int cur, uint32_t stage) {
     const uint32_t n = st.counters[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.counters[24] = 0;  // work counter of the next k_trace_closest
     const float4* __restrict__ q_d = st.ext_d[cur];
     float4* __restrict__ n_o = st.ext_o[cur ^ 1];
     float4* __restrict__ n_d = st.ext_d[cur ^ 1];
@@ -410,17 +407,14 @@ __global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ acc,
 // ---------------------------------------------------------------- single-stage probes for parity tests and the traversal micro-benchmark
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
-                                                     int any_hit, float4* __restrict__ hit0, uint2* __restrict__ hit1, unsigned long long* stats) {
-    const uint32_t stride = gridDim.x * blockDim.x;
+                                                     int any_hit, float4* __restrict__ hit0, uint2* __restrict__ hit1, unsigned long long* stats, uint32_t* work) {
     uint32_t nb = 0, nt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 o = q_o[i], d = q_d[i];
-        DHit h;
-        if (any_hit) h = trace_ray<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
-        else h = trace_ray<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, &nb, &nt);
+    auto store = [&](uint32_t i, const DHit& h) {
         hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
         hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
-    }
+    };
+    if (any_hit) trace_queue<true, COUNT>(sc, q_o, q_d, n, work, &nb, &nt, store);
+    else trace_queue<false, COUNT>(sc, q_o, q_d, n, work, &nb, &nt, store);
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)nb); atomicAdd(&stats[3], (unsigned long long)nt); }
 }
 

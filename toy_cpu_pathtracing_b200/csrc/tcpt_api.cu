@@ -518,8 +518,10 @@ int tcpt_trace_device(tcpt_ctx* ctx, const void* dev_rays, int n, int any_hit, v
     const float4* q_o = (const float4*)dev_rays; const float4* q_d = q_o + n;
     float4* h0 = (float4*)dev_hits; uint2* h1 = (uint2*)(h0 + n);
     const int grid = grid_for(ctx, (uint64_t)n, 128);
-    if (ctx->opt.count_tests) k_trace_rays<true><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, ctx->d_stats);
-    else k_trace_rays<false><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, nullptr);
+    uint32_t* work = ctx->d_counters + 26;  // work counter of the persistent trace loop
+    CU(cudaMemsetAsync(work, 0, sizeof(uint32_t), s));
+    if (ctx->opt.count_tests) k_trace_rays<true><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, ctx->d_stats, work);
+    else k_trace_rays<false><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, nullptr, work);
     CU(cudaGetLastError());
     return TCPT_OK;
 }
