@@ -250,14 +250,11 @@ def main_gpu(args, wl):
     value = rays_all / (ms_max * 1e-3) / 1e6
 
     # ---- e2e through the reference-facing API with host buffers (every rank renders its share; rank 0 reports the sum / max time)
-    pix = np.zeros((H, W, 3), dtype=np.float32)
     def e2e_step(k):
         lo = (k * world * S) % wl["frame_spp"]
         sh = shard_plan(rank, world, "spp", wl["frame_spp"], lo, min(lo + world * S, wl["frame_spp"]))
-        p = renderer.params(wl["sampler"], max_slots=args.max_slots, **sh.as_kwargs())
-        ctx.check(ctx.lib.tcpt_render(ctx.handle, C.byref(p), None, capi.as_ptr(pix, C.c_float)))
-        st = ctx.stats()
-        return st["closest_rays"] + st["shadow_rays"]
+        image.render(wl["sampler"], want_accumulators=False, max_slots=args.max_slots, **sh.as_kwargs())   # the reference-facing call; fills image.pixels (host)
+        return image.stats["closest_rays"] + image.stats["shadow_rays"]
     e2e_step(0)
     barrier()
     t0 = time.perf_counter(); e2e_rays = 0
@@ -308,7 +305,7 @@ def main_gpu(args, wl):
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl),
         "mpaths_per_s": paths_all / (ms_max * 1e-3) / 1e6, "rays_per_path": rays_all / max(1.0, paths_all),
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.RenderParams), "d2h_bytes_per_step": int(pix.nbytes), "steps": n_e2e,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(capi.RenderParams), "d2h_bytes_per_step": int(image.pixels.nbytes), "steps": n_e2e,
                 "call": "RendererImage.render -> tcpt_render(params, host sRGB frame out)"},
         "gpu_launches": int(launches_all),
         "clocks": clk_s,

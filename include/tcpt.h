@@ -95,6 +95,9 @@ typedef struct {
 int tcpt_create(int device_id, tcpt_ctx** out);
 void tcpt_destroy(tcpt_ctx* ctx);
 const char* tcpt_last_error(const tcpt_ctx* ctx);
+/* options: "count_tests" (box/triangle test counters), "stage_timing" (per-kernel event timing), "blocks_per_sm",
+ * "binned_builder" (fast non-reference BVH for synthetic soups), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
+ * buffers on first use and keeps them registered while the same pointers are passed; 0: releases them — set 0 before freeing) */
 int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
 /* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65: spectrum/src/presets.rs);
  * rgb2spec = rgb_to_spec table, 64 z-nodes + [3][64][64][64][3] f32 (spectrum/src/rgb_sigmoid_polynomial.rs:35-84) */

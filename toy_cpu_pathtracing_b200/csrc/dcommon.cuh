@@ -191,18 +191,21 @@ struct DSampler {
     }
 
     __device__ __forceinline__ static uint32_t perm_digit(uint32_t p, uint32_t digit) {
-        // rows of PERMUTATIONS (z_sobol_sampler.rs:102-127): one byte per row, digit d stored at bits [2d, 2d+2); four rows per
-        // word, selected with predicated moves so the table lives in registers (a local array would be a divergent LDC/LDL)
-        const uint32_t w0 = 0x78D8B4E4u, w1 = 0xB1E19C6Cu, w2 = 0x8D2D39C9u, w3 = 0x72D236C6u, w4 = 0x87271E4Eu, w5 = 0x93634B1Bu;
-        const uint32_t q = p >> 2;
-        uint32_t w = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : (q == 3 ? w3 : (q == 4 ? w4 : w5))));
-        return (w >> (8u * (p & 3u) + 2u * digit)) & 3u;
+        // rows of PERMUTATIONS (z_sobol_sampler.rs:102-127): one byte per row, digit d stored at bits [2d, 2d+2).  The 24 bytes
+        // live in six immediates; the row is picked with three byte-permutes and mask arithmetic, so there is no table in
+        // memory and no branch (a ?: chain compiled to six divergent paths: 7 of 32 lanes active in the first profile).
+        const uint32_t k = p & 7u, g = p >> 3;
+        const uint32_t r0 = __byte_perm(0x78D8B4E4u, 0xB1E19C6Cu, k), r1 = __byte_perm(0x8D2D39C9u, 0x72D236C6u, k), r2 = __byte_perm(0x87271E4Eu, 0x93634B1Bu, k);
+        const uint32_t m0 = 0u - (uint32_t)(g == 0u), m1 = 0u - (uint32_t)(g == 1u), m2 = 0u - (uint32_t)(g == 2u);
+        const uint32_t row = (r0 & m0) | (r1 & m1) | (r2 & m2);
+        return (row >> (2u * digit)) & 3u;
     }
     // (v >> 24) % 24 of a 64-bit hash with 32-bit arithmetic: v' = hi * 2^32 + lo with hi < 2^8 and 2^32 mod 24 = 16
     __device__ __forceinline__ static uint32_t perm_index(uint64_t mixed) {
         const uint64_t v = mixed >> 24;
         const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-        return (hi * 16u + lo % 24u) % 24u;
+        const uint32_t t = hi * 16u + lo % 24u;          // <= 255 * 16 + 23 = 4103
+        return t - 24u * ((t * 2731u) >> 16);             // exact t % 24 for t < 4104 (2731 = ceil(2^16 / 24))
     }
     // ZSobolSampler::get_sample_index (z_sobol_sampler.rs:101-156)
     __device__ __noinline__ uint64_t sample_index() const {
@@ -211,13 +214,13 @@ struct DSampler {
         const int last_digit = pow2 ? 1 : 0;
         const uint64_t dk = 0x55555555ull * (uint64_t)dim;
         int i = (int)nb4 - 1;
+#pragma unroll 1
         for (; i >= last_digit; --i) {
             const int digit_shift = 2 * i - (pow2 ? 1 : 0);
-            uint32_t digit = (uint32_t)(((uint64_t)morton >> digit_shift) & 3ull);
+            const uint32_t digit = (uint32_t)(((uint64_t)morton >> digit_shift) & 3ull);
             const uint64_t higher = (uint64_t)morton >> (digit_shift + 2);
             const uint32_t p = perm_index(mix_bits(higher ^ dk));
-            digit = perm_digit(p, digit);
-            sidx |= (uint64_t)digit << digit_shift;
+            sidx |= (uint64_t)perm_digit(p, digit) << digit_shift;
         }
         if (pow2) {
             // quirk: the reference ANDs with the loop variable (0 after the loop whenever n_base4_digits >= 1); pbrt-v4 has `& 1`
@@ -233,6 +236,9 @@ struct DSampler {
         return v;
     }
 
+    // get_1d whose value the caller provably does not use: both samplers are pure functions of the dimension counter, so
+    // advancing the counter is all that has to happen (the reference computes and discards the value)
+    __device__ __forceinline__ void skip_1d() { dim += 1; }
     __device__ __noinline__ float get_1d() {
         if (kind == TCPT_SAMPLER_SOBOL) {
             const uint64_t a = sample_index();

@@ -114,10 +114,12 @@ __device__ __forceinline__ float cull_limit(float t_best) { return t_best * 1.00
 #define TCPT_TLAS_ITEM_BIT 0x80000000u
 #define TCPT_ABSENT 0xffffffffu
 
-// One ray in flight.  The walk is written as an explicit state machine (init / step) so that a warp can keep all 32 lanes
-// busy: a lane whose ray is finished picks up the next ray of the queue instead of idling until the slowest ray of the warp
-// is done (persistent threads with dynamic fetch; ncu on the first, one-ray-per-thread version: 4.2 of 32 lanes active on
-// bounce rays because per-ray work is heavy-tailed).
+// One ray in flight.  The walk is an explicit state machine so that a warp can keep its lanes busy:
+//   * a lane whose ray is finished picks up the next ray of the queue instead of idling until the slowest ray of the warp is
+//     done (persistent threads with dynamic fetch; first profile, one ray per thread: 4.2 of 32 lanes active on bounce rays);
+//   * reaching a leaf only RECORDS its triangle slots; the warp switches to a triangle phase (one triangle per lane per
+//     iteration) once enough lanes hold pending triangles (second profile: the inline leaf loops ran with 1.9 lanes active and
+//     were 60 % of the kernel's warp instructions).
 struct Traversal {
     float3 o, d;                 // the ray in Render space
     float t_max, limit;          // caller's t_max; box-culling bound (t_max until the first hit)
@@ -127,6 +129,8 @@ struct Traversal {
     int sp, blas_sp;             // stack height; stack height at BLAS entry (-1 = traversing the TLAS)
     uint32_t node_base, slot_base, node;
     int cur_prim; uint32_t cur_tleaf, cur_tslot;
+    uint32_t pend_slot, pend_cnt;  // triangle slots (relative to slot_base) recorded but not yet tested
+    bool need_pop;                 // the next node comes from the stack (deferred so pending triangles keep their BLAS state)
 
     __device__ __forceinline__ void init(float3 o_, float3 d_, float t_max_) {
         o = o_; d = d_; t_max = t_max_; limit = t_max_;
@@ -134,12 +138,61 @@ struct Traversal {
         best_tleaf = best_tslot = best_bleaf = best_bslot = 0;
         ray_setup(rw, o, d); rl = rw;
         sp = 0; blas_sp = -1; node_base = 0; slot_base = 0; node = 0; cur_prim = -1; cur_tleaf = cur_tslot = 0;
+        pend_slot = 0; pend_cnt = 0; need_pop = false;
     }
 
-    // Visits one child-pair record (both slab tests, any leaf children, descend or pop).  Returns true when the ray is finished.
-    // ANY = Scene::intersect_p (scene.rs:93-103): order independent, finished at the first accepted triangle (best.prim = 0).
+    // Tests ONE pending triangle.  ANY = Scene::intersect_p (scene.rs:93-103): returns true (ray finished) at the first accepted triangle.
     template <bool ANY, bool COUNT>
-    __device__ __forceinline__ bool step(const DScene& sc, uint32_t* stack, uint32_t* n_box, uint32_t* n_tri) {
+    __device__ __forceinline__ bool tri_step(const DScene& sc, uint32_t* n_tri) {
+        const uint32_t bslot = pend_slot;
+        pend_slot += 1; pend_cnt -= 1;
+        const size_t s = 3 * (size_t)(slot_base + bslot);
+        const float4 v0 = __ldg(&sc.tri_verts[s]), v1 = __ldg(&sc.tri_verts[s + 1]), v2 = __ldg(&sc.tri_verts[s + 2]);
+        float t, b0, b1, b2;
+        if (COUNT) (*n_tri)++;
+        if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) {
+            if (ANY) { best.prim = 0; best.t = t; return true; }
+            // total order: smaller t; then (TLAS) later leaf, earlier slot; then (BLAS) later leaf, earlier slot
+            const uint32_t bleaf = __float_as_uint(v2.w);
+            bool take;
+            if (best.prim < 0) take = true;
+            else if (t != best.t) take = t < best.t;
+            else if (cur_tleaf != best_tleaf) take = cur_tleaf > best_tleaf;
+            else if (cur_tslot != best_tslot) take = cur_tslot < best_tslot;
+            else if (bleaf != best_bleaf) take = bleaf > best_bleaf;
+            else take = bslot < best_bslot;
+            if (take) {
+                best.t = t; best.b0 = b0; best.b1 = b1; best.b2 = b2; best.prim = cur_prim; best.tri = __float_as_uint(v0.w);
+                best_tleaf = cur_tleaf; best_tslot = cur_tslot; best_bleaf = bleaf; best_bslot = bslot;
+                limit = fminf(t_max, cull_limit(t));
+            }
+        }
+        return false;
+    }
+
+    // Visits one child-pair record (both slab tests; leaf children are recorded / TLAS items queued; descend, or defer a pop).
+    // Returns true when the ray is finished (stack empty and nothing pending).
+    template <bool COUNT>
+    __device__ __forceinline__ bool node_step(const DScene& sc, uint32_t* stack, uint32_t* n_box) {
+        if (need_pop) {
+            need_pop = false;
+            if (sp == blas_sp) { blas_sp = -1; node_base = 0; }  // this BLAS is exhausted: back in the TLAS
+            if (sp == 0) return true;
+            const uint32_t top = stack[--sp];
+            if (top & TCPT_TLAS_ITEM_BIT) {
+                const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
+                const int2 item = __ldg(&sc.tlas_items[tslot]);
+                cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
+                const tcpt_flat_primitive& P = sc.primitives[cur_prim];
+                const tcpt_flat_geometry& G = sc.geometries[P.geometry];
+                ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
+                node_base = G.node_base; slot_base = G.slot_base;
+                blas_sp = sp;
+                node = node_base;  // entry record: tests the BLAS root box
+            } else {
+                node = top;
+            }
+        }
         const float4* rec = sc.nodes + 4 * (size_t)node;
         const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
         const bool in_blas = blas_sp >= 0;
@@ -149,73 +202,32 @@ struct Traversal {
         const bool h0 = slab_test(q0, q1, r, limit, &te0);
         const bool h1 = (ref1 != TCPT_ABSENT) && slab_test(q2, q3, r, limit, &te1);
         if (COUNT) (*n_box) += (ref1 != TCPT_ABSENT) ? 2u : 1u;
-
-        // leaves are handled as soon as they are reached
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const bool hk = k == 0 ? h0 : h1;
-            const uint32_t cnt = k == 0 ? cnt0 : cnt1, first = k == 0 ? ref0 : ref1;
-            if (!hk || cnt == 0) continue;
-            if (in_blas) {
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    const size_t s = 3 * (size_t)(slot_base + first + i);
-                    const float4 v0 = __ldg(&sc.tri_verts[s]), v1 = __ldg(&sc.tri_verts[s + 1]), v2 = __ldg(&sc.tri_verts[s + 2]);
-                    float t, b0, b1, b2;
-                    if (COUNT) (*n_tri)++;
-                    if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) {
-                        if (ANY) { best.prim = 0; best.t = t; return true; }
-                        // total order: smaller t; then (TLAS) later leaf, earlier slot; then (BLAS) later leaf, earlier slot
-                        const uint32_t bslot = first + i;
-                        bool take;
-                        if (best.prim < 0) take = true;
-                        else if (t != best.t) take = t < best.t;
-                        else if (cur_tleaf != best_tleaf) take = cur_tleaf > best_tleaf;
-                        else if (cur_tslot != best_tslot) take = cur_tslot < best_tslot;
-                        else if (first != best_bleaf) take = first > best_bleaf;
-                        else take = bslot < best_bslot;
-                        if (take) {
-                            best.t = t; best.b0 = b0; best.b1 = b1; best.b2 = b2; best.prim = cur_prim; best.tri = __float_as_uint(v0.w);
-                            best_tleaf = cur_tleaf; best_tslot = cur_tslot; best_bleaf = first; best_bslot = bslot;
-                            limit = fminf(t_max, cull_limit(t));
-                        }
-                    }
-                }
-            } else {
-                // TLAS leaf: queue its primitives (each opens a BLAS when popped)
-                for (uint32_t i = 0; i < cnt; ++i) stack[sp++] = TCPT_TLAS_ITEM_BIT | (first + cnt - 1u - i);
-            }
+        const bool l0 = h0 && cnt0 != 0, l1 = h1 && cnt1 != 0;
+        if (in_blas) {
+            // sibling leaves occupy adjacent slots (leaf order = DFS order), so both fit one pending range
+            if (l0) { pend_slot = ref0; pend_cnt = cnt0 + (l1 ? cnt1 : 0u); }
+            else if (l1) { pend_slot = ref1; pend_cnt = cnt1; }
+        } else {
+            // TLAS leaf: queue its primitives (each opens a BLAS when popped)
+            if (l0) for (uint32_t i = 0; i < cnt0; ++i) stack[sp++] = TCPT_TLAS_ITEM_BIT | (ref0 + cnt0 - 1u - i);
+            if (l1) for (uint32_t i = 0; i < cnt1; ++i) stack[sp++] = TCPT_TLAS_ITEM_BIT | (ref1 + cnt1 - 1u - i);
         }
         const bool i0 = h0 && cnt0 == 0, i1 = h1 && cnt1 == 0;
         if (i0 && i1) {
             const uint32_t c0 = node_base + ref0, c1 = node_base + ref1;
             if (te1 < te0) { stack[sp++] = c0; node = c1; } else { stack[sp++] = c1; node = c0; }
-            return false;
-        }
-        if (i0) { node = node_base + ref0; return false; }
-        if (i1) { node = node_base + ref1; return false; }
-        // pop
-        if (sp == blas_sp) { blas_sp = -1; node_base = 0; }  // this BLAS is exhausted: back in the TLAS
-        if (sp == 0) return true;
-        const uint32_t top = stack[--sp];
-        if (top & TCPT_TLAS_ITEM_BIT) {
-            const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
-            const int2 item = __ldg(&sc.tlas_items[tslot]);
-            cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
-            const tcpt_flat_primitive& P = sc.primitives[cur_prim];
-            const tcpt_flat_geometry& G = sc.geometries[P.geometry];
-            ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
-            node_base = G.node_base; slot_base = G.slot_base;
-            blas_sp = sp;
-            node = node_base;  // entry record: tests the BLAS root box
-        } else {
-            node = top;
-        }
+        } else if (i0) node = node_base + ref0;
+        else if (i1) node = node_base + ref1;
+        else need_pop = true;
         return false;
     }
 };
 
 #ifndef TCPT_REFILL_IDLE_LANES
 #define TCPT_REFILL_IDLE_LANES 8   // a warp fetches new rays once this many of its lanes are idle
+#endif
+#ifndef TCPT_TRI_PHASE_LANES
+#define TCPT_TRI_PHASE_LANES 12    // a warp runs a triangle iteration once this many lanes hold pending triangles
 #endif
 
 // Traces the rays of a queue with persistent warps.  `work` is a global counter zeroed before the launch; `done(i, hit)` is
@@ -227,6 +239,7 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t stack[TCPT_TRAVERSAL_STACK];
     Traversal T;
+    T.pend_cnt = 0;
     uint32_t ray = NONE;
     bool exhausted = false;
     for (;;) {
@@ -250,9 +263,16 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
         const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;
         uint32_t n_idle_now;
         do {
-            if (ray != NONE) {
-                if (T.template step<ANY, COUNT>(sc, stack, n_box, n_tri)) { done(ray, T.best); ray = NONE; }
+            const bool has_tri = ray != NONE && T.pend_cnt != 0u;
+            const uint32_t tri_mask = __ballot_sync(FULL, has_tri);
+            const uint32_t node_mask = __ballot_sync(FULL, ray != NONE && !has_tri);
+            bool finished = false;
+            if (tri_mask != 0u && ((uint32_t)__popc(tri_mask) >= (uint32_t)TCPT_TRI_PHASE_LANES || node_mask == 0u)) {
+                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, n_tri);
+            } else {
+                if (ray != NONE && !has_tri) finished = T.template node_step<COUNT>(sc, stack, n_box);
             }
+            if (finished) { done(ray, T.best); ray = NONE; T.pend_cnt = 0; }
             n_idle_now = (uint32_t)__popc(__ballot_sync(FULL, ray == NONE));
         } while (n_idle_now < stop_at);
     }

@@ -235,7 +235,9 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     const float3 wo = m3_vector(r2t, hit.wo);
     const float3 ng_t = m3_normal_by_inverse(t2r, hit.normal);  // Transform * Normal = inverse(r2t)^T n, normalised
     MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
-    const float uc = smp.get_1d();
+    // `uc` only selects between lobes; LambertMaterial::sample never reads it (lambert_material.rs:42-97)
+    float uc = 0.0f;
+    if (mat.type == TCPT_MAT_LAMBERT) smp.skip_1d(); else uc = smp.get_1d();
     const float2 uv = smp.get_2d();
     const bool was_terminated = wl.terminated;
     const MatSample ms = material_sample(mc, mat, uc, uv, wl, wo, ng_t, hit.uv);
@@ -244,14 +246,25 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     if (!ms.is_specular() && integrator != TCPT_INTEGRATOR_PT) {
         // next event estimation (nee_renderer.rs:18-102, mis_renderer.rs:21-123)
         const bool with_mis = integrator == TCPT_INTEGRATOR_MIS;
-        const float u = smp.get_1d();
         float p_light = 0.0f;
-        const int li = sample_light(sc, lights(), u, &p_light);
+        int li;
+        if (sc.n_lights == 1) {
+            // one light: sample_light returns it for every u (light_sampler.rs:31-43), with probability w/w
+            smp.skip_1d();
+            const LightTable& t1 = lights();
+            li = t1.sum == 0.0f ? -1 : 0;
+            p_light = t1.w[0] / t1.sum;
+        } else {
+            const float u = smp.get_1d();
+            li = sample_light(sc, lights(), u, &p_light);
+        }
         if (li >= 0) {
-            const float s = smp.get_1d();
-            const float2 luv = smp.get_2d();
             const int lprim = sc.light_list[li];
             const tcpt_flat_primitive& LP = sc.primitives[lprim];
+            // `s` picks the triangle of an area light; the environment light ignores it (scene.rs:127-153)
+            float s = 0.0f;
+            if (LP.kind == 2) smp.skip_1d(); else s = smp.get_1d();
+            const float2 luv = smp.get_2d();
             float3 sh_dir; float sh_tmax; S4 pending;
             if (LP.kind == 2) {
                 // EnvironmentLight::sample_infinite_light (environment_light.rs:326-350) + evaluate_infinite_light{,_with_mis} (common.rs:174-241)

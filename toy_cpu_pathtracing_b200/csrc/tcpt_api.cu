@@ -24,7 +24,8 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0; };
+struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
 
@@ -49,6 +50,9 @@ struct tcpt_ctx {
     int sm_count = 148;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0; std::vector<int> ev_stage;  // stage timing (see StageTimer)
+    // tcpt_render's own film buffers (grow-only) and the caller's output buffers currently page-locked for direct DMA
+    float* film_acc = nullptr; float* film_srgb = nullptr; size_t film_cap = 0;
+    HostPin pins[2];
 };
 
 namespace {
@@ -276,6 +280,27 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     return TCPT_OK;
 }
 
+void unpin_all(tcpt_ctx* ctx) {
+    for (HostPin& h : ctx->pins) { if (h.ptr) cudaHostUnregister(h.ptr); h = HostPin(); }
+}
+
+// Device -> caller's host buffer.  With option "pin_host_buffers" the buffer is page-locked once (and stays so while the same
+// pointer is passed again) so the copy is a direct DMA at PCIe rate instead of a staged pageable copy.
+int copy_out(tcpt_ctx* ctx, int slot, float* host, const float* dev, size_t bytes) {
+    if (ctx->opt.pin_host_buffers) {
+        HostPin& h = ctx->pins[slot];
+        if (h.ptr != host || h.bytes != bytes) {
+            if (h.ptr) cudaHostUnregister(h.ptr);
+            h = HostPin();
+            if (cudaHostRegister(host, bytes, cudaHostRegisterDefault) == cudaSuccess) { h.ptr = host; h.bytes = bytes; }
+            else cudaGetLastError();  // not registrable (e.g. already pinned by the caller): plain copy below
+        }
+    }
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TCPT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -311,6 +336,9 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->stream) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     free_scene(ctx->dev);
     for (void* p : ctx->st_allocs) cudaFree(p);
+    unpin_all(ctx);
+    if (ctx->film_acc) cudaFree(ctx->film_acc);
+    if (ctx->film_srgb) cudaFree(ctx->film_srgb);
     if (ctx->d_cmf) cudaFree(ctx->d_cmf);
     if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
@@ -331,6 +359,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "stage_timing") ctx->opt.stage_timing = value;
     else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
     else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
+    else if (n == "pin_host_buffers") { ctx->opt.pin_host_buffers = value != 0; if (!value) unpin_all(ctx); }
     else return fail(ctx, TCPT_ERR_INVALID, "unknown option " + n);
     return TCPT_OK;
 }
@@ -484,22 +513,24 @@ int tcpt_render(tcpt_ctx* ctx, const tcpt_render_params* params, float* out_acc,
     if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
     CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)params->width * params->height * 3;
-    float* d_acc = nullptr; float* d_srgb = nullptr;
-    CU(cudaMalloc((void**)&d_acc, n * sizeof(float)));
-    cudaError_t e = cudaMemsetAsync(d_acc, 0, n * sizeof(float), ctx->stream);
-    int rc = e == cudaSuccess ? tcpt_render_device(ctx, params, d_acc, nullptr) : fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
-    if (rc == TCPT_OK && out_acc) { e = cudaMemcpy(out_acc, d_acc, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
-    if (rc == TCPT_OK && out_srgb) {
-        e = cudaMalloc((void**)&d_srgb, n * sizeof(float));
-        if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
-        else {
-            rc = tcpt_finalize_device(ctx, d_acc, params->width, params->height, params->spp, d_srgb, nullptr);
-            if (rc == TCPT_OK) { e = cudaMemcpy(out_srgb, d_srgb, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
-        }
+    if (ctx->film_cap < n) {
+        if (ctx->film_acc) cudaFree(ctx->film_acc);
+        if (ctx->film_srgb) cudaFree(ctx->film_srgb);
+        ctx->film_acc = ctx->film_srgb = nullptr; ctx->film_cap = 0;
+        CU(cudaMalloc((void**)&ctx->film_acc, n * sizeof(float)));
+        CU(cudaMalloc((void**)&ctx->film_srgb, n * sizeof(float)));
+        ctx->film_cap = n;
     }
-    if (d_acc) cudaFree(d_acc);
-    if (d_srgb) cudaFree(d_srgb);
-    return rc;
+    CU(cudaMemsetAsync(ctx->film_acc, 0, n * sizeof(float), ctx->stream));
+    int rc = tcpt_render_device(ctx, params, ctx->film_acc, nullptr);
+    if (rc) return rc;
+    if (out_acc && (rc = copy_out(ctx, 0, out_acc, ctx->film_acc, n * sizeof(float))) != TCPT_OK) return rc;
+    if (out_srgb) {
+        k_finalize<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->film_acc, ctx->film_srgb, (uint32_t)n, (float)params->spp);
+        CU(cudaGetLastError());
+        if ((rc = copy_out(ctx, 1, out_srgb, ctx->film_srgb, n * sizeof(float))) != TCPT_OK) return rc;
+    }
+    return TCPT_OK;
 }
 
 int tcpt_get_stats(const tcpt_ctx* ctx, tcpt_stats* out) {

@@ -108,15 +108,27 @@ class RendererImage:                  # renderer/src/renderer.rs:101-149
     def new(cls, width, height, renderer):
         return cls(width, height, renderer)
 
-    def render(self, sampler=ZSobolSampler, **shard) -> "RendererImage":
+    def render(self, sampler=ZSobolSampler, want_accumulators: bool = True, **shard) -> "RendererImage":
         r = self.renderer
         ctx = r.args.scene.ctx
         if not r.args.scene.built:
             r.args.scene.build(r.args.camera)
         p = r.params(sampler, **shard)
-        ctx.check(ctx.lib.tcpt_render(ctx.handle, C.byref(p), capi.as_ptr(self.accumulators, C.c_float), capi.as_ptr(self.pixels, C.c_float)))
+        # `pixels` / `accumulators` live as long as this image: let libtcpt page-lock them once for direct DMA
+        ctx.set_option("pin_host_buffers", 1)
+        self._pinned_ctx = ctx
+        ctx.check(ctx.lib.tcpt_render(ctx.handle, C.byref(p), capi.as_ptr(self.accumulators, C.c_float) if want_accumulators else None,
+                                      capi.as_ptr(self.pixels, C.c_float)))
         self.stats = ctx.stats()
         return self
+
+    def __del__(self):
+        ctx = getattr(self, "_pinned_ctx", None)
+        if ctx is not None and getattr(ctx, "handle", None):
+            try:
+                ctx.set_option("pin_host_buffers", 0)   # release the page locks before the arrays are freed
+            except Exception:
+                pass
 
     def path_samples(self, sampler, pixels_xy, sample_indices) -> np.ndarray:
         """Sensor contribution of individual (pixel, sample) paths (parity probe)."""
