@@ -80,10 +80,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+    lib_path = Path(os.environ.get("TCPT_LIB", LIB_PATH))   # developer knob: benchmark an alternative build of the same sources
+    if not lib_path.exists():
+        raise FileNotFoundError(f"{lib_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
                                 "There is no CPU fallback for the path-integration hot path.")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     P, I, U, F = C.c_void_p, C.c_int, C.c_uint32, C.c_float
     fp, up, ip, bp = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     sig = {

@@ -227,7 +227,7 @@ struct Traversal {
 #define TCPT_REFILL_IDLE_LANES 8   // a warp fetches new rays once this many of its lanes are idle
 #endif
 #ifndef TCPT_TRI_PHASE_LANES
-#define TCPT_TRI_PHASE_LANES 12    // a warp runs a triangle iteration once this many lanes hold pending triangles
+#define TCPT_TRI_PHASE_LANES 8    // a warp runs a triangle iteration once this many lanes hold pending triangles
 #endif
 
 // Traces the rays of a queue with persistent warps.  `work` is a global counter zeroed before the launch; `done(i, hit)` is
