@@ -15,6 +15,7 @@ for r in det[1:]:
         seen.setdefault((r[idc], r[kn].split("(")[0]), []).append(f"{r[mn]}={r[mv]}{r[mu]}")
 for k, v in seen.items():
     print("##", k[0], k[1]); print("   " + "; ".join(v))
+SRC_PLACEHOLDER = None
 src = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
 # the source page holds one table per launch, each starting with a header row
 tables, cur = [], None
