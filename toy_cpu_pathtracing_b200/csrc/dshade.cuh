@@ -498,12 +498,15 @@ __device__ __forceinline__ Coat load_coat(const DScene& sc, const tcpt_flat_mate
 __device__ __forceinline__ Schlick coat_bsdf(const Coat& c) { return make_schlick(s4(r0_of(c.ior)), c.roughness * c.roughness); }
 
 // `ng_t` = geometric normal in the tangent frame, `sp_uv` = surface uv
-__device__ __noinline__ MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
+// MT = the material type as a compile-time constant: k_shade is instantiated once per shading bucket, so each instantiation
+// carries only its own material's code (I-cache footprint and register pressure of the fused kernel were the first bottleneck)
+template <int MT>
+__device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
     const DScene& sc = *c.sc;
     M3 to_nm, from_nm;
     normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
     const float3 wo_nm = m3_vector(to_nm, wo);
-    switch (m.type) {
+    switch (MT) {
         case TCPT_MAT_LAMBERT: {  // lambert_material.rs:42-97
             const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
             BsdfSample s;
@@ -543,14 +546,15 @@ __device__ __noinline__ MatSample material_sample(const MatCtx& c, const tcpt_fl
 }
 
 // evaluate() and pdf() of the same (wo, wi) pair, as the NEE helpers call them back to back (common.rs:142-158)
-__device__ __noinline__ void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
+template <int MT>
+__device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
                                          bool want_pdf, S4* f_out, float* pdf_out) {
     const DScene& sc = *c.sc;
     M3 to_nm, from_nm;
     normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
     const float3 wo_nm = m3_vector(to_nm, wo), wi_nm = m3_vector(to_nm, wi);
     *pdf_out = 0.0f;
-    switch (m.type) {
+    switch (MT) {
         case TCPT_MAT_LAMBERT: {  // lambert_material.rs:99-170
             if (signum(dot(ng_t, wi)) != signum(dot(ng_t, wo))) { *f_out = s4(0.0f); return; }
             const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);

@@ -143,8 +143,16 @@ struct ShadeOut {
     float4 eo, ed, so, sd, sc;
 };
 
-__device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DState& st, const PathList& L, uint32_t stage,
-                                    float3 ray_d, uint32_t slot, const float4 h0, const uint2 h1, ShadeOut& out) {
+// bucket -> compile-time material type (see bucket_of)
+template <int B> struct BucketInfo {
+    static constexpr bool miss = B == 5;
+    static constexpr int mat = B == 0 ? TCPT_MAT_CLEARCOAT_PBR : B == 1 ? TCPT_MAT_SIMPLE_PBR : B == 2 ? TCPT_MAT_PLASTIC : B == 3 ? TCPT_MAT_LAMBERT : TCPT_MAT_EMISSIVE;
+};
+
+template <int B>
+__device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R, const DState& st, const PathList& L, uint32_t stage,
+                                             float3 ray_d, uint32_t slot, const float4 h0, const uint2 h1, ShadeOut& out) {
+    constexpr int MT = BucketInfo<B>::mat;
     out.push_ext = false; out.push_sh = false;
     const float4 misc = st.misc[slot];
     float pdf_prev = misc.x;
@@ -157,7 +165,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     smp.dim = __float_as_uint(misc.z);
     S4 thr = s4(st.thr[slot]), con = s4(st.con[slot]);
     const int integrator = R.integrator;
-    const bool miss = (int)h1.x < 0;
+    constexpr bool miss = BucketInfo<B>::miss;
 
     auto finish = [&]() {
         const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
@@ -168,7 +176,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     LightTable lt; bool lt_ready = false;
     auto lights = [&]() -> const LightTable& { if (!lt_ready) { light_table(sc, wl, lt); lt_ready = true; } return lt; };
 
-    if (miss) {
+    if constexpr (miss) {
         if (sc.n_envs != 0) {
             if (stage == 0) {
                 con = con + thr * scene_env_radiance(sc, ray_d, wl);  // base_renderer.rs:180-186
@@ -188,12 +196,12 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
         }
         finish();
         return;
-    }
+    } else {
 
     DSurface hit;
     reconstruct_hit(sc, (int)h1.x, h1.y, h0.y, h0.z, h0.w, ray_d, hit);
     const tcpt_flat_material& mat = sc.materials[hit.material];
-    const bool emissive = mat.type == TCPT_MAT_EMISSIVE;
+    constexpr bool emissive = MT == TCPT_MAT_EMISSIVE;
 
     if (stage == 0) {
         if (emissive) con = con + thr * emissive_radiance(sc, mat, hit.uv, wl);  // base_renderer.rs:190-194
@@ -228,6 +236,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
         }
     }
     if (stage >= R.max_depth || emissive) { finish(); return; }  // depth loop bound (:197) / emitters have no BSDF (:199-202)
+    if constexpr (!emissive) {
 
     // ---- one bounce (base_renderer.rs:199-237)
     M3 r2t, t2r;
@@ -237,10 +246,10 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
     // `uc` only selects between lobes; LambertMaterial::sample never reads it (lambert_material.rs:42-97)
     float uc = 0.0f;
-    if (mat.type == TCPT_MAT_LAMBERT) smp.skip_1d(); else uc = smp.get_1d();
+    if (MT == TCPT_MAT_LAMBERT) smp.skip_1d(); else uc = smp.get_1d();
     const float2 uv = smp.get_2d();
     const bool was_terminated = wl.terminated;
-    const MatSample ms = material_sample(mc, mat, uc, uv, wl, wo, ng_t, hit.uv);
+    const MatSample ms = material_sample<MT>(mc, mat, uc, uv, wl, wo, ng_t, hit.uv);
     if (wl.terminated != was_terminated) lt_ready = false;  // a dispersive material collapsed the wavelengths: light powers change
 
     if (!ms.is_specular() && integrator != TCPT_INTEGRATOR_PT) {
@@ -279,7 +288,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
                 const S4 radiance = env_direction_radiance(sc, LP, wi_r, wl);
                 const float3 wi = m3_vector(r2t, wi_r);
                 S4 f; float bpdf;
-                material_eval_pdf(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
+                material_eval_pdf<MT>(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
                 const float w = with_mis ? ((pdf_dir == 0.0f && bpdf == 0.0f) ? 0.0f : pdf_dir / (pdf_dir + bpdf)) : 1.0f;
                 const S4 c = f * radiance / (pdf_dir * p_light);
                 pending = with_mis ? thr * c * w : thr * c;
@@ -315,7 +324,7 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
                 const float pdf_dir = pdf_area * (distance * distance) / rmax(fabsf(dot(lnormal, -wi_r)), 1e-8f);
                 const float3 wi = m3_vector(r2t, wi_r);
                 S4 f; float bpdf;
-                material_eval_pdf(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
+                material_eval_pdf<MT>(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
                 const float distance2 = length_squared(dv);
                 const float3 ln_t = m3_normal_by_inverse(t2r, lnormal);
                 const float cos_light = fabsf(dot(ln_t, -wi));
@@ -356,36 +365,40 @@ __device__ inline void shade_vertex(const DScene& sc, const DRender& R, const DS
     st.ppos[slot] = make_float4(hit.position.x, hit.position.y, hit.position.z, 0.0f);
     flags = (ms.is_specular() ? FLAG_SPEC_PREV : 0u) | (wl.terminated ? FLAG_LAMBDA_TERMINATED : 0u);
     st.misc[slot] = make_float4(ms.pdf, lambda0, __uint_as_float(smp.dim), __uint_as_float(flags));
+    }  // !emissive
+    }  // !miss
 }
 
-__global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st,
-                                                const __grid_constant__ PathList L, int cur, uint32_t stage) {
-    const uint32_t n = st.counters[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) st.counters[24] = 0;  // work counter of the next k_trace_closest
+// One instantiation per shading bucket; each walks only its own range of the bucketed order.
+template <int B>
+__global__ void __launch_bounds__(128, (B >= 4 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
+                                                                                     const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, uint32_t stage) {
+    if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) st.counters[24] = 0;  // work counter of the next k_trace_closest
     const float4* __restrict__ q_d = st.ext_d[cur];
     float4* __restrict__ n_o = st.ext_o[cur ^ 1];
     float4* __restrict__ n_d = st.ext_d[cur ^ 1];
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
-    // bucket b occupies sorted positions [off[b], off[b+1]) (sizes written by this bounce's k_trace_closest)
-    uint32_t off[TCPT_N_BUCKETS + 1];
-    off[0] = 0;
+    // bucket B occupies sorted positions [begin, begin + n) (sizes written by this bounce's k_trace_closest)
+    uint32_t begin = 0;
 #pragma unroll
-    for (int b = 0; b < TCPT_N_BUCKETS; ++b) off[b + 1] = off[b] + st.counters[4 + 8 * cur + b];
+    for (int b = 0; b < B; ++b) begin += st.counters[4 + 8 * cur + b];
+    const uint32_t n = st.counters[4 + 8 * cur + B];
+    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
+    const uint32_t* __restrict__ order = st.order + (size_t)B * st.capacity;
+    (void)begin;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
         ShadeOut out; out.push_ext = false; out.push_sh = false;
         if (p < n) {
-            uint32_t b = 0;
-#pragma unroll
-            for (int k = 1; k < TCPT_N_BUCKETS; ++k) b += (p >= off[k]) ? 1u : 0u;
-            const uint32_t i = st.order[(size_t)b * st.capacity + (p - off[b])];
+            const uint32_t i = order[p];
             const float4 d = q_d[i];
-            shade_vertex(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+            shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
         }
-        const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
-        if (out.push_ext) { n_o[pe] = out.eo; n_d[pe] = out.ed; }
-        const uint32_t ps = warp_push(&st.counters[2], out.push_sh);
-        if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
+        if (B < 4) {  // emissive hits and misses end the path: nothing to push
+            const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
+            if (out.push_ext) { n_o[pe] = out.eo; n_d[pe] = out.ed; }
+            const uint32_t ps = warp_push(&st.counters[2], out.push_sh);
+            if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
+        }
     }
 }
 

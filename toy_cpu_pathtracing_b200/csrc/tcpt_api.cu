@@ -215,9 +215,14 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         }
         {
             StageTimer t(ctx, STAGE_SHADE, stream);
-            k_shade<<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<0><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<1><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<2><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
         }
-        ctx->stats.kernel_launches += 2;
+        ctx->stats.kernel_launches += 7;
         if (R.integrator != TCPT_INTEGRATOR_PT && stage < R.max_depth) {
             StageTimer t(ctx, STAGE_SHADOW, stream);
             if (count) k_trace_shadow<true><<<g128, 128, 0, stream>>>(sc, R, st);
