@@ -78,6 +78,11 @@ typedef struct {
     float total_weight;
     tcpt_flat_spectrum integrated;
     int32_t primitive;
+    /* guide tables for the CDF searches (an acceleration structure, not reference data): for a CDF of n entries and G = the
+     * power of two >= n, guide[j] = #{i : cdf[i] <= j/G}, j = 0..G, so the search for u only looks at cdf[guide[j] .. guide[j+1])
+     * with j = floor(u*G).  marginal: guide_h + 1 entries; conditional: height rows of guide_w + 1 entries. */
+    uint32_t guide_h, guide_w;
+    uint64_t marginal_guide_offset, conditional_guide_offset; /* into env_guides */
 } tcpt_flat_env;
 
 typedef struct {
@@ -97,6 +102,7 @@ typedef struct {
     const int32_t* light_list; uint32_t n_lights;   /* primitive indices, LightSamplerFactory order (light_sampler.rs:168-187) */
     const tcpt_flat_env* envs; uint32_t n_envs;
     const float* env_floats; uint64_t n_env_floats;
+    const uint32_t* env_guides; uint64_t n_env_guides;
     uint32_t max_bvh_depth;                 /* TLAS depth + largest TLAS leaf + deepest BLAS depth, must be < TCPT_TRAVERSAL_STACK */
 } tcpt_flat_scene;
 

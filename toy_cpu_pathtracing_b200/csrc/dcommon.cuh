@@ -94,6 +94,7 @@ __device__ __forceinline__ S4 s4_clamp(const S4& a, float lo, float hi) { S4 r; 
 struct DTexture { const uint8_t* data; uint32_t w, h, channels, pad; };
 struct DEnv {
     const float* data; const float* marginal; const float* conditional;
+    const uint32_t* marginal_guide; const uint32_t* conditional_guide; uint32_t guide_h, guide_w;
     float intensity, total_weight; uint32_t w, h; tcpt_flat_spectrum integrated; int32_t primitive;
 };
 struct DScene {
@@ -144,6 +145,9 @@ enum : uint32_t { FLAG_SPEC_PREV = 1u, FLAG_LAMBDA_TERMINATED = 2u, FLAG_SAMPLED
 
 // ---------------------------------------------------------------- samplers
 __constant__ uint32_t c_sobol_dim1[52];  // SOBOL_MATRICES_32[52..104) (dimension 1); dimension 0 is the bit reversal
+// the same matrix folded per index byte: tab[pos * 256 + b] = XOR of c_sobol_dim1[8 * pos + i] over the set bits i of b
+// (7 x 256 words in global memory, L1 resident); XOR is associative, so 5-7 gathers replace up to 52 bit-serial steps
+__constant__ const uint32_t* c_sobol_dim1_bytes;
 
 struct DSampler {
     uint32_t kind, seed, log2_spp, nb4, morton, dim, key;
@@ -230,12 +234,12 @@ struct DSampler {
         return sidx;
     }
     __device__ __forceinline__ static uint32_t sobol_dim1(uint64_t a) {
-        uint32_t v = 0;
-        for (int i = 0; a != 0; a >>= 1, ++i)
-            if (a & 1ull) v ^= c_sobol_dim1[i];
+        const uint32_t* __restrict__ tab = c_sobol_dim1_bytes;
+        uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+        uint32_t v = __ldg(tab + (lo & 255u)) ^ __ldg(tab + 256 + ((lo >> 8) & 255u)) ^ __ldg(tab + 512 + ((lo >> 16) & 255u)) ^ __ldg(tab + 768 + (lo >> 24));
+        if (hi != 0u) v ^= __ldg(tab + 1024 + (hi & 255u)) ^ __ldg(tab + 1280 + ((hi >> 8) & 255u)) ^ __ldg(tab + 1536 + ((hi >> 16) & 15u));  // matrix has 52 rows
         return v;
     }
-
     // get_1d whose value the caller provably does not use: both samplers are pure functions of the dimension counter, so
     // advancing the counter is all that has to happen (the reference computes and discards the value)
     __device__ __forceinline__ void skip_1d() { dim += 1; }

@@ -690,17 +690,20 @@ __device__ inline float scene_env_pdf(const DScene& sc, const LightTable& lt, fl
     }
     return tot;
 }
-// Rust slice::binary_search_by(partial_cmp) then clamp (environment_light.rs:218-223)
-__device__ __noinline__ uint32_t sample_from_cdf(const float* cdf, uint32_t n, float u) {
-    uint32_t size = n, base = 0;
-    while (size > 1) {
-        const uint32_t half = size / 2, mid = base + half;
-        if (!(__ldg(cdf + mid) > u)) base = mid;
-        size -= half;
-    }
-    const float c = __ldg(cdf + base);
-    if (c == u) return base;
-    return min(base + (c < u ? 1u : 0u), n - 1u);
+// Rust slice::binary_search_by(partial_cmp) then clamp (environment_light.rs:218-223).  On a non-decreasing CDF the
+// reference's probing sequence ends at base = (#entries <= u) - 1 (or 0), so with k = #{i : cdf[i] <= u} the result is
+//   k == 0 -> 0 ;  cdf[k-1] == u -> k-1 ;  else min(k, n-1)
+// and k is found with the guide table (tcpt_flat_env) plus a scan of the one or two entries it leaves, instead of
+// log2(n) dependent loads (profile: the 19 serial L2 round trips of the two searches were the top stall of bounce-0 shading).
+__device__ __noinline__ uint32_t sample_from_cdf(const float* cdf, uint32_t n, const uint32_t* guide, uint32_t G, float u) {
+    const uint32_t j = min(f2u_sat(u * (float)G), G - 1u);   // u * 2^m is exact
+    uint32_t k = __ldg(guide + j);
+    const uint32_t hi = __ldg(guide + j + 1);
+    while (k < hi && __ldg(cdf + k) <= u) ++k;
+    if (k == 0u) return 0u;
+    const float c = __ldg(cdf + k - 1u);
+    if (c == u) return k - 1u;
+    return min(k, n - 1u);
 }
 
 // Scene::pdf_light_sample (scene.rs:156-181) for a BSDF-sampled hit on an emissive mesh

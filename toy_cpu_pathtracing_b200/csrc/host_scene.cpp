@@ -213,6 +213,21 @@ int HostScene::add_env_light(float intensity, const float* rgb, uint32_t w, uint
     e.marginal.resize(h);
     float run = 0.0f;
     for (uint32_t y = 0; y < h; ++y) { run += row_w[y]; e.marginal[y] = total > 0.0f ? run / total : (float)(y + 1) / (float)h; }
+    // guide tables: guide[j] = #{i : cdf[i] <= j/G} for j = 0..G (cdf is non-decreasing, j/G is exact in f32)
+    auto pow2_at_least = [](uint32_t n) { uint32_t g = 1; while (g < n) g <<= 1; return g; };
+    auto build_guide = [](const float* cdf, uint32_t n, uint32_t G, uint32_t* out) {
+        uint32_t k = 0;
+        for (uint32_t j = 0; j <= G; ++j) {
+            const float edge = (float)j / (float)G;
+            while (k < n && cdf[k] <= edge) ++k;
+            out[j] = k;
+        }
+    };
+    e.guide_h = pow2_at_least(h); e.guide_w = pow2_at_least(w);
+    e.marginal_guide.resize(e.guide_h + 1);
+    build_guide(e.marginal.data(), h, e.guide_h, e.marginal_guide.data());
+    e.conditional_guide.resize((size_t)h * (e.guide_w + 1));
+    for (uint32_t y = 0; y < h; ++y) build_guide(&e.conditional[(size_t)y * w], w, e.guide_w, &e.conditional_guide[(size_t)y * (e.guide_w + 1)]);
     envs.push_back(std::move(e));
     HostPrimitive p; p.kind = 2; p.env = (int)envs.size() - 1;
     std::memcpy(p.local_to_world.m, l2w, 64);
@@ -373,6 +388,9 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         fe.data_offset = S.env_floats.size(); S.env_floats.insert(S.env_floats.end(), e.data.begin(), e.data.end());
         fe.marginal_offset = S.env_floats.size(); S.env_floats.insert(S.env_floats.end(), e.marginal.begin(), e.marginal.end());
         fe.conditional_offset = S.env_floats.size(); S.env_floats.insert(S.env_floats.end(), e.conditional.begin(), e.conditional.end());
+        fe.guide_h = e.guide_h; fe.guide_w = e.guide_w;
+        fe.marginal_guide_offset = S.env_guides.size(); S.env_guides.insert(S.env_guides.end(), e.marginal_guide.begin(), e.marginal_guide.end());
+        fe.conditional_guide_offset = S.env_guides.size(); S.env_guides.insert(S.env_guides.end(), e.conditional_guide.begin(), e.conditional_guide.end());
         fe.primitive = -1;
         for (size_t k = 0; k < primitives.size(); ++k) if (primitives[k].env == (int)i) fe.primitive = (int)k;
         S.envs.push_back(fe);
@@ -393,6 +411,7 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     v.light_list = S.light_list.data(); v.n_lights = (uint32_t)S.light_list.size();
     v.envs = S.envs.data(); v.n_envs = (uint32_t)S.envs.size();
     v.env_floats = S.env_floats.data(); v.n_env_floats = S.env_floats.size();
+    v.env_guides = S.env_guides.data(); v.n_env_guides = S.env_guides.size();
     v.max_bvh_depth = tlas.depth + tlas_max_leaf + deepest;
     if (v.max_bvh_depth + 2 >= TCPT_TRAVERSAL_STACK) { error = "build: BVH deeper than the traversal stack"; return TCPT_ERR_LIMIT; }
     return TCPT_OK;

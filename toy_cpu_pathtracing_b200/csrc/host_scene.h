@@ -41,6 +41,8 @@ struct HostEnv {
     float intensity;
     uint32_t w, h;
     std::vector<float> data, marginal, conditional;
+    std::vector<uint32_t> marginal_guide, conditional_guide;  // see tcpt_flat_env
+    uint32_t guide_h = 0, guide_w = 0;
     float total_weight;
     tcpt_flat_spectrum integrated;
 };
@@ -50,7 +52,7 @@ struct FlatStorage {
     std::vector<tcpt_bvh_node> nodes;
     std::vector<int32_t> tlas_items;
     std::vector<float> tri_verts, positions, normals, uvs, tangents, area_list, area_table, env_floats;
-    std::vector<uint32_t> indices;
+    std::vector<uint32_t> indices, env_guides;
     std::vector<tcpt_flat_geometry> geometries;
     std::vector<tcpt_flat_primitive> primitives;
     std::vector<tcpt_flat_material> materials;

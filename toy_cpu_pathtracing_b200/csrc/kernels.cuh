@@ -278,8 +278,8 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
             if (LP.kind == 2) {
                 // EnvironmentLight::sample_infinite_light (environment_light.rs:326-350) + evaluate_infinite_light{,_with_mis} (common.rs:174-241)
                 const DEnv& e = sc.envs[LP.env];
-                const uint32_t yy = sample_from_cdf(e.marginal, e.h, luv.x);
-                const uint32_t xx = sample_from_cdf(e.conditional + (size_t)yy * e.w, e.w, luv.y);
+                const uint32_t yy = sample_from_cdf(e.marginal, e.h, e.marginal_guide, e.guide_h, luv.x);
+                const uint32_t xx = sample_from_cdf(e.conditional + (size_t)yy * e.w, e.w, e.conditional_guide + (size_t)yy * (e.guide_w + 1u), e.guide_w, luv.y);
                 const float eu = ((float)xx + 0.5f) / (float)e.w, ev = ((float)yy + 0.5f) / (float)e.h;
                 const float theta = ev * TCPT_PI, phi = eu * 2.0f * TCPT_PI;
                 const float3 wl_local = f3(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));

@@ -38,6 +38,7 @@ struct tcpt_ctx {
     DeviceBuffers dev;
     // tables on the device
     float4* d_cmf = nullptr; float* d_rgb2spec = nullptr;  // d_rgb2spec = 64 z nodes + table
+    uint32_t* d_sobol_bytes = nullptr;                      // Sobol matrix 1 folded per index byte (7 x 256)
     float xyz_to_rgb[9];
     // wavefront buffers
     DState st{};
@@ -345,6 +346,7 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->film_acc) cudaFree(ctx->film_acc);
     if (ctx->film_srgb) cudaFree(ctx->film_srgb);
     if (ctx->d_cmf) cudaFree(ctx->d_cmf);
+    if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
     if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -386,6 +388,19 @@ int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const
     if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyToSymbol(c_sobol_dim1, T.sobol + 52, 52 * 4));
+    {
+        std::vector<uint32_t> tab(7 * 256, 0u);
+        for (int pos = 0; pos < 7; ++pos)
+            for (int b = 0; b < 256; ++b) {
+                uint32_t v = 0;
+                for (int i = 0; i < 8; ++i) if ((b >> i) & 1) { const int row = 8 * pos + i; if (row < 52) v ^= T.sobol[52 + row]; }
+                tab[pos * 256 + b] = v;
+            }
+        if (!ctx->d_sobol_bytes) CU(cudaMalloc((void**)&ctx->d_sobol_bytes, tab.size() * 4));
+        CU(cudaMemcpy(ctx->d_sobol_bytes, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        const uint32_t* p = ctx->d_sobol_bytes;
+        CU(cudaMemcpyToSymbol(c_sobol_dim1_bytes, &p, sizeof p));
+    }
     std::vector<float> cmf(470 * 4);
     for (int i = 0; i < 470; ++i) { cmf[4 * i] = T.cie_x[i]; cmf[4 * i + 1] = T.cie_y[i]; cmf[4 * i + 2] = T.cie_z[i]; cmf[4 * i + 3] = T.d65[i]; }
     if (!ctx->d_cmf) CU(cudaMalloc((void**)&ctx->d_cmf, 470 * sizeof(float4)));
@@ -461,10 +476,12 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     for (uint32_t i = 0; i < s->n_lights; ++i) v.light_list[i] = s->light_list[i];
     v.n_lights = s->n_lights;
     const float* envf; UP(upload(ctx, db, s->env_floats, s->n_env_floats, &envf));
+    const uint32_t* envg; UP(upload(ctx, db, s->env_guides, s->n_env_guides, &envg));
     std::vector<DEnv> de(s->n_envs);
     for (uint32_t i = 0; i < s->n_envs; ++i) {
         const tcpt_flat_env& e = s->envs[i];
-        de[i] = DEnv{envf + e.data_offset, envf + e.marginal_offset, envf + e.conditional_offset, e.intensity, e.total_weight, e.width, e.height, e.integrated, e.primitive};
+        de[i] = DEnv{envf + e.data_offset, envf + e.marginal_offset, envf + e.conditional_offset,
+                     envg + e.marginal_guide_offset, envg + e.conditional_guide_offset, e.guide_h, e.guide_w, e.intensity, e.total_weight, e.width, e.height, e.integrated, e.primitive};
     }
     UP(upload(ctx, db, de.data(), de.size(), &v.envs)); v.n_envs = s->n_envs;
 #undef UP
