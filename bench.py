@@ -34,6 +34,8 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "scene19_4k": dict(scene=19, width=3840, height=2160, frame_spp=4096, integrator="mis", sampler="sobol"),
     "scene17_1080p": dict(scene=17, width=1920, height=1080, frame_spp=1024, integrator="mis", sampler="sobol"),
+    "scene17_1080p_nocoat": dict(scene=17, width=1920, height=1080, frame_spp=1024, integrator="mis", sampler="sobol", kw={"coat": False}),
+    "scene10_test": dict(scene=10, width=200, height=150, frame_spp=512, integrator="mis", sampler="sobol"),
     "scene3_test": dict(scene=3, width=200, height=150, frame_spp=512, integrator="mis", sampler="sobol"),
 }
 
@@ -97,7 +99,7 @@ def build_scene(wl, device, require_gpu=True):
     from toy_cpu_pathtracing_b200 import scenes
     scene = tp.Scene(device=device, require_gpu=require_gpu)
     cam = tp.Camera(45.0, wl["width"], wl["height"])
-    scenes.load_scene(wl["scene"], scene, cam)
+    scenes.load_scene(wl["scene"], scene, cam, **wl.get("kw", {}))
     return tp, scene, cam
 
 
@@ -173,7 +175,7 @@ def main_reference(args, wl):
 
 def workload_config(args, wl):
     return {"workload": f"scene{wl['scene']} {wl['width']}x{wl['height']} {wl['integrator']}+{wl['sampler']} max_depth 16, {wl['frame_spp']}-spp frame, "
-                        f"{args.spp_per_step} sample indices of every pixel per GPU per step (BASELINE.json configs[3])",
+                        f"{args.spp_per_step} sample indices of every pixel per GPU per step" + (" (BASELINE.json configs[3])" if wl["scene"] == 19 else "") + (" no-coat" if wl.get("kw") else ""),
             "paths_per_gpu_per_step": wl["width"] * wl["height"] * args.spp_per_step, "sharding": "spp-pass", "collective": "one NCCL reduce of the film accumulators per step",
             "cache": "working set (path state + ray queues, about 1 GB per GPU) exceeds the 126 MB L2; no explicit flush", "assets": "procedural stand-ins (reference assets are LFS stubs)"}
 

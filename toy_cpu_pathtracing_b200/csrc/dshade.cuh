@@ -313,7 +313,8 @@ struct Schlick {
     __device__ S4 fresnel_at(float cos_theta) const {
         cos_theta = clampf(cos_theta, 0.0f, 1.0f);
         const float omc = 1.0f - cos_theta;
-        return r0 + (s4(1.0f) - r0) * powf(omc, 5.0f);
+        const float o2 = omc * omc;
+        return r0 + (s4(1.0f) - r0) * (o2 * o2 * omc);  // (1 - cos)^5: three roundings, within 2 ulp of powf(omc, 5.0)
     }
     __device__ __noinline__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
         if (wo.z == 0.0f) return false;
@@ -469,6 +470,7 @@ __device__ __noinline__ float3 param_normal(const DScene& sc, const tcpt_flat_ma
     return normalize(f3(0, 0, 1));
 }
 // Transform::from_normal_map (math/src/transform.rs:216-244)
+struct NmFrame { M3 to_nm, from_nm; bool identity; };
 __device__ __noinline__ void normal_map_frame(float3 nm, M3& to_nm, M3& from_nm) {
     const float3 z = normalize(nm);
     const float3 cand = fabsf(dot(z, f3(1, 0, 0))) < 0.9f ? f3(1, 0, 0) : f3(0, 1, 0);
@@ -478,6 +480,15 @@ __device__ __noinline__ void normal_map_frame(float3 nm, M3& to_nm, M3& from_nm)
     to_nm = m3_inverse(m);
     from_nm = m3_inverse(to_nm);
 }
+// The normal-map frame of a vertex: the reference rebuilds it inside sample(), evaluate() and pdf() from the same inputs
+// (e.g. lambert_material.rs:53-59, 107-113, 146-152); it is built once per vertex here.  Without a normal map the normal is
+// (0,0,1) and both matrices are exactly the identity (every cofactor is 0 or 1), so the transforms are skipped.
+__device__ __forceinline__ void material_frame(const DScene& sc, const tcpt_flat_material& m, float2 sp_uv, NmFrame& f) {
+    f.identity = m.normal_texture < 0;
+    if (!f.identity) normal_map_frame(param_normal(sc, m, sp_uv), f.to_nm, f.from_nm);
+}
+__device__ __forceinline__ float3 to_nm(const NmFrame& f, float3 v) { return f.identity ? v : m3_vector(f.to_nm, v); }
+
 __device__ __forceinline__ PbrBase load_pbr(const DScene& sc, const tcpt_flat_material& m, float2 uv, const DWavelengths& wl) {
     PbrBase b;
     b.base_color = spectrum_sample(sc, param_spectrum(sc, m.color, uv), wl);
@@ -501,11 +512,11 @@ __device__ __forceinline__ Schlick coat_bsdf(const Coat& c) { return make_schlic
 // MT = the material type as a compile-time constant: k_shade is instantiated once per shading bucket, so each instantiation
 // carries only its own material's code (I-cache footprint and register pressure of the fused kernel were the first bottleneck)
 template <int MT>
-__device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
+__device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt_flat_material& m, const NmFrame& fr, float uc, float2 uv, DWavelengths& wl, float3 wo, float3 ng_t, float2 sp_uv) {
     const DScene& sc = *c.sc;
-    M3 to_nm, from_nm;
-    normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
-    const float3 wo_nm = m3_vector(to_nm, wo);
+    M3 from_nm;
+    if (fr.identity) { from_nm.c0 = f3(1, 0, 0); from_nm.c1 = f3(0, 1, 0); from_nm.c2 = f3(0, 0, 1); } else from_nm = fr.from_nm;
+    const float3 wo_nm = to_nm(fr, wo);
     switch (MT) {
         case TCPT_MAT_LAMBERT: {  // lambert_material.rs:42-97
             const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
@@ -547,12 +558,10 @@ __device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt
 
 // evaluate() and pdf() of the same (wo, wi) pair, as the NEE helpers call them back to back (common.rs:142-158)
 template <int MT>
-__device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
+__device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_flat_material& m, const NmFrame& fr, const DWavelengths& wl, float3 wo, float3 wi, float3 ng_t, float2 sp_uv,
                                          bool want_pdf, S4* f_out, float* pdf_out) {
     const DScene& sc = *c.sc;
-    M3 to_nm, from_nm;
-    normal_map_frame(param_normal(sc, m, sp_uv), to_nm, from_nm);
-    const float3 wo_nm = m3_vector(to_nm, wo), wi_nm = m3_vector(to_nm, wi);
+    const float3 wo_nm = to_nm(fr, wo), wi_nm = to_nm(fr, wi);
     *pdf_out = 0.0f;
     switch (MT) {
         case TCPT_MAT_LAMBERT: {  // lambert_material.rs:99-170
@@ -650,11 +659,8 @@ __device__ inline float3 env_texel_bilinear(const DEnv& e, float u, float v) {  
     }
     return f3(o[0], o[1], o[2]);
 }
-__device__ __noinline__ float env_direction_pdf(const DScene& sc, const tcpt_flat_primitive& P, float3 dir) {  // environment_light.rs:234-259
-    const DEnv& e = sc.envs[P.env];
+__device__ __noinline__ float env_pdf_spherical(const DEnv& e, float theta, float phi) {  // environment_light.rs:234-259
     if (e.total_weight <= 0.0f) return 0.0f;
-    float theta, phi;
-    direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
     const float u = phi / (2.0f * TCPT_PI), v = theta / TCPT_PI;
     const uint32_t x = min(f2u_sat(floorf(u * (float)e.w)), e.w - 1u), y = min(f2u_sat(floorf(v * (float)e.h)), e.h - 1u);
     const float* px = e.data + ((size_t)y * e.w + x) * 3;
@@ -664,12 +670,21 @@ __device__ __noinline__ float env_direction_pdf(const DScene& sc, const tcpt_fla
     const float jac = (float)e.w * (float)e.h / (2.0f * TCPT_PI * TCPT_PI * sin_theta);
     return pdf_texture * jac;
 }
-__device__ __noinline__ S4 env_direction_radiance(const DScene& sc, const tcpt_flat_primitive& P, float3 dir, const DWavelengths& wl) {  // environment_light.rs:304-316
-    const DEnv& e = sc.envs[P.env];
-    float theta, phi;
-    direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
+__device__ __noinline__ S4 env_radiance_spherical(const DScene& sc, const DEnv& e, float theta, float phi, const DWavelengths& wl) {  // environment_light.rs:304-316
     const float3 rgb = env_texel_bilinear(e, phi / (2.0f * TCPT_PI), theta / TCPT_PI);
     return spectrum_sample(sc, illuminant_from_rgb(sc, rgb), wl) * e.intensity;
+}
+// direction -> (theta, phi) is evaluated once per direction and shared by the pdf and radiance lookups (the reference
+// recomputes it inside each from the same direction: identical values)
+__device__ __forceinline__ float env_direction_pdf(const DScene& sc, const tcpt_flat_primitive& P, float3 dir) {
+    float theta, phi;
+    direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
+    return env_pdf_spherical(sc.envs[P.env], theta, phi);
+}
+__device__ __forceinline__ S4 env_direction_radiance(const DScene& sc, const tcpt_flat_primitive& P, float3 dir, const DWavelengths& wl) {
+    float theta, phi;
+    direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
+    return env_radiance_spherical(sc, sc.envs[P.env], theta, phi, wl);
 }
 // Scene::evaluate_infinite_light_radiance (scene.rs:213-231)
 __device__ inline S4 scene_env_radiance(const DScene& sc, float3 dir, const DWavelengths& wl) {
@@ -689,6 +704,24 @@ __device__ inline float scene_env_pdf(const DScene& sc, const LightTable& lt, fl
         if (P.kind == 2) tot += (lt.w[i] / inf_sum) * env_direction_pdf(sc, P, dir);
     }
     return tot;
+}
+// radiance (scene.rs:213-231) and, for MIS, the light-sampling pdf (scene.rs:184-210) of an escaped direction in one pass over the
+// environment lights, sharing the spherical coordinates; both sums run in primitive order like the reference's loops
+__device__ inline void scene_env_radiance_pdf(const DScene& sc, const LightTable* lt, float3 dir, const DWavelengths& wl, S4* radiance, float* pdf) {
+    S4 tot = s4(0.0f);
+    float inf_sum = 0.0f, ptot = 0.0f;
+    const bool want_pdf = lt != nullptr && sc.n_lights != 0 && lt->sum != 0.0f;
+    if (want_pdf) for (uint32_t i = 0; i < sc.n_lights; ++i) if (sc.primitives[sc.light_list[i]].kind == 2) inf_sum += lt->w[i];
+    for (uint32_t i = 0; i < sc.n_envs; ++i) {
+        const DEnv& e = sc.envs[i];
+        const tcpt_flat_primitive& P = sc.primitives[e.primitive];
+        float theta, phi;
+        direction_to_spherical(xf_vector(P.r2l, dir), &theta, &phi);
+        tot = tot + env_radiance_spherical(sc, e, theta, phi, wl);
+        if (want_pdf && inf_sum != 0.0f && P.light_index >= 0) ptot += (lt->w[P.light_index] / inf_sum) * env_pdf_spherical(e, theta, phi);
+    }
+    *radiance = tot;
+    if (pdf) *pdf = ptot;
 }
 // Rust slice::binary_search_by(partial_cmp) then clamp (environment_light.rs:218-223).  On a non-decreasing CDF the
 // reference's probing sequence ends at base = (#entries <= u) - 1 (or 0), so with k = #{i : cdf[i] <= u} the result is

@@ -179,14 +179,18 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     if constexpr (miss) {
         if (sc.n_envs != 0) {
             if (stage == 0) {
-                con = con + thr * scene_env_radiance(sc, ray_d, wl);  // base_renderer.rs:180-186
+                S4 radiance;
+                scene_env_radiance_pdf(sc, nullptr, ray_d, wl, &radiance, nullptr);
+                con = con + thr * radiance;  // base_renderer.rs:180-186
             } else if (integrator != TCPT_INTEGRATOR_NEE) {
                 const S4 fprev = s4(st.fprev[slot]);
-                const S4 radiance = scene_env_radiance(sc, ray_d, wl);
                 if (integrator == TCPT_INTEGRATOR_PT) {
+                    S4 radiance;
+                    scene_env_radiance_pdf(sc, nullptr, ray_d, wl, &radiance, nullptr);
                     con = con + thr * fprev * radiance / pdf_prev;  // pt_renderer.rs:80-81
                 } else {
-                    const float light_pdf = scene_env_pdf(sc, lights(), ray_d);
+                    S4 radiance; float light_pdf;
+                    scene_env_radiance_pdf(sc, &lights(), ray_d, wl, &radiance, &light_pdf);
                     const float a = pdf_prev, b = light_pdf;
                     const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
                     const float tf = 1.0f / pdf_prev;
@@ -249,7 +253,9 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     if (MT == TCPT_MAT_LAMBERT) smp.skip_1d(); else uc = smp.get_1d();
     const float2 uv = smp.get_2d();
     const bool was_terminated = wl.terminated;
-    const MatSample ms = material_sample<MT>(mc, mat, uc, uv, wl, wo, ng_t, hit.uv);
+    NmFrame nmf;
+    material_frame(sc, mat, hit.uv, nmf);
+    const MatSample ms = material_sample<MT>(mc, mat, nmf, uc, uv, wl, wo, ng_t, hit.uv);
     if (wl.terminated != was_terminated) lt_ready = false;  // a dispersive material collapsed the wavelengths: light powers change
 
     if (!ms.is_specular() && integrator != TCPT_INTEGRATOR_PT) {
@@ -284,11 +290,13 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
                 const float theta = ev * TCPT_PI, phi = eu * 2.0f * TCPT_PI;
                 const float3 wl_local = f3(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));
                 const float3 wi_r = xf_vector(LP.l2r, wl_local);
-                const float pdf_dir = env_direction_pdf(sc, LP, wi_r);
-                const S4 radiance = env_direction_radiance(sc, LP, wi_r, wl);
+                float th_l, ph_l;
+                direction_to_spherical(xf_vector(LP.r2l, wi_r), &th_l, &ph_l);
+                const float pdf_dir = env_pdf_spherical(e, th_l, ph_l);
+                const S4 radiance = env_radiance_spherical(sc, e, th_l, ph_l, wl);
                 const float3 wi = m3_vector(r2t, wi_r);
                 S4 f; float bpdf;
-                material_eval_pdf<MT>(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
+                material_eval_pdf<MT>(mc, mat, nmf, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
                 const float w = with_mis ? ((pdf_dir == 0.0f && bpdf == 0.0f) ? 0.0f : pdf_dir / (pdf_dir + bpdf)) : 1.0f;
                 const S4 c = f * radiance / (pdf_dir * p_light);
                 pending = with_mis ? thr * c * w : thr * c;
@@ -324,7 +332,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
                 const float pdf_dir = pdf_area * (distance * distance) / rmax(fabsf(dot(lnormal, -wi_r)), 1e-8f);
                 const float3 wi = m3_vector(r2t, wi_r);
                 S4 f; float bpdf;
-                material_eval_pdf<MT>(mc, mat, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
+                material_eval_pdf<MT>(mc, mat, nmf, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
                 const float distance2 = length_squared(dv);
                 const float3 ln_t = m3_normal_by_inverse(t2r, lnormal);
                 const float cos_light = fabsf(dot(ln_t, -wi));
