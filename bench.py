@@ -43,7 +43,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="scene19_4k", choices=sorted(WORKLOADS))
@@ -56,13 +56,40 @@ def parse():
 
 # ---------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML from a thread every 10 ms
+    (ctypes calls into libtcpt release the GIL), nvidia-smi polling as a fallback when pynvml is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.stop = index, [], None, None, False
+        self.sm, self.sm_max, self.reasons = [], None, set()
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop:
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.reasons |= {k for k, b in bits.items() if r & b}
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it holds plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -77,6 +104,7 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
@@ -84,13 +112,17 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif self.thread:
+            self.thread.join(timeout=1)
 
     def summary(self):
+        if self.sm:
+            return {"sm_mhz": int(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------- shared setup
@@ -205,7 +237,10 @@ def main_gpu(args, wl):
     image = tp.RendererImage(W, H, renderer)
     acc = torch.zeros((H, W, 3), dtype=torch.float32, device=f"cuda:{local}")
     frame = torch.zeros_like(acc) if rank == 0 else None
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: libtcpt launches on the handle it is given, NCCL and the torch events use the same stream,
+    # so the CUDA events bracket exactly the kernels of the timed steps
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
 
     def step(k, timing=False):
         # step k of the job: `world * S` fresh sample indices of the frame, rank r takes its S of them (spp-pass sharding)
@@ -296,6 +331,12 @@ def main_gpu(args, wl):
     closest_s = tot["closest_ms"] * 1e-3
     bytes_per_ray = 48.0  # 32 B ray read + 16 B hit write (compulsory wavefront traffic; the BVH is L2 resident)
     achieved = bytes_per_ray * tot["closest"] / closest_s / 1e9 if closest_s > 0 else 0.0
+    traffic = None
+    try:  # measured DRAM traffic of the same kernel from the committed ncu capture, scaled to this run's rays per launch
+        tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["k_trace_closest"]
+        traffic = tr["dram_bytes"] / tr["rays"] * (tot["closest"] / n_closest_launches)
+    except Exception:
+        pass
     clk_s = clk.summary()
     sm_mhz = clk_s["sm_mhz"] or 1965
     flops_per_ray = 18.0 * box_per_ray + 64.0 * tri_per_ray + 60.0
@@ -311,7 +352,7 @@ def main_gpu(args, wl):
                 "call": "RendererImage.render -> tcpt_render(params, host sRGB frame out)"},
         "gpu_launches": int(launches_all),
         "clocks": clk_s,
-        "roofline": {"kernel": "k_trace_closest", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+        "roofline": {"kernel": "k_trace_closest", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "rays_per_launch": tot["closest"] / n_closest_launches,
                      "avg_launch_ms": tot["closest_ms"] / n_closest_launches, "share_of_step": tot["closest_ms"] / stage_sum if stage_sum else None,
                      "note": "BVH+textures are L2 resident: the path is FP32-issue/latency bound, see roofline_fp32"},

@@ -19,6 +19,7 @@ import toy_cpu_pathtracing_b200 as tp  # noqa: E402
 from toy_cpu_pathtracing_b200 import assets, scenes  # noqa: E402
 
 W, H = 1920, 1080
+STREAM = None
 
 
 def primaries():
@@ -41,7 +42,8 @@ def pack(o, d, tmax):
 
 def trace(ctx, rays, n, any_hit=False, reps=5):
     hits = torch.empty(n * 24, dtype=torch.uint8, device="cuda")
-    s = torch.cuda.current_stream()
+    s = STREAM   # a real (non-default) stream: libtcpt launches on the handle it is given, so the events bracket the kernel
+    torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -54,6 +56,8 @@ def trace(ctx, rays, n, any_hit=False, reps=5):
 
 
 def main():
+    global STREAM
+    STREAM = torch.cuda.Stream()
     for n_tri in [int(a) for a in sys.argv[1:]] or [1_000_000]:
         scene = tp.Scene(device=0)
         scene.ctx.set_option("binned_builder", 1)

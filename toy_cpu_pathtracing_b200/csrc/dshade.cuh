@@ -373,14 +373,39 @@ struct Schlick {
             for (int i = 0; i < 64; ++i) sum = sum + term;
             return sum / 64.0f;
         }
+        // rough coat: 64 calls of sample(wo, uv) (generalized_schlick.rs:893-918 -> :419-458).  Everything that only depends on
+        // wo -- the stretched direction and its frame in sample_wm, Lambda(wo) inside G1 and G, |wo.z| -- is evaluated once;
+        // D(wm), which sample() evaluates inside Dvis and again for f, is evaluated once per sample.  Same expressions in the
+        // same order as Ggx::sample_wm / Dvis / G, so every term has the bits of the straightforward loop.
+        if (wo.z == 0.0f) return sum / 64.0f;
+        float3 wh = normalize(f3(g.ax * wo.x, g.ay * wo.y, wo.z));
+        if (wh.z < 0.0f) wh = -wh;
+        const float3 t1 = wh.z < 0.99999f ? normalize(cross(f3(0, 0, 1), wh)) : f3(1, 0, 0);
+        const float3 t2 = cross(wh, t1);
+        const float lf = (1.0f + wh.z) / 2.0f;
+        const float lam_o = g.lambda(wo), g1_o = 1.0f / (1.0f + lam_o), co = fabsf(wo.z);
         for (int i = 0; i < 64; ++i) {
             rng.next();  // uc (unused by the R-mode sampler, but drawn by the reference)
             float2 uv; uv.x = rng.next(); uv.y = rng.next();
-            BsdfSample s;
-            if (sample(wo, uv, &s)) {
-                const float ci = fabsf(s.wi.z);
-                if (ci > 0.0f && s.pdf > 0.0f) sum = sum + s.f * ci / s.pdf;
-            }
+            const float2 p = sample_uniform_disk_polar(uv);
+            const float h = sqrtf(rmax(1.0f - p.x * p.x, 0.0f));
+            const float py = h * (1.0f - lf) + p.y * lf;
+            const float pz = sqrtf(rmax(1.0f - p.x * p.x - py * py, 0.0f));
+            const float3 nh = (t1 * p.x + t2 * py) + wh * pz;
+            const float3 wm = normalize(f3(g.ax * nh.x, g.ay * nh.y, rmax(1e-6f, nh.z)));
+            const float cd = fabsf(dot(wo, wm));
+            const S4 fr = fresnel_at(cd);
+            const float3 wi = reflect(wo, wm);
+            if (!same_hemisphere(wo, wi)) continue;
+            if (cd < 1e-6f) continue;
+            const float d = g.D(wm);
+            const float dvis = co == 0.0f ? 0.0f : g1_o / co * d * cd;
+            const float pdf = dvis / (4.0f * cd) * 1.0f;
+            const float gg = 1.0f / (1.0f + lam_o + g.lambda(wi));
+            const float ci = fabsf(wi.z);
+            if (ci == 0.0f || co == 0.0f) continue;
+            const S4 f = fr * d * gg / (4.0f * co);
+            if (ci > 0.0f && pdf > 0.0f) sum = sum + f * ci / pdf;
         }
         return sum / 64.0f;
     }

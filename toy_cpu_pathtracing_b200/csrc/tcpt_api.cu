@@ -573,8 +573,15 @@ int tcpt_trace_device(tcpt_ctx* ctx, const void* dev_rays, int n, int any_hit, v
     const int grid = grid_for(ctx, (uint64_t)n, 128);
     uint32_t* work = ctx->d_counters + 26;  // work counter of the persistent trace loop
     CU(cudaMemsetAsync(work, 0, sizeof(uint32_t), s));
-    if (ctx->opt.count_tests) k_trace_rays<true><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, ctx->d_stats, work);
-    else k_trace_rays<false><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, nullptr, work);
+    if (ctx->opt.count_tests) {
+        // counting mode is synchronous: the box / triangle test totals of this call are readable through tcpt_get_stats afterwards
+        CU(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), s));
+        k_trace_rays<true><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, ctx->d_stats, work);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+        return fetch_stats(ctx);
+    }
+    k_trace_rays<false><<<grid, 128, 0, s>>>(ctx->dev.view, q_o, q_d, (uint32_t)n, any_hit, h0, h1, nullptr, work);
     CU(cudaGetLastError());
     return TCPT_OK;
 }
