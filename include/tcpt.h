@@ -39,7 +39,9 @@ enum {
     TCPT_MAT_EMISSIVE = 1,      /* EmissiveMaterial::new(radiance, intensity)                   emissive_material.rs:15-37 */
     TCPT_MAT_PLASTIC = 2,       /* PlasticMaterial::new(eta, color, normal, thin, roughness)    plastic_material.rs:17-52 */
     TCPT_MAT_SIMPLE_PBR = 3,    /* SimplePbrMaterial::new(base, metallic, roughness, normal, ior) simple_pbr_material.rs:38-53 */
-    TCPT_MAT_CLEARCOAT_PBR = 4  /* SimpleClearcoatPbrMaterial::new(...)                          simple_pbr_clearcoat_material.rs:17-73 */
+    TCPT_MAT_CLEARCOAT_PBR = 4, /* SimpleClearcoatPbrMaterial::new(...)                          simple_pbr_clearcoat_material.rs:17-73 */
+    TCPT_MAT_METAL = 5,         /* MetalMaterial::new(metal_type, normal, roughness): color = eta preset, coat_tint = k preset   metal_material.rs:39-110 */
+    TCPT_MAT_GLASS = 6          /* GlassMaterial::new(glass_type, normal, thin_surface, roughness): color = eta preset          glass_material.rs:49-86 */
 };
 /* SpectrumParameter (material/parameter.rs:13-21) over the Spectrum kinds that reach the hot path */
 enum {
@@ -47,7 +49,15 @@ enum {
     TCPT_SPEC_RGB_ALBEDO_SRGB = 1, /* RgbAlbedoSpectrum::<ColorSrgb>::new(value)        (gamma-encoded sRGB colour) */
     TCPT_SPEC_RGB_ALBEDO_LINEAR = 2, /* RgbAlbedoSpectrum::<ColorSrgbLinear>::new(value) */
     TCPT_SPEC_D65 = 3,             /* presets::cie_illum_d6500() */
-    TCPT_SPEC_TEXTURE_SRGB = 4     /* SpectrumParameter::texture(RgbTexture::load_srgb, SpectrumType::Albedo) */
+    TCPT_SPEC_TEXTURE_SRGB = 4,    /* SpectrumParameter::texture(RgbTexture::load_srgb, SpectrumType::Albedo) */
+    TCPT_SPEC_PRESET = 5           /* a DenselySampledSpectrum preset of spectrum/src/presets.rs; `texture` holds the TCPT_PRESET_* id */
+};
+/* presets::au_eta() ... presets::glass_sf11_eta() (spectrum/src/presets.rs:336-462), in the order the std_tables blob stores them */
+enum {
+    TCPT_PRESET_AU_ETA = 0, TCPT_PRESET_AU_K, TCPT_PRESET_AG_ETA, TCPT_PRESET_AG_K, TCPT_PRESET_CU_ETA, TCPT_PRESET_CU_K,
+    TCPT_PRESET_AL_ETA, TCPT_PRESET_AL_K, TCPT_PRESET_CU_ZN_ETA, TCPT_PRESET_CU_ZN_K,
+    TCPT_PRESET_GLASS_BK7, TCPT_PRESET_GLASS_BAF10, TCPT_PRESET_GLASS_FK51A, TCPT_PRESET_GLASS_LASF9, TCPT_PRESET_GLASS_SF5,
+    TCPT_PRESET_GLASS_SF10, TCPT_PRESET_GLASS_SF11, TCPT_PRESET_COUNT
 };
 typedef struct { int32_t kind; float value[3]; int32_t texture; } tcpt_spectrum_param;
 typedef struct { int32_t kind; /* 0 constant, 1 gray8 FloatTexture */ float value; int32_t texture; int32_t gamma_corrected; } tcpt_float_param;
@@ -99,7 +109,8 @@ const char* tcpt_last_error(const tcpt_ctx* ctx);
  * "binned_builder" (fast non-reference BVH for synthetic soups), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
  * buffers on first use and keeps them registered while the same pointers are passed; 0: releases them — set 0 before freeing) */
 int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
-/* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65: spectrum/src/presets.rs);
+/* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65 and the metal / glass presets:
+ * spectrum/src/presets.rs; layout in tools/extract_reference_tables.py);
  * rgb2spec = rgb_to_spec table, 64 z-nodes + [3][64][64][64][3] f32 (spectrum/src/rgb_sigmoid_polynomial.rs:35-84) */
 int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_floats);
 

@@ -56,7 +56,7 @@ typedef struct {
     int32_t env;
 } tcpt_flat_primitive;
 
-typedef struct { int32_t kind; float c[3]; float scale; int32_t texture; } tcpt_flat_spectrum; /* kind: 0 const(c[0]) 1 sigmoid(c) 2 sigmoid*scale*D65 3 D65 4 texture */
+typedef struct { int32_t kind; float c[3]; float scale; int32_t texture; } tcpt_flat_spectrum; /* kind: 0 const(c[0]) 1 sigmoid(c) 2 sigmoid*scale*D65 3 D65 4 texture 5 dense preset table (texture = preset id) */
 typedef struct { int32_t is_texture; float value; int32_t texture; int32_t gamma_corrected; } tcpt_flat_float;
 typedef struct {
     int32_t type;

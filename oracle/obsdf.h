@@ -69,7 +69,7 @@ struct NormalParam {
     bool flip_y = false;
 };
 
-enum MaterialType : int { MAT_LAMBERT = 0, MAT_EMISSIVE = 1, MAT_PLASTIC = 2, MAT_SIMPLE_PBR = 3, MAT_CLEARCOAT_PBR = 4 };
+enum MaterialType : int { MAT_LAMBERT = 0, MAT_EMISSIVE = 1, MAT_PLASTIC = 2, MAT_SIMPLE_PBR = 3, MAT_CLEARCOAT_PBR = 4, MAT_METAL = 5, MAT_GLASS = 6 };
 enum SampleType : int { ST_DIFFUSE = 0, ST_SPECULAR_REFLECTION = 1, ST_SPECULAR_TRANSMISSION = 2, ST_GLOSSY_REFLECTION = 3, ST_GLOSSY_TRANSMISSION = 4 };
 
 struct BsdfSample {
@@ -422,6 +422,86 @@ struct GeneralizedSchlickBsdf {
     }
 };
 
+// ---------------------------------------------------------------- bsdf/conductor.rs
+struct Complex {
+    float re, im;
+    float norm() const { return re * re + im * im; }
+    Complex sqrt() const {  // conductor.rs:30-36: polar form
+        float r = std::sqrt(re * re + im * im);
+        float theta = std::atan2(im, re);
+        float sr = std::sqrt(r), ht = theta * 0.5f;
+        return Complex{sr * std::cos(ht), sr * std::sin(ht)};
+    }
+};
+inline Complex operator+(Complex a, Complex b) { return {a.re + b.re, a.im + b.im}; }
+inline Complex operator-(Complex a, Complex b) { return {a.re - b.re, a.im - b.im}; }
+inline Complex operator*(Complex a, Complex b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+inline Complex operator*(Complex a, float s) { return {a.re * s, a.im * s}; }
+inline Complex operator/(Complex a, Complex b) {
+    float denom = b.re * b.re + b.im * b.im;
+    if (denom == 0.0f) return {0.0f, 0.0f};
+    return {(a.re * b.re + a.im * b.im) / denom, (a.im * b.re - a.re * b.im) / denom};
+}
+// fresnel_complex (conductor.rs:91-123)
+inline SampledSpectrum fresnel_complex(float cos_theta_i, const SampledSpectrum& eta, const SampledSpectrum& k) {
+    cos_theta_i = clampf(cos_theta_i, 0.0f, 1.0f);
+    SampledSpectrum r;
+    for (int i = 0; i < NS; ++i) {
+        Complex ce{eta.v[i], k.v[i]};
+        float sin2_i = 1.0f - cos_theta_i * cos_theta_i;
+        Complex sin2_t = Complex{sin2_i, 0.0f} / (ce * ce);
+        Complex cos_t = (Complex{1.0f, 0.0f} - sin2_t).sqrt();
+        Complex r_parl = (ce * cos_theta_i - cos_t) / (ce * cos_theta_i + cos_t);
+        Complex r_perp = (Complex{cos_theta_i, 0.0f} - ce * cos_t) / (Complex{cos_theta_i, 0.0f} + ce * cos_t);
+        r.v[i] = (r_parl.norm() + r_perp.norm()) * 0.5f;
+    }
+    return r;
+}
+struct ConductorBsdf {  // conductor.rs:125-439; the GGX helpers are the same functions as dielectric.rs / generalized_schlick.rs
+    SampledSpectrum eta, k;
+    Ggx g;
+    SampledSpectrum torrance_sparrow(Vec3 wo, Vec3 wi, Vec3 wm) const {
+        float co = std::fabs(wo.z), ci = std::fabs(wi.z);
+        if (co == 0.0f || ci == 0.0f) return SampledSpectrum::zero();
+        SampledSpectrum fr = fresnel_complex(std::fabs(dot(wo, wm)), eta, k);
+        float d = g.D(wm), gg = g.G(wo, wi);
+        return fr * d * gg / (4.0f * co);
+    }
+    float pdf_microfacet(Vec3 wo, Vec3 wi) const {
+        if (!same_hemisphere(wo, wi)) return 0.0f;
+        Vec3 wm;
+        if (!half_vector(wo, wi, &wm)) return 0.0f;
+        float vis = g.Dvis(wo, wm);
+        float jac = 4.0f * std::fabs(dot(wo, wm));
+        if (jac == 0.0f) return 0.0f;
+        return vis / jac;
+    }
+    bool sample(Vec3 wo, Vec2 uv, BsdfSample* out) const {
+        if (wo.z == 0.0f) return false;
+        if (g.effectively_smooth()) {
+            Vec3 wi(-wo.x, -wo.y, wo.z);
+            if (wi.z == 0.0f) return false;
+            *out = BsdfSample{fresnel_complex(std::fabs(wi.z), eta, k), wi, 1.0f, ST_SPECULAR_REFLECTION};
+            return true;
+        }
+        Vec3 wm = g.sample_wm(wo, uv);
+        Vec3 wi = reflect(wo, wm);
+        if (!same_hemisphere(wo, wi)) return false;
+        *out = BsdfSample{torrance_sparrow(wo, wi, wm), wi, pdf_microfacet(wo, wi), ST_GLOSSY_REFLECTION};
+        return true;
+    }
+    SampledSpectrum evaluate(Vec3 wo, Vec3 wi) const {
+        if (g.effectively_smooth()) return SampledSpectrum::zero();
+        float co = std::fabs(wo.z), ci = std::fabs(wi.z);
+        if (co == 0.0f || ci == 0.0f) return SampledSpectrum::zero();
+        if (!same_hemisphere(wo, wi)) return SampledSpectrum::zero();
+        Vec3 wm;
+        if (!half_vector(wo, wi, &wm)) return SampledSpectrum::zero();
+        return torrance_sparrow(wo, wi, wm);
+    }
+    float pdf(Vec3 wo, Vec3 wi) const { return g.effectively_smooth() ? 0.0f : pdf_microfacet(wo, wi); }
+};
+
 // ---------------------------------------------------------------- math/src/transform.rs:216-244
 struct NormalMapFrame {
     Mat4 to_nm, from_nm;
@@ -605,6 +685,26 @@ inline MaterialSample material_sample(const MaterialContext& c, const Material& 
             PbrBase b = load_pbr_base(c, m, sp.uv, wl);
             return b.sample(wo_nm, uc, uv, fr.from_nm);
         }
+        case MAT_METAL: {  // metal_material.rs:122-173: eta/k presets in `color` / `coat_tint`, alpha = roughness^2
+            SampledSpectrum eta = m.color.spectrum.sample(*c.T, wl), k = m.coat_tint.spectrum.sample(*c.T, wl);
+            float rough = sample_float_param(c, m.roughness, sp.uv);
+            float alpha = rough * rough;
+            ConductorBsdf cb{eta, k, Ggx{alpha, alpha}};
+            BsdfSample s;
+            if (!cb.sample(wo_nm, uv, &s)) return MaterialSample{};
+            Vec3 wi_sh = transform_vector3(fr.from_nm, s.wi);
+            if (signum(dot(sp.normal, wi_sh)) != signum(dot(sp.normal, wo))) return MaterialSample{};
+            return make_sample(s.f, wi_sh, s.pdf, s.sample_type);
+        }
+        case MAT_GLASS: {  // glass_material.rs:97-147: DielectricBsdf with the glass's eta(lambda), roughness passed unsquared
+            SampledSpectrum eta = m.color.spectrum.sample(*c.T, wl);
+            float rough = sample_float_param(c, m.roughness, sp.uv);
+            bool entering = dot(sp.normal, wo) > 0.0f;
+            DielectricBsdf d(eta, entering, m.thin_surface, rough, rough);
+            BsdfSample s;
+            if (!d.sample(wo_nm, uv, uc, wl, &s)) return MaterialSample{};
+            return make_sample(s.f, transform_vector3(fr.from_nm, s.wi), s.pdf, s.sample_type);
+        }
         case MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:121-250
             PbrBase b = load_pbr_base(c, m, sp.uv, wl);
             ClearcoatParams cp = load_coat(c, m, sp.uv, wl);
@@ -646,6 +746,17 @@ inline SampledSpectrum material_evaluate(const MaterialContext& c, const Materia
             return f;
         }
         case MAT_SIMPLE_PBR: return load_pbr_base(c, m, sp.uv, wl).evaluate(wo_nm, wi_nm);
+        case MAT_METAL: {  // metal_material.rs:175-213
+            if (signum(dot(sp.normal, wi)) != signum(dot(sp.normal, wo))) return SampledSpectrum::zero();
+            float rough = sample_float_param(c, m.roughness, sp.uv);
+            float alpha = rough * rough;
+            return ConductorBsdf{m.color.spectrum.sample(*c.T, wl), m.coat_tint.spectrum.sample(*c.T, wl), Ggx{alpha, alpha}}.evaluate(wo_nm, wi_nm);
+        }
+        case MAT_GLASS: {  // glass_material.rs:149-185
+            float rough = sample_float_param(c, m.roughness, sp.uv);
+            bool entering = dot(sp.normal, wo) > 0.0f;
+            return DielectricBsdf(m.color.spectrum.sample(*c.T, wl), entering, m.thin_surface, rough, rough).evaluate(wo_nm, wi_nm);
+        }
         case MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:252-353
             PbrBase b = load_pbr_base(c, m, sp.uv, wl);
             ClearcoatParams cp = load_coat(c, m, sp.uv, wl);
@@ -675,6 +786,17 @@ inline float material_pdf(const MaterialContext& c, const Material& m, const Sam
             return DielectricBsdf(SampledSpectrum::constant(m.eta), entering, m.thin_surface, rough, rough).pdf(wo_nm, wi_nm);
         }
         case MAT_SIMPLE_PBR: return load_pbr_base(c, m, sp.uv, wl).pdf(wo_nm, wi_nm);
+        case MAT_METAL: {  // metal_material.rs:215-252
+            if (signum(dot(sp.normal, wi)) != signum(dot(sp.normal, wo))) return 0.0f;
+            float rough = sample_float_param(c, m.roughness, sp.uv);
+            float alpha = rough * rough;
+            return ConductorBsdf{m.color.spectrum.sample(*c.T, wl), m.coat_tint.spectrum.sample(*c.T, wl), Ggx{alpha, alpha}}.pdf(wo_nm, wi_nm);
+        }
+        case MAT_GLASS: {  // glass_material.rs:187-221
+            float rough = sample_float_param(c, m.roughness, sp.uv);
+            bool entering = dot(sp.normal, wo) > 0.0f;
+            return DielectricBsdf(m.color.spectrum.sample(*c.T, wl), entering, m.thin_surface, rough, rough).pdf(wo_nm, wi_nm);
+        }
         case MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:355-433
             PbrBase b = load_pbr_base(c, m, sp.uv, wl);
             ClearcoatParams cp = load_coat(c, m, sp.uv, wl);

@@ -52,7 +52,10 @@ void orc_scene_free(void* h) { delete (OrcScene*)h; }
 // std_tables = contents of data/std_tables.bin; rgb2spec = contents of data/srgb_table.bin (64 z nodes + table)
 int orc_set_tables(void* h, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_len) {
     OrcScene* s = (OrcScene*)h;
-    if (std_len != 8 + 104 * 4 + 4 * N_DENSE * 4 || std::memcmp(std_tables, "TCPTSTD1", 8)) return -1;
+    const size_t base_len = 8 + 104 * 4 + 4 * N_DENSE * 4;
+    const bool v1 = std_len == base_len && !std::memcmp(std_tables, "TCPTSTD1", 8);
+    const bool v2 = std_len >= base_len + 4 && !std::memcmp(std_tables, "TCPTSTD2", 8);
+    if (!v1 && !v2) return -1;
     if (rgb2spec_len != 64 + (size_t)3 * 64 * 64 * 64 * 3) return -2;
     Tables& T = s->scene.T;
     const uint8_t* p = (const uint8_t*)std_tables + 8;
@@ -60,7 +63,14 @@ int orc_set_tables(void* h, const void* std_tables, size_t std_len, const float*
     std::memcpy(T.cie_x, p, N_DENSE * 4); p += N_DENSE * 4;
     std::memcpy(T.cie_y, p, N_DENSE * 4); p += N_DENSE * 4;
     std::memcpy(T.cie_z, p, N_DENSE * 4); p += N_DENSE * 4;
-    std::memcpy(T.d65, p, N_DENSE * 4);
+    std::memcpy(T.d65, p, N_DENSE * 4); p += N_DENSE * 4;
+    T.presets.clear();
+    if (v2) {
+        uint32_t n; std::memcpy(&n, p, 4); p += 4;
+        if (std_len != base_len + 4 + (size_t)n * N_DENSE * 4) return -1;
+        T.presets.resize((size_t)n * N_DENSE);
+        std::memcpy(T.presets.data(), p, T.presets.size() * 4);
+    }
     s->rgb2spec.assign(rgb2spec, rgb2spec + rgb2spec_len);
     std::memcpy(T.z_nodes, s->rgb2spec.data(), 64 * 4);
     T.rgb2spec = s->rgb2spec.data() + 64;
@@ -97,6 +107,7 @@ static SpectrumParam conv_spec(const Tables& T, const orc_spectrum_param& p) {
         case 2: r.spectrum = make_rgb_albedo(T, Vec3(p.value[0], p.value[1], p.value[2]), false); break;
         case 3: r.spectrum.kind = SPEC_D65; break;
         case 4: r.is_texture = true; r.texture = p.texture; break;
+        case 5: r.spectrum.kind = SPEC_PRESET; r.spectrum.table = p.texture; break;
     }
     return r;
 }

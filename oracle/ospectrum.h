@@ -105,6 +105,7 @@ struct Tables {
     float d65_max = 0.0f;
     float z_nodes[64];
     const float* rgb2spec = nullptr;  // [3][64][64][64][3]
+    std::vector<float> presets;       // n x 470: metal eta/k and glass eta tables, densely resampled (presets.rs:129-200)
     Mat3 xyz_to_rgb, rgb_to_xyz;
 };
 
@@ -156,12 +157,13 @@ inline bool rgb_to_coeffs(const Tables& T, Vec3 rgb_in, bool gamma_encoded, floa
 }
 
 // Tagged union over the Spectrum kinds that reach the hot path.
-enum SpectrumKind : int { SPEC_CONSTANT = 0, SPEC_RGB_ALBEDO = 1, SPEC_RGB_ILLUMINANT = 2, SPEC_D65 = 3 };
+enum SpectrumKind : int { SPEC_CONSTANT = 0, SPEC_RGB_ALBEDO = 1, SPEC_RGB_ILLUMINANT = 2, SPEC_D65 = 3, SPEC_PRESET = 5 };
 struct Spectrum {
     int kind = SPEC_CONSTANT;
     float c = 0.0f;                      // constant
     float coef[3] = {0, 0, 0};           // sigmoid polynomial
     float scale = 1.0f;                  // illuminant
+    int table = 0;                       // SPEC_PRESET: index of a DenselySampledSpectrum preset (presets::au_eta() ...)
     // SpectrumTrait::value
     float value(const Tables& T, float lambda) const {
         switch (kind) {
@@ -174,6 +176,7 @@ struct Spectrum {
                 float t = (lambda - LAMBDA_MIN) / (LAMBDA_MAX - LAMBDA_MIN);
                 return scale * sigmoid(parabolic(t, coef)) * dense_value(T.d65, lambda);  // rgb_illuminant_spectrum.rs:43-45
             }
+            case SPEC_PRESET: return dense_value(T.presets.data() + (size_t)table * N_DENSE, lambda);
             default: return dense_value(T.d65, lambda);
         }
     }

@@ -18,7 +18,7 @@ def recorded_rays(b, integrator, sampler, spp, window):
     return rays, shadow
 
 
-@pytest.mark.parametrize("scene_id,kw", [(3, {}), (10, {}), (17, {}), (19, {})])
+@pytest.mark.parametrize("scene_id,kw", [(3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
 def test_hit_records_bit_exact_on_path_rays(bundle_factory, scene_id, kw):
     """Every ray a MIS render issues inside a pixel window (camera, bounce and shadow rays, incl. the non-identity instance of
     scene 17 and the three instances of scene 19): closest hits and any-hits must equal the oracle's exhaustive traversal."""
@@ -74,7 +74,10 @@ def test_hit_records_soup_random_rays(bundle_factory):
 
 
 CASES = [(3, {}, "pt"), (3, {}, "nee"), (3, {}, "mis"), (10, {}, "pt"), (10, {}, "nee"), (10, {}, "mis"),
-         (17, {}, "mis"), (17, {"coat": False}, "mis"), (19, {}, "pt"), (19, {}, "mis")]
+         (17, {}, "mis"), (17, {"coat": False}, "mis"), (19, {}, "pt"), (19, {}, "mis"),
+         # MetalMaterial / ConductorBsdf (scene 6 smooth, scene 7 rough + scaled instances), GlassMaterial with a
+         # dispersive eta -> terminate_secondary (scene 8), solid plastic (scene 9)
+         (6, {}, "pt"), (6, {}, "mis"), (7, {}, "nee"), (7, {}, "mis"), (8, {}, "pt"), (8, {}, "nee"), (8, {}, "mis"), (9, {}, "mis")]
 
 
 @pytest.mark.parametrize("sampler", ["sobol", "random"])
@@ -82,7 +85,16 @@ CASES = [(3, {}, "pt"), (3, {}, "nee"), (3, {}, "mis"), (10, {}, "pt"), (10, {},
 def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler):
     """Same scene, integrator, sampler, resolution and spp on both sides: identical ray counts (every path takes the same
     decisions) and a film within the stated tolerance."""
+    # Scene 9 (solid constant-eta plastic) sits on a knife edge of the reference algorithm: a specular reflection has
+    # f / pdf = R / (R / (R + (1 - R))), which rounds to exactly 1.0 or to 1 - 2^-24 depending on the last bits of R, and Russian
+    # roulette draws a sampler dimension only when max(throughput) < 1 (base_renderer.rs:76-92).  A one-ulp difference in an
+    # upstream sinf/cosf (CUDA vs glibc) therefore shifts every later Sobol dimension of about 0.1 % of the paths -- both
+    # versions are valid paths of the same estimator, but they are different paths.  The oracle shows the same against itself
+    # when 1/16 of its Lambert sin/cos results are moved by one ulp (MRE 3e-4; scenes 3, 6, 8, 10: < 1e-7).  With q = 1e-3
+    # diverged paths the mean ABSOLUTE error stays near q until spp >> 1/q, so this case gets its own bound; the per-path
+    # test below checks that the other 99.9 % agree to the stated tolerance.
     w, h, spp = 64, 48, 32
+    mre_tol = 5e-3 if scene_id == 9 else MRE_TOL
     b = bundle_factory(scene_id, w, h, **kw)
     img = b.image(integrator, spp).render(sampler)
     acc, srgb, st = b.oracle.render(b.oparams(integrator, sampler, spp))
@@ -94,14 +106,17 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
     g, o = img.accumulators / spp, acc / spp
     assert np.isfinite(g).all()
     mre = np.abs(g - o).mean() / np.abs(o).mean()
-    assert mre <= MRE_TOL, f"mean relative error {mre:.3e}"
+    assert mre <= mre_tol, f"mean relative error {mre:.3e}"
     # tone-mapped output: a single path that branches differently (last-ulp transcendental at a threshold) can move one pixel of
     # a high-variance pt frame visibly, so the bound is on the 99.9th percentile and the mean, not the maximum
     d = np.abs(img.pixels - srgb)
-    assert np.quantile(d, 0.999) <= 2e-2 and d.mean() <= 1e-4
+    if scene_id == 9:   # about 1.5 % of the pixels hold one diverged path at 32 spp (see above): bound the bulk, not the tail
+        assert np.quantile(d, 0.97) <= 1e-3 and d.mean() <= 2e-3
+    else:
+        assert np.quantile(d, 0.999) <= 2e-2 and d.mean() <= 1e-4
 
 
-@pytest.mark.parametrize("scene_id,integrator,sampler", [(3, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
+@pytest.mark.parametrize("scene_id,integrator,sampler", [(3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
 def test_individual_paths_match_oracle(bundle_factory, scene_id, integrator, sampler):
     """Per-(pixel, sample) sensor contributions: the overwhelming majority identical to the last bits, the rest within 1e-4."""
     w, h, spp = 64, 48, 64
@@ -114,7 +129,7 @@ def test_individual_paths_match_oracle(bundle_factory, scene_id, integrator, sam
     o = b.oracle.path_samples(b.oparams(integrator, sampler, spp), xy, si)
     err = np.abs(g - o).max(1)
     rel = err / (np.abs(o).max(1) + 1e-6)
-    assert (rel > 1e-4).mean() <= 2e-3, f"{(rel > 1e-4).sum()} of {n} paths differ by more than 1e-4"
+    assert (rel > 1e-4).mean() <= (5e-3 if scene_id == 9 else 2e-3), f"{(rel > 1e-4).sum()} of {n} paths differ by more than 1e-4"
     assert (err == 0).mean() >= (0.4 if scene_id == 19 else 0.8)
 
 

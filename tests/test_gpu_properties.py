@@ -67,7 +67,7 @@ def median3(img):
     return np.median(stack, 0)
 
 
-@pytest.mark.parametrize("scene_id", [3])
+@pytest.mark.parametrize("scene_id", [3, 7])
 def test_cross_integrator_consistency_like_the_reference(bundle_factory, scene_id):
     """renderer/tests/renderer_consistency_test.rs:319-353: pt vs nee and pt vs mis, random sampler, 2048 spp, 200x150, u8
     images, 3x3 median, RMSE in gamma-2.2-linearised space <= 0.013."""
@@ -79,3 +79,12 @@ def test_cross_integrator_consistency_like_the_reference(bundle_factory, scene_i
     for other in ("nee", "mis"):
         rmse = np.sqrt(np.mean((imgs["pt"] - imgs[other]) ** 2))
         assert rmse <= 0.013, f"pt vs {other}: RMSE {rmse:.4f}"
+
+
+def test_cross_integrator_means_with_dispersive_glass(bundle_factory):
+    """Scene 8 (SF11 glass: caustics, hero-wavelength collapse after `terminate_secondary`) is too noisy in pt for the image-level
+    RMSE bound above at 2048 spp, but the three estimators still integrate the same image: per-channel frame means agree."""
+    b = bundle_factory(8, 200, 150)
+    means = {i: b.image(i, 4096).render("random").accumulators.astype(np.float64).mean(axis=(0, 1)) / 4096 for i in ("pt", "nee", "mis")}
+    assert np.allclose(means["nee"], means["mis"], rtol=0.015), means
+    assert np.allclose(means["pt"], means["mis"], rtol=0.015), means

@@ -17,8 +17,12 @@ The dense 470-entry tables are produced with the reference's own float32 arithme
   PiecewiseLinearSpectrum::from_interleaved(normalized=true)     spectrum/src/spectrum/piecewise_linear_spectrum.rs:34-64
   inner_product                                                  spectrum/src/spectrum.rs:67-79
 
+  spectrum/src/presets.rs:2365-2978            metal eta/k and glass eta tables (pbrt-v4 data), interleaved (lambda, value);
+                                               densely resampled like CachedSpectrum::init does (presets.rs:129-200)
+
 File layout (little endian):
-  magic 'TCPTSTD1' | u32 sobol[104] | f32 cie_x[470] | f32 cie_y[470] | f32 cie_z[470] | f32 d65[470]
+  magic 'TCPTSTD2' | u32 sobol[104] | f32 cie_x[470] | f32 cie_y[470] | f32 cie_z[470] | f32 d65[470]
+  | u32 n_presets | f32 preset[n_presets][470]      preset order = PRESETS below (include/tcpt.h TCPT_PRESET_*)
 """
 import re
 import struct
@@ -55,6 +59,10 @@ def dense_from_pwl(lams, vals):
     return np.array([pwl_value(lams, vals, f32(360.0) + f32(i)) for i in range(470)], dtype=f32)
 
 
+PRESETS = ["AU_ETA", "AU_K", "AG_ETA", "AG_K", "CU_ETA", "CU_K", "AL_ETA", "AL_K", "CU_ZN_ETA", "CU_ZN_K",
+           "GLASS_BK7_ETA", "GLASS_BAF10_ETA", "GLASS_FK51A_ETA", "GLASS_LASF9_ETA", "GLASS_SF5_ETA", "GLASS_SF10_ETA", "GLASS_SF11_ETA"]
+
+
 def main():
     sob = rust_array((REF / "renderer/src/sampler/sobol_matrices.rs").read_text(), "SOBOL_MATRICES_32")
     sobol = np.array([int(t, 16) for t in sob[:104]], dtype=np.uint32)
@@ -78,12 +86,20 @@ def main():
     d65 = np.array([f32(pwl_value(dl, dv, f32(360.0) + f32(i)) / y_self) for i in range(470)], dtype=f32)
 
     OUT.parent.mkdir(parents=True, exist_ok=True)
+    presets_dense = []
+    for name in PRESETS:
+        raw = np.array([f32(t) for t in rust_array(presets, name)], dtype=f32)
+        presets_dense.append(dense_from_pwl(raw[0::2].copy(), raw[1::2].copy()))
+
     with open(OUT, "wb") as fh:
-        fh.write(b"TCPTSTD1")
+        fh.write(b"TCPTSTD2")
         fh.write(sobol.astype("<u4").tobytes())
         for k in ("CIE_X", "CIE_Y", "CIE_Z"):
             fh.write(cie[k].astype("<f4").tobytes())
         fh.write(d65.astype("<f4").tobytes())
+        fh.write(struct.pack("<I", len(presets_dense)))
+        for t in presets_dense:
+            fh.write(t.astype("<f4").tobytes())
     print("wrote", OUT, OUT.stat().st_size, "bytes; y_self =", y_self, "sum(Y) =", cie["CIE_Y"].sum())
 
 

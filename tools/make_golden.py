@@ -13,7 +13,8 @@ import toy_cpu_pathtracing_b200 as tp  # noqa: E402
 from toy_cpu_pathtracing_b200 import capi, scenes  # noqa: E402
 from oracle import oracle  # noqa: E402
 
-CASES = [(3, {}, "mis", "sobol"), (10, {}, "nee", "sobol"), (17, {}, "mis", "sobol"), (17, {"coat": False}, "pt", "random"), (19, {}, "mis", "sobol")]
+CASES = [(3, {}, "mis", "sobol"), (10, {}, "nee", "sobol"), (17, {}, "mis", "sobol"), (17, {"coat": False}, "pt", "random"), (19, {}, "mis", "sobol"),
+         (7, {}, "mis", "sobol"), (8, {}, "mis", "sobol")]
 W, H, SPP = 24, 18, 8
 
 

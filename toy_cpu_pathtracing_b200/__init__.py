@@ -8,6 +8,6 @@ from .capi import Context, TcptError  # noqa: F401
 from .renderer import (BoxFilter, Camera, RandomSampler, ReinhardToneMap, RendererArgs, RendererImage, SrgbRendererMis,  # noqa: F401
                        SrgbRendererNee, SrgbRendererPt, ZSobolSampler, RENDERERS)
 from .scene import (ColorSrgb, ColorSrgbLinear, ConstantSpectrum, CreatePrimitiveDesc, EmissiveMaterial, FloatParameter,  # noqa: F401
-                    FloatTexture, LambertMaterial, NormalParameter, NormalTexture, PlasticMaterial, RgbAlbedoSpectrum, RgbTexture,
+                    FloatTexture, GlassMaterial, GlassType, LambertMaterial, MetalMaterial, MetalType, NormalParameter, NormalTexture, PlasticMaterial, RgbAlbedoSpectrum, RgbTexture,
                     Scene, SceneDescription, SimpleClearcoatPbrMaterial, SimplePbrMaterial, SpectrumParameter, SpectrumType,
                     Transform, presets)

@@ -15,8 +15,11 @@ DATA_DIR = PKG_DIR / "data"
 TCPT_OK, TCPT_ERR_INVALID, TCPT_ERR_CUDA, TCPT_ERR_LIMIT, TCPT_ERR_NOMEM = 0, -1, -2, -3, -4
 INTEGRATORS = {"pt": 0, "nee": 1, "mis": 2}
 SAMPLERS = {"random": 0, "sobol": 1}
-MAT_LAMBERT, MAT_EMISSIVE, MAT_PLASTIC, MAT_SIMPLE_PBR, MAT_CLEARCOAT_PBR = range(5)
-SPEC_CONSTANT, SPEC_RGB_ALBEDO_SRGB, SPEC_RGB_ALBEDO_LINEAR, SPEC_D65, SPEC_TEXTURE_SRGB = range(5)
+MAT_LAMBERT, MAT_EMISSIVE, MAT_PLASTIC, MAT_SIMPLE_PBR, MAT_CLEARCOAT_PBR, MAT_METAL, MAT_GLASS = range(7)
+SPEC_CONSTANT, SPEC_RGB_ALBEDO_SRGB, SPEC_RGB_ALBEDO_LINEAR, SPEC_D65, SPEC_TEXTURE_SRGB, SPEC_PRESET = range(6)
+# TCPT_PRESET_* (include/tcpt.h): presets::au_eta() ... presets::glass_sf11_eta() in the order data/std_tables.bin stores them
+PRESETS = ["au_eta", "au_k", "ag_eta", "ag_k", "cu_eta", "cu_k", "al_eta", "al_k", "cu_zn_eta", "cu_zn_k",
+           "glass_bk7_eta", "glass_baf10_eta", "glass_fk51a_eta", "glass_lasf9_eta", "glass_sf5_eta", "glass_sf10_eta", "glass_sf11_eta"]
 
 
 class TcptError(RuntimeError):

@@ -111,6 +111,7 @@ struct DScene {
     const DEnv* envs; uint32_t n_envs;
     const float4* cmf;              // 470 x {x_bar, y_bar, z_bar, d65}  (spectrum/src/presets.rs tables, densely resampled)
     const float* z_nodes; const float* rgb2spec;
+    const float* presets;           // dense metal / glass tables (spectrum/src/presets.rs), n x 470
     float xyz_to_rgb[9];            // column major (color/src/gamut.rs:43-69)
 };
 
@@ -342,10 +343,15 @@ __device__ __noinline__ void rgb_to_coeffs(const DScene& sc, float3 rgb_in, floa
 }
 
 // a resolved Spectrum (SpectrumTrait object) on the device
-struct DSpectrum { int kind; float c[3]; float scale; };  // 0 const 1 sigmoid 2 sigmoid*scale*D65 3 D65
+struct DSpectrum { int kind; float c[3]; float scale; int table; };  // 0 const 1 sigmoid 2 sigmoid*scale*D65 3 D65 5 dense preset table
 __device__ __forceinline__ float spectrum_value(const DScene& sc, const DSpectrum& s, float lambda) {
     if (s.kind == 0) return s.c[0];
     if (s.kind == 3) return cmf_at(sc, lambda).w;
+    if (s.kind == 5) {  // DenselySampledSpectrum::value (densely_sampled_spectrum.rs:57-67)
+        if (!(lambda >= 360.0f && lambda <= 830.0f)) return 0.0f;
+        const uint32_t i = f2u_sat(floorf(lambda - 360.0f));
+        return i < 470u ? __ldg(sc.presets + (size_t)s.table * 470u + i) : 0.0f;
+    }
     const float t = (lambda - 360.0f) / (830.0f - 360.0f);
     const float sg = sigmoidf(t * t * s.c[0] + t * s.c[1] + s.c[2]);
     if (s.kind == 1) return sg;
@@ -360,11 +366,11 @@ __device__ __noinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s,
     return r;
 }
 __device__ __forceinline__ DSpectrum spectrum_from_flat(const tcpt_flat_spectrum& p) {
-    DSpectrum s; s.kind = p.kind; s.c[0] = p.c[0]; s.c[1] = p.c[1]; s.c[2] = p.c[2]; s.scale = p.scale; return s;
+    DSpectrum s; s.kind = p.kind; s.c[0] = p.c[0]; s.c[1] = p.c[1]; s.c[2] = p.c[2]; s.scale = p.scale; s.table = p.texture; return s;
 }
 // RgbIlluminantSpectrum::<ColorSrgb>::new (rgb_illuminant_spectrum.rs:27-40)
 __device__ __forceinline__ DSpectrum illuminant_from_rgb(const DScene& sc, float3 rgb) {
-    DSpectrum s; s.kind = 2;
+    DSpectrum s; s.kind = 2; s.table = 0;
     const float mx = rmax(rgb.x, rmax(rgb.y, rgb.z));
     s.scale = 2.0f * mx;
     rgb_to_coeffs(sc, rgb / s.scale, s.c);
@@ -405,7 +411,7 @@ __device__ __noinline__ float tex_gray(const DTexture& t, float2 uv) {
 
 __device__ __forceinline__ DSpectrum param_spectrum(const DScene& sc, const tcpt_flat_spectrum& p, float2 uv) {
     DSpectrum s;
-    if (p.kind == 4) { s.kind = 1; s.scale = 1.0f; rgb_to_coeffs(sc, tex_rgb(sc.textures[p.texture], uv), s.c); return s; }  // rgb_texture.rs:48-66
+    if (p.kind == 4) { s.kind = 1; s.scale = 1.0f; s.table = 0; rgb_to_coeffs(sc, tex_rgb(sc.textures[p.texture], uv), s.c); return s; }  // rgb_texture.rs:48-66
     return spectrum_from_flat(p);
 }
 __device__ __forceinline__ float param_float(const DScene& sc, const tcpt_flat_float& p, float2 uv) {

@@ -299,9 +299,89 @@ struct Dielectric {
         return g.Dvis(wo, wm) * dwm_dwi * pt / (pr + pt);
     }
 };
-__device__ __forceinline__ Dielectric make_dielectric(float eta, bool entering, bool thin, float alpha) {
-    Dielectric d; d.eta = s4(eta == 0.0f ? 1.0f : eta); d.entering = entering; d.thin = thin; d.g.ax = alpha; d.g.ay = alpha; return d;
+// DielectricBsdf::new (dielectric.rs:127-148): an eta whose first lane is 0 falls back to the constant 1
+__device__ __forceinline__ Dielectric make_dielectric(const S4& eta, bool entering, bool thin, float alpha) {
+    Dielectric d; d.eta = eta.v[0] == 0.0f ? s4(1.0f) : eta; d.entering = entering; d.thin = thin; d.g.ax = alpha; d.g.ay = alpha; return d;
 }
+__device__ __forceinline__ Dielectric make_dielectric(float eta, bool entering, bool thin, float alpha) { return make_dielectric(s4(eta), entering, thin, alpha); }
+
+// ---------------------------------------------------------------- bsdf/conductor.rs
+struct Cplx { float re, im; };
+__device__ __forceinline__ Cplx cadd(Cplx a, Cplx b) { return Cplx{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return Cplx{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) { return Cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cplx cscale(Cplx a, float s) { return Cplx{a.re * s, a.im * s}; }
+__device__ __forceinline__ Cplx cdiv(Cplx a, Cplx b) {
+    const float denom = b.re * b.re + b.im * b.im;
+    if (denom == 0.0f) return Cplx{0.0f, 0.0f};
+    return Cplx{(a.re * b.re + a.im * b.im) / denom, (a.im * b.re - a.re * b.im) / denom};
+}
+__device__ __forceinline__ Cplx csqrt(Cplx a) {  // polar form (conductor.rs:30-36)
+    const float r = sqrtf(a.re * a.re + a.im * a.im);
+    const float theta = atan2f(a.im, a.re);
+    const float sr = sqrtf(r), ht = theta * 0.5f;
+    return Cplx{sr * cosf(ht), sr * sinf(ht)};
+}
+__device__ __forceinline__ float cnorm(Cplx a) { return a.re * a.re + a.im * a.im; }
+// fresnel_complex (conductor.rs:91-123)
+__device__ __noinline__ S4 fresnel_complex(float cos_theta_i, const S4& eta, const S4& k) {
+    cos_theta_i = clampf(cos_theta_i, 0.0f, 1.0f);
+    S4 r;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const Cplx ce{eta.v[i], k.v[i]};
+        const float sin2_i = 1.0f - cos_theta_i * cos_theta_i;
+        const Cplx sin2_t = cdiv(Cplx{sin2_i, 0.0f}, cmul(ce, ce));
+        const Cplx cos_t = csqrt(csub(Cplx{1.0f, 0.0f}, sin2_t));
+        const Cplx r_parl = cdiv(csub(cscale(ce, cos_theta_i), cos_t), cadd(cscale(ce, cos_theta_i), cos_t));
+        const Cplx r_perp = cdiv(csub(Cplx{cos_theta_i, 0.0f}, cmul(ce, cos_t)), cadd(Cplx{cos_theta_i, 0.0f}, cmul(ce, cos_t)));
+        r.v[i] = (cnorm(r_parl) + cnorm(r_perp)) * 0.5f;
+    }
+    return r;
+}
+struct Conductor {  // conductor.rs:125-439
+    S4 eta, k; Ggx g;
+    __device__ S4 torrance_sparrow(float3 wo, float3 wi, float3 wm) const {
+        const float co = fabsf(wo.z), ci = fabsf(wi.z);
+        if (co == 0.0f || ci == 0.0f) return s4(0.0f);
+        const S4 fr = fresnel_complex(fabsf(dot(wo, wm)), eta, k);
+        const float d = g.D(wm), gg = g.G(wo, wi);
+        return fr * d * gg / (4.0f * co);
+    }
+    __device__ float pdf_microfacet(float3 wo, float3 wi) const {
+        if (!same_hemisphere(wo, wi)) return 0.0f;
+        float3 wm;
+        if (!half_vector(wo, wi, &wm)) return 0.0f;
+        const float vis = g.Dvis(wo, wm);
+        const float jac = 4.0f * fabsf(dot(wo, wm));
+        if (jac == 0.0f) return 0.0f;
+        return vis / jac;
+    }
+    __device__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
+        if (wo.z == 0.0f) return false;
+        if (g.effectively_smooth()) {
+            const float3 wi = f3(-wo.x, -wo.y, wo.z);
+            if (wi.z == 0.0f) return false;
+            out->f = fresnel_complex(fabsf(wi.z), eta, k); out->wi = wi; out->pdf = 1.0f; out->type = ST_SPECULAR_REFLECTION;
+            return true;
+        }
+        const float3 wm = g.sample_wm(wo, uv);
+        const float3 wi = reflect(wo, wm);
+        if (!same_hemisphere(wo, wi)) return false;
+        out->f = torrance_sparrow(wo, wi, wm); out->wi = wi; out->pdf = pdf_microfacet(wo, wi); out->type = ST_GLOSSY_REFLECTION;
+        return true;
+    }
+    __device__ S4 evaluate(float3 wo, float3 wi) const {
+        if (g.effectively_smooth()) return s4(0.0f);
+        const float co = fabsf(wo.z), ci = fabsf(wi.z);
+        if (co == 0.0f || ci == 0.0f) return s4(0.0f);
+        if (!same_hemisphere(wo, wi)) return s4(0.0f);
+        float3 wm;
+        if (!half_vector(wo, wi, &wm)) return s4(0.0f);
+        return torrance_sparrow(wo, wi, wm);
+    }
+    __device__ float pdf(float3 wo, float3 wi) const { return g.effectively_smooth() ? 0.0f : pdf_microfacet(wo, wi); }
+};
 
 // ---------------------------------------------------------------- bsdf/generalized_schlick.rs (ScatterMode::R)
 // The materials only ever build it with r90 = 1, exponent = 5, tint = 1 (simple_pbr_material.rs:290-520,
@@ -560,6 +640,25 @@ __device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt
             return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
         }
         case TCPT_MAT_SIMPLE_PBR: return load_pbr(sc, m, sp_uv, wl).sample(wo_nm, uc, uv, from_nm);
+        case TCPT_MAT_METAL: {  // metal_material.rs:122-173: eta / k presets in `color` / `coat_tint`, alpha = roughness^2
+            Conductor cb;
+            cb.eta = spectrum_sample(sc, spectrum_from_flat(m.color), wl); cb.k = spectrum_sample(sc, spectrum_from_flat(m.coat_tint), wl);
+            const float rough = param_float(sc, m.roughness, sp_uv);
+            cb.g.ax = cb.g.ay = rough * rough;
+            BsdfSample s;
+            if (!cb.sample(wo_nm, uv, &s)) return mat_fail();
+            const float3 wi_sh = m3_vector(from_nm, s.wi);
+            if (signum(dot(ng_t, wi_sh)) != signum(dot(ng_t, wo))) return mat_fail();
+            return mat_ok(s.f, wi_sh, s.pdf, s.type);
+        }
+        case TCPT_MAT_GLASS: {  // glass_material.rs:97-147: eta(lambda) preset in `color`, roughness passed unsquared as alpha
+            const S4 eta = spectrum_sample(sc, spectrum_from_flat(m.color), wl);
+            const float rough = param_float(sc, m.roughness, sp_uv);
+            const Dielectric d = make_dielectric(eta, dot(ng_t, wo) > 0.0f, m.thin_surface != 0, rough);
+            BsdfSample s;
+            if (!d.sample(wo_nm, uv, uc, wl, &s)) return mat_fail();
+            return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
+        }
         case TCPT_MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:121-250
             const PbrBase b = load_pbr(sc, m, sp_uv, wl);
             const Coat cp = load_coat(sc, m, sp_uv, wl);
@@ -609,6 +708,23 @@ __device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_fl
             const PbrBase b = load_pbr(sc, m, sp_uv, wl);
             *f_out = b.evaluate(wo_nm, wi_nm);
             if (want_pdf) *pdf_out = b.pdf(wo_nm, wi_nm);
+            return;
+        }
+        case TCPT_MAT_METAL: {  // metal_material.rs:175-252
+            if (signum(dot(ng_t, wi)) != signum(dot(ng_t, wo))) { *f_out = s4(0.0f); return; }
+            Conductor cb;
+            cb.eta = spectrum_sample(sc, spectrum_from_flat(m.color), wl); cb.k = spectrum_sample(sc, spectrum_from_flat(m.coat_tint), wl);
+            const float rough = param_float(sc, m.roughness, sp_uv);
+            cb.g.ax = cb.g.ay = rough * rough;
+            *f_out = cb.evaluate(wo_nm, wi_nm);
+            if (want_pdf) *pdf_out = cb.pdf(wo_nm, wi_nm);
+            return;
+        }
+        case TCPT_MAT_GLASS: {  // glass_material.rs:149-221
+            const float rough = param_float(sc, m.roughness, sp_uv);
+            const Dielectric d = make_dielectric(spectrum_sample(sc, spectrum_from_flat(m.color), wl), dot(ng_t, wo) > 0.0f, m.thin_surface != 0, rough);
+            *f_out = d.evaluate(wo_nm, wi_nm);
+            if (want_pdf) *pdf_out = d.pdf(wo_nm, wi_nm);
             return;
         }
         case TCPT_MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:252-433: evaluate and pdf each draw their OWN albedo estimate

@@ -121,6 +121,7 @@ tcpt_flat_spectrum HostScene::resolve_spectrum(const tcpt_spectrum_param& p) con
             break;
         case TCPT_SPEC_D65: s.kind = 3; break;
         case TCPT_SPEC_TEXTURE_SRGB: s.kind = 4; s.texture = p.texture; break;
+        case TCPT_SPEC_PRESET: s.kind = 5; s.texture = p.texture; break;
         default: s.kind = 0; break;
     }
     return s;
@@ -142,6 +143,12 @@ int HostScene::add_material(const tcpt_material_desc& d) {
     auto cf = [](const tcpt_float_param& p) { return tcpt_flat_float{p.kind == 1, p.value, p.texture, p.gamma_corrected}; };
     auto tex_ok = [&](int t) { return t >= 0 && t < (int)textures.size(); };
     if ((d.color.kind == TCPT_SPEC_TEXTURE_SRGB && !tex_ok(d.color.texture)) || (d.normal.texture >= 0 && !tex_ok(d.normal.texture))) { error = "add_material: texture index out of range"; return TCPT_ERR_INVALID; }
+    auto preset_ok = [&](const tcpt_spectrum_param& p) { return p.kind != TCPT_SPEC_PRESET || (p.texture >= 0 && (size_t)p.texture * 470 < tables.presets.size()); };
+    if (!preset_ok(d.color) || !preset_ok(d.coat_tint)) { error = "add_material: spectrum preset id out of range (std_tables blob without presets?)"; return TCPT_ERR_INVALID; }
+    if (d.type < TCPT_MAT_LAMBERT || d.type > TCPT_MAT_GLASS) { error = "add_material: unknown material type"; return TCPT_ERR_INVALID; }
+    if ((d.type == TCPT_MAT_METAL && (d.color.kind != TCPT_SPEC_PRESET || d.coat_tint.kind != TCPT_SPEC_PRESET)) || (d.type == TCPT_MAT_GLASS && d.color.kind != TCPT_SPEC_PRESET)) {
+        error = "add_material: metal needs eta and k presets (color, coat_tint), glass an eta preset (color)"; return TCPT_ERR_INVALID;
+    }
     tcpt_flat_material m{};
     m.type = d.type;
     m.color = resolve_spectrum(d.color);

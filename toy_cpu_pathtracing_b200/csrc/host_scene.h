@@ -17,6 +17,7 @@ struct HostTables {
     uint32_t sobol[104];
     std::vector<float> cie_x, cie_y, cie_z, d65;  // 470 each
     std::vector<float> rgb2spec;                  // 64 z nodes + 3*64^3*3
+    std::vector<float> presets;                   // n x 470 dense metal / glass tables
 };
 
 struct HostMesh {

@@ -71,15 +71,16 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 // Besides the hit record, every ray is filed into a BUCKET by what k_shade will have to do with it (miss / material type of
 // the hit), so that k_shade's warps run one material's code instead of serialising up to six branches (ncu on the first
 // version: 8.6 of 32 lanes active in the bounce-1 shade launch).  Filing = one warp-aggregated atomic per distinct bucket.
-#define TCPT_N_BUCKETS 6
+#define TCPT_N_BUCKETS 8
 #ifndef TCPT_SHADE_MIN_BLOCKS
 #define TCPT_SHADE_MIN_BLOCKS 4
 #endif
 // shading order: heaviest code first so the tail of the launch is made of cheap vertices
 __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim) {
-    if (prim < 0) return 5u;                                     // miss: environment lookup only
+    if (prim < 0) return 7u;                                     // miss: environment lookup only
     const int t = sc.materials[sc.primitives[prim].material].type;
-    return t == TCPT_MAT_CLEARCOAT_PBR ? 0u : t == TCPT_MAT_SIMPLE_PBR ? 1u : t == TCPT_MAT_PLASTIC ? 2u : t == TCPT_MAT_LAMBERT ? 3u : 4u;
+    return t == TCPT_MAT_CLEARCOAT_PBR ? 0u : t == TCPT_MAT_SIMPLE_PBR ? 1u : t == TCPT_MAT_PLASTIC ? 2u : t == TCPT_MAT_GLASS ? 3u : t == TCPT_MAT_METAL ? 4u
+         : t == TCPT_MAT_LAMBERT ? 5u : 6u;
 }
 
 // work counters of the persistent trace kernels: counters[24] closest, counters[25] shadow.  Each is zeroed by an earlier kernel
@@ -145,8 +146,9 @@ struct ShadeOut {
 
 // bucket -> compile-time material type (see bucket_of)
 template <int B> struct BucketInfo {
-    static constexpr bool miss = B == 5;
-    static constexpr int mat = B == 0 ? TCPT_MAT_CLEARCOAT_PBR : B == 1 ? TCPT_MAT_SIMPLE_PBR : B == 2 ? TCPT_MAT_PLASTIC : B == 3 ? TCPT_MAT_LAMBERT : TCPT_MAT_EMISSIVE;
+    static constexpr bool miss = B == 7;
+    static constexpr int mat = B == 0 ? TCPT_MAT_CLEARCOAT_PBR : B == 1 ? TCPT_MAT_SIMPLE_PBR : B == 2 ? TCPT_MAT_PLASTIC : B == 3 ? TCPT_MAT_GLASS : B == 4 ? TCPT_MAT_METAL
+                              : B == 5 ? TCPT_MAT_LAMBERT : TCPT_MAT_EMISSIVE;
 };
 
 template <int B>
@@ -248,9 +250,9 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     const float3 wo = m3_vector(r2t, hit.wo);
     const float3 ng_t = m3_normal_by_inverse(t2r, hit.normal);  // Transform * Normal = inverse(r2t)^T n, normalised
     MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
-    // `uc` only selects between lobes; LambertMaterial::sample never reads it (lambert_material.rs:42-97)
+    // `uc` only selects between lobes; LambertMaterial::sample and MetalMaterial::sample never read it (lambert_material.rs:42-97, metal_material.rs:124)
     float uc = 0.0f;
-    if (MT == TCPT_MAT_LAMBERT) smp.skip_1d(); else uc = smp.get_1d();
+    if (MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) smp.skip_1d(); else uc = smp.get_1d();
     const float2 uv = smp.get_2d();
     const bool was_terminated = wl.terminated;
     NmFrame nmf;
@@ -379,7 +381,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
 
 // One instantiation per shading bucket; each walks only its own range of the bucketed order.
 template <int B>
-__global__ void __launch_bounds__(128, (B >= 4 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
+__global__ void __launch_bounds__(128, (B >= 6 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
                                                                                      const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, uint32_t stage) {
     if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) st.counters[24] = 0;  // work counter of the next k_trace_closest
     const float4* __restrict__ q_d = st.ext_d[cur];
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(128, (B >= 4 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_s
             const float4 d = q_d[i];
             shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
         }
-        if (B < 4) {  // emissive hits and misses end the path: nothing to push
+        if (B < 6) {  // emissive hits and misses end the path: nothing to push
             const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
             if (out.push_ext) { n_o[pe] = out.eo; n_d[pe] = out.ed; }
             const uint32_t ps = warp_push(&st.counters[2], out.push_sh);

@@ -24,7 +24,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -39,6 +39,7 @@ struct tcpt_ctx {
     // tables on the device
     float4* d_cmf = nullptr; float* d_rgb2spec = nullptr;  // d_rgb2spec = 64 z nodes + table
     uint32_t* d_sobol_bytes = nullptr;                      // Sobol matrix 1 folded per index byte (7 x 256)
+    float* d_presets = nullptr;                             // dense metal / glass tables, n x 470
     float xyz_to_rgb[9];
     // wavefront buffers
     DState st{};
@@ -196,6 +197,22 @@ void collect_stage_times(tcpt_ctx* ctx) {  // call after the stream has been syn
     ctx->ev_stage.clear();
 }
 
+// developer option "debug_path_log": with a single path in flight, print its queue entries and state after every stage (stderr)
+static void debug_dump(tcpt_ctx* ctx, const char* what, uint32_t stage, int cur, cudaStream_t stream) {
+    const DState& st = ctx->st;
+    cudaStreamSynchronize(stream);
+    uint32_t cnt[4]; float4 o, d, h0, thr, con, misc, so, sd, sc_; uint2 h1;
+    cudaMemcpy(cnt, st.counters, sizeof cnt, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&o, st.ext_o[cur], 16, cudaMemcpyDeviceToHost); cudaMemcpy(&d, st.ext_d[cur], 16, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&h0, st.hit0, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&h1, st.hit1, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&thr, st.thr, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&con, st.con, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&misc, st.misc, 16, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&so, st.sh_o, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&sd, st.sh_d, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&sc_, st.sh_c, 16, cudaMemcpyDeviceToHost);
+    uint32_t dim, fl; std::memcpy(&dim, &misc.z, 4); std::memcpy(&fl, &misc.w, 4);
+    std::fprintf(stderr, "[tcpt %s stage %u] q=%u/%u sh=%u ray o(%.9g %.9g %.9g) d(%.9g %.9g %.9g) tmax %.9g | hit t %.9g prim %d tri %d | thr %.9g %.9g %.9g %.9g con %.9g %.9g %.9g %.9g pdf_prev %.9g dim %u flags %u | shadow o(%.9g %.9g %.9g) d(%.9g %.9g %.9g) tmax %.9g c %.9g %.9g %.9g %.9g\n",
+                 what, stage, cnt[0], cnt[1], cnt[2], o.x, o.y, o.z, d.x, d.y, d.z, o.w, h0.x, (int)h1.x, (int)h1.y, thr.x, thr.y, thr.z, thr.w, con.x, con.y, con.z, con.w, misc.x, dim, fl,
+                 so.x, so.y, so.z, sd.x, sd.y, sd.z, so.w, sc_.x, sc_.y, sc_.z, sc_.w);
+}
+
 // one pass = generate + (max_depth + 1) x {closest, shade, shadow} (+ film when acc != nullptr)
 int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList& L, uint32_t n_slots, float* dev_acc, cudaStream_t stream) {
     const DScene& sc = ctx->dev.view;
@@ -222,8 +239,11 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
             k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
             k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
             k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
         }
-        ctx->stats.kernel_launches += 7;
+        ctx->stats.kernel_launches += 9;
+        if (ctx->opt.debug_path_log && n_slots == 1) debug_dump(ctx, "after shade", stage, cur ^ 1, stream);
         if (R.integrator != TCPT_INTEGRATOR_PT && stage < R.max_depth) {
             StageTimer t(ctx, STAGE_SHADOW, stream);
             if (count) k_trace_shadow<true><<<g128, 128, 0, stream>>>(sc, R, st);
@@ -347,6 +367,7 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->film_srgb) cudaFree(ctx->film_srgb);
     if (ctx->d_cmf) cudaFree(ctx->d_cmf);
     if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
+    if (ctx->d_presets) cudaFree(ctx->d_presets);
     if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -364,6 +385,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     const std::string n(name);
     if (n == "count_tests") ctx->opt.count_tests = value;
     else if (n == "stage_timing") ctx->opt.stage_timing = value;
+    else if (n == "debug_path_log") ctx->opt.debug_path_log = value;
     else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
     else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
     else if (n == "pin_host_buffers") { ctx->opt.pin_host_buffers = value != 0; if (!value) unpin_all(ctx); }
@@ -373,7 +395,10 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
 
 int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_floats) {
     if (!ctx) return TCPT_ERR_INVALID;
-    if (!std_tables || std_len != 8 + 104 * 4 + 4 * 470 * 4 || std::memcmp(std_tables, "TCPTSTD1", 8) != 0) return fail(ctx, TCPT_ERR_INVALID, "set_tables: bad std_tables blob");
+    const size_t base_len = 8 + 104 * 4 + 4 * 470 * 4;
+    const bool v1 = std_tables && std_len == base_len && std::memcmp(std_tables, "TCPTSTD1", 8) == 0;
+    const bool v2 = std_tables && std_len >= base_len + 4 && std::memcmp(std_tables, "TCPTSTD2", 8) == 0;
+    if (!v1 && !v2) return fail(ctx, TCPT_ERR_INVALID, "set_tables: bad std_tables blob");
     if (!rgb2spec || rgb2spec_floats != 64 + (size_t)3 * 64 * 64 * 64 * 3) return fail(ctx, TCPT_ERR_INVALID, "set_tables: bad rgb2spec table size");
     HostTables& T = ctx->host.tables;
     const uint8_t* p = (const uint8_t*)std_tables + 8;
@@ -381,6 +406,13 @@ int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const
     const float* f = (const float*)p;
     T.cie_x.assign(f, f + 470); T.cie_y.assign(f + 470, f + 940); T.cie_z.assign(f + 940, f + 1410); T.d65.assign(f + 1410, f + 1880);
     T.rgb2spec.assign(rgb2spec, rgb2spec + rgb2spec_floats);
+    T.presets.clear();
+    if (v2) {
+        uint32_t n_presets; std::memcpy(&n_presets, (const uint8_t*)std_tables + base_len, 4);
+        if (std_len != base_len + 4 + (size_t)n_presets * 470 * 4) return fail(ctx, TCPT_ERR_INVALID, "set_tables: bad preset table size");
+        const float* pf = (const float*)((const uint8_t*)std_tables + base_len + 4);
+        T.presets.assign(pf, pf + (size_t)n_presets * 470);
+    }
     T.set = true;
     // Sobol matrix 0 must be the bit-reversal identity (the device uses __brev for dimension 0) and its rows >= 32 zero
     for (int i = 0; i < 52; ++i) if (T.sobol[i] != (i < 32 ? (0x80000000u >> i) : 0u)) return fail(ctx, TCPT_ERR_INVALID, "set_tables: Sobol matrix 0 is not the identity");
@@ -405,6 +437,9 @@ int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const
     for (int i = 0; i < 470; ++i) { cmf[4 * i] = T.cie_x[i]; cmf[4 * i + 1] = T.cie_y[i]; cmf[4 * i + 2] = T.cie_z[i]; cmf[4 * i + 3] = T.d65[i]; }
     if (!ctx->d_cmf) CU(cudaMalloc((void**)&ctx->d_cmf, 470 * sizeof(float4)));
     CU(cudaMemcpy(ctx->d_cmf, cmf.data(), 470 * sizeof(float4), cudaMemcpyHostToDevice));
+    if (ctx->d_presets) { cudaFree(ctx->d_presets); ctx->d_presets = nullptr; }
+    CU(cudaMalloc((void**)&ctx->d_presets, (T.presets.size() + 1) * sizeof(float)));
+    if (!T.presets.empty()) CU(cudaMemcpy(ctx->d_presets, T.presets.data(), T.presets.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (!ctx->d_rgb2spec) CU(cudaMalloc((void**)&ctx->d_rgb2spec, rgb2spec_floats * sizeof(float)));
     CU(cudaMemcpy(ctx->d_rgb2spec, rgb2spec, rgb2spec_floats * sizeof(float), cudaMemcpyHostToDevice));
     return TCPT_OK;
@@ -485,7 +520,7 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     }
     UP(upload(ctx, db, de.data(), de.size(), &v.envs)); v.n_envs = s->n_envs;
 #undef UP
-    v.cmf = ctx->d_cmf; v.z_nodes = ctx->d_rgb2spec; v.rgb2spec = ctx->d_rgb2spec + 64;
+    v.cmf = ctx->d_cmf; v.z_nodes = ctx->d_rgb2spec; v.rgb2spec = ctx->d_rgb2spec + 64; v.presets = ctx->d_presets;
     std::memcpy(v.xyz_to_rgb, ctx->xyz_to_rgb, sizeof v.xyz_to_rgb);
     db.max_bvh_depth = s->max_bvh_depth;
     ctx->stats.max_bvh_depth = s->max_bvh_depth;

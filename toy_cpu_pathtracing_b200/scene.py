@@ -47,10 +47,23 @@ class RgbAlbedoSpectrum:    # spectrum::RgbAlbedoSpectrum::<C>::new(color)
     color: object
 
 
-class presets:
+@dataclass
+class PresetSpectrum:       # one of the DenselySampledSpectrum presets of spectrum/src/presets.rs:336-462 (metal eta/k, glass eta)
+    name: str
+
+
+class _Presets:
     @staticmethod
     def cie_illum_d6500():
         return "D65"
+
+    def __getattr__(self, name):     # presets::au_eta(), presets::glass_sf11_eta(), ...
+        if name in capi.PRESETS:
+            return lambda: PresetSpectrum(name)
+        raise AttributeError(name)
+
+
+presets = _Presets()
 
 
 @dataclass
@@ -209,6 +222,49 @@ class SimpleClearcoatPbrMaterial:
         return cls(*a)
 
 
+class MetalType:            # metal_material.rs:15-27; value = (eta preset, k preset) as MetalMaterial::get_eta / get_k choose them (:84-108)
+    Gold = ("au_eta", "au_k")
+    Silver = ("ag_eta", "ag_k")
+    Copper = ("cu_eta", "cu_k")
+    Aluminum = ("al_eta", "al_k")
+    Brass = ("cu_zn_eta", "cu_zn_k")
+
+
+@dataclass
+class MetalMaterial:        # metal_material.rs:39-75
+    metal_type: tuple
+    normal: NormalParameter
+    roughness: FloatParameter
+
+    @classmethod
+    def new(cls, metal_type, normal, roughness):
+        return cls(metal_type, normal, roughness)
+
+    new_with_roughness = new
+
+
+class GlassType:            # glass_material.rs:13-29; value = eta preset (GlassMaterial::get_eta, :49-60)
+    Bk7 = "glass_bk7_eta"
+    Baf10 = "glass_baf10_eta"
+    Fk51a = "glass_fk51a_eta"
+    Lasf9 = "glass_lasf9_eta"
+    Sf5 = "glass_sf5_eta"
+    Sf10 = "glass_sf10_eta"
+    Sf11 = "glass_sf11_eta"
+
+
+@dataclass
+class GlassMaterial:        # glass_material.rs:31-47
+    glass_type: str
+    normal: NormalParameter
+    thin_surface: bool
+    roughness: FloatParameter
+
+    @classmethod
+    def new(cls, glass_type, normal, thin_surface, roughness):
+        return cls(glass_type, normal, thin_surface, roughness)
+
+
 # ------------------------------------------------------------------ transforms (math/src/transform.rs:84-161): T.translate(v) = translation * T, etc.
 class Transform:
     def __init__(self, m=None):
@@ -323,6 +379,8 @@ class SceneDescription:
         elif isinstance(s, RgbAlbedoSpectrum):
             out.kind = capi.SPEC_RGB_ALBEDO_SRGB if s.color.gamma_encoded else capi.SPEC_RGB_ALBEDO_LINEAR
             out.value[0], out.value[1], out.value[2] = s.color.r, s.color.g, s.color.b
+        elif isinstance(s, PresetSpectrum):
+            out.kind, out.texture = capi.SPEC_PRESET, capi.PRESETS.index(s.name)
         elif s == "D65":
             out.kind = capi.SPEC_D65
         else:
@@ -363,6 +421,14 @@ class SceneDescription:
             if isinstance(m, SimpleClearcoatPbrMaterial):
                 d.coat_ior, d.coat_roughness = self._float(m.clearcoat_ior), self._float(m.clearcoat_roughness)
                 d.coat_tint, d.coat_thickness = self._spectrum(m.clearcoat_tint_color), self._float(m.clearcoat_thickness)
+        elif isinstance(m, MetalMaterial):
+            d.type, d.normal, d.roughness = capi.MAT_METAL, self._normal(m.normal), self._float(m.roughness)
+            d.color = self._spectrum(SpectrumParameter.constant(PresetSpectrum(m.metal_type[0])))
+            d.coat_tint = self._spectrum(SpectrumParameter.constant(PresetSpectrum(m.metal_type[1])))
+        elif isinstance(m, GlassMaterial):
+            d.type, d.normal, d.roughness = capi.MAT_GLASS, self._normal(m.normal), self._float(m.roughness)
+            d.thin_surface = int(m.thin_surface)
+            d.color = self._spectrum(SpectrumParameter.constant(PresetSpectrum(m.glass_type)))
         else:
             raise TypeError(f"unsupported material {m!r}")
         return d

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import assets
 from .scene import (ColorSrgb, ColorSrgbLinear, ConstantSpectrum, CreatePrimitiveDesc, EmissiveMaterial, FloatParameter, FloatTexture,
-                    LambertMaterial, NormalParameter, NormalTexture, PlasticMaterial, RgbAlbedoSpectrum, RgbTexture, SimpleClearcoatPbrMaterial,
+                    GlassMaterial, GlassType, LambertMaterial, MetalMaterial, MetalType, NormalParameter, NormalTexture, PlasticMaterial, RgbAlbedoSpectrum, RgbTexture, SimpleClearcoatPbrMaterial,
                     SimplePbrMaterial, SpectrumParameter, SpectrumType, Transform, presets)
 
 GP = CreatePrimitiveDesc.GeometryPrimitive
@@ -102,6 +102,45 @@ def load_scene_10(scene, camera):
     camera.set_look_to((0.0, 3.5, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
 
 
+def _camera_10(camera):
+    d = np.array([0.0, -1.0, -3.0], dtype=np.float32)
+    camera.set_look_to((0.0, 3.5, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
+def load_scene_6(scene, camera):
+    """Cornell box with a mirror-smooth gold bunny (scene_6.rs:13-111): MetalMaterial / ConductorBsdf, specular reflection."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), MetalMaterial.new(MetalType.Gold, NormalParameter.none(), FloatParameter.constant(0.0)), Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_7(scene, camera):
+    """Four instances of the bunny in gold with roughness 0.05 / 0.25 / 0.5 / 0.75 (scene_7.rs:13-131): rough conductor, instance transforms."""
+    bunny = scene.load_obj(_asset("bunny"))
+    for pos, rough in zip(((-1.3, 0.0, -0.5), (-0.5, 0.0, -0.5), (0.3, 0.0, -0.5), (1.1, 0.0, -0.5)), (0.05, 0.25, 0.5, 0.75)):
+        scene.create_primitive(GP(bunny, MetalMaterial.new(MetalType.Gold, NormalParameter.none(), FloatParameter.constant(rough)),
+                                  Transform.identity().scale((0.6, 0.6, 0.6)).translate(pos)))
+    _cornell_rest(scene)
+    d = np.array([0.0, -0.7, -2.5], dtype=np.float32)
+    camera.set_look_to((0.0, 2.5, 5.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
+def load_scene_8(scene, camera):
+    """SF11 glass bunny, smooth, not thin (scene_8.rs:13-112): dispersive eta(lambda) -> the path keeps only its hero wavelength."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), GlassMaterial.new(GlassType.Sf11, NormalParameter.none(), False, FloatParameter.constant(0.0)), Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_9(scene, camera):
+    """Same box; the bunny is solid plastic, eta 1.8, roughness 0, thin film off (scene_9.rs:13-113)."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")),
+                              PlasticMaterial.new(1.8, SpectrumParameter.Constant(ConstantSpectrum(1.0)), NormalParameter.none(), False, FloatParameter.constant(0.0)),
+                              Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
 def _clearcoat(coat_roughness):
     tint = SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(0.7, 0.8, 1.0)))
     return SimpleClearcoatPbrMaterial.new(_grey(0.8), FloatParameter.constant(1.0), FloatParameter.constant(0.7), NormalParameter.none(), FloatParameter.constant(1.5),
@@ -143,7 +182,7 @@ def load_soup(scene, camera, n_triangles: int, seed: int = 42):
     camera.set_look_to((0.0, 0.0, 3.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
 
 
-SCENES = {3: load_scene_3, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
+SCENES = {3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
 
 
 def load_scene(scene_id, scene, camera, **kw):
