@@ -97,6 +97,8 @@ typedef struct {
     double render_ms;        /* device time of the last tcpt_render* (CUDA events) */
     double trace_closest_ms, trace_shadow_ms, shade_ms, generate_ms, film_ms; /* per stage, when option "stage_timing" = 1 */
     uint32_t passes, max_bvh_depth;
+    double sobol_prefix_ms;  /* device time of the last build of the ZSobol pixel-prefix table (once per resolution / spp; 0 when reused) */
+    uint64_t sobol_prefix_bytes; /* size of that table in device memory */
 } tcpt_stats;
 
 /* ---- context.  tcpt_create returns TCPT_ERR_CUDA when no sm_100 device is usable; *out is then still a context on which only
@@ -106,7 +108,8 @@ int tcpt_create(int device_id, tcpt_ctx** out);
 void tcpt_destroy(tcpt_ctx* ctx);
 const char* tcpt_last_error(const tcpt_ctx* ctx);
 /* options: "count_tests" (box/triangle test counters), "stage_timing" (per-kernel event timing), "blocks_per_sm",
- * "binned_builder" (fast non-reference BVH for synthetic soups), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
+ * "binned_builder" (fast non-reference BVH for synthetic soups), "sobol_prefix" (1: Z-Sobol pixel-digit table, default; 0: recompute
+ * every digit per sampler call), "sobol_prefix_mb" (memory cap of that table, default 8192), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
  * buffers on first use and keeps them registered while the same pointers are passed; 0: releases them — set 0 before freeing) */
 int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
 /* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65 and the metal / glass presets:

@@ -23,6 +23,31 @@ def test_pass_tiling_does_not_change_the_film(bundle_factory):
     assert np.array_equal(full.view(np.uint32), tiny.view(np.uint32))
 
 
+@pytest.mark.parametrize("spp", [8, 64])   # odd and even log2(spp): the sample digits sit at odd / even bit offsets
+def test_sobol_prefix_table_is_bit_transparent(bundle_factory, spp):
+    """The Z-Sobol pixel-prefix table only caches the pixel digits of get_sample_index: table on, table off and a table that
+    covers only the first dimensions (the rest computed in full) must give the same film to the bit."""
+    b = bundle_factory(3, 200, 150)
+    ctx = b.scene.ctx
+    try:
+        on = b.image("mis", spp).render("sobol")
+        assert on.stats["sobol_prefix_bytes"] == 200 * 150 * 4 * (3 + 8 * 17)
+        a = on.accumulators.copy()
+        ctx.set_option("sobol_prefix", 0)
+        off = b.image("mis", spp).render("sobol")
+        assert off.stats["sobol_prefix_bytes"] == 0
+        ctx.set_option("sobol_prefix", 1)
+        ctx.set_option("sobol_prefix_mb", 1)          # 1 MiB / (30 000 px x 4 B) = 8 dimensions
+        b.image("mis", spp * 2).render("sobol")       # another spp in between: the cached table must be rebuilt
+        part = b.image("mis", spp).render("sobol")
+        assert part.stats["sobol_prefix_bytes"] == 200 * 150 * 4 * 8
+        assert np.array_equal(a.view(np.uint32), off.accumulators.view(np.uint32))
+        assert np.array_equal(a.view(np.uint32), part.accumulators.view(np.uint32))
+    finally:
+        ctx.set_option("sobol_prefix", 1)
+        ctx.set_option("sobol_prefix_mb", 8192)
+
+
 def test_row_shards_sum_bitwise_to_the_full_frame(bundle_factory):
     """Tile (row-interleaved) sharding: each pixel is rendered entirely by one shard; the others hold exact zeros."""
     b = bundle_factory(10, 200, 150)

@@ -60,7 +60,8 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("box_tests", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
                 ("trace_closest_ms", C.c_double), ("trace_shadow_ms", C.c_double), ("shade_ms", C.c_double),
-                ("generate_ms", C.c_double), ("film_ms", C.c_double), ("passes", C.c_uint32), ("max_bvh_depth", C.c_uint32)]
+                ("generate_ms", C.c_double), ("film_ms", C.c_double), ("passes", C.c_uint32), ("max_bvh_depth", C.c_uint32),
+                ("sobol_prefix_ms", C.c_double), ("sobol_prefix_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

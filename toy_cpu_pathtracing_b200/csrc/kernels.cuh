@@ -30,8 +30,24 @@ __device__ __forceinline__ void path_coords(const DRender& R, const PathList& L,
 __device__ __forceinline__ DSampler make_sampler(const DRender& R, uint32_t px, uint32_t py, uint32_t si) {
     DSampler s;
     s.kind = (uint32_t)R.sampler; s.seed = R.seed; s.log2_spp = R.log2_spp; s.nb4 = R.n_base4_digits;
+    s.prefix = R.sobol_prefix ? R.sobol_prefix + ((size_t)py * R.width + px) : nullptr;
+    s.prefix_dims = R.sobol_prefix ? R.prefix_dims : 0u; s.prefix_stride = R.prefix_stride;
     s.start(px, py, si);
     return s;
+}
+
+// builds DRender::sobol_prefix: entry (dim, pixel) = permuted pixel digits of ZSobolSampler::get_sample_index (see DSampler)
+__global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ table, uint32_t width, uint32_t height, uint32_t log2_spp, uint32_t nb4, uint32_t dims) {
+    const size_t n_pix = (size_t)width * height, total = n_pix * dims;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t dim = (uint32_t)(i / n_pix), k = (uint32_t)(i - (size_t)dim * n_pix);
+        const uint32_t py = k / width, px = k - py * width;
+        DSampler s;
+        s.kind = TCPT_SAMPLER_SOBOL; s.seed = 0; s.log2_spp = log2_spp; s.nb4 = nb4; s.prefix = nullptr; s.prefix_dims = 0; s.prefix_stride = 0;
+        s.start(px, py, 0u);
+        s.dim = dim;
+        table[i] = s.pixel_prefix();
+    }
 }
 
 // ---------------------------------------------------------------- K0 generate

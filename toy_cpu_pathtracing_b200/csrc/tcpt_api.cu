@@ -24,7 +24,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -55,6 +55,9 @@ struct tcpt_ctx {
     // tcpt_render's own film buffers (grow-only) and the caller's output buffers currently page-locked for direct DMA
     float* film_acc = nullptr; float* film_srgb = nullptr; size_t film_cap = 0;
     HostPin pins[2];
+    // ZSobol pixel-prefix table (DSampler::sample_index), cached per (width, height, log2_spp); grows when more dimensions are asked for
+    uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0; size_t prefix_cap = 0;
+    double prefix_build_ms = 0.0;
 };
 
 namespace {
@@ -169,6 +172,43 @@ int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera&
     return TCPT_OK;
 }
 
+// ZSobol pixel-prefix table: one u32 per (dimension, pixel) holding the permuted Morton digits of the pixel (everything of
+// ZSobolSampler::get_sample_index that does not depend on the sample index), built on `stream` ahead of the frame's first pass and
+// kept until the resolution or spp changes.  Dimensions covered: what a max_depth path can draw (3 + 8 per bounce), capped by
+// option "sobol_prefix_mb"; deeper dimensions are computed in full by the sampler.
+int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
+    R.sobol_prefix = nullptr; R.prefix_dims = 0; R.prefix_stride = 0;
+    if (R.sampler != TCPT_SAMPLER_SOBOL || !ctx->opt.sobol_prefix) return TCPT_OK;
+    const size_t n_pix = (size_t)R.width * R.height;
+    size_t dims = 3 + 8 * ((size_t)R.max_depth + 1);
+    const size_t cap_dims = ((size_t)ctx->opt.sobol_prefix_mb << 20) / (n_pix * 4);
+    if (dims > cap_dims) dims = cap_dims;
+    if (dims == 0) return TCPT_OK;
+    const bool same = ctx->d_prefix && ctx->prefix_w == R.width && ctx->prefix_h == R.height && ctx->prefix_log2spp == R.log2_spp;
+    if (!same || ctx->prefix_dims < dims) {
+        const size_t need = n_pix * dims;
+        if (need > ctx->prefix_cap) {
+            if (ctx->d_prefix) { cudaStreamSynchronize(stream); cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr; ctx->prefix_cap = 0; }
+            if (cudaMalloc((void**)&ctx->d_prefix, need * 4) != cudaSuccess) { cudaGetLastError(); ctx->prefix_dims = 0; return TCPT_OK; }  // no table: full loop
+            ctx->prefix_cap = need;
+        }
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, stream);
+        const size_t total = n_pix * dims;
+        const int grid = (int)((total + 255) / 256 < (size_t)ctx->sm_count * 64 ? (total + 255) / 256 : (size_t)ctx->sm_count * 64);
+        k_sobol_prefix<<<grid, 256, 0, stream>>>(ctx->d_prefix, R.width, R.height, R.log2_spp, R.n_base4_digits, (uint32_t)dims);
+        cudaEventRecord(b, stream);
+        CU(cudaEventSynchronize(b));
+        float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); ctx->prefix_build_ms = ms; ctx->stats.sobol_prefix_ms = ms;
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        CU(cudaGetLastError());
+        ctx->prefix_w = R.width; ctx->prefix_h = R.height; ctx->prefix_log2spp = R.log2_spp; ctx->prefix_dims = (uint32_t)dims;
+    }
+    R.sobol_prefix = ctx->d_prefix; R.prefix_dims = ctx->prefix_dims; R.prefix_stride = (uint32_t)n_pix;
+    ctx->stats.sobol_prefix_bytes = (uint64_t)n_pix * ctx->prefix_dims * 4;
+    return TCPT_OK;
+}
+
 // Per-stage device timing without host round trips: an event pair is recorded around every launch on the launching stream
 // and the pairs are read back once, after the frame's final synchronisation (option "stage_timing").
 struct StageTimer {
@@ -280,6 +320,8 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     int rc = make_render(ctx, p, R, cam);
     if (rc) return rc;
     if (R.row_offset >= R.row_stride) return fail(ctx, TCPT_ERR_INVALID, "render: row_offset must be < row_stride");
+    rc = ensure_sobol_prefix(ctx, R, stream);
+    if (rc) return rc;
     const uint32_t s0 = (p->spp_begin == 0 && p->spp_end == 0) ? 0 : p->spp_begin;
     const uint32_t s1 = (p->spp_begin == 0 && p->spp_end == 0) ? p->spp : p->spp_end;
     if (s1 > p->spp || s0 > s1) return fail(ctx, TCPT_ERR_INVALID, "render: bad sample range");
@@ -368,6 +410,7 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->d_cmf) cudaFree(ctx->d_cmf);
     if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
     if (ctx->d_presets) cudaFree(ctx->d_presets);
+    if (ctx->d_prefix) cudaFree(ctx->d_prefix);
     if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -386,6 +429,8 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     if (n == "count_tests") ctx->opt.count_tests = value;
     else if (n == "stage_timing") ctx->opt.stage_timing = value;
     else if (n == "debug_path_log") ctx->opt.debug_path_log = value;
+    else if (n == "sobol_prefix") ctx->opt.sobol_prefix = value;
+    else if (n == "sobol_prefix_mb") ctx->opt.sobol_prefix_mb = value;
     else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
     else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
     else if (n == "pin_host_buffers") { ctx->opt.pin_host_buffers = value != 0; if (!value) unpin_all(ctx); }
@@ -696,6 +741,8 @@ int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uin
     cudaMemcpyAsync(d_xy, pixels_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_s, sample_indices, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
     reset_stats(ctx);
+    rc = ensure_sobol_prefix(ctx, R, ctx->stream);
+    if (rc) { cudaFree(d_xy); cudaFree(d_s); return rc; }
     R.n_pix = (uint32_t)n; R.s_count = 1;
     PathList L{d_xy, d_s};
     rc = run_pass(ctx, R, cam, L, (uint32_t)n, nullptr, ctx->stream);
