@@ -4,14 +4,14 @@
 Workload (BASELINE.json configs[3], the configuration the metric's 1/2/4/8-GPU numbers are quoted on): scene 19 (floor + three
 dragon instances: textured SimplePbr, smooth clearcoat, plastic; environment light) at 3840x2160, MIS integrator, Z-Sobol
 sampler, max_depth 16, as a 4096-spp frame.  One STEP = one pass of the hot path over one batch = `--spp-per-step` sample
-indices of every pixel of the frame per GPU (default 4 -> 33.2 M paths per GPU per step), including the film kernel and, at
+indices of every pixel of the frame per GPU (default 16 -> 132.7 M paths per GPU per step, 35 GB of wavefront state in HBM), including the film kernel and, at
 N > 1, the NCCL reduce of the film accumulators.  Ranks render disjoint sample-index ranges of the same frame (spp-pass
 sharding), so per-GPU work is fixed as N grows: "scaling": "weak".  configs[0..2] are parity-test cases (tests/), not bench lines.
 
   value    whole-job Mrays/s, film accumulators resident in HBM (tcpt_render_device), CUDA events on the launching stream
   e2e      the same metric through the reference-facing call RendererImage.render() -> tcpt_render() with HOST buffers:
            per step the render parameters go host->device and the tone-mapped sRGB frame comes device->host
-  roofline dominant kernel k_trace_closest; see DESIGN.md "Measurement" for the byte/flop definitions
+  roofline dominant kernel k_trace_fused (closest-hit + any-hit traversal); see DESIGN.md "Measurement" for the byte/flop definitions
   cpu_baseline / --impl reference: the CPU restatement of the reference algorithm (oracle, kind "port": the Rust reference
            cannot be compiled in this image) on all host threads, on a bounded window of the same frame
 """
@@ -47,9 +47,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="scene19_4k", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--max-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="developer knob: libtcpt option as name=value (tcpt_set_option), repeatable")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -209,7 +210,7 @@ def workload_config(args, wl):
     return {"workload": f"scene{wl['scene']} {wl['width']}x{wl['height']} {wl['integrator']}+{wl['sampler']} max_depth 16, {wl['frame_spp']}-spp frame, "
                         f"{args.spp_per_step} sample indices of every pixel per GPU per step" + (" (BASELINE.json configs[3])" if wl["scene"] == 19 else "") + (" no-coat" if wl.get("kw") else ""),
             "paths_per_gpu_per_step": wl["width"] * wl["height"] * args.spp_per_step, "sharding": "spp-pass", "collective": "one NCCL reduce of the film accumulators per step",
-            "cache": "working set (path state + ray queues, about 1 GB per GPU) exceeds the 126 MB L2; no explicit flush", "assets": "procedural stand-ins (reference assets are LFS stubs)"}
+            "cache": f"working set (path state + ray queues, {wl['width'] * wl['height'] * args.spp_per_step * 264 / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no explicit flush", "assets": "procedural stand-ins (reference assets are LFS stubs)"}
 
 
 # ---------------------------------------------------------------- GPU arm
@@ -232,6 +233,9 @@ def main_gpu(args, wl):
     tp, scene, cam = build_scene(wl, local)
     t0 = time.time(); scene.build(cam); build_s = time.time() - t0
     ctx = scene.ctx
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        ctx.set_option(name, int(val))
     W, H, S = wl["width"], wl["height"], args.spp_per_step
     renderer = tp.RENDERERS[wl["integrator"]](tp.RendererArgs((W, H), wl["frame_spp"], scene, cam, seed=0))
     image = tp.RendererImage(W, H, renderer)
@@ -327,21 +331,21 @@ def main_gpu(args, wl):
     ctx.set_option("count_tests", 0)
     rays_c = max(1, cs["closest_rays"] + cs["shadow_rays"])
     box_per_ray, tri_per_ray = cs["box_tests"] / rays_c, cs["tri_tests"] / rays_c
-    n_closest_launches = max(1, tot["passes"] * 17)
-    closest_s = tot["closest_ms"] * 1e-3
+    # dominant kernel: k_trace_fused (one launch per bounce: the shadow rays of the previous bounce + this bounce's extension rays)
+    n_trace_launches = max(1, tot["passes"] * 17)
+    trace_s = (tot["closest_ms"] + tot["shadow_ms"]) * 1e-3
     bytes_per_ray = 48.0  # 32 B ray read + 16 B hit write (compulsory wavefront traffic; the BVH is L2 resident)
-    achieved = bytes_per_ray * tot["closest"] / closest_s / 1e9 if closest_s > 0 else 0.0
+    achieved = bytes_per_ray * tot["rays"] / trace_s / 1e9 if trace_s > 0 else 0.0
     traffic = None
     try:  # measured DRAM traffic of the same kernel from the committed ncu capture, scaled to this run's rays per launch
-        tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["k_trace_closest"]
-        traffic = tr["dram_bytes"] / tr["rays"] * (tot["closest"] / n_closest_launches)
+        tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["k_trace_fused"]
+        traffic = tr["dram_bytes"] / tr["rays"] * (tot["rays"] / n_trace_launches)
     except Exception:
         pass
     clk_s = clk.summary()
     sm_mhz = clk_s["sm_mhz"] or 1965
     flops_per_ray = 18.0 * box_per_ray + 64.0 * tri_per_ray + 60.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    trace_s = (tot["closest_ms"] + tot["shadow_ms"]) * 1e-3
     fp32_ach = flops_per_ray * tot["rays"] / trace_s / 1e12 if trace_s > 0 else 0.0
     stage_sum = tot["closest_ms"] + tot["shade_ms"] + tot["shadow_ms"] + tot["gen_ms"] + tot["film_ms"]
     line = {
@@ -352,11 +356,11 @@ def main_gpu(args, wl):
                 "call": "RendererImage.render -> tcpt_render(params, host sRGB frame out)"},
         "gpu_launches": int(launches_all),
         "clocks": clk_s,
-        "roofline": {"kernel": "k_trace_closest", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                     "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "rays_per_launch": tot["closest"] / n_closest_launches,
-                     "avg_launch_ms": tot["closest_ms"] / n_closest_launches, "share_of_step": tot["closest_ms"] / stage_sum if stage_sum else None,
+        "roofline": {"kernel": "k_trace_fused", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "rays_per_launch": tot["rays"] / n_trace_launches,
+                     "avg_launch_ms": 1e3 * trace_s / n_trace_launches, "share_of_step": 1e3 * trace_s / stage_sum if stage_sum else None,
                      "note": "BVH+textures are L2 resident: the path is FP32-issue/latency bound, see roofline_fp32"},
-        "roofline_fp32": {"kernels": "k_trace_closest + k_trace_shadow", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
+        "roofline_fp32": {"kernels": "k_trace_fused", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
                           "flops_per_ray": flops_per_ray, "box_tests_per_ray": box_per_ray, "tri_tests_per_ray": tri_per_ray, "sm_mhz": sm_mhz,
                           "definition": "18*B + 64*T + 60 flops per ray (SURVEY.md 8d); peak = 148 SM x 128 lanes x 2 x f_SM"},
         "stage_ms_per_step": {k: tot[k] / args.steps for k in ("gen_ms", "closest_ms", "shade_ms", "shadow_ms", "film_ms")},

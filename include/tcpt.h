@@ -85,7 +85,7 @@ typedef struct {
      * (0,0 = all rows / all samples).  Tile(row) sharding keeps the per-pixel sample order => bitwise equal to one GPU. */
     uint32_t row_offset, row_stride;
     uint32_t spp_begin, spp_end;
-    uint32_t max_slots;                      /* wavefront size in paths (0 = default 32 Mi, about 272 B of device memory each) */
+    uint32_t max_slots;                      /* wavefront size in paths (0 = default: up to 128 Mi, 264 B of device memory each, at most 45 % of free memory) */
 } tcpt_render_params;
 
 typedef struct {
@@ -109,7 +109,9 @@ void tcpt_destroy(tcpt_ctx* ctx);
 const char* tcpt_last_error(const tcpt_ctx* ctx);
 /* options: "count_tests" (box/triangle test counters), "stage_timing" (per-kernel event timing), "blocks_per_sm",
  * "binned_builder" (fast non-reference BVH for synthetic soups), "sobol_prefix" (1: Z-Sobol pixel-digit table, default; 0: recompute
- * every digit per sampler call), "sobol_prefix_mb" (memory cap of that table, default 8192), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
+ * every digit per sampler call), "sobol_prefix_mb" (memory cap of that table, default 8192),
+ * "fused_launches" (bit 0: shadow rays of one bounce and extension rays of the next in one launch, bit 1: all shading buckets in one
+ * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
  * buffers on first use and keeps them registered while the same pointers are passed; 0: releases them — set 0 before freeing) */
 int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
 /* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65 and the metal / glass presets:

@@ -48,6 +48,24 @@ def test_sobol_prefix_table_is_bit_transparent(bundle_factory, spp):
         ctx.set_option("sobol_prefix_mb", 8192)
 
 
+@pytest.mark.parametrize("scene_id,integrator", [(19, "mis"), (10, "nee"), (8, "pt")])
+def test_fused_launches_do_not_change_the_film(bundle_factory, scene_id, integrator):
+    """Two launches per bounce (k_trace_fused, k_shade_all) against one launch per queue and per shading bucket: the same
+    work in another launch structure, so film and ray counts must be identical to the bit."""
+    b = bundle_factory(scene_id, 200, 150)
+    ctx = b.scene.ctx
+    try:
+        fused = b.image(integrator, 16).render("sobol")
+        a, sa = fused.accumulators.copy(), dict(fused.stats)
+        ctx.set_option("fused_launches", 0)
+        plain = b.image(integrator, 16).render("sobol")
+    finally:
+        ctx.set_option("fused_launches", 1)
+    assert np.array_equal(a.view(np.uint32), plain.accumulators.view(np.uint32))
+    assert (sa["closest_rays"], sa["shadow_rays"], sa["paths"]) == (plain.stats["closest_rays"], plain.stats["shadow_rays"], plain.stats["paths"])
+    assert sa["kernel_launches"] < plain.stats["kernel_launches"] / 2
+
+
 def test_row_shards_sum_bitwise_to_the_full_frame(bundle_factory):
     """Tile (row-interleaved) sharding: each pixel is rendered entirely by one shard; the others hold exact zeros."""
     b = bundle_factory(10, 200, 150)

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(smp.dim), __uint_as_float(0u));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0;
+        st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0;
         for (int b = 0; b < 16; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
         st.counters[24] = 0; st.counters[25] = 0;             // work counters of the persistent trace kernels
         atomicAdd(&st.stats[4], (unsigned long long)n_slots);
@@ -101,6 +101,39 @@ __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim) {
 
 // work counters of the persistent trace kernels: counters[24] closest, counters[25] shadow.  Each is zeroed by an earlier kernel
 // of the same bounce (stream order): k_generate / k_shade zero [24] for the next k_trace_closest, k_trace_closest zeroes [25].
+// what a finished extension ray leaves behind: its hit record and its place in a shading bucket
+__device__ __forceinline__ void commit_closest(const DScene& sc, const DState& st, float4* __restrict__ hit0, uint2* __restrict__ hit1, uint32_t* bcount, uint32_t i, const DHit& h) {
+    hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
+    hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
+    const uint32_t b = bucket_of(sc, h.prim);
+    const uint32_t peers = __match_any_sync(__activemask(), b);
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    st.order[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+}
+// what a finished shadow ray does: add the pending NEE contribution if the light is visible (common.rs:134-170); hand a path that
+// ended at this vertex (failed BSDF sample) to the sensor
+__device__ __forceinline__ void commit_shadow(const DScene& sc, const DRender& R, const DState& st, uint32_t i, const DHit& h) {
+    const uint32_t tag = __float_as_uint(st.sh_d[i].w);
+    const uint32_t slot = tag & 0x7fffffffu;
+    const bool visible = h.prim < 0, last = (tag & 0x80000000u) != 0;
+    if (!visible && !last) return;
+    S4 con = s4(st.con[slot]);
+    if (visible) {
+        con = con + s4(st.sh_c[i]);
+        st.con[slot] = to_f4(con);
+    }
+    if (last) {
+        const float4 misc = st.misc[slot];
+        const DWavelengths wl = wavelengths_uniform(misc.y, (__float_as_uint(misc.w) & FLAG_LAMBDA_TERMINATED) != 0);
+        const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
+        st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+    }
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                         float4* __restrict__ hit0, uint2* __restrict__ hit1, const __grid_constant__ DState st, int cur) {
@@ -113,18 +146,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ D
         atomicAdd(&st.stats[0], (unsigned long long)n);
     }
     uint32_t nb = 0, nt = 0;
-    trace_queue<false, COUNT>(sc, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) {
-        hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
-        hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
-        const uint32_t b = bucket_of(sc, h.prim);
-        const uint32_t peers = __match_any_sync(__activemask(), b);
-        const uint32_t lane = threadIdx.x & 31u;
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        st.order[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
-    });
+    trace_queue<false, COUNT>(sc, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, hit0, hit1, bcount, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -134,23 +156,32 @@ __global__ void __launch_bounds__(128) k_trace_shadow(const __grid_constant__ DS
     const uint32_t n = st.counters[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st.stats[1], (unsigned long long)n);
     uint32_t nb = 0, nt = 0;
-    trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) {
-        const uint32_t tag = __float_as_uint(st.sh_d[i].w);
-        const uint32_t slot = tag & 0x7fffffffu;
-        const bool visible = h.prim < 0, last = (tag & 0x80000000u) != 0;
-        if (!visible && !last) return;
-        S4 con = s4(st.con[slot]);
-        if (visible) {
-            con = con + s4(st.sh_c[i]);
-            st.con[slot] = to_f4(con);
-        }
-        if (last) {  // the path ended at this vertex (failed BSDF sample): hand its radiance to the sensor
-            const float4 misc = st.misc[slot];
-            const DWavelengths wl = wavelengths_uniform(misc.y, (__float_as_uint(misc.w) & FLAG_LAMBDA_TERMINATED) != 0);
-            const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
-            st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
-        }
-    });
+    trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
+    if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
+}
+
+// ---------------------------------------------------------------- fused trace: the shadow rays of bounce s and the extension rays of bounce s + 1
+// Both queues are written by k_shade of bounce s and are independent of each other, so one persistent launch drains them back
+// to back (shadow first: it is the shorter one) instead of two launches each paying its own ramp-up and tail.  Deep bounces
+// hold few rays and are pure launch latency: measured 7.8 ms of fixed cost per pass at about 170 launches (36 ms step).
+// `cur` = parity of the extension queue to trace, `sh` = index (2 or 3) of the shadow-queue size to read; the sizes the next
+// k_shade appends to (counters[cur ^ 1], counters[sh ^ 1]) were last read one launch ago and are reset here.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
+    const uint32_t n_sh = st.counters[sh], n = st.counters[cur];
+    uint32_t* bcount = st.counters + 4 + 8 * cur;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st.counters[cur ^ 1] = 0; st.counters[sh ^ 1] = 0;
+        for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + 8 * (cur ^ 1) + b] = 0;
+        atomicAdd(&st.stats[0], (unsigned long long)n);
+        atomicAdd(&st.stats[1], (unsigned long long)n_sh);
+    }
+    uint32_t nb = 0, nt = 0;
+    // (shadow first: it is the shorter queue.  Letting half of the blocks start on the extension queue so that short queues are
+    // walked side by side was measured slower: 16.6 vs 15.3 ms per 33 M paths.)
+    if (n_sh) trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
+    float4* __restrict__ hit0 = st.hit0; uint2* __restrict__ hit1 = st.hit1;
+    if (n) trace_queue<false, COUNT>(sc, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, hit0, hit1, bcount, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -395,34 +426,76 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     }  // !miss
 }
 
+// Shades position p of bucket B's range of the bucketed order (p >= n: the lane only takes part in the warp-collective pushes).
+template <int B>
+__device__ __forceinline__ void shade_position(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, int sh, uint32_t stage, uint32_t p, uint32_t n) {
+    const uint32_t* __restrict__ order = st.order + (size_t)B * st.capacity;
+    ShadeOut out; out.push_ext = false; out.push_sh = false;
+    if (p < n) {
+        const uint32_t i = order[p];
+        const float4 d = st.ext_d[cur][i];
+        shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+    }
+    if (B < 6) {  // emissive hits and misses end the path: nothing to push
+        const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
+        if (out.push_ext) { st.ext_o[cur ^ 1][pe] = out.eo; st.ext_d[cur ^ 1][pe] = out.ed; }
+        const uint32_t ps = warp_push(&st.counters[sh], out.push_sh);
+        if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
+    }
+}
+
 // One instantiation per shading bucket; each walks only its own range of the bucketed order.
 template <int B>
 __global__ void __launch_bounds__(128, (B >= 6 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
-                                                                                     const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, uint32_t stage) {
-    if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) st.counters[24] = 0;  // work counter of the next k_trace_closest
-    const float4* __restrict__ q_d = st.ext_d[cur];
-    float4* __restrict__ n_o = st.ext_o[cur ^ 1];
-    float4* __restrict__ n_d = st.ext_d[cur ^ 1];
+                                                                                     const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, int sh, uint32_t stage) {
+    if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
     const uint32_t stride = gridDim.x * blockDim.x;
-    // bucket B occupies sorted positions [begin, begin + n) (sizes written by this bounce's k_trace_closest)
-    uint32_t begin = 0;
-#pragma unroll
-    for (int b = 0; b < B; ++b) begin += st.counters[4 + 8 * cur + b];
     const uint32_t n = st.counters[4 + 8 * cur + B];
     const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
-    const uint32_t* __restrict__ order = st.order + (size_t)B * st.capacity;
-    (void)begin;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) shade_position<B>(sc, R, st, L, cur, sh, stage, p, n);
+}
+
+// shade_vertex<B> behind a call, so that the eight instantiations keep their own register allocation inside k_shade_all
+template <int B>
+__device__ __noinline__ void shade_vertex_call(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, uint32_t stage, uint32_t i, ShadeOut& out) {
+    const float4 d = st.ext_d[cur][i];
+    shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+}
+
+// All buckets in one launch: the launch is cut into chunks of 128 consecutive positions of ONE bucket, numbered bucket by bucket
+// (heaviest code first), and blocks take chunks round-robin.  A block only ever runs one material's code at a time and
+// neighbouring blocks mostly run the same one, so the instruction cache behaves as with eight launches, without seven
+// launch boundaries per bounce (each bounded below by the latency of one warp running a 5000-instruction program from a cold
+// instruction cache: about 0.3 ms per bounce whatever the queue length).
+__global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade_all(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st,
+                                                                           const __grid_constant__ PathList L, int cur, int sh, uint32_t stage) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
+    uint32_t cnt[TCPT_N_BUCKETS], total = 0;
+#pragma unroll
+    for (int b = 0; b < TCPT_N_BUCKETS; ++b) { cnt[b] = st.counters[4 + 8 * cur + b]; total += (cnt[b] + 127u) >> 7; }
+    for (uint32_t v = blockIdx.x; v < total; v += gridDim.x) {
+        uint32_t c = v, n = cnt[0]; int b = 0;
+#pragma unroll
+        for (int k = 0; k < TCPT_N_BUCKETS - 1; ++k) { const uint32_t ch = (cnt[k] + 127u) >> 7; if (b == k && c >= ch) { c -= ch; b = k + 1; n = cnt[k + 1]; } }
+        const uint32_t p = c * 128u + threadIdx.x;
         ShadeOut out; out.push_ext = false; out.push_sh = false;
         if (p < n) {
-            const uint32_t i = order[p];
-            const float4 d = q_d[i];
-            shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+            const uint32_t i = st.order[(size_t)b * st.capacity + p];
+            switch (b) {
+                case 0: shade_vertex_call<0>(sc, R, st, L, cur, stage, i, out); break;
+                case 1: shade_vertex_call<1>(sc, R, st, L, cur, stage, i, out); break;
+                case 2: shade_vertex_call<2>(sc, R, st, L, cur, stage, i, out); break;
+                case 3: shade_vertex_call<3>(sc, R, st, L, cur, stage, i, out); break;
+                case 4: shade_vertex_call<4>(sc, R, st, L, cur, stage, i, out); break;
+                case 5: shade_vertex_call<5>(sc, R, st, L, cur, stage, i, out); break;
+                case 6: shade_vertex_call<6>(sc, R, st, L, cur, stage, i, out); break;
+                default: shade_vertex_call<7>(sc, R, st, L, cur, stage, i, out); break;
+            }
         }
-        if (B < 6) {  // emissive hits and misses end the path: nothing to push
+        if (b < 6) {  // emissive hits and misses end the path: nothing to push (b is uniform over the block)
             const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
-            if (out.push_ext) { n_o[pe] = out.eo; n_d[pe] = out.ed; }
-            const uint32_t ps = warp_push(&st.counters[2], out.push_sh);
+            if (out.push_ext) { st.ext_o[cur ^ 1][pe] = out.eo; st.ext_d[cur ^ 1][pe] = out.ed; }
+            const uint32_t ps = warp_push(&st.counters[sh], out.push_sh);
             if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
         }
     }

@@ -24,7 +24,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, fused_launches = 3, fused_shade_from = 3; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -264,27 +264,48 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         ctx->stats.kernel_launches++;
     }
     const int g128 = grid_for(ctx, n_slots, 128);
+    // option "fused_launches": bit 0 = k_trace_fused (shadow rays of the previous bounce + this bounce's extension rays in one
+    // launch), bit 1 = k_shade_all (all shading buckets in one launch); 0 = one launch per queue and per bucket
+    const bool fuse_trace = (ctx->opt.fused_launches & 1) != 0;
     for (uint32_t stage = 0; stage <= R.max_depth; ++stage) {
         const int cur = (int)(stage & 1u);
+        // the first bounces hold most of the vertices and run faster as one launch per bucket (17.6 vs 22.1 ms of shading per 33 M
+        // paths); from bounce "fused_shade_from" on the queues are short and launch latency dominates
+        const bool fuse_shade = (ctx->opt.fused_launches & 2) != 0 && stage >= (uint32_t)ctx->opt.fused_shade_from;
+        // size of the shadow queue this bounce's shading appends to: ping-pong 2 / 3 with the fused trace (it resets the one it is
+        // not reading), always 2 otherwise (k_trace_closest resets it)
+        const int sh = fuse_trace ? 2 + cur : 2, sh_prev = 2 + (int)((stage + 1u) & 1u);
         {
             StageTimer t(ctx, STAGE_CLOSEST, stream);
-            if (count) k_trace_closest<true><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
-            else k_trace_closest<false><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
+            if (fuse_trace) {
+                if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, cur, sh_prev);
+                else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, cur, sh_prev);
+            } else {
+                if (count) k_trace_closest<true><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
+                else k_trace_closest<false><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
+            }
+            ctx->stats.kernel_launches++;
         }
         {
             StageTimer t(ctx, STAGE_SHADE, stream);
-            k_shade<0><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<1><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<2><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
-            k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, stage);
+            if (fuse_shade) {
+                k_shade_all<<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                ctx->stats.kernel_launches++;
+            } else {
+                k_shade<0><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<1><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<2><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                ctx->stats.kernel_launches += 8;
+            }
         }
-        ctx->stats.kernel_launches += 9;
         if (ctx->opt.debug_path_log && n_slots == 1) debug_dump(ctx, "after shade", stage, cur ^ 1, stream);
-        if (R.integrator != TCPT_INTEGRATOR_PT && stage < R.max_depth) {
+        // k_shade of bounce max_depth ends every remaining path before it samples a light or a direction: nothing left to trace
+        if (!fuse_trace && R.integrator != TCPT_INTEGRATOR_PT && stage < R.max_depth) {
             StageTimer t(ctx, STAGE_SHADOW, stream);
             if (count) k_trace_shadow<true><<<g128, 128, 0, stream>>>(sc, R, st);
             else k_trace_shadow<false><<<g128, 128, 0, stream>>>(sc, R, st);
@@ -328,7 +349,18 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     const uint32_t rows = R.row_offset < p->height ? (p->height - R.row_offset + R.row_stride - 1) / R.row_stride : 0;
     const uint64_t owned = (uint64_t)rows * p->width;
     if (owned == 0 || s0 == s1) return TCPT_OK;
-    const uint64_t budget = p->max_slots ? p->max_slots : (32u << 20);  // 33.5 M path slots (about 9 GB of wavefront buffers)
+    // Path-slot budget of one pass.  Every pass pays a fixed latency (about 35 launches whose deep-bounce queues are nearly
+    // empty: 4 to 8 ms on the 4K frame), so passes are made as large as memory comfortably allows: up to 128 Mi slots
+    // (264 B each: 34 GB of the 180 GB), never more than 45 % of the memory that is free.
+    uint64_t budget = p->max_slots;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)16 << 30; }
+        const uint64_t avail = (uint64_t)free_b + (uint64_t)ctx->st_capacity * 264u;
+        budget = (uint64_t)(0.45 * (double)avail) / 264u;
+        if (budget > (128ull << 20)) budget = 128ull << 20;
+        if (budget < (1ull << 20)) budget = 1ull << 20;
+    }
     const uint32_t np = (uint32_t)(owned < budget ? owned : budget);
     uint32_t sc_per_pass = (uint32_t)(budget / np);
     if (sc_per_pass < 1) sc_per_pass = 1;
@@ -430,6 +462,8 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "stage_timing") ctx->opt.stage_timing = value;
     else if (n == "debug_path_log") ctx->opt.debug_path_log = value;
     else if (n == "sobol_prefix") ctx->opt.sobol_prefix = value;
+    else if (n == "fused_launches") ctx->opt.fused_launches = value;
+    else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "sobol_prefix_mb") ctx->opt.sobol_prefix_mb = value;
     else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
     else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
