@@ -185,7 +185,12 @@ struct Traversal {
                 cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
                 const tcpt_flat_primitive& P = sc.primitives[cur_prim];
                 const tcpt_flat_geometry& G = sc.geometries[P.geometry];
-                ray_setup(rl, xf_point(P.r2l, o), xf_vector(P.r2l, d));
+                // local_to_render.inverse() * ray (primitive/impls/triangle_mesh.rs:97).  An instance without rotation or scale maps the
+                // direction onto the same bits, and everything ray_setup derives (1/d, the shear constants) depends on the direction
+                // alone: keep the Render-space values instead of six IEEE divisions (ray_setup was 12 % of the kernel's instructions)
+                const float3 ol = xf_point(P.r2l, o), dl = xf_vector(P.r2l, d);
+                if (__float_as_uint(dl.x) == __float_as_uint(d.x) && __float_as_uint(dl.y) == __float_as_uint(d.y) && __float_as_uint(dl.z) == __float_as_uint(d.z)) { rl = rw; rl.o = ol; }
+                else ray_setup(rl, ol, dl);
                 node_base = G.node_base; slot_base = G.slot_base;
                 blas_sp = sp;
                 node = node_base;  // entry record: tests the BLAS root box
@@ -244,25 +249,44 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
     Traversal T;
     T.pend_cnt = 0;
     uint32_t ray = NONE, fin = NONE;
-    bool exhausted = false;
+    // Ray indices are reserved from the global counter a CHUNK at a time and handed out from a warp-local pool, so most refills
+    // cost no global atomic (fourth profile: the warp waiting on the counter's round trip at every refill was the top stall).
+    // The chunk shrinks with the queue so that short queues (deep bounces) still spread over the whole grid.
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t chunk = n / (n_warps * 8u);
+    chunk = chunk < 32u ? 32u : (chunk > 512u ? 512u : chunk);
+    uint32_t pool = 0, pool_end = 0;  // warp-uniform: indices [pool, pool_end) belong to this warp
+    bool drained = false;             // the global counter has passed n
     for (;;) {
-        if (fin != NONE) { commit(fin, T.best); fin = NONE; }
         const uint32_t idle = __ballot_sync(FULL, ray == NONE);
-        if (idle != 0u && !exhausted) {
-            const uint32_t n_idle = (uint32_t)__popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(work, n_idle);
-            base = __shfl_sync(FULL, base, 0);
+        const uint32_t n_idle = (uint32_t)__popc(idle);
+        const uint32_t left = pool_end - pool;
+        const bool fetch = n_idle > left && !drained;
+        uint32_t fetched = 0;
+        if (fetch && lane == 0) fetched = atomicAdd(work, chunk);  // in flight while the finished rays are committed
+        if (fin != NONE) { commit(fin, T.best); fin = NONE; }
+        if (n_idle != 0u) {
+            uint32_t base_b = 0;
+            if (fetch) {
+                base_b = __shfl_sync(FULL, fetched, 0);
+                drained = base_b + chunk >= n;
+            }
             if (ray == NONE) {
-                const uint32_t mine = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                // the first `left` idle lanes take what remains of the old chunk, the others start the new one
+                const uint32_t r = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                uint32_t mine = NONE;
+                if (r < left) mine = pool + r;
+                else if (fetch) mine = base_b + (r - left);
                 if (mine < n) {
                     const float4 o = q_o[mine], d = q_d[mine];
                     T.init(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
                     ray = mine;
                 }
             }
-            exhausted = base + n_idle >= n;
+            if (fetch) { pool = base_b + (n_idle - left); pool_end = base_b + chunk; if (pool_end > n) pool_end = n; if (pool > pool_end) pool = pool_end; }
+            else { pool += n_idle; if (pool > pool_end) pool = pool_end; }
         }
+        const bool exhausted = drained && pool >= pool_end;
         if (__ballot_sync(FULL, ray != NONE) == 0u) break;  // nothing in flight and nothing left to fetch
         const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;
         uint32_t n_idle_now;

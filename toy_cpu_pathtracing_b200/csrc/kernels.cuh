@@ -135,7 +135,7 @@ __device__ __forceinline__ void commit_shadow(const DScene& sc, const DRender& R
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
+__global__ void __launch_bounds__(128, 6) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                         float4* __restrict__ hit0, uint2* __restrict__ hit1, const __grid_constant__ DState st, int cur) {
     const uint32_t n = st.counters[cur];
     uint32_t* bcount = st.counters + 4 + 8 * cur;  // this bounce's bucket sizes (zeroed one bounce ago)
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(const __grid_constant__ D
 
 // ---------------------------------------------------------------- K3/K4 shadow rays + visible-branch accumulation
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_shadow(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st) {
+__global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st) {
     const uint32_t n = st.counters[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st.stats[1], (unsigned long long)n);
     uint32_t nb = 0, nt = 0;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128) k_trace_shadow(const __grid_constant__ DS
 // `cur` = parity of the extension queue to trace, `sh` = index (2 or 3) of the shadow-queue size to read; the sizes the next
 // k_shade appends to (counters[cur ^ 1], counters[sh ^ 1]) were last read one launch ago and are reset here.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
+__global__ void __launch_bounds__(128, 6) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
     const uint32_t n_sh = st.counters[sh], n = st.counters[cur];
     uint32_t* bcount = st.counters + 4 + 8 * cur;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
