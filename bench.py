@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--max-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=0.05, help="seconds between NVML clock samples during the timed region")
     ap.add_argument("--opt", action="append", default=[], help="developer knob: libtcpt option as name=value (tcpt_set_option), repeatable")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -61,8 +62,8 @@ class ClockSampler:
     (ctypes calls into libtcpt release the GIL), nvidia-smi polling as a fallback when pynvml is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread, self.stop = index, [], None, None, False
+    def __init__(self, index: int, period: float = 0.05):
+        self.index, self.rows, self.proc, self.thread, self.stop, self.period = index, [], None, None, False, period
         self.sm, self.sm_max, self.reasons = [], None, set()
 
     def _nvml_loop(self, nv, h):
@@ -75,7 +76,7 @@ class ClockSampler:
                 self.reasons |= {k for k, b in bits.items() if r & b}
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.period)
 
     def __enter__(self):
         try:
@@ -270,7 +271,7 @@ def main_gpu(args, wl):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tot = {"rays": 0, "paths": 0, "closest": 0, "shadow": 0, "launches": 0, "closest_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "gen_ms": 0.0, "film_ms": 0.0, "passes": 0}
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, args.clock_period) as clk:
         e0.record(stream)
         for k in range(args.steps):
             st = step(args.warmup + k)

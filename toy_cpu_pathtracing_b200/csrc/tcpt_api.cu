@@ -58,6 +58,7 @@ struct tcpt_ctx {
     // ZSobol pixel-prefix table (DSampler::sample_index), cached per (width, height, log2_spp); grows when more dimensions are asked for
     uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0; size_t prefix_cap = 0;
     double prefix_build_ms = 0.0;
+    uint64_t default_slots = 0;  // path-slot budget of a pass when the caller gives none (see render_into)
 };
 
 namespace {
@@ -354,12 +355,16 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     // (264 B each: 34 GB of the 180 GB), never more than 45 % of the memory that is free.
     uint64_t budget = p->max_slots;
     if (budget == 0) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)16 << 30; }
-        const uint64_t avail = (uint64_t)free_b + (uint64_t)ctx->st_capacity * 264u;
-        budget = (uint64_t)(0.45 * (double)avail) / 264u;
-        if (budget > (128ull << 20)) budget = 128ull << 20;
-        if (budget < (1ull << 20)) budget = 1ull << 20;
+        if (ctx->default_slots == 0) {  // asked once per context: cudaMemGetInfo was measured to stall a render by up to 80 ms
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)16 << 30; }
+            const uint64_t avail = (uint64_t)free_b + (uint64_t)ctx->st_capacity * 264u;
+            uint64_t b = (uint64_t)(0.45 * (double)avail) / 264u;
+            if (b > (128ull << 20)) b = 128ull << 20;
+            if (b < (1ull << 20)) b = 1ull << 20;
+            ctx->default_slots = b;
+        }
+        budget = ctx->default_slots;
     }
     const uint32_t np = (uint32_t)(owned < budget ? owned : budget);
     uint32_t sc_per_pass = (uint32_t)(budget / np);
