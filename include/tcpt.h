@@ -129,6 +129,11 @@ int tcpt_scene_add_material(tcpt_ctx* ctx, const tcpt_material_desc* desc);
 int tcpt_scene_add_primitive(tcpt_ctx* ctx, int geometry, int material, const float local_to_world[16] /*column major*/);
 int tcpt_scene_add_env_light(tcpt_ctx* ctx, float intensity, const float* rgb /*h*w*3*/, uint32_t width, uint32_t height,
                              const float local_to_world[16]);                    /* EnvironmentLight::new environment_light.rs:34-84 */
+/* CreatePrimitiveDesc::{PointLight,SpotLight,DirectionalLight}Primitive (primitive/repository.rs:108-134; point_light.rs:22-35,
+ * spot_light.rs:28-44, directional_light.rs:23-38).  The light sits at the local origin / shines along local +z; angles in radians. */
+enum { TCPT_LIGHT_POINT = 3, TCPT_LIGHT_SPOT = 4, TCPT_LIGHT_DIRECTIONAL = 5 };   /* = tcpt_flat_primitive.kind */
+int tcpt_scene_add_delta_light(tcpt_ctx* ctx, int kind, float intensity, const tcpt_spectrum_param* spectrum, float angle_inner, float angle_outer,
+                               const float local_to_world[16]);
 /* Scene::build(&camera): bakes world_to_render = translate(-cam_pos), builds BLAS/TLAS with the reference's exact SAH topology,
  * flattens to the device layout and uploads (scene.rs:64-76, bvh.rs:92-295). */
 int tcpt_scene_build(tcpt_ctx* ctx, const float cam_pos[3]);

@@ -43,20 +43,24 @@ typedef struct {
     uint32_t has_uv;
 } tcpt_flat_geometry;
 
+typedef struct { int32_t kind; float c[3]; float scale; int32_t texture; } tcpt_flat_spectrum; /* kind: 0 const(c[0]) 1 sigmoid(c) 2 sigmoid*scale*D65 3 D65 4 texture 5 dense preset table (texture = preset id) */
+
 typedef struct {
     float l2r[12];     /* local_to_render, 3 rows x 4 columns stored column major 4x(x,y,z): c0.xyz c1.xyz c2.xyz c3.xyz */
     float r2l[12];     /* inverse (glam Mat4::inverse), same storage */
     int32_t geometry;  /* -1 for the environment light */
     int32_t material;
-    int32_t kind;      /* 0 mesh, 1 emissive mesh, 2 environment light */
+    int32_t kind;      /* 0 mesh, 1 emissive mesh, 2 environment light, 3 point light, 4 spot light, 5 directional light */
     int32_t light_index; /* position in light_list or -1 */
     uint32_t identity; /* l2r is exactly the identity */
     uint32_t area_base; /* emissive: into area_list / area_table (tri_count entries) */
     float area_sum;
     int32_t env;
+    /* delta lights (kind 3..5): intensity, spectrum, spot cone angles, DirectionalLight::preprocess area = pi r^2 of the scene's bounding sphere */
+    float light_intensity, angle_inner, angle_outer, dir_area;
+    tcpt_flat_spectrum light_spectrum;
 } tcpt_flat_primitive;
 
-typedef struct { int32_t kind; float c[3]; float scale; int32_t texture; } tcpt_flat_spectrum; /* kind: 0 const(c[0]) 1 sigmoid(c) 2 sigmoid*scale*D65 3 D65 4 texture 5 dense preset table (texture = preset id) */
 typedef struct { int32_t is_texture; float value; int32_t texture; int32_t gamma_corrected; } tcpt_flat_float;
 typedef struct {
     int32_t type;

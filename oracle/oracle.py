@@ -43,7 +43,7 @@ def lib() -> C.CDLL:
         _lib.orc_scene_new.restype = C.c_void_p
         _lib.orc_build.restype = C.c_double
         for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
-                     "orc_add_env_light", "orc_set_modes", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
+                     "orc_add_env_light", "orc_add_delta_light", "orc_set_modes", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
                      "orc_sampler_stream", "orc_get_bvh", "orc_get_mesh_tangents"):
             getattr(_lib, name).argtypes = None
     return _lib
@@ -97,6 +97,9 @@ class OracleScene:
     def add_env_light(self, intensity, rgb, l2w):
         hgt, wid = rgb.shape[:2]
         return self.l.orc_add_env_light(_vp(self.h), C.c_float(intensity), _p(rgb), C.c_uint32(wid), C.c_uint32(hgt), _p(l2w))
+
+    def add_delta_light(self, kind, intensity, spectrum, angle_inner, angle_outer, l2w):
+        return self.l.orc_add_delta_light(_vp(self.h), kind, C.c_float(intensity), C.byref(spectrum), C.c_float(angle_inner), C.c_float(angle_outer), _p(l2w))
 
     def build(self, cam_pos) -> float:
         a = np.asarray(cam_pos, dtype=f32)

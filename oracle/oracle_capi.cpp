@@ -163,6 +163,17 @@ int orc_add_env_light(void* h, float intensity, const float* rgb, uint32_t w, ui
     return (int)s->scene.primitives.size() - 1;
 }
 
+// CreatePrimitiveDesc::{PointLight,SpotLight,DirectionalLight}Primitive (primitive/repository.rs:108-134); kind = PRIM_POINT_LIGHT ...
+int orc_add_delta_light(void* h, int kind, float intensity, const orc_spectrum_param* spectrum, float angle_inner, float angle_outer, const float local_to_world[16]) {
+    OrcScene* s = (OrcScene*)h;
+    if (kind < PRIM_POINT_LIGHT || kind > PRIM_DIRECTIONAL_LIGHT || !s->tables_set) return -1;
+    Primitive p; p.kind = kind; p.light_intensity = intensity; p.angle_inner = angle_inner; p.angle_outer = angle_outer;
+    p.light_spectrum = conv_spec(s->scene.T, *spectrum).spectrum;
+    p.local_to_world = mat_from(local_to_world);
+    s->scene.primitives.push_back(std::move(p));
+    return (int)s->scene.primitives.size() - 1;
+}
+
 // faithful = reference cost model (exhaustive traversal is always used; this adds per-call inverses/attribute work);
 // literal_build = O(N^2) SAH sweep exactly as the reference, else the prefix/suffix sweep (bit-identical result)
 void orc_set_modes(void* h, int faithful, int literal_build) { OrcScene* s = (OrcScene*)h; s->scene.faithful = faithful != 0; s->scene.literal_build = literal_build != 0; }

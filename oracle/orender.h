@@ -145,6 +145,43 @@ struct PathTracer {
             *contribution = f * is.radiance / (is.pdf_dir * p_light);
             return;
         }
+        const Primitive& LP = scene.primitives[prim];
+        if (LP.kind == PRIM_POINT_LIGHT || LP.kind == PRIM_SPOT_LIGHT) {
+            // PointLight / SpotLight::calculate_intensity (point_light.rs:75-88, spot_light.rs:98-122) + evaluate_delta_point_light (common.rs:23-55)
+            Vec3 lpos = transform_point3(LP.local_to_render, Vec3(0, 0, 0));
+            SampledSpectrum inten = LP.light_spectrum.sample(scene.T, wl) * LP.light_intensity;
+            if (LP.kind == PRIM_SPOT_LIGHT) {
+                Vec3 wi_l = normalize(lpos - sp.position);
+                // quirk: the cosine of the angle to the axis is compared with the cone ANGLES themselves, smoothstep(outer, inner, cos)
+                float cos_theta = transform_vector3(LP.render_to_local, wi_l).z;
+                float t = clampf((cos_theta - LP.angle_outer) / (LP.angle_inner - LP.angle_outer), 0.0f, 1.0f);
+                inten = inten * (t * t * (3.0f - 2.0f * t));
+            }
+            Vec3 dv = lpos - sp.position;
+            Ray shadow = Ray{sp.position, normalize(dv)}.move_forward(1e-4f);
+            float t = length(dv) - 2.0f * 1e-4f;
+            if (probe.shadow_rays) { probe.shadow_rays->push_back(shadow); probe.shadow_tmax->push_back(t); }
+            if (scene.intersect_p(shadow, t, st)) return;
+            Vec3 wo = transform_vector3(r2t, hit.wo), wi = transform_vector3(r2t, normalize(dv));
+            make_tsp();
+            SampledSpectrum f = material_evaluate(mc, mat, wl, wo, wi, tsp);
+            *contribution = f * inten / (length_squared(dv) * p_light);  // delta lights: no MIS (weight stays 1)
+            return;
+        }
+        if (LP.kind == PRIM_DIRECTIONAL_LIGHT) {
+            // DirectionalLight::calculate_intensity (directional_light.rs:92-107) + evaluate_delta_directional_light (common.rs:58-79):
+            // the shadow ray starts ON the surface (no forward offset) and is unbounded
+            Vec3 dir = normalize(transform_vector3(LP.local_to_render, Vec3(0, 0, 1)));
+            SampledSpectrum inten = LP.light_spectrum.sample(scene.T, wl) * LP.light_intensity;
+            Ray shadow = Ray{sp.position, dir};
+            if (probe.shadow_rays) { probe.shadow_rays->push_back(shadow); probe.shadow_tmax->push_back(std::numeric_limits<float>::max()); }
+            if (scene.intersect_p(shadow, std::numeric_limits<float>::max(), st)) return;
+            Vec3 wo = transform_vector3(r2t, hit.wo), wi = transform_vector3(r2t, normalize(dir));
+            make_tsp();
+            SampledSpectrum f = material_evaluate(mc, mat, wl, wo, wi, tsp);
+            *contribution = f * inten / p_light;
+            return;
+        }
         Scene::AreaSample as = scene.sample_area_light(mc, prim, sp.position, wl, s, uv);
         Vec3 dv = as.position - sp.position;
         Ray shadow = Ray{sp.position, normalize(dv)}.move_forward(1e-4f);

@@ -125,7 +125,7 @@ inline Mat4 shading_transform(const SurfaceInteraction& si) {
     return inverse(Mat4::from_cols3(t, b, n));
 }
 
-enum PrimitiveKind : int { PRIM_MESH = 0, PRIM_EMISSIVE_MESH = 1, PRIM_ENV_LIGHT = 2 };
+enum PrimitiveKind : int { PRIM_MESH = 0, PRIM_EMISSIVE_MESH = 1, PRIM_ENV_LIGHT = 2, PRIM_POINT_LIGHT = 3, PRIM_SPOT_LIGHT = 4, PRIM_DIRECTIONAL_LIGHT = 5 };
 
 struct EnvLight {
     float intensity = 1.0f;
@@ -148,6 +148,12 @@ struct Primitive {
     std::vector<float> area_list, area_table;
     float area_sum = 0;
     int env = -1;
+    // delta lights (primitive/impls/{point,spot,directional}_light.rs)
+    float light_intensity = 0.0f, angle_inner = 0.0f, angle_outer = 0.0f;
+    Spectrum light_spectrum;
+    float dir_area = 0.0f;  // DirectionalLight::preprocess: pi * r^2 of the scene's bounding sphere
+    bool is_light() const { return kind != PRIM_MESH; }
+    bool is_delta() const { return kind >= PRIM_POINT_LIGHT; }
 };
 
 struct LightSampler {
@@ -189,9 +195,19 @@ struct Scene {
             ib.push_back(transform_bounds(primitives[i].local_to_render, meshes[primitives[i].geometry].bounds));
         }
         tlas.build(ib, literal_build);
+        // LightSamplerFactory::build (light_sampler.rs:168-187): every light in primitive order, preprocess(scene_bounds) on the way
         light_list.clear();
-        for (size_t i = 0; i < primitives.size(); ++i)
-            if (primitives[i].kind == PRIM_EMISSIVE_MESH || primitives[i].kind == PRIM_ENV_LIGHT) light_list.push_back((int)i);
+        for (size_t i = 0; i < primitives.size(); ++i) {
+            Primitive& p = primitives[i];
+            if (!p.is_light()) continue;
+            if (p.kind == PRIM_DIRECTIONAL_LIGHT) {  // directional_light.rs:85-89, Bounds::bounding_sphere (math/src/bounds.rs:73-77)
+                Bounds sb = tlas.nodes.empty() ? Bounds{Vec3(0, 0, 0), Vec3(0, 0, 0)} : tlas.nodes[0].bounds;  // PrimitiveBvh::scene_bounds (primitive/bvh.rs:139-141)
+                Vec3 center = (sb.mn + sb.mx) * 0.5f;
+                float radius = length(sb.mx - center);
+                p.dir_area = PI_F * radius * radius;
+            }
+            light_list.push_back((int)i);
+        }
     }
 
     void init_emissive(Primitive& p) const {
@@ -304,6 +320,12 @@ struct Scene {
     SampledSpectrum phi(const MaterialContext& c, int prim_index, const SampledWavelengths& wl) const {
         const Primitive& p = primitives[prim_index];
         if (p.kind == PRIM_EMISSIVE_MESH) return emissive_average_intensity(c, materials[p.material], wl) * p.area_sum;  // emissive_triangle_mesh.rs:166-173
+        if (p.kind == PRIM_POINT_LIGHT) return p.light_spectrum.sample(T, wl) * (4.0f * PI_F * p.light_intensity);  // point_light.rs:70-72: 4.0 * PI * intensity * spectrum
+        if (p.kind == PRIM_SPOT_LIGHT) {  // spot_light.rs:84-95: intensity * spectrum * 2.0 * PI * (...), left to right
+            float ci = std::cos(p.angle_inner), co = std::cos(p.angle_outer);
+            return p.light_spectrum.sample(T, wl) * p.light_intensity * 2.0f * PI_F * ((1.0f - ci) + (ci - co) / 2.0f);
+        }
+        if (p.kind == PRIM_DIRECTIONAL_LIGHT) return p.light_spectrum.sample(T, wl) * (p.light_intensity * p.dir_area);  // directional_light.rs:80-83
         const EnvLight& e = envs[p.env];
         return e.intensity * e.integrated.sample(T, wl);  // environment_light.rs:299-301
     }

@@ -18,7 +18,7 @@ def recorded_rays(b, integrator, sampler, spp, window):
     return rays, shadow
 
 
-@pytest.mark.parametrize("scene_id,kw", [(3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
+@pytest.mark.parametrize("scene_id,kw", [(2, {}), ("lights", {"directional": True}), (3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
 def test_hit_records_bit_exact_on_path_rays(bundle_factory, scene_id, kw):
     """Every ray a MIS render issues inside a pixel window (camera, bounce and shadow rays, incl. the non-identity instance of
     scene 17 and the three instances of scene 19): closest hits and any-hits must equal the oracle's exhaustive traversal."""
@@ -77,11 +77,14 @@ CASES = [(3, {}, "pt"), (3, {}, "nee"), (3, {}, "mis"), (10, {}, "pt"), (10, {},
          (17, {}, "mis"), (17, {"coat": False}, "mis"), (19, {}, "pt"), (19, {}, "mis"),
          # MetalMaterial / ConductorBsdf (scene 6 smooth, scene 7 rough + scaled instances), GlassMaterial with a
          # dispersive eta -> terminate_secondary (scene 8), solid plastic (scene 9)
-         (6, {}, "pt"), (6, {}, "mis"), (7, {}, "nee"), (7, {}, "mis"), (8, {}, "pt"), (8, {}, "nee"), (8, {}, "mis"), (9, {}, "mis")]
+         (6, {}, "pt"), (6, {}, "mis"), (7, {}, "nee"), (7, {}, "mis"), (8, {}, "pt"), (8, {}, "nee"), (8, {}, "mis"), (9, {}, "mis"),
+         # delta lights.  Scene 2 = the reference's point-light Cornell box; "lights" = point + spot + directional
+         # light next to the area lamp (the reference has no scene with a spot or a directional light)
+         (2, {}, "pt"), (2, {}, "nee"), (2, {}, "mis"), ("lights", {}, "nee"), ("lights", {}, "mis"), ("lights", {"directional": True}, "mis")]
 
 
 @pytest.mark.parametrize("sampler", ["sobol", "random"])
-@pytest.mark.parametrize("scene_id,kw,integrator", CASES, ids=[f"s{c[0]}{'nocoat' if c[1] else ''}-{c[2]}" for c in CASES])
+@pytest.mark.parametrize("scene_id,kw,integrator", CASES, ids=[f"s{c[0]}{''.join(c[1])}-{c[2]}" for c in CASES])
 def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler):
     """Same scene, integrator, sampler, resolution and spp on both sides: identical ray counts (every path takes the same
     decisions) and a film within the stated tolerance."""
@@ -94,7 +97,11 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
     # diverged paths the mean ABSOLUTE error stays near q until spp >> 1/q, so this case gets its own bound; the per-path
     # test below checks that the other 99.9 % agree to the stated tolerance.
     w, h, spp = 64, 48, 32
-    mre_tol = 5e-3 if scene_id == 9 else MRE_TOL
+    # A directional light is the second knife edge: its shadow rays start exactly on the surface (no offset, common.rs:70-72), so
+    # self-shadowing is decided by the rounding noise of the hit position and flips wherever an earlier sinf/cosf differed by an ulp
+    # (first vertices, whose positions are bit-identical, agree to 1e-8; from the second vertex on about 0.3 % of the paths flip).
+    knife_edge = scene_id == 9 or bool(kw.get("directional"))
+    mre_tol = 5e-3 if knife_edge else MRE_TOL
     b = bundle_factory(scene_id, w, h, **kw)
     img = b.image(integrator, spp).render(sampler)
     acc, srgb, st = b.oracle.render(b.oparams(integrator, sampler, spp))
@@ -105,23 +112,26 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
     assert abs(img.stats["shadow_rays"] - st["shadow_rays"]) <= 1e-3 * max(1, st["shadow_rays"])
     g, o = img.accumulators / spp, acc / spp
     assert np.isfinite(g).all()
+    if not np.abs(o).any():     # scene 2 under pt: a point light cannot be hit, the frame is black on both sides
+        assert not np.abs(g).any()
+        return
     mre = np.abs(g - o).mean() / np.abs(o).mean()
     assert mre <= mre_tol, f"mean relative error {mre:.3e}"
     # tone-mapped output: a single path that branches differently (last-ulp transcendental at a threshold) can move one pixel of
     # a high-variance pt frame visibly, so the bound is on the 99.9th percentile and the mean, not the maximum
     d = np.abs(img.pixels - srgb)
-    if scene_id == 9:   # about 1.5 % of the pixels hold one diverged path at 32 spp (see above): bound the bulk, not the tail
-        assert np.quantile(d, 0.97) <= 1e-3 and d.mean() <= 2e-3
+    if knife_edge:   # a few percent of the pixels hold one diverged path at 32 spp (see above): bound the bulk, not the tail
+        assert np.quantile(d, 0.93) <= 1e-3 and d.mean() <= 2e-3
     else:
         assert np.quantile(d, 0.999) <= 2e-2 and d.mean() <= 1e-4
 
 
-@pytest.mark.parametrize("scene_id,integrator,sampler", [(3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
+@pytest.mark.parametrize("scene_id,integrator,sampler", [(2, "nee", "sobol"), ("lights", "mis", "sobol"), (3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
 def test_individual_paths_match_oracle(bundle_factory, scene_id, integrator, sampler):
     """Per-(pixel, sample) sensor contributions: the overwhelming majority identical to the last bits, the rest within 1e-4."""
     w, h, spp = 64, 48, 64
     b = bundle_factory(scene_id, w, h)
-    rng = np.random.default_rng(scene_id)
+    rng = np.random.default_rng(scene_id if isinstance(scene_id, int) else 1234)
     n = 5000
     xy = np.stack([rng.integers(0, w, n), rng.integers(0, h, n)], 1).astype(np.uint32)
     si = rng.integers(0, spp, n).astype(np.uint32)
@@ -130,7 +140,8 @@ def test_individual_paths_match_oracle(bundle_factory, scene_id, integrator, sam
     err = np.abs(g - o).max(1)
     rel = err / (np.abs(o).max(1) + 1e-6)
     assert (rel > 1e-4).mean() <= (5e-3 if scene_id == 9 else 2e-3), f"{(rel > 1e-4).sum()} of {n} paths differ by more than 1e-4"
-    assert (err == 0).mean() >= (0.4 if scene_id == 19 else 0.8)
+    # (scene 19: acos/atan2/sin/cos of the environment lookup in every path; "lights": the spot light's cos() sits in every light probability)
+    assert (err == 0).mean() >= (0.4 if scene_id == 19 else 0.7 if scene_id == "lights" else 0.8)
 
 
 def test_max_depth_and_seed_are_honoured(bundle_factory):

@@ -10,8 +10,8 @@ GOLD = sorted((Path(__file__).parent / "golden").glob("oracle_*.npz"))
 
 def _bundle(bundle_factory, name):
     parts = name.replace("oracle_scene", "").replace(".npz", "").split("_")
-    sid = int(parts[0])
-    kw = {"coat": False} if "nocoat" in parts else {}
+    sid = int(parts[0]) if parts[0].isdigit() else parts[0]
+    kw = {"coat": False} if "nocoat" in parts else {"directional": True} if "directional" in parts else {}
     return bundle_factory(sid, 24, 18, require_gpu=False, **kw), parts[-2], parts[-1]
 
 

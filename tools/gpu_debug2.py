@@ -9,7 +9,7 @@ from toy_cpu_pathtracing_b200 import capi, scenes
 from oracle import oracle
 
 std, tab = capi.load_tables()
-sid, integ, smp = int(sys.argv[1]), sys.argv[2], sys.argv[3]
+sid, integ, smp = (int(sys.argv[1]) if sys.argv[1].isdigit() else sys.argv[1]), sys.argv[2], sys.argv[3]
 spp = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 w, h = 64, 48
 sc = tp.Scene(device=0); cam = tp.Camera(45.0, w, h)

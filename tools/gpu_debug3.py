@@ -7,7 +7,7 @@ import toy_cpu_pathtracing_b200 as tp
 from toy_cpu_pathtracing_b200 import capi, scenes
 from oracle import oracle
 std, tab = capi.load_tables()
-sid, integ, smp, spp = int(sys.argv[1]), sys.argv[2], sys.argv[3], int(sys.argv[4])
+sid, integ, smp, spp = (int(sys.argv[1]) if sys.argv[1].isdigit() else sys.argv[1]), sys.argv[2], sys.argv[3], int(sys.argv[4])
 w, h = 64, 48
 sc = tp.Scene(device=0); cam = tp.Camera(45.0, w, h)
 scenes.load_scene(sid, sc, cam); sc.build(cam)

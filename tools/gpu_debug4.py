@@ -8,7 +8,7 @@ import toy_cpu_pathtracing_b200 as tp
 from toy_cpu_pathtracing_b200 import capi, scenes
 from oracle import oracle
 std, tab = capi.load_tables()
-sid, integ, smp, spp, x, y, s = int(sys.argv[1]), sys.argv[2], sys.argv[3], *[int(a) for a in sys.argv[4:8]]
+sid, integ, smp, spp, x, y, s = (int(sys.argv[1]) if sys.argv[1].isdigit() else sys.argv[1]), sys.argv[2], sys.argv[3], *[int(a) for a in sys.argv[4:8]]
 w, h = 64, 48
 sc = tp.Scene(device=0); cam = tp.Camera(45.0, w, h)
 scenes.load_scene(sid, sc, cam); sc.build(cam)

@@ -14,7 +14,7 @@ from toy_cpu_pathtracing_b200 import capi, scenes  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 CASES = [(3, {}, "mis", "sobol"), (10, {}, "nee", "sobol"), (17, {}, "mis", "sobol"), (17, {"coat": False}, "pt", "random"), (19, {}, "mis", "sobol"),
-         (7, {}, "mis", "sobol"), (8, {}, "mis", "sobol")]
+         (7, {}, "mis", "sobol"), (8, {}, "mis", "sobol"), (2, {}, "nee", "sobol"), ("lights", {"directional": True}, "mis", "sobol")]
 W, H, SPP = 24, 18, 8
 
 
@@ -30,7 +30,7 @@ def main():
         closest, shadow = osc.record_rays(osc.params(W, H, 1, integ, smp, cam, window=(8, 6, 16, 12)))
         rays = np.concatenate([closest, np.full((len(closest), 1), np.finfo(np.float32).max, np.float32)], 1)[:400]
         hits, _, _ = osc.trace(rays)
-        name = f"oracle_scene{sid}{'_nocoat' if kw else ''}_{integ}_{smp}.npz"
+        name = f"oracle_scene{sid}{''.join('_' + ('nocoat' if k == 'coat' else k) for k in kw)}_{integ}_{smp}.npz"
         np.savez_compressed(out / name, acc=acc, rays=rays, hits=hits, counts=np.array([st["closest_rays"], st["shadow_rays"]], dtype=np.int64))
         print(name, acc.mean(), st["closest_rays"], st["shadow_rays"])
 

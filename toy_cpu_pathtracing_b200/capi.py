@@ -17,6 +17,7 @@ INTEGRATORS = {"pt": 0, "nee": 1, "mis": 2}
 SAMPLERS = {"random": 0, "sobol": 1}
 MAT_LAMBERT, MAT_EMISSIVE, MAT_PLASTIC, MAT_SIMPLE_PBR, MAT_CLEARCOAT_PBR, MAT_METAL, MAT_GLASS = range(7)
 SPEC_CONSTANT, SPEC_RGB_ALBEDO_SRGB, SPEC_RGB_ALBEDO_LINEAR, SPEC_D65, SPEC_TEXTURE_SRGB, SPEC_PRESET = range(6)
+LIGHT_POINT, LIGHT_SPOT, LIGHT_DIRECTIONAL = 3, 4, 5
 # TCPT_PRESET_* (include/tcpt.h): presets::au_eta() ... presets::glass_sf11_eta() in the order data/std_tables.bin stores them
 PRESETS = ["au_eta", "au_k", "ag_eta", "ag_k", "cu_eta", "cu_k", "al_eta", "al_k", "cu_zn_eta", "cu_zn_k",
            "glass_bk7_eta", "glass_baf10_eta", "glass_fk51a_eta", "glass_lasf9_eta", "glass_sf5_eta", "glass_sf10_eta", "glass_sf11_eta"]
@@ -71,7 +72,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "tcpt_create", "tcpt_destroy", "tcpt_last_error", "tcpt_set_option", "tcpt_set_tables", "tcpt_scene_clear",
     "tcpt_scene_add_mesh", "tcpt_scene_add_texture", "tcpt_scene_add_material", "tcpt_scene_add_primitive",
-    "tcpt_scene_add_env_light", "tcpt_scene_build", "tcpt_render", "tcpt_render_device", "tcpt_finalize_device",
+    "tcpt_scene_add_env_light", "tcpt_scene_add_delta_light", "tcpt_scene_build", "tcpt_render", "tcpt_render_device", "tcpt_finalize_device",
     "tcpt_get_stats", "tcpt_trace", "tcpt_trace_device", "tcpt_sampler_stream", "tcpt_path_samples", "tcpt_get_bvh",
     "tcpt_build_bvh_boxes", "tcpt_rgb_to_coeffs", "tcpt_get_mesh_tangents", "tcpt_upload_flat_scene",
 ]
@@ -97,6 +98,7 @@ def load_library() -> C.CDLL:
         "tcpt_scene_clear": (I, [P]), "tcpt_scene_add_mesh": (I, [P, fp, fp, fp, I, up, I]),
         "tcpt_scene_add_texture": (I, [P, bp, U, U, U]), "tcpt_scene_add_material": (I, [P, C.POINTER(MaterialDesc)]),
         "tcpt_scene_add_primitive": (I, [P, I, I, fp]), "tcpt_scene_add_env_light": (I, [P, F, fp, U, U, fp]),
+        "tcpt_scene_add_delta_light": (I, [P, I, F, C.POINTER(SpectrumParam), F, F, fp]),
         "tcpt_scene_build": (I, [P, fp]), "tcpt_render": (I, [P, C.POINTER(RenderParams), fp, fp]),
         "tcpt_render_device": (I, [P, C.POINTER(RenderParams), C.c_void_p, C.c_void_p]),
         "tcpt_finalize_device": (I, [P, C.c_void_p, U, U, U, C.c_void_p, C.c_void_p]),

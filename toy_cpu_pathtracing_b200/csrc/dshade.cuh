@@ -760,6 +760,11 @@ __device__ __noinline__ void light_table(const DScene& sc, const DWavelengths& w
         const tcpt_flat_primitive& P = sc.primitives[sc.light_list[i]];
         S4 phi;
         if (P.kind == 1) phi = emissive_radiance(sc, sc.materials[P.material], make_float2(0.5f, 0.5f), wl) * P.area_sum;  // emissive_triangle_mesh.rs:166-173
+        else if (P.kind == 3) phi = spectrum_sample(sc, spectrum_from_flat(P.light_spectrum), wl) * (4.0f * TCPT_PI * P.light_intensity);  // point_light.rs:70-72
+        else if (P.kind == 4) {  // spot_light.rs:84-95
+            const float ci = cosf(P.angle_inner), co = cosf(P.angle_outer);
+            phi = spectrum_sample(sc, spectrum_from_flat(P.light_spectrum), wl) * P.light_intensity * 2.0f * TCPT_PI * ((1.0f - ci) + (ci - co) / 2.0f);
+        } else if (P.kind == 5) phi = spectrum_sample(sc, spectrum_from_flat(P.light_spectrum), wl) * (P.light_intensity * P.dir_area);  // directional_light.rs:80-83
         else { const DEnv& e = sc.envs[P.env]; phi = e.intensity * spectrum_sample(sc, spectrum_from_flat(e.integrated), wl); }  // environment_light.rs:299-301
         lt.w[i] = s4_avg(phi);
         lt.sum += lt.w[i];

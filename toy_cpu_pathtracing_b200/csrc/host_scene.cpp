@@ -242,6 +242,18 @@ int HostScene::add_env_light(float intensity, const float* rgb, uint32_t w, uint
     return (int)primitives.size() - 1;
 }
 
+int HostScene::add_delta_light(int kind, float intensity, const tcpt_spectrum_param& spectrum, float angle_inner, float angle_outer, const float l2w[16]) {
+    if (!tables.set) { error = "add_delta_light: call tcpt_set_tables first"; return TCPT_ERR_INVALID; }
+    if (kind < TCPT_LIGHT_POINT || kind > TCPT_LIGHT_DIRECTIONAL) { error = "add_delta_light: unknown light kind"; return TCPT_ERR_INVALID; }
+    if (spectrum.kind == TCPT_SPEC_TEXTURE_SRGB) { error = "add_delta_light: a light spectrum cannot be a texture"; return TCPT_ERR_INVALID; }
+    if (spectrum.kind == TCPT_SPEC_PRESET && (spectrum.texture < 0 || (size_t)spectrum.texture * 470 >= tables.presets.size())) { error = "add_delta_light: spectrum preset id out of range"; return TCPT_ERR_INVALID; }
+    HostPrimitive p; p.kind = kind; p.light_intensity = intensity; p.angle_inner = angle_inner; p.angle_outer = angle_outer;
+    p.light_spectrum = resolve_spectrum(spectrum);
+    std::memcpy(p.local_to_world.m, l2w, 64);
+    primitives.push_back(std::move(p));
+    return (int)primitives.size() - 1;
+}
+
 // Convert the reference-order tree (pre-order inner/leaf records) into the device's child-pair records (include/tcpt_flat.h).
 // Returns the number of records appended; *max_leaf receives the largest leaf item count.
 static uint32_t put_nodes(const BuiltBvh& b, std::vector<tcpt_bvh_node>& out, uint32_t* max_leaf) {
@@ -362,7 +374,16 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     }
 
     // light list in primitive order (light_sampler.rs:168-187)
-    for (size_t i = 0; i < primitives.size(); ++i) if (primitives[i].kind == 1 || primitives[i].kind == 2) S.light_list.push_back((int)i);
+    for (size_t i = 0; i < primitives.size(); ++i) if (primitives[i].kind != 0) S.light_list.push_back((int)i);
+    // DirectionalLight::preprocess (directional_light.rs:85-89): bounding sphere of the scene bounds = root box of the TLAS
+    // (primitive/bvh.rs:139-141, math/src/bounds.rs:62-77)
+    float dir_area = 0.0f;
+    {
+        const Box sb = tlas.nodes[0].box;
+        const V3 center = scale(add(sb.lo, sb.hi), 0.5f);
+        const float radius = len3(sub(center, sb.hi));  // center.distance(max)
+        dir_area = 3.14159265358979323846f * radius * radius;
+    }
     if (S.light_list.size() > TCPT_MAX_LIGHTS) { error = "build: too many lights"; return TCPT_ERR_LIMIT; }
 
     for (size_t i = 0; i < primitives.size(); ++i) {
@@ -375,6 +396,8 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         fp.identity = m4_is_identity(l2r[i]) && m4_is_identity(inv);
         fp.light_index = -1;
         for (size_t k = 0; k < S.light_list.size(); ++k) if (S.light_list[k] == (int)i) fp.light_index = (int)k;
+        fp.light_intensity = p.light_intensity; fp.angle_inner = p.angle_inner; fp.angle_outer = p.angle_outer; fp.light_spectrum = p.light_spectrum;
+        fp.dir_area = p.kind == TCPT_LIGHT_DIRECTIONAL ? dir_area : 0.0f;
         fp.area_base = (uint32_t)S.area_list.size(); fp.area_sum = p.area_sum;
         S.area_list.insert(S.area_list.end(), p.area_list.begin(), p.area_list.end());
         S.area_table.insert(S.area_table.end(), p.area_table.begin(), p.area_table.end());

@@ -36,6 +36,8 @@ struct HostPrimitive {
     M4 local_to_world;
     std::vector<float> area_list, area_table;
     float area_sum = 0.0f;
+    float light_intensity = 0.0f, angle_inner = 0.0f, angle_outer = 0.0f;  // delta lights (kind 3..5)
+    tcpt_flat_spectrum light_spectrum{};
 };
 
 struct HostEnv {
@@ -83,6 +85,7 @@ class HostScene {
     int add_material(const tcpt_material_desc& d);
     int add_primitive(int geometry, int material, const float l2w[16]);
     int add_env_light(float intensity, const float* rgb, uint32_t w, uint32_t h, const float l2w[16]);
+    int add_delta_light(int kind, float intensity, const tcpt_spectrum_param& spectrum, float angle_inner, float angle_outer, const float l2w[16]);
     // Scene::build; fills `out`
     int build(const float cam_pos[3], FlatStorage& out);
 

@@ -326,11 +326,41 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
             const int lprim = sc.light_list[li];
             const tcpt_flat_primitive& LP = sc.primitives[lprim];
             // `s` picks the triangle of an area light; the environment light ignores it (scene.rs:127-153)
+            // (delta lights read neither: the reference draws s and uv before it looks at the kind of light, nee_renderer.rs:41-43)
             float s = 0.0f;
-            if (LP.kind == 2) smp.skip_1d(); else s = smp.get_1d();
-            const float2 luv = smp.get_2d();
-            float3 sh_dir; float sh_tmax; S4 pending;
-            if (LP.kind == 2) {
+            if (LP.kind == 1) s = smp.get_1d(); else smp.skip_1d();
+            float2 luv = make_float2(0.0f, 0.0f);
+            if (LP.kind <= 2) luv = smp.get_2d(); else { smp.skip_1d(); smp.skip_1d(); }
+            float3 sh_dir; float sh_tmax; S4 pending; float sh_eps = 1e-4f;
+            if (LP.kind == 3 || LP.kind == 4) {
+                // PointLight / SpotLight::calculate_intensity (point_light.rs:75-88, spot_light.rs:98-122) + evaluate_delta_point_light
+                // (common.rs:23-55); delta lights carry no MIS weight (nee_renderer.rs:52-77, mis_renderer.rs:65-100)
+                const float3 lpos = xf_point(LP.l2r, f3(0.0f, 0.0f, 0.0f));
+                S4 inten = spectrum_sample(sc, spectrum_from_flat(LP.light_spectrum), wl) * LP.light_intensity;
+                const float3 dv = lpos - hit.position;
+                const float3 wi_r = normalize(dv);
+                if (LP.kind == 4) {
+                    // quirk: the cosine to the cone axis is compared with the cone ANGLES, smoothstep(angle_outer, angle_inner, cos)
+                    const float cos_theta = xf_vector(LP.r2l, wi_r).z;
+                    const float t = clampf((cos_theta - LP.angle_outer) / (LP.angle_inner - LP.angle_outer), 0.0f, 1.0f);
+                    inten = inten * (t * t * (3.0f - 2.0f * t));
+                }
+                const float3 wi = m3_vector(r2t, wi_r);
+                S4 f; float bpdf;
+                material_eval_pdf<MT>(mc, mat, nmf, wl, wo, wi, ng_t, hit.uv, false, &f, &bpdf);
+                pending = thr * (f * inten / (length_squared(dv) * p_light));
+                sh_dir = wi_r; sh_tmax = length(dv) - 2.0f * 1e-4f;
+            } else if (LP.kind == 5) {
+                // DirectionalLight::calculate_intensity (directional_light.rs:92-107) + evaluate_delta_directional_light (common.rs:58-79):
+                // the shadow ray starts ON the surface (no forward offset) and is unbounded
+                const float3 dir = normalize(xf_vector(LP.l2r, f3(0.0f, 0.0f, 1.0f)));
+                const S4 inten = spectrum_sample(sc, spectrum_from_flat(LP.light_spectrum), wl) * LP.light_intensity;
+                const float3 wi = m3_vector(r2t, normalize(dir));
+                S4 f; float bpdf;
+                material_eval_pdf<MT>(mc, mat, nmf, wl, wo, wi, ng_t, hit.uv, false, &f, &bpdf);
+                pending = thr * (f * inten / p_light);
+                sh_dir = dir; sh_tmax = TCPT_FLT_MAX; sh_eps = 0.0f;
+            } else if (LP.kind == 2) {
                 // EnvironmentLight::sample_infinite_light (environment_light.rs:326-350) + evaluate_infinite_light{,_with_mis} (common.rs:174-241)
                 const DEnv& e = sc.envs[LP.env];
                 const uint32_t yy = sample_from_cdf(e.marginal, e.h, e.marginal_guide, e.guide_h, luv.x);
@@ -391,7 +421,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
                 pending = with_mis ? thr * c * w : thr * c;
                 sh_dir = wi_r; sh_tmax = distance - 2.0f * 1e-4f;
             }
-            const float3 so = hit.position + sh_dir * 1e-4f;  // move_forward(1e-4), no normal offset (common.rs:12,134-140)
+            const float3 so = sh_eps != 0.0f ? hit.position + sh_dir * sh_eps : hit.position;  // move_forward(1e-4), no normal offset (common.rs:12,134-140)
             out.push_sh = true;
             out.so = make_float4(so.x, so.y, so.z, sh_tmax);
             out.sd = make_float4(sh_dir.x, sh_dir.y, sh_dir.z, __uint_as_float(slot));

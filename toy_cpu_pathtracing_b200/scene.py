@@ -274,6 +274,18 @@ class Transform:
     def identity():
         return Transform()
 
+    @staticmethod
+    def from_translate(v):      # Transform::from_translate (math/src/transform.rs:100-104)
+        return Transform().translate(v)
+
+    @staticmethod
+    def from_scale(v):
+        return Transform().scale(v)
+
+    @staticmethod
+    def from_rotate_y(degrees):  # Transform::from_rotate(glam::Quat::from_rotation_y(deg.to_radians()))
+        return Transform().rotate_y(degrees)
+
     def translate(self, v):
         t = np.eye(4, dtype=f32)
         t[:3, 3] = np.asarray(v, dtype=f32)
@@ -307,9 +319,35 @@ class EnvironmentLightPrimitive:    # CreatePrimitiveDesc::EnvironmentLightPrimi
     transform: Transform = field(default_factory=Transform)
 
 
+@dataclass
+class PointLightPrimitive:          # CreatePrimitiveDesc::PointLightPrimitive { intensity, spectrum, transform }
+    intensity: float
+    spectrum: object
+    transform: Transform = field(default_factory=Transform)
+
+
+@dataclass
+class SpotLightPrimitive:           # CreatePrimitiveDesc::SpotLightPrimitive { angle_inner, angle_outer, intensity, spectrum, transform }
+    angle_inner: float
+    angle_outer: float
+    intensity: float
+    spectrum: object
+    transform: Transform = field(default_factory=Transform)
+
+
+@dataclass
+class DirectionalLightPrimitive:    # CreatePrimitiveDesc::DirectionalLightPrimitive { intensity, spectrum, transform }
+    intensity: float
+    spectrum: object
+    transform: Transform = field(default_factory=Transform)
+
+
 class CreatePrimitiveDesc:
     GeometryPrimitive = GeometryPrimitive
     EnvironmentLightPrimitive = EnvironmentLightPrimitive
+    PointLightPrimitive = PointLightPrimitive
+    SpotLightPrimitive = SpotLightPrimitive
+    DirectionalLightPrimitive = DirectionalLightPrimitive
 
 
 def load_obj(path) -> MeshData:
@@ -355,7 +393,7 @@ class SceneDescription:
         self.textures: list[np.ndarray] = []
         self._tex_ids: dict[int, tuple] = {}   # id(array) -> (index, array kept alive so the id stays unique)
         self.materials: list[capi.MaterialDesc] = []
-        self.primitives: list[tuple] = []   # ("geom", geometry, material, l2w16) | ("env", intensity, rgb, l2w16)
+        self.primitives: list[tuple] = []   # ("geom", geometry, material, l2w16) | ("env", intensity, rgb, l2w16) | ("delta", kind, intensity, spectrum, inner, outer, l2w16)
 
     # --- textures are de-duplicated by object identity so one image shared by several parameters is uploaded once
     def _texture(self, arr: np.ndarray) -> int:
@@ -434,7 +472,8 @@ class SceneDescription:
         return d
 
     def replay(self, backend):
-        """backend: add_mesh(pos, nrm, uv|None, idx) / add_texture(arr) / add_material(desc) / add_primitive(g, m, l2w) / add_env_light(i, rgb, l2w)"""
+        """backend: add_mesh(pos, nrm, uv|None, idx) / add_texture(arr) / add_material(desc) / add_primitive(g, m, l2w) / add_env_light(i, rgb, l2w) /
+        add_delta_light(kind, intensity, spectrum_param, angle_inner, angle_outer, l2w)"""
         for mesh in self.meshes:
             backend.add_mesh(mesh.positions, mesh.normals, mesh.uvs, mesh.indices)
         for t in self.textures:
@@ -444,6 +483,8 @@ class SceneDescription:
         for p in self.primitives:
             if p[0] == "geom":
                 backend.add_primitive(p[1], p[2], p[3])
+            elif p[0] == "delta":
+                backend.add_delta_light(*p[1:])
             else:
                 backend.add_env_light(p[1], p[2], p[3])
 
@@ -478,6 +519,11 @@ class Scene:
                 import cv2
                 tex = cv2.imread(str(tex), cv2.IMREAD_UNCHANGED)[..., 2::-1]
             d.primitives.append(("env", float(desc.intensity), np.ascontiguousarray(tex, dtype=f32), desc.transform.column_major()))
+        elif isinstance(desc, (PointLightPrimitive, SpotLightPrimitive, DirectionalLightPrimitive)):
+            kind = capi.LIGHT_POINT if isinstance(desc, PointLightPrimitive) else capi.LIGHT_SPOT if isinstance(desc, SpotLightPrimitive) else capi.LIGHT_DIRECTIONAL
+            spec = d._spectrum(SpectrumParameter.constant(desc.spectrum))
+            d.primitives.append(("delta", kind, float(desc.intensity), spec, float(getattr(desc, "angle_inner", 0.0)), float(getattr(desc, "angle_outer", 0.0)),
+                                 desc.transform.column_major()))
         else:
             raise TypeError(desc)
         return len(d.primitives) - 1
@@ -511,6 +557,9 @@ class Scene:
     def add_env_light(self, intensity, rgb, l2w):
         hgt, wid = rgb.shape[:2]
         return self.ctx.check(self.ctx.lib.tcpt_scene_add_env_light(self.ctx.handle, intensity, capi.as_ptr(rgb, C.c_float), wid, hgt, capi.as_ptr(l2w, C.c_float)))
+
+    def add_delta_light(self, kind, intensity, spectrum, angle_inner, angle_outer, l2w):
+        return self.ctx.check(self.ctx.lib.tcpt_scene_add_delta_light(self.ctx.handle, kind, intensity, C.byref(spectrum), angle_inner, angle_outer, capi.as_ptr(l2w, C.c_float)))
 
     # --- introspection used by the bit-exactness tests
     def get_bvh(self, which: int) -> np.ndarray:

@@ -107,6 +107,35 @@ def _camera_10(camera):
     camera.set_look_to((0.0, 3.5, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
 
 
+def load_scene_2(scene, camera):
+    """Cornell box without the ceiling lamp, lit by one point light at (0, 3, 0) (scene_2.rs:12-102): delta-light NEE, no MIS weight."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("box")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("hidari")), _lambert(0.9, 0.0, 0.0), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("migi")), _lambert(0.0, 0.9, 0.0), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("yuka")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("oku")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(GP(scene.load_obj(_asset("tenjou")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.PointLightPrimitive(10.0, presets.cie_illum_d6500(), Transform.from_translate((0.0, 3.0, 0.0))))
+    _camera_10(camera)
+
+
+def load_scene_lights(scene, camera, directional=False):
+    """Not a reference scene: the Cornell box under a point and a spot light next to the lamp, so that the power-weighted light choice
+    mixes delta and area lights (the reference builds Spot and Directional lights in no scene of its own;
+    primitive/impls/{spot,directional}_light.rs).  directional=True adds a directional light: its shadow rays start ON the surface
+    without any offset (common.rs:70-72), so whether a surface shadows itself is decided by rounding noise -- a knife edge of the
+    reference that parity tests have to bound separately."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    _cornell_rest(scene)
+    scene.create_primitive(CreatePrimitiveDesc.PointLightPrimitive(6.0, presets.cie_illum_d6500(), Transform.from_translate((-1.5, 2.0, 1.0))))
+    scene.create_primitive(CreatePrimitiveDesc.SpotLightPrimitive(0.3, 0.9, 3.0, RgbAlbedoSpectrum(ColorSrgb(1.0, 0.7, 0.4)),
+                                                                  Transform.identity().rotate_y(200.0).translate((1.5, 3.5, 2.0))))
+    if directional:
+        scene.create_primitive(CreatePrimitiveDesc.DirectionalLightPrimitive(0.8, ConstantSpectrum(1.0), Transform.identity().rotate_y(35.0)))
+    _camera_10(camera)
+
+
 def load_scene_6(scene, camera):
     """Cornell box with a mirror-smooth gold bunny (scene_6.rs:13-111): MetalMaterial / ConductorBsdf, specular reflection."""
     scene.create_primitive(GP(scene.load_obj(_asset("bunny")), MetalMaterial.new(MetalType.Gold, NormalParameter.none(), FloatParameter.constant(0.0)), Transform.identity()))
@@ -182,7 +211,7 @@ def load_soup(scene, camera, n_triangles: int, seed: int = 42):
     camera.set_look_to((0.0, 0.0, 3.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
 
 
-SCENES = {3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
+SCENES = {2: load_scene_2, "lights": load_scene_lights, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
 
 
 def load_scene(scene_id, scene, camera, **kw):
