@@ -124,6 +124,10 @@ int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const
 int tcpt_scene_clear(tcpt_ctx* ctx);
 int tcpt_scene_add_mesh(tcpt_ctx* ctx, const float* positions, const float* normals, const float* uvs /*nullable*/, int n_vertices,
                         const uint32_t* indices, int n_triangles);               /* returns geometry index */
+/* geometry of CreatePrimitiveDesc::SingleTrianglePrimitive (primitive/impls/single_triangle.rs:24-41): one triangle given inline; it is
+ * intersected without any box test, its TLAS box is the box of the transformed vertices and its tangent is not re-orthogonalised.
+ * Returns a geometry index for tcpt_scene_add_primitive. */
+int tcpt_scene_add_single_triangle(tcpt_ctx* ctx, const float positions[9], const float normals[9], const float uvs[6]);
 int tcpt_scene_add_texture(tcpt_ctx* ctx, const uint8_t* data, uint32_t width, uint32_t height, uint32_t channels /*1|3*/);
 int tcpt_scene_add_material(tcpt_ctx* ctx, const tcpt_material_desc* desc);
 int tcpt_scene_add_primitive(tcpt_ctx* ctx, int geometry, int material, const float local_to_world[16] /*column major*/);

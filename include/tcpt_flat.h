@@ -41,6 +41,7 @@ typedef struct {
     uint32_t index_base;              /* into indices (x3 per triangle) */
     uint32_t tangent_base;            /* into tangents (per triangle), valid when has_uv */
     uint32_t has_uv;
+    uint32_t single;                  /* SingleTriangle primitive (primitive/impls/single_triangle.rs): no box tests, tangent used as stored */
 } tcpt_flat_geometry;
 
 typedef struct { int32_t kind; float c[3]; float scale; int32_t texture; } tcpt_flat_spectrum; /* kind: 0 const(c[0]) 1 sigmoid(c) 2 sigmoid*scale*D65 3 D65 4 texture 5 dense preset table (texture = preset id) */

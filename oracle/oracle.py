@@ -42,7 +42,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(LIB))
         _lib.orc_scene_new.restype = C.c_void_p
         _lib.orc_build.restype = C.c_double
-        for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
+        for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_add_single_triangle", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
                      "orc_add_env_light", "orc_add_delta_light", "orc_set_modes", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
                      "orc_sampler_stream", "orc_get_bvh", "orc_get_mesh_tangents"):
             getattr(_lib, name).argtypes = None
@@ -83,6 +83,9 @@ class OracleScene:
     # --- replay protocol
     def add_mesh(self, pos, nrm, uv, idx):
         return self.l.orc_add_mesh(_vp(self.h), _p(pos), _p(nrm), _p(uv) if uv is not None else None, len(pos), _p(idx, C.c_uint32), len(idx))
+
+    def add_single_triangle(self, pos, nrm, uv):
+        return self.l.orc_add_single_triangle(_vp(self.h), _p(pos), _p(nrm), _p(uv))
 
     def add_texture(self, arr):
         hgt, wid = arr.shape[:2]

@@ -91,6 +91,23 @@ int orc_add_mesh(void* h, const float* pos, const float* nrm, const float* uv, i
     return (int)s->scene.meshes.size() - 1;
 }
 
+// geometry of CreatePrimitiveDesc::SingleTrianglePrimitive (single_triangle.rs:24-41)
+int orc_add_single_triangle(void* h, const float pos[9], const float nrm[9], const float uv[6]) {
+    OrcScene* s = (OrcScene*)h;
+    Mesh m;
+    m.single = true;
+    for (int i = 0; i < 3; ++i) {
+        m.positions.push_back(Vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
+        m.normals.push_back(Vec3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+        Vec2 t; t.x = uv[2 * i]; t.y = uv[2 * i + 1];
+        m.uvs.push_back(t);
+    }
+    m.indices = {0, 1, 2};
+    m.finalize();
+    s->scene.meshes.push_back(std::move(m));
+    return (int)s->scene.meshes.size() - 1;
+}
+
 int orc_add_texture(void* h, const uint8_t* data, uint32_t w, uint32_t hgt, uint32_t channels) {
     OrcScene* s = (OrcScene*)h;
     Texture t; t.w = w; t.h = hgt; t.channels = channels;

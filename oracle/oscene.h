@@ -22,6 +22,7 @@ struct Mesh {
     Bounds bounds;
     Bvh bvh;
     bool bvh_built = false;
+    bool single = false;  // geometry of a SingleTriangle primitive (primitive/impls/single_triangle.rs): no BVH, no box tests, raw tangent
 
     // load_obj post-processing (triangle_mesh.rs:161-243): normalise normals, per-triangle tangents when UVs exist
     void finalize() {
@@ -42,7 +43,8 @@ struct Mesh {
                     Vec3 n = make_normal(normalize(cp));
                     return generate_tangent(n);
                 };
-                if (std::fabs(denom) < 1e-6f) tangent = fallback();
+                if (single) tangent = normalize(tangent);  // single_triangle.rs:118-124: no fallbacks
+                else if (std::fabs(denom) < 1e-6f) tangent = fallback();
                 else {
                     tangent = normalize(tangent);
                     if (is_nan(tangent)) tangent = fallback();
@@ -100,7 +102,8 @@ inline void fill_local_hit(const Mesh& m, uint32_t tri, const TriangleHit& h, Lo
         out->uv.x = a.x * h.bary[0] + b.x * h.bary[1] + c.x * h.bary[2];
         out->uv.y = a.y * h.bary[0] + b.y * h.bary[1] + c.y * h.bary[2];
     }
-    out->tangent = m.tangents.empty() ? Mesh::generate_tangent(out->shading_normal) : Mesh::orthogonalize(out->shading_normal, m.tangents[tri]);
+    if (m.single) out->tangent = m.tangents[tri];  // SingleTriangle::intersect passes its tangent on without orthogonalising it
+    else out->tangent = m.tangents.empty() ? Mesh::generate_tangent(out->shading_normal) : Mesh::orthogonalize(out->shading_normal, m.tangents[tri]);
 }
 
 struct SurfaceInteraction {
@@ -192,7 +195,13 @@ struct Scene {
         for (size_t i = 0; i < primitives.size(); ++i) {
             if (primitives[i].geometry < 0) continue;
             tlas_items.push_back((int)i);
-            ib.push_back(transform_bounds(primitives[i].local_to_render, meshes[primitives[i].geometry].bounds));
+            const Mesh& gm = meshes[primitives[i].geometry];
+            if (gm.single) {  // SingleTriangle::bounds (single_triangle.rs:86-94): box of the transformed vertices
+                const float inf = INFINITY;
+                Vec3 mn(inf, inf, inf), mx(-inf, -inf, -inf);
+                for (int k = 0; k < 3; ++k) { Vec3 q = transform_point3(primitives[i].local_to_render, gm.positions[k]); mn = vmin(mn, q); mx = vmax(mx, q); }
+                ib.push_back(Bounds{mn, mx});
+            } else ib.push_back(transform_bounds(primitives[i].local_to_render, gm.bounds));
         }
         tlas.build(ib, literal_build);
         // LightSamplerFactory::build (light_sampler.rs:168-187): every light in primitive order, preprocess(scene_bounds) on the way
@@ -242,7 +251,10 @@ struct Scene {
             return true;
         };
         float t; uint64_t payload;
-        if (!m.bvh.intersect(rl, t_max, item_fn, &t, &payload, ctr)) return false;
+        if (m.single) {  // SingleTriangle::intersect (single_triangle.rs:100-141): the triangle test alone
+            if (ctr) ctr->tri_tests++;
+            if (!item_fn(0, t_max, &t, &payload)) return false;
+        } else if (!m.bvh.intersect(rl, t_max, item_fn, &t, &payload, ctr)) return false;
         if (!out) return true;
         uint32_t tri = (uint32_t)payload;
         Vec3 ps[3];
@@ -275,6 +287,7 @@ struct Scene {
             m.tri_positions(tri, ps);
             return intersect_triangle(rl, tmax, ps, nullptr);
         };
+        if (m.single) { if (ctr) ctr->tri_tests++; return item_fn(0, t_max); }
         return m.bvh.intersect_p(rl, t_max, item_fn, ctr);
     }
 

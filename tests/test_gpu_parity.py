@@ -18,7 +18,7 @@ def recorded_rays(b, integrator, sampler, spp, window):
     return rays, shadow
 
 
-@pytest.mark.parametrize("scene_id,kw", [(2, {}), ("lights", {"directional": True}), (3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
+@pytest.mark.parametrize("scene_id,kw", [(1, {}), (2, {}), ("lights", {"directional": True}), (3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
 def test_hit_records_bit_exact_on_path_rays(bundle_factory, scene_id, kw):
     """Every ray a MIS render issues inside a pixel window (camera, bounce and shadow rays, incl. the non-identity instance of
     scene 17 and the three instances of scene 19): closest hits and any-hits must equal the oracle's exhaustive traversal."""
@@ -78,9 +78,10 @@ CASES = [(3, {}, "pt"), (3, {}, "nee"), (3, {}, "mis"), (10, {}, "pt"), (10, {},
          # MetalMaterial / ConductorBsdf (scene 6 smooth, scene 7 rough + scaled instances), GlassMaterial with a
          # dispersive eta -> terminate_secondary (scene 8), solid plastic (scene 9)
          (6, {}, "pt"), (6, {}, "mis"), (7, {}, "nee"), (7, {}, "mis"), (8, {}, "pt"), (8, {}, "nee"), (8, {}, "mis"), (9, {}, "mis"),
-         # delta lights.  Scene 2 = the reference's point-light Cornell box; "lights" = point + spot + directional
+         # delta lights and single-triangle primitives.  Scene 1 = two bunny instances, an inline SingleTriangle and two
+         # point lights; scene 2 = the reference's point-light Cornell box; "lights" = point + spot + directional
          # light next to the area lamp (the reference has no scene with a spot or a directional light)
-         (2, {}, "pt"), (2, {}, "nee"), (2, {}, "mis"), ("lights", {}, "nee"), ("lights", {}, "mis"), ("lights", {"directional": True}, "mis")]
+         (1, {}, "nee"), (1, {}, "mis"), (2, {}, "pt"), (2, {}, "nee"), (2, {}, "mis"), ("lights", {}, "nee"), ("lights", {}, "mis"), ("lights", {"directional": True}, "mis")]
 
 
 @pytest.mark.parametrize("sampler", ["sobol", "random"])
@@ -126,7 +127,7 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
         assert np.quantile(d, 0.999) <= 2e-2 and d.mean() <= 1e-4
 
 
-@pytest.mark.parametrize("scene_id,integrator,sampler", [(2, "nee", "sobol"), ("lights", "mis", "sobol"), (3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
+@pytest.mark.parametrize("scene_id,integrator,sampler", [(1, "mis", "sobol"), (2, "nee", "sobol"), ("lights", "mis", "sobol"), (3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
 def test_individual_paths_match_oracle(bundle_factory, scene_id, integrator, sampler):
     """Per-(pixel, sample) sensor contributions: the overwhelming majority identical to the last bits, the rest within 1e-4."""
     w, h, spp = 64, 48, 64

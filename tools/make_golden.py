@@ -14,7 +14,7 @@ from toy_cpu_pathtracing_b200 import capi, scenes  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 CASES = [(3, {}, "mis", "sobol"), (10, {}, "nee", "sobol"), (17, {}, "mis", "sobol"), (17, {"coat": False}, "pt", "random"), (19, {}, "mis", "sobol"),
-         (7, {}, "mis", "sobol"), (8, {}, "mis", "sobol"), (2, {}, "nee", "sobol"), ("lights", {"directional": True}, "mis", "sobol")]
+         (7, {}, "mis", "sobol"), (8, {}, "mis", "sobol"), (1, {}, "mis", "sobol"), (2, {}, "nee", "sobol"), ("lights", {"directional": True}, "mis", "sobol")]
 W, H, SPP = 24, 18, 8
 
 

@@ -21,6 +21,7 @@ class MeshData:
     normals: np.ndarray    # (V,3) f32 (need not be normalised; the loader normalises)
     uvs: np.ndarray | None  # (V,2) f32 or None
     indices: np.ndarray    # (T,3) u32
+    single: bool = False   # geometry of a SingleTrianglePrimitive (primitive/impls/single_triangle.rs): three inline vertices
 
     def __post_init__(self):
         self.positions = np.ascontiguousarray(self.positions, dtype=f32)

@@ -71,7 +71,7 @@ class Stats(C.Structure):
 # every symbol include/tcpt.h and include/tcpt_flat.h declare (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "tcpt_create", "tcpt_destroy", "tcpt_last_error", "tcpt_set_option", "tcpt_set_tables", "tcpt_scene_clear",
-    "tcpt_scene_add_mesh", "tcpt_scene_add_texture", "tcpt_scene_add_material", "tcpt_scene_add_primitive",
+    "tcpt_scene_add_mesh", "tcpt_scene_add_single_triangle", "tcpt_scene_add_texture", "tcpt_scene_add_material", "tcpt_scene_add_primitive",
     "tcpt_scene_add_env_light", "tcpt_scene_add_delta_light", "tcpt_scene_build", "tcpt_render", "tcpt_render_device", "tcpt_finalize_device",
     "tcpt_get_stats", "tcpt_trace", "tcpt_trace_device", "tcpt_sampler_stream", "tcpt_path_samples", "tcpt_get_bvh",
     "tcpt_build_bvh_boxes", "tcpt_rgb_to_coeffs", "tcpt_get_mesh_tangents", "tcpt_upload_flat_scene",
@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
         "tcpt_create": (I, [I, C.POINTER(P)]), "tcpt_destroy": (None, [P]), "tcpt_last_error": (C.c_char_p, [P]),
         "tcpt_set_option": (I, [P, C.c_char_p, I]), "tcpt_set_tables": (I, [P, C.c_void_p, C.c_size_t, fp, C.c_size_t]),
         "tcpt_scene_clear": (I, [P]), "tcpt_scene_add_mesh": (I, [P, fp, fp, fp, I, up, I]),
+        "tcpt_scene_add_single_triangle": (I, [P, fp, fp, fp]),
         "tcpt_scene_add_texture": (I, [P, bp, U, U, U]), "tcpt_scene_add_material": (I, [P, C.POINTER(MaterialDesc)]),
         "tcpt_scene_add_primitive": (I, [P, I, I, fp]), "tcpt_scene_add_env_light": (I, [P, F, fp, U, U, fp]),
         "tcpt_scene_add_delta_light": (I, [P, I, F, C.POINTER(SpectrumParam), F, F, fp]),

@@ -59,7 +59,8 @@ __device__ __noinline__ void reconstruct_hit(const DScene& sc, int prim, uint32_
         const float2 c = make_float2(__ldg(uu + 2 * (size_t)i2), __ldg(uu + 2 * (size_t)i2 + 1));
         s.uv = make_float2((a.x * b0 + b.x * b1) + c.x * b2, (a.y * b0 + b.y * b1) + c.y * b2);
         const float* tt = sc.tangents + 3 * ((size_t)G.tangent_base + tri);
-        tan_l = orthogonalize(ns_l, f3(__ldg(tt), __ldg(tt + 1), __ldg(tt + 2)));
+        tan_l = f3(__ldg(tt), __ldg(tt + 1), __ldg(tt + 2));
+        if (!G.single) tan_l = orthogonalize(ns_l, tan_l);  // SingleTriangle hands its tangent on as computed (single_triangle.rs:118-135)
     } else {
         s.uv = make_float2(0.0f, 0.0f);
         tan_l = generate_tangent(ns_l);

@@ -213,6 +213,7 @@ struct Traversal {
                 else ray_setup(rl, ol, dl);
                 node_base = G.node_base; slot_base = G.slot_base;
                 blas_sp = sp;
+                if (G.single) { pend_slot = 0; pend_cnt = 1; need_pop = true; return false; }  // SingleTriangle: straight to the triangle test, no boxes
                 node = node_base;  // entry record: tests the BLAS root box
             } else {
                 node = top;

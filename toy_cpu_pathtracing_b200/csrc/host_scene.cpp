@@ -67,6 +67,21 @@ int HostScene::add_mesh(const float* pos, const float* nrm, const float* uv, int
     return (int)meshes.size() - 1;
 }
 
+int HostScene::add_single_triangle(const float pos[9], const float nrm[9], const float uv[6]) {
+    if (!pos || !nrm || !uv) { error = "add_single_triangle: null argument"; return TCPT_ERR_INVALID; }
+    const uint32_t idx[3] = {0, 1, 2};
+    const int g = add_mesh(pos, nrm, uv, 3, idx, 1);
+    if (g < 0) return g;
+    HostMesh& m = meshes[g];
+    m.single = true;
+    // SingleTriangle::intersect computes the tangent per hit, without the mesh loader's fallbacks (single_triangle.rs:118-124)
+    const V3 e1 = sub(m.positions[1], m.positions[0]), e2 = sub(m.positions[2], m.positions[0]);
+    const float du1 = m.uvs[1].x - m.uvs[0].x, dv1 = m.uvs[1].y - m.uvs[0].y, du2 = m.uvs[2].x - m.uvs[0].x, dv2 = m.uvs[2].y - m.uvs[0].y;
+    const float r = 1.0f / (du1 * dv2 - dv1 * du2);
+    m.tangents[0] = unit(scale(sub(scale(e1, dv2), scale(e2, dv1)), r));
+    return g;
+}
+
 int HostScene::add_texture(const uint8_t* data, uint32_t w, uint32_t h, uint32_t channels) {
     if (!data || w == 0 || h == 0 || (channels != 1 && channels != 3)) { error = "add_texture: bad arguments"; return TCPT_ERR_INVALID; }
     HostTexture t; t.w = w; t.h = h; t.channels = channels;
@@ -324,7 +339,13 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         l2r[i] = m4_mul(world_to_render, primitives[i].local_to_world);
         if (primitives[i].geometry < 0) continue;
         tlas_prims.push_back((int)i);
-        tb.push_back(transform_box(l2r[i], meshes[primitives[i].geometry].bounds));
+        const HostMesh& gm = meshes[primitives[i].geometry];
+        if (gm.single) {  // SingleTriangle::bounds: box of the three transformed vertices (single_triangle.rs:86-94)
+            const float inf = INFINITY;
+            Box b{{inf, inf, inf}, {-inf, -inf, -inf}};
+            for (int k = 0; k < 3; ++k) { const V3 q = m4_point(l2r[i], gm.positions[k]); b.lo = min3(b.lo, q); b.hi = max3(b.hi, q); }
+            tb.push_back(b);
+        } else tb.push_back(transform_box(l2r[i], gm.bounds));
     }
     if (tb.empty()) { error = "build: no geometry primitives"; return TCPT_ERR_INVALID; }
     tlas = SahBuilder(tb).build();
@@ -346,7 +367,7 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         fg.node_base = (uint32_t)S.nodes.size();
         fg.slot_base = (uint32_t)(S.tri_verts.size() / 12); fg.tri_count = (uint32_t)(m.indices.size() / 3);
         fg.vertex_base = (uint32_t)(S.positions.size() / 3); fg.index_base = (uint32_t)(S.indices.size() / 3);
-        fg.tangent_base = (uint32_t)(S.tangents.size() / 3); fg.has_uv = m.uvs.empty() ? 0 : 1;
+        fg.tangent_base = (uint32_t)(S.tangents.size() / 3); fg.has_uv = m.uvs.empty() ? 0 : 1; fg.single = m.single ? 1 : 0;
         uint32_t blas_max_leaf = 0;
         fg.node_count = put_nodes(m.bvh, S.nodes, &blas_max_leaf);
         const std::vector<uint32_t> lf = leaf_first_of_slots(m.bvh);

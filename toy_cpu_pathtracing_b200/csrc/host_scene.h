@@ -27,6 +27,7 @@ struct HostMesh {
     Box bounds;
     BuiltBvh bvh;
     bool built = false;
+    bool single = false;  // SingleTriangle primitive: see tcpt_flat_geometry.single
 };
 
 struct HostTexture { std::vector<uint8_t> data; uint32_t w, h, channels; };
@@ -81,6 +82,7 @@ class HostScene {
 
     void clear();
     int add_mesh(const float* pos, const float* nrm, const float* uv, int nverts, const uint32_t* idx, int ntris);
+    int add_single_triangle(const float pos[9], const float nrm[9], const float uv[6]);
     int add_texture(const uint8_t* data, uint32_t w, uint32_t h, uint32_t channels);
     int add_material(const tcpt_material_desc& d);
     int add_primitive(int geometry, int material, const float l2w[16]);

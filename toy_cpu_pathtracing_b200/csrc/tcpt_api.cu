@@ -561,6 +561,13 @@ int tcpt_scene_add_env_light(tcpt_ctx* ctx, float intensity, const float* rgb, u
     return r;
 }
 
+int tcpt_scene_add_single_triangle(tcpt_ctx* ctx, const float positions[9], const float normals[9], const float uvs[6]) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    int r = ctx->host.add_single_triangle(positions, normals, uvs);
+    if (r < 0) ctx->error = ctx->host.error;
+    return r;
+}
+
 int tcpt_scene_add_delta_light(tcpt_ctx* ctx, int kind, float intensity, const tcpt_spectrum_param* spectrum, float angle_inner, float angle_outer, const float local_to_world[16]) {
     if (!ctx || !spectrum || !local_to_world) return TCPT_ERR_INVALID;
     int r = ctx->host.add_delta_light(kind, intensity, *spectrum, angle_inner, angle_outer, local_to_world);

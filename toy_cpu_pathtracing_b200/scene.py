@@ -320,6 +320,15 @@ class EnvironmentLightPrimitive:    # CreatePrimitiveDesc::EnvironmentLightPrimi
 
 
 @dataclass
+class SingleTrianglePrimitive:      # CreatePrimitiveDesc::SingleTrianglePrimitive { positions, normals, uvs, surface_material, transform }
+    positions: object
+    normals: object
+    uvs: object
+    surface_material: object
+    transform: Transform = field(default_factory=Transform)
+
+
+@dataclass
 class PointLightPrimitive:          # CreatePrimitiveDesc::PointLightPrimitive { intensity, spectrum, transform }
     intensity: float
     spectrum: object
@@ -345,6 +354,7 @@ class DirectionalLightPrimitive:    # CreatePrimitiveDesc::DirectionalLightPrimi
 class CreatePrimitiveDesc:
     GeometryPrimitive = GeometryPrimitive
     EnvironmentLightPrimitive = EnvironmentLightPrimitive
+    SingleTrianglePrimitive = SingleTrianglePrimitive
     PointLightPrimitive = PointLightPrimitive
     SpotLightPrimitive = SpotLightPrimitive
     DirectionalLightPrimitive = DirectionalLightPrimitive
@@ -475,7 +485,10 @@ class SceneDescription:
         """backend: add_mesh(pos, nrm, uv|None, idx) / add_texture(arr) / add_material(desc) / add_primitive(g, m, l2w) / add_env_light(i, rgb, l2w) /
         add_delta_light(kind, intensity, spectrum_param, angle_inner, angle_outer, l2w)"""
         for mesh in self.meshes:
-            backend.add_mesh(mesh.positions, mesh.normals, mesh.uvs, mesh.indices)
+            if mesh.single:
+                backend.add_single_triangle(mesh.positions, mesh.normals, mesh.uvs)
+            else:
+                backend.add_mesh(mesh.positions, mesh.normals, mesh.uvs, mesh.indices)
         for t in self.textures:
             backend.add_texture(t)
         for m in self.materials:
@@ -519,6 +532,12 @@ class Scene:
                 import cv2
                 tex = cv2.imread(str(tex), cv2.IMREAD_UNCHANGED)[..., 2::-1]
             d.primitives.append(("env", float(desc.intensity), np.ascontiguousarray(tex, dtype=f32), desc.transform.column_major()))
+        elif isinstance(desc, SingleTrianglePrimitive):
+            tri = MeshData(np.asarray(desc.positions, dtype=f32).reshape(3, 3), np.asarray(desc.normals, dtype=f32).reshape(3, 3),
+                           np.asarray(desc.uvs, dtype=f32).reshape(3, 2), np.array([[0, 1, 2]], dtype=np.uint32), single=True)
+            d.meshes.append(tri)
+            d.materials.append(d.material_desc(desc.surface_material))
+            d.primitives.append(("geom", len(d.meshes) - 1, len(d.materials) - 1, desc.transform.column_major()))
         elif isinstance(desc, (PointLightPrimitive, SpotLightPrimitive, DirectionalLightPrimitive)):
             kind = capi.LIGHT_POINT if isinstance(desc, PointLightPrimitive) else capi.LIGHT_SPOT if isinstance(desc, SpotLightPrimitive) else capi.LIGHT_DIRECTIONAL
             spec = d._spectrum(SpectrumParameter.constant(desc.spectrum))
@@ -542,6 +561,9 @@ class Scene:
         lib, h = self.ctx.lib, self.ctx.handle
         uvp = capi.as_ptr(uv, C.c_float) if uv is not None else None
         return self.ctx.check(lib.tcpt_scene_add_mesh(h, capi.as_ptr(pos, C.c_float), capi.as_ptr(nrm, C.c_float), uvp, len(pos), capi.as_ptr(idx, C.c_uint32), len(idx)))
+
+    def add_single_triangle(self, pos, nrm, uv):
+        return self.ctx.check(self.ctx.lib.tcpt_scene_add_single_triangle(self.ctx.handle, capi.as_ptr(pos, C.c_float), capi.as_ptr(nrm, C.c_float), capi.as_ptr(uv, C.c_float)))
 
     def add_texture(self, arr):
         hgt, wid = arr.shape[:2]

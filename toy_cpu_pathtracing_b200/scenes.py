@@ -107,6 +107,22 @@ def _camera_10(camera):
     camera.set_look_to((0.0, 3.5, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
 
 
+def load_scene_1(scene, camera):
+    """Two bunny instances (one rotated 30 degrees about Y and translated), the floor, one inline SingleTriangle rotated 60 degrees and
+    two point lights (scene_1.rs:12-87)."""
+    bunny = scene.load_obj(_asset("bunny"))
+    scene.create_primitive(GP(bunny, _lambert(0.5, 0.5, 0.8), Transform.identity()))
+    scene.create_primitive(GP(bunny, _lambert(0.5, 0.8, 0.5), Transform.from_rotate_y(30.0).translate((-1.0, 1.0, 3.0))))
+    scene.create_primitive(GP(scene.load_obj(_asset("yuka")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.SingleTrianglePrimitive(
+        [(-2.0, 0.0, 0.0), (2.0, 0.0, 0.0), (-2.0, 4.0, 0.0)], [(0.0, 0.0, 1.0)] * 3, [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0)],
+        _lambert(0.8, 0.5, 0.5), Transform.from_rotate_y(60.0)))
+    scene.create_primitive(CreatePrimitiveDesc.PointLightPrimitive(10.0, presets.cie_illum_d6500(), Transform.from_translate((0.0, 3.0, 0.0))))
+    scene.create_primitive(CreatePrimitiveDesc.PointLightPrimitive(10.0, presets.cie_illum_d6500(), Transform.from_translate((3.0, 5.0, 0.0))))
+    d = np.array([0.0, -1.0, -3.0], dtype=np.float32)
+    camera.set_look_to((0.0, 3.5, 7.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
 def load_scene_2(scene, camera):
     """Cornell box without the ceiling lamp, lit by one point light at (0, 3, 0) (scene_2.rs:12-102): delta-light NEE, no MIS weight."""
     scene.create_primitive(GP(scene.load_obj(_asset("bunny")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
@@ -211,7 +227,7 @@ def load_soup(scene, camera, n_triangles: int, seed: int = 42):
     camera.set_look_to((0.0, 0.0, 3.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
 
 
-SCENES = {2: load_scene_2, "lights": load_scene_lights, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
+SCENES = {1: load_scene_1, 2: load_scene_2, "lights": load_scene_lights, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
 
 
 def load_scene(scene_id, scene, camera, **kw):
