@@ -81,6 +81,9 @@ CASES = [(3, {}, "pt"), (3, {}, "nee"), (3, {}, "mis"), (10, {}, "pt"), (10, {},
          # delta lights and single-triangle primitives.  Scene 1 = two bunny instances, an inline SingleTriangle and two
          # point lights; scene 2 = the reference's point-light Cornell box; "lights" = point + spot + directional
          # light next to the area lamp (the reference has no scene with a spot or a directional light)
+         # the rest of main.rs's scene switch (same features in other combinations): rough dispersive glass (11, 12), rough coloured
+         # plastic (14), textured SimplePbr dragon (15), smooth coat with textured thickness (18), plain and normal-mapped Lambert (0, 5)
+         (0, {}, "mis"), (5, {}, "mis"), (11, {}, "nee"), (11, {}, "mis"), (12, {}, "mis"), (14, {}, "mis"), (15, {}, "mis"), (18, {}, "mis"),
          (1, {}, "nee"), (1, {}, "mis"), (2, {}, "pt"), (2, {}, "nee"), (2, {}, "mis"), ("lights", {}, "nee"), ("lights", {}, "mis"), ("lights", {"directional": True}, "mis")]
 
 
@@ -112,7 +115,21 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
     assert abs(img.stats["closest_rays"] - st["closest_rays"]) <= 1e-3 * st["closest_rays"]
     assert abs(img.stats["shadow_rays"] - st["shadow_rays"]) <= 1e-3 * max(1, st["shadow_rays"])
     g, o = img.accumulators / spp, acc / spp
-    assert np.isfinite(g).all()
+    # Scene 11 under MIS produces NaN pixels in the reference itself: GLASS_SF11_ETA starts at 370 nm (presets.rs:2925-2927), so a
+    # hero wavelength in [360, 370) reads eta = 0, DielectricBsdf::new falls back to eta = 1 (dielectric.rs:143-148), and rough
+    # transmission at eta = 1 divides by (wi.wm + wo.wm / eta)^2 = 0; the infinite pdf then meets inf / (inf + x) in the balance
+    # heuristic.  Whether that denominator is exactly 0 or 1e-15 is rounding noise, so the NaN pixels (4 % of the frame at 32 spp,
+    # black after Sensor::to_rgb's max(0)) only agree approximately; the comparison runs on the pixels finite on both sides.
+    finite = np.isfinite(o).all(axis=2)
+    nan_mismatch = (np.isfinite(g).all(axis=2) != finite).mean()
+    if scene_id == 11 and integrator == "mis":
+        assert nan_mismatch <= 0.04 and 0.01 <= 1.0 - finite.mean() <= 0.1
+        both = finite & np.isfinite(g).all(axis=2)
+        rel = np.abs(g[both] - o[both]).sum(axis=1) / (np.abs(o[both]).sum(axis=1) + 1e-6)
+        assert np.median(rel) <= 1e-5 and np.quantile(rel, 0.95) <= 1e-3
+        return
+    assert nan_mismatch == 0 and finite.all()
+    g, o = g[finite], o[finite]
     if not np.abs(o).any():     # scene 2 under pt: a point light cannot be hit, the frame is black on both sides
         assert not np.abs(g).any()
         return
@@ -120,7 +137,7 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
     assert mre <= mre_tol, f"mean relative error {mre:.3e}"
     # tone-mapped output: a single path that branches differently (last-ulp transcendental at a threshold) can move one pixel of
     # a high-variance pt frame visibly, so the bound is on the 99.9th percentile and the mean, not the maximum
-    d = np.abs(img.pixels - srgb)
+    d = np.abs(img.pixels - srgb)[finite]
     if knife_edge:   # a few percent of the pixels hold one diverged path at 32 spp (see above): bound the bulk, not the tail
         assert np.quantile(d, 0.93) <= 1e-3 and d.mean() <= 2e-3
     else:

@@ -1,6 +1,7 @@
-"""The config scenes of BASELINE.json, restated from the reference's scene builders with stand-in assets.
+"""All twenty scenes of the reference's `match args.scene` (renderer/src/main.rs:70-92; BASELINE.json names 3, 10, 17 and 19), restated from
+the reference's scene builders with stand-in assets.
 
-Materials, transforms, lights and cameras are the reference's (renderer/src/scene/scene_{3,10,17,19}.rs); every mesh,
+Materials, transforms, lights and cameras are the reference's (renderer/src/scene/scene_N.rs); every mesh,
 texture and HDRI it loads is a git-LFS stub in the checkout, so geometry and images come from the
 deterministic generators in assets.py (Cornell walls = axis-aligned quads spanning x,z in [-2.5,2.5], y in [0,5]).
 """
@@ -43,6 +44,12 @@ def _asset(name: str):
         return assets.base_color_texture(1024, seed=0)
     if name == "bunny_normal":
         return assets.normal_texture(1024, seed=10)
+    if name == "bunny1_basecolor":
+        return assets.base_color_texture(1024, seed=1)
+    if name == "bunny1_normal":
+        return assets.normal_texture(1024, seed=11)
+    if name == "dragon_coat_thickness":
+        return assets.gray_texture(1024, seed=22, lo=0.1, hi=0.95)
     if name == "dragon_basecolor":
         return assets.base_color_texture(1024, seed=3)
     if name == "dragon_normal":
@@ -105,6 +112,32 @@ def load_scene_10(scene, camera):
 def _camera_10(camera):
     d = np.array([0.0, -1.0, -3.0], dtype=np.float32)
     camera.set_look_to((0.0, 3.5, 6.0), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
+
+
+def load_scene_0(scene, camera):
+    """Plain Cornell box: grey Lambert bunny and box, coloured walls, ceiling lamp (scene_0.rs:12-107)."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_4(scene, camera):
+    """Scene 3 with the second bunny material (bunny-material-1 base colour + normal map) and the scene-10 camera (scene_4.rs:12-115)."""
+    tex = RgbTexture.load_srgb(_asset("bunny1_basecolor"))
+    nrm = NormalTexture.load(_asset("bunny1_normal"), False)
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")),
+                              LambertMaterial.new(SpectrumParameter.texture(tex, SpectrumType.Albedo), NormalParameter.texture(nrm)), Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_5(scene, camera):
+    """Grey Lambert bunny with the normal map only, close-up camera (scene_5.rs:12-113)."""
+    nrm = NormalTexture.load(_asset("bunny_normal"), False)
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), LambertMaterial.new(_grey(0.8), NormalParameter.texture(nrm)), Transform.identity()))
+    _cornell_rest(scene)
+    d = np.array([0.0, -0.5, -2.0], dtype=np.float32)
+    camera.set_look_to((0.3, 1.6, 2.8), d / np.float32(np.sqrt(np.float32((d * d).sum()))), (0.0, 1.0, 0.0))
 
 
 def load_scene_1(scene, camera):
@@ -186,10 +219,79 @@ def load_scene_9(scene, camera):
     _camera_10(camera)
 
 
-def _clearcoat(coat_roughness):
+_FOUR_POSITIONS = ((-1.3, 0.0, -0.5), (-0.5, 0.0, -0.5), (0.3, 0.0, -0.5), (1.1, 0.0, -0.5))
+
+
+def load_scene_11(scene, camera):
+    """SF11 glass bunny with roughness 0.2 (scene_11.rs:12-117): rough dielectric reflection and transmission."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), GlassMaterial.new(GlassType.Sf11, NormalParameter.none(), False, FloatParameter.constant(0.2)), Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_12(scene, camera):
+    """Four BK7 glass bunnies, roughness 0.05 / 0.25 / 0.5 / 0.75 (scene_12.rs:12-130)."""
+    bunny = scene.load_obj(_asset("bunny"))
+    for pos, rough in zip(_FOUR_POSITIONS, (0.05, 0.25, 0.5, 0.75)):
+        scene.create_primitive(GP(bunny, GlassMaterial.new(GlassType.Bk7, NormalParameter.none(), False, FloatParameter.constant(rough)),
+                                  Transform.from_scale((0.6, 0.6, 0.6)).translate(pos)))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_13(scene, camera):
+    """Solid light-blue plastic bunny, eta 1.5, smooth (scene_13.rs:12-120)."""
+    color = SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(0.4, 0.9, 1.0)))
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), PlasticMaterial.new(1.5, color, NormalParameter.none(), False, FloatParameter.constant(0.0)), Transform.identity()))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def load_scene_14(scene, camera):
+    """Four coloured plastic bunnies, roughness 0.05 / 0.1 / 0.3 / 0.5 (scene_14.rs:12-140)."""
+    bunny = scene.load_obj(_asset("bunny"))
+    colors = ((1.0, 0.5, 0.5), (0.5, 1.0, 0.5), (0.5, 0.5, 1.0), (1.0, 0.8, 0.4))
+    for pos, rough, c in zip(_FOUR_POSITIONS, (0.05, 0.1, 0.3, 0.5), colors):
+        mat = PlasticMaterial.new(1.5, SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(*c))), NormalParameter.none(), False, FloatParameter.constant(rough))
+        scene.create_primitive(GP(bunny, mat, Transform.from_scale((0.6, 0.6, 0.6)).translate(pos)))
+    _cornell_rest(scene)
+    _camera_10(camera)
+
+
+def _dragon_transform():
+    return Transform.identity().rotate_y(120.0).scale((2.5, 2.5, 2.5)).translate((0.0, 0.0, 0.5))
+
+
+def load_scene_15(scene, camera):
+    """Textured SimplePbr dragon (base colour, metallic, roughness, normal map) in the Cornell box (scene_15.rs:12-155)."""
+    pbr = SimplePbrMaterial.new(SpectrumParameter.texture(RgbTexture.load_srgb(_asset("dragon_basecolor")), SpectrumType.Albedo),
+                                FloatParameter.texture(FloatTexture.load(_asset("dragon_metallic"), False)),
+                                FloatParameter.texture(FloatTexture.load(_asset("dragon_roughness"), False)),
+                                NormalParameter.texture(NormalTexture.load(_asset("dragon_normal"), False)), FloatParameter.constant(1.5))
+    scene.create_primitive(GP(scene.load_obj(_asset("dragon")), pbr, _dragon_transform()))
+    _cornell_rest(scene)
+    _cornell_camera(camera)
+
+
+def load_scene_16(scene, camera):
+    """Scene 17 with a smooth coat (clearcoat roughness 0.01) (scene_16.rs:12-155)."""
+    scene.create_primitive(GP(scene.load_obj(_asset("dragon")), _clearcoat(0.01), _dragon_transform()))
+    _cornell_rest(scene)
+    _cornell_camera(camera)
+
+
+def load_scene_18(scene, camera):
+    """Smooth clearcoat whose thickness comes from a texture (scene_18.rs:12-160)."""
+    scene.create_primitive(GP(scene.load_obj(_asset("dragon")),
+                              _clearcoat(0.01, FloatParameter.texture(FloatTexture.load(_asset("dragon_coat_thickness"), False))), _dragon_transform()))
+    _cornell_rest(scene)
+    _cornell_camera(camera)
+
+
+def _clearcoat(coat_roughness, thickness=None):
     tint = SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(0.7, 0.8, 1.0)))
     return SimpleClearcoatPbrMaterial.new(_grey(0.8), FloatParameter.constant(1.0), FloatParameter.constant(0.7), NormalParameter.none(), FloatParameter.constant(1.5),
-                                          FloatParameter.constant(1.5), FloatParameter.constant(coat_roughness), tint, FloatParameter.constant(0.8))
+                                          FloatParameter.constant(1.5), FloatParameter.constant(coat_roughness), tint, thickness or FloatParameter.constant(0.8))
 
 
 def load_scene_17(scene, camera, coat=True):
@@ -227,7 +329,8 @@ def load_soup(scene, camera, n_triangles: int, seed: int = 42):
     camera.set_look_to((0.0, 0.0, 3.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
 
 
-SCENES = {1: load_scene_1, 2: load_scene_2, "lights": load_scene_lights, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
+SCENES = {0: load_scene_0, 1: load_scene_1, 2: load_scene_2, 4: load_scene_4, 5: load_scene_5, 11: load_scene_11, 12: load_scene_12, 13: load_scene_13,
+          14: load_scene_14, 15: load_scene_15, 16: load_scene_16, 18: load_scene_18, "lights": load_scene_lights, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
 
 
 def load_scene(scene_id, scene, camera, **kw):
