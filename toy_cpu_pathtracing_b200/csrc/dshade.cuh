@@ -561,9 +561,11 @@ __device__ __noinline__ S4 coat_attenuation(const S4& tint, float thickness, flo
 }
 
 // ---------------------------------------------------------------- materials (BsdfSurfaceMaterial::{sample,evaluate,pdf}, material/traits.rs:29-83)
+struct MatParams;
 struct MatCtx {
     const DScene* sc;
     uint32_t path_key, depth;  // aux RNG keying
+    const MatParams* mp;        // this vertex's material parameters, looked up once (see load_mat_params)
 };
 
 __device__ __noinline__ float3 param_normal(const DScene& sc, const tcpt_flat_material& m, float2 uv) {  // normal_texture.rs:40-66
@@ -614,6 +616,21 @@ __device__ __forceinline__ Coat load_coat(const DScene& sc, const tcpt_flat_mate
 }
 __device__ __forceinline__ Schlick coat_bsdf(const Coat& c) { return make_schlick(s4(r0_of(c.ior)), c.roughness * c.roughness); }
 
+// The parameters a material reads at a vertex are functions of (material, surface uv, wavelengths) only; sample(), evaluate() and
+// pdf() of the reference each look them up again (texture taps, rgb -> spectrum, sigmoids).  Looked up once per vertex here and
+// shared: same values, same bits.  Not for the dispersive dielectrics, whose sample() may collapse the wavelengths in between.
+struct MatParams { PbrBase pbr; Coat coat; S4 k; };
+template <int MT>
+__device__ __forceinline__ void load_mat_params(const DScene& sc, const tcpt_flat_material& m, float2 sp_uv, const DWavelengths& wl, MatParams& p) {
+    if (MT == TCPT_MAT_LAMBERT) p.pbr.base_color = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
+    if (MT == TCPT_MAT_SIMPLE_PBR || MT == TCPT_MAT_CLEARCOAT_PBR) p.pbr = load_pbr(sc, m, sp_uv, wl);
+    if (MT == TCPT_MAT_CLEARCOAT_PBR) p.coat = load_coat(sc, m, sp_uv, wl);
+    if (MT == TCPT_MAT_METAL) {
+        p.pbr.base_color = spectrum_sample(sc, spectrum_from_flat(m.color), wl); p.k = spectrum_sample(sc, spectrum_from_flat(m.coat_tint), wl);
+        p.pbr.roughness = param_float(sc, m.roughness, sp_uv);
+    }
+}
+
 // `ng_t` = geometric normal in the tangent frame, `sp_uv` = surface uv
 // MT = the material type as a compile-time constant: k_shade is instantiated once per shading bucket, so each instantiation
 // carries only its own material's code (I-cache footprint and register pressure of the fused kernel were the first bottleneck)
@@ -625,7 +642,7 @@ __device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt
     const float3 wo_nm = to_nm(fr, wo);
     switch (MT) {
         case TCPT_MAT_LAMBERT: {  // lambert_material.rs:42-97
-            const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
+            const S4 albedo = c.mp->pbr.base_color;
             BsdfSample s;
             if (!lambert_sample(albedo, wo_nm, uv, &s)) return mat_fail();
             const float3 wi_sh = m3_vector(from_nm, s.wi);
@@ -640,11 +657,11 @@ __device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt
             if (dot(s.wi, wo_nm) < 0.0f) s.f = s.f * spectrum_sample(sc, param_spectrum(sc, m.color, uv), wl);  // quirk: filter looked up at the RANDOM uv (:167)
             return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
         }
-        case TCPT_MAT_SIMPLE_PBR: return load_pbr(sc, m, sp_uv, wl).sample(wo_nm, uc, uv, from_nm);
+        case TCPT_MAT_SIMPLE_PBR: return c.mp->pbr.sample(wo_nm, uc, uv, from_nm);
         case TCPT_MAT_METAL: {  // metal_material.rs:122-173: eta / k presets in `color` / `coat_tint`, alpha = roughness^2
             Conductor cb;
-            cb.eta = spectrum_sample(sc, spectrum_from_flat(m.color), wl); cb.k = spectrum_sample(sc, spectrum_from_flat(m.coat_tint), wl);
-            const float rough = param_float(sc, m.roughness, sp_uv);
+            cb.eta = c.mp->pbr.base_color; cb.k = c.mp->k;
+            const float rough = c.mp->pbr.roughness;
             cb.g.ax = cb.g.ay = rough * rough;
             BsdfSample s;
             if (!cb.sample(wo_nm, uv, &s)) return mat_fail();
@@ -661,8 +678,8 @@ __device__ __forceinline__ MatSample material_sample(const MatCtx& c, const tcpt
             return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
         }
         case TCPT_MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:121-250
-            const PbrBase b = load_pbr(sc, m, sp_uv, wl);
-            const Coat cp = load_coat(sc, m, sp_uv, wl);
+            const PbrBase& b = c.mp->pbr;
+            const Coat& cp = c.mp->coat;
             if (cp.thickness <= 0.0f) return b.sample(wo_nm, uc, uv, from_nm);
             const Schlick coat = coat_bsdf(cp);
             const float fc = s4_avg(coat.directional_albedo(wo_nm, aux_rng(c.path_key, c.depth, 0)));
@@ -691,7 +708,7 @@ __device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_fl
     switch (MT) {
         case TCPT_MAT_LAMBERT: {  // lambert_material.rs:99-170
             if (signum(dot(ng_t, wi)) != signum(dot(ng_t, wo))) { *f_out = s4(0.0f); return; }
-            const S4 albedo = spectrum_sample(sc, param_spectrum(sc, m.color, sp_uv), wl);
+            const S4 albedo = c.mp->pbr.base_color;
             *f_out = lambert_eval(albedo, wo_nm, wi_nm);
             if (want_pdf) *pdf_out = lambert_pdf(wo_nm, wi_nm);
             return;
@@ -706,7 +723,7 @@ __device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_fl
             return;
         }
         case TCPT_MAT_SIMPLE_PBR: {
-            const PbrBase b = load_pbr(sc, m, sp_uv, wl);
+            const PbrBase& b = c.mp->pbr;
             *f_out = b.evaluate(wo_nm, wi_nm);
             if (want_pdf) *pdf_out = b.pdf(wo_nm, wi_nm);
             return;
@@ -714,8 +731,8 @@ __device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_fl
         case TCPT_MAT_METAL: {  // metal_material.rs:175-252
             if (signum(dot(ng_t, wi)) != signum(dot(ng_t, wo))) { *f_out = s4(0.0f); return; }
             Conductor cb;
-            cb.eta = spectrum_sample(sc, spectrum_from_flat(m.color), wl); cb.k = spectrum_sample(sc, spectrum_from_flat(m.coat_tint), wl);
-            const float rough = param_float(sc, m.roughness, sp_uv);
+            cb.eta = c.mp->pbr.base_color; cb.k = c.mp->k;
+            const float rough = c.mp->pbr.roughness;
             cb.g.ax = cb.g.ay = rough * rough;
             *f_out = cb.evaluate(wo_nm, wi_nm);
             if (want_pdf) *pdf_out = cb.pdf(wo_nm, wi_nm);
@@ -729,8 +746,8 @@ __device__ __forceinline__ void material_eval_pdf(const MatCtx& c, const tcpt_fl
             return;
         }
         case TCPT_MAT_CLEARCOAT_PBR: {  // simple_pbr_clearcoat_material.rs:252-433: evaluate and pdf each draw their OWN albedo estimate
-            const PbrBase b = load_pbr(sc, m, sp_uv, wl);
-            const Coat cp = load_coat(sc, m, sp_uv, wl);
+            const PbrBase& b = c.mp->pbr;
+            const Coat& cp = c.mp->coat;
             if (cp.thickness <= 0.0f) { *f_out = b.evaluate(wo_nm, wi_nm); if (want_pdf) *pdf_out = b.pdf(wo_nm, wi_nm); return; }
             const Schlick coat = coat_bsdf(cp);
             const float fc = s4_avg(coat.directional_albedo(wo_nm, aux_rng(c.path_key, c.depth, 1)));

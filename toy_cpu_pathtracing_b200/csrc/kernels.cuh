@@ -304,6 +304,9 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     const bool was_terminated = wl.terminated;
     NmFrame nmf;
     material_frame(sc, mat, hit.uv, nmf);
+    MatParams mp;
+    load_mat_params<MT>(sc, mat, hit.uv, wl, mp);
+    mc.mp = &mp;
     const MatSample ms = material_sample<MT>(mc, mat, nmf, uc, uv, wl, wo, ng_t, hit.uv);
     if (wl.terminated != was_terminated) lt_ready = false;  // a dispersive material collapsed the wavelengths: light powers change
 
