@@ -117,8 +117,8 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
     g, o = img.accumulators / spp, acc / spp
     # Scene 11 under MIS produces NaN pixels in the reference itself: GLASS_SF11_ETA starts at 370 nm (presets.rs:2925-2927), so a
     # hero wavelength in [360, 370) reads eta = 0, DielectricBsdf::new falls back to eta = 1 (dielectric.rs:143-148), and rough
-    # transmission at eta = 1 divides by (wi.wm + wo.wm / eta)^2 = 0; the infinite pdf then meets inf / (inf + x) in the balance
-    # heuristic.  Whether that denominator is exactly 0 or 1e-15 is rounding noise, so the NaN pixels (4 % of the frame at 32 spp,
+    # transmission at eta = 1 divides by (wi.wm + wo.wm / eta)^2 = 0; the infinite pdf then meets inf / (inf + 0) in the balance
+    # heuristic of calculate_bsdf_contribution (evaluated for non-emissive hits too), and 0 * NaN poisons the contribution.  Whether that denominator is exactly 0 or 1e-15 is rounding noise, so the NaN pixels (4 % of the frame at 32 spp,
     # black after Sensor::to_rgb's max(0)) only agree approximately; the comparison runs on the pixels finite on both sides.
     finite = np.isfinite(o).all(axis=2)
     nan_mismatch = (np.isfinite(g).all(axis=2) != finite).mean()

@@ -13,6 +13,10 @@
 #include "dshade.cuh"
 #include "dtraverse.cuh"
 
+// shading buckets (see bucket_of): counters[4 + TCPT_BUCKET_STRIDE * parity + bucket] holds their sizes
+#define TCPT_N_BUCKETS 9
+#define TCPT_BUCKET_STRIDE 10
+
 namespace tcpt {
 
 struct PathList { const uint32_t* xy; const uint32_t* sample; };  // explicit (pixel, sample) lists for tcpt_path_samples
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0;
-        for (int b = 0; b < 16; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
+        for (int b = 0; b < 2 * TCPT_BUCKET_STRIDE; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
         st.counters[24] = 0; st.counters[25] = 0;             // work counters of the persistent trace kernels
         atomicAdd(&st.stats[4], (unsigned long long)n_slots);
     }
@@ -87,14 +91,16 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 // Besides the hit record, every ray is filed into a BUCKET by what k_shade will have to do with it (miss / material type of
 // the hit), so that k_shade's warps run one material's code instead of serialising up to six branches (ncu on the first
 // version: 8.6 of 32 lanes active in the bounce-1 shade launch).  Filing = one warp-aggregated atomic per distinct bucket.
-#define TCPT_N_BUCKETS 8
 #ifndef TCPT_SHADE_MIN_BLOCKS
 #define TCPT_SHADE_MIN_BLOCKS 4
 #endif
 // shading order: heaviest code first so the tail of the launch is made of cheap vertices
-__device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim) {
+// `killed`: Russian roulette already ended the path behind this ray (decided when the ray was spawned, see shade_vertex); its hit
+// only matters if it is a light, so non-emissive hits go to a terminal bucket that just hands the path to the sensor.
+__device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim, bool killed) {
     if (prim < 0) return 7u;                                     // miss: environment lookup only
     const int t = sc.materials[sc.primitives[prim].material].type;
+    if (killed && t != TCPT_MAT_EMISSIVE) return 8u;
     return t == TCPT_MAT_CLEARCOAT_PBR ? 0u : t == TCPT_MAT_SIMPLE_PBR ? 1u : t == TCPT_MAT_PLASTIC ? 2u : t == TCPT_MAT_GLASS ? 3u : t == TCPT_MAT_METAL ? 4u
          : t == TCPT_MAT_LAMBERT ? 5u : 6u;
 }
@@ -102,10 +108,11 @@ __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim) {
 // work counters of the persistent trace kernels: counters[24] closest, counters[25] shadow.  Each is zeroed by an earlier kernel
 // of the same bounce (stream order): k_generate / k_shade zero [24] for the next k_trace_closest, k_trace_closest zeroes [25].
 // what a finished extension ray leaves behind: its hit record and its place in a shading bucket
-__device__ __forceinline__ void commit_closest(const DScene& sc, const DState& st, float4* __restrict__ hit0, uint2* __restrict__ hit1, uint32_t* bcount, uint32_t i, const DHit& h) {
+__device__ __forceinline__ void commit_closest(const DScene& sc, const DState& st, const float4* __restrict__ q_d, float4* __restrict__ hit0, uint2* __restrict__ hit1, uint32_t* bcount, uint32_t i, const DHit& h) {
     hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
     hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
-    const uint32_t b = bucket_of(sc, h.prim);
+    const bool killed = (__float_as_uint(q_d[i].w) & 0x80000000u) != 0u;  // ext_d.w = slot | killed << 31
+    const uint32_t b = bucket_of(sc, h.prim, killed);
     const uint32_t peers = __match_any_sync(__activemask(), b);
     const uint32_t lane = threadIdx.x & 31u;
     const int leader = __ffs(peers) - 1;
@@ -138,15 +145,15 @@ template <bool COUNT>
 __global__ void __launch_bounds__(128, 6) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                         float4* __restrict__ hit0, uint2* __restrict__ hit1, const __grid_constant__ DState st, int cur) {
     const uint32_t n = st.counters[cur];
-    uint32_t* bcount = st.counters + 4 + 8 * cur;  // this bounce's bucket sizes (zeroed one bounce ago)
+    uint32_t* bcount = st.counters + 4 + TCPT_BUCKET_STRIDE * cur;  // this bounce's bucket sizes (zeroed one bounce ago)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // the queues this bounce's k_shade appends to were last read one bounce ago (stream order): reset them here
         st.counters[cur ^ 1] = 0; st.counters[2] = 0; st.counters[25] = 0;
-        for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + 8 * (cur ^ 1) + b] = 0;
+        for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + TCPT_BUCKET_STRIDE * (cur ^ 1) + b] = 0;
         atomicAdd(&st.stats[0], (unsigned long long)n);
     }
     uint32_t nb = 0, nt = 0;
-    trace_queue<false, COUNT>(sc, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, hit0, hit1, bcount, i, h); });
+    trace_queue<false, COUNT>(sc, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, q_d, hit0, hit1, bcount, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -169,10 +176,10 @@ __global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__
 template <bool COUNT>
 __global__ void __launch_bounds__(128, 6) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
     const uint32_t n_sh = st.counters[sh], n = st.counters[cur];
-    uint32_t* bcount = st.counters + 4 + 8 * cur;
+    uint32_t* bcount = st.counters + 4 + TCPT_BUCKET_STRIDE * cur;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st.counters[cur ^ 1] = 0; st.counters[sh ^ 1] = 0;
-        for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + 8 * (cur ^ 1) + b] = 0;
+        for (int b = 0; b < TCPT_N_BUCKETS; ++b) st.counters[4 + TCPT_BUCKET_STRIDE * (cur ^ 1) + b] = 0;
         atomicAdd(&st.stats[0], (unsigned long long)n);
         atomicAdd(&st.stats[1], (unsigned long long)n_sh);
     }
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(128, 6) k_trace_fused(const __grid_constant__ 
     // walked side by side was measured slower: 16.6 vs 15.3 ms per 33 M paths.)
     if (n_sh) trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
     float4* __restrict__ hit0 = st.hit0; uint2* __restrict__ hit1 = st.hit1;
-    if (n) trace_queue<false, COUNT>(sc, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, hit0, hit1, bcount, i, h); });
+    if (n) trace_queue<false, COUNT>(sc, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, st.ext_d[cur], hit0, hit1, bcount, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -194,6 +201,7 @@ struct ShadeOut {
 // bucket -> compile-time material type (see bucket_of)
 template <int B> struct BucketInfo {
     static constexpr bool miss = B == 7;
+    static constexpr bool terminal = B == 8;   // Russian roulette ended the path and the hit is not a light: nothing left to shade
     static constexpr int mat = B == 0 ? TCPT_MAT_CLEARCOAT_PBR : B == 1 ? TCPT_MAT_SIMPLE_PBR : B == 2 ? TCPT_MAT_PLASTIC : B == 3 ? TCPT_MAT_GLASS : B == 4 ? TCPT_MAT_METAL
                               : B == 5 ? TCPT_MAT_LAMBERT : TCPT_MAT_EMISSIVE;
 };
@@ -225,6 +233,21 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     LightTable lt; bool lt_ready = false;
     auto lights = [&]() -> const LightTable& { if (!lt_ready) { light_table(sc, wl, lt); lt_ready = true; } return lt; };
 
+    if constexpr (BucketInfo<B>::terminal) {
+        // calculate_bsdf_contribution of a NON-emissive hit: the reference still adds throughput * next_emissive(= 0) [* w], and with an
+        // infinite BSDF pdf the MIS weight inf / (inf + 0) is NaN, which poisons the contribution (scene 11's NaN pixels): same arithmetic here
+        const S4 zero = s4(0.0f);
+        const bool spec_prev = (flags & FLAG_SPEC_PREV) != 0;
+        if (integrator == TCPT_INTEGRATOR_PT) con = con + thr * zero;
+        else if (integrator == TCPT_INTEGRATOR_NEE || spec_prev) { if (spec_prev) con = con + thr * zero; }
+        else {
+            const float a = pdf_prev, b = 0.0f;  // Scene::pdf_light_sample of a non-emissive primitive
+            const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
+            con = con + thr * zero * w;
+        }
+        finish();
+        return;
+    }
     if constexpr (miss) {
         if (sc.n_envs != 0) {
             if (stage == 0) {
@@ -280,13 +303,12 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
                 con = con + thr * next_emissive * w;                          // mis_renderer.rs:164-179
             }
         }
+        // Russian roulette (base_renderer.rs:76-92) was DECIDED one launch ago, when this ray was spawned (see the end of this
+        // function): the throughput after the bounce does not depend on what the ray hits.  A ray that reaches a material bucket
+        // survived; its random number is already drawn, only the rescaling is left.
         thr = thr * modifier;
-        const float p_rr = s4_max(thr);                                       // base_renderer.rs:76-92
-        if (!(p_rr >= 1.0f)) {
-            const float ur = smp.get_1d();
-            if (ur < p_rr) { if (p_rr != 0.0f) { thr.v[0] /= p_rr; thr.v[1] /= p_rr; thr.v[2] /= p_rr; thr.v[3] /= p_rr; } }
-            else { finish(); return; }
-        }
+        const float p_rr = s4_max(thr);
+        if (!emissive && !(p_rr >= 1.0f) && p_rr != 0.0f) { thr.v[0] /= p_rr; thr.v[1] /= p_rr; thr.v[2] /= p_rr; thr.v[3] /= p_rr; }
     }
     if (stage >= R.max_depth || emissive) { finish(); return; }  // depth loop bound (:197) / emitters have no BSDF (:199-202)
     if constexpr (!emissive) {
@@ -446,9 +468,19 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     const float sign = dot(hit.normal, wi_render) < 0.0f ? -1.0f : 1.0f;
     const float3 origin = hit.position + (sign * hit.normal) * 1e-5f;
     const float3 o2 = origin + wi_render * 1e-5f;
+    // Russian roulette of this bounce, decided now (base_renderer.rs:76-92 runs it after the next intersection, but neither the
+    // throughput nor the sampler dimension depends on that hit, and an emissive or missed hit ends the path whatever the outcome).
+    // A killed path still needs its ray traced -- the hit may be a light -- but then goes to the terminal bucket instead of
+    // riding through a material's shading code with its lane switched off (bounce-1 shading ran at 16-22 of 32 lanes).
+    bool killed = false;
+    if (stage + 1 <= R.max_depth) {
+        const S4 thr2 = thr * (ms.f * (1.0f / ms.pdf));
+        const float p_rr = s4_max(thr2);
+        if (!(p_rr >= 1.0f)) killed = !(smp.get_1d() < p_rr);
+    }
     out.push_ext = true;
     out.eo = make_float4(o2.x, o2.y, o2.z, TCPT_FLT_MAX);
-    out.ed = make_float4(wi_render.x, wi_render.y, wi_render.z, __uint_as_float(slot));
+    out.ed = make_float4(wi_render.x, wi_render.y, wi_render.z, __uint_as_float(slot | (killed ? 0x80000000u : 0u)));
     st.thr[slot] = to_f4(thr);
     st.con[slot] = to_f4(con);
     st.fprev[slot] = to_f4(ms.f);
@@ -467,7 +499,7 @@ __device__ __forceinline__ void shade_position(const DScene& sc, const DRender& 
     if (p < n) {
         const uint32_t i = order[p];
         const float4 d = st.ext_d[cur][i];
-        shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+        shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
     }
     if (B < 6) {  // emissive hits and misses end the path: nothing to push
         const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
@@ -483,7 +515,7 @@ __global__ void __launch_bounds__(128, (B >= 6 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_s
                                                                                      const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, int sh, uint32_t stage) {
     if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n = st.counters[4 + 8 * cur + B];
+    const uint32_t n = st.counters[4 + TCPT_BUCKET_STRIDE * cur + B];
     const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) shade_position<B>(sc, R, st, L, cur, sh, stage, p, n);
 }
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(128, (B >= 6 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_s
 template <int B>
 __device__ __noinline__ void shade_vertex_call(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, uint32_t stage, uint32_t i, ShadeOut& out) {
     const float4 d = st.ext_d[cur][i];
-    shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w), st.hit0[i], st.hit1[i], out);
+    shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
 }
 
 // All buckets in one launch: the launch is cut into chunks of 128 consecutive positions of ONE bucket, numbered bucket by bucket
@@ -505,7 +537,7 @@ __global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade_all(const 
     if (blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
     uint32_t cnt[TCPT_N_BUCKETS], total = 0;
 #pragma unroll
-    for (int b = 0; b < TCPT_N_BUCKETS; ++b) { cnt[b] = st.counters[4 + 8 * cur + b]; total += (cnt[b] + 127u) >> 7; }
+    for (int b = 0; b < TCPT_N_BUCKETS; ++b) { cnt[b] = st.counters[4 + TCPT_BUCKET_STRIDE * cur + b]; total += (cnt[b] + 127u) >> 7; }
     for (uint32_t v = blockIdx.x; v < total; v += gridDim.x) {
         uint32_t c = v, n = cnt[0]; int b = 0;
 #pragma unroll
@@ -522,7 +554,8 @@ __global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade_all(const 
                 case 4: shade_vertex_call<4>(sc, R, st, L, cur, stage, i, out); break;
                 case 5: shade_vertex_call<5>(sc, R, st, L, cur, stage, i, out); break;
                 case 6: shade_vertex_call<6>(sc, R, st, L, cur, stage, i, out); break;
-                default: shade_vertex_call<7>(sc, R, st, L, cur, stage, i, out); break;
+                case 7: shade_vertex_call<7>(sc, R, st, L, cur, stage, i, out); break;
+                default: shade_vertex_call<8>(sc, R, st, L, cur, stage, i, out); break;
             }
         }
         if (b < 6) {  // emissive hits and misses end the path: nothing to push (b is uniform over the block)

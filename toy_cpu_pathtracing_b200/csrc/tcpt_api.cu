@@ -301,7 +301,8 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
                 k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                 k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                 k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                ctx->stats.kernel_launches += 8;
+                k_shade<8><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                ctx->stats.kernel_launches += 9;
             }
         }
         if (ctx->opt.debug_path_log && n_slots == 1) debug_dump(ctx, "after shade", stage, cur ^ 1, stream);
