@@ -367,7 +367,7 @@ def main_gpu(args, wl):
         "stage_ms_per_step": {k: tot[k] / args.steps for k in ("gen_ms", "closest_ms", "shade_ms", "shadow_ms", "film_ms")},
         "scene_build_s": build_s,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only
         try:
             mr, mp, info = run_cpu(wl, scene.desc, cam, args.cpu_seconds)
             line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": info["cores"], "kind": "port", "sample": info["sample"], "mpaths_per_s": mp}
