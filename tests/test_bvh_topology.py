@@ -55,9 +55,10 @@ def test_single_item_is_a_leaf(built):
     assert np.array_equal(ref, host_build_boxes(b))
 
 
-@pytest.mark.parametrize("scene_id", [3, 17, 19])
+@pytest.mark.parametrize("scene_id", [1, 3, 7, 17, 19])
 def test_scene_bvhs_match_literal_reference_build(bundle_factory, tables, scene_id):
-    """TLAS (incl. the rotate-scale-translate instance of scene 17 and the three instances of scene 19) and every BLAS."""
+    """TLAS (incl. the rotate-scale-translate instance of scene 17, the three instances of scene 19, the four scaled instances of scene 7
+    and the vertex-tight box of scene 1's SingleTriangle next to its rotated mesh instance) and every BLAS."""
     from oracle import oracle
     b = bundle_factory(scene_id, 64, 48, require_gpu=False)
     lit = oracle.scene_from_description(b.scene.desc, b.camera.position, tables[0], tables[1], literal_build=len(b.scene.desc.meshes[0].indices) <= 6000)
@@ -69,6 +70,25 @@ def test_scene_bvhs_match_literal_reference_build(bundle_factory, tables, scene_
             ref = lit.get_bvh(which) if which < 0 or len(b.scene.desc.meshes[which].indices) <= 6000 else b.oracle.get_bvh(which)
         got = b.scene.get_bvh(which)
         assert got.shape == ref.shape and np.array_equal(got, ref), f"scene {scene_id} bvh {which}"
+
+
+def test_single_triangle_tangent_and_delta_light_errors(bundle_factory):
+    """SingleTriangle geometry keeps the reference's unfallbacked per-hit tangent (single_triangle.rs:118-124); delta lights validate
+    their arguments with codes."""
+    import ctypes as C
+    from toy_cpu_pathtracing_b200 import capi
+    b = bundle_factory(1, 64, 48, require_gpu=False)
+    single = [i for i, m in enumerate(b.scene.desc.meshes) if m.single]
+    assert len(single) == 1
+    t_h, t_o = b.scene.mesh_tangents(single[0]), b.oracle.mesh_tangents(single[0])
+    assert t_h.shape == (1, 3) and np.array_equal(t_h.view(np.uint32), t_o.view(np.uint32)) and np.allclose(t_h[0], [1, 0, 0])
+    ctx = b.scene.ctx
+    spec = capi.SpectrumParam(capi.SPEC_D65, (C.c_float * 3)(0, 0, 0), -1)
+    eye = np.eye(4, dtype=np.float32)
+    assert ctx.lib.tcpt_scene_add_delta_light(ctx.handle, 9, 1.0, C.byref(spec), 0.0, 0.0, capi.as_ptr(eye, C.c_float)) == capi.TCPT_ERR_INVALID
+    spec.kind = capi.SPEC_TEXTURE_SRGB
+    assert ctx.lib.tcpt_scene_add_delta_light(ctx.handle, capi.LIGHT_POINT, 1.0, C.byref(spec), 0.0, 0.0, capi.as_ptr(eye, C.c_float)) == capi.TCPT_ERR_INVALID
+    assert ctx.lib.tcpt_scene_add_single_triangle(ctx.handle, None, None, None) == capi.TCPT_ERR_INVALID
 
 
 def test_load_time_tangents_and_table_indices_match(bundle_factory):

@@ -19,8 +19,50 @@ from .scene import (ColorSrgb, ColorSrgbLinear, ConstantSpectrum, CreatePrimitiv
 GP = CreatePrimitiveDesc.GeometryPrimitive
 
 
+# the reference's own asset files (renderer/assets/, git-LFS payloads): used instead of the stand-ins when TCPT_ASSET_DIR points at a
+# checkout that holds them; an LFS pointer stub or a missing file falls back to the procedural stand-in
+_REAL_ASSETS = {
+    "bunny": "bunny.obj", "dragon": "dragon.min.obj", "box": "box.obj", "light": "light.obj", "hidari": "hidari.obj", "migi": "migi.obj",
+    "yuka": "yuka.obj", "oku": "oku.obj", "tenjou": "tenjou.obj",
+    "bunny_basecolor": "bunny-material-0/BaseColor.png", "bunny_normal": "bunny-material-0/Normal.png",
+    "bunny1_basecolor": "bunny-material-1/BaseColor.png", "bunny1_normal": "bunny-material-1/Normal.png",
+    "dragon_basecolor": "dragon-material/BaseColor.png", "dragon_normal": "dragon-material/Normal.png", "dragon_metallic": "dragon-material/Metallic.png",
+    "dragon_roughness": "dragon-material/Roughness.png", "dragon_coat_thickness": "dragon-material/ClearcoatThickness.png",
+    "sky": "sky/scythian_tombs_2_1k.exr",
+}
+_GRAY = {"dragon_metallic", "dragon_roughness", "dragon_coat_thickness"}
+
+
+def real_asset_path(name: str):
+    """Path of the reference's own file for `name` if TCPT_ASSET_DIR holds its payload, else None."""
+    import os
+    from pathlib import Path
+    root = os.environ.get("TCPT_ASSET_DIR")
+    if not root or name not in _REAL_ASSETS:
+        return None
+    p = Path(root) / _REAL_ASSETS[name]
+    if not p.is_file() or p.stat().st_size < 1024 and p.read_bytes().startswith(b"version https://git-lfs"):
+        return None
+    return p
+
+
+def _load_real(name: str, path):
+    from .scene import _load_image, load_obj
+    if str(path).endswith(".obj"):
+        return load_obj(path)
+    if str(path).endswith(".exr"):
+        import os
+        os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+        import cv2
+        return np.ascontiguousarray(cv2.imread(str(path), cv2.IMREAD_UNCHANGED)[..., 2::-1], dtype=np.float32)
+    return _load_image(path, 1 if name in _GRAY else 3)
+
+
 @functools.lru_cache(maxsize=None)
 def _asset(name: str):
+    real = real_asset_path(name)
+    if real is not None:
+        return _load_real(name, real)
     if name == "bunny":
         return assets.blob(center=(-0.8, 1.0, 0.4), radius=1.0, nu=50, nv=50)
     if name == "dragon":
