@@ -15,6 +15,12 @@
 
 // shading buckets (see bucket_of): counters[4 + TCPT_BUCKET_STRIDE * parity + bucket] holds their sizes
 #define TCPT_N_BUCKETS 9
+#ifndef TCPT_SHADE_MIN_BLOCKS_LAMBERT
+#define TCPT_SHADE_MIN_BLOCKS_LAMBERT 4
+#endif
+#ifndef TCPT_TRACE_MIN_BLOCKS
+#define TCPT_TRACE_MIN_BLOCKS 7   // 72 registers: 28 warps per SM (swept 5..8: 3.47 / 3.22 / 3.15 / 3.18 ms per spp)
+#endif
 #define TCPT_BUCKET_STRIDE 10
 
 namespace tcpt {
@@ -75,8 +81,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         const float3 o = f3(0.0f, 0.0f, 0.0f) + d * 1e-5f;  // move_forward(1e-5) (base_renderer.rs:177)
         st.ext_o[0][slot] = make_float4(o.x, o.y, o.z, TCPT_FLT_MAX);
         st.ext_d[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
-        st.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-        st.con[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // throughput = 1 and contribution = 0 are implied at bounce 0 (shade_vertex does not load them there): 32 B per path less each way
         st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(smp.dim), __uint_as_float(0u));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__
 // `cur` = parity of the extension queue to trace, `sh` = index (2 or 3) of the shadow-queue size to read; the sizes the next
 // k_shade appends to (counters[cur ^ 1], counters[sh ^ 1]) were last read one launch ago and are reset here.
 template <bool COUNT>
-__global__ void __launch_bounds__(128, 6) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
+__global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
     const uint32_t n_sh = st.counters[sh], n = st.counters[cur];
     uint32_t* bcount = st.counters + 4 + TCPT_BUCKET_STRIDE * cur;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -206,10 +211,12 @@ template <int B> struct BucketInfo {
                               : B == 5 ? TCPT_MAT_LAMBERT : TCPT_MAT_EMISSIVE;
 };
 
-template <int B>
-__device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R, const DState& st, const PathList& L, uint32_t stage,
+// FIRST = compiled for bounce 0 only (k_shade<B, true>): no previous-bounce half, no state loads beyond the wavelength record
+template <int B, bool FIRST = false>
+__device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R, const DState& st, const PathList& L, uint32_t stage_in,
                                              float3 ray_d, uint32_t slot, const float4 h0, const uint2 h1, ShadeOut& out) {
     constexpr int MT = BucketInfo<B>::mat;
+    const uint32_t stage = FIRST ? 0u : stage_in;
     out.push_ext = false; out.push_sh = false;
     const float4 misc = st.misc[slot];
     float pdf_prev = misc.x;
@@ -220,7 +227,8 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     path_coords(R, L, slot, &px, &py, &si);
     DSampler smp = make_sampler(R, px, py, si);
     smp.dim = __float_as_uint(misc.z);
-    S4 thr = s4(st.thr[slot]), con = s4(st.con[slot]);
+    S4 thr = s4(1.0f), con = s4(0.0f);
+    if (!FIRST && stage != 0u) { thr = s4(st.thr[slot]); con = s4(st.con[slot]); }
     const int integrator = R.integrator;
     constexpr bool miss = BucketInfo<B>::miss;
 
@@ -250,7 +258,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     }
     if constexpr (miss) {
         if (sc.n_envs != 0) {
-            if (stage == 0) {
+            if (FIRST || stage == 0) {
                 S4 radiance;
                 scene_env_radiance_pdf(sc, nullptr, ray_d, wl, &radiance, nullptr);
                 con = con + thr * radiance;  // base_renderer.rs:180-186
@@ -279,7 +287,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     const tcpt_flat_material& mat = sc.materials[hit.material];
     constexpr bool emissive = MT == TCPT_MAT_EMISSIVE;
 
-    if (stage == 0) {
+    if (FIRST || stage == 0) {
         if (emissive) con = con + thr * emissive_radiance(sc, mat, hit.uv, wl);  // base_renderer.rs:190-194
     } else {
         // second half of the previous bounce: calculate_bsdf_contribution, throughput update, Russian roulette
@@ -492,14 +500,14 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
 }
 
 // Shades position p of bucket B's range of the bucketed order (p >= n: the lane only takes part in the warp-collective pushes).
-template <int B>
+template <int B, bool FIRST = false>
 __device__ __forceinline__ void shade_position(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, int sh, uint32_t stage, uint32_t p, uint32_t n) {
     const uint32_t* __restrict__ order = st.order + (size_t)B * st.capacity;
     ShadeOut out; out.push_ext = false; out.push_sh = false;
     if (p < n) {
         const uint32_t i = order[p];
         const float4 d = st.ext_d[cur][i];
-        shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
+        shade_vertex<B, FIRST>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
     }
     if (B < 6) {  // emissive hits and misses end the path: nothing to push
         const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
@@ -510,14 +518,14 @@ __device__ __forceinline__ void shade_position(const DScene& sc, const DRender& 
 }
 
 // One instantiation per shading bucket; each walks only its own range of the bucketed order.
-template <int B>
-__global__ void __launch_bounds__(128, (B >= 6 ? 8 : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
+template <int B, bool FIRST = false>
+__global__ void __launch_bounds__(128, (B >= 6 ? 8 : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
                                                                                      const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, int sh, uint32_t stage) {
     if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n = st.counters[4 + TCPT_BUCKET_STRIDE * cur + B];
     const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) shade_position<B>(sc, R, st, L, cur, sh, stage, p, n);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n);
 }
 
 // shade_vertex<B> behind a call, so that the eight instantiations keep their own register allocation inside k_shade_all

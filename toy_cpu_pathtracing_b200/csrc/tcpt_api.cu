@@ -293,15 +293,27 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
                 k_shade_all<<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                 ctx->stats.kernel_launches++;
             } else {
-                k_shade<0><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<1><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<2><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                k_shade<8><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                if (stage == 0) {  // bounce 0 has its own instantiations (no previous-bounce half; the terminal bucket is empty)
+                    k_shade<0, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<1, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<2, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<3, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<4, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<5, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<6, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<7, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<8, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                } else {
+                    k_shade<0><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<1><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<2><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<8><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                }
                 ctx->stats.kernel_launches += 9;
             }
         }
