@@ -364,6 +364,11 @@ def main_gpu(args, wl):
         "roofline_fp32": {"kernels": "k_trace_fused", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
                           "flops_per_ray": flops_per_ray, "box_tests_per_ray": box_per_ray, "tri_tests_per_ray": tri_per_ray, "sm_mhz": sm_mhz,
                           "definition": "18*B + 64*T + 60 flops per ray (SURVEY.md 8d); peak = 148 SM x 128 lanes x 2 x f_SM"},
+        # node records (64 B per visited pair = 32 B per box test) and triangle records (48 B per test) are served by
+        # L1 / L2 (the BVH is L2 resident); informational, no measured L1/L2 peak to divide by
+        "bvh_traffic": {"kernel": "k_trace_fused", "bytes_per_ray": 32.0 * box_per_ray + 48.0 * tri_per_ray,
+                        "achieved": (32.0 * box_per_ray + 48.0 * tri_per_ray) * tot["rays"] / trace_s / 1e9 if trace_s > 0 else 0.0, "unit": "GB/s",
+                        "served_by": "L1/L2", "trace_only_mrays_per_s": tot["rays"] / trace_s / 1e6 if trace_s > 0 else 0.0},
         "stage_ms_per_step": {k: tot[k] / args.steps for k in ("gen_ms", "closest_ms", "shade_ms", "shadow_ms", "film_ms")},
         "scene_build_s": build_s,
     }
