@@ -30,7 +30,8 @@ enum {
 };
 
 /* ---- enumerations mirrored from the reference CLI (renderer/src/main.rs:20-53) */
-enum { TCPT_INTEGRATOR_PT = 0, TCPT_INTEGRATOR_NEE = 1, TCPT_INTEGRATOR_MIS = 2 }; /* SrgbRendererPt / Nee / Mis */
+enum { TCPT_INTEGRATOR_PT = 0, TCPT_INTEGRATOR_NEE = 1, TCPT_INTEGRATOR_MIS = 2, /* SrgbRendererPt / Nee / Mis */
+       TCPT_INTEGRATOR_ALBEDO = 3, TCPT_INTEGRATOR_NORMAL = 4 }; /* AOV renderers: AlbedoRenderer / NormalRenderer (renderer/src/renderer/{albedo,normal}_renderer.rs); max_depth, sharding by samples and exposure do not apply */
 enum { TCPT_SAMPLER_RANDOM = 0, TCPT_SAMPLER_SOBOL = 1 };                          /* RandomSampler / ZSobolSampler */
 
 /* ---- material description (scene/src/material/impls/ constructors) */

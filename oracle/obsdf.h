@@ -728,6 +728,17 @@ inline MaterialSample material_sample(const MaterialContext& c, const Material& 
 }
 
 // BsdfSurfaceMaterial::evaluate (f only; the reference's `pdf: 1.0` field is never read)
+// BsdfSurfaceMaterial::sample_albedo_spectrum (lambert_material.rs:172-178, plastic_material.rs:266-273, simple_pbr_material.rs:259-266,
+// simple_pbr_clearcoat_material.rs:435-442, metal_material.rs:267-278, glass_material.rs:224-231)
+inline SampledSpectrum material_albedo(const MaterialContext& c, const Material& m, const SampledWavelengths& wl, Vec2 uv) {
+    switch (m.type) {
+        case MAT_LAMBERT: case MAT_SIMPLE_PBR: case MAT_CLEARCOAT_PBR: return sample_spectrum_param(c, m.color, uv).sample(*c.T, wl);
+        case MAT_METAL: return fresnel_complex(1.0f, m.color.spectrum.sample(*c.T, wl), m.coat_tint.spectrum.sample(*c.T, wl));
+        case MAT_PLASTIC: case MAT_GLASS: return SampledSpectrum::constant(1.0f);
+        default: return SampledSpectrum::zero();
+    }
+}
+
 inline SampledSpectrum material_evaluate(const MaterialContext& c, const Material& m, const SampledWavelengths& wl, Vec3 wo, Vec3 wi, const TangentShadingPoint& sp) {
     NormalMapFrame fr(sample_normal_param(c, m.normal, sp.uv));
     Vec3 wo_nm = transform_vector3(fr.to_nm, wo), wi_nm = transform_vector3(fr.to_nm, wi);

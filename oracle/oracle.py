@@ -113,7 +113,7 @@ class OracleScene:
     def params(width, height, spp, integrator, sampler, camera, seed=0, max_depth=16, exposure=1.0, threads=0, window=(0, 0, 0, 0)) -> OrcRenderParams:
         p = OrcRenderParams()
         p.width, p.height, p.spp, p.seed, p.max_depth = width, height, spp, seed, max_depth
-        p.integrator = {"pt": 0, "nee": 1, "mis": 2}[integrator]
+        p.integrator = {"pt": 0, "nee": 1, "mis": 2, "albedo": 3, "normal": 4}[integrator]
         p.sampler = {"random": 0, "sobol": 1}[sampler]
         p.exposure, p.fov_deg, p.threads = exposure, camera.fov, threads
         for k in range(3):

@@ -11,7 +11,7 @@
 
 namespace orc {
 
-enum Integrator : int { INTEG_PT = 0, INTEG_NEE = 1, INTEG_MIS = 2 };
+enum Integrator : int { INTEG_PT = 0, INTEG_NEE = 1, INTEG_MIS = 2, INTEG_ALBEDO = 3, INTEG_NORMAL = 4 };
 enum SamplerKind : int { SAMPLER_RANDOM = 0, SAMPLER_SOBOL = 1 };
 
 struct Camera {
@@ -71,6 +71,10 @@ struct Sensor {
         return rgb * exposure;
     }
     void add_sample(const Tables& T, const SampledWavelengths& wl, const SampledSpectrum& s) { acc = acc + sample_to_rgb(T, wl, s, exposure); }
+    static Vec3 finalize_no_tone_map(Vec3 acc, uint32_t spp) {  // Sensor<GamutSrgb, NoneToneMap, GammaSrgb>::to_rgb (albedo_renderer.rs:38-39)
+        Vec3 c = vmax(acc / (float)spp, Vec3(0, 0, 0));
+        return Vec3(srgb_oetf(c.x), srgb_oetf(c.y), srgb_oetf(c.z));
+    }
     static Vec3 finalize(Vec3 acc, uint32_t spp) {
         Vec3 avg = acc / (float)spp;
         Vec3 c = vmax(avg, Vec3(0, 0, 0));
@@ -202,7 +206,37 @@ struct PathTracer {
     }
 
     // BaseSrgbRenderer::render, one (pixel, sample_index) path (base_renderer.rs:160-276); returns the RGB the sensor would add
+    // AlbedoRenderer / NormalRenderer (renderer/src/renderer/{albedo,normal}_renderer.rs): one camera ray, no offset along the ray
+    Vec3 aov_path(SamplerBase& smp, uint32_t px, uint32_t py, uint32_t sample_index, RayStats* st) const {
+        const Tables& T = scene.T;
+        smp.start_pixel_sample(px, py, sample_index);
+        const float FMAX = std::numeric_limits<float>::max();
+        if (rp.integrator == INTEG_NORMAL) {  // normal_renderer.rs:33-69: the pixel sample is the FIRST thing drawn
+            Vec2 uvp = smp.get_2d_pixel();
+            Ray ray = cam.sample_ray(px, py, uvp);
+            Intersection hit;
+            if (!scene.intersect(ray, FMAX, &hit, st)) return Vec3(0, 0, 0);
+            Vec3 n = hit.si.shading_normal;
+            if (scene.materials[hit.si.material].type != MAT_EMISSIVE) n = transform_normal(shading_transform(hit.si), hit.si.shading_normal);
+            return Vec3(n.x * 0.5f + 0.5f, n.y * 0.5f + 0.5f, n.z * 0.5f + 0.5f) * 1.0f;
+        }
+        float u = smp.get_1d();  // albedo_renderer.rs:41-66
+        SampledWavelengths wl = SampledWavelengths::new_uniform(u);
+        Vec2 uvp = smp.get_2d_pixel();
+        Ray ray = cam.sample_ray(px, py, uvp);
+        Intersection hit;
+        if (!scene.intersect(ray, FMAX, &hit, st)) return Vec3(0, 0, 0);
+        const Material& m = scene.materials[hit.si.material];
+        if (m.type == MAT_EMISSIVE) return Vec3(0, 0, 0);
+        MaterialContext mc{&T, &scene.textures, smp.aux_base(), 0};
+        SampledSpectrum a = material_albedo(mc, m, wl, hit.si.uv) * 1.0f;
+        SampledSpectrum out;
+        for (int i = 0; i < NS; ++i) out.v[i] = a.v[i] * dense_value(T.d65, wl.lambda[i]);  // multiply_spectrum (sampled_spectrum.rs:270-281)
+        return Sensor::sample_to_rgb(T, wl, out, 1.0f);
+    }
+
     Vec3 trace_path(SamplerBase& smp, uint32_t px, uint32_t py, uint32_t sample_index, RayStats* st) const {
+        if (rp.integrator >= INTEG_ALBEDO) return aov_path(smp, px, py, sample_index, st);
         const Tables& T = scene.T;
         smp.start_pixel_sample(px, py, sample_index);
         MaterialContext mc{&T, &scene.textures, smp.aux_base(), 0};
@@ -323,7 +357,7 @@ struct PathTracer {
                 for (uint32_t s = 0; s < rp.spp; ++s) acc = acc + trace_path(*smp, px, py, s, &stats[tid]);
                 size_t o = ((size_t)py * rp.width + px) * 3;
                 if (out_acc) { out_acc[o] = acc.x; out_acc[o + 1] = acc.y; out_acc[o + 2] = acc.z; }
-                if (out_srgb) { Vec3 c = Sensor::finalize(acc, rp.spp); out_srgb[o] = c.x; out_srgb[o + 1] = c.y; out_srgb[o + 2] = c.z; }
+                if (out_srgb) { Vec3 c = rp.integrator == INTEG_NORMAL ? acc / (float)rp.spp : rp.integrator == INTEG_ALBEDO ? Sensor::finalize_no_tone_map(acc, rp.spp) : Sensor::finalize(acc, rp.spp); out_srgb[o] = c.x; out_srgb[o + 1] = c.y; out_srgb[o + 2] = c.z; }
             }
         };
         std::vector<std::thread> th;

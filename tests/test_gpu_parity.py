@@ -169,3 +169,20 @@ def test_max_depth_and_seed_are_honoured(bundle_factory):
         acc, _, st = b.oracle.render(b.oparams("mis", "sobol", 16, seed=seed, max_depth=depth))
         assert abs(img.stats["closest_rays"] - st["closest_rays"]) <= 1e-3 * st["closest_rays"]
         assert np.abs(img.accumulators - acc).mean() / np.abs(acc).mean() <= MRE_TOL
+
+
+@pytest.mark.parametrize("scene_id", [3, 7, 17, 19])
+@pytest.mark.parametrize("aov", ["albedo", "normal"])
+def test_aov_renderers_match_oracle(bundle_factory, scene_id, aov):
+    """AlbedoRenderer / NormalRenderer (renderer/src/renderer/{albedo,normal}_renderer.rs): one unoffset camera ray per sample; the
+    normal renderer draws no wavelength, the albedo renderer's sensor has no tone map."""
+    w, h, spp = 64, 48, 16
+    b = bundle_factory(scene_id, w, h)
+    img = b.image(aov, spp).render("sobol")
+    acc, srgb, st = b.oracle.render(b.oparams(aov, "sobol", spp))
+    assert img.stats["closest_rays"] == w * h * spp == st["closest_rays"] and img.stats["shadow_rays"] == 0
+    assert np.abs(img.accumulators - acc).mean() <= 1e-5 * np.abs(acc).mean()
+    assert np.abs(img.pixels - srgb).max() <= 2e-5
+    if aov == "normal":   # a normal in its own shading frame is +z: every hit pixel is (0.5, 0.5, 1) except on emitters
+        hit = srgb.sum(axis=2) > 0
+        assert np.allclose(np.median(srgb[hit], axis=0), [0.5, 0.5, 1.0], atol=1e-5)

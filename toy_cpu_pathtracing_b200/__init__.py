@@ -5,7 +5,7 @@ package is the host-side mirror of the reference's `scene` / `renderer` construc
 """
 from . import capi  # noqa: F401
 from .capi import Context, TcptError  # noqa: F401
-from .renderer import (BoxFilter, Camera, RandomSampler, ReinhardToneMap, RendererArgs, RendererImage, SrgbRendererMis,  # noqa: F401
+from .renderer import (AlbedoRenderer, NormalRenderer, BoxFilter, Camera, RandomSampler, ReinhardToneMap, RendererArgs, RendererImage, SrgbRendererMis,  # noqa: F401
                        SrgbRendererNee, SrgbRendererPt, ZSobolSampler, RENDERERS)
 from .scene import (ColorSrgb, ColorSrgbLinear, ConstantSpectrum, CreatePrimitiveDesc, EmissiveMaterial, FloatParameter,  # noqa: F401
                     FloatTexture, GlassMaterial, GlassType, LambertMaterial, MetalMaterial, MetalType, NormalParameter, NormalTexture, PlasticMaterial, RgbAlbedoSpectrum, RgbTexture,

@@ -13,7 +13,7 @@ LIB_PATH = PKG_DIR / "lib" / "libtcpt.so"
 DATA_DIR = PKG_DIR / "data"
 
 TCPT_OK, TCPT_ERR_INVALID, TCPT_ERR_CUDA, TCPT_ERR_LIMIT, TCPT_ERR_NOMEM = 0, -1, -2, -3, -4
-INTEGRATORS = {"pt": 0, "nee": 1, "mis": 2}
+INTEGRATORS = {"pt": 0, "nee": 1, "mis": 2, "albedo": 3, "normal": 4}
 SAMPLERS = {"random": 0, "sobol": 1}
 MAT_LAMBERT, MAT_EMISSIVE, MAT_PLASTIC, MAT_SIMPLE_PBR, MAT_CLEARCOAT_PBR, MAT_METAL, MAT_GLASS = range(7)
 SPEC_CONSTANT, SPEC_RGB_ALBEDO_SRGB, SPEC_RGB_ALBEDO_LINEAR, SPEC_D65, SPEC_TEXTURE_SRGB, SPEC_PRESET = range(6)

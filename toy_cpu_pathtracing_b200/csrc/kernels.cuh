@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         uint32_t px, py, si;
         path_coords(R, L, slot, &px, &py, &si);
         DSampler smp = make_sampler(R, px, py, si);
-        const float u = smp.get_1d();
+        // NormalRenderer draws the pixel sample first and no wavelength (normal_renderer.rs:33-40); the AOV renderers do not push the ray forward
+        const bool aov = R.integrator >= TCPT_INTEGRATOR_ALBEDO;
+        float u = 0.0f;
+        if (R.integrator != TCPT_INTEGRATOR_NORMAL) u = smp.get_1d();
         const float lambda0 = 360.0f + u * (830.0f - 360.0f);  // SampledWavelengths::new_uniform (sampled_spectrum.rs:318-336)
         const float2 uv = smp.get_2d();
         // BoxFilter::sample + Camera::sample_ray / generate_ray (filter.rs:24-30, camera.rs:51-81)
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         const float dir_y = (1.0f - 2.0f * y / (float)R.height) * cam.scale;
         const float3 rd = normalize(f3(dir_x, dir_y, -1.0f));
         const float3 d = normalize((cam.s * rd.x + cam.u * rd.y) + cam.nf * rd.z);
-        const float3 o = f3(0.0f, 0.0f, 0.0f) + d * 1e-5f;  // move_forward(1e-5) (base_renderer.rs:177)
+        const float3 o = aov ? f3(0.0f, 0.0f, 0.0f) : f3(0.0f, 0.0f, 0.0f) + d * 1e-5f;  // move_forward(1e-5) (base_renderer.rs:177)
         st.ext_o[0][slot] = make_float4(o.x, o.y, o.z, TCPT_FLT_MAX);
         st.ext_d[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
         // throughput = 1 and contribution = 0 are implied at bounce 0 (shade_vertex does not load them there): 32 B per path less each way
@@ -575,6 +578,43 @@ __global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade_all(const 
     }
 }
 
+// ---------------------------------------------------------------- AOV renderers (renderer/src/renderer/{albedo,normal}_renderer.rs): one camera ray per sample
+__device__ __noinline__ S4 material_albedo(const DScene& sc, const tcpt_flat_material& m, float2 uv, const DWavelengths& wl) {  // BsdfSurfaceMaterial::sample_albedo_spectrum
+    switch (m.type) {
+        case TCPT_MAT_LAMBERT: case TCPT_MAT_SIMPLE_PBR: case TCPT_MAT_CLEARCOAT_PBR: return spectrum_sample(sc, param_spectrum(sc, m.color, uv), wl);
+        case TCPT_MAT_METAL: return fresnel_complex(1.0f, spectrum_sample(sc, spectrum_from_flat(m.color), wl), spectrum_sample(sc, spectrum_from_flat(m.coat_tint), wl));  // metal_material.rs:267-278
+        case TCPT_MAT_PLASTIC: case TCPT_MAT_GLASS: return s4(1.0f);
+        default: return s4(0.0f);
+    }
+}
+__global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st) {
+    const uint32_t n = st.counters[0], stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 d = st.ext_d[0][i];
+        const uint32_t slot = __float_as_uint(d.w) & 0x7fffffffu;
+        const float4 h0 = st.hit0[i]; const uint2 h1 = st.hit1[i];
+        float3 rgb = f3(0.0f, 0.0f, 0.0f);
+        if ((int)h1.x >= 0) {
+            DSurface hit;
+            reconstruct_hit(sc, (int)h1.x, h1.y, h0.y, h0.z, h0.w, f3(d.x, d.y, d.z), hit);
+            const tcpt_flat_material& mat = sc.materials[hit.material];
+            if (R.integrator == TCPT_INTEGRATOR_NORMAL) {  // normal_renderer.rs:44-66
+                float3 nrm = hit.shading_normal;
+                if (mat.type != TCPT_MAT_EMISSIVE) { M3 r2t, t2r; shading_frame(hit, r2t, t2r); nrm = m3_normal_by_inverse(t2r, hit.shading_normal); }
+                rgb = f3(nrm.x * 0.5f + 0.5f, nrm.y * 0.5f + 0.5f, nrm.z * 0.5f + 0.5f) * 1.0f;
+            } else if (mat.type != TCPT_MAT_EMISSIVE) {    // albedo_renderer.rs:52-62
+                const DWavelengths wl = wavelengths_uniform(st.misc[slot].y, false);
+                const S4 a = material_albedo(sc, mat, hit.uv, wl) * 1.0f;
+                S4 s;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s.v[k] = a.v[k] * cmf_at(sc, wl.lambda[k]).w;  // multiply_spectrum with D65 (sampled_spectrum.rs:270-281)
+                rgb = sensor_rgb(sc, wl, s, 1.0f);
+            }
+        }
+        st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+    }
+}
+
 // ---------------------------------------------------------------- K5 film: acc[pixel] += rgb of samples s_begin .. s_begin + s_count, in order
 __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DRender R, const float4* __restrict__ rgb, float* __restrict__ acc) {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -593,12 +633,14 @@ __global__ void __launch_bounds__(256) k_film(const __grid_constant__ DRender R,
 }
 
 // Sensor::to_rgb (sensor.rs:81-88) + ReinhardToneMap (tone_map.rs:20-28) + sRGB OETF (color/src/eotf.rs:53-61)
-__global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ acc, float* __restrict__ out, uint32_t n_values, float spp) {
+// mode: 0 = the integrators (Reinhard), 1 = AlbedoRenderer (NoneToneMap sensor: no tone map), 2 = NormalRenderer (mean only, normal_renderer.rs:72-74)
+__global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ acc, float* __restrict__ out, uint32_t n_values, float spp, int mode) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_values; i += stride) {
         float c = acc[i] / spp;
+        if (mode == 2) { out[i] = c; continue; }
         c = c > 0.0f ? c : 0.0f;  // Vec3::max(ZERO)
-        c = c / (1.0f + c);
+        if (mode == 0) c = c / (1.0f + c);
         out[i] = linear_to_srgb(c);
     }
 }

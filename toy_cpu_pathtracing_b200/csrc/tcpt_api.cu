@@ -148,7 +148,7 @@ uint32_t round_up_pow2(uint32_t v) { return v <= 1 ? 1u : 1u << (32 - __builtin_
 
 int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera& cam) {
     if (!p || p->width == 0 || p->height == 0 || p->spp == 0) return fail(ctx, TCPT_ERR_INVALID, "render: width, height and spp must be positive");
-    if (p->integrator < 0 || p->integrator > 2 || p->sampler < 0 || p->sampler > 1) return fail(ctx, TCPT_ERR_INVALID, "render: unknown integrator or sampler");
+    if (p->integrator < 0 || p->integrator > TCPT_INTEGRATOR_NORMAL || p->sampler < 0 || p->sampler > 1) return fail(ctx, TCPT_ERR_INVALID, "render: unknown integrator or sampler");
     if (!ctx->dev.valid) return fail(ctx, TCPT_ERR_INVALID, "render: no scene uploaded (call tcpt_scene_build or tcpt_upload_flat_scene)");
     std::memset(&R, 0, sizeof R);
     R.width = p->width; R.height = p->height; R.spp = p->spp; R.seed = p->seed; R.max_depth = p->max_depth;
@@ -265,6 +265,12 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         ctx->stats.kernel_launches++;
     }
     const int g128 = grid_for(ctx, n_slots, 128);
+    if (R.integrator >= TCPT_INTEGRATOR_ALBEDO) {  // AOV renderers: one camera ray per sample, no bounces
+        if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
+        else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
+        k_aov<<<g128, 128, 0, stream>>>(sc, R, st);
+        ctx->stats.kernel_launches += 2;
+    } else {
     // option "fused_launches": bit 0 = k_trace_fused (shadow rays of the previous bounce + this bounce's extension rays in one
     // launch), bit 1 = k_shade_all (all shading buckets in one launch); 0 = one launch per queue and per bucket
     const bool fuse_trace = (ctx->opt.fused_launches & 1) != 0;
@@ -325,6 +331,7 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
             else k_trace_shadow<false><<<g128, 128, 0, stream>>>(sc, R, st);
             ctx->stats.kernel_launches++;
         }
+    }
     }
     if (dev_acc) {
         StageTimer t(ctx, STAGE_FILM, stream);
@@ -670,7 +677,7 @@ int tcpt_finalize_device(tcpt_ctx* ctx, const void* dev_acc, uint32_t width, uin
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     const uint32_t n = width * height * 3;
-    k_finalize<<<grid_for(ctx, n, 256), 256, 0, s>>>((const float*)dev_acc, (float*)dev_srgb, n, (float)spp);
+    k_finalize<<<grid_for(ctx, n, 256), 256, 0, s>>>((const float*)dev_acc, (float*)dev_srgb, n, (float)spp, 0);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     return TCPT_OK;
@@ -694,7 +701,8 @@ int tcpt_render(tcpt_ctx* ctx, const tcpt_render_params* params, float* out_acc,
     if (rc) return rc;
     if (out_acc && (rc = copy_out(ctx, 0, out_acc, ctx->film_acc, n * sizeof(float))) != TCPT_OK) return rc;
     if (out_srgb) {
-        k_finalize<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->film_acc, ctx->film_srgb, (uint32_t)n, (float)params->spp);
+        k_finalize<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->film_acc, ctx->film_srgb, (uint32_t)n, (float)params->spp,
+                                                                    params->integrator == TCPT_INTEGRATOR_NORMAL ? 2 : params->integrator == TCPT_INTEGRATOR_ALBEDO ? 1 : 0);
         CU(cudaGetLastError());
         if ((rc = copy_out(ctx, 1, out_srgb, ctx->film_srgb, n * sizeof(float))) != TCPT_OK) return rc;
     }

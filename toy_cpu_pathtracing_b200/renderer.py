@@ -94,7 +94,21 @@ class SrgbRendererMis(_SrgbRenderer):  # renderer/src/renderer/mis_renderer.rs:2
     integrator = "mis"
 
 
-RENDERERS = {"pt": SrgbRendererPt, "nee": SrgbRendererNee, "mis": SrgbRendererMis}
+class AlbedoRenderer(_SrgbRenderer):   # renderer/src/renderer/albedo_renderer.rs (AOV: albedo under D65 at the first hit, no tone map)
+    integrator = "albedo"
+
+    def __init__(self, args: RendererArgs, **_):
+        super().__init__(args, exposure=1.0, max_depth=0)
+
+
+class NormalRenderer(_SrgbRenderer):   # renderer/src/renderer/normal_renderer.rs (AOV: shading normal * 0.5 + 0.5 at the first hit)
+    integrator = "normal"
+
+    def __init__(self, args: RendererArgs, **_):
+        super().__init__(args, exposure=1.0, max_depth=0)
+
+
+RENDERERS = {"pt": SrgbRendererPt, "nee": SrgbRendererNee, "mis": SrgbRendererMis, "albedo": AlbedoRenderer, "normal": NormalRenderer}
 
 
 class RendererImage:                  # renderer/src/renderer.rs:101-149
