@@ -112,7 +112,8 @@ const char* tcpt_last_error(const tcpt_ctx* ctx);
  * "binned_builder" (fast non-reference BVH for synthetic soups), "sobol_prefix" (1: Z-Sobol pixel-digit table, default; 0: recompute
  * every digit per sampler call), "sobol_prefix_mb" (memory cap of that table, default 8192),
  * "fused_launches" (bit 0: shadow rays of one bounce and extension rays of the next in one launch, bit 1: all shading buckets in one
- * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
+ * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "light_shortcut" (1: a scene whose
+ * only light has strictly positive power skips the per-vertex light-power table, its selection probability being exactly 1), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
  * buffers on first use and keeps them registered while the same pointers are passed; 0: releases them — set 0 before freeing) */
 int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
 /* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65 and the metal / glass presets:

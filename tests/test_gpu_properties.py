@@ -66,6 +66,23 @@ def test_fused_launches_do_not_change_the_film(bundle_factory, scene_id, integra
     assert sa["kernel_launches"] < plain.stats["kernel_launches"] / 2
 
 
+@pytest.mark.parametrize("scene_id", [19, 3, 2])   # one environment light / one emissive mesh / one point light
+def test_single_light_shortcut_is_bit_transparent(bundle_factory, scene_id):
+    """With one light of strictly positive power its selection probability is w / w = 1 for every wavelength set; skipping the
+    per-vertex power table must not change a bit."""
+    b = bundle_factory(scene_id, 200, 150)
+    ctx = b.scene.ctx
+    a = b.image("mis", 16).render("sobol").accumulators.copy()
+    try:
+        ctx.set_option("light_shortcut", 0)
+        b.scene.build(b.camera)                      # the flag is decided when the scene is uploaded
+        c = b.image("mis", 16).render("sobol").accumulators.copy()
+    finally:
+        ctx.set_option("light_shortcut", 1)
+        b.scene.build(b.camera)
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
 def test_row_shards_sum_bitwise_to_the_full_frame(bundle_factory):
     """Tile (row-interleaved) sharding: each pixel is rendered entirely by one shard; the others hold exact zeros."""
     b = bundle_factory(10, 200, 150)

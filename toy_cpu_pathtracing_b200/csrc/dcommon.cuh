@@ -108,6 +108,7 @@ struct DScene {
     const DTexture* textures;
     const float* area_list; const float* area_table;
     int32_t light_list[TCPT_MAX_LIGHTS]; uint32_t n_lights;
+    uint32_t one_light_always_on;   // one light, power finite and > 0 at every wavelength: it is chosen with probability exactly 1 (see tcpt_upload_flat_scene)
     const DEnv* envs; uint32_t n_envs;
     const float4* cmf;              // 470 x {x_bar, y_bar, z_bar, d65}  (spectrum/src/presets.rs tables, densely resampled)
     const float* z_nodes; const float* rgb2spec;

@@ -242,7 +242,14 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     // LightSamplerFactory::create is re-run by the reference at every use (light_sampler.rs:190-220); its result only depends
     // on the wavelengths, so one evaluation per vertex serves the BSDF-side MIS weight and the NEE draw
     LightTable lt; bool lt_ready = false;
-    auto lights = [&]() -> const LightTable& { if (!lt_ready) { light_table(sc, wl, lt); lt_ready = true; } return lt; };
+    auto lights = [&]() -> const LightTable& {
+        if (!lt_ready) {
+            if (sc.one_light_always_on) { lt.w[0] = 1.0f; lt.sum = 1.0f; }  // w / w = 1 / 1: every probability derived from the table is exactly 1
+            else light_table(sc, wl, lt);
+            lt_ready = true;
+        }
+        return lt;
+    };
 
     if constexpr (BucketInfo<B>::terminal) {
         // calculate_bsdf_contribution of a NON-emissive hit: the reference still adds throughput * next_emissive(= 0) [* w], and with an

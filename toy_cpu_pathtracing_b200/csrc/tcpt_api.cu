@@ -24,7 +24,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, fused_launches = 3, fused_shade_from = 3; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -489,6 +489,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "sobol_prefix") ctx->opt.sobol_prefix = value;
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
+    else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
     else if (n == "sobol_prefix_mb") ctx->opt.sobol_prefix_mb = value;
     else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
     else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
@@ -595,6 +596,39 @@ int tcpt_scene_add_delta_light(tcpt_ctx* ctx, int kind, float intensity, const t
     return r;
 }
 
+// A scene with ONE light whose power phi(lambda).average() is finite and strictly positive for every wavelength set: the light
+// sampler then returns that light with probability w / w = 1 whatever the wavelengths (light_sampler.rs:26-44, 190-220), so the
+// device skips evaluating phi at every vertex (DScene::one_light_always_on).  Checked on the 1 nm grid of the dense tables.
+static bool spectrum_strictly_positive(const tcpt_flat_spectrum& sp, const HostTables& T) {
+    for (int i = 0; i < 470; ++i) {
+        const float lambda = 360.0f + (float)i;
+        float v;
+        if (sp.kind == 0) v = sp.c[0];
+        else if (sp.kind == 3) v = T.d65[i];
+        else if (sp.kind == 5) { if ((size_t)sp.texture * 470 + i >= T.presets.size()) return false; v = T.presets[(size_t)sp.texture * 470 + i]; }
+        else if (sp.kind == 1 || sp.kind == 2) {
+            const float t = (lambda - 360.0f) / (830.0f - 360.0f);
+            const float sg = 1.0f / (1.0f + std::exp(-(t * t * sp.c[0] + t * sp.c[1] + sp.c[2])));
+            v = sp.kind == 1 ? sg : sp.scale * sg * T.d65[i];
+        } else return false;  // textures: not decided here
+        if (!(v > 1e-20f) || !(v < 1e20f)) return false;
+    }
+    return true;
+}
+static bool one_light_always_on(const tcpt_flat_scene* s, const HostTables& T) {
+    if (s->n_lights != 1) return false;
+    const tcpt_flat_primitive& P = s->primitives[s->light_list[0]];
+    auto ok = [](float x) { return x > 1e-20f && x < 1e20f; };
+    if (P.kind == 1) {
+        const tcpt_flat_material& m = s->materials[P.material];
+        return !m.intensity.is_texture && ok(m.intensity.value) && ok(P.area_sum) && spectrum_strictly_positive(m.color, T);
+    }
+    if (P.kind == 2) { const tcpt_flat_env& e = s->envs[P.env]; return ok(e.intensity) && spectrum_strictly_positive(e.integrated, T); }
+    if (P.kind == 3) return ok(P.light_intensity) && spectrum_strictly_positive(P.light_spectrum, T);
+    if (P.kind == 5) return ok(P.light_intensity) && ok(P.dir_area) && spectrum_strictly_positive(P.light_spectrum, T);
+    return false;  // spot lights: the cone factor can vanish
+}
+
 int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     if (!ctx || !s) return TCPT_ERR_INVALID;
     if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
@@ -628,6 +662,7 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     UP(upload(ctx, db, s->area_table, s->n_area, &v.area_table));
     for (uint32_t i = 0; i < s->n_lights; ++i) v.light_list[i] = s->light_list[i];
     v.n_lights = s->n_lights;
+    v.one_light_always_on = (ctx->opt.light_shortcut && one_light_always_on(s, ctx->host.tables)) ? 1u : 0u;
     const float* envf; UP(upload(ctx, db, s->env_floats, s->n_env_floats, &envf));
     const uint32_t* envg; UP(upload(ctx, db, s->env_guides, s->n_env_guides, &envg));
     std::vector<DEnv> de(s->n_envs);
