@@ -32,14 +32,16 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = max((os.path.join(tmp, f) for f in os.listdir(tmp)), key=os.path.getsize)
 sass = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-m = re.match(r"(?:void )?(?:tcpt::)?(\w+)(?:<\(?(?:int|bool)?\)?(\w+)>)?", kname)
-fn, targ = m.group(1), m.group(2)
+m = re.match(r"(?:void )?(?:tcpt::)?(\w+)(?:<([^>]*)>)?", kname)
+fn = m.group(1)
+targs = [re.sub(r"\((?:int|bool)\)", "", a).strip() for a in m.group(2).split(",")] if m.group(2) else []
+targ_pat = "".join(r"L[ib]" + a + "E" for a in targs)   # <5, 1> -> ILi5ELb1E in the mangled name
 sec, lines_info, chain = None, {}, []
 want = None
 for ln in sass:
     if ln.startswith(".text."):
         sec = ln.strip().rstrip(":")
-        ok = fn in sec and (targ is None or re.search(r"IL[ib]" + targ + "E", sec))
+        ok = fn in sec and (not targs or re.search("I" + targ_pat + "E", sec))
         want = sec if ok else None
         chain = []
         continue

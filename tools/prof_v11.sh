@@ -2,7 +2,7 @@
 B="python bench.py --steps 1 --warmup 0 --spp-per-step 1 --no-cpu-baseline"
 $B > gpurun_out/plain_v11.json 2> gpurun_out/plain_v11.err || exit 1
 if [ "$1" = shade ]; then
-  ncu --set full --clock-control none --import-source on -k regex:k_shade -c 16 -o gpurun_out/prof_shade_v11 -f $B > gpurun_out/ncu_s11.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_shade -c 16 -o gpurun_out/prof_shade_v12 -f $B > gpurun_out/ncu_s12.log 2>&1
 else
   ncu --set full --clock-control none --import-source on -k regex:k_trace_fused -c 2 -o gpurun_out/prof_trace_v11 -f $B > gpurun_out/ncu_t11.log 2>&1
 fi
