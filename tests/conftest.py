@@ -42,7 +42,9 @@ class SceneBundle:
         self.width, self.height = width, height
         self.scene = tp.Scene(device=0, require_gpu=require_gpu)
         self.camera = tp.Camera(45.0, width, height)
-        if scene_id == "soup":
+        if callable(scene_id):            # a test's own scene: loader(scene, camera, **kw)
+            scene_id(self.scene, self.camera, **kw)
+        elif scene_id == "soup":
             scenes.load_soup(self.scene, self.camera, **kw)
         else:
             scenes.load_scene(scene_id, self.scene, self.camera, **kw)

@@ -1,0 +1,213 @@
+"""The integrators against closed-form radiometry instead of against another restatement.
+
+The Rust reference cannot be run here, so oracle-vs-GPU parity alone would leave errors common to both undetected.  These scenes have
+answers that follow from the rendering equation itself; every stage of the path has to be right for them to come out: sampler ->
+wavelengths -> camera (camera.rs:51-81) -> traversal -> BSDF sample / evaluate / pdf -> light sampling and its pdfs (scene.rs:107-231,
+emissive_triangle_mesh.rs:166-353, environment_light.rs:218-350) -> NEE / MIS weights (common.rs:82-241) -> Sensor::add_sample (sensor.rs:41-88).
+
+  * furnace: a CONVEX Lambert body of albedo rho under a uniform environment of radiance L.  No point of a convex body sees another,
+    so the radiance leaving it is exactly rho * L for every integrator; pixels that miss see L.
+  * white furnace: a non-absorbing thin dielectric (R + T = 1, dielectric.rs thin-surface series) is invisible in a uniform environment.
+  * form factor: a Lambert floor under a parallel square lamp.  L_o(x) = rho / pi * L_e * Int_A cos(t) cos(t') / r^2 dA, evaluated by
+    float64 quadrature at every pixel centre; a plane cannot light itself and the lamp has no BSDF, so this is the whole answer.
+
+The CPU tests run the oracle, the GPU tests run libtcpt through the C ABI on the same scenes: both are pinned to the same numbers.
+"""
+import numpy as np
+import pytest
+
+from toy_cpu_pathtracing_b200 import assets
+from toy_cpu_pathtracing_b200.scene import (ColorSrgbLinear, ConstantSpectrum, CreatePrimitiveDesc, EmissiveMaterial, FloatParameter, GlassMaterial, GlassType,
+                                            LambertMaterial, NormalParameter, PlasticMaterial, RgbAlbedoSpectrum, SpectrumParameter, Transform, presets)
+
+GP = CreatePrimitiveDesc.GeometryPrimitive
+W, H = 96, 72
+
+
+# ------------------------------------------------------------------ scenes
+def _unit(v):
+    v = np.asarray(v, dtype=np.float32)
+    return v / np.float32(np.sqrt(np.float32((v * v).sum())))
+
+
+def furnace(scene, camera, material="lambert", rgb=(0.5, 0.5, 0.5), env=1.0):
+    mat = {"lambert": lambda: LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(*rgb))), NormalParameter.none()),
+           "thin_plastic": lambda: PlasticMaterial.new(1.5, SpectrumParameter.Constant(ConstantSpectrum(1.0)), NormalParameter.none(), True, FloatParameter.constant(0.0)),
+           "thin_glass": lambda: GlassMaterial.new(GlassType.Bk7, NormalParameter.none(), True, FloatParameter.constant(0.0))}[material]()
+    scene.create_primitive(GP(scene.load_obj(assets.box((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), rot_y_deg=25.0)), mat, Transform.identity()))
+    sky = np.full((64, 128, 3), env, dtype=np.float32)   # NEE draws pixel-CENTRE directions only (environment_light.rs:332-339): a fine grid keeps that quadrature error small
+    scene.create_primitive(CreatePrimitiveDesc.EnvironmentLightPrimitive(1.0, sky, Transform.identity()))
+    camera.set_look_to((1.2, 1.4, 2.6), _unit((-1.2, -1.4, -2.6)), (0.0, 1.0, 0.0))
+
+
+LAMP_Y, LAMP_HALF, FLOOR_HALF, FLOOR_RHO = 1.5, 0.5, 3.0, 0.6
+
+
+def lamp_over_floor(scene, camera):
+    f = FLOOR_HALF
+    floor = assets.quad((-f, 0, f), (f, 0, f), (f, 0, -f), (-f, 0, -f), (0, 1, 0))
+    scene.create_primitive(GP(scene.load_obj(floor), LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(FLOOR_RHO, FLOOR_RHO, FLOOR_RHO))),
+                                                                          NormalParameter.none()), Transform.identity()))
+    a = LAMP_HALF
+    lamp = assets.quad((-a, LAMP_Y, -a), (a, LAMP_Y, -a), (a, LAMP_Y, a), (-a, LAMP_Y, a), (0, -1, 0))
+    scene.create_primitive(GP(scene.load_obj(lamp), EmissiveMaterial.new(SpectrumParameter.constant(presets.cie_illum_d6500()), FloatParameter.constant(10.0)), Transform.identity()))
+    camera.set_look_to((0.0, 1.2, 4.5), _unit((0.0, -0.45, -1.0)), (0.0, 1.0, 0.0))
+
+
+# ------------------------------------------------------------------ helpers
+def env_radiance(e):
+    """Linear-sRGB radiance of a grey environment texel (e, e, e).  The reference reads the f32 texel as a GAMMA-ENCODED ColorSrgb and
+    RgbIlluminantSpectrum halves it before the table lookup (environment_light.rs:312-315, rgb_illuminant_spectrum.rs:27-33): the
+    spectrum is scale * sigmoid * D65 = 2e * eotf^-1(0.5) * D65(lambda), and D65 is normalised to Y = 1 -> 0.42808 e."""
+    return 2.0 * e * (((0.5 + 0.055) / 1.055) ** 2.4)
+
+
+def pixel_centre_rays(camera, width, height):
+    """Camera::generate_ray at the pixel centres (camera.rs:51-81, box-filter mean), float64."""
+    f = camera.direction.astype(np.float64); f /= np.linalg.norm(f)
+    s = np.cross(f, camera.up.astype(np.float64)); s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    scale = np.tan(np.deg2rad(camera.fov) / 2.0)
+    x, y = np.meshgrid(np.arange(width) + 0.5, np.arange(height) + 0.5)
+    dx = (2.0 * x / width - 1.0) * (width / height) * scale
+    dy = (1.0 - 2.0 * y / height) * scale
+    d = dx[..., None] * s + dy[..., None] * u + f
+    return d / np.linalg.norm(d, axis=-1, keepdims=True)
+
+
+def eroded(mask, r=1):
+    """Pixels whose (2r+1)^2 neighbourhood is entirely inside `mask` (pixel footprints that straddle a silhouette are left out)."""
+    m = mask.copy()
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            sh = np.roll(np.roll(mask, dy, 0), dx, 1)
+            m &= sh
+    m[:r] = m[-r:] = False; m[:, :r] = m[:, -r:] = False
+    return m
+
+
+def form_factor(points, n=400):
+    """1/pi * Int_lamp cos cos' / r^2 dA for floor points (x, 0, z): midpoint rule on an n x n grid of the lamp, float64."""
+    g = (np.arange(n) + 0.5) / n * 2 * LAMP_HALF - LAMP_HALF
+    lx, lz = np.meshgrid(g, g)
+    dA = (2 * LAMP_HALF / n) ** 2
+    out = np.empty(len(points))
+    for i, (x, z) in enumerate(points):
+        r2 = (lx - x) ** 2 + LAMP_Y ** 2 + (lz - z) ** 2
+        out[i] = (LAMP_Y * LAMP_Y / (r2 * r2)).sum() * dA / np.pi      # cos = cos' = LAMP_Y / r
+    return out
+
+
+class Backend:
+    """mean linear-sRGB film (Sensor accumulators / spp) and the first-hit mask from either implementation"""
+
+    def __init__(self, bundle, gpu):
+        self.b, self.gpu = bundle, gpu
+
+    def film(self, integrator, spp, sampler="sobol", max_depth=16):
+        b = self.b
+        if self.gpu:
+            return b.image(integrator, spp, max_depth=max_depth).render(sampler).accumulators / np.float32(spp)
+        acc, _, _ = b.oracle.render(b.oparams(integrator, sampler, spp, max_depth=max_depth))
+        return acc / np.float32(spp)
+
+    def hit_mask(self):
+        """pixels whose centre ray hits primitive 0 first"""
+        b = self.b
+        d = pixel_centre_rays(b.camera, b.width, b.height).reshape(-1, 3).astype(np.float32)
+        rays = np.concatenate([np.zeros_like(d), d, np.full((len(d), 1), np.finfo(np.float32).max, np.float32)], 1)
+        hits = b.scene.trace(rays) if self.gpu else b.oracle.trace(rays)[0]
+        return (hits[:, 0] == 0).reshape(b.height, b.width), (hits[:, 0] < 0).reshape(b.height, b.width)
+
+
+def backend(bundle_factory, loader, gpu, **kw):
+    return Backend(bundle_factory(loader, W, H, require_gpu=gpu, **kw), gpu)
+
+
+CPU_GPU = [pytest.param(False, id="oracle"), pytest.param(True, id="gpu", marks=pytest.mark.gpu)]
+
+
+# ------------------------------------------------------------------ tests
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("integrator", ["pt", "nee", "mis"])
+def test_convex_lambert_body_in_a_uniform_environment(bundle_factory, gpu, integrator):
+    rho = 0.5
+    be = backend(bundle_factory, furnace, gpu)
+    img = be.film(integrator, 64)
+    body, sky = be.hit_mask()
+    body, sky = eroded(body), eroded(sky)
+    assert body.sum() > 500 and sky.sum() > 1500
+    # sky: L x D65 with D65 normalised to Y = 1 -> grey.  body: rho * L.  (per-pixel spectral noise averages out)
+    L = env_radiance(1.0)
+    assert np.allclose(img[sky].mean(0), [L] * 3, rtol=0.01), img[sky].mean(0)
+    assert np.allclose(img[body].mean(0), [rho * L] * 3, rtol=0.01), img[body].mean(0)
+    # and it is flat: no face, edge or corner of the body is brighter than another (8x8 tiles inside the body)
+    lum = img @ np.array([0.2126, 0.7152, 0.0722], dtype=np.float32)
+    assert abs(np.median(lum[body]) / (rho * L) - 1) < 0.02 and np.quantile(np.abs(lum[body] / (rho * L) - 1), 0.99) < 0.25
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+def test_coloured_body_and_dim_environment(bundle_factory, gpu):
+    """rho(lambda) * L(lambda) integrated against the observer must come back as the product of the two colours' RGB up to the
+    smoothness of the three-coefficient spectra (tests/test_rgb2spec.py bounds that round trip at about 1e-2)."""
+    rgb, env = (0.7, 0.4, 0.2), 0.5
+    be = backend(bundle_factory, furnace, gpu, rgb=rgb, env=env)
+    img = be.film("mis", 64)
+    body, sky = be.hit_mask()
+    L = env_radiance(env)
+    assert np.allclose(img[eroded(sky)].mean(0), [L] * 3, rtol=0.01)
+    assert np.allclose(img[eroded(body)].mean(0) / L, np.array(rgb), atol=0.015), img[eroded(body)].mean(0) / L
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("material", ["thin_plastic", "thin_glass"])
+def test_white_furnace_thin_dielectrics_are_invisible(bundle_factory, gpu, material):
+    """PT: every path leaves after a handful of specular events, each with expected weight R + T = 1 (the thin-surface series of
+    dielectric.rs:398-412 only shapes the selection probabilities; Russian roulette is unbiased) -> the body shows the environment.
+
+    The same scene exposes two properties of the REFERENCE that are reproduced, not fixed (parity is the contract):
+      * NeeStrategy::calculate_bsdf_infinite_light_contribution is empty (nee_renderer.rs:150-163) and NEE is skipped at specular
+        vertices: a specular path that escapes to the environment contributes nothing -> the body is exactly black under `nee`;
+      * MisStrategy applies balance_heuristic(bsdf_pdf, light_pdf) to the escaped ray even when the sample was specular
+        (mis_renderer.rs:181-231 has no is_specular branch, unlike :160-163 for area lights), with nothing on the NEE side to
+        compensate -> the body is darker than the environment under `mis` (weight pr / (pr + 1/(4 pi)) per escaping path)."""
+    be = backend(bundle_factory, furnace, gpu, material=material)
+    body, _ = be.hit_mask()
+    body = eroded(body)
+    L = env_radiance(1.0)
+    pt = be.film("pt", 64)[body].mean(0) / L
+    assert np.allclose(pt, [1.0, 1.0, 1.0], atol=0.012), pt
+    nee = be.film("nee", 16)[body]
+    assert np.all(nee == 0.0)
+    mis = be.film("mis", 64)[body].mean(0) / L
+    assert np.all(mis < 0.97) and np.all(mis > 0.75), mis
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("integrator,sampler", [("pt", "sobol"), ("nee", "sobol"), ("mis", "sobol"), ("mis", "random")])
+def test_floor_under_a_square_lamp_matches_the_form_factor(bundle_factory, gpu, integrator, sampler):
+    be = backend(bundle_factory, lamp_over_floor, gpu)
+    b = be.b
+    spp = 1024 if integrator == "pt" else 128
+    img = be.film(integrator, spp, sampler)
+    # floor points under the pixel centres; keep pixels well inside the floor whose view of it is not blocked by the lamp
+    d = pixel_centre_rays(b.camera, W, H)
+    o = b.camera.position.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = -o[1] / d[..., 1]
+        p = o + t[..., None] * d
+        tl = (LAMP_Y - o[1]) / d[..., 1]
+        pl = o + tl[..., None] * d
+    on_floor = (d[..., 1] < 0) & (np.abs(p[..., 0]) < FLOOR_HALF - 0.1) & (np.abs(p[..., 2]) < FLOOR_HALF - 0.1)
+    behind_lamp = (tl > 0) & (tl < t) & (np.abs(pl[..., 0]) < LAMP_HALF + 0.05) & (np.abs(pl[..., 2]) < LAMP_HALF + 0.05)
+    sel = eroded(on_floor & ~behind_lamp)
+    assert sel.sum() > 1500
+    expect = FLOOR_RHO * 10.0 * form_factor(p[sel][:, [0, 2]])        # L_e = 10 x D65 = linear sRGB (10, 10, 10)
+    got = img[sel]
+    # (i) total flux over the window, (ii) the brightest tenth (under the lamp), (iii) the profile pixel by pixel in luminance
+    assert np.allclose(got.mean(0), [expect.mean()] * 3, rtol=0.01), (got.mean(0), expect.mean())
+    bright = expect > np.quantile(expect, 0.9)
+    assert np.allclose(got[bright].mean(0), [expect[bright].mean()] * 3, rtol=0.015), (got[bright].mean(0), expect[bright].mean())
+    lum = got @ np.array([0.2126, 0.7152, 0.0722])
+    rel = np.abs(lum - expect) / expect
+    assert np.median(rel) < (0.08 if integrator == "pt" else 0.04), np.median(rel)
