@@ -402,6 +402,11 @@ struct Scene {
             luv.x = a.x * b0 + b.x * b1 + cc.x * b2;
             luv.y = a.y * b0 + b.y * b1 + cc.y * b2;
         }
+        // EmissiveSingleTriangle::sample_radiance hands the two RANDOM NUMBERS on as the sample point's uv, not the interpolated
+        // vertex uvs (emissive_single_triangle.rs:190-252: `uv` is the sample argument) -- visible with textured emission only.
+        // Everything else of EmissiveSingleTriangle coincides with a one-triangle EmissiveTriangleMesh: area (:38-43, same bits as
+        // emissive_triangle_mesh.rs:40-48 since cross(-a,-b) = cross(a,b)), pdf 1/area (:271,304), phi (:160-167).
+        if (m.single) luv = uv;
         Vec3 wi = normalize(pos - shading_pos);
         AreaSample r;
         // UniformEdf: radiance is direction independent, so the light's tangent frame (:253-266) does not enter the value

@@ -54,6 +54,20 @@ def lamp_over_floor(scene, camera):
     camera.set_look_to((0.0, 1.2, 4.5), _unit((0.0, -0.45, -1.0)), (0.0, 1.0, 0.0))
 
 
+TRI = np.array([(-0.7, LAMP_Y, -0.5), (0.8, LAMP_Y, -0.4), (0.1, LAMP_Y, 0.9)])
+
+
+def triangle_lamp_over_floor(scene, camera):
+    """The lamp is an EmissiveSingleTriangle (primitive/impls/emissive_single_triangle.rs): SingleTrianglePrimitive + emissive material."""
+    f = FLOOR_HALF
+    floor = assets.quad((-f, 0, f), (f, 0, f), (f, 0, -f), (-f, 0, -f), (0, 1, 0))
+    scene.create_primitive(GP(scene.load_obj(floor), LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(FLOOR_RHO, FLOOR_RHO, FLOOR_RHO))),
+                                                                          NormalParameter.none()), Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.SingleTrianglePrimitive([tuple(v) for v in TRI], [(0.0, -1.0, 0.0)] * 3, [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0)],
+                           EmissiveMaterial.new(SpectrumParameter.constant(presets.cie_illum_d6500()), FloatParameter.constant(10.0)), Transform.identity()))
+    camera.set_look_to((0.0, 1.2, 4.5), _unit((0.0, -0.45, -1.0)), (0.0, 1.0, 0.0))
+
+
 # ------------------------------------------------------------------ helpers
 def env_radiance(e):
     """Linear-sRGB radiance of a grey environment texel (e, e, e).  The reference reads the f32 texel as a GAMMA-ENCODED ColorSrgb and
@@ -95,6 +109,23 @@ def form_factor(points, n=400):
     for i, (x, z) in enumerate(points):
         r2 = (lx - x) ** 2 + LAMP_Y ** 2 + (lz - z) ** 2
         out[i] = (LAMP_Y * LAMP_Y / (r2 * r2)).sum() * dA / np.pi      # cos = cos' = LAMP_Y / r
+    return out
+
+
+def triangle_form_factor(points, n=300):
+    """1/pi * Int_triangle cos cos' / r^2 dA for floor points: midpoint rule over a uniform barycentric grid of n^2 sub-triangles."""
+    a, b, c = TRI
+    area = 0.5 * np.linalg.norm(np.cross(b - a, c - a))
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    lower = (i + j) < n                      # n(n+1)/2 upright + n(n-1)/2 inverted cells, centroids in barycentric coordinates
+    upper = (i + j) < n - 1
+    u = np.concatenate([(i[lower] + 1 / 3) / n, (i[upper] + 2 / 3) / n]); v = np.concatenate([(j[lower] + 1 / 3) / n, (j[upper] + 2 / 3) / n])
+    q = a + u[:, None] * (b - a) + v[:, None] * (c - a)
+    dA = area / len(q)
+    out = np.empty(len(points))
+    for k, (x, z) in enumerate(points):
+        r2 = (q[:, 0] - x) ** 2 + LAMP_Y ** 2 + (q[:, 2] - z) ** 2
+        out[k] = (LAMP_Y * LAMP_Y / (r2 * r2)).sum() * dA / np.pi
     return out
 
 
@@ -211,3 +242,28 @@ def test_floor_under_a_square_lamp_matches_the_form_factor(bundle_factory, gpu, 
     lum = got @ np.array([0.2126, 0.7152, 0.0722])
     rel = np.abs(lum - expect) / expect
     assert np.median(rel) < (0.08 if integrator == "pt" else 0.04), np.median(rel)
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("integrator", ["pt", "nee", "mis"])
+def test_floor_under_an_emissive_single_triangle(bundle_factory, gpu, integrator):
+    be = backend(bundle_factory, triangle_lamp_over_floor, gpu)
+    b = be.b
+    spp = 1024 if integrator == "pt" else 128
+    img = be.film(integrator, spp)
+    d = pixel_centre_rays(b.camera, W, H)
+    o = b.camera.position.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = -o[1] / d[..., 1]
+        p = o + t[..., None] * d
+        tl = (LAMP_Y - o[1]) / d[..., 1]
+        pl = o + tl[..., None] * d
+    on_floor = (d[..., 1] < 0) & (np.abs(p[..., 0]) < FLOOR_HALF - 0.1) & (np.abs(p[..., 2]) < FLOOR_HALF - 0.1)
+    behind_lamp = (tl > 0) & (tl < t) & (np.abs(pl[..., 0]) < 1.0) & (np.abs(pl[..., 2]) < 1.0)   # bounding square of the triangle
+    sel = eroded(on_floor & ~behind_lamp)
+    assert sel.sum() > 1500
+    expect = FLOOR_RHO * 10.0 * triangle_form_factor(p[sel][:, [0, 2]])
+    got = img[sel]
+    assert np.allclose(got.mean(0), [expect.mean()] * 3, rtol=0.01), (got.mean(0), expect.mean())
+    bright = expect > np.quantile(expect, 0.9)
+    assert np.allclose(got[bright].mean(0), [expect[bright].mean()] * 3, rtol=0.015), (got[bright].mean(0), expect[bright].mean())

@@ -18,7 +18,7 @@ def recorded_rays(b, integrator, sampler, spp, window):
     return rays, shadow
 
 
-@pytest.mark.parametrize("scene_id,kw", [(1, {}), (2, {}), ("lights", {"directional": True}), (3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
+@pytest.mark.parametrize("scene_id,kw", [(1, {}), (2, {}), ("lights", {"directional": True}), ("tri_lamp", {}), (3, {}), (7, {}), (8, {}), (10, {}), (17, {}), (19, {})])
 def test_hit_records_bit_exact_on_path_rays(bundle_factory, scene_id, kw):
     """Every ray a MIS render issues inside a pixel window (camera, bounce and shadow rays, incl. the non-identity instance of
     scene 17 and the three instances of scene 19): closest hits and any-hits must equal the oracle's exhaustive traversal."""
@@ -84,6 +84,8 @@ CASES = [(3, {}, "pt"), (3, {}, "nee"), (3, {}, "mis"), (10, {}, "pt"), (10, {},
          # the rest of main.rs's scene switch (same features in other combinations): rough dispersive glass (11, 12), rough coloured
          # plastic (14), textured SimplePbr dragon (15), smooth coat with textured thickness (18), plain and normal-mapped Lambert (0, 5)
          (0, {}, "mis"), (5, {}, "mis"), (11, {}, "nee"), (11, {}, "mis"), (12, {}, "mis"), (14, {}, "mis"), (15, {}, "mis"), (18, {}, "mis"),
+         # EmissiveSingleTriangle (emissive_single_triangle.rs): a textured one-triangle lamp (light-sample uv = the random numbers) and a constant one
+         ("tri_lamp", {}, "pt"), ("tri_lamp", {}, "nee"), ("tri_lamp", {}, "mis"), ("tri_lamp", {"textured": False}, "mis"),
          (1, {}, "nee"), (1, {}, "mis"), (2, {}, "pt"), (2, {}, "nee"), (2, {}, "mis"), ("lights", {}, "nee"), ("lights", {}, "mis"), ("lights", {"directional": True}, "mis")]
 
 
@@ -144,12 +146,12 @@ def test_frame_matches_oracle(bundle_factory, scene_id, kw, integrator, sampler)
         assert np.quantile(d, 0.999) <= 2e-2 and d.mean() <= 1e-4
 
 
-@pytest.mark.parametrize("scene_id,integrator,sampler", [(1, "mis", "sobol"), (2, "nee", "sobol"), ("lights", "mis", "sobol"), (3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
+@pytest.mark.parametrize("scene_id,integrator,sampler", [(1, "mis", "sobol"), (2, "nee", "sobol"), ("lights", "mis", "sobol"), ("tri_lamp", "mis", "sobol"), ("tri_lamp", "nee", "random"), (3, "mis", "sobol"), (7, "mis", "sobol"), (8, "mis", "sobol"), (9, "mis", "sobol"), (10, "nee", "random"), (17, "mis", "sobol"), (19, "mis", "sobol")])
 def test_individual_paths_match_oracle(bundle_factory, scene_id, integrator, sampler):
     """Per-(pixel, sample) sensor contributions: the overwhelming majority identical to the last bits, the rest within 1e-4."""
     w, h, spp = 64, 48, 64
     b = bundle_factory(scene_id, w, h)
-    rng = np.random.default_rng(scene_id if isinstance(scene_id, int) else 1234)
+    rng = np.random.default_rng(scene_id if isinstance(scene_id, int) else 1234)   # (a seed per scene; the named extra scenes share one)
     n = 5000
     xy = np.stack([rng.integers(0, w, n), rng.integers(0, h, n)], 1).astype(np.uint32)
     si = rng.integers(0, spp, n).astype(np.uint32)

@@ -446,6 +446,9 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
                     tuv.x = (__ldg(uu + 2 * (size_t)i0) * b0 + __ldg(uu + 2 * (size_t)i1) * b1) + __ldg(uu + 2 * (size_t)i2) * b2;
                     tuv.y = (__ldg(uu + 2 * (size_t)i0 + 1) * b0 + __ldg(uu + 2 * (size_t)i1 + 1) * b1) + __ldg(uu + 2 * (size_t)i2 + 1) * b2;
                 }
+                // EmissiveSingleTriangle::sample_radiance passes the sample's random numbers on as the light point's uv
+                // (emissive_single_triangle.rs:190-252); the rest of it coincides with a one-triangle EmissiveTriangleMesh
+                if (G.single) tuv = luv;
                 const float3 dv = lpos - hit.position;
                 const float3 wi_r = normalize(dv);
                 const S4 radiance = emissive_radiance(sc, sc.materials[LP.material], tuv, wl);

@@ -113,7 +113,7 @@ def _lambert(r, g, b):
     return LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgb(r, g, b))), NormalParameter.none())
 
 
-def _cornell_rest(scene, with_box=True):
+def _cornell_rest(scene, with_box=True, with_lamp=True):
     """box, hidari, migi, yuka, oku, tenjou, light: identical in scenes 3, 10 and 17 (scene_3.rs:33-108)."""
     if with_box:
         scene.create_primitive(GP(scene.load_obj(_asset("box")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
@@ -122,7 +122,8 @@ def _cornell_rest(scene, with_box=True):
     scene.create_primitive(GP(scene.load_obj(_asset("yuka")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
     scene.create_primitive(GP(scene.load_obj(_asset("oku")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
     scene.create_primitive(GP(scene.load_obj(_asset("tenjou")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
-    scene.create_primitive(GP(scene.load_obj(_asset("light")),
+    if with_lamp:
+        scene.create_primitive(GP(scene.load_obj(_asset("light")),
                               EmissiveMaterial.new(SpectrumParameter.constant(presets.cie_illum_d6500()), FloatParameter.constant(10.0)), Transform.identity()))
 
 
@@ -224,6 +225,20 @@ def load_scene_lights(scene, camera, directional=False):
                                                                   Transform.identity().rotate_y(200.0).translate((1.5, 3.5, 2.0))))
     if directional:
         scene.create_primitive(CreatePrimitiveDesc.DirectionalLightPrimitive(0.8, ConstantSpectrum(1.0), Transform.identity().rotate_y(35.0)))
+    _camera_10(camera)
+
+
+def load_scene_tri_lamp(scene, camera, textured=True):
+    """Not a reference scene: the Cornell box lit by an EmissiveSingleTriangle instead of the lamp mesh (the reference builds that
+    primitive in no scene of its own; primitive/impls/emissive_single_triangle.rs, chosen by repository.rs:84-105 when a
+    SingleTrianglePrimitive carries an emissive material).  A textured intensity shows the one place where it differs from a
+    one-triangle EmissiveTriangleMesh: the light sample's uv is the pair of random numbers (:190-252), a hit's uv is interpolated."""
+    scene.create_primitive(GP(scene.load_obj(_asset("bunny")), _lambert(0.8, 0.8, 0.8), Transform.identity()))
+    _cornell_rest(scene, with_lamp=False)
+    intensity = FloatParameter.texture(FloatTexture.load(assets.gray_texture(256, seed=33, lo=0.3, hi=1.0), False)) if textured else FloatParameter.constant(0.7)
+    scene.create_primitive(CreatePrimitiveDesc.SingleTrianglePrimitive(
+        [(-1.2, 0.0, -1.0), (1.2, 0.0, -1.0), (0.0, 0.0, 1.3)], [(0.0, -1.0, 0.0)] * 3, [(0.0, 0.0), (1.0, 0.0), (0.5, 1.0)],
+        EmissiveMaterial.new(SpectrumParameter.constant(presets.cie_illum_d6500()), intensity), Transform.from_rotate_y(20.0).translate((0.2, 4.6, 0.1))))
     _camera_10(camera)
 
 
@@ -372,7 +387,7 @@ def load_soup(scene, camera, n_triangles: int, seed: int = 42):
 
 
 SCENES = {0: load_scene_0, 1: load_scene_1, 2: load_scene_2, 4: load_scene_4, 5: load_scene_5, 11: load_scene_11, 12: load_scene_12, 13: load_scene_13,
-          14: load_scene_14, 15: load_scene_15, 16: load_scene_16, 18: load_scene_18, "lights": load_scene_lights, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
+          14: load_scene_14, 15: load_scene_15, 16: load_scene_16, 18: load_scene_18, "lights": load_scene_lights, "tri_lamp": load_scene_tri_lamp, 3: load_scene_3, 6: load_scene_6, 7: load_scene_7, 8: load_scene_8, 9: load_scene_9, 10: load_scene_10, 17: load_scene_17, 19: load_scene_19}
 
 
 def load_scene(scene_id, scene, camera, **kw):
