@@ -1,6 +1,8 @@
 """ORACLE (test infrastructure, NOT product code): ctypes wrapper over oracle/liboracle.so, the CPU restatement of the
 reference's path-integration hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this module.  PARITY UNPINNED below the Sobol known-answer vectors (the Rust reference cannot be built here)."""
+legs may import this module.  PARITY UNPINNED against the reference's own outputs below the Sobol known-answer vectors and the BVH
+topology checks (the Rust reference cannot be built here and holds no fixtures below image level); pinned to restatement-independent
+ground truth instead by tests/test_{intersection,analytic}_ground_truth.py and tests/test_rgb2spec.py."""
 from __future__ import annotations
 
 import ctypes as C
