@@ -1,0 +1,152 @@
+//! `extern "C"` mirror of include/tcpt.h, one to one (field order and widths are the header's; every struct is `#[repr(C)]`).
+#![allow(non_camel_case_types, dead_code)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct TcptCtx {
+    _opaque: [u8; 0],
+}
+
+pub const TCPT_OK: c_int = 0;
+pub const TCPT_ERR_INVALID: c_int = -1;
+pub const TCPT_ERR_CUDA: c_int = -2;
+pub const TCPT_ERR_LIMIT: c_int = -3;
+pub const TCPT_ERR_NOMEM: c_int = -4;
+
+pub const INTEGRATOR_PT: i32 = 0;
+pub const INTEGRATOR_NEE: i32 = 1;
+pub const INTEGRATOR_MIS: i32 = 2;
+pub const INTEGRATOR_ALBEDO: i32 = 3;
+pub const INTEGRATOR_NORMAL: i32 = 4;
+pub const SAMPLER_RANDOM: i32 = 0;
+pub const SAMPLER_SOBOL: i32 = 1;
+
+pub const MAT_LAMBERT: i32 = 0;
+pub const MAT_EMISSIVE: i32 = 1;
+pub const MAT_PLASTIC: i32 = 2;
+pub const MAT_SIMPLE_PBR: i32 = 3;
+pub const MAT_CLEARCOAT_PBR: i32 = 4;
+pub const MAT_METAL: i32 = 5;
+pub const MAT_GLASS: i32 = 6;
+
+pub const SPEC_CONSTANT: i32 = 0;
+pub const SPEC_RGB_ALBEDO_SRGB: i32 = 1;
+pub const SPEC_RGB_ALBEDO_LINEAR: i32 = 2;
+pub const SPEC_D65: i32 = 3;
+pub const SPEC_TEXTURE_SRGB: i32 = 4;
+pub const SPEC_PRESET: i32 = 5;
+
+pub const LIGHT_POINT: c_int = 3;
+pub const LIGHT_SPOT: c_int = 4;
+pub const LIGHT_DIRECTIONAL: c_int = 5;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct TcptSpectrumParam {
+    pub kind: i32,
+    pub value: [f32; 3],
+    pub texture: i32, // texture index (SPEC_TEXTURE_SRGB) or TCPT_PRESET_* id (SPEC_PRESET)
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct TcptFloatParam {
+    pub kind: i32, // 0 constant, 1 gray8 FloatTexture
+    pub value: f32,
+    pub texture: i32,
+    pub gamma_corrected: i32,
+}
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct TcptNormalParam {
+    pub texture: i32, // -1 = NormalParameter::none()
+    pub flip_y: i32,
+}
+impl Default for TcptNormalParam {
+    fn default() -> Self {
+        Self { texture: -1, flip_y: 0 }
+    }
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct TcptMaterialDesc {
+    pub ty: i32,
+    pub color: TcptSpectrumParam,
+    pub intensity: TcptFloatParam,
+    pub normal: TcptNormalParam,
+    pub eta: f32,
+    pub thin_surface: i32,
+    pub roughness: TcptFloatParam,
+    pub metallic: TcptFloatParam,
+    pub ior: TcptFloatParam,
+    pub coat_ior: TcptFloatParam,
+    pub coat_roughness: TcptFloatParam,
+    pub coat_thickness: TcptFloatParam,
+    pub coat_tint: TcptSpectrumParam,
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct TcptRenderParams {
+    pub width: u32,
+    pub height: u32,
+    pub spp: u32,
+    pub seed: u32,
+    pub max_depth: u32,
+    pub integrator: i32,
+    pub sampler: i32,
+    pub exposure: f32,
+    pub fov_deg: f32,
+    pub cam_pos: [f32; 3],
+    pub cam_dir: [f32; 3],
+    pub cam_up: [f32; 3],
+    pub row_offset: u32,
+    pub row_stride: u32,
+    pub spp_begin: u32,
+    pub spp_end: u32,
+    pub max_slots: u32,
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct TcptStats {
+    pub paths: u64,
+    pub closest_rays: u64,
+    pub shadow_rays: u64,
+    pub box_tests: u64,
+    pub tri_tests: u64,
+    pub kernel_launches: u64,
+    pub render_ms: f64,
+    pub trace_closest_ms: f64,
+    pub trace_shadow_ms: f64,
+    pub shade_ms: f64,
+    pub generate_ms: f64,
+    pub film_ms: f64,
+    pub passes: u32,
+    pub max_bvh_depth: u32,
+    pub sobol_prefix_ms: f64,
+    pub sobol_prefix_bytes: u64,
+}
+
+unsafe extern "C" {
+    pub fn tcpt_create(device_id: c_int, out: *mut *mut TcptCtx) -> c_int;
+    pub fn tcpt_destroy(ctx: *mut TcptCtx);
+    pub fn tcpt_last_error(ctx: *const TcptCtx) -> *const c_char;
+    pub fn tcpt_set_option(ctx: *mut TcptCtx, name: *const c_char, value: c_int) -> c_int;
+    pub fn tcpt_set_tables(ctx: *mut TcptCtx, std_tables: *const c_void, std_len: usize, rgb2spec: *const f32, rgb2spec_floats: usize) -> c_int;
+
+    pub fn tcpt_scene_clear(ctx: *mut TcptCtx) -> c_int;
+    pub fn tcpt_scene_add_mesh(ctx: *mut TcptCtx, positions: *const f32, normals: *const f32, uvs: *const f32, n_vertices: c_int,
+                               indices: *const u32, n_triangles: c_int) -> c_int;
+    pub fn tcpt_scene_add_single_triangle(ctx: *mut TcptCtx, positions: *const f32, normals: *const f32, uvs: *const f32) -> c_int;
+    pub fn tcpt_scene_add_texture(ctx: *mut TcptCtx, data: *const u8, width: u32, height: u32, channels: u32) -> c_int;
+    pub fn tcpt_scene_add_material(ctx: *mut TcptCtx, desc: *const TcptMaterialDesc) -> c_int;
+    pub fn tcpt_scene_add_primitive(ctx: *mut TcptCtx, geometry: c_int, material: c_int, local_to_world: *const f32) -> c_int;
+    pub fn tcpt_scene_add_env_light(ctx: *mut TcptCtx, intensity: f32, rgb: *const f32, width: u32, height: u32, local_to_world: *const f32) -> c_int;
+    pub fn tcpt_scene_add_delta_light(ctx: *mut TcptCtx, kind: c_int, intensity: f32, spectrum: *const TcptSpectrumParam, angle_inner: f32,
+                                      angle_outer: f32, local_to_world: *const f32) -> c_int;
+    pub fn tcpt_scene_build(ctx: *mut TcptCtx, cam_pos: *const f32) -> c_int;
+
+    pub fn tcpt_render(ctx: *mut TcptCtx, params: *const TcptRenderParams, out_acc: *mut f32, out_srgb: *mut f32) -> c_int;
+    pub fn tcpt_render_device(ctx: *mut TcptCtx, params: *const TcptRenderParams, dev_acc: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn tcpt_finalize_device(ctx: *mut TcptCtx, dev_acc: *const c_void, width: u32, height: u32, spp: u32, dev_srgb: *mut c_void,
+                                stream: *mut c_void) -> c_int;
+    pub fn tcpt_get_stats(ctx: *const TcptCtx, out: *mut TcptStats) -> c_int;
+}

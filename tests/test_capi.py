@@ -70,3 +70,27 @@ def test_argument_errors_are_codes_not_crashes(built):
     cam = np.zeros(3, dtype=np.float32)
     lib.tcpt_scene_clear(h)
     assert lib.tcpt_scene_build(h, capi.as_ptr(cam, C.c_float)) == capi.TCPT_ERR_INVALID  # empty scene
+
+
+def test_rust_binding_source_is_in_sync_with_the_header(built):
+    """integration/rust/gpu_backend/src/ffi.rs cannot be compiled here (no Rust toolchain): at least keep its `extern "C"` block and
+    `#[repr(C)]` structs field-for-field in step with include/tcpt.h, through the ctypes structs the tests above tie to the header."""
+    from toy_cpu_pathtracing_b200 import capi
+    text = (ROOT / "integration" / "rust" / "gpu_backend" / "src" / "ffi.rs").read_text()
+    fns = set(re.findall(r"pub fn (tcpt_[a-z0-9_]+)\(", text))
+    declared = set(declared_symbols())
+    assert fns <= declared, fns - declared
+    product = {s for s in declared if not re.search(r"trace|sampler_stream|path_samples|get_bvh|build_bvh|rgb_to_coeffs|mesh_tangents|upload_flat", s)}
+    assert product <= fns, f"ffi.rs misses {product - fns}"        # everything but the test / introspection probes is bound
+
+    def rust_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, text, flags=re.S).group(1)
+        return [(f, t) for f, t in re.findall(r"pub (\w+): ([^,]+),", body)]
+
+    ctype_of = {"i32": C.c_int32, "u32": C.c_uint32, "f32": C.c_float, "u64": C.c_uint64, "f64": C.c_double, "[f32; 3]": C.c_float * 3,
+                "TcptSpectrumParam": capi.SpectrumParam, "TcptFloatParam": capi.FloatParam, "TcptNormalParam": capi.NormalParam}
+    for rust, py in (("TcptSpectrumParam", capi.SpectrumParam), ("TcptFloatParam", capi.FloatParam), ("TcptNormalParam", capi.NormalParam),
+                     ("TcptMaterialDesc", capi.MaterialDesc), ("TcptRenderParams", capi.RenderParams), ("TcptStats", capi.Stats)):
+        rf = rust_fields(rust)
+        assert [f if f != "ty" else "type" for f, _ in rf] == [f for f, _ in py._fields_], rust
+        assert [ctype_of[t.strip()] for _, t in rf] == [t for _, t in py._fields_], rust
