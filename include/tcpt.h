@@ -110,7 +110,8 @@ void tcpt_destroy(tcpt_ctx* ctx);
 const char* tcpt_last_error(const tcpt_ctx* ctx);
 /* options: "count_tests" (box/triangle test counters), "stage_timing" (per-kernel event timing), "blocks_per_sm",
  * "binned_builder" (fast non-reference BVH for synthetic soups), "sobol_prefix" (1: Z-Sobol pixel-digit table, default; 0: recompute
- * every digit per sampler call), "sobol_prefix_mb" (memory cap of that table, default 8192),
+ * every digit per sampler call), "sobol_prefix_mb" (memory cap of that table, default 8192), "sobol_pass" (1: per-pass table of the permuted
+ * sample digits shared by all samples of a pixel inside one pass, default; 0: off), "sobol_pass_dims" (dimensions it covers, default 11),
  * "fused_launches" (bit 0: shadow rays of one bounce and extension rays of the next in one launch, bit 1: all shading buckets in one
  * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "light_shortcut" (1: a scene whose
  * only light has strictly positive power skips the per-vertex light-power table, its selection probability being exactly 1), "pin_host_buffers" (1: tcpt_render page-locks the caller's output

@@ -83,6 +83,37 @@ def test_single_light_shortcut_is_bit_transparent(bundle_factory, scene_id):
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
 
 
+@pytest.mark.parametrize("scene_id,spp", [(3, 64), (19, 256), (10, 16)])
+def test_sobol_pass_table_is_bit_transparent(bundle_factory, scene_id, spp):
+    """The per-pass table caches the permuted sample digits that all samples of a pixel share inside one pass (and the permutation row
+    of the first digit that varies): on, off, covering only a few dimensions, with passes of 4 / 16 / odd numbers of samples, with
+    row shards and with sample ranges that are not aligned to their length -- always the same film to the bit."""
+    b = bundle_factory(scene_id, 200, 150)
+    ctx = b.scene.ctx
+    n = 200 * 150
+    try:
+        ctx.set_option("sobol_pass", 0)
+        ref = b.image("mis", spp).render("sobol").accumulators.copy()
+        ctx.set_option("sobol_pass", 1)
+        for dims, slots in ((40, 0), (40, 16 * n), (5, 4 * n), (200, 7 * n), (40, 16 * 7777)):
+            ctx.set_option("sobol_pass_dims", dims)
+            img = b.image("mis", spp).render("sobol", max_slots=slots)
+            assert np.array_equal(ref.view(np.uint32), img.accumulators.view(np.uint32)), (dims, slots)
+        ctx.set_option("sobol_pass_dims", 11)
+        parts = [b.image("mis", spp).render("sobol", row_offset=r, row_stride=3).accumulators.copy() for r in range(3)]
+        assert np.array_equal(sum(parts).view(np.uint32), ref.view(np.uint32))
+        # sample ranges [3, 3 + 9) and [12, spp): the digits that vary inside a range depend on where it starts
+        ctx.set_option("sobol_pass", 0)
+        a = [b.image("mis", spp).render("sobol", spp_begin=s0, spp_end=s1).accumulators.copy() for s0, s1 in ((3, 12), (12, spp))]
+        ctx.set_option("sobol_pass", 1)
+        c = [b.image("mis", spp).render("sobol", spp_begin=s0, spp_end=s1).accumulators.copy() for s0, s1 in ((3, 12), (12, spp))]
+        for x, y in zip(a, c):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    finally:
+        ctx.set_option("sobol_pass", 1)
+        ctx.set_option("sobol_pass_dims", 11)
+
+
 def test_row_shards_sum_bitwise_to_the_full_frame(bundle_factory):
     """Tile (row-interleaved) sharding: each pixel is rendered entirely by one shard; the others hold exact zeros."""
     b = bundle_factory(10, 200, 150)

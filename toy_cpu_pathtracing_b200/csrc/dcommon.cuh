@@ -128,6 +128,9 @@ struct DRender {
     uint32_t n_pix, pix_begin, s_begin, s_count, row_offset, row_stride;
     // ZSobol pixel-prefix table (see DSampler::sample_index): prefix[dim * prefix_stride + y * width + x], dims < prefix_dims
     const uint32_t* sobol_prefix; uint32_t prefix_dims, prefix_stride;
+    // ZSobol pass table (see DSampler::sample_index): rows prefix_dims .. prefix_dims + pass_dims of the same allocation, rebuilt for
+    // every pass by k_sobol_pass.  pass_info = pass_dims | n_varying_digits << 8 (0 = no pass table)
+    uint32_t pass_info;
 };
 
 // Wavefront buffers.  Path state is a structure of arrays of 16-byte records indexed by path slot; ray queues, hit records
@@ -155,7 +158,7 @@ __constant__ const uint32_t* c_sobol_dim1_bytes;
 
 struct DSampler {
     uint32_t kind, seed, log2_spp, nb4, morton, dim, key;
-    const uint32_t* prefix; uint32_t prefix_dims, prefix_stride;  // this pixel's column of DRender::sobol_prefix
+    const uint32_t* prefix; uint32_t prefix_dims, prefix_stride;  // this pixel's column of DRender::sobol_prefix; prefix_dims = dims | DRender::pass_info << 16
 
     __device__ __forceinline__ static uint32_t part1by1(uint32_t x) {  // left_shift2 of a 32-bit value truncated to u32 (z_sobol_sampler.rs:54-65)
         x &= 0x0000ffffu;
@@ -241,7 +244,24 @@ struct DSampler {
         const bool pow2 = (log2_spp & 1u) == 1u;
         const int last_digit = pow2 ? 1 : 0;
         uint64_t sidx;
-        if (dim < prefix_dims) {
+        const uint32_t n_prefix = prefix_dims & 0xffffu, n_pass = (prefix_dims >> 16) & 0xffu;
+        if (dim < n_pass) {
+            // Pass table: the samples of one pass differ in their lowest `iv` base-4 digits only, so the permuted digits above those
+            // (they are keyed by the digits above them: pixel and pass, not sample) and the permutation of digit iv - 1 (keyed by
+            // everything above it) are the same for every sample of the pixel in this pass: computed once per (dimension, pixel,
+            // pass) by k_sobol_pass instead of once per path vertex.  Left here: one table-driven digit and iv - 1 hashed ones.
+            const uint32_t iv = prefix_dims >> 24;
+            const uint32_t hi = __ldg(prefix + (size_t)dim * prefix_stride);
+            const uint32_t e = __ldg(prefix + (size_t)(n_prefix + dim) * prefix_stride);
+            sidx = ((uint64_t)hi << log2_spp) | ((uint64_t)(e & 0xffffu) << (2u * iv));
+            if (iv >= 1u) {
+                const uint32_t sh = 2u * iv - 2u;
+                sidx |= (uint64_t)perm_digit(e >> 16, (morton >> sh) & 3u) << sh;
+                if (iv >= 2u) sidx |= permuted_digits((int)iv - 2, 0);
+            }
+            return sidx;   // (the pass table is only built for even log2_spp: no trailing binary digit)
+        }
+        if (dim < n_prefix) {
             const uint32_t hi = __ldg(prefix + (size_t)dim * prefix_stride);
             sidx = ((uint64_t)hi << log2_spp) | permuted_digits(first_pixel_digit() - 1, last_digit);
         } else {
@@ -257,6 +277,15 @@ struct DSampler {
     }
     // table entry of (this pixel, this dimension): the permuted pixel digits, shifted down by log2_spp
     __device__ __forceinline__ uint32_t pixel_prefix() const { return (uint32_t)(permuted_digits((int)nb4 - 1, first_pixel_digit()) >> log2_spp); }
+    // pass-table entry of (this pixel, this dimension) for a pass whose samples differ in their lowest iv digits (log2_spp even):
+    // bits 0-15 = permuted sample digits iv .. log2_spp/2 - 1, shifted down; bits 16-20 = permutation row of digit iv - 1
+    __device__ __forceinline__ uint32_t pass_entry(uint32_t iv) const {
+        const int top = (int)(log2_spp >> 1) - 1;
+        uint32_t c = 0u, p = 0u;
+        if (top >= (int)iv) c = (uint32_t)(permuted_digits(top, (int)iv) >> (2u * iv));
+        if (iv >= 1u) p = perm_index(mix_bits(((uint64_t)morton >> (2u * iv)) ^ (0x55555555ull * (uint64_t)dim)));
+        return c | (p << 16);
+    }
     __device__ __forceinline__ static uint32_t sobol_dim1(uint64_t a) {
         const uint32_t* __restrict__ tab = c_sobol_dim1_bytes;
         uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);

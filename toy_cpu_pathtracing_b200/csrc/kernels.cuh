@@ -41,7 +41,7 @@ __device__ __forceinline__ DSampler make_sampler(const DRender& R, uint32_t px, 
     DSampler s;
     s.kind = (uint32_t)R.sampler; s.seed = R.seed; s.log2_spp = R.log2_spp; s.nb4 = R.n_base4_digits;
     s.prefix = R.sobol_prefix ? R.sobol_prefix + ((size_t)py * R.width + px) : nullptr;
-    s.prefix_dims = R.sobol_prefix ? R.prefix_dims : 0u; s.prefix_stride = R.prefix_stride;
+    s.prefix_dims = R.sobol_prefix ? (R.prefix_dims | (R.pass_info << 16)) : 0u; s.prefix_stride = R.prefix_stride;
     s.start(px, py, si);
     return s;
 }
@@ -57,6 +57,22 @@ __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ tab
         s.start(px, py, 0u);
         s.dim = dim;
         table[i] = s.pixel_prefix();
+    }
+}
+
+// builds the pass rows of DRender::sobol_prefix for the pixels and the sample block of ONE pass (see DSampler::sample_index):
+// row prefix_dims + dim, column = the pixel's frame index
+__global__ void __launch_bounds__(256) k_sobol_pass(uint32_t* __restrict__ table, const __grid_constant__ DRender R, uint32_t dims, uint32_t iv) {
+    const size_t total = (size_t)R.n_pix * dims;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t dim = (uint32_t)(i / R.n_pix), p_local = (uint32_t)(i - (size_t)dim * R.n_pix);
+        const uint32_t k = R.pix_begin + p_local, row = k / R.width;
+        const uint32_t px = k - row * R.width, py = R.row_offset + row * R.row_stride;
+        DSampler s;
+        s.kind = TCPT_SAMPLER_SOBOL; s.seed = 0; s.log2_spp = R.log2_spp; s.nb4 = R.n_base4_digits; s.prefix = nullptr; s.prefix_dims = 0; s.prefix_stride = 0;
+        s.start(px, py, R.s_begin);
+        s.dim = dim;
+        table[(size_t)(R.prefix_dims + dim) * R.prefix_stride + (size_t)py * R.width + px] = s.pass_entry(iv);
     }
 }
 

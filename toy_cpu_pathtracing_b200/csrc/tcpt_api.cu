@@ -24,7 +24,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -56,7 +56,7 @@ struct tcpt_ctx {
     float* film_acc = nullptr; float* film_srgb = nullptr; size_t film_cap = 0;
     HostPin pins[2];
     // ZSobol pixel-prefix table (DSampler::sample_index), cached per (width, height, log2_spp); grows when more dimensions are asked for
-    uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0; size_t prefix_cap = 0;
+    uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0, pass_rows = 0; size_t prefix_cap = 0;
     double prefix_build_ms = 0.0;
     uint64_t default_slots = 0;  // path-slot budget of a pass when the caller gives none (see render_into)
 };
@@ -178,16 +178,22 @@ int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera&
 // kept until the resolution or spp changes.  Dimensions covered: what a max_depth path can draw (3 + 8 per bounce), capped by
 // option "sobol_prefix_mb"; deeper dimensions are computed in full by the sampler.
 int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
-    R.sobol_prefix = nullptr; R.prefix_dims = 0; R.prefix_stride = 0;
+    R.sobol_prefix = nullptr; R.prefix_dims = 0; R.prefix_stride = 0; R.pass_info = 0;
     if (R.sampler != TCPT_SAMPLER_SOBOL || !ctx->opt.sobol_prefix) return TCPT_OK;
     const size_t n_pix = (size_t)R.width * R.height;
     size_t dims = 3 + 8 * ((size_t)R.max_depth + 1);
     const size_t cap_dims = ((size_t)ctx->opt.sobol_prefix_mb << 20) / (n_pix * 4);
     if (dims > cap_dims) dims = cap_dims;
     if (dims == 0) return TCPT_OK;
-    const bool same = ctx->d_prefix && ctx->prefix_w == R.width && ctx->prefix_h == R.height && ctx->prefix_log2spp == R.log2_spp;
+    // rows behind the prefix rows for the per-pass table (k_sobol_pass).  Default 11 = the camera's 3 dimensions + the 8 of bounce 0, where
+    // every path still is (measured on the 4K frame, 16 samples per pass: 0.115 ms per row to build; 0 / 3 / 11 / 16 / 40 rows give
+    // 105.5 / 103.8 / 102.7 / 103.4 / 106.6 ms per step: deeper bounces hold too few vertices to pay for their rows)
+    size_t pass_rows = ctx->opt.sobol_pass ? (size_t)(ctx->opt.sobol_pass_dims < 0 ? 0 : ctx->opt.sobol_pass_dims) : 0;
+    if (pass_rows > dims) pass_rows = dims;
+    if (pass_rows > 255) pass_rows = 255;
+    const bool same = ctx->d_prefix && ctx->prefix_w == R.width && ctx->prefix_h == R.height && ctx->prefix_log2spp == R.log2_spp && ctx->pass_rows == pass_rows;
     if (!same || ctx->prefix_dims < dims) {
-        const size_t need = n_pix * dims;
+        const size_t need = n_pix * (dims + pass_rows);
         if (need > ctx->prefix_cap) {
             if (ctx->d_prefix) { cudaStreamSynchronize(stream); cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr; ctx->prefix_cap = 0; }
             if (cudaMalloc((void**)&ctx->d_prefix, need * 4) != cudaSuccess) { cudaGetLastError(); ctx->prefix_dims = 0; return TCPT_OK; }  // no table: full loop
@@ -203,7 +209,7 @@ int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
         float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); ctx->prefix_build_ms = ms; ctx->stats.sobol_prefix_ms = ms;
         cudaEventDestroy(a); cudaEventDestroy(b);
         CU(cudaGetLastError());
-        ctx->prefix_w = R.width; ctx->prefix_h = R.height; ctx->prefix_log2spp = R.log2_spp; ctx->prefix_dims = (uint32_t)dims;
+        ctx->prefix_w = R.width; ctx->prefix_h = R.height; ctx->prefix_log2spp = R.log2_spp; ctx->prefix_dims = (uint32_t)dims; ctx->pass_rows = (uint32_t)pass_rows;
     }
     R.sobol_prefix = ctx->d_prefix; R.prefix_dims = ctx->prefix_dims; R.prefix_stride = (uint32_t)n_pix;
     ctx->stats.sobol_prefix_bytes = (uint64_t)n_pix * ctx->prefix_dims * 4;
@@ -227,6 +233,23 @@ struct StageTimer {
     cudaStream_t stream = nullptr;
 };
 enum { STAGE_GENERATE = 0, STAGE_CLOSEST = 1, STAGE_SHADE = 2, STAGE_SHADOW = 3, STAGE_FILM = 4 };
+
+// ZSobol pass table: the rows behind the prefix rows, rebuilt on `stream` at the start of every pass for the pass's pixels and sample
+// block (see DSampler::sample_index).  Worth it when a pass holds several samples per pixel (each entry costs about what it saves one
+// sampler call); needs the prefix table, an even log2(spp) (no trailing binary digit) and sample digits that fit 16 bits.
+void build_sobol_pass(tcpt_ctx* ctx, DRender& Rp, cudaStream_t stream) {
+    Rp.pass_info = 0;
+    if (!Rp.sobol_prefix || ctx->pass_rows == 0 || (Rp.log2_spp & 1u) || Rp.log2_spp > 16u || Rp.s_count < 4u) return;
+    uint32_t v = 0;   // number of low sample-index bits that differ inside [s_begin, s_begin + s_count)
+    while ((Rp.s_begin >> v) != ((Rp.s_begin + Rp.s_count - 1u) >> v)) ++v;
+    const uint32_t iv = (v + 1u) >> 1;
+    const size_t total = (size_t)Rp.n_pix * ctx->pass_rows;
+    const int grid = (int)((total + 255) / 256 < (size_t)ctx->sm_count * 64 ? (total + 255) / 256 : (size_t)ctx->sm_count * 64);
+    StageTimer t(ctx, STAGE_GENERATE, stream);
+    k_sobol_pass<<<grid, 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv);
+    ctx->stats.kernel_launches++;
+    Rp.pass_info = ctx->pass_rows | (iv << 8);
+}
 
 void collect_stage_times(tcpt_ctx* ctx) {  // call after the stream has been synchronised
     double* acc[5] = {&ctx->stats.generate_ms, &ctx->stats.trace_closest_ms, &ctx->stats.shade_ms, &ctx->stats.trace_shadow_ms, &ctx->stats.film_ms};
@@ -398,6 +421,7 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
         for (uint32_t sb = s0; sb < s1; sb += sc_per_pass) {
             DRender Rp = R;
             Rp.n_pix = n_pix; Rp.pix_begin = (uint32_t)pb; Rp.s_begin = sb; Rp.s_count = (s1 - sb) < sc_per_pass ? (s1 - sb) : sc_per_pass;
+            build_sobol_pass(ctx, Rp, stream);
             rc = run_pass(ctx, Rp, cam, none, n_pix * Rp.s_count, dev_acc, stream);
             if (rc) return rc;
         }
@@ -491,6 +515,8 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
     else if (n == "sobol_prefix_mb") ctx->opt.sobol_prefix_mb = value;
+    else if (n == "sobol_pass") ctx->opt.sobol_pass = value;
+    else if (n == "sobol_pass_dims") ctx->opt.sobol_pass_dims = value;
     else if (n == "blocks_per_sm") ctx->opt.blocks_per_sm = value > 0 ? value : 8;
     else if (n == "binned_builder") ctx->host.use_binned_builder = value != 0;
     else if (n == "pin_host_buffers") { ctx->opt.pin_host_buffers = value != 0; if (!value) unpin_all(ctx); }
