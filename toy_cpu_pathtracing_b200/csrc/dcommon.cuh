@@ -360,12 +360,15 @@ __device__ __forceinline__ float4 cmf_at(const DScene& sc, float lambda) {  // D
 }
 
 // RgbToSpectrumTable::get (rgb_sigmoid_polynomial.rs:87-155), sRGB-gamma typed colour
-__device__ __noinline__ void rgb_to_coeffs(const DScene& sc, float3 rgb_in, float cs[3]) {
+// (returns by value: an out-array lived in local memory and cost a store -> load -> store -> load chain through L1 before the first
+// wavelength could be evaluated)
+__device__ __noinline__ float3 rgb_to_coeffs(const DScene& sc, float3 rgb_in) {
+    float cs[3];
     float rgb[3] = {srgb_to_linear(rgb_in.x), srgb_to_linear(rgb_in.y), srgb_to_linear(rgb_in.z)};
 #pragma unroll
     for (int k = 0; k < 3; ++k) rgb[k] = rgb[k] > 0.0f ? rgb[k] : 0.0f;
     // (component > 1 panics in the reference; u8/255 texels and half-scaled illuminant colours never exceed 1)
-    if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) { cs[0] = 0.0f; cs[1] = 0.0f; cs[2] = logf(rgb[0] / (1.0f - rgb[0])); return; }
+    if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) return f3(0.0f, 0.0f, logf(rgb[0] / (1.0f - rgb[0])));
     int m = 0;
     { float best = rgb[0]; if (rgb[1] > best) { best = rgb[1]; m = 1; } if (rgb[2] > best) m = 2; }
     const float z = m == 0 ? rgb[0] : (m == 1 ? rgb[1] : rgb[2]);
@@ -392,6 +395,7 @@ __device__ __noinline__ void rgb_to_coeffs(const DScene& sc, float3 rgb_in, floa
         const float a = a0 + (a1 - a0) * dy, b = b0 + (b1 - b0) * dy;
         cs[i] = a + (b - a) * dz;
     }
+    return f3(cs[0], cs[1], cs[2]);
 }
 
 // a resolved Spectrum (SpectrumTrait object) on the device
@@ -409,12 +413,17 @@ __device__ __forceinline__ float spectrum_value(const DScene& sc, const DSpectru
     if (s.kind == 1) return sg;
     return s.scale * sg * cmf_at(sc, lambda).w;
 }
-__device__ __noinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl) {
+// (the spectrum travels by value and the wavelengths are read once up front: by reference both sat in the caller's stack frame and every
+// one of the 4 x 3 coefficient reads was a separate local-memory load)
+__device__ __noinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum s, const DWavelengths& wl) {
+    const float l0 = wl.lambda[0], l1 = wl.lambda[1], l2 = wl.lambda[2], l3 = wl.lambda[3];
+    const bool terminated = wl.terminated;
     S4 r = s4(0.0f);
-    r.v[0] = spectrum_value(sc, s, wl.lambda[0]);
-    if (wl.terminated) return r;
-#pragma unroll
-    for (int i = 1; i < 4; ++i) r.v[i] = spectrum_value(sc, s, wl.lambda[i]);
+    r.v[0] = spectrum_value(sc, s, l0);
+    if (terminated) return r;
+    r.v[1] = spectrum_value(sc, s, l1);
+    r.v[2] = spectrum_value(sc, s, l2);
+    r.v[3] = spectrum_value(sc, s, l3);
     return r;
 }
 __device__ __forceinline__ DSpectrum spectrum_from_flat(const tcpt_flat_spectrum& p) {
@@ -425,7 +434,8 @@ __device__ __forceinline__ DSpectrum illuminant_from_rgb(const DScene& sc, float
     DSpectrum s; s.kind = 2; s.table = 0;
     const float mx = rmax(rgb.x, rmax(rgb.y, rgb.z));
     s.scale = 2.0f * mx;
-    rgb_to_coeffs(sc, rgb / s.scale, s.c);
+    const float3 c = rgb_to_coeffs(sc, rgb / s.scale);
+    s.c[0] = c.x; s.c[1] = c.y; s.c[2] = c.z;
     return s;
 }
 
@@ -463,7 +473,12 @@ __device__ __noinline__ float tex_gray(const DTexture& t, float2 uv) {
 
 __device__ __forceinline__ DSpectrum param_spectrum(const DScene& sc, const tcpt_flat_spectrum& p, float2 uv) {
     DSpectrum s;
-    if (p.kind == 4) { s.kind = 1; s.scale = 1.0f; s.table = 0; rgb_to_coeffs(sc, tex_rgb(sc.textures[p.texture], uv), s.c); return s; }  // rgb_texture.rs:48-66
+    if (p.kind == 4) {  // rgb_texture.rs:48-66
+        s.kind = 1; s.scale = 1.0f; s.table = 0;
+        const float3 c = rgb_to_coeffs(sc, tex_rgb(sc.textures[p.texture], uv));
+        s.c[0] = c.x; s.c[1] = c.y; s.c[2] = c.z;
+        return s;
+    }
     return spectrum_from_flat(p);
 }
 __device__ __forceinline__ float param_float(const DScene& sc, const tcpt_flat_float& p, float2 uv) {
