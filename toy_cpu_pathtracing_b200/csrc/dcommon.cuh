@@ -156,9 +156,18 @@ __constant__ uint32_t c_sobol_dim1[52];  // SOBOL_MATRICES_32[52..104) (dimensio
 // (7 x 256 words in global memory, L1 resident); XOR is associative, so 5-7 gathers replace up to 52 bit-serial steps
 __constant__ const uint32_t* c_sobol_dim1_bytes;
 
+// Z-Sobol / counter-hash sampler.  The per-path part is four registers (Morton index, dimension counter, counter-hash key, pixel
+// index); everything the frame fixes (seed, log2 spp, digit count, tables) is read from the kernel parameters at the call.  The heavy
+// work sits in two __noinline__ functions that take every input BY VALUE: as member functions they took `this`, which forced the
+// sampler into the caller's stack frame and turned every field read of every call into a local-memory load.
+struct SobolFrame {  // the frame-constant inputs of a Sobol call, packed for the by-value call
+    const uint32_t* prefix;   // DRender::sobol_prefix (nullptr: no tables)
+    uint32_t prefix_stride, tables;  // tables = prefix_dims | pass_dims << 16 | n_varying_digits << 24
+    uint32_t cfg;             // log2_spp | n_base4_digits << 8
+    uint32_t seed;
+};
 struct DSampler {
-    uint32_t kind, seed, log2_spp, nb4, morton, dim, key;
-    const uint32_t* prefix; uint32_t prefix_dims, prefix_stride;  // this pixel's column of DRender::sobol_prefix; prefix_dims = dims | DRender::pass_info << 16
+    uint32_t morton, dim, key, pix;
 
     __device__ __forceinline__ static uint32_t part1by1(uint32_t x) {  // left_shift2 of a 32-bit value truncated to u32 (z_sobol_sampler.rs:54-65)
         x &= 0x0000ffffu;
@@ -195,11 +204,22 @@ struct DSampler {
     __device__ __forceinline__ static float unit_float(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
     __device__ __forceinline__ static float to_unit(uint32_t v) { return fminf((float)v * 2.3283064365386963e-10f, 0.99999994f); }
 
-    __device__ __forceinline__ void start(uint32_t px, uint32_t py, uint32_t sample_index) {
-        dim = 0;
+    __device__ __forceinline__ static uint32_t morton_of(uint32_t px, uint32_t py, uint32_t sample_index, uint32_t log2_spp) {
         // encode_morton2 computes in u64 then truncates to u32: only the low 16 bits of x and y survive (z_sobol_sampler.rs:54-66)
-        morton = (((part1by1(py) << 1) | part1by1(px)) << log2_spp) | sample_index;
-        key = (px * 0x9e3779b9u) ^ (py * 0x85ebca6bu) ^ (sample_index * 0xc2b2ae35u) ^ seed;
+        return (((part1by1(py) << 1) | part1by1(px)) << log2_spp) | sample_index;
+    }
+    __device__ __forceinline__ void start(const DRender& R, uint32_t px, uint32_t py, uint32_t sample_index) {
+        dim = 0;
+        morton = morton_of(px, py, sample_index, R.log2_spp);
+        key = (px * 0x9e3779b9u) ^ (py * 0x85ebca6bu) ^ (sample_index * 0xc2b2ae35u) ^ R.seed;
+        pix = py * R.width + px;
+    }
+    __device__ __forceinline__ static SobolFrame frame_of(const DRender& R) {
+        SobolFrame f;
+        f.prefix = R.sobol_prefix; f.prefix_stride = R.prefix_stride;
+        f.tables = R.sobol_prefix ? (R.prefix_dims | (R.pass_info << 16)) : 0u;
+        f.cfg = R.log2_spp | (R.n_base4_digits << 8); f.seed = R.seed;
+        return f;
     }
 
     __device__ __forceinline__ static uint32_t perm_digit(uint32_t p, uint32_t digit) {
@@ -225,7 +245,7 @@ struct DSampler {
     // or the path -- and are read from a table built once per (resolution, spp) by k_sobol_prefix; only the log2_spp / 2 sample
     // digits are permuted here (6 of 18 digits for a 4096-spp 4K frame: HBM capacity traded for ~700 integer instructions per
     // sampler call).  Dimensions past the table fall back to the full loop.
-    __device__ __forceinline__ uint64_t permuted_digits(int i_from, int i_to) const {  // digits i_from down to i_to
+    __device__ __forceinline__ static uint64_t permuted_digits(uint32_t morton, uint32_t dim, uint32_t log2_spp, int i_from, int i_to) {  // digits i_from down to i_to
         uint64_t sidx = 0;
         const int odd = (int)(log2_spp & 1u);
         const uint64_t dk = 0x55555555ull * (uint64_t)dim;
@@ -239,33 +259,35 @@ struct DSampler {
         }
         return sidx;
     }
-    __device__ __forceinline__ int first_pixel_digit() const { return (int)((log2_spp + 1u) >> 1); }
-    __device__ __noinline__ uint64_t sample_index() const {
+    __device__ __forceinline__ static int first_pixel_digit(uint32_t log2_spp) { return (int)((log2_spp + 1u) >> 1); }
+    __device__ __forceinline__ static uint64_t sample_index(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
+        const uint32_t log2_spp = f.cfg & 0xffu, nb4 = f.cfg >> 8;
         const bool pow2 = (log2_spp & 1u) == 1u;
         const int last_digit = pow2 ? 1 : 0;
         uint64_t sidx;
-        const uint32_t n_prefix = prefix_dims & 0xffffu, n_pass = (prefix_dims >> 16) & 0xffu;
+        const uint32_t n_prefix = f.tables & 0xffffu, n_pass = (f.tables >> 16) & 0xffu;
+        const uint32_t* __restrict__ col = f.prefix + pix;   // this pixel's column of the tables
         if (dim < n_pass) {
             // Pass table: the samples of one pass differ in their lowest `iv` base-4 digits only, so the permuted digits above those
             // (they are keyed by the digits above them: pixel and pass, not sample) and the permutation of digit iv - 1 (keyed by
             // everything above it) are the same for every sample of the pixel in this pass: computed once per (dimension, pixel,
             // pass) by k_sobol_pass instead of once per path vertex.  Left here: one table-driven digit and iv - 1 hashed ones.
-            const uint32_t iv = prefix_dims >> 24;
-            const uint32_t hi = __ldg(prefix + (size_t)dim * prefix_stride);
-            const uint32_t e = __ldg(prefix + (size_t)(n_prefix + dim) * prefix_stride);
+            const uint32_t iv = f.tables >> 24;
+            const uint32_t hi = __ldg(col + (size_t)dim * f.prefix_stride);
+            const uint32_t e = __ldg(col + (size_t)(n_prefix + dim) * f.prefix_stride);
             sidx = ((uint64_t)hi << log2_spp) | ((uint64_t)(e & 0xffffu) << (2u * iv));
             if (iv >= 1u) {
                 const uint32_t sh = 2u * iv - 2u;
                 sidx |= (uint64_t)perm_digit(e >> 16, (morton >> sh) & 3u) << sh;
-                if (iv >= 2u) sidx |= permuted_digits((int)iv - 2, 0);
+                if (iv >= 2u) sidx |= permuted_digits(morton, dim, log2_spp, (int)iv - 2, 0);
             }
             return sidx;   // (the pass table is only built for even log2_spp: no trailing binary digit)
         }
         if (dim < n_prefix) {
-            const uint32_t hi = __ldg(prefix + (size_t)dim * prefix_stride);
-            sidx = ((uint64_t)hi << log2_spp) | permuted_digits(first_pixel_digit() - 1, last_digit);
+            const uint32_t hi = __ldg(col + (size_t)dim * f.prefix_stride);
+            sidx = ((uint64_t)hi << log2_spp) | permuted_digits(morton, dim, log2_spp, first_pixel_digit(log2_spp) - 1, last_digit);
         } else {
-            sidx = permuted_digits((int)nb4 - 1, last_digit);
+            sidx = permuted_digits(morton, dim, log2_spp, (int)nb4 - 1, last_digit);
         }
         if (pow2) {
             // quirk: the reference ANDs with the loop variable, which is last_digit - 1 = 0 after the loop; pbrt-v4 has `& 1`
@@ -275,14 +297,16 @@ struct DSampler {
         }
         return sidx;
     }
-    // table entry of (this pixel, this dimension): the permuted pixel digits, shifted down by log2_spp
-    __device__ __forceinline__ uint32_t pixel_prefix() const { return (uint32_t)(permuted_digits((int)nb4 - 1, first_pixel_digit()) >> log2_spp); }
-    // pass-table entry of (this pixel, this dimension) for a pass whose samples differ in their lowest iv digits (log2_spp even):
+    // table entry of (pixel, dimension): the permuted pixel digits, shifted down by log2_spp
+    __device__ __forceinline__ static uint32_t pixel_prefix(uint32_t morton, uint32_t dim, uint32_t log2_spp, uint32_t nb4) {
+        return (uint32_t)(permuted_digits(morton, dim, log2_spp, (int)nb4 - 1, first_pixel_digit(log2_spp)) >> log2_spp);
+    }
+    // pass-table entry of (pixel, dimension) for a pass whose samples differ in their lowest iv digits (log2_spp even):
     // bits 0-15 = permuted sample digits iv .. log2_spp/2 - 1, shifted down; bits 16-20 = permutation row of digit iv - 1
-    __device__ __forceinline__ uint32_t pass_entry(uint32_t iv) const {
+    __device__ __forceinline__ static uint32_t pass_entry(uint32_t morton, uint32_t dim, uint32_t log2_spp, uint32_t iv) {
         const int top = (int)(log2_spp >> 1) - 1;
         uint32_t c = 0u, p = 0u;
-        if (top >= (int)iv) c = (uint32_t)(permuted_digits(top, (int)iv) >> (2u * iv));
+        if (top >= (int)iv) c = (uint32_t)(permuted_digits(morton, dim, log2_spp, top, (int)iv) >> (2u * iv));
         if (iv >= 1u) p = perm_index(mix_bits(((uint64_t)morton >> (2u * iv)) ^ (0x55555555ull * (uint64_t)dim)));
         return c | (p << 16);
     }
@@ -293,28 +317,39 @@ struct DSampler {
         if (hi != 0u) v ^= __ldg(tab + 1024 + (hi & 255u)) ^ __ldg(tab + 1280 + ((hi >> 8) & 255u)) ^ __ldg(tab + 1536 + ((hi >> 16) & 15u));  // matrix has 52 rows
         return v;
     }
+    // ZSobolSampler::get_1d / get_2d (z_sobol_sampler.rs:198-235); `dim` = the dimension counter BEFORE the call (the reference
+    // increments it before hashing, :204-207,215-218)
+    __device__ __noinline__ static float sobol_1d(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
+        const uint64_t a = sample_index(morton, dim, pix, f);
+        const uint64_t h = hash(dim + 1u, f.seed);
+        return to_unit(owen(__brev((uint32_t)a), (uint32_t)h));  // Sobol matrix 0 = identity on reversed bits; rows >= 32 are zero
+    }
+    __device__ __noinline__ static float2 sobol_2d(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
+        const uint64_t a = sample_index(morton, dim, pix, f);
+        const uint64_t h = hash(dim + 2u, f.seed);
+        float2 r;
+        r.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+        r.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+        return r;
+    }
     // get_1d whose value the caller provably does not use: both samplers are pure functions of the dimension counter, so
     // advancing the counter is all that has to happen (the reference computes and discards the value)
     __device__ __forceinline__ void skip_1d() { dim += 1; }
-    __device__ __noinline__ float get_1d() {
-        if (kind == TCPT_SAMPLER_SOBOL) {
-            const uint64_t a = sample_index();
+    __device__ __forceinline__ float get_1d(const DRender& R) {
+        if (R.sampler == TCPT_SAMPLER_SOBOL) {
+            const float r = sobol_1d(morton, dim, pix, frame_of(R));
             dim += 1;
-            const uint64_t h = hash(dim, seed);
-            return to_unit(owen(__brev((uint32_t)a), (uint32_t)h));  // Sobol matrix 0 = identity on reversed bits; rows >= 32 are zero
+            return r;
         }
         return unit_float(pcg_hash2(key, dim++));
     }
-    __device__ __noinline__ float2 get_2d() {
-        float2 r;
-        if (kind == TCPT_SAMPLER_SOBOL) {
-            const uint64_t a = sample_index();
+    __device__ __forceinline__ float2 get_2d(const DRender& R) {
+        if (R.sampler == TCPT_SAMPLER_SOBOL) {
+            const float2 r = sobol_2d(morton, dim, pix, frame_of(R));
             dim += 2;
-            const uint64_t h = hash(dim, seed);
-            r.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
-            r.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
             return r;
         }
+        float2 r;
         r.x = unit_float(pcg_hash2(key, dim++));
         r.y = unit_float(pcg_hash2(key, dim++));
         return r;

@@ -39,10 +39,7 @@ __device__ __forceinline__ void path_coords(const DRender& R, const PathList& L,
 
 __device__ __forceinline__ DSampler make_sampler(const DRender& R, uint32_t px, uint32_t py, uint32_t si) {
     DSampler s;
-    s.kind = (uint32_t)R.sampler; s.seed = R.seed; s.log2_spp = R.log2_spp; s.nb4 = R.n_base4_digits;
-    s.prefix = R.sobol_prefix ? R.sobol_prefix + ((size_t)py * R.width + px) : nullptr;
-    s.prefix_dims = R.sobol_prefix ? (R.prefix_dims | (R.pass_info << 16)) : 0u; s.prefix_stride = R.prefix_stride;
-    s.start(px, py, si);
+    s.start(R, px, py, si);
     return s;
 }
 
@@ -52,11 +49,7 @@ __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ tab
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t dim = (uint32_t)(i / n_pix), k = (uint32_t)(i - (size_t)dim * n_pix);
         const uint32_t py = k / width, px = k - py * width;
-        DSampler s;
-        s.kind = TCPT_SAMPLER_SOBOL; s.seed = 0; s.log2_spp = log2_spp; s.nb4 = nb4; s.prefix = nullptr; s.prefix_dims = 0; s.prefix_stride = 0;
-        s.start(px, py, 0u);
-        s.dim = dim;
-        table[i] = s.pixel_prefix();
+        table[i] = DSampler::pixel_prefix(DSampler::morton_of(px, py, 0u, log2_spp), dim, log2_spp, nb4);
     }
 }
 
@@ -68,11 +61,8 @@ __global__ void __launch_bounds__(256) k_sobol_pass(uint32_t* __restrict__ table
         const uint32_t dim = (uint32_t)(i / R.n_pix), p_local = (uint32_t)(i - (size_t)dim * R.n_pix);
         const uint32_t k = R.pix_begin + p_local, row = k / R.width;
         const uint32_t px = k - row * R.width, py = R.row_offset + row * R.row_stride;
-        DSampler s;
-        s.kind = TCPT_SAMPLER_SOBOL; s.seed = 0; s.log2_spp = R.log2_spp; s.nb4 = R.n_base4_digits; s.prefix = nullptr; s.prefix_dims = 0; s.prefix_stride = 0;
-        s.start(px, py, R.s_begin);
-        s.dim = dim;
-        table[(size_t)(R.prefix_dims + dim) * R.prefix_stride + (size_t)py * R.width + px] = s.pass_entry(iv);
+        table[(size_t)(R.prefix_dims + dim) * R.prefix_stride + (size_t)py * R.width + px] =
+            DSampler::pass_entry(DSampler::morton_of(px, py, R.s_begin, R.log2_spp), dim, R.log2_spp, iv);
     }
 }
 
@@ -87,9 +77,9 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         // NormalRenderer draws the pixel sample first and no wavelength (normal_renderer.rs:33-40); the AOV renderers do not push the ray forward
         const bool aov = R.integrator >= TCPT_INTEGRATOR_ALBEDO;
         float u = 0.0f;
-        if (R.integrator != TCPT_INTEGRATOR_NORMAL) u = smp.get_1d();
+        if (R.integrator != TCPT_INTEGRATOR_NORMAL) u = smp.get_1d(R);
         const float lambda0 = 360.0f + u * (830.0f - 360.0f);  // SampledWavelengths::new_uniform (sampled_spectrum.rs:318-336)
-        const float2 uv = smp.get_2d();
+        const float2 uv = smp.get_2d(R);
         // BoxFilter::sample + Camera::sample_ray / generate_ray (filter.rs:24-30, camera.rs:51-81)
         const float fx = uv.x * 1.0f - 1.0f * 0.5f, fy = uv.y * 1.0f - 1.0f * 0.5f;
         const float x = (float)px + fx + 0.5f, y = (float)py + fy + 0.5f;
@@ -355,8 +345,8 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
     // `uc` only selects between lobes; LambertMaterial::sample and MetalMaterial::sample never read it (lambert_material.rs:42-97, metal_material.rs:124)
     float uc = 0.0f;
-    if (MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) smp.skip_1d(); else uc = smp.get_1d();
-    const float2 uv = smp.get_2d();
+    if (MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) smp.skip_1d(); else uc = smp.get_1d(R);
+    const float2 uv = smp.get_2d(R);
     const bool was_terminated = wl.terminated;
     NmFrame nmf;
     material_frame(sc, mat, hit.uv, nmf);
@@ -378,7 +368,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
             li = t1.sum == 0.0f ? -1 : 0;
             p_light = t1.w[0] / t1.sum;
         } else {
-            const float u = smp.get_1d();
+            const float u = smp.get_1d(R);
             li = sample_light(sc, lights(), u, &p_light);
         }
         if (li >= 0) {
@@ -387,9 +377,9 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
             // `s` picks the triangle of an area light; the environment light ignores it (scene.rs:127-153)
             // (delta lights read neither: the reference draws s and uv before it looks at the kind of light, nee_renderer.rs:41-43)
             float s = 0.0f;
-            if (LP.kind == 1) s = smp.get_1d(); else smp.skip_1d();
+            if (LP.kind == 1) s = smp.get_1d(R); else smp.skip_1d();
             float2 luv = make_float2(0.0f, 0.0f);
-            if (LP.kind <= 2) luv = smp.get_2d(); else { smp.skip_1d(); smp.skip_1d(); }
+            if (LP.kind <= 2) luv = smp.get_2d(R); else { smp.skip_1d(); smp.skip_1d(); }
             float3 sh_dir; float sh_tmax; S4 pending; float sh_eps = 1e-4f;
             if (LP.kind == 3 || LP.kind == 4) {
                 // PointLight / SpotLight::calculate_intensity (point_light.rs:75-88, spot_light.rs:98-122) + evaluate_delta_point_light
@@ -513,7 +503,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     if (stage + 1 <= R.max_depth) {
         const S4 thr2 = thr * (ms.f * (1.0f / ms.pdf));
         const float p_rr = s4_max(thr2);
-        if (!(p_rr >= 1.0f)) killed = !(smp.get_1d() < p_rr);
+        if (!(p_rr >= 1.0f)) killed = !(smp.get_1d(R) < p_rr);
     }
     out.push_ext = true;
     out.eo = make_float4(o2.x, o2.y, o2.z, TCPT_FLT_MAX);
@@ -690,8 +680,8 @@ __global__ void k_sampler_stream(const __grid_constant__ DRender R, uint32_t px,
     DSampler smp = make_sampler(R, px, py, si);
     int k = 0;
     for (int i = 0; i < n; ++i) {
-        if (kinds[i] == 1) out[k++] = smp.get_1d();
-        else { const float2 v = smp.get_2d(); out[k++] = v.x; out[k++] = v.y; }
+        if (kinds[i] == 1) out[k++] = smp.get_1d(R);
+        else { const float2 v = smp.get_2d(R); out[k++] = v.x; out[k++] = v.y; }
     }
 }
 
