@@ -36,7 +36,7 @@ struct DSurface {
 __device__ __forceinline__ float3 orthogonalize(float3 n, float3 v) { const float pm = dot(n, v); return normalize(v - n * pm); }
 __device__ __forceinline__ float3 generate_tangent(float3 n) { return orthogonalize(n, fabsf(n.x) > 0.999f ? f3(0, 1, 0) : f3(1, 0, 0)); }
 
-__device__ __noinline__ void reconstruct_hit(const DScene& sc, int prim, uint32_t tri, float b0, float b1, float b2, float3 ray_d, DSurface& s) {
+__device__ __forceinline__ void reconstruct_hit(const DScene& sc, int prim, uint32_t tri, float b0, float b1, float b2, float3 ray_d, DSurface& s) {
     const tcpt_flat_primitive& P = sc.primitives[prim];
     const tcpt_flat_geometry& G = sc.geometries[P.geometry];
     const uint32_t* idx = sc.indices + 3 * ((size_t)G.index_base + tri);
@@ -904,18 +904,19 @@ __device__ __noinline__ uint32_t sample_from_cdf(const float* cdf, uint32_t n, c
 }
 
 // Scene::pdf_light_sample (scene.rs:156-181) for a BSDF-sampled hit on an emissive mesh
-__device__ __noinline__ float scene_pdf_light_sample(const DScene& sc, const LightTable& lt, float3 shading_pos, const DSurface& hit) {
-    const tcpt_flat_primitive& P = sc.primitives[hit.prim];
+// (takes the four things it reads of the hit by value: a `const DSurface&` kept the whole surface record in the caller's stack frame)
+__device__ __noinline__ float scene_pdf_light_sample(const DScene& sc, const LightTable& lt, float3 shading_pos, int hit_prim, uint32_t hit_tri, float3 hit_position, float3 hit_normal) {
+    const tcpt_flat_primitive& P = sc.primitives[hit_prim];
     if (P.kind != 1) return 0.0f;
     float probability = 0.0f;
     if (sc.n_lights != 0 && lt.sum != 0.0f && P.light_index >= 0) probability = lt.w[P.light_index] / lt.sum;
     const float* table = sc.area_table + P.area_base;
-    const float tri_prob = hit.tri == 0 ? __ldg(table) : __ldg(table + hit.tri) - __ldg(table + hit.tri - 1);
-    const float pdf_area = 1.0f / __ldg(sc.area_list + P.area_base + hit.tri) * tri_prob;  // emissive_triangle_mesh.rs:331-353
-    const float3 dv = shading_pos - hit.position;
+    const float tri_prob = hit_tri == 0 ? __ldg(table) : __ldg(table + hit_tri) - __ldg(table + hit_tri - 1);
+    const float pdf_area = 1.0f / __ldg(sc.area_list + P.area_base + hit_tri) * tri_prob;  // emissive_triangle_mesh.rs:331-353
+    const float3 dv = shading_pos - hit_position;
     const float distance = length(dv);
     const float3 wo = -normalize(dv);
-    const float pdf_dir = pdf_area * (distance * distance) / fabsf(dot(hit.normal, wo));
+    const float pdf_dir = pdf_area * (distance * distance) / fabsf(dot(hit_normal, wo));
     return probability * pdf_dir;
 }
 

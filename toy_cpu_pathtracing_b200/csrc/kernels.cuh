@@ -321,7 +321,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
             if (spec_prev) con = con + thr * next_emissive;                   // mis_renderer.rs:160-163
             else {
                 const float4 pp = st.ppos[slot];
-                const float pdf_light = scene_pdf_light_sample(sc, lights(), f3(pp.x, pp.y, pp.z), hit);
+                const float pdf_light = scene_pdf_light_sample(sc, lights(), f3(pp.x, pp.y, pp.z), hit.prim, hit.tri, hit.position, hit.normal);
                 const float a = pdf_prev, b = pdf_light;
                 const float w = (a == 0.0f && b == 0.0f) ? 0.0f : a / (a + b);
                 con = con + thr * next_emissive * w;                          // mis_renderer.rs:164-179
