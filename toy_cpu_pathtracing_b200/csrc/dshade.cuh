@@ -171,7 +171,7 @@ __device__ inline bool generalized_half_vector(float3 wo, float3 wi, float eta, 
 }
 
 // ---------------------------------------------------------------- bsdf/lambert.rs
-__device__ __noinline__ bool lambert_sample(const S4& albedo, float3 wo, float2 uv, BsdfSample* out) {
+__device__ __forceinline__ bool lambert_sample(const S4& albedo, float3 wo, float2 uv, BsdfSample* out) {
     const float wo_cos = wo.z;
     if (wo_cos == 0.0f) return false;
     const float r = sqrtf(uv.x), th = 2.0f * TCPT_PI * uv.y;
@@ -921,7 +921,10 @@ __device__ __noinline__ float scene_pdf_light_sample(const DScene& sc, const Lig
 }
 
 // ---------------------------------------------------------------- sensor (renderer/src/sensor.rs:41-78)
-__device__ __noinline__ float3 sensor_rgb(const DScene& sc, const DWavelengths& wl, const S4& s, float exposure) {
+// (by value: the wavelength record is a pure function of (lambda0, terminated) -- terminate_secondary, sampled_spectrum.rs:351-360, leaves
+// exactly what wavelengths_uniform builds for a terminated path -- and is rebuilt here instead of being read from the caller's stack)
+__device__ __noinline__ float3 sensor_rgb(const DScene& sc, float lambda0, bool terminated, const S4 s, float exposure) {
+    const DWavelengths wl = wavelengths_uniform(lambda0, terminated);
     const int count = wl.terminated ? 1 : 4;
     float x = 0.0f, y = 0.0f, z = 0.0f;
     for (int k = 0; k < count; ++k) {

@@ -150,7 +150,7 @@ __device__ __forceinline__ void commit_shadow(const DScene& sc, const DRender& R
     if (last) {
         const float4 misc = st.misc[slot];
         const DWavelengths wl = wavelengths_uniform(misc.y, (__float_as_uint(misc.w) & FLAG_LAMBDA_TERMINATED) != 0);
-        const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
+        const float3 rgb = sensor_rgb(sc, wl.lambda[0], wl.terminated, con, R.exposure);
         st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
     }
 }
@@ -242,7 +242,7 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     constexpr bool miss = BucketInfo<B>::miss;
 
     auto finish = [&]() {
-        const float3 rgb = sensor_rgb(sc, wl, con, R.exposure);
+        const float3 rgb = sensor_rgb(sc, wl.lambda[0], wl.terminated, con, R.exposure);
         st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
     };
     // LightSamplerFactory::create is re-run by the reference at every use (light_sampler.rs:190-220); its result only depends
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(128) k_aov(const __grid_constant__ DScene sc, 
                 S4 s;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) s.v[k] = a.v[k] * cmf_at(sc, wl.lambda[k]).w;  // multiply_spectrum with D65 (sampled_spectrum.rs:270-281)
-                rgb = sensor_rgb(sc, wl, s, 1.0f);
+                rgb = sensor_rgb(sc, wl.lambda[0], wl.terminated, s, 1.0f);
             }
         }
         st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
