@@ -448,19 +448,24 @@ __device__ __forceinline__ float spectrum_value(const DScene& sc, const DSpectru
     if (s.kind == 1) return sg;
     return s.scale * sg * cmf_at(sc, lambda).w;
 }
-// (the spectrum travels by value and the wavelengths are read once up front: by reference both sat in the caller's stack frame and every
-// one of the 4 x 3 coefficient reads was a separate local-memory load)
-__device__ __noinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum s, const DWavelengths& wl) {
-    const float l0 = wl.lambda[0], l1 = wl.lambda[1], l2 = wl.lambda[2], l3 = wl.lambda[3];
-    const bool terminated = wl.terminated;
+// (everything by value: by reference the spectrum and the wavelength record sat in the caller's stack frame and each of the 4 x 3
+// coefficient reads and 5 wavelength reads was a separate local-memory load.  A wavelength record is always
+// wavelengths_uniform(lambda[0], terminated) -- that is also what terminate_secondary leaves -- so two scalars carry it.)
+__device__ __noinline__ S4 spectrum_sample_v(const DScene& sc, const DSpectrum s, float lambda0, bool terminated) {
     S4 r = s4(0.0f);
-    r.v[0] = spectrum_value(sc, s, l0);
+    r.v[0] = spectrum_value(sc, s, lambda0);
     if (terminated) return r;
-    r.v[1] = spectrum_value(sc, s, l1);
-    r.v[2] = spectrum_value(sc, s, l2);
-    r.v[3] = spectrum_value(sc, s, l3);
+    const float delta = (830.0f - 360.0f) / 4.0f;
+    float l = lambda0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {   // the same arithmetic as wavelengths_uniform
+        l = l + delta;
+        if (l >= 830.0f) l = 360.0f + (l - 830.0f);
+        r.v[i] = spectrum_value(sc, s, l);
+    }
     return r;
 }
+__device__ __forceinline__ S4 spectrum_sample(const DScene& sc, const DSpectrum& s, const DWavelengths& wl) { return spectrum_sample_v(sc, s, wl.lambda[0], wl.terminated); }
 __device__ __forceinline__ DSpectrum spectrum_from_flat(const tcpt_flat_spectrum& p) {
     DSpectrum s; s.kind = p.kind; s.c[0] = p.c[0]; s.c[1] = p.c[1]; s.c[2] = p.c[2]; s.scale = p.scale; s.table = p.texture; return s;
 }

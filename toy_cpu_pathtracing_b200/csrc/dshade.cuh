@@ -497,28 +497,35 @@ __device__ __forceinline__ Schlick make_schlick(const S4& r0, float alpha) { Sch
 // ---------------------------------------------------------------- SimplePbr (simple_pbr_material.rs:274-537 == simple_pbr_clearcoat_material.rs:540-845)
 struct PbrBase {
     S4 base_color; float metallic, roughness, ior;
-    __device__ MatSample sample_metallic(float alpha, float3 wo, float2 uv, const M3& from_nm) const {
+    // sample*: `wi` comes back in the NORMAL-MAP frame; the caller rotates it into the shading frame (pbr_sample below).  Taking the
+    // matrix by reference here kept it in the caller's stack frame: 9 stores and 27+ local loads per vertex.
+    __device__ MatSample sample_metallic(float alpha, float3 wo, float2 uv) const {
         BsdfSample s;
         if (!make_schlick(base_color, alpha).sample(wo, uv, &s)) return mat_fail();
-        return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf, s.type);
+        return mat_ok(s.f, s.wi, s.pdf, s.type);
     }
-    __device__ MatSample sample_dielectric(float alpha, float3 wo, float uc, float2 uv, const M3& from_nm) const {
+    __device__ MatSample sample_dielectric(float alpha, float3 wo, float uc, float2 uv) const {
         const Schlick gs = make_schlick(s4(r0_of(ior)), alpha);
         const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
         BsdfSample s;
         if (uc < fresnel) {
             if (!gs.sample(wo, uv, &s)) return mat_fail();
-            return mat_ok(s.f, m3_vector(from_nm, s.wi), s.pdf * fresnel, s.type);
+            return mat_ok(s.f, s.wi, s.pdf * fresnel, s.type);
         }
         if (!lambert_sample(base_color, wo, uv, &s)) return mat_fail();
-        return mat_ok(s.f * (1.0f - fresnel), m3_vector(from_nm, s.wi), s.pdf * (1.0f - fresnel), s.type);
+        return mat_ok(s.f * (1.0f - fresnel), s.wi, s.pdf * (1.0f - fresnel), s.type);
     }
-    __device__ __noinline__ MatSample sample(float3 wo, float uc, float2 uv, const M3& from_nm) const {
+    __device__ __noinline__ MatSample sample_nm(float3 wo, float uc, float2 uv) const {
         const float alpha = roughness * roughness;
-        if (metallic >= 1.0f) return sample_metallic(alpha, wo, uv, from_nm);
-        if (metallic <= 0.0f) return sample_dielectric(alpha, wo, uc, uv, from_nm);
-        if (uc <= metallic) return sample_metallic(alpha, wo, uv, from_nm);
-        return sample_dielectric(alpha, wo, (uc - metallic) / (1.0f - metallic), uv, from_nm);
+        if (metallic >= 1.0f) return sample_metallic(alpha, wo, uv);
+        if (metallic <= 0.0f) return sample_dielectric(alpha, wo, uc, uv);
+        if (uc <= metallic) return sample_metallic(alpha, wo, uv);
+        return sample_dielectric(alpha, wo, (uc - metallic) / (1.0f - metallic), uv);
+    }
+    __device__ __forceinline__ MatSample sample(float3 wo, float uc, float2 uv, const M3& from_nm) const {
+        MatSample ms = sample_nm(wo, uc, uv);
+        if (ms.sampled) ms.wi = m3_vector(from_nm, ms.wi);
+        return ms;
     }
     __device__ S4 eval_dielectric(float alpha, float3 wo, float3 wi) const {
         const Schlick gs = make_schlick(s4(r0_of(ior)), alpha);
