@@ -15,6 +15,20 @@
 #pragma once
 #include "dcommon.cuh"
 
+// Three micro-variants of the walk, measured one by one on the 4K frame and left off (trace 46.1 ms per step without them):
+//   TCPT_OPT_TOS    top stack entry in a register, so a pop does not wait for local memory           46.7 ms
+//   TCPT_OPT_RL     one "current ray" record restored at BLAS exit instead of a per-visit select     46.6 ms
+//   TCPT_OPT_BALLOT idle lanes derived from the next iteration's two masks (one ballot less)         46.5 ms
+// Each removes instructions from the loop but moves the 72-register allocation to a worse place.
+#ifndef TCPT_OPT_TOS
+#define TCPT_OPT_TOS 0
+#endif
+#ifndef TCPT_OPT_RL
+#define TCPT_OPT_RL 0
+#endif
+#ifndef TCPT_OPT_BALLOT
+#define TCPT_OPT_BALLOT 0
+#endif
 #ifndef TCPT_SPECULATE
 #define TCPT_SPECULATE 0          // 1: walk one leaf ahead of the triangle tests (Aila & Laine postponed leaf); measured 6 % slower (3.52 vs 3.32 ms/spp)
 #endif
@@ -131,6 +145,9 @@ struct Traversal {
     DHit best;
     uint32_t best_tleaf, best_tslot, best_bleaf, best_bslot;  // tie-break keys of `best`: TLAS (leaf first slot, slot), BLAS (same)
     int sp, blas_sp;             // stack height; stack height at BLAS entry (-1 = traversing the TLAS)
+    uint32_t tos;                // the top stack entry lives in a register (entries 0 .. sp-2 in local memory): a pop hands it out at once
+                                 // and the load of the entry below overlaps the node visit that follows (the pop's local-memory load
+                                 // was 6 % of the kernel's stall samples)
     uint32_t node_base, slot_base, node;
     int cur_prim; uint32_t cur_tleaf, cur_tslot;
     uint32_t pend_slot, pend_cnt;  // triangle slots (relative to slot_base) recorded but not yet tested
@@ -144,7 +161,7 @@ struct Traversal {
         best.prim = -1; best.t = t_max_; best.b0 = best.b1 = best.b2 = 0.0f; best.tri = 0;
         best_tleaf = best_tslot = best_bleaf = best_bslot = 0;
         ray_setup(rw, o, d); rl = rw;
-        sp = 0; blas_sp = -1; node_base = 0; slot_base = 0; node = 0; cur_prim = -1; cur_tleaf = cur_tslot = 0;
+        sp = 0; tos = 0; blas_sp = -1; node_base = 0; slot_base = 0; node = 0; cur_prim = -1; cur_tleaf = cur_tslot = 0;
         pend_slot = 0; pend_cnt = 0; need_pop = false;
 #if TCPT_SPECULATE
         pend2_slot = 0; pend2_cnt = 0;
@@ -156,6 +173,14 @@ struct Traversal {
     __device__ __forceinline__ bool can_walk() const { return pend_cnt == 0u || (pend2_cnt == 0u && (!need_pop || sp > blas_sp)); }
 #else
     __device__ __forceinline__ bool can_walk() const { return pend_cnt == 0u; }
+#endif
+
+#if TCPT_OPT_TOS
+    __device__ __forceinline__ void push(uint32_t* stack, uint32_t v) { if (sp > 0) stack[sp - 1] = tos; tos = v; ++sp; }
+    __device__ __forceinline__ uint32_t pop(uint32_t* stack) { const uint32_t v = tos; --sp; if (sp > 0) tos = stack[sp - 1]; return v; }
+#else
+    __device__ __forceinline__ void push(uint32_t* stack, uint32_t v) { stack[sp++] = v; }
+    __device__ __forceinline__ uint32_t pop(uint32_t* stack) { return stack[--sp]; }
 #endif
 
     // Tests ONE pending triangle.  ANY = Scene::intersect_p (scene.rs:93-103): returns true (ray finished) at the first accepted triangle.
@@ -196,9 +221,9 @@ struct Traversal {
     __device__ __forceinline__ bool node_step(const DScene& sc, uint32_t* stack, uint32_t* n_box) {
         if (need_pop) {
             need_pop = false;
-            if (sp == blas_sp) { blas_sp = -1; node_base = 0; }  // this BLAS is exhausted: back in the TLAS
+            if (sp == blas_sp) { blas_sp = -1; node_base = 0; if (TCPT_OPT_RL) rl = rw; }  // this BLAS is exhausted: back in the TLAS (and to the Render-space ray)
             if (sp == 0) return true;
-            const uint32_t top = stack[--sp];
+            const uint32_t top = pop(stack);
             if (top & TCPT_TLAS_ITEM_BIT) {
                 const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
                 const int2 item = __ldg(&sc.tlas_items[tslot]);
@@ -222,7 +247,7 @@ struct Traversal {
         const float4* rec = sc.nodes + 4 * (size_t)node;
         const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
         const bool in_blas = blas_sp >= 0;
-        const RayXform& r = in_blas ? rl : rw;
+        const RayXform& r = TCPT_OPT_RL ? rl : (in_blas ? rl : rw);   // TCPT_OPT_RL: the CURRENT ray: Render space in the TLAS (restored at BLAS exit), instance space inside a BLAS -- no per-visit selects
         const uint32_t ref0 = __float_as_uint(q0.w), cnt0 = __float_as_uint(q1.w), ref1 = __float_as_uint(q2.w), cnt1 = __float_as_uint(q3.w);
         float te0, te1;
         const bool h0 = slab_test(q0, q1, r, limit, &te0);
@@ -241,13 +266,13 @@ struct Traversal {
 #endif
         } else {
             // TLAS leaf: queue its primitives (each opens a BLAS when popped)
-            if (l0) for (uint32_t i = 0; i < cnt0; ++i) stack[sp++] = TCPT_TLAS_ITEM_BIT | (ref0 + cnt0 - 1u - i);
-            if (l1) for (uint32_t i = 0; i < cnt1; ++i) stack[sp++] = TCPT_TLAS_ITEM_BIT | (ref1 + cnt1 - 1u - i);
+            if (l0) for (uint32_t i = 0; i < cnt0; ++i) push(stack, TCPT_TLAS_ITEM_BIT | (ref0 + cnt0 - 1u - i));
+            if (l1) for (uint32_t i = 0; i < cnt1; ++i) push(stack, TCPT_TLAS_ITEM_BIT | (ref1 + cnt1 - 1u - i));
         }
         const bool i0 = h0 && cnt0 == 0, i1 = h1 && cnt1 == 0;
         if (i0 && i1) {
             const uint32_t c0 = node_base + ref0, c1 = node_base + ref1;
-            if (te1 < te0) { stack[sp++] = c0; node = c1; } else { stack[sp++] = c1; node = c0; }
+            if (te1 < te0) { push(stack, c0); node = c1; } else { push(stack, c1); node = c0; }
         } else if (i0) node = node_base + ref0;
         else if (i1) node = node_base + ref1;
         else need_pop = true;
@@ -316,6 +341,29 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
         const bool exhausted = drained && pool >= pool_end;
         if (__ballot_sync(FULL, ray != NONE) == 0u) break;  // nothing in flight and nothing left to fetch
         const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;
+#if TCPT_OPT_BALLOT
+        // A ray in flight either holds pending triangles or may walk (never neither), so the lanes without a ray are the complement
+        // of the two masks: the masks of the next iteration double as this iteration's idle count (one ballot less per iteration).
+        uint32_t n_idle_now;
+        bool has_tri = ray != NONE && T.pend_cnt != 0u;
+        bool walks = ray != NONE && T.can_walk();
+        uint32_t tri_mask = __ballot_sync(FULL, has_tri);
+        uint32_t node_mask = __ballot_sync(FULL, walks);
+        do {
+            bool finished = false;
+            if (tri_mask != 0u && ((uint32_t)__popc(tri_mask) >= (uint32_t)TCPT_TRI_PHASE_LANES || node_mask == 0u)) {
+                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, n_tri);
+            } else {
+                if (walks) finished = T.template node_step<COUNT>(sc, stack, n_box);
+            }
+            if (finished) { fin = ray; ray = NONE; T.pend_cnt = 0; }
+            has_tri = ray != NONE && T.pend_cnt != 0u;
+            walks = ray != NONE && T.can_walk();
+            tri_mask = __ballot_sync(FULL, has_tri);
+            node_mask = __ballot_sync(FULL, walks);
+            n_idle_now = 32u - (uint32_t)__popc(tri_mask | node_mask);
+        } while (n_idle_now < stop_at);
+#else
         uint32_t n_idle_now;
         do {
             const bool has_tri = ray != NONE && T.pend_cnt != 0u;
@@ -331,6 +379,7 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
             if (finished) { fin = ray; ray = NONE; T.pend_cnt = 0; }
             n_idle_now = (uint32_t)__popc(__ballot_sync(FULL, ray == NONE));
         } while (n_idle_now < stop_at);
+#endif
     }
 }
 
