@@ -122,19 +122,23 @@ __device__ inline bool refract(float3 wi, float3 n, float eta, float3* wt) {
 struct Ggx {
     float ax, ay;
     __device__ __forceinline__ bool effectively_smooth() const { return rmax(ax, ay) < 1e-3f; }
-    __device__ __noinline__ float D(float3 wm) const {
+    __device__ __forceinline__ float D_i(float3 wm) const {
         const float t2 = tan2_theta(wm);
         if (!isfinite(t2)) return 0.0f;
         const float cos4 = pow2(cos2_theta(wm));
         const float e = t2 * (pow2(cos_phi(wm)) / pow2(ax) + pow2(sin_phi(wm)) / pow2(ay));
         return 1.0f / (TCPT_PI * ax * ay * cos4 * pow2(1.0f + e));
     }
-    __device__ __noinline__ float lambda(float3 w) const {
+    __device__ __noinline__ static float D_v(const Ggx self, float3 wm) { return self.D_i(wm); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ float D(float3 wm) const { return D_v(*this, wm); }
+    __device__ __forceinline__ float lambda_i(float3 w) const {
         const float t2 = tan2_theta(w);
         if (isinf(t2)) return 0.0f;
         const float a2 = pow2(cos_phi(w) * ax) + pow2(sin_phi(w) * ay);
         return (sqrtf(1.0f + a2 * t2) - 1.0f) / 2.0f;
     }
+    __device__ __noinline__ static float lambda_v(const Ggx self, float3 w) { return self.lambda_i(w); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ float lambda(float3 w) const { return lambda_v(*this, w); }
     __device__ float G1(float3 w) const { return 1.0f / (1.0f + lambda(w)); }
     __device__ float G(float3 wo, float3 wi) const { return 1.0f / (1.0f + lambda(wo) + lambda(wi)); }
     __device__ float Dvis(float3 w, float3 wm) const {
@@ -142,7 +146,7 @@ struct Ggx {
         if (c == 0.0f) return 0.0f;
         return G1(w) / c * D(wm) * fabsf(dot(w, wm));
     }
-    __device__ __noinline__ float3 sample_wm(float3 w, float2 u) const {
+    __device__ __forceinline__ float3 sample_wm_i(float3 w, float2 u) const {
         float3 wh = normalize(f3(ax * w.x, ay * w.y, w.z));
         if (wh.z < 0.0f) wh = -wh;
         const float3 t1 = wh.z < 0.99999f ? normalize(cross(f3(0, 0, 1), wh)) : f3(1, 0, 0);
@@ -155,6 +159,8 @@ struct Ggx {
         const float3 nh = (t1 * p.x + t2 * py) + wh * pz;
         return normalize(f3(ax * nh.x, ay * nh.y, rmax(1e-6f, nh.z)));
     }
+    __device__ __noinline__ static float3 sample_wm_v(const Ggx self, float3 w, float2 u) { return self.sample_wm_i(w, u); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ float3 sample_wm(float3 w, float2 u) const { return sample_wm_v(*this, w, u); }
 };
 
 __device__ inline bool generalized_half_vector(float3 wo, float3 wi, float eta, float3* out) {
@@ -397,7 +403,7 @@ struct Schlick {
         const float o2 = omc * omc;
         return r0 + (s4(1.0f) - r0) * (o2 * o2 * omc);  // (1 - cos)^5: three roundings, within 2 ulp of powf(omc, 5.0)
     }
-    __device__ __noinline__ bool sample(float3 wo, float2 uv, BsdfSample* out) const {
+    __device__ __forceinline__ bool sample_i(float3 wo, float2 uv, BsdfSample* out) const {
         if (wo.z == 0.0f) return false;
         if (g.effectively_smooth()) {
             const float3 wi = f3(-wo.x, -wo.y, wo.z);
@@ -418,7 +424,9 @@ struct Schlick {
         out->f = fr * d * gg / (4.0f * co); out->wi = wi; out->pdf = pdf; out->type = ST_GLOSSY_REFLECTION;
         return true;
     }
-    __device__ __noinline__ S4 evaluate(float3 wo, float3 wi) const {
+    __device__ __noinline__ static bool sample_v(const Schlick self, float3 wo, float2 uv, BsdfSample* out) { return self.sample_i(wo, uv, out); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ bool sample(float3 wo, float2 uv, BsdfSample* out) const { return sample_v(*this, wo, uv, out); }
+    __device__ __forceinline__ S4 evaluate_i(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return s4(0.0f);
         const float co = fabsf(wo.z), ci = fabsf(wi.z);
         if (co == 0.0f || ci == 0.0f) return s4(0.0f);
@@ -429,7 +437,9 @@ struct Schlick {
         const float d = g.D(wm), gg = g.G(wo, wi);
         return fr * d * gg / (4.0f * co);
     }
-    __device__ __noinline__ float pdf(float3 wo, float3 wi) const {
+    __device__ __noinline__ static S4 evaluate_v(const Schlick self, float3 wo, float3 wi) { return self.evaluate_i(wo, wi); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ S4 evaluate(float3 wo, float3 wi) const { return evaluate_v(*this, wo, wi); }
+    __device__ __forceinline__ float pdf_i(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return 0.0f;
         if (!same_hemisphere(wo, wi)) return 0.0f;
         float3 wm;
@@ -439,8 +449,10 @@ struct Schlick {
         if (jac == 0.0f) return 0.0f;
         return vis / jac;
     }
+    __device__ __noinline__ static float pdf_v(const Schlick self, float3 wo, float3 wi) { return self.pdf_i(wo, wi); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ float pdf(float3 wo, float3 wi) const { return pdf_v(*this, wo, wi); }
     // 64-sample stochastic estimate (generalized_schlick.rs:893-918); `f` already holds a cosine, reproduced as is
-    __device__ __noinline__ S4 directional_albedo(float3 wo, DAuxRng rng) const {
+    __device__ __forceinline__ S4 directional_albedo_i(float3 wo, DAuxRng rng) const {
         S4 sum = s4(0.0f);
         if (g.effectively_smooth()) {
             // every one of the 64 samples is the same mirror sample (the random numbers are drawn but unused), so the term is
@@ -490,6 +502,8 @@ struct Schlick {
         }
         return sum / 64.0f;
     }
+    __device__ __noinline__ static S4 directional_albedo_v(const Schlick self, float3 wo, DAuxRng rng) { return self.directional_albedo_i(wo, rng); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ S4 directional_albedo(float3 wo, DAuxRng rng) const { return directional_albedo_v(*this, wo, rng); }
 };
 __device__ __forceinline__ float r0_of(float ior) { const float r = (ior - 1.0f) / (ior + 1.0f); return r * r; }
 __device__ __forceinline__ Schlick make_schlick(const S4& r0, float alpha) { Schlick s; s.r0 = r0; s.g.ax = alpha; s.g.ay = alpha; return s; }
@@ -515,13 +529,15 @@ struct PbrBase {
         if (!lambert_sample(base_color, wo, uv, &s)) return mat_fail();
         return mat_ok(s.f * (1.0f - fresnel), s.wi, s.pdf * (1.0f - fresnel), s.type);
     }
-    __device__ __noinline__ MatSample sample_nm(float3 wo, float uc, float2 uv) const {
+    __device__ __forceinline__ MatSample sample_nm_i(float3 wo, float uc, float2 uv) const {
         const float alpha = roughness * roughness;
         if (metallic >= 1.0f) return sample_metallic(alpha, wo, uv);
         if (metallic <= 0.0f) return sample_dielectric(alpha, wo, uc, uv);
         if (uc <= metallic) return sample_metallic(alpha, wo, uv);
         return sample_dielectric(alpha, wo, (uc - metallic) / (1.0f - metallic), uv);
     }
+    __device__ __noinline__ static MatSample sample_nm_v(const PbrBase self, float3 wo, float uc, float2 uv) { return self.sample_nm_i(wo, uc, uv); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ MatSample sample_nm(float3 wo, float uc, float2 uv) const { return sample_nm_v(*this, wo, uc, uv); }
     __device__ __forceinline__ MatSample sample(float3 wo, float uc, float2 uv, const M3& from_nm) const {
         MatSample ms = sample_nm(wo, uc, uv);
         if (ms.sampled) ms.wi = m3_vector(from_nm, ms.wi);
@@ -533,24 +549,28 @@ struct PbrBase {
         const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
         return direct + (1.0f - fresnel) * lambert_eval(base_color, wo, wi);
     }
-    __device__ __noinline__ S4 evaluate(float3 wo, float3 wi) const {
+    __device__ __forceinline__ S4 evaluate_i(float3 wo, float3 wi) const {
         const float alpha = roughness * roughness;
         if (metallic >= 1.0f) return make_schlick(base_color, alpha).evaluate(wo, wi);
         if (metallic <= 0.0f) return eval_dielectric(alpha, wo, wi);
         return make_schlick(base_color, alpha).evaluate(wo, wi) * metallic + eval_dielectric(alpha, wo, wi) * (1.0f - metallic);
     }
+    __device__ __noinline__ static S4 evaluate_v(const PbrBase self, float3 wo, float3 wi) { return self.evaluate_i(wo, wi); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ S4 evaluate(float3 wo, float3 wi) const { return evaluate_v(*this, wo, wi); }
     __device__ float pdf_dielectric(float alpha, float3 wo, float3 wi) const {
         const Schlick gs = make_schlick(s4(r0_of(ior)), alpha);
         const float direct = gs.pdf(wo, wi);
         const float fresnel = s4_avg(gs.fresnel_at(fabsf(wo.z)));
         return fresnel * direct + (1.0f - fresnel) * lambert_pdf(wo, wi);
     }
-    __device__ __noinline__ float pdf(float3 wo, float3 wi) const {
+    __device__ __forceinline__ float pdf_i(float3 wo, float3 wi) const {
         const float alpha = roughness * roughness;
         if (metallic >= 1.0f) return make_schlick(s4(1.0f), alpha).pdf(wo, wi);
         if (metallic <= 0.0f) return pdf_dielectric(alpha, wo, wi);
         return make_schlick(s4(1.0f), alpha).pdf(wo, wi) * metallic + pdf_dielectric(alpha, wo, wi) * (1.0f - metallic);
     }
+    __device__ __noinline__ static float pdf_v(const PbrBase self, float3 wo, float3 wi) { return self.pdf_i(wo, wi); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ float pdf(float3 wo, float3 wi) const { return pdf_v(*this, wo, wi); }
 };
 
 // Beer-Lambert coat attenuation (simple_pbr_clearcoat_material.rs:88-107)
