@@ -257,7 +257,7 @@ struct Dielectric {
         out->wi = wi; out->type = ST_GLOSSY_TRANSMISSION;
         return true;
     }
-    __device__ __noinline__ bool sample(float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) const {
+    __device__ __forceinline__ bool sample_i(float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) const {
         if (wo.z == 0.0f) return false;
         if (g.effectively_smooth()) return sample_specular(wo, uc, wl, out);  // selector = uc (dielectric.rs:180)
         const float3 wm = g.sample_wm(wo, uv);
@@ -277,7 +277,9 @@ struct Dielectric {
         if (!s4_is_constant(eta) && !wl.terminated) wl = wavelengths_uniform(wl.lambda[0], true);
         return mf_transmission(wo, wm, s4(1.0f) - fresnel, pt / (pr + pt), eta_scalar, out);
     }
-    __device__ __noinline__ S4 evaluate(float3 wo, float3 wi) const {
+    __device__ __noinline__ static bool sample_v(const Dielectric self, float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) { return self.sample_i(wo, uv, uc, wl, out); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ bool sample(float3 wo, float2 uv, float uc, DWavelengths& wl, BsdfSample* out) const { return sample_v(*this, wo, uv, uc, wl, out); }
+    __device__ __forceinline__ S4 evaluate_i(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return s4(0.0f);
         const S4 es = eta_spectrum();
         const float eta_scalar = es.v[0];
@@ -290,7 +292,9 @@ struct Dielectric {
         const float denom = pow2(dot(wi, wm) + dot(wo, wm) / eta_scalar);
         return (s4(1.0f) - fresnel) * d * gg * fabsf(dot(wi, wm)) * fabsf(dot(wo, wm)) / (denom * fabsf(wo.z) * eta_scalar * eta_scalar);
     }
-    __device__ __noinline__ float pdf(float3 wo, float3 wi) const {
+    __device__ __noinline__ static S4 evaluate_v(const Dielectric self, float3 wo, float3 wi) { return self.evaluate_i(wo, wi); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ S4 evaluate(float3 wo, float3 wi) const { return evaluate_v(*this, wo, wi); }
+    __device__ __forceinline__ float pdf_i(float3 wo, float3 wi) const {
         if (g.effectively_smooth()) return 0.0f;
         const S4 es = eta_spectrum();
         const float eta_scalar = es.v[0];
@@ -305,6 +309,8 @@ struct Dielectric {
         const float dwm_dwi = fabsf(dot(wi, wm)) / denom;
         return g.Dvis(wo, wm) * dwm_dwi * pt / (pr + pt);
     }
+    __device__ __noinline__ static float pdf_v(const Dielectric self, float3 wo, float3 wi) { return self.pdf_i(wo, wi); }   // `this` travels by value, not through the caller's stack frame
+    __device__ __forceinline__ float pdf(float3 wo, float3 wi) const { return pdf_v(*this, wo, wi); }
 };
 // DielectricBsdf::new (dielectric.rs:127-148): an eta whose first lane is 0 falls back to the constant 1
 __device__ __forceinline__ Dielectric make_dielectric(const S4& eta, bool entering, bool thin, float alpha) {
