@@ -1,4 +1,4 @@
-"""Developer probe: image-level GPU-vs-oracle error by max_depth.  usage: gpu_debug3.py scene integrator sampler spp"""
+"""Developer probe: image-level GPU-vs-oracle error by max_depth.  usage: probe_error_by_depth.py scene integrator sampler spp"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))

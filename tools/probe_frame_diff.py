@@ -1,5 +1,5 @@
 """Developer probe (not a test): locate the pixels / paths where a GPU frame differs from the oracle's.  Run under gpurun.
-usage: gpu_debug2.py scene integrator sampler [spp]"""
+usage: probe_frame_diff.py scene integrator sampler [spp]"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))

@@ -1,5 +1,5 @@
 """Developer probe: per-bounce rays of ONE path, GPU (option debug_path_log, stderr) next to the oracle's recorded rays.
-usage: gpu_debug4.py scene integrator sampler spp x y sample"""
+usage: probe_one_path.py scene integrator sampler spp x y sample"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
