@@ -175,3 +175,27 @@ def test_gpu_stream_bit_exact(tables, sampler):
         assert n == total
         exp = o.sampler_stream(sampler, spp, w, h, seed, px, py, i, kinds)
         assert out.view(np.uint32).tolist() == exp.view(np.uint32).tolist(), (sampler, spp, w, h, px, py, i, seed)
+
+
+@pytest.mark.parametrize("spp", [16, 64, 256])
+def test_samples_of_a_pixel_form_a_base2_net(tables, spp):
+    """Ground truth that does not depend on any restatement: the samples of one pixel are an aligned block of 2^m consecutive Sobol
+    indices (the Morton prefix selects the block, the digit permutations only reorder it), and Owen scrambling keeps the net property,
+    so the 2-D points of ANY get_2d call form a (0, m, 2)-net: every elementary interval of area 2^-m holds exactly one of them.  A
+    wrong generator matrix, a wrong bit order, a broken scramble or a permutation that leaves the block would all break this.
+    (Even log2(spp) only: for odd ones the reference draws every sample twice, z_sobol_sampler.rs:131-155, see the quirk test above.)"""
+    o = _oracle(tables)
+    m = spp.bit_length() - 1
+    assert m % 2 == 0
+    kinds = [1, 2, 1, 2, 2]                      # wavelength, pixel sample, lobe choice, BSDF sample, light sample
+    for px, py, seed in ((0, 0, 0), (13, 7, 0), (199, 149, 5)):
+        pts = np.array([o.sampler_stream("sobol", spp, 200, 150, seed, px, py, i, kinds) for i in range(spp)], dtype=np.float64)
+        for cols in ((1, 2), (4, 5), (6, 7)):     # the three get_2d calls
+            xy = pts[:, cols]
+            assert xy.min() >= 0.0 and xy.max() < 1.0
+            for a in range(m + 1):
+                cells = np.floor(xy[:, 0] * (1 << a)).astype(np.int64) * (1 << (m - a)) + np.floor(xy[:, 1] * (1 << (m - a))).astype(np.int64)
+                assert len(np.unique(cells)) == spp, (px, py, cols, a)
+        # and every 1-D draw is stratified into spp equal intervals
+        for c in (0, 3):
+            assert len(np.unique(np.floor(pts[:, c] * spp).astype(np.int64))) == spp
