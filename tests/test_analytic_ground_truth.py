@@ -267,3 +267,46 @@ def test_floor_under_an_emissive_single_triangle(bundle_factory, gpu, integrator
     assert np.allclose(got.mean(0), [expect.mean()] * 3, rtol=0.01), (got.mean(0), expect.mean())
     bright = expect > np.quantile(expect, 0.9)
     assert np.allclose(got[bright].mean(0), [expect[bright].mean()] * 3, rtol=0.015), (got[bright].mean(0), expect[bright].mean())
+
+
+# ------------------------------------------------------------------ texture lookup convention (texture/sampler.rs:6-45, rgb_texture.rs:48-66)
+TEX = (np.arange(16, dtype=np.uint8).reshape(4, 4) * 13 + 20)            # 4 x 4 grey levels 20 .. 215, all different
+
+
+def textured_quad(scene, camera):
+    from toy_cpu_pathtracing_b200.scene import RgbTexture, SpectrumType
+    tex = RgbTexture.load_srgb(np.ascontiguousarray(np.repeat(TEX[:, :, None], 3, axis=2)))
+    quad = assets.quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), (0, 0, 1))          # uv (0,0) (1,0) (1,1) (0,1)
+    scene.create_primitive(GP(scene.load_obj(quad), LambertMaterial.new(SpectrumParameter.texture(tex, SpectrumType.Albedo), NormalParameter.none()), Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.EnvironmentLightPrimitive(1.0, np.full((8, 16, 3), 1.0, dtype=np.float32), Transform.identity()))
+    camera.set_look_to((0.0, 0.0, 3.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+def test_texture_lookup_convention(bundle_factory, gpu):
+    """AlbedoRenderer on a textured quad seen head-on, against the lookup rule written out independently in numpy: u = |fract(u)|,
+    v = 1 - |fract(v)|, texel coordinate = uv * (size - 1), four-tap bilinear on the GAMMA-ENCODED u8 / 255 values, the result typed
+    as ColorSrgb -> inverse EOTF -> grey shortcut of the coefficient table -> constant spectrum -> (under D65) that grey again."""
+    be = backend(bundle_factory, textured_quad, gpu)
+    b = be.b
+    img = be.film("albedo", 64)
+    d = pixel_centre_rays(b.camera, W, H)
+    t = -3.0 / d[..., 2]
+    x, y = t * d[..., 0], t * d[..., 1]
+    inside = eroded((np.abs(x) < 1) & (np.abs(y) < 1), 2)
+    assert inside.sum() > 1500
+    u, v = (x + 1) / 2, (y + 1) / 2
+    uu, vv = np.abs(u - np.trunc(u)), 1.0 - np.abs(v - np.trunc(v))
+    fx, fy = uu * 3.0, vv * 3.0
+    x0, y0 = np.floor(fx).astype(int), np.floor(fy).astype(int)
+    x1, y1 = np.minimum(x0 + 1, 3), np.minimum(y0 + 1, 3)
+    ax, ay = fx - x0, fy - y0
+    g = TEX.astype(np.float64) / 255.0
+    enc = (g[y0, x0] * (1 - ax) + g[y0, x1] * ax) * (1 - ay) + (g[y1, x0] * (1 - ax) + g[y1, x1] * ax) * ay
+    lin = np.where(enc <= 0.04045, enc / 12.92, ((enc + 0.055) / 1.055) ** 2.4)
+    got = img[inside]
+    rel = np.abs(got - lin[inside][:, None]) / lin[inside][:, None]
+    # per pixel: spectral noise of 64 stratified wavelengths + the pixel footprint averaging a smooth function
+    assert np.median(rel) < 0.01 and np.quantile(rel, 0.99) < 0.06, (np.median(rel), np.quantile(rel, 0.99))
+    # the texture is not mirrored or transposed: its darkest corner (row 0 = top of the image, v = 1) is where the rule puts it
+    assert got[:, 1].reshape(-1)[np.argmin(lin[inside])] < np.quantile(got[:, 1], 0.05)
