@@ -310,3 +310,37 @@ def test_texture_lookup_convention(bundle_factory, gpu):
     assert np.median(rel) < 0.01 and np.quantile(rel, 0.99) < 0.06, (np.median(rel), np.quantile(rel, 0.99))
     # the texture is not mirrored or transposed: its darkest corner (row 0 = top of the image, v = 1) is where the rule puts it
     assert got[:, 1].reshape(-1)[np.argmin(lin[inside])] < np.quantile(got[:, 1], 0.05)
+
+
+# ------------------------------------------------------------------ delta light: inverse-square law (point_light.rs:75-88, common.rs:23-55)
+def point_lamp_over_floor(scene, camera):
+    f = FLOOR_HALF
+    floor = assets.quad((-f, 0, f), (f, 0, f), (f, 0, -f), (-f, 0, -f), (0, 1, 0))
+    scene.create_primitive(GP(scene.load_obj(floor), LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(FLOOR_RHO, FLOOR_RHO, FLOOR_RHO))),
+                                                                          NormalParameter.none()), Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.PointLightPrimitive(10.0, presets.cie_illum_d6500(), Transform.from_translate((0.0, LAMP_Y, 0.0))))
+    camera.set_look_to((0.0, 1.2, 4.5), _unit((0.0, -0.45, -1.0)), (0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("integrator", ["nee", "mis"])
+def test_floor_under_a_point_light_follows_the_inverse_square_law(bundle_factory, gpu, integrator):
+    """L_o = rho / pi * I * cos(theta) / d^2 with I = 10 x D65 (linear sRGB 10): one deterministic light sample per path, so the only
+    noise is spectral.  (A point light cannot be hit: `pt` renders black, which the parity tests cover.)"""
+    be = backend(bundle_factory, point_lamp_over_floor, gpu)
+    b = be.b
+    img = be.film(integrator, 64)
+    d = pixel_centre_rays(b.camera, W, H)
+    o = b.camera.position.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = -o[1] / d[..., 1]
+        p = o + t[..., None] * d
+    sel = eroded((d[..., 1] < 0) & (np.abs(p[..., 0]) < FLOOR_HALF - 0.1) & (np.abs(p[..., 2]) < FLOOR_HALF - 0.1))
+    assert sel.sum() > 1500
+    r2 = p[sel][:, 0] ** 2 + LAMP_Y ** 2 + p[sel][:, 2] ** 2
+    expect = FLOOR_RHO / np.pi * 10.0 * LAMP_Y / r2 ** 1.5
+    got = img[sel]
+    assert np.allclose(got.mean(0), [expect.mean()] * 3, rtol=0.01), (got.mean(0), expect.mean())
+    lum = got @ np.array([0.2126, 0.7152, 0.0722])
+    rel = np.abs(lum - expect) / expect
+    assert np.median(rel) < 0.01 and np.quantile(rel, 0.99) < 0.05, (np.median(rel), np.quantile(rel, 0.99))
