@@ -344,3 +344,74 @@ def test_floor_under_a_point_light_follows_the_inverse_square_law(bundle_factory
     lum = got @ np.array([0.2126, 0.7152, 0.0722])
     rel = np.abs(lum - expect) / expect
     assert np.median(rel) < 0.01 and np.quantile(rel, 0.99) < 0.05, (np.median(rel), np.quantile(rel, 0.99))
+
+
+# ------------------------------------------------------------------ refraction and conductors in the furnace
+def furnace_body(scene, camera, material):
+    from toy_cpu_pathtracing_b200.scene import MetalMaterial, MetalType
+    mat = {"thick_plastic": lambda: PlasticMaterial.new(1.5, SpectrumParameter.Constant(ConstantSpectrum(1.0)), NormalParameter.none(), False, FloatParameter.constant(0.0)),
+           "thick_glass": lambda: GlassMaterial.new(GlassType.Bk7, NormalParameter.none(), False, FloatParameter.constant(0.0)),
+           "gold": lambda: MetalMaterial.new(MetalType.Gold, NormalParameter.none(), FloatParameter.constant(0.0))}[material]()
+    scene.create_primitive(GP(scene.load_obj(assets.box((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), rot_y_deg=25.0)), mat, Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.EnvironmentLightPrimitive(1.0, np.full((64, 128, 3), 1.0, dtype=np.float32), Transform.identity()))
+    camera.set_look_to((1.2, 1.4, 2.6), _unit((-1.2, -1.4, -2.6)), (0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("material,spp", [("thick_plastic", 64), ("thick_glass", 1024)])
+def test_white_furnace_solid_dielectrics_under_pt(bundle_factory, gpu, material, spp):
+    """Refraction in and out (radiance scaling, total internal reflection, Russian roulette, depth 16) conserves energy: a solid,
+    non-absorbing dielectric body shows the uniform environment.  The dispersive glass collapses every path to its hero wavelength
+    (terminate_secondary, single-lane sensor path), which is unbiased but noisy in colour: it needs 1024 samples to show it."""
+    be = backend(bundle_factory, furnace_body, gpu, material=material)
+    body, _ = be.hit_mask()
+    body = eroded(body)
+    got = be.film("pt", spp)[body].mean(0) / env_radiance(1.0)
+    assert np.allclose(got, [1.0, 1.0, 1.0], atol=0.012), got
+
+
+def conductor_reflectance(cos_i, n, k):
+    """Unpolarised Fresnel reflectance of a conductor, textbook form in complex arithmetic (not the reference's real-valued expansion)."""
+    eta = n + 1j * k
+    sin2 = 1.0 - cos_i * cos_i
+    cos_t = np.sqrt(1.0 - sin2 / (eta * eta))
+    r_par = (eta * cos_i - cos_t) / (eta * cos_i + cos_t)
+    r_per = (cos_i - eta * cos_t) / (cos_i + eta * cos_t)
+    return 0.5 * (np.abs(r_par) ** 2 + np.abs(r_per) ** 2)
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+def test_gold_mirror_in_the_furnace_shows_its_fresnel_reflectance(bundle_factory, gpu, tables):
+    """A convex mirror in a uniform environment: every pixel is R(lambda, cos theta_i) x L integrated against the observer.  R from the
+    measured n, k of gold (the reference's preset tables) through the textbook complex formula, theta_i from the face a pixel sees."""
+    be = backend(bundle_factory, furnace_body, gpu, material="gold")
+    b = be.b
+    img = be.film("pt", 256) / env_radiance(1.0)
+    std = tables[0]
+    base = 8 + 104 * 4
+    f = np.frombuffer(std[base: base + 4 * 470 * 4], dtype="<f4").reshape(4, 470).astype(np.float64)
+    cx, cy, cz, d65 = f
+    n_presets = np.frombuffer(std[base + 4 * 470 * 4: base + 4 * 470 * 4 + 4], dtype="<u4")[0]
+    presets_tab = np.frombuffer(std[base + 4 * 470 * 4 + 4:], dtype="<f4").reshape(n_presets, 470).astype(np.float64)
+    n_au, k_au = presets_tab[0], presets_tab[1]                            # TCPT_PRESET_AU_ETA, TCPT_PRESET_AU_K
+    xyz_to_rgb = np.array([[3.2404542, -1.5371385, -0.4985314], [-0.9692660, 1.8760108, 0.0415560], [0.0556434, -0.2040259, 1.0572252]])
+    d = pixel_centre_rays(b.camera, W, H)
+    rays = np.concatenate([np.zeros((W * H, 3)), d.reshape(-1, 3), np.full((W * H, 1), np.finfo(np.float32).max)], 1).astype(np.float32)
+    hits = b.scene.trace(rays) if gpu else b.oracle.trace(rays)[0]
+    prim, tri = hits[:, 0].reshape(H, W), hits[:, 1].reshape(H, W)
+    a = np.deg2rad(25.0)
+    rot = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    normals = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], dtype=np.float64) @ rot.T   # assets.box face order
+    seen = 0
+    for face in range(6):
+        sel = eroded((prim == 0) & (tri // 2 == face), 1)
+        if sel.sum() < 60:
+            continue
+        seen += 1
+        cos_i = np.abs(d[sel] @ normals[face])
+        refl = conductor_reflectance(cos_i[:, None], n_au[None, :], k_au[None, :])            # (pixels, 470)
+        xyz = np.stack([(refl * cx * d65).sum(1), (refl * cy * d65).sum(1), (refl * cz * d65).sum(1)], 1)
+        expect = xyz @ xyz_to_rgb.T
+        got = img[sel]
+        assert np.allclose(got.mean(0), expect.mean(0), atol=0.012), (face, got.mean(0), expect.mean(0))
+    assert seen >= 2          # the camera sees three faces; the narrowest may fall under the pixel threshold
