@@ -415,3 +415,34 @@ def test_gold_mirror_in_the_furnace_shows_its_fresnel_reflectance(bundle_factory
         got = img[sel]
         assert np.allclose(got.mean(0), expect.mean(0), atol=0.012), (face, got.mean(0), expect.mean(0))
     assert seen >= 2          # the camera sees three faces; the narrowest may fall under the pixel threshold
+
+
+# ------------------------------------------------------------------ directional light (directional_light.rs:92-107, common.rs:58-79)
+WALL_RHO, SUN_DEG = 0.5, 30.0
+
+
+def wall_under_a_directional_light(scene, camera):
+    wall = assets.quad((-2, -2, 0), (2, -2, 0), (2, 2, 0), (-2, 2, 0), (0, 0, 1))
+    scene.create_primitive(GP(scene.load_obj(wall), LambertMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(WALL_RHO, WALL_RHO, WALL_RHO))),
+                                                                         NormalParameter.none()), Transform.identity()))
+    # the light points along its local +z; rotated 30 degrees about Y the direction TOWARDS the light is (sin 30, 0, cos 30)
+    scene.create_primitive(CreatePrimitiveDesc.DirectionalLightPrimitive(2.0, presets.cie_illum_d6500(), Transform.identity().rotate_y(SUN_DEG)))
+    camera.set_look_to((0.0, 0.0, 4.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("integrator", ["nee", "mis"])
+def test_wall_under_a_directional_light(bundle_factory, gpu, integrator):
+    """L_o = rho / pi * E * cos(theta) with E = 2 x D65 and theta = 30 degrees, the same on every point of the wall.  (The reference starts
+    the shadow ray ON the surface, common.rs:70-72; on a single flat quad the conservative t > delta_t test of the triangle intersection
+    rejects the self-hit, so no pixel is shadowed.)"""
+    be = backend(bundle_factory, wall_under_a_directional_light, gpu)
+    img = be.film(integrator, 64)
+    wall, _ = be.hit_mask()
+    wall = eroded(wall, 2)
+    assert wall.sum() > 2000
+    expect = WALL_RHO / np.pi * 2.0 * np.cos(np.deg2rad(SUN_DEG))
+    got = img[wall]
+    assert np.allclose(got.mean(0), [expect] * 3, rtol=0.01), (got.mean(0), expect)
+    lum = got @ np.array([0.2126, 0.7152, 0.0722])
+    assert np.quantile(np.abs(lum / expect - 1.0), 0.99) < 0.05
