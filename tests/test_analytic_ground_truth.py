@@ -446,3 +446,93 @@ def test_wall_under_a_directional_light(bundle_factory, gpu, integrator):
     assert np.allclose(got.mean(0), [expect] * 3, rtol=0.01), (got.mean(0), expect)
     lum = got @ np.array([0.2126, 0.7152, 0.0722])
     assert np.quantile(np.abs(lum / expect - 1.0), 0.99) < 0.05
+
+
+# ------------------------------------------------------------------ SimplePbr, smooth: Schlick mirror / Schlick coat over Lambert
+def pbr_body(scene, camera, metallic):
+    from toy_cpu_pathtracing_b200.scene import SimplePbrMaterial
+    mat = SimplePbrMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(0.8, 0.8, 0.8))), FloatParameter.constant(metallic),
+                                FloatParameter.constant(0.0), NormalParameter.none(), FloatParameter.constant(1.5))
+    scene.create_primitive(GP(scene.load_obj(assets.box((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), rot_y_deg=25.0)), mat, Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.EnvironmentLightPrimitive(1.0, np.full((64, 128, 3), 1.0, dtype=np.float32), Transform.identity()))
+    camera.set_look_to((1.2, 1.4, 2.6), _unit((-1.2, -1.4, -2.6)), (0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("metallic", [1.0, 0.0])
+def test_smooth_simple_pbr_in_the_furnace(bundle_factory, gpu, metallic):
+    """simple_pbr_material.rs with roughness 0 under pt on a convex body: metallic 1 is a Schlick mirror with r0 = base colour,
+    F = r0 + (1 - r0)(1 - cos)^5; metallic 0 picks the r0 = ((n-1)/(n+1))^2 mirror with probability F and the (1 - F)-scaled Lambert lobe
+    otherwise, so the pixel is (F + (1 - F) rho) L.  Checked face by face at each face's angle of incidence."""
+    be = backend(bundle_factory, pbr_body, gpu, metallic=metallic)
+    b = be.b
+    img = be.film("pt", 256) / env_radiance(1.0)
+    d = pixel_centre_rays(b.camera, W, H)
+    rays = np.concatenate([np.zeros((W * H, 3)), d.reshape(-1, 3), np.full((W * H, 1), np.finfo(np.float32).max)], 1).astype(np.float32)
+    hits = b.scene.trace(rays) if gpu else b.oracle.trace(rays)[0]
+    prim, tri = hits[:, 0].reshape(H, W), hits[:, 1].reshape(H, W)
+    a = np.deg2rad(25.0)
+    rot = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    normals = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], dtype=np.float64) @ rot.T
+    rho, seen = 0.8, 0
+    for face in range(6):
+        sel = eroded((prim == 0) & (tri // 2 == face), 1)
+        if sel.sum() < 60:
+            continue
+        seen += 1
+        c = np.abs(d[sel] @ normals[face])
+        if metallic >= 1.0:
+            expect = rho + (1.0 - rho) * (1.0 - c) ** 5
+        else:
+            r0 = ((1.5 - 1.0) / (1.5 + 1.0)) ** 2
+            fr = r0 + (1.0 - r0) * (1.0 - c) ** 5
+            expect = fr + (1.0 - fr) * rho
+        got = img[sel].mean(0)
+        assert np.allclose(got, [expect.mean()] * 3, atol=0.012), (face, got, expect.mean())
+    assert seen >= 2
+
+
+def coated_body(scene, camera, tint=1.0):
+    from toy_cpu_pathtracing_b200.scene import SimpleClearcoatPbrMaterial
+    mat = SimpleClearcoatPbrMaterial.new(SpectrumParameter.constant(RgbAlbedoSpectrum(ColorSrgbLinear(0.8, 0.8, 0.8))), FloatParameter.constant(1.0),
+                                         FloatParameter.constant(0.0), NormalParameter.none(), FloatParameter.constant(1.5),
+                                         FloatParameter.constant(1.5), FloatParameter.constant(0.0),
+                                         SpectrumParameter.Constant(ConstantSpectrum(tint)), FloatParameter.constant(0.8))
+    scene.create_primitive(GP(scene.load_obj(assets.box((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), rot_y_deg=25.0)), mat, Transform.identity()))
+    scene.create_primitive(CreatePrimitiveDesc.EnvironmentLightPrimitive(1.0, np.full((64, 128, 3), 1.0, dtype=np.float32), Transform.identity()))
+    camera.set_look_to((1.2, 1.4, 2.6), _unit((-1.2, -1.4, -2.6)), (0.0, 1.0, 0.0))
+
+
+@pytest.mark.parametrize("gpu", CPU_GPU)
+@pytest.mark.parametrize("tint", [1.0, 0.5])
+def test_smooth_clearcoat_in_the_furnace(bundle_factory, gpu, tint):
+    """simple_pbr_clearcoat_material.rs:121-250 with a mirror coat over a mirror metal, as the reference defines it: the coat lobe is
+    chosen with probability Fc = F(c) c (its `directional_albedo` sums f |cos| / pdf with an f that already holds the cosine) and weighs
+    f / (pdf Fc) = 1 / c, the substrate is chosen with 1 - Fc and divided by it, so the pixel is [F_coat(c) + att(c)^2 M(c)] L with
+    M = r0 + (1 - r0)(1 - c)^5 the metal's Schlick mirror and att = tint^(thickness / c) the Beer-Lambert coat (:88-107); the substrate is
+    NOT dimmed by 1 - F_coat -- the layered material adds energy -- which is reproduced, not corrected."""
+    be = backend(bundle_factory, coated_body, gpu, tint=tint)
+    b = be.b
+    img = be.film("pt", 256) / env_radiance(1.0)
+    d = pixel_centre_rays(b.camera, W, H)
+    rays = np.concatenate([np.zeros((W * H, 3)), d.reshape(-1, 3), np.full((W * H, 1), np.finfo(np.float32).max)], 1).astype(np.float32)
+    hits = b.scene.trace(rays) if gpu else b.oracle.trace(rays)[0]
+    prim, tri = hits[:, 0].reshape(H, W), hits[:, 1].reshape(H, W)
+    a = np.deg2rad(25.0)
+    rot = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    normals = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], dtype=np.float64) @ rot.T
+    rho, seen = 0.8, 0
+    for face in range(6):
+        sel = eroded((prim == 0) & (tri // 2 == face), 1)
+        if sel.sum() < 60:
+            continue
+        seen += 1
+        c = np.abs(d[sel] @ normals[face])
+        r0 = ((1.5 - 1.0) / (1.5 + 1.0)) ** 2
+        f_coat = r0 + (1.0 - r0) * (1.0 - c) ** 5
+        metal = rho + (1.0 - rho) * (1.0 - c) ** 5
+        att = tint ** (0.8 / np.maximum(c, 1e-4))          # exp(-sigma L), sigma = -ln(tint) / 0.001, L = thickness 0.001 / cos; in and out at the same angle
+        expect = f_coat + att * att * metal
+        got = img[sel].mean(0)
+        assert np.allclose(got, [expect.mean()] * 3, atol=0.015), (face, got, expect.mean())
+    assert seen >= 2
