@@ -565,3 +565,27 @@ def test_reference_inconsistencies_between_sample_and_evaluate(bundle_factory, g
     body = eroded(be.hit_mask()[0])
     pt, nee = [float(np.median(be.film(i, 64)[body] @ lum_w)) for i in ("pt", "nee")]
     assert nee > 3.0 * pt, (pt, nee)
+
+
+# ------------------------------------------------------------------ output transform (sensor.rs:81-88, tone_map.rs:20-28, color/src/eotf.rs:51-72, renderer.rs:140-144)
+@pytest.mark.parametrize("gpu", CPU_GPU)
+def test_output_transform_from_the_accumulators(bundle_factory, gpu):
+    """`pixels` = sRGB OETF(Reinhard(max(accumulator / spp, 0))) and the PNG byte = trunc(v * 255): written out in float64 numpy from the
+    IEC 61966-2-1 definition and applied to the accumulators either implementation returns."""
+    be = backend(bundle_factory, lamp_over_floor, gpu)
+    b = be.b
+    spp = 16
+    if gpu:
+        im = b.image("mis", spp).render("sobol")
+        acc, srgb = im.accumulators, im.pixels
+        u8 = im.to_u8()
+    else:
+        acc, srgb, _ = b.oracle.render(b.oparams("mis", "sobol", spp))
+        u8 = np.clip(np.nan_to_num(srgb * np.float32(255.0), nan=0.0), 0, 255).astype(np.uint8)
+    c = np.maximum(acc.astype(np.float64) / spp, 0.0)
+    c = c / (1.0 + c)
+    expect = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1.0 / 2.4) - 0.055)
+    assert np.abs(srgb - expect).max() < 2e-6
+    assert srgb.min() >= 0.0 and srgb.max() < 1.0 and (srgb > 0.5).any() and (srgb < 0.05).any()   # the lamp and the dark floor rim are both in frame
+    # truncating quantiser: never rounds up
+    assert np.array_equal(u8, np.floor(srgb * np.float32(255.0)).astype(np.uint8))      # f32 product, like `(v * 255.0) as u8`
