@@ -56,7 +56,7 @@ class Bvh {
     bool intersect(const Ray& ray, float t_max, ItemFn&& item_fn, float* t_out, uint64_t* payload_out, TraversalCounters* ctr) const {
         if (nodes.empty()) return false;
         Vec3 inv_dir(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
-        Cand c = traverse(0, ray, t_max, inv_dir, item_fn, ctr);
+        Cand c = shrink ? traverse_shrink(0, ray, t_max, inv_dir, item_fn, ctr) : traverse(0, ray, t_max, inv_dir, item_fn, ctr);
         if (!c.hit) return false;
         *t_out = c.t;
         *payload_out = c.payload;
@@ -69,6 +69,12 @@ class Bvh {
         Vec3 inv_dir(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
         return traverse_p(0, ray, t_max, inv_dir, item_fn, ctr);
     }
+
+    // "optimised CPU" cost model for bench.py's cpu_baseline only: near child first, the far child and its triangles see
+    // t_max shrunk to the best hit so far.  The combine rules are the reference's (node ties -> second child, leaf ties -> earlier
+    // item) and equal-t candidates still pass the shrunk bound, so the hit is the reference's except when a candidate's scaled-t
+    // comparison rounds differently against the tighter t_max.  Parity tests never use this mode.
+    bool shrink = false;
 
    private:
     const std::vector<Bounds>* ib_ = nullptr;
@@ -187,6 +193,70 @@ class Bvh {
             }
         }
         return best;
+    }
+
+    static bool slab_entry(const Bounds& b, const Ray& ray, float t_max, Vec3 inv_dir, float* t_entry) {
+        float t0 = 0.0f, t1 = t_max;
+        for (int i = 0; i < 3; ++i) {
+            float t_near = (b.mn[i] - ray.o[i]) * inv_dir[i];
+            float t_far = (b.mx[i] - ray.o[i]) * inv_dir[i];
+            if (t_near > t_far) { float t = t_near; t_near = t_far; t_far = t; }
+            t0 = t_near > t0 ? t_near : t0;
+            t1 = t_far < t1 ? t_far : t1;
+            if (t0 > t1) return false;
+        }
+        *t_entry = t0;
+        return true;
+    }
+    // the node's own box has been tested by the caller
+    template <class ItemFn>
+    Cand traverse_shrink_in(size_t index, const Ray& ray, float t_max, Vec3 inv_dir, ItemFn& item_fn, TraversalCounters* ctr) const {
+        const FlatNode& n = nodes[index];
+        if (n.kind == NODE_INNER) {
+            const size_t i1 = index + 1, i2 = index + n.value;
+            float e1 = 0, e2 = 0;
+            if (ctr) ctr->box_tests += 2;
+            const bool h1 = slab_entry(nodes[i1].bounds, ray, t_max, inv_dir, &e1), h2 = slab_entry(nodes[i2].bounds, ray, t_max, inv_dir, &e2);
+            Cand first, second;
+            if (h1 && h2) {
+                if (e2 < e1) {
+                    second = traverse_shrink_in(i2, ray, t_max, inv_dir, item_fn, ctr);
+                    const float lim = second.hit ? second.t : t_max;
+                    if (!second.hit || e1 <= lim) first = traverse_shrink_in(i1, ray, lim, inv_dir, item_fn, ctr);
+                } else {
+                    first = traverse_shrink_in(i1, ray, t_max, inv_dir, item_fn, ctr);
+                    const float lim = first.hit ? first.t : t_max;
+                    if (!first.hit || e2 <= lim) second = traverse_shrink_in(i2, ray, lim, inv_dir, item_fn, ctr);
+                }
+            } else if (h1) first = traverse_shrink_in(i1, ray, t_max, inv_dir, item_fn, ctr);
+            else if (h2) second = traverse_shrink_in(i2, ray, t_max, inv_dir, item_fn, ctr);
+            if (first.hit && second.hit) return first.t < second.t ? first : second;
+            if (first.hit) return first;
+            return second;
+        }
+        Cand best;
+        float lim = t_max;
+        for (uint32_t i = 1; i <= n.value; ++i) {
+            uint32_t item = nodes[index + i].value;
+            float t;
+            uint64_t payload;
+            if (ctr) ctr->tri_tests++;
+            if (item_fn(item, lim, &t, &payload)) {
+                if (best.hit) {
+                    if (t < best.t) { best = Cand{true, t, payload}; lim = t; }
+                } else {
+                    best = Cand{true, t, payload}; lim = t;
+                }
+            }
+        }
+        return best;
+    }
+    template <class ItemFn>
+    Cand traverse_shrink(size_t index, const Ray& ray, float t_max, Vec3 inv_dir, ItemFn& item_fn, TraversalCounters* ctr) const {
+        float e;
+        if (ctr) ctr->box_tests++;
+        if (!slab_entry(nodes[index].bounds, ray, t_max, inv_dir, &e)) return Cand{};
+        return traverse_shrink_in(index, ray, t_max, inv_dir, item_fn, ctr);
     }
 
     template <class ItemFn>

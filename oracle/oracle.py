@@ -45,7 +45,7 @@ def lib() -> C.CDLL:
         _lib.orc_scene_new.restype = C.c_void_p
         _lib.orc_build.restype = C.c_double
         for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_add_single_triangle", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
-                     "orc_add_env_light", "orc_add_delta_light", "orc_set_modes", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
+                     "orc_add_env_light", "orc_add_delta_light", "orc_set_modes", "orc_set_optimised", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
                      "orc_sampler_stream", "orc_get_bvh", "orc_get_mesh_tangents"):
             getattr(_lib, name).argtypes = None
     return _lib
@@ -109,6 +109,10 @@ class OracleScene:
     def build(self, cam_pos) -> float:
         a = np.asarray(cam_pos, dtype=f32)
         return self.l.orc_build(_vp(self.h), _p(a))
+
+    def set_optimised(self, on: bool = True):
+        """bench.py only: ordered, t-shrinking traversal + cached inverses (the "optimised CPU" figure of SURVEY 8d); call after build()."""
+        self.l.orc_set_optimised(_vp(self.h), int(on))
 
     # --- queries
     @staticmethod

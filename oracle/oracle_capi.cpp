@@ -193,6 +193,14 @@ int orc_add_delta_light(void* h, int kind, float intensity, const orc_spectrum_p
 
 // faithful = reference cost model (exhaustive traversal is always used; this adds per-call inverses/attribute work);
 // literal_build = O(N^2) SAH sweep exactly as the reference, else the prefix/suffix sweep (bit-identical result)
+// bench.py's "optimised CPU" figure: ordered, t-shrinking traversal in the TLAS and every BLAS, cached instance inverses (see Bvh::shrink).
+// Call after orc_build.
+void orc_set_optimised(void* h, int on) {
+    OrcScene* s = (OrcScene*)h;
+    s->scene.tlas.shrink = on != 0;
+    for (auto& m : s->scene.meshes) m.bvh.shrink = on != 0;
+    if (on) s->scene.faithful = false;
+}
 void orc_set_modes(void* h, int faithful, int literal_build) { OrcScene* s = (OrcScene*)h; s->scene.faithful = faithful != 0; s->scene.literal_build = literal_build != 0; }
 
 double orc_build(void* h, const float cam_pos[3]) {

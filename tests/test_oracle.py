@@ -50,3 +50,23 @@ def test_failed_samples_and_specular_paths_follow_the_reference_rules(bundle_fac
     assert pt["shadow_rays"] == 0 and 0 < nee["shadow_rays"] < nee["closest_rays"]
     # every path starts with one camera ray; NEE draws extra sampler dimensions, so later decisions differ between pt and nee
     assert pt["closest_rays"] > pt["paths"] and nee["closest_rays"] > nee["paths"]
+
+
+import pytest
+
+
+@pytest.mark.parametrize("scene_id", [3, 17, 19])
+def test_optimised_cpu_mode_renders_the_same_film(bundle_factory, tables, scene_id):
+    """bench.py's "optimised CPU" figure (ordered, t-shrinking traversal, cached instance inverses: oracle.set_optimised) must be the same
+    computation with fewer box and triangle tests, not another renderer: same film to the bit, same ray counts, fewer tests."""
+    import numpy as np
+    from oracle import oracle
+    b = bundle_factory(scene_id, 64, 48, require_gpu=False)
+    p = b.oparams("mis", "sobol", 8)
+    acc, _, st = b.oracle.render(p)
+    fast = oracle.scene_from_description(b.scene.desc, b.camera.position, tables[0], tables[1])
+    fast.set_optimised(True)
+    acc2, _, st2 = fast.render(fast.params(64, 48, 8, "mis", "sobol", b.camera))
+    assert np.array_equal(acc.view(np.uint32), acc2.view(np.uint32))
+    assert (st["closest_rays"], st["shadow_rays"]) == (st2["closest_rays"], st2["shadow_rays"])
+    assert st2["box_tests"] < st["box_tests"] and st2["tri_tests"] <= st["tri_tests"]
