@@ -171,6 +171,10 @@ int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uin
 /* which = -1: TLAS, else geometry index.  Records of 8 x u32 in the REFERENCE's flattened order (bvh.rs:234-295):
  * {kind 0 inner|1 leaf|2 item, value = second_offset|item_count|item, min.xyz bits, max.xyz bits}.  Returns the node count. */
 int tcpt_get_bvh(tcpt_ctx* ctx, int which, uint32_t* out, int max_nodes);
+/* the DEVICE layout of the same BVH (include/tcpt_flat.h): 4-wide records of 32 x u32 (rows lo.x hi.x lo.y hi.y lo.z hi.z entries counts).
+ * Entries are absolute: *first_record = index of record 0 of this BVH in the flat node array, *slot_base = its first item slot.
+ * Returns the record count.  The tests check that every reference leaf survives the collapse with its box bits and item order. */
+int tcpt_get_wide_bvh(tcpt_ctx* ctx, int which, uint32_t* out, int max_records, uint32_t* first_record, uint32_t* slot_base);
 int tcpt_build_bvh_boxes(const float* boxes /*n x {min[3],max[3]}*/, int n, uint32_t* out, int max_nodes); /* builder alone, no device */
 int tcpt_rgb_to_coeffs(tcpt_ctx* ctx, const float rgb[3], int gamma_encoded, float coeffs[3], int32_t index[4] /*m,zi,yi,xi*/);
 int tcpt_get_mesh_tangents(tcpt_ctx* ctx, int geometry, float* out, int max_triangles);

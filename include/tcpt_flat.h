@@ -4,17 +4,24 @@
  * builder in csrc/host_scene.cpp which stands in for it here) produces one tcpt_flat_scene and hands it to
  * tcpt_upload_flat_scene(); everything device-side reads only these arrays.
  *
- * BVH nodes (TLAS and all BLAS, concatenated) are 64-byte CHILD-PAIR records fetched as four 16-byte loads.  One record per
- * inner node of the reference tree, holding the boxes of BOTH children, so one fetch decides both slab tests:
- *     q0 = {lo0.xyz, bits(ref0)}   q1 = {hi0.xyz, bits(cnt0)}   q2 = {lo1.xyz, bits(ref1)}   q3 = {hi1.xyz, bits(cnt1)}
- *     child k inner : cnt_k == 0, ref_k = index of the child's own pair record (relative to the BVH's node_base)
- *     child k leaf  : cnt_k  > 0 = item_count, ref_k = first item slot (relative to slot_base)   [scene/src/bvh.rs:271-286]
- *     child k absent: cnt_k == 0, ref_k = 0xffffffff
- * Record 0 of every BVH is an entry record {child0 = the root (inner or leaf) with the ROOT box, child1 = absent}, so the root
- * box is tested like the reference does (bvh.rs:362).  Records are emitted in the reference's pre-order of inner nodes
- * (bvh.rs:234-295 with leaf/item records removed); item slots enumerate leaf items in the reference's leaf order, so
- * "later leaf in DFS order" == larger first-slot.  The tree SHAPE, every box and every per-leaf item order are the
- * reference's; only the storage differs (tcpt_get_bvh() returns the reference's own flattened order for comparison).
+ * BVH nodes (TLAS and all BLAS, concatenated) are 128-byte 4-WIDE records fetched as 16-byte rows.  A record holds up to four
+ * children of a 4-wide COLLAPSE of the reference's binary tree (scene/src/bvh.rs:92-295): starting from a binary node's two
+ * children, the largest-area inner child is replaced by its own two children until four are held (DFS order is kept):
+ *     row 0 = lo.x of children 0..3   row 1 = hi.x   row 2 = lo.y   row 3 = hi.y   row 4 = lo.z   row 5 = hi.z
+ *     row 6 = entry of children 0..3  row 7 = item count of children 0..3 (0 for inner / absent children; informational)
+ *     entry, inner child : index of the child's own record in bvh_nodes (ABSOLUTE, < 2^31)
+ *     entry, leaf child  : 0x80000000 | (item_count - 1) << 27 | first item slot (ABSOLUTE into tri_verts / tlas_items, < 2^27 - 1),
+ *                          item_count <= 16                                                     [scene/src/bvh.rs:271-286]
+ *     entry, absent child: 0xffffffff, box = (+inf, -inf)
+ * so that the near / far planes of all four children along one axis are two adjacent 16-byte rows (picked by the sign of the ray
+ * direction) and an entry is what the traversal stack holds.  Every reference LEAF is kept with its own box bits and its item
+ * order; a reference leaf of more than 16 items becomes a record of up to four item ranges that all carry the leaf's box (nested
+ * for more than 64).  Reference inner boxes that end up interior to a record are not stored: an inner box is the exact min / max
+ * merge of the boxes below it and the slab test is monotone in the box, so a ray that passes a leaf box passes every ancestor
+ * box -- the leaves reached, hence the candidates, are the reference's (csrc/dtraverse.cuh).  Record 0 of the array is
+ * the TLAS root; tcpt_flat_geometry.node_base is the BLAS root record.  A BVH whose root is a leaf is one record with one child.
+ * Records are emitted in pre-order; item slots enumerate leaf items in the reference's leaf order, so "later leaf in DFS order" ==
+ * larger first-slot (tcpt_get_bvh() returns the reference's own flattened order for comparison).
  * BLAS items are stored pre-gathered: tri_verts[3*slot+k] = {p_k.xyz, bits(w_k)} with w_0 = triangle index,
  * w_1 = degenerate flag (|e1 x e2|^2 == 0, math/src/ray.rs:50-57), w_2 = first slot of the leaf holding this slot.
  * TLAS items: tlas_items[2*slot] = primitive index, tlas_items[2*slot+1] = first slot of the leaf holding this slot.
@@ -30,13 +37,13 @@ extern "C" {
 #endif
 
 #define TCPT_MAX_LIGHTS 16
-#define TCPT_TRAVERSAL_STACK 64
+#define TCPT_TRAVERSAL_STACK 96
 
-typedef struct { float q[16]; } tcpt_bvh_node; /* 4 x float4, see above */
+typedef struct { float q[32]; } tcpt_bvh_node; /* 8 rows x 4 children, see above */
 
 typedef struct {
-    uint32_t node_base, node_count;   /* into bvh_nodes */
-    uint32_t slot_base, tri_count;    /* into tri_verts (x3) */
+    uint32_t node_base, node_count;   /* into bvh_nodes: the BLAS root record, number of records */
+    uint32_t slot_base, tri_count;    /* into tri_verts (x3): first item slot */
     uint32_t vertex_base;             /* into positions/normals/uvs */
     uint32_t index_base;              /* into indices (x3 per triangle) */
     uint32_t tangent_base;            /* into tangents (per triangle), valid when has_uv */
@@ -108,7 +115,7 @@ typedef struct {
     const tcpt_flat_env* envs; uint32_t n_envs;
     const float* env_floats; uint64_t n_env_floats;
     const uint32_t* env_guides; uint64_t n_env_guides;
-    uint32_t max_bvh_depth;                 /* TLAS depth + largest TLAS leaf + deepest BLAS depth, must be < TCPT_TRAVERSAL_STACK */
+    uint32_t max_bvh_depth;                 /* worst-case height of the traversal stack (siblings waiting along the deepest TLAS path + 1 + the same in the deepest BLAS), must be < TCPT_TRAVERSAL_STACK */
 } tcpt_flat_scene;
 
 /* copies everything to the device owned by ctx; replaces any previously uploaded scene */

@@ -20,7 +20,7 @@ class OrcRenderParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("seed", C.c_uint32), ("max_depth", C.c_uint32),
                 ("integrator", C.c_int32), ("sampler", C.c_int32), ("exposure", C.c_float), ("fov_deg", C.c_float),
                 ("cam_pos", C.c_float * 3), ("cam_dir", C.c_float * 3), ("cam_up", C.c_float * 3), ("threads", C.c_int32),
-                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32)]
+                ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32), ("y1", C.c_uint32), ("stride", C.c_uint32)]
 
 
 class OrcStats(C.Structure):
@@ -116,7 +116,7 @@ class OracleScene:
 
     # --- queries
     @staticmethod
-    def params(width, height, spp, integrator, sampler, camera, seed=0, max_depth=16, exposure=1.0, threads=0, window=(0, 0, 0, 0)) -> OrcRenderParams:
+    def params(width, height, spp, integrator, sampler, camera, seed=0, max_depth=16, exposure=1.0, threads=0, window=(0, 0, 0, 0), stride=1) -> OrcRenderParams:
         p = OrcRenderParams()
         p.width, p.height, p.spp, p.seed, p.max_depth = width, height, spp, seed, max_depth
         p.integrator = {"pt": 0, "nee": 1, "mis": 2, "albedo": 3, "normal": 4}[integrator]
@@ -125,6 +125,7 @@ class OracleScene:
         for k in range(3):
             p.cam_pos[k], p.cam_dir[k], p.cam_up[k] = float(camera.position[k]), float(camera.direction[k]), float(camera.up[k])
         p.x0, p.y0, p.x1, p.y1 = window
+        p.stride = stride
         return p
 
     def render(self, p: OrcRenderParams):

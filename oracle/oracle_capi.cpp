@@ -2,6 +2,7 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can drive it through ctypes.
 // The product library (toy_cpu_pathtracing_b200/csrc) never links or calls anything in this directory.
 // PARITY UNPINNED below the Sobol known-answer vectors: the Rust reference cannot be built here.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -33,6 +34,7 @@ typedef struct {
     float cam_pos[3], cam_dir[3], cam_up[3];
     int32_t threads;
     uint32_t x0, y0, x1, y1;  // pixel window (0,0,0,0 = full frame)
+    uint32_t stride;          // > 1: only every stride-th pixel of the window in x and in y is rendered (a sparse sample of the WHOLE frame for bench.py)
 } orc_render_params;
 
 typedef struct {
@@ -224,10 +226,11 @@ int orc_render(void* h, const orc_render_params* p, float* out_acc, float* out_s
     RayStats rs;
     int threads = p->threads > 0 ? p->threads : (int)std::thread::hardware_concurrency();
     auto t0 = std::chrono::steady_clock::now();
-    pt.render(out_acc, out_srgb, threads, &rs, p->x0, p->y0, p->x1, p->y1);
+    const uint32_t stride = p->stride > 1 ? p->stride : 1;
+    pt.render(out_acc, out_srgb, threads, &rs, p->x0, p->y0, p->x1, p->y1, stride);
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (stats) {
-        uint32_t rw = (p->x1 ? p->x1 : p->width) - p->x0, rh = (p->y1 ? p->y1 : p->height) - p->y0;
+        uint32_t rw = ((p->x1 ? p->x1 : p->width) - p->x0 + stride - 1) / stride, rh = ((p->y1 ? p->y1 : p->height) - p->y0 + stride - 1) / stride;
         stats->closest_rays = rs.closest; stats->shadow_rays = rs.shadow; stats->paths = (uint64_t)rw * rh * p->spp;
         stats->box_tests = rs.tc.box_tests; stats->tri_tests = rs.tc.tri_tests; stats->seconds = sec;
     }
@@ -238,13 +241,32 @@ int orc_render(void* h, const orc_render_params* p, float* out_acc, float* out_s
 int orc_path_samples(void* h, const orc_render_params* p, const uint32_t* pixels_xy, const uint32_t* sample_indices, int n, float* out_rgb) {
     OrcScene* s = (OrcScene*)h;
     Camera cam = make_camera(p);
-    PathTracer pt(s->scene, cam, make_rp(p));
-    std::unique_ptr<SamplerBase> smp;
-    if (p->sampler == SAMPLER_SOBOL) smp.reset(new ZSobolSampler(s->scene.T.sobol, p->spp, p->width, p->height, p->seed));
-    else smp.reset(new RandomSampler(p->seed));
-    for (int i = 0; i < n; ++i) {
-        Vec3 c = pt.trace_path(*smp, pixels_xy[2 * i], pixels_xy[2 * i + 1], sample_indices[i], nullptr);
-        out_rgb[3 * i] = c.x; out_rgb[3 * i + 1] = c.y; out_rgb[3 * i + 2] = c.z;
+    // every (pixel, sample) path is a pure function of its coordinates: the list is cut into blocks handed to worker threads
+    // (p->threads, 0 = all cores), each with its own sampler and tracer state; the values do not depend on the thread count
+    int threads = p->threads > 0 ? p->threads : (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (n < 2048) threads = 1;
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        PathTracer pt(s->scene, cam, make_rp(p));
+        std::unique_ptr<SamplerBase> smp;
+        if (p->sampler == SAMPLER_SOBOL) smp.reset(new ZSobolSampler(s->scene.T.sobol, p->spp, p->width, p->height, p->seed));
+        else smp.reset(new RandomSampler(p->seed));
+        for (;;) {
+            const int b = next.fetch_add(1024);
+            if (b >= n) break;
+            const int e = b + 1024 < n ? b + 1024 : n;
+            for (int i = b; i < e; ++i) {
+                Vec3 c = pt.trace_path(*smp, pixels_xy[2 * i], pixels_xy[2 * i + 1], sample_indices[i], nullptr);
+                out_rgb[3 * i] = c.x; out_rgb[3 * i + 1] = c.y; out_rgb[3 * i + 2] = c.z;
+            }
+        }
+    };
+    if (threads == 1) work();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
     }
     return 0;
 }

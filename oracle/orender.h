@@ -339,10 +339,10 @@ struct PathTracer {
     }
 
     // RendererImage::render (renderer.rs:120-134): dynamic per-pixel scheduling over `threads` host threads
-    void render(float* out_acc, float* out_srgb, int threads, RayStats* total, uint32_t x0 = 0, uint32_t y0 = 0, uint32_t x1 = 0, uint32_t y1 = 0) const {
+    void render(float* out_acc, float* out_srgb, int threads, RayStats* total, uint32_t x0 = 0, uint32_t y0 = 0, uint32_t x1 = 0, uint32_t y1 = 0, uint32_t stride = 1) const {
         if (x1 == 0) x1 = rp.width;
         if (y1 == 0) y1 = rp.height;
-        uint32_t rw = x1 - x0, rh = y1 - y0;
+        uint32_t rw = (x1 - x0 + stride - 1) / stride, rh = (y1 - y0 + stride - 1) / stride;   // pixels x0, x0 + stride, ... of the window
         std::atomic<uint32_t> next{0};
         std::vector<RayStats> stats(threads);
         auto work = [&](int tid) {
@@ -352,7 +352,7 @@ struct PathTracer {
             for (;;) {
                 uint32_t i = next.fetch_add(1);
                 if (i >= rw * rh) break;
-                uint32_t px = x0 + i % rw, py = y0 + i / rw;
+                uint32_t px = x0 + (i % rw) * stride, py = y0 + (i / rw) * stride;
                 Vec3 acc(0, 0, 0);
                 for (uint32_t s = 0; s < rp.spp; ++s) acc = acc + trace_path(*smp, px, py, s, &stats[tid]);
                 size_t o = ((size_t)py * rp.width + px) * 3;

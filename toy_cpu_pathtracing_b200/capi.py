@@ -74,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "tcpt_scene_add_mesh", "tcpt_scene_add_single_triangle", "tcpt_scene_add_texture", "tcpt_scene_add_material", "tcpt_scene_add_primitive",
     "tcpt_scene_add_env_light", "tcpt_scene_add_delta_light", "tcpt_scene_build", "tcpt_render", "tcpt_render_device", "tcpt_finalize_device",
     "tcpt_get_stats", "tcpt_trace", "tcpt_trace_device", "tcpt_sampler_stream", "tcpt_path_samples", "tcpt_get_bvh",
-    "tcpt_build_bvh_boxes", "tcpt_rgb_to_coeffs", "tcpt_get_mesh_tangents", "tcpt_upload_flat_scene",
+    "tcpt_get_wide_bvh", "tcpt_build_bvh_boxes", "tcpt_rgb_to_coeffs", "tcpt_get_mesh_tangents", "tcpt_upload_flat_scene",
 ]
 
 _lib = None
@@ -107,7 +107,7 @@ def load_library() -> C.CDLL:
         "tcpt_trace_device": (I, [P, C.c_void_p, I, I, C.c_void_p, C.c_void_p]),
         "tcpt_sampler_stream": (I, [P, I, U, U, U, U, U, U, U, ip, I, fp]),
         "tcpt_path_samples": (I, [P, C.POINTER(RenderParams), up, up, I, fp]),
-        "tcpt_get_bvh": (I, [P, I, up, I]), "tcpt_build_bvh_boxes": (I, [fp, I, up, I]),
+        "tcpt_get_bvh": (I, [P, I, up, I]), "tcpt_get_wide_bvh": (I, [P, I, up, I, up, up]), "tcpt_build_bvh_boxes": (I, [fp, I, up, I]),
         "tcpt_rgb_to_coeffs": (I, [P, fp, I, fp, ip]), "tcpt_get_mesh_tangents": (I, [P, I, fp, I]),
     }
     for name, (res, args) in sig.items():

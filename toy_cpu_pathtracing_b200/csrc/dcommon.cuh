@@ -98,7 +98,7 @@ struct DEnv {
     float intensity, total_weight; uint32_t w, h; tcpt_flat_spectrum integrated; int32_t primitive;
 };
 struct DScene {
-    const float4* nodes;            // 4 x float4 per child-pair record (include/tcpt_flat.h)
+    const float4* nodes;            // 8 x float4 per 4-wide record (include/tcpt_flat.h)
     const int2* tlas_items;         // {primitive, leaf_first_slot}
     const float4* tri_verts;        // 3 x float4 per slot
     const float* positions; const float* normals; const float* uvs; const uint32_t* indices; const float* tangents;

@@ -1,36 +1,36 @@
 // Two-level BVH traversal on the device (software; B200 has no RT cores).
 //
 // Reproduces the RESULT of the reference's exhaustive recursive traversal (/root/reference/scene/src/bvh.rs:344-520) with an
-// ordered, t-shrinking, stack-based walk over 64-byte child-pair records (include/tcpt_flat.h):
-//   * slab test = math/src/bounds.rs:27-55, same operations in the same order (sub, mul, compare-selects; no FMA);
+// ordered, t-shrinking, stack-based walk over a 4-WIDE COLLAPSE of the reference's binary tree (include/tcpt_flat.h):
+//   * slab test = math/src/bounds.rs:27-55.  Rays whose origin and reciprocal direction are finite take a NaN-free form of it
+//     (near / far plane picked by the direction's sign, 3-input min / max) that is the same function on those inputs (see
+//     slab4_fast); axis-parallel rays (an infinite reciprocal: 0 * inf = NaN is then possible and the reference's
+//     compare-selects ignore NaNs in a particular way) run the reference's own sequence of operations (slab_exact);
 //   * triangle test = math/src/ray.rs:44-158 (watertight shear, f64 fallback when an edge function is 0, conservative t > delta_t);
 //   * instance transform = primitive/impls/triangle_mesh.rs:97 (ray parameter t preserved, direction not re-normalised);
 //   * the reference never shrinks t_max and keeps candidates by  Node: ties -> second child,  Leaf: ties -> earlier item
 //     (bvh.rs:384-388, 413-420).  That is the total order  (t, later leaf first, earlier item first)  applied per level
 //     (TLAS, then BLAS), so any visiting order that sees every candidate the winner competes with gives the same hit.
-//     Every box on the path to a candidate is tested with the reference's own slab arithmetic, so the candidate set is a
-//     subset of the reference's; boxes are additionally culled against  t_best * (1 + 2^-10) + 2^-10  instead of t_best:
-//     the slab interval of a box and the watertight t of a triangle inside it are rounded independently, so the margin keeps
-//     every box that could still hold an equal-or-smaller t (the triangle test itself always runs with the caller's t_max).
+//
+// Why a wide tree sees the same candidates ("containment").  A candidate of the reference is an item of a
+// LEAF whose own box and all of whose ancestors' boxes pass Bounds::intersect.  Every inner box is the exact component-wise
+// min / max of the boxes below it (bvh.rs:83-89: a fold of `merge`, and min / max do not round), and the slab test is monotone in
+// the box: (b - o) * inv_d is a composition of correctly rounded, hence monotone, operations, so enlarging the box can only lower
+// t0 and raise t1, axis by axis (a NaN on an axis drops that axis' constraint, which is weaker still).  A ray that passes a leaf
+// box therefore passes every ancestor box: testing the LEAF boxes alone, with the reference's arithmetic, yields exactly the
+// reference's candidate set, whatever inner boxes are tested (or skipped) on the way down.  The wide tree keeps every reference
+// leaf, its box bits and its item order; inner boxes of the reference that became interior to a wide node are simply not tested.
+// Boxes are additionally culled against  t_best * (1 + 2^-10) + 2^-10  instead of t_best: the slab interval of a box and the
+// watertight t of a triangle inside it are rounded independently, so the margin (empirical, not derived: the bit-exact hit tests
+// are its gate) keeps every box that could still hold an equal-or-smaller t; the triangle test always runs with the caller's t_max.
 #pragma once
 #include "dcommon.cuh"
 
-// Three micro-variants of the walk, measured one by one on the 4K frame and left off (trace 46.1 ms per step without them):
-//   TCPT_OPT_TOS    top stack entry in a register, so a pop does not wait for local memory           46.7 ms
-//   TCPT_OPT_RL     one "current ray" record restored at BLAS exit instead of a per-visit select     46.6 ms
-//   TCPT_OPT_BALLOT idle lanes derived from the next iteration's two masks (one ballot less)         46.5 ms
-// Each removes instructions from the loop but moves the 72-register allocation to a worse place.
-#ifndef TCPT_OPT_TOS
-#define TCPT_OPT_TOS 0
+#ifndef TCPT_SORT_FULL
+#define TCPT_SORT_FULL 1          // 1: the hit children of a wide node are visited nearest first, the rest pushed far to near; 0: nearest first, rest unordered
 #endif
-#ifndef TCPT_OPT_RL
-#define TCPT_OPT_RL 0
-#endif
-#ifndef TCPT_OPT_BALLOT
-#define TCPT_OPT_BALLOT 0
-#endif
-#ifndef TCPT_SPECULATE
-#define TCPT_SPECULATE 0          // 1: walk one leaf ahead of the triangle tests (Aila & Laine postponed leaf); measured 6 % slower (3.52 vs 3.32 ms/spp)
+#ifndef TCPT_SMEM_STACK
+#define TCPT_SMEM_STACK 0         // traversal-stack entries kept in shared memory (the rest, or all of them when 0, live in local memory)
 #endif
 
 namespace tcpt {
@@ -43,9 +43,12 @@ struct DHit {
 
 struct RayXform {  // per-space ray constants for the slab and watertight tests (math/src/ray.rs:63-78)
     float3 o, inv_d;
-    int kz;
+    int kz;        // bits 0-1: the shear axis; bits 4-6: byte offsets (0 | 16) of the NEAR plane vector inside an axis pair of a wide node, x y z;
+                   // bit 8: the ray takes the NaN-free slab test
     float sx, sy, sz;
 };
+
+#define TCPT_RAY_FAST 0x100
 
 __device__ __forceinline__ void ray_setup(RayXform& r, float3 o, float3 d) {
     r.o = o;
@@ -54,26 +57,36 @@ __device__ __forceinline__ void ray_setup(RayXform& r, float3 o, float3 d) {
     int kz = 0; float m = ax;
     if (ay > m) { m = ay; kz = 1; }
     if (az > m) { kz = 2; }
-    r.kz = kz;
     const float dx = kz == 0 ? d.y : (kz == 1 ? d.z : d.x), dy = kz == 0 ? d.z : (kz == 1 ? d.x : d.y), dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
     r.sx = -dx / dz; r.sy = -dy / dz; r.sz = 1.0f / dz;
+    // finite origin and finite reciprocal direction: no product of the slab test can be NaN (0 * inf needs an infinity)
+    const bool fast = fabsf(r.inv_d.x) < TCPT_INF && fabsf(r.inv_d.y) < TCPT_INF && fabsf(r.inv_d.z) < TCPT_INF &&
+                      fabsf(o.x) < TCPT_INF && fabsf(o.y) < TCPT_INF && fabsf(o.z) < TCPT_INF;
+    r.kz = kz | (r.inv_d.x < 0.0f ? 0x10 : 0) | (r.inv_d.y < 0.0f ? 0x20 : 0) | (r.inv_d.z < 0.0f ? 0x40 : 0) | (fast ? TCPT_RAY_FAST : 0);
+}
+// the origin moved into another space with the direction bits unchanged: everything but `o` and the fast flag carries over
+__device__ __forceinline__ void ray_move_origin(RayXform& r, float3 o) {
+    r.o = o;
+    const bool fin = fabsf(o.x) < TCPT_INF && fabsf(o.y) < TCPT_INF && fabsf(o.z) < TCPT_INF &&
+                     fabsf(r.inv_d.x) < TCPT_INF && fabsf(r.inv_d.y) < TCPT_INF && fabsf(r.inv_d.z) < TCPT_INF;
+    r.kz = (r.kz & ~TCPT_RAY_FAST) | (fin ? TCPT_RAY_FAST : 0);
 }
 
-// Bounds::intersect; NaNs (0 * inf) are ignored by the ordered compare-selects exactly as in the reference
-__device__ __forceinline__ bool slab_test(const float4 lo, const float4 hi, const RayXform& r, float t_max, float* t_entry) {
+// Bounds::intersect as written (bounds.rs:35-52); NaNs (0 * inf) are ignored by the ordered compare-selects exactly as in the reference
+__device__ __forceinline__ bool slab_exact(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayXform& r, float t_max, float* t_entry) {
     float t0 = 0.0f, t1 = t_max;
     {
-        float tn = (lo.x - r.o.x) * r.inv_d.x, tf = (hi.x - r.o.x) * r.inv_d.x;
+        float tn = (lox - r.o.x) * r.inv_d.x, tf = (hix - r.o.x) * r.inv_d.x;
         if (tn > tf) { const float s = tn; tn = tf; tf = s; }
         t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
     }
     {
-        float tn = (lo.y - r.o.y) * r.inv_d.y, tf = (hi.y - r.o.y) * r.inv_d.y;
+        float tn = (loy - r.o.y) * r.inv_d.y, tf = (hiy - r.o.y) * r.inv_d.y;
         if (tn > tf) { const float s = tn; tn = tf; tf = s; }
         t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
     }
     {
-        float tn = (lo.z - r.o.z) * r.inv_d.z, tf = (hi.z - r.o.z) * r.inv_d.z;
+        float tn = (loz - r.o.z) * r.inv_d.z, tf = (hiz - r.o.z) * r.inv_d.z;
         if (tn > tf) { const float s = tn; tn = tf; tf = s; }
         t0 = tn > t0 ? tn : t0; t1 = tf < t1 ? tf : t1;
     }
@@ -88,8 +101,9 @@ __device__ __forceinline__ bool tri_test(const float4 v0, const float4 v1, const
     const float bx = v1.x - r.o.x, by = v1.y - r.o.y, bz = v1.z - r.o.z;
     const float cx = v2.x - r.o.x, cy = v2.y - r.o.y, cz = v2.z - r.o.z;
     float p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z;
-    if (r.kz == 0) { p0x = ay; p0y = az; p0z = ax; p1x = by; p1y = bz; p1z = bx; p2x = cy; p2y = cz; p2z = cx; }
-    else if (r.kz == 1) { p0x = az; p0y = ax; p0z = ay; p1x = bz; p1y = bx; p1z = by; p2x = cz; p2y = cx; p2z = cy; }
+    const int kz = r.kz & 3;
+    if (kz == 0) { p0x = ay; p0y = az; p0z = ax; p1x = by; p1y = bz; p1z = bx; p2x = cy; p2y = cz; p2z = cx; }
+    else if (kz == 1) { p0x = az; p0y = ax; p0z = ay; p1x = bz; p1y = bx; p1z = by; p2x = cz; p2y = cx; p2z = cy; }
     else { p0x = ax; p0y = ay; p0z = az; p1x = bx; p1y = by; p1z = bz; p2x = cx; p2y = cy; p2z = cz; }
     p0x += r.sx * p0z; p0y += r.sy * p0z;
     p1x += r.sx * p1z; p1y += r.sy * p1z;
@@ -129,153 +143,192 @@ __device__ __forceinline__ bool tri_test(const float4 v0, const float4 v1, const
 
 __device__ __forceinline__ float cull_limit(float t_best) { return t_best * 1.0009765625f + 0.0009765625f; }
 
-#define TCPT_TLAS_ITEM_BIT 0x80000000u
-#define TCPT_ABSENT 0xffffffffu
+// ---- stack / child entries (include/tcpt_flat.h): bit 31 = leaf range {bits 27-30: count - 1, bits 0-26: first item slot}, else a wide-node index
+// (a reference leaf of more than 16 items is cut into ranges by the host, all under the leaf's own box: same box test, same candidates)
+#define TCPT_ENTRY_LEAF 0x80000000u
+#define TCPT_ENTRY_NONE 0xffffffffu
+#define TCPT_ENTRY_SLOT_MASK 0x07ffffffu
+#define TCPT_ENTRY_ONE_ITEM (1u - (1u << 27))   // entry + this = the same range without its first item
+__device__ __forceinline__ uint32_t entry_slot(uint32_t e) { return e & TCPT_ENTRY_SLOT_MASK; }
+__device__ __forceinline__ uint32_t entry_more(uint32_t e) { return (e >> 27) & 15u; }   // items behind the first one
+
+// Per-thread state that is touched a few times per ray lives in shared memory, one word per thread and row (bank = lane: no conflicts),
+// so that the registers hold only what every step reads.
+enum {
+    TS_OX = 0, TS_OY, TS_OZ, TS_DX, TS_DY, TS_DZ,             // the ray in Render space (read when an instance is entered)
+    TS_WIX, TS_WIY, TS_WIZ, TS_WKZ, TS_WSX, TS_WSY, TS_WSZ,   // Render-space ray constants (restored when a BLAS is left)
+    TS_BT, TS_B0, TS_B1, TS_B2, TS_BPRIM, TS_BTRI,            // best hit
+    TS_BTLEAF, TS_BTSLOT, TS_BBLEAF, TS_BBSLOT,               // its tie-break keys: TLAS (leaf first slot, slot), BLAS (same)
+    TS_CPRIM, TS_CTLEAF, TS_CTSLOT,                           // the instance being traversed
+    TS_WORDS
+};
+struct TraceShared {
+    uint32_t w[TS_WORDS][128];
+#if TCPT_SMEM_STACK > 0
+    uint32_t stack[TCPT_SMEM_STACK][128];
+#endif
+};
+#define TS_F(row) __uint_as_float(S.w[row][tid])
+#define TS_U(row) S.w[row][tid]
 
 // One ray in flight.  The walk is an explicit state machine so that a warp can keep its lanes busy:
 //   * a lane whose ray is finished picks up the next ray of the queue instead of idling until the slowest ray of the warp is
 //     done (persistent threads with dynamic fetch; first profile, one ray per thread: 4.2 of 32 lanes active on bounce rays);
-//   * reaching a leaf only RECORDS its triangle slots; the warp switches to a triangle phase (one triangle per lane per
+//   * reaching a leaf only RECORDS its triangle range; the warp switches to a triangle phase (one triangle per lane per
 //     iteration) once enough lanes hold pending triangles (second profile: the inline leaf loops ran with 1.9 lanes active and
 //     were 60 % of the kernel's warp instructions).
 struct Traversal {
-    float3 o, d;                 // the ray in Render space
+    RayXform r;                  // ray constants of the space being traversed (Render space in the TLAS, instance space inside a BLAS)
     float t_max, limit;          // caller's t_max; box-culling bound (t_max until the first hit)
-    RayXform rw, rl;             // Render-space and current BLAS-space ray constants
-    DHit best;
-    uint32_t best_tleaf, best_tslot, best_bleaf, best_bslot;  // tie-break keys of `best`: TLAS (leaf first slot, slot), BLAS (same)
+    uint32_t cur;                // what this lane looks at next: a wide node, a leaf range, or NONE (= take the next entry off the stack)
     int sp, blas_sp;             // stack height; stack height at BLAS entry (-1 = traversing the TLAS)
-    uint32_t tos;                // the top stack entry lives in a register (entries 0 .. sp-2 in local memory): a pop hands it out at once
-                                 // and the load of the entry below overlaps the node visit that follows (the pop's local-memory load
-                                 // was 6 % of the kernel's stall samples)
-    uint32_t node_base, slot_base, node;
-    int cur_prim; uint32_t cur_tleaf, cur_tslot;
-    uint32_t pend_slot, pend_cnt;  // triangle slots (relative to slot_base) recorded but not yet tested
-#if TCPT_SPECULATE
-    uint32_t pend2_slot, pend2_cnt;  // a second recorded leaf range: the walk may run one leaf ahead of the triangle tests
-#endif
-    bool need_pop;                 // the next node comes from the stack (deferred so pending triangles keep their BLAS state)
 
-    __device__ __forceinline__ void init(float3 o_, float3 d_, float t_max_) {
-        o = o_; d = d_; t_max = t_max_; limit = t_max_;
-        best.prim = -1; best.t = t_max_; best.b0 = best.b1 = best.b2 = 0.0f; best.tri = 0;
-        best_tleaf = best_tslot = best_bleaf = best_bslot = 0;
-        ray_setup(rw, o, d); rl = rw;
-        sp = 0; tos = 0; blas_sp = -1; node_base = 0; slot_base = 0; node = 0; cur_prim = -1; cur_tleaf = cur_tslot = 0;
-        pend_slot = 0; pend_cnt = 0; need_pop = false;
-#if TCPT_SPECULATE
-        pend2_slot = 0; pend2_cnt = 0;
+    __device__ __forceinline__ void init(TraceShared& S, uint32_t tid, float3 o, float3 d, float t_max_) {
+        t_max = t_max_; limit = t_max_;
+        ray_setup(r, o, d);
+        TS_U(TS_OX) = __float_as_uint(o.x); TS_U(TS_OY) = __float_as_uint(o.y); TS_U(TS_OZ) = __float_as_uint(o.z);
+        TS_U(TS_DX) = __float_as_uint(d.x); TS_U(TS_DY) = __float_as_uint(d.y); TS_U(TS_DZ) = __float_as_uint(d.z);
+        TS_U(TS_WIX) = __float_as_uint(r.inv_d.x); TS_U(TS_WIY) = __float_as_uint(r.inv_d.y); TS_U(TS_WIZ) = __float_as_uint(r.inv_d.z);
+        TS_U(TS_WKZ) = (uint32_t)r.kz; TS_U(TS_WSX) = __float_as_uint(r.sx); TS_U(TS_WSY) = __float_as_uint(r.sy); TS_U(TS_WSZ) = __float_as_uint(r.sz);
+        TS_U(TS_BT) = __float_as_uint(t_max_); TS_U(TS_BPRIM) = 0xffffffffu; TS_U(TS_BTRI) = 0u;
+        TS_U(TS_B0) = 0u; TS_U(TS_B1) = 0u; TS_U(TS_B2) = 0u;
+        sp = 0; blas_sp = -1; cur = 0u;   // wide node 0 = the TLAS root
+    }
+    __device__ __forceinline__ void result(const TraceShared& S, uint32_t tid, DHit& h) const {
+        h.t = TS_F(TS_BT); h.b0 = TS_F(TS_B0); h.b1 = TS_F(TS_B1); h.b2 = TS_F(TS_B2); h.prim = (int)TS_U(TS_BPRIM); h.tri = TS_U(TS_BTRI);
+    }
+    __device__ __forceinline__ bool holds_triangles() const { return cur != TCPT_ENTRY_NONE && (cur & TCPT_ENTRY_LEAF) != 0u && blas_sp >= 0; }
+
+    __device__ __forceinline__ void push(TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t v) {
+#if TCPT_SMEM_STACK > 0
+        if (sp < TCPT_SMEM_STACK) S.stack[sp][tid] = v; else stack[sp - TCPT_SMEM_STACK] = v;
+        ++sp;
+#else
+        stack[sp++] = v;
 #endif
     }
-#if TCPT_SPECULATE
-    // With triangles pending the walk may still advance inside the same BLAS (the pending slots keep their meaning) as long as
-    // the second range is free; leaving the BLAS, or finding a third leaf, has to wait for the triangle phase.
-    __device__ __forceinline__ bool can_walk() const { return pend_cnt == 0u || (pend2_cnt == 0u && (!need_pop || sp > blas_sp)); }
+    __device__ __forceinline__ uint32_t pop(TraceShared& S, uint32_t tid, uint32_t* stack) {
+#if TCPT_SMEM_STACK > 0
+        --sp;
+        return sp < TCPT_SMEM_STACK ? S.stack[sp][tid] : stack[sp - TCPT_SMEM_STACK];
 #else
-    __device__ __forceinline__ bool can_walk() const { return pend_cnt == 0u; }
+        return stack[--sp];
 #endif
+    }
 
-#if TCPT_OPT_TOS
-    __device__ __forceinline__ void push(uint32_t* stack, uint32_t v) { if (sp > 0) stack[sp - 1] = tos; tos = v; ++sp; }
-    __device__ __forceinline__ uint32_t pop(uint32_t* stack) { const uint32_t v = tos; --sp; if (sp > 0) tos = stack[sp - 1]; return v; }
-#else
-    __device__ __forceinline__ void push(uint32_t* stack, uint32_t v) { stack[sp++] = v; }
-    __device__ __forceinline__ uint32_t pop(uint32_t* stack) { return stack[--sp]; }
-#endif
-
-    // Tests ONE pending triangle.  ANY = Scene::intersect_p (scene.rs:93-103): returns true (ray finished) at the first accepted triangle.
+    // Tests the first triangle of the pending leaf range.  ANY = Scene::intersect_p (scene.rs:93-103): returns true (ray finished) at the first accepted triangle.
     template <bool ANY, bool COUNT>
-    __device__ __forceinline__ bool tri_step(const DScene& sc, uint32_t* n_tri) {
-        const uint32_t bslot = pend_slot;
-        pend_slot += 1; pend_cnt -= 1;
-#if TCPT_SPECULATE
-        if (pend_cnt == 0u && pend2_cnt != 0u) { pend_slot = pend2_slot; pend_cnt = pend2_cnt; pend2_cnt = 0u; }
-#endif
-        const size_t s = 3 * (size_t)(slot_base + bslot);
+    __device__ __forceinline__ bool tri_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* n_tri) {
+        const uint32_t bslot = entry_slot(cur);
+        cur = entry_more(cur) != 0u ? cur + TCPT_ENTRY_ONE_ITEM : TCPT_ENTRY_NONE;
+        const size_t s = 3 * (size_t)bslot;
         const float4 v0 = __ldg(&sc.tri_verts[s]), v1 = __ldg(&sc.tri_verts[s + 1]), v2 = __ldg(&sc.tri_verts[s + 2]);
         float t, b0, b1, b2;
         if (COUNT) (*n_tri)++;
-        if (tri_test(v0, v1, v2, rl, t_max, &t, &b0, &b1, &b2)) {
-            if (ANY) { best.prim = 0; best.t = t; return true; }
+        if (tri_test(v0, v1, v2, r, t_max, &t, &b0, &b1, &b2)) {
+            if (ANY) { TS_U(TS_BPRIM) = 0u; TS_U(TS_BT) = __float_as_uint(t); return true; }
             // total order: smaller t; then (TLAS) later leaf, earlier slot; then (BLAS) later leaf, earlier slot
             const uint32_t bleaf = __float_as_uint(v2.w);
+            const float best_t = TS_F(TS_BT);
             bool take;
-            if (best.prim < 0) take = true;
-            else if (t != best.t) take = t < best.t;
-            else if (cur_tleaf != best_tleaf) take = cur_tleaf > best_tleaf;
-            else if (cur_tslot != best_tslot) take = cur_tslot < best_tslot;
-            else if (bleaf != best_bleaf) take = bleaf > best_bleaf;
-            else take = bslot < best_bslot;
+            if ((int)TS_U(TS_BPRIM) < 0) take = true;
+            else if (t != best_t) take = t < best_t;
+            else {
+                const uint32_t ctleaf = TS_U(TS_CTLEAF), ctslot = TS_U(TS_CTSLOT);
+                if (ctleaf != TS_U(TS_BTLEAF)) take = ctleaf > TS_U(TS_BTLEAF);
+                else if (ctslot != TS_U(TS_BTSLOT)) take = ctslot < TS_U(TS_BTSLOT);
+                else if (bleaf != TS_U(TS_BBLEAF)) take = bleaf > TS_U(TS_BBLEAF);
+                else take = bslot < TS_U(TS_BBSLOT);
+            }
             if (take) {
-                best.t = t; best.b0 = b0; best.b1 = b1; best.b2 = b2; best.prim = cur_prim; best.tri = __float_as_uint(v0.w);
-                best_tleaf = cur_tleaf; best_tslot = cur_tslot; best_bleaf = bleaf; best_bslot = bslot;
+                TS_U(TS_BT) = __float_as_uint(t); TS_U(TS_B0) = __float_as_uint(b0); TS_U(TS_B1) = __float_as_uint(b1); TS_U(TS_B2) = __float_as_uint(b2);
+                TS_U(TS_BPRIM) = TS_U(TS_CPRIM); TS_U(TS_BTRI) = __float_as_uint(v0.w);
+                TS_U(TS_BTLEAF) = TS_U(TS_CTLEAF); TS_U(TS_BTSLOT) = TS_U(TS_CTSLOT); TS_U(TS_BBLEAF) = bleaf; TS_U(TS_BBSLOT) = bslot;
                 limit = fminf(t_max, cull_limit(t));
             }
         }
         return false;
     }
 
-    // Visits one child-pair record (both slab tests; leaf children are recorded / TLAS items queued; descend, or defer a pop).
-    // Returns true when the ray is finished (stack empty and nothing pending).
+    // One walking step: take the next entry off the stack if the lane has nothing at hand, open the instance of a TLAS item, visit a
+    // wide node (four slab tests; the nearest hit child is looked at next, the others are pushed).  Returns true when the ray is
+    // finished (stack empty and nothing at hand).
     template <bool COUNT>
-    __device__ __forceinline__ bool node_step(const DScene& sc, uint32_t* stack, uint32_t* n_box) {
-        if (need_pop) {
-            need_pop = false;
-            if (sp == blas_sp) { blas_sp = -1; node_base = 0; if (TCPT_OPT_RL) rl = rw; }  // this BLAS is exhausted: back in the TLAS (and to the Render-space ray)
-            if (sp == 0) return true;
-            const uint32_t top = pop(stack);
-            if (top & TCPT_TLAS_ITEM_BIT) {
-                const uint32_t tslot = top & ~TCPT_TLAS_ITEM_BIT;
-                const int2 item = __ldg(&sc.tlas_items[tslot]);
-                cur_prim = item.x; cur_tleaf = (uint32_t)item.y; cur_tslot = tslot;
-                const tcpt_flat_primitive& P = sc.primitives[cur_prim];
-                const tcpt_flat_geometry& G = sc.geometries[P.geometry];
-                // local_to_render.inverse() * ray (primitive/impls/triangle_mesh.rs:97).  An instance without rotation or scale maps the
-                // direction onto the same bits, and everything ray_setup derives (1/d, the shear constants) depends on the direction
-                // alone: keep the Render-space values instead of six IEEE divisions (ray_setup was 12 % of the kernel's instructions)
-                const float3 ol = xf_point(P.r2l, o), dl = xf_vector(P.r2l, d);
-                if (__float_as_uint(dl.x) == __float_as_uint(d.x) && __float_as_uint(dl.y) == __float_as_uint(d.y) && __float_as_uint(dl.z) == __float_as_uint(d.z)) { rl = rw; rl.o = ol; }
-                else ray_setup(rl, ol, dl);
-                node_base = G.node_base; slot_base = G.slot_base;
-                blas_sp = sp;
-                if (G.single) { pend_slot = 0; pend_cnt = 1; need_pop = true; return false; }  // SingleTriangle: straight to the triangle test, no boxes
-                node = node_base;  // entry record: tests the BLAS root box
-            } else {
-                node = top;
+    __device__ __forceinline__ bool node_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t* n_box) {
+        if (cur == TCPT_ENTRY_NONE) {
+            if (sp == blas_sp) {   // this BLAS is exhausted: back in the TLAS, with the Render-space ray
+                blas_sp = -1;
+                r.o = f3(TS_F(TS_OX), TS_F(TS_OY), TS_F(TS_OZ));
+                r.inv_d = f3(TS_F(TS_WIX), TS_F(TS_WIY), TS_F(TS_WIZ));
+                r.kz = (int)TS_U(TS_WKZ); r.sx = TS_F(TS_WSX); r.sy = TS_F(TS_WSY); r.sz = TS_F(TS_WSZ);
             }
+            if (sp == 0) return true;
+            cur = pop(S, tid, stack);
         }
-        const float4* rec = sc.nodes + 4 * (size_t)node;
-        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
-        const bool in_blas = blas_sp >= 0;
-        const RayXform& r = TCPT_OPT_RL ? rl : (in_blas ? rl : rw);   // TCPT_OPT_RL: the CURRENT ray: Render space in the TLAS (restored at BLAS exit), instance space inside a BLAS -- no per-visit selects
-        const uint32_t ref0 = __float_as_uint(q0.w), cnt0 = __float_as_uint(q1.w), ref1 = __float_as_uint(q2.w), cnt1 = __float_as_uint(q3.w);
-        float te0, te1;
-        const bool h0 = slab_test(q0, q1, r, limit, &te0);
-        const bool h1 = (ref1 != TCPT_ABSENT) && slab_test(q2, q3, r, limit, &te1);
-        if (COUNT) (*n_box) += (ref1 != TCPT_ABSENT) ? 2u : 1u;
-        const bool l0 = h0 && cnt0 != 0, l1 = h1 && cnt1 != 0;
-        if (in_blas) {
-            // sibling leaves occupy adjacent slots (leaf order = DFS order), so both fit one pending range
-            uint32_t ns = 0, nc = 0;
-            if (l0) { ns = ref0; nc = cnt0 + (l1 ? cnt1 : 0u); }
-            else if (l1) { ns = ref1; nc = cnt1; }
-#if TCPT_SPECULATE
-            if (nc != 0u) { if (pend_cnt == 0u) { pend_slot = ns; pend_cnt = nc; } else { pend2_slot = ns; pend2_cnt = nc; } }
-#else
-            if (nc != 0u) { pend_slot = ns; pend_cnt = nc; }
-#endif
+        if (cur & TCPT_ENTRY_LEAF) {
+            if (blas_sp >= 0) return false;   // a triangle range came off the stack: the triangle phase takes it from here
+            // TLAS leaf: open its first primitive, leave the others on the stack
+            const uint32_t tslot = entry_slot(cur);
+            if (entry_more(cur) != 0u) push(S, tid, stack, cur + TCPT_ENTRY_ONE_ITEM);
+            const int2 item = __ldg(&sc.tlas_items[tslot]);
+            TS_U(TS_CPRIM) = (uint32_t)item.x; TS_U(TS_CTLEAF) = (uint32_t)item.y; TS_U(TS_CTSLOT) = tslot;
+            const tcpt_flat_primitive& P = sc.primitives[item.x];
+            const tcpt_flat_geometry& G = sc.geometries[P.geometry];
+            // local_to_render.inverse() * ray (primitive/impls/triangle_mesh.rs:97).  An instance without rotation or scale maps the
+            // direction onto the same bits, and everything ray_setup derives (1/d, the shear constants) depends on the direction
+            // alone: keep the Render-space values instead of six IEEE divisions
+            const float3 o = f3(TS_F(TS_OX), TS_F(TS_OY), TS_F(TS_OZ)), d = f3(TS_F(TS_DX), TS_F(TS_DY), TS_F(TS_DZ));
+            const float3 ol = xf_point(P.r2l, o), dl = xf_vector(P.r2l, d);
+            if (__float_as_uint(dl.x) == __float_as_uint(d.x) && __float_as_uint(dl.y) == __float_as_uint(d.y) && __float_as_uint(dl.z) == __float_as_uint(d.z)) ray_move_origin(r, ol);
+            else ray_setup(r, ol, dl);
+            blas_sp = sp;
+            if (G.single) { cur = TCPT_ENTRY_LEAF | G.slot_base; return false; }   // SingleTriangle: straight to the triangle test, no boxes
+            cur = G.node_base;   // the root wide node of the BLAS
+        }
+        // ---- wide-node visit: rows {lo.x, hi.x, lo.y, hi.y, lo.z, hi.z} x 4 children, then the children's entries and item counts
+        const float4* rec = sc.nodes + 8 * (size_t)cur;
+        const uint4 ent = __ldg((const uint4*)(rec + 6));
+        float te0, te1, te2, te3; bool h0, h1, h2, h3;
+        if (r.kz & TCPT_RAY_FAST) {
+            // NaN-free slab test.  With finite o and inv_d every product is a number, (lo - o) <= (hi - o) survives the rounding, so the
+            // reference's `if tn > tf swap` picks near = lo for inv_d > 0 and near = hi for inv_d < 0 (equal products: same values
+            // either way), and its compare-selects are max / min.  The near / far rows are picked by ADDRESS (16 bytes apart).
+            const char* base = (const char*)rec;
+            const uint32_t nx = (uint32_t)r.kz & 0x10u, ny = ((uint32_t)r.kz >> 1) & 0x10u, nz = ((uint32_t)r.kz >> 2) & 0x10u;
+            const float4 ax = __ldg((const float4*)(base + nx)), bx = __ldg((const float4*)(base + (nx ^ 16u)));
+            const float4 ay = __ldg((const float4*)(base + 32 + ny)), by = __ldg((const float4*)(base + 32 + (ny ^ 16u)));
+            const float4 az = __ldg((const float4*)(base + 64 + nz)), bz = __ldg((const float4*)(base + 64 + (nz ^ 16u)));
+#define TCPT_SLAB(c, TE, H)                                                                                                          \
+            {                                                                                                                        \
+                const float tnx = (ax.c - r.o.x) * r.inv_d.x, tny = (ay.c - r.o.y) * r.inv_d.y, tnz = (az.c - r.o.z) * r.inv_d.z;     \
+                const float tfx = (bx.c - r.o.x) * r.inv_d.x, tfy = (by.c - r.o.y) * r.inv_d.y, tfz = (bz.c - r.o.z) * r.inv_d.z;     \
+                const float t0 = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), t1 = fminf(fminf(tfx, tfy), fminf(tfz, limit));             \
+                TE = t0; H = !(t0 > t1);                                                                                             \
+            }
+            TCPT_SLAB(x, te0, h0) TCPT_SLAB(y, te1, h1) TCPT_SLAB(z, te2, h2) TCPT_SLAB(w, te3, h3)
+#undef TCPT_SLAB
+            // (an absent child has the box (+inf, -inf): near = +-inf gives t0 = +inf > t1 = -inf, no separate check)
         } else {
-            // TLAS leaf: queue its primitives (each opens a BLAS when popped)
-            if (l0) for (uint32_t i = 0; i < cnt0; ++i) push(stack, TCPT_TLAS_ITEM_BIT | (ref0 + cnt0 - 1u - i));
-            if (l1) for (uint32_t i = 0; i < cnt1; ++i) push(stack, TCPT_TLAS_ITEM_BIT | (ref1 + cnt1 - 1u - i));
+            const float4 lx = __ldg(rec), hx = __ldg(rec + 1), ly = __ldg(rec + 2), hy = __ldg(rec + 3), lz = __ldg(rec + 4), hz = __ldg(rec + 5);
+            h0 = ent.x != TCPT_ENTRY_NONE && slab_exact(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, r, limit, &te0);
+            h1 = ent.y != TCPT_ENTRY_NONE && slab_exact(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, r, limit, &te1);
+            h2 = ent.z != TCPT_ENTRY_NONE && slab_exact(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, r, limit, &te2);
+            h3 = ent.w != TCPT_ENTRY_NONE && slab_exact(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, r, limit, &te3);
         }
-        const bool i0 = h0 && cnt0 == 0, i1 = h1 && cnt1 == 0;
-        if (i0 && i1) {
-            const uint32_t c0 = node_base + ref0, c1 = node_base + ref1;
-            if (te1 < te0) { push(stack, c0); node = c1; } else { push(stack, c1); node = c0; }
-        } else if (i0) node = node_base + ref0;
-        else if (i1) node = node_base + ref1;
-        else need_pop = true;
+        if (COUNT) (*n_box) += (ent.x != TCPT_ENTRY_NONE) + (ent.y != TCPT_ENTRY_NONE) + (ent.z != TCPT_ENTRY_NONE) + (ent.w != TCPT_ENTRY_NONE);
+        // order the hit children by entry distance (misses sort last)
+        float k0 = h0 ? te0 : TCPT_INF, k1 = h1 ? te1 : TCPT_INF, k2 = h2 ? te2 : TCPT_INF, k3 = h3 ? te3 : TCPT_INF;
+        uint32_t e0 = h0 ? ent.x : TCPT_ENTRY_NONE, e1 = h1 ? ent.y : TCPT_ENTRY_NONE, e2 = h2 ? ent.z : TCPT_ENTRY_NONE, e3 = h3 ? ent.w : TCPT_ENTRY_NONE;
+#define TCPT_CE(ka, ea, kb, eb) { const bool sw = kb < ka; const float kt = sw ? kb : ka; kb = sw ? ka : kb; ka = kt; const uint32_t et = sw ? eb : ea; eb = sw ? ea : eb; ea = et; }
+        TCPT_CE(k0, e0, k1, e1) TCPT_CE(k2, e2, k3, e3) TCPT_CE(k0, e0, k2, e2)
+#if TCPT_SORT_FULL
+        TCPT_CE(k1, e1, k3, e3) TCPT_CE(k1, e1, k2, e2)
+#endif
+#undef TCPT_CE
+        if (e3 != TCPT_ENTRY_NONE) push(S, tid, stack, e3);
+        if (e2 != TCPT_ENTRY_NONE) push(S, tid, stack, e2);
+        if (e1 != TCPT_ENTRY_NONE) push(S, tid, stack, e1);
+        cur = e0;   // NONE when nothing was hit: the next step pops
         return false;
     }
 };
@@ -286,20 +339,21 @@ struct Traversal {
 #ifndef TCPT_TRI_PHASE_LANES
 #define TCPT_TRI_PHASE_LANES 8    // a warp runs a triangle iteration once this many lanes hold pending triangles
 #endif
+#define TCPT_LOCAL_STACK (TCPT_TRAVERSAL_STACK - TCPT_SMEM_STACK)
 
 // Traces the rays of a queue with persistent warps.  `work` is a global counter zeroed before the launch.  A finished ray's
-// result stays in the lane until the warp's next refill point, where `commit(i, hit)` is called for all finished lanes
-// together (converged): result stores, bucket filing and shadow accumulation then cost one memory round trip per refill
+// result stays in the lane's shared-memory rows until the warp's next refill point, where `commit(i, hit)` is called for all finished
+// lanes together (converged): result stores, bucket filing and shadow accumulation then cost one memory round trip per refill
 // instead of one per finishing lane in a divergent branch (third profile: the filing atomic at 4 lanes was the top stall).
-// Every warp of the grid must call this with all 32 lanes.
+// Every warp of the grid must call this with all 32 lanes; blocks are 128 threads (TraceShared).
 template <bool ANY, bool COUNT, class Commit>
-__device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
+__device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
                                             uint32_t* work, uint32_t* n_box, uint32_t* n_tri, Commit&& commit) {
     const uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t stack[TCPT_TRAVERSAL_STACK];
+    const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
+    uint32_t stack[TCPT_LOCAL_STACK];
     Traversal T;
-    T.pend_cnt = 0;
+    T.cur = TCPT_ENTRY_NONE; T.blas_sp = -1;
     uint32_t ray = NONE, fin = NONE;
     // Ray indices are reserved from the global counter a CHUNK at a time and handed out from a warp-local pool, so most refills
     // cost no global atomic (fourth profile: the warp waiting on the counter's round trip at every refill was the top stall).
@@ -316,7 +370,7 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
         const bool fetch = n_idle > left && !drained;
         uint32_t fetched = 0;
         if (fetch && lane == 0) fetched = atomicAdd(work, chunk);  // in flight while the finished rays are committed
-        if (fin != NONE) { commit(fin, T.best); fin = NONE; }
+        if (fin != NONE) { DHit h; T.result(S, tid, h); commit(fin, h); fin = NONE; }
         if (n_idle != 0u) {
             uint32_t base_b = 0;
             if (fetch) {
@@ -325,13 +379,13 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
             }
             if (ray == NONE) {
                 // the first `left` idle lanes take what remains of the old chunk, the others start the new one
-                const uint32_t r = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                const uint32_t rk = (uint32_t)__popc(idle & ((1u << lane) - 1u));
                 uint32_t mine = NONE;
-                if (r < left) mine = pool + r;
-                else if (fetch) mine = base_b + (r - left);
+                if (rk < left) mine = pool + rk;
+                else if (fetch) mine = base_b + (rk - left);
                 if (mine < n) {
                     const float4 o = q_o[mine], d = q_d[mine];
-                    T.init(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
+                    T.init(S, tid, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
                     ray = mine;
                 }
             }
@@ -341,46 +395,25 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, const float4* __re
         const bool exhausted = drained && pool >= pool_end;
         if (__ballot_sync(FULL, ray != NONE) == 0u) break;  // nothing in flight and nothing left to fetch
         const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;
-#if TCPT_OPT_BALLOT
-        // A ray in flight either holds pending triangles or may walk (never neither), so the lanes without a ray are the complement
-        // of the two masks: the masks of the next iteration double as this iteration's idle count (one ballot less per iteration).
-        uint32_t n_idle_now;
-        bool has_tri = ray != NONE && T.pend_cnt != 0u;
-        bool walks = ray != NONE && T.can_walk();
-        uint32_t tri_mask = __ballot_sync(FULL, has_tri);
-        uint32_t node_mask = __ballot_sync(FULL, walks);
-        do {
-            bool finished = false;
-            if (tri_mask != 0u && ((uint32_t)__popc(tri_mask) >= (uint32_t)TCPT_TRI_PHASE_LANES || node_mask == 0u)) {
-                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, n_tri);
-            } else {
-                if (walks) finished = T.template node_step<COUNT>(sc, stack, n_box);
-            }
-            if (finished) { fin = ray; ray = NONE; T.pend_cnt = 0; }
-            has_tri = ray != NONE && T.pend_cnt != 0u;
-            walks = ray != NONE && T.can_walk();
-            tri_mask = __ballot_sync(FULL, has_tri);
-            node_mask = __ballot_sync(FULL, walks);
-            n_idle_now = 32u - (uint32_t)__popc(tri_mask | node_mask);
-        } while (n_idle_now < stop_at);
-#else
         uint32_t n_idle_now;
         do {
-            const bool has_tri = ray != NONE && T.pend_cnt != 0u;
-            const bool walks = ray != NONE && T.can_walk();
+            const bool has_tri = ray != NONE && T.holds_triangles();
+            const bool walks = ray != NONE && !has_tri;
             const uint32_t tri_mask = __ballot_sync(FULL, has_tri);
             const uint32_t node_mask = __ballot_sync(FULL, walks);
             bool finished = false;
             if (tri_mask != 0u && ((uint32_t)__popc(tri_mask) >= (uint32_t)TCPT_TRI_PHASE_LANES || node_mask == 0u)) {
-                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, n_tri);
+                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, n_tri);
             } else {
-                if (walks) finished = T.template node_step<COUNT>(sc, stack, n_box);
+                if (walks) finished = T.template node_step<COUNT>(sc, S, tid, stack, n_box);
             }
-            if (finished) { fin = ray; ray = NONE; T.pend_cnt = 0; }
+            if (finished) { fin = ray; ray = NONE; T.cur = TCPT_ENTRY_NONE; }
             n_idle_now = (uint32_t)__popc(__ballot_sync(FULL, ray == NONE));
         } while (n_idle_now < stop_at);
-#endif
     }
 }
+
+#undef TS_F
+#undef TS_U
 
 }  // namespace tcpt

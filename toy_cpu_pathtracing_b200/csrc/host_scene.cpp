@@ -1,6 +1,8 @@
 // Host scene preparation (product code, plain C++; compiled with -ffp-contract=off).  See host_scene.h.
 #include "host_scene.h"
 
+#include <functional>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -269,38 +271,80 @@ int HostScene::add_delta_light(int kind, float intensity, const tcpt_spectrum_pa
     return (int)primitives.size() - 1;
 }
 
-// Convert the reference-order tree (pre-order inner/leaf records) into the device's child-pair records (include/tcpt_flat.h).
-// Returns the number of records appended; *max_leaf receives the largest leaf item count.
-static uint32_t put_nodes(const BuiltBvh& b, std::vector<tcpt_bvh_node>& out, uint32_t* max_leaf) {
+// Convert the reference-order binary tree (pre-order inner / leaf records) into the device's 4-wide records (include/tcpt_flat.h).
+// A wide node starts from a binary node's two children and repeatedly replaces its largest-area inner child by that child's two
+// children, in place, until it holds four children or only leaves (the children keep the reference's DFS order).  Every reference
+// LEAF survives with its own box bits and item order; reference inner boxes that end up interior to a wide node are not stored:
+// a ray that passes a leaf box passes all of its ancestors' boxes (exact min / max merges, monotone slab test; dtraverse.cuh).
+// `slot_base` = absolute index of the BVH's first item slot; node indices written into the records are absolute (`out` index).
+// Returns the number of records appended; *max_stack receives the deepest the traversal stack can get inside this BVH.
+static uint32_t put_nodes(const BuiltBvh& b, std::vector<tcpt_bvh_node>& out, uint32_t slot_base, uint32_t* max_stack) {
     const size_t base = out.size();
-    auto set_child = [&](size_t rec, int k, const Box* box, uint32_t ref, uint32_t cnt) {
-        float* q = out[rec].q + 8 * k;
-        const float inf = INFINITY;
-        q[0] = box ? box->lo.x : inf; q[1] = box ? box->lo.y : inf; q[2] = box ? box->lo.z : inf;
-        q[4] = box ? box->hi.x : -inf; q[5] = box ? box->hi.y : -inf; q[6] = box ? box->hi.z : -inf;
-        std::memcpy(&q[3], &ref, 4);
-        std::memcpy(&q[7], &cnt, 4);
+    const float inf = INFINITY;
+    auto blank = [&]() {
+        tcpt_bvh_node n;
+        for (int k = 0; k < 4; ++k) {
+            n.q[0 + k] = inf; n.q[4 + k] = -inf; n.q[8 + k] = inf; n.q[12 + k] = -inf; n.q[16 + k] = inf; n.q[20 + k] = -inf;
+            const uint32_t none = 0xffffffffu, zero = 0u;
+            std::memcpy(&n.q[24 + k], &none, 4); std::memcpy(&n.q[28 + k], &zero, 4);
+        }
+        return n;
     };
-    *max_leaf = 0;
-    for (const BuildNode& n : b.nodes) if (n.count > *max_leaf) *max_leaf = n.count;
-    // iterative pre-order over inner nodes; rec_of[i] = record index (relative) of inner node i
-    out.push_back(tcpt_bvh_node{});
-    set_child(base, 1, nullptr, 0xffffffffu, 0);
-    if (b.nodes.empty()) { set_child(base, 0, nullptr, 0xffffffffu, 0); return 1; }
-    struct Todo { uint32_t node; size_t parent_rec; int slot; };
-    std::vector<Todo> stack;
-    stack.push_back(Todo{0, base, 0});
-    while (!stack.empty()) {
-        const Todo t = stack.back(); stack.pop_back();
-        const BuildNode& n = b.nodes[t.node];
-        if (n.count) { set_child(t.parent_rec, t.slot, &n.box, n.first_item, n.count); continue; }
+    auto set_child = [&](size_t rec, int k, const Box& box, uint32_t entry, uint32_t cnt) {
+        float* q = out[rec].q;
+        q[0 + k] = box.lo.x; q[4 + k] = box.hi.x; q[8 + k] = box.lo.y; q[12 + k] = box.hi.y; q[16 + k] = box.lo.z; q[20 + k] = box.hi.z;
+        std::memcpy(&q[24 + k], &entry, 4); std::memcpy(&q[28 + k], &cnt, 4);
+    };
+    *max_stack = 0;
+    if (b.nodes.empty()) { out.push_back(blank()); return 1; }
+    // a range of leaf items as a child: one entry for up to 16 items; a longer reference leaf becomes a wide node of up to four
+    // sub-ranges that all carry the LEAF's box (the same test decides all of them, as it decides the whole leaf in the reference)
+    struct Pending { size_t rec; int slot; uint32_t node; };            // binary node `node` to be written as child `slot` of record `rec`
+    std::vector<Pending> todo;
+    // returns the stack depth the subtree can reach
+    std::function<uint32_t(size_t, int, const Box&, uint32_t, uint32_t)> put_range = [&](size_t rec, int k, const Box& box, uint32_t first, uint32_t cnt) -> uint32_t {
+        if (cnt <= 16) { set_child(rec, k, box, 0x80000000u | ((cnt - 1u) << 27) | (slot_base + first), cnt); return 0; }
+        const size_t sub = out.size();
+        out.push_back(blank());
+        set_child(rec, k, box, (uint32_t)sub, 0);
+        uint32_t parts = (cnt + 15u) / 16u; if (parts > 4u) parts = 4u;
+        uint32_t depth = 0, done = 0;
+        for (uint32_t i = 0; i < parts; ++i) {
+            const uint32_t take = (cnt - done) / (parts - i);
+            depth = std::max(depth, put_range(sub, (int)i, box, first + done, take));
+            done += take;
+        }
+        return depth + parts - 1u;
+    };
+    std::function<uint32_t(uint32_t)> put_wide = [&](uint32_t root) -> uint32_t {   // binary inner node (or a leaf root) -> one wide record; pre-order
         const size_t rec = out.size();
-        out.push_back(tcpt_bvh_node{});
-        set_child(t.parent_rec, t.slot, &n.box, (uint32_t)(rec - base), 0);
-        // child0 subtree is emitted first (pre-order): push child1 then child0
-        stack.push_back(Todo{n.second, rec, 1});
-        stack.push_back(Todo{t.node + 1, rec, 0});
-    }
+        out.push_back(blank());
+        std::vector<uint32_t> kids;
+        const BuildNode& rn = b.nodes[root];
+        if (rn.count) kids.push_back(root);
+        else { kids.push_back(root + 1); kids.push_back(rn.second); }
+        while (kids.size() < 4) {
+            int best = -1; float best_area = -1.0f;
+            for (size_t i = 0; i < kids.size(); ++i) {
+                const BuildNode& c = b.nodes[kids[i]];
+                if (c.count == 0 && c.box.half_area2() > best_area) { best_area = c.box.half_area2(); best = (int)i; }
+            }
+            if (best < 0) break;
+            const uint32_t c = kids[best];
+            kids[best] = c + 1;
+            kids.insert(kids.begin() + best + 1, b.nodes[c].second);
+        }
+        uint32_t depth = 0;
+        for (size_t i = 0; i < kids.size(); ++i) {
+            const BuildNode& c = b.nodes[kids[i]];
+            uint32_t d;
+            if (c.count) d = put_range(rec, (int)i, c.box, c.first_item, c.count);
+            else { const size_t child_rec = out.size(); d = put_wide(kids[i]); set_child(rec, (int)i, c.box, (uint32_t)child_rec, 0); }
+            depth = std::max(depth, d);
+        }
+        return depth + (uint32_t)kids.size() - 1u;   // the siblings of the child being walked wait on the stack
+    };
+    *max_stack = put_wide(0);
     return (uint32_t)(out.size() - base);
 }
 
@@ -350,8 +394,8 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     if (tb.empty()) { error = "build: no geometry primitives"; return TCPT_ERR_INVALID; }
     tlas = SahBuilder(tb).build();
 
-    uint32_t tlas_max_leaf = 0;
-    put_nodes(tlas, S.nodes, &tlas_max_leaf);
+    uint32_t tlas_stack = 0;
+    put_nodes(tlas, S.nodes, 0, &tlas_stack);
     {
         const std::vector<uint32_t> lf = leaf_first_of_slots(tlas);
         for (size_t k = 0; k < tlas.items.size(); ++k) { S.tlas_items.push_back(tlas_prims[tlas.items[k]]); S.tlas_items.push_back((int32_t)lf[k]); }
@@ -359,7 +403,7 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     const uint32_t tlas_nodes = (uint32_t)S.nodes.size();
 
     uint32_t deepest = 0;
-    std::vector<int> geom_flat(meshes.size(), -1);
+    geom_flat.assign(meshes.size(), -1);
     for (size_t g = 0; g < meshes.size(); ++g) {
         const HostMesh& m = meshes[g];
         if (!m.built) continue;
@@ -368,8 +412,8 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         fg.slot_base = (uint32_t)(S.tri_verts.size() / 12); fg.tri_count = (uint32_t)(m.indices.size() / 3);
         fg.vertex_base = (uint32_t)(S.positions.size() / 3); fg.index_base = (uint32_t)(S.indices.size() / 3);
         fg.tangent_base = (uint32_t)(S.tangents.size() / 3); fg.has_uv = m.uvs.empty() ? 0 : 1; fg.single = m.single ? 1 : 0;
-        uint32_t blas_max_leaf = 0;
-        fg.node_count = put_nodes(m.bvh, S.nodes, &blas_max_leaf);
+        uint32_t blas_stack = 0;
+        fg.node_count = put_nodes(m.bvh, S.nodes, fg.slot_base, &blas_stack);
         const std::vector<uint32_t> lf = leaf_first_of_slots(m.bvh);
         for (size_t slot = 0; slot < m.bvh.items.size(); ++slot) {
             const uint32_t tri = m.bvh.items[slot];
@@ -391,7 +435,7 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
         else for (const V3& v : m.tangents) S.tangents.insert(S.tangents.end(), {v.x, v.y, v.z});
         geom_flat[g] = (int)S.geometries.size();
         S.geometries.push_back(fg);
-        deepest = std::max(deepest, m.bvh.depth);
+        deepest = std::max(deepest, blas_stack);
     }
 
     // light list in primitive order (light_sampler.rs:168-187)
@@ -463,8 +507,11 @@ int HostScene::build(const float cam_pos[3], FlatStorage& S) {
     v.envs = S.envs.data(); v.n_envs = (uint32_t)S.envs.size();
     v.env_floats = S.env_floats.data(); v.n_env_floats = S.env_floats.size();
     v.env_guides = S.env_guides.data(); v.n_env_guides = S.env_guides.size();
-    v.max_bvh_depth = tlas.depth + tlas_max_leaf + deepest;
-    if (v.max_bvh_depth + 2 >= TCPT_TRAVERSAL_STACK) { error = "build: BVH deeper than the traversal stack"; return TCPT_ERR_LIMIT; }
+    // worst-case height of the traversal stack: the siblings waiting along the deepest TLAS path, the rest of a TLAS leaf's items
+    // (one range entry), then the same inside the deepest BLAS (put_nodes walks every root-to-leaf path)
+    v.max_bvh_depth = tlas_stack + 1 + deepest;
+    if (v.max_bvh_depth >= TCPT_TRAVERSAL_STACK) { error = "build: BVH deeper than the traversal stack"; return TCPT_ERR_LIMIT; }
+    if (v.n_tri_slots >= 0x07ffffffu || v.n_tlas_items >= 0x07ffffffu) { error = "build: more item slots than a stack entry can address (2^27)"; return TCPT_ERR_LIMIT; }
     return TCPT_OK;
 }
 

@@ -77,6 +77,7 @@ class HostScene {
     std::vector<HostEnv> envs;
     BuiltBvh tlas;
     std::vector<int> tlas_prims;
+    std::vector<int> geom_flat;       // mesh index -> index into the flat geometry table of the last build (-1: not referenced)
     bool use_binned_builder = false;  // soups only (outside topology-parity scope)
     std::string error;
 

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(128, 6) k_trace_closest(const __grid_constant_
         atomicAdd(&st.stats[0], (unsigned long long)n);
     }
     uint32_t nb = 0, nt = 0;
-    trace_queue<false, COUNT>(sc, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, q_d, hit0, hit1, bcount, i, h); });
+    __shared__ TraceShared ts;
+    trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, q_d, hit0, hit1, bcount, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__
     const uint32_t n = st.counters[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st.stats[1], (unsigned long long)n);
     uint32_t nb = 0, nt = 0;
-    trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
+    __shared__ TraceShared ts;
+    trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -198,11 +200,12 @@ __global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(cons
         atomicAdd(&st.stats[1], (unsigned long long)n_sh);
     }
     uint32_t nb = 0, nt = 0;
+    __shared__ TraceShared ts;
     // (shadow first: it is the shorter queue.  Letting half of the blocks start on the extension queue so that short queues are
     // walked side by side was measured slower: 16.6 vs 15.3 ms per 33 M paths.)
-    if (n_sh) trace_queue<true, COUNT>(sc, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
+    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
     float4* __restrict__ hit0 = st.hit0; uint2* __restrict__ hit1 = st.hit1;
-    if (n) trace_queue<false, COUNT>(sc, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, st.ext_d[cur], hit0, hit1, bcount, i, h); });
+    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, st.ext_d[cur], hit0, hit1, bcount, i, h); });
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -666,12 +669,13 @@ template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
                                                      int any_hit, float4* __restrict__ hit0, uint2* __restrict__ hit1, unsigned long long* stats, uint32_t* work) {
     uint32_t nb = 0, nt = 0;
+    __shared__ TraceShared ts;
     auto store = [&](uint32_t i, const DHit& h) {
         hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
         hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
     };
-    if (any_hit) trace_queue<true, COUNT>(sc, q_o, q_d, n, work, &nb, &nt, store);
-    else trace_queue<false, COUNT>(sc, q_o, q_d, n, work, &nb, &nt, store);
+    if (any_hit) trace_queue<true, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, store);
+    else trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, store);
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)nb); atomicAdd(&stats[3], (unsigned long long)nt); }
 }
 

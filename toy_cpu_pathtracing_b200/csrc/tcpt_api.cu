@@ -180,6 +180,10 @@ int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera&
 int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
     R.sobol_prefix = nullptr; R.prefix_dims = 0; R.prefix_stride = 0; R.pass_info = 0;
     if (R.sampler != TCPT_SAMPLER_SOBOL || !ctx->opt.sobol_prefix) return TCPT_OK;
+    // Both tables assume that the bits of the Morton index at and above log2_spp belong to the pixel alone.  The reference takes any
+    // spp (main.rs only warns) with log2_spp = floor(log2(spp)) and ORs the sample index in (z_sobol_sampler.rs:200), so for a spp that
+    // is not a power of two the samples >= 2^log2_spp spill into the pixel digits: no tables then, every digit is computed per call.
+    if ((R.spp & (R.spp - 1u)) != 0u) return TCPT_OK;
     const size_t n_pix = (size_t)R.width * R.height;
     size_t dims = 3 + 8 * ((size_t)R.max_depth + 1);
     const size_t cap_dims = ((size_t)ctx->opt.sobol_prefix_mb << 20) / (n_pix * 4);
@@ -660,7 +664,7 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
     if (!ctx->d_cmf) return fail(ctx, TCPT_ERR_INVALID, "upload: call tcpt_set_tables first");
     if (s->n_lights > TCPT_MAX_LIGHTS) return fail(ctx, TCPT_ERR_LIMIT, "upload: too many lights");
-    if (s->max_bvh_depth + 2 >= TCPT_TRAVERSAL_STACK) return fail(ctx, TCPT_ERR_LIMIT, "upload: BVH deeper than the traversal stack");
+    if (s->max_bvh_depth >= TCPT_TRAVERSAL_STACK) return fail(ctx, TCPT_ERR_LIMIT, "upload: BVH deeper than the traversal stack");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     free_scene(ctx->dev);
@@ -711,6 +715,7 @@ int tcpt_scene_build(tcpt_ctx* ctx, const float cam_pos[3]) {
     if (!ctx || !cam_pos) return TCPT_ERR_INVALID;
     int r = ctx->host.build(cam_pos, ctx->flat);
     if (r != TCPT_OK) { ctx->error = ctx->host.error; return r; }
+    ctx->stats.max_bvh_depth = ctx->flat.view.max_bvh_depth;   // readable on a host-only context too
     return tcpt_upload_flat_scene(ctx, &ctx->flat.view);
 }
 
@@ -897,6 +902,22 @@ int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uin
 int tcpt_get_bvh(tcpt_ctx* ctx, int which, uint32_t* out, int max_nodes) {
     if (!ctx || (!out && max_nodes > 0)) return TCPT_ERR_INVALID;
     return ctx->host.dump_bvh(which, out, max_nodes);
+}
+
+int tcpt_get_wide_bvh(tcpt_ctx* ctx, int which, uint32_t* out, int max_records, uint32_t* first_record, uint32_t* slot_base) {
+    if (!ctx || (!out && max_records > 0)) return TCPT_ERR_INVALID;
+    const tcpt_flat_scene& v = ctx->flat.view;
+    if (!v.bvh_nodes) return fail(ctx, TCPT_ERR_INVALID, "get_wide_bvh: no scene built");
+    uint32_t first = 0, count = v.tlas_node_count, sbase = 0;
+    if (which >= 0) {
+        if (which >= (int)ctx->host.geom_flat.size() || ctx->host.geom_flat[which] < 0) return fail(ctx, TCPT_ERR_INVALID, "get_wide_bvh: geometry not in the scene");
+        const tcpt_flat_geometry& g = v.geometries[ctx->host.geom_flat[which]];
+        first = g.node_base; count = g.node_count; sbase = g.slot_base;
+    }
+    if (first_record) *first_record = first;
+    if (slot_base) *slot_base = sbase;
+    for (uint32_t i = 0; i < count && (int)i < max_records; ++i) std::memcpy(out + 32 * (size_t)i, v.bvh_nodes[first + i].q, 128);
+    return (int)count;
 }
 
 int tcpt_build_bvh_boxes(const float* boxes, int n, uint32_t* out, int max_nodes) {

@@ -590,6 +590,22 @@ class Scene:
         self.ctx.check(self.ctx.lib.tcpt_get_bvh(self.ctx.handle, which, capi.as_ptr(out, C.c_uint32), n))
         return out
 
+    def get_wide_bvh(self, which: int):
+        """(records [n, 8 rows, 4 children] u32, first_record, slot_base) of the device's 4-wide layout (include/tcpt_flat.h)."""
+        first, sbase = C.c_uint32(0), C.c_uint32(0)
+        n = self.ctx.check(self.ctx.lib.tcpt_get_wide_bvh(self.ctx.handle, which, None, 0, C.byref(first), C.byref(sbase)))
+        out = np.zeros((n, 8, 4), dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.tcpt_get_wide_bvh(self.ctx.handle, which, capi.as_ptr(out, C.c_uint32), n, C.byref(first), C.byref(sbase)))
+        return out, first.value, sbase.value
+
+    def sampler_stream(self, sampler, spp, width, height, seed, px, py, sample_index, kinds) -> np.ndarray:
+        """The values a sampler hands out for one (pixel, sample): kinds = 1 (get_1d) / 2 (get_2d) per call (parity probe)."""
+        k = np.ascontiguousarray(kinds, dtype=np.int32)
+        out = np.zeros(int(sum(1 if x == 1 else 2 for x in kinds)), dtype=f32)
+        self.ctx.check(self.ctx.lib.tcpt_sampler_stream(self.ctx.handle, capi.SAMPLERS[sampler], spp, width, height, seed, px, py, sample_index,
+                                                        capi.as_ptr(k, C.c_int32), len(k), capi.as_ptr(out, C.c_float)))
+        return out
+
     def mesh_tangents(self, geometry: int) -> np.ndarray:
         n = self.ctx.check(self.ctx.lib.tcpt_get_mesh_tangents(self.ctx.handle, geometry, None, 0))
         out = np.zeros((n, 3), dtype=f32)
