@@ -100,6 +100,7 @@ typedef struct {
     uint32_t passes, max_bvh_depth;
     double sobol_prefix_ms;  /* device time of the last build of the ZSobol pixel-prefix table (once per resolution / spp; 0 when reused) */
     uint64_t sobol_prefix_bytes; /* size of that table in device memory */
+    double reduce_ms;        /* device time of the film reduce of the last tcpt_render_sharded* (0 on one GPU) */
 } tcpt_stats;
 
 /* ---- context.  tcpt_create returns TCPT_ERR_CUDA when no sm_100 device is usable; *out is then still a context on which only
@@ -154,6 +155,41 @@ int tcpt_render_device(tcpt_ctx* ctx, const tcpt_render_params* params, void* de
 /* Sensor::to_rgb on a device accumulator (after the NCCL reduce): dev_srgb = OETF(Reinhard(max(acc/spp,0))) */
 int tcpt_finalize_device(tcpt_ctx* ctx, const void* dev_acc, uint32_t width, uint32_t height, uint32_t spp, void* dev_srgb, void* stream);
 int tcpt_get_stats(const tcpt_ctx* ctx, tcpt_stats* out);
+
+/* ---- multi-GPU.  The reference has no distributed path; every (pixel, sample) is independent and the only shared
+ * output is the per-pixel Sensor accumulator (sensor.rs:76-77), so a frame is split across GPUs and summed once.  The library owns
+ * the NCCL communicator (libnccl.so.2 is opened when the first one is made; a single-GPU host never loads it).
+ *   one process per GPU : tcpt_create -> tcpt_comm_init(nranks, rank, id) on every rank (id from tcpt_comm_get_unique_id on one rank,
+ *                         handed over by any transport) -> tcpt_render_sharded on every rank, same job
+ *   one process, N GPUs : tcpt_group_* below (one context per GPU, one host thread per GPU inside tcpt_group_render)
+ * shard modes: TILE = rank r renders rows y % nranks == r with every sample: the reduced film is BITWISE the one-GPU film;
+ *              SPP  = rank r renders an equal slice of the job's sample indices of every pixel: best balance, sums re-associated.
+ * Exactly one collective per frame: ncclReduce(sum) of width*height*3 f32 onto rank 0, then Sensor::to_rgb and ONE device -> host
+ * copy per requested buffer on rank 0. */
+#define TCPT_COMM_ID_BYTES 128
+enum { TCPT_SHARD_TILE = 0, TCPT_SHARD_SPP = 1 };
+int tcpt_comm_get_unique_id(void* id128);
+int tcpt_comm_init(tcpt_ctx* ctx, int nranks, int rank, const void* id128);   /* collective: every rank calls it */
+int tcpt_comm_destroy(tcpt_ctx* ctx);
+/* the slice of `job` rank `rank` of `nranks` renders (pure function; job->row_offset / row_stride must be 0, [spp_begin, spp_end) = the
+ * job's sample range, 0,0 = all `spp`) */
+int tcpt_shard_params(const tcpt_render_params* job, int shard_mode, int rank, int nranks, tcpt_render_params* out);
+/* One complete frame from all ranks.  Every rank passes the SAME job; out_acc / out_srgb (host, width*height*3 f32, either may be NULL)
+ * are written on rank 0 only and may be NULL elsewhere.  out_srgb = Sensor::to_rgb over the job's sample count.  Without a
+ * communicator (one GPU) it is tcpt_render. */
+int tcpt_render_sharded(tcpt_ctx* ctx, const tcpt_render_params* job, int shard_mode, float* out_acc, float* out_srgb);
+/* same, accumulating into a caller-owned DEVICE buffer (zeroed by the caller) on `stream`; after the call rank 0's buffer holds the sum */
+int tcpt_render_sharded_device(tcpt_ctx* ctx, const tcpt_render_params* job, int shard_mode, void* dev_acc, void* stream);
+
+typedef struct tcpt_group tcpt_group;
+int tcpt_group_create(const int* device_ids, int n, tcpt_group** out);     /* n contexts + one communicator clique */
+void tcpt_group_destroy(tcpt_group* g);
+int tcpt_group_size(const tcpt_group* g);
+tcpt_ctx* tcpt_group_context(tcpt_group* g, int i);                        /* describe the scene on context 0 (tcpt_scene_add_*) */
+const char* tcpt_group_last_error(const tcpt_group* g);
+int tcpt_group_set_tables(tcpt_group* g, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_floats);
+int tcpt_group_build(tcpt_group* g, const float cam_pos[3]);               /* Scene::build on context 0, replica on every other GPU */
+int tcpt_group_render(tcpt_group* g, const tcpt_render_params* job, int shard_mode, float* out_acc, float* out_srgb);
 
 /* ---- single stages, exposed for parity tests and the traversal micro-benchmark */
 /* rays: n x {o[3], d[3], tmax}; out: n x {prim, tri, t bits, b0 bits, b1 bits, b2 bits} (prim -1 = miss; any_hit: out[0] = 0|1) */

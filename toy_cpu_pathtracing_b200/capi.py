@@ -18,6 +18,8 @@ SAMPLERS = {"random": 0, "sobol": 1}
 MAT_LAMBERT, MAT_EMISSIVE, MAT_PLASTIC, MAT_SIMPLE_PBR, MAT_CLEARCOAT_PBR, MAT_METAL, MAT_GLASS = range(7)
 SPEC_CONSTANT, SPEC_RGB_ALBEDO_SRGB, SPEC_RGB_ALBEDO_LINEAR, SPEC_D65, SPEC_TEXTURE_SRGB, SPEC_PRESET = range(6)
 LIGHT_POINT, LIGHT_SPOT, LIGHT_DIRECTIONAL = 3, 4, 5
+SHARD_MODES = {"tile": 0, "spp": 1}
+COMM_ID_BYTES = 128
 # TCPT_PRESET_* (include/tcpt.h): presets::au_eta() ... presets::glass_sf11_eta() in the order data/std_tables.bin stores them
 PRESETS = ["au_eta", "au_k", "ag_eta", "ag_k", "cu_eta", "cu_k", "al_eta", "al_k", "cu_zn_eta", "cu_zn_k",
            "glass_bk7_eta", "glass_baf10_eta", "glass_fk51a_eta", "glass_lasf9_eta", "glass_sf5_eta", "glass_sf10_eta", "glass_sf11_eta"]
@@ -62,7 +64,7 @@ class Stats(C.Structure):
                 ("tri_tests", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
                 ("trace_closest_ms", C.c_double), ("trace_shadow_ms", C.c_double), ("shade_ms", C.c_double),
                 ("generate_ms", C.c_double), ("film_ms", C.c_double), ("passes", C.c_uint32), ("max_bvh_depth", C.c_uint32),
-                ("sobol_prefix_ms", C.c_double), ("sobol_prefix_bytes", C.c_uint64)]
+                ("sobol_prefix_ms", C.c_double), ("sobol_prefix_bytes", C.c_uint64), ("reduce_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -75,6 +77,9 @@ EXPORTED_SYMBOLS = [
     "tcpt_scene_add_env_light", "tcpt_scene_add_delta_light", "tcpt_scene_build", "tcpt_render", "tcpt_render_device", "tcpt_finalize_device",
     "tcpt_get_stats", "tcpt_trace", "tcpt_trace_device", "tcpt_sampler_stream", "tcpt_path_samples", "tcpt_get_bvh",
     "tcpt_get_wide_bvh", "tcpt_build_bvh_boxes", "tcpt_rgb_to_coeffs", "tcpt_get_mesh_tangents", "tcpt_upload_flat_scene",
+    "tcpt_comm_get_unique_id", "tcpt_comm_init", "tcpt_comm_destroy", "tcpt_shard_params", "tcpt_render_sharded", "tcpt_render_sharded_device",
+    "tcpt_group_create", "tcpt_group_destroy", "tcpt_group_size", "tcpt_group_context", "tcpt_group_last_error", "tcpt_group_set_tables",
+    "tcpt_group_build", "tcpt_group_render",
 ]
 
 _lib = None
@@ -109,6 +114,14 @@ def load_library() -> C.CDLL:
         "tcpt_path_samples": (I, [P, C.POINTER(RenderParams), up, up, I, fp]),
         "tcpt_get_bvh": (I, [P, I, up, I]), "tcpt_get_wide_bvh": (I, [P, I, up, I, up, up]), "tcpt_build_bvh_boxes": (I, [fp, I, up, I]),
         "tcpt_rgb_to_coeffs": (I, [P, fp, I, fp, ip]), "tcpt_get_mesh_tangents": (I, [P, I, fp, I]),
+        "tcpt_comm_get_unique_id": (I, [C.c_void_p]), "tcpt_comm_init": (I, [P, I, I, C.c_void_p]), "tcpt_comm_destroy": (I, [P]),
+        "tcpt_shard_params": (I, [C.POINTER(RenderParams), I, I, I, C.POINTER(RenderParams)]),
+        "tcpt_render_sharded": (I, [P, C.POINTER(RenderParams), I, fp, fp]),
+        "tcpt_render_sharded_device": (I, [P, C.POINTER(RenderParams), I, C.c_void_p, C.c_void_p]),
+        "tcpt_group_create": (I, [ip, I, C.POINTER(P)]), "tcpt_group_destroy": (None, [P]), "tcpt_group_size": (I, [P]),
+        "tcpt_group_context": (P, [P, I]), "tcpt_group_last_error": (C.c_char_p, [P]),
+        "tcpt_group_set_tables": (I, [P, C.c_void_p, C.c_size_t, fp, C.c_size_t]), "tcpt_group_build": (I, [P, fp]),
+        "tcpt_group_render": (I, [P, C.POINTER(RenderParams), I, fp, fp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -136,6 +149,7 @@ class Context:
         self.handle = C.c_void_p()
         rc = self.lib.tcpt_create(device, C.byref(self.handle))
         self.has_gpu = rc == TCPT_OK
+        self.comm_rank, self.comm_size = 0, 1
         if rc != TCPT_OK and (require_gpu or not self.handle):
             msg = self.last_error()
             self.close()
@@ -157,6 +171,24 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self.check(self.lib.tcpt_set_option(self.handle, name.encode(), int(value)))
+
+    # ---- multi-GPU: the NCCL communicator lives inside libtcpt (include/tcpt.h "multi-GPU")
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load_library().tcpt_comm_get_unique_id(buf)
+        if rc != TCPT_OK:
+            raise TcptError(rc, "tcpt_comm_get_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == COMM_ID_BYTES
+        self.check(self.lib.tcpt_comm_init(self.handle, nranks, rank, C.c_char_p(unique_id)))
+        self.comm_rank, self.comm_size = rank, nranks
+
+    def comm_destroy(self):
+        self.check(self.lib.tcpt_comm_destroy(self.handle))
+        self.comm_rank, self.comm_size = 0, 1
 
     def stats(self) -> dict:
         s = Stats()

@@ -105,6 +105,7 @@ struct DScene {
     const tcpt_flat_geometry* geometries;
     const tcpt_flat_primitive* primitives; uint32_t n_primitives;
     const tcpt_flat_material* materials;
+    const uint8_t* prim_mat_type;   // material type of every primitive (0xff: none), so that filing a hit into its shading bucket is one load
     const DTexture* textures;
     const float* area_list; const float* area_table;
     int32_t light_list[TCPT_MAX_LIGHTS]; uint32_t n_lights;

@@ -4,7 +4,7 @@
 // ordered, t-shrinking, stack-based walk over a 4-WIDE COLLAPSE of the reference's binary tree (include/tcpt_flat.h):
 //   * slab test = math/src/bounds.rs:27-55.  Rays whose origin and reciprocal direction are finite take a NaN-free form of it
 //     (near / far plane picked by the direction's sign, 3-input min / max) that is the same function on those inputs (see
-//     slab4_fast); axis-parallel rays (an infinite reciprocal: 0 * inf = NaN is then possible and the reference's
+//     node_step); axis-parallel rays (an infinite reciprocal: 0 * inf = NaN is then possible and the reference's
 //     compare-selects ignore NaNs in a particular way) run the reference's own sequence of operations (slab_exact);
 //   * triangle test = math/src/ray.rs:44-158 (watertight shear, f64 fallback when an edge function is 0, conservative t > delta_t);
 //   * instance transform = primitive/impls/triangle_mesh.rs:97 (ray parameter t preserved, direction not re-normalised);
@@ -28,6 +28,9 @@
 
 #ifndef TCPT_SORT_FULL
 #define TCPT_SORT_FULL 1          // 1: the hit children of a wide node are visited nearest first, the rest pushed far to near; 0: nearest first, rest unordered
+#endif
+#ifndef TCPT_BOTH_PHASES
+#define TCPT_BOTH_PHASES 0       // 1: no phase vote, every iteration runs a triangle step for the lanes holding triangles and a walking step for the others
 #endif
 #ifndef TCPT_SMEM_STACK
 #define TCPT_SMEM_STACK 0         // traversal-stack entries kept in shared memory (the rest, or all of them when 0, live in local memory)
@@ -197,7 +200,7 @@ struct Traversal {
     __device__ __forceinline__ void result(const TraceShared& S, uint32_t tid, DHit& h) const {
         h.t = TS_F(TS_BT); h.b0 = TS_F(TS_B0); h.b1 = TS_F(TS_B1); h.b2 = TS_F(TS_B2); h.prim = (int)TS_U(TS_BPRIM); h.tri = TS_U(TS_BTRI);
     }
-    __device__ __forceinline__ bool holds_triangles() const { return cur != TCPT_ENTRY_NONE && (cur & TCPT_ENTRY_LEAF) != 0u && blas_sp >= 0; }
+    __device__ __forceinline__ bool holds_triangles() const { return (cur & TCPT_ENTRY_LEAF) != 0u && blas_sp >= 0; }   // (cur is never NONE between steps)
 
     __device__ __forceinline__ void push(TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t v) {
 #if TCPT_SMEM_STACK > 0
@@ -218,7 +221,7 @@ struct Traversal {
 
     // Tests the first triangle of the pending leaf range.  ANY = Scene::intersect_p (scene.rs:93-103): returns true (ray finished) at the first accepted triangle.
     template <bool ANY, bool COUNT>
-    __device__ __forceinline__ bool tri_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* n_tri) {
+    __device__ __forceinline__ bool tri_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t* n_tri) {
         const uint32_t bslot = entry_slot(cur);
         cur = entry_more(cur) != 0u ? cur + TCPT_ENTRY_ONE_ITEM : TCPT_ENTRY_NONE;
         const size_t s = 3 * (size_t)bslot;
@@ -247,27 +250,15 @@ struct Traversal {
                 limit = fminf(t_max, cull_limit(t));
             }
         }
-        return false;
+        return advance(S, tid, stack);
     }
 
-    // One walking step: take the next entry off the stack if the lane has nothing at hand, open the instance of a TLAS item, visit a
-    // wide node (four slab tests; the nearest hit child is looked at next, the others are pushed).  Returns true when the ray is
-    // finished (stack empty and nothing at hand).
+    // One walking step: open the instance of a TLAS item if that is what the lane holds, then visit a wide node (four slab tests; the
+    // nearest hit child is looked at next, the others are pushed).  Returns true when the ray is finished.
     template <bool COUNT>
     __device__ __forceinline__ bool node_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t* n_box) {
-        if (cur == TCPT_ENTRY_NONE) {
-            if (sp == blas_sp) {   // this BLAS is exhausted: back in the TLAS, with the Render-space ray
-                blas_sp = -1;
-                r.o = f3(TS_F(TS_OX), TS_F(TS_OY), TS_F(TS_OZ));
-                r.inv_d = f3(TS_F(TS_WIX), TS_F(TS_WIY), TS_F(TS_WIZ));
-                r.kz = (int)TS_U(TS_WKZ); r.sx = TS_F(TS_WSX); r.sy = TS_F(TS_WSY); r.sz = TS_F(TS_WSZ);
-            }
-            if (sp == 0) return true;
-            cur = pop(S, tid, stack);
-        }
         if (cur & TCPT_ENTRY_LEAF) {
-            if (blas_sp >= 0) return false;   // a triangle range came off the stack: the triangle phase takes it from here
-            // TLAS leaf: open its first primitive, leave the others on the stack
+            // TLAS leaf (a leaf inside a BLAS belongs to the triangle phase): open its first primitive, leave the others on the stack
             const uint32_t tslot = entry_slot(cur);
             if (entry_more(cur) != 0u) push(S, tid, stack, cur + TCPT_ENTRY_ONE_ITEM);
             const int2 item = __ldg(&sc.tlas_items[tslot]);
@@ -282,7 +273,7 @@ struct Traversal {
             if (__float_as_uint(dl.x) == __float_as_uint(d.x) && __float_as_uint(dl.y) == __float_as_uint(d.y) && __float_as_uint(dl.z) == __float_as_uint(d.z)) ray_move_origin(r, ol);
             else ray_setup(r, ol, dl);
             blas_sp = sp;
-            if (G.single) { cur = TCPT_ENTRY_LEAF | G.slot_base; return false; }   // SingleTriangle: straight to the triangle test, no boxes
+            if (G.single) { cur = TCPT_ENTRY_LEAF | G.slot_base; return false; }   // SingleTriangle: straight to the triangle test, no boxes (cur != NONE: nothing to advance)
             cur = G.node_base;   // the root wide node of the BLAS
         }
         // ---- wide-node visit: rows {lo.x, hi.x, lo.y, hi.y, lo.z, hi.z} x 4 children, then the children's entries and item counts
@@ -328,16 +319,33 @@ struct Traversal {
         if (e3 != TCPT_ENTRY_NONE) push(S, tid, stack, e3);
         if (e2 != TCPT_ENTRY_NONE) push(S, tid, stack, e2);
         if (e1 != TCPT_ENTRY_NONE) push(S, tid, stack, e1);
-        cur = e0;   // NONE when nothing was hit: the next step pops
+        cur = e0;   // NONE when nothing was hit
+        return advance(S, tid, stack);
+    }
+
+    // The cheap transitions, taken eagerly at the end of a step so that a lane enters the next iteration with a wide node, an instance
+    // or a triangle at hand -- or is finished NOW: with nothing at hand, the ray is done when the stack is empty; a stack back at
+    // its height of BLAS entry means this instance is exhausted (back to the Render-space ray); otherwise the next entry comes off.
+    // (As separate walking steps these cost every ray one or two of its five or so iterations: rays here are short.)
+    __device__ __forceinline__ bool advance(TraceShared& S, uint32_t tid, uint32_t* stack) {
+        if (cur != TCPT_ENTRY_NONE) return false;
+        if (sp == 0) return true;
+        if (sp == blas_sp) {
+            blas_sp = -1;
+            r.o = f3(TS_F(TS_OX), TS_F(TS_OY), TS_F(TS_OZ));
+            r.inv_d = f3(TS_F(TS_WIX), TS_F(TS_WIY), TS_F(TS_WIZ));
+            r.kz = (int)TS_U(TS_WKZ); r.sx = TS_F(TS_WSX); r.sy = TS_F(TS_WSY); r.sz = TS_F(TS_WSZ);
+        }
+        cur = pop(S, tid, stack);
         return false;
     }
 };
 
 #ifndef TCPT_REFILL_IDLE_LANES
-#define TCPT_REFILL_IDLE_LANES 12  // a warp fetches new rays once this many of its lanes are idle (swept 4..16 with the pooled fetch: 12 is best)
+#define TCPT_REFILL_IDLE_LANES 16  // a warp fetches new rays once this many of its lanes are idle (4-wide tree, eager advance: 8 / 12 / 16 / 20 give 31.8 / 30.4 / 29.9 / 30.0 ms of tracing per step)
 #endif
 #ifndef TCPT_TRI_PHASE_LANES
-#define TCPT_TRI_PHASE_LANES 8    // a warp runs a triangle iteration once this many lanes hold pending triangles
+#define TCPT_TRI_PHASE_LANES 8    // a warp runs a triangle iteration once this many lanes hold pending triangles (4 / 8 / 12: 31.4 / 30.4 / 30.9 ms; no vote at all, both phases every iteration: 31.2)
 #endif
 #define TCPT_LOCAL_STACK (TCPT_TRAVERSAL_STACK - TCPT_SMEM_STACK)
 
@@ -399,14 +407,21 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
         do {
             const bool has_tri = ray != NONE && T.holds_triangles();
             const bool walks = ray != NONE && !has_tri;
+#if TCPT_BOTH_PHASES
+            // no vote: the lanes holding triangles test one, then the walking lanes visit a node, every iteration
+            bool finished = false;
+            if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, stack, n_tri);
+            if (walks) finished = T.template node_step<COUNT>(sc, S, tid, stack, n_box);
+#else
             const uint32_t tri_mask = __ballot_sync(FULL, has_tri);
             const uint32_t node_mask = __ballot_sync(FULL, walks);
             bool finished = false;
             if (tri_mask != 0u && ((uint32_t)__popc(tri_mask) >= (uint32_t)TCPT_TRI_PHASE_LANES || node_mask == 0u)) {
-                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, n_tri);
+                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, stack, n_tri);
             } else {
                 if (walks) finished = T.template node_step<COUNT>(sc, S, tid, stack, n_box);
             }
+#endif
             if (finished) { fin = ray; ray = NONE; T.cur = TCPT_ENTRY_NONE; }
             n_idle_now = (uint32_t)__popc(__ballot_sync(FULL, ray == NONE));
         } while (n_idle_now < stop_at);

@@ -19,7 +19,7 @@
 #define TCPT_SHADE_MIN_BLOCKS_LAMBERT 4
 #endif
 #ifndef TCPT_TRACE_MIN_BLOCKS
-#define TCPT_TRACE_MIN_BLOCKS 7   // 72 registers: 28 warps per SM (swept 5..8: 3.47 / 3.22 / 3.15 / 3.18 ms per spp)
+#define TCPT_TRACE_MIN_BLOCKS 8   // 64 registers + 13 KB of shared memory per block: 32 warps per SM (measured 6 / 7 / 8 blocks: 35.7 / 33.5 / 32.1 ms per step)
 #endif
 #define TCPT_BUCKET_STRIDE 10
 
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
 // only matters if it is a light, so non-emissive hits go to a terminal bucket that just hands the path to the sensor.
 __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim, bool killed) {
     if (prim < 0) return 7u;                                     // miss: environment lookup only
-    const int t = sc.materials[sc.primitives[prim].material].type;
+    const int t = (int)__ldg(sc.prim_mat_type + prim);
     if (killed && t != TCPT_MAT_EMISSIVE) return 8u;
     return t == TCPT_MAT_CLEARCOAT_PBR ? 0u : t == TCPT_MAT_SIMPLE_PBR ? 1u : t == TCPT_MAT_PLASTIC ? 2u : t == TCPT_MAT_GLASS ? 3u : t == TCPT_MAT_METAL ? 4u
          : t == TCPT_MAT_LAMBERT ? 5u : 6u;

@@ -1,11 +1,15 @@
 // libtcpt: context, device memory, frame orchestration and the C ABI of include/tcpt.h / include/tcpt_flat.h.
 // Product code.  There is no CPU fallback: without a usable sm_100 device every computing entry point fails with TCPT_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is opened at run time by tcpt_comm_init (see NcclApi)
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tcpt.h"
@@ -28,6 +32,40 @@ struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_h
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
+
+// NCCL entry points, resolved from libnccl.so.2 when the first communicator is made.  libtcpt carries no link-time dependency on NCCL:
+// a single-GPU host never loads it, and inside a process that already holds an NCCL (PyTorch's) the same copy is reused by soname.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        static std::mutex m;
+        std::lock_guard<std::mutex> lock(m);
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+        if (!handle) { error = std::string("cannot open libnccl.so.2: ") + dlerror(); return false; }
+        bool ok = true;
+        auto sym = [&](const char* name) { void* p = dlsym(handle, name); if (!p) { ok = false; error = std::string("libnccl lacks ") + name; } return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        Reduce = (decltype(Reduce))sym("ncclReduce");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!ok) { dlclose(handle); handle = nullptr; }
+        return ok;
+    }
+};
+static NcclApi g_nccl;
 
 struct tcpt_ctx {
     int device = 0;
@@ -59,6 +97,9 @@ struct tcpt_ctx {
     uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0, pass_rows = 0; size_t prefix_cap = 0;
     double prefix_build_ms = 0.0;
     uint64_t default_slots = 0;  // path-slot budget of a pass when the caller gives none (see render_into)
+    // multi-GPU: this context's rank in an NCCL communicator (tcpt_comm_init); the ctx owns the communicator
+    ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
+    cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
 };
 
 namespace {
@@ -487,6 +528,9 @@ int tcpt_create(int device_id, tcpt_ctx** out) {
 void tcpt_destroy(tcpt_ctx* ctx) {
     if (!ctx) return;
     if (ctx->stream) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (ctx->ev_r0) cudaEventDestroy(ctx->ev_r0);
+    if (ctx->ev_r1) cudaEventDestroy(ctx->ev_r1);
     free_scene(ctx->dev);
     for (void* p : ctx->st_allocs) cudaFree(p);
     unpin_all(ctx);
@@ -684,6 +728,11 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     UP(upload(ctx, db, s->geometries, s->n_geometries, &v.geometries));
     UP(upload(ctx, db, s->primitives, s->n_primitives, &v.primitives)); v.n_primitives = s->n_primitives;
     UP(upload(ctx, db, s->materials, s->n_materials, &v.materials));
+    {
+        std::vector<uint8_t> pt(s->n_primitives, 0xff);
+        for (uint32_t i = 0; i < s->n_primitives; ++i) { const int m = s->primitives[i].material; if (m >= 0 && (uint32_t)m < s->n_materials) pt[i] = (uint8_t)s->materials[m].type; }
+        UP(upload(ctx, db, pt.data(), pt.size(), &v.prim_mat_type));
+    }
     const uint8_t* tex_bytes; UP(upload(ctx, db, s->texture_bytes, s->n_texture_bytes, &tex_bytes));
     std::vector<DTexture> dt(s->n_textures);
     for (uint32_t i = 0; i < s->n_textures; ++i) dt[i] = DTexture{tex_bytes + s->textures[i].offset, s->textures[i].width, s->textures[i].height, s->textures[i].channels, 0};
@@ -772,6 +821,204 @@ int tcpt_render(tcpt_ctx* ctx, const tcpt_render_params* params, float* out_acc,
         CU(cudaGetLastError());
         if ((rc = copy_out(ctx, 1, out_srgb, ctx->film_srgb, n * sizeof(float))) != TCPT_OK) return rc;
     }
+    return TCPT_OK;
+}
+
+
+// ---------------------------------------------------------------- multi-GPU: NCCL inside the library
+int tcpt_comm_get_unique_id(void* id128) {
+    if (!id128) return TCPT_ERR_INVALID;
+    if (!g_nccl.load()) return TCPT_ERR_CUDA;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return TCPT_ERR_CUDA;
+    static_assert(sizeof id == TCPT_COMM_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id128, &id, sizeof id);
+    return TCPT_OK;
+}
+
+int tcpt_comm_init(tcpt_ctx* ctx, int nranks, int rank, const void* id128) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    if (!g_nccl.load()) return fail(ctx, TCPT_ERR_CUDA, g_nccl.error);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId id; std::memcpy(&id, id128, sizeof id);
+    const ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != ncclSuccess) { ctx->comm = nullptr; return fail(ctx, TCPT_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+    ctx->comm_rank = rank; ctx->comm_size = nranks;
+    if (!ctx->ev_r0) { cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1); }
+    return TCPT_OK;
+}
+
+int tcpt_comm_destroy(tcpt_ctx* ctx) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    if (ctx->comm) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ctx->comm_rank = 0; ctx->comm_size = 1;
+    return TCPT_OK;
+}
+
+int tcpt_shard_params(const tcpt_render_params* job, int shard_mode, int rank, int nranks, tcpt_render_params* out) {
+    if (!job || !out || nranks < 1 || rank < 0 || rank >= nranks) return TCPT_ERR_INVALID;
+    if (job->row_stride != 0 || job->row_offset != 0) return TCPT_ERR_INVALID;   // the job describes the whole frame
+    *out = *job;
+    const uint32_t s0 = (job->spp_begin == 0 && job->spp_end == 0) ? 0 : job->spp_begin;
+    const uint32_t s1 = (job->spp_begin == 0 && job->spp_end == 0) ? job->spp : job->spp_end;
+    if (s1 > job->spp || s0 > s1) return TCPT_ERR_INVALID;
+    if (shard_mode == TCPT_SHARD_TILE) {
+        // rows y with y % nranks == rank, every sample of the job: each pixel is summed on ONE rank in the reference's sample order
+        // (sensor.rs:76-77), the other ranks add exact zeros, so the reduced film is bitwise the one-GPU film
+        out->row_offset = (uint32_t)rank; out->row_stride = (uint32_t)nranks; out->spp_begin = s0; out->spp_end = s1;
+    } else if (shard_mode == TCPT_SHARD_SPP) {
+        // an equal slice of the job's sample indices for every pixel: best balance; per-pixel sums are re-associated across ranks
+        const uint64_t n = s1 - s0;
+        out->spp_begin = s0 + (uint32_t)(n * (uint64_t)rank / (uint64_t)nranks);
+        out->spp_end = s0 + (uint32_t)(n * (uint64_t)(rank + 1) / (uint64_t)nranks);
+    } else return TCPT_ERR_INVALID;
+    return TCPT_OK;
+}
+
+int tcpt_render_sharded_device(tcpt_ctx* ctx, const tcpt_render_params* job, int shard_mode, void* dev_acc, void* stream) {
+    if (!ctx || !job || !dev_acc) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    if (ctx->comm_size > 1 && !ctx->comm) return fail(ctx, TCPT_ERR_INVALID, "render_sharded: call tcpt_comm_init first");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    tcpt_render_params mine;
+    if (tcpt_shard_params(job, shard_mode, ctx->comm_rank, ctx->comm_size, &mine) != TCPT_OK) return fail(ctx, TCPT_ERR_INVALID, "render_sharded: bad job (row shard or sample range) or shard mode");
+    reset_stats(ctx);
+    if (s != ctx->stream) CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, s));
+    // a rank without samples (more ranks than sample indices) renders nothing and contributes zeros
+    if (mine.spp_begin != mine.spp_end) { int rc = render_into(ctx, &mine, (float*)dev_acc, s); if (rc) return rc; }
+    if (ctx->comm_size > 1) {
+        // the ONE collective of a frame: sum of the Sensor accumulators onto rank 0, in place, on the rendering stream
+        if (!ctx->ev_r0) { cudaEventCreate(&ctx->ev_r0); cudaEventCreate(&ctx->ev_r1); }
+        CU(cudaEventRecord(ctx->ev_r0, s));
+        const ncclResult_t r = g_nccl.Reduce(dev_acc, dev_acc, (size_t)job->width * job->height * 3, ncclFloat32, ncclSum, 0, ctx->comm, s);
+        if (r != ncclSuccess) return fail(ctx, TCPT_ERR_CUDA, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
+        CU(cudaEventRecord(ctx->ev_r1, s));
+    }
+    CU(cudaEventRecord(ctx->ev1, s));
+    CU(cudaEventSynchronize(ctx->ev1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.render_ms = ms;
+    if (ctx->comm_size > 1) { float rms = 0; if (cudaEventElapsedTime(&rms, ctx->ev_r0, ctx->ev_r1) == cudaSuccess) ctx->stats.reduce_ms = rms; }
+    collect_stage_times(ctx);
+    return fetch_stats(ctx);
+}
+
+int tcpt_render_sharded(tcpt_ctx* ctx, const tcpt_render_params* job, int shard_mode, float* out_acc, float* out_srgb) {
+    if (!ctx || !job) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    const bool root = ctx->comm_rank == 0;
+    if (root && !out_acc && !out_srgb) return TCPT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)job->width * job->height * 3;
+    if (ctx->film_cap < n) {
+        if (ctx->film_acc) cudaFree(ctx->film_acc);
+        if (ctx->film_srgb) cudaFree(ctx->film_srgb);
+        ctx->film_acc = ctx->film_srgb = nullptr; ctx->film_cap = 0;
+        CU(cudaMalloc((void**)&ctx->film_acc, n * sizeof(float)));
+        CU(cudaMalloc((void**)&ctx->film_srgb, n * sizeof(float)));
+        ctx->film_cap = n;
+    }
+    CU(cudaMemsetAsync(ctx->film_acc, 0, n * sizeof(float), ctx->stream));
+    int rc = tcpt_render_sharded_device(ctx, job, shard_mode, ctx->film_acc, nullptr);
+    if (rc || !root) return rc;
+    // rank 0 holds the whole film: Sensor::to_rgb over the job's sample count, one device -> host copy per requested buffer
+    const uint32_t s0 = (job->spp_begin == 0 && job->spp_end == 0) ? 0 : job->spp_begin, s1 = (job->spp_begin == 0 && job->spp_end == 0) ? job->spp : job->spp_end;
+    if (out_acc && (rc = copy_out(ctx, 0, out_acc, ctx->film_acc, n * sizeof(float))) != TCPT_OK) return rc;
+    if (out_srgb) {
+        k_finalize<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->film_acc, ctx->film_srgb, (uint32_t)n, (float)(s1 - s0),
+                                                                    job->integrator == TCPT_INTEGRATOR_NORMAL ? 2 : job->integrator == TCPT_INTEGRATOR_ALBEDO ? 1 : 0);
+        CU(cudaGetLastError());
+        if ((rc = copy_out(ctx, 1, out_srgb, ctx->film_srgb, n * sizeof(float))) != TCPT_OK) return rc;
+    }
+    return TCPT_OK;
+}
+
+
+// ---------------------------------------------------------------- one host process, several GPUs (the shape a Rust `GpuRendererImage` would use)
+struct tcpt_group {
+    std::vector<tcpt_ctx*> ctx;
+    std::string error;
+};
+
+int tcpt_group_create(const int* device_ids, int n, tcpt_group** out) {
+    if (!out || !device_ids || n < 1) return TCPT_ERR_INVALID;
+    *out = nullptr;
+    tcpt_group* g = new tcpt_group();
+    *out = g;   // returned even on failure so the message can be read; destroy it
+    for (int i = 0; i < n; ++i) {
+        tcpt_ctx* c = nullptr;
+        const int rc = tcpt_create(device_ids[i], &c);
+        if (c) g->ctx.push_back(c);
+        if (rc != TCPT_OK) { g->error = c ? c->error : "tcpt_create failed"; return rc; }
+    }
+    if (n > 1) {
+        // one communicator clique over the group's devices: a unique id, then every rank's ncclCommInitRank inside one NCCL group call
+        // (a single thread may only initialise several ranks that way)
+        if (!g_nccl.load()) { g->error = g_nccl.error; return TCPT_ERR_CUDA; }
+        ncclUniqueId id;
+        if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g->error = "ncclGetUniqueId failed"; return TCPT_ERR_CUDA; }
+        g_nccl.GroupStart();
+        ncclResult_t bad = ncclSuccess;
+        for (int i = 0; i < n; ++i) {
+            cudaSetDevice(g->ctx[i]->device);
+            const ncclResult_t r = g_nccl.CommInitRank(&g->ctx[i]->comm, n, id, i);
+            if (r != ncclSuccess) bad = r;
+            g->ctx[i]->comm_rank = i; g->ctx[i]->comm_size = n;
+        }
+        const ncclResult_t e = g_nccl.GroupEnd();
+        if (bad != ncclSuccess || e != ncclSuccess) {
+            for (tcpt_ctx* c : g->ctx) c->comm = nullptr;
+            g->error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(bad != ncclSuccess ? bad : e);
+            return TCPT_ERR_CUDA;
+        }
+    }
+    return TCPT_OK;
+}
+
+void tcpt_group_destroy(tcpt_group* g) {
+    if (!g) return;
+    for (tcpt_ctx* c : g->ctx) tcpt_destroy(c);
+    delete g;
+}
+
+int tcpt_group_size(const tcpt_group* g) { return g ? (int)g->ctx.size() : 0; }
+tcpt_ctx* tcpt_group_context(tcpt_group* g, int i) { return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[i] : nullptr; }
+const char* tcpt_group_last_error(const tcpt_group* g) { return g ? g->error.c_str() : "null group"; }
+
+int tcpt_group_set_tables(tcpt_group* g, const void* std_tables, size_t std_len, const float* rgb2spec, size_t rgb2spec_floats) {
+    if (!g) return TCPT_ERR_INVALID;
+    for (tcpt_ctx* c : g->ctx) { const int rc = tcpt_set_tables(c, std_tables, std_len, rgb2spec, rgb2spec_floats); if (rc) { g->error = c->error; return rc; } }
+    return TCPT_OK;
+}
+
+// Scene::build on context 0 (the scene is described through tcpt_scene_add_* on tcpt_group_context(g, 0)), then the same flattened
+// scene is uploaded to every other device: the scene is small and read-only, every GPU keeps a replica
+int tcpt_group_build(tcpt_group* g, const float cam_pos[3]) {
+    if (!g || g->ctx.empty()) return TCPT_ERR_INVALID;
+    int rc = tcpt_scene_build(g->ctx[0], cam_pos);
+    if (rc) { g->error = g->ctx[0]->error; return rc; }
+    for (size_t i = 1; i < g->ctx.size(); ++i) {
+        g->ctx[i]->host.tables = g->ctx[0]->host.tables;   // one_light_always_on reads the dense tables
+        rc = tcpt_upload_flat_scene(g->ctx[i], &g->ctx[0]->flat.view);
+        if (rc) { g->error = g->ctx[i]->error; return rc; }
+    }
+    return TCPT_OK;
+}
+
+// One complete frame from all GPUs of the group: one host thread per GPU (tcpt_render_sharded), out_* filled from device 0.
+int tcpt_group_render(tcpt_group* g, const tcpt_render_params* job, int shard_mode, float* out_acc, float* out_srgb) {
+    if (!g || g->ctx.empty() || !job || (!out_acc && !out_srgb)) return TCPT_ERR_INVALID;
+    const size_t n = g->ctx.size();
+    std::vector<int> rcs(n, TCPT_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; ++i) th.emplace_back([&, i] { rcs[i] = tcpt_render_sharded(g->ctx[i], job, shard_mode, nullptr, nullptr); });
+    rcs[0] = tcpt_render_sharded(g->ctx[0], job, shard_mode, out_acc, out_srgb);
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < n; ++i) if (rcs[i]) { g->error = g->ctx[i]->error; return rcs[i]; }
     return TCPT_OK;
 }
 

@@ -1,7 +1,12 @@
-"""Frame sharding across the GPUs of one box: one process per GPU (torch.distributed), scene replicated, the frame split by
-image rows or by sample-index range, and ONE reduction of the film accumulators per frame (NCCL over NVLink on GPUs; the
-same code runs on gloo/CPU tensors in tests).  The reference has no distributed path; the only shared
-output of the hot path is the per-pixel Sensor accumulator (sensor.rs:76-77), so a sum of accumulators is the whole exchange.
+"""Frame sharding across the GPUs of one box.  One process per GPU; the scene is replicated; the frame is split by image rows or
+by sample-index range; ONE reduction of the film accumulators per frame.  The reference has no distributed path (SURVEY.md
+section 8e); the only shared output of the hot path is the per-pixel Sensor accumulator (sensor.rs:76-77), so a sum of
+accumulators is the whole exchange.
+
+The exchange itself lives INSIDE libtcpt (include/tcpt.h "multi-GPU"): `tcpt_comm_init` makes an NCCL communicator owned by the
+context, `tcpt_render_sharded` renders this rank's shard, runs one `ncclReduce` onto rank 0 and hands back one complete frame
+there.  torch.distributed is only the plumbing that carries the 128-byte NCCL unique id from rank 0 to the other ranks
+(`init_comm`); a host without PyTorch passes the id over any transport it likes.
 
   mode "tile": rank r renders rows y with y % world == r and ALL samples -> every pixel is summed in the reference's
                sample order on one GPU, other ranks contribute exact zeros: the reduced film is bitwise equal to 1 GPU.
@@ -25,7 +30,8 @@ class Shard:
 
 
 def shard_plan(rank: int, world: int, mode: str, spp: int, spp_begin: int = 0, spp_end: int | None = None) -> Shard:
-    """The slice of the frame rank `rank` of `world` renders.  [spp_begin, spp_end) restricts the whole job to a sample window."""
+    """The slice of the frame rank `rank` of `world` renders (the rule of tcpt_shard_params, restated for host-side planning and for
+    the CPU tests).  [spp_begin, spp_end) restricts the whole job to a sample window."""
     spp_end = spp if spp_end is None else spp_end
     if not (0 <= rank < world) or not (0 <= spp_begin <= spp_end <= spp):
         raise ValueError("bad shard request")
@@ -39,8 +45,25 @@ def shard_plan(rank: int, world: int, mode: str, spp: int, spp_begin: int = 0, s
     raise ValueError(f"unknown shard mode {mode!r}")
 
 
+def init_comm(ctx, rank: int | None = None, world: int | None = None) -> None:
+    """Give `ctx` (a capi.Context on this rank's GPU) its NCCL communicator.  Collective: every rank calls it.  The unique id is made on
+    rank 0 (tcpt_comm_get_unique_id) and carried by torch.distributed's broadcast; everything after that is libtcpt's own NCCL."""
+    import torch.distributed as dist
+    from . import capi
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return
+    box = [capi.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(world, rank, box[0])
+
+
 def reduce_film(acc, dst: int = 0, all_ranks: bool = False):
-    """Sum the film accumulators over ranks (in place on `dst`, or everywhere with all_ranks).  One collective per frame."""
+    """Sum film accumulators held in torch tensors over ranks (host-logic tests on gloo / CPU tensors; the GPU path reduces inside
+    libtcpt, see render_sharded)."""
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return acc
@@ -52,30 +75,20 @@ def reduce_film(acc, dst: int = 0, all_ranks: bool = False):
 
 
 def render_sharded(image, sampler, mode: str = "tile", device_acc=None, stream=None, spp_window=None, max_slots: int = 0):
-    """Render this rank's shard of `image` (a RendererImage) into a device accumulator (torch CUDA tensor [H, W, 3] f32, zeroed
-    by the caller), then reduce to rank 0.  Returns the (reduced on rank 0) accumulator tensor."""
+    """Render this rank's shard of `image` (a RendererImage) and reduce to rank 0 through libtcpt's communicator (init_comm first).
+    With `device_acc` (a zeroed torch CUDA tensor [H, W, 3] f32) the film stays on the device (tcpt_render_sharded_device) and the
+    tensor is returned; without it, rank 0's `image.pixels` / `image.accumulators` receive the complete frame (tcpt_render_sharded)."""
     import ctypes as C
 
-    import torch
-    import torch.distributed as dist
     from . import capi
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    r = image.renderer
-    spp = r.args.spp
-    w0, w1 = spp_window if spp_window else (0, spp)
-    shard = shard_plan(rank, world, mode, spp, w0, w1)
-    ctx = r.args.scene.ctx
     if device_acc is None:
-        device_acc = torch.zeros((image.height, image.width, 3), dtype=torch.float32, device=f"cuda:{torch.cuda.current_device()}")
-    p = r.params(sampler, max_slots=max_slots, **shard.as_kwargs())
-    if p.spp_begin == 0 and p.spp_end == 0:
-        p.spp_end = spp  # an explicit full range (0,0 would also mean "all")
-    if shard.spp_begin == shard.spp_end:
-        pass  # nothing to render on this rank (more ranks than samples): contributes zeros
-    else:
-        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        ctx.check(ctx.lib.tcpt_render_device(ctx.handle, C.byref(p), C.c_void_p(device_acc.data_ptr()), C.c_void_p(s)))
-        image.stats = ctx.stats()
-    reduce_film(device_acc, dst=0)
+        return image.render_sharded(sampler, mode=mode, spp_window=spp_window, max_slots=max_slots)
+    import torch
+    r = image.renderer
+    ctx = r.args.scene.ctx
+    kw = {"spp_begin": spp_window[0], "spp_end": spp_window[1]} if spp_window else {}
+    p = r.params(sampler, max_slots=max_slots, **kw)
+    s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    ctx.check(ctx.lib.tcpt_render_sharded_device(ctx.handle, C.byref(p), capi.SHARD_MODES[mode], C.c_void_p(device_acc.data_ptr()), C.c_void_p(s)))
+    image.stats = ctx.stats()
     return device_acc

@@ -136,6 +136,27 @@ class RendererImage:                  # renderer/src/renderer.rs:101-149
         self.stats = ctx.stats()
         return self
 
+    def render_sharded(self, sampler=ZSobolSampler, mode: str = "tile", want_accumulators: bool = True, spp_window=None, max_slots: int = 0) -> "RendererImage":
+        """One complete frame from every GPU of the communicator (tcpt_comm_init on each rank's context): every rank calls this with the
+        same arguments, renders its shard (mode "tile": image rows y % N == rank, bitwise equal to one GPU; "spp": an equal slice of the
+        sample indices), ONE ncclReduce inside libtcpt sums the film onto rank 0, which tone-maps and copies out: `pixels` /
+        `accumulators` are filled on rank 0 only.  spp_window = (begin, end) restricts the whole job to a block of sample indices."""
+        r = self.renderer
+        ctx = r.args.scene.ctx
+        if not r.args.scene.built:
+            r.args.scene.build(r.args.camera)
+        kw = {"spp_begin": spp_window[0], "spp_end": spp_window[1]} if spp_window else {}
+        p = r.params(sampler, max_slots=max_slots, **kw)
+        root = ctx.comm_rank == 0
+        if root:
+            ctx.set_option("pin_host_buffers", 1)
+            self._pinned_ctx = ctx
+        ctx.check(ctx.lib.tcpt_render_sharded(ctx.handle, C.byref(p), capi.SHARD_MODES[mode],
+                                              capi.as_ptr(self.accumulators, C.c_float) if (root and want_accumulators) else None,
+                                              capi.as_ptr(self.pixels, C.c_float) if root else None))
+        self.stats = ctx.stats()
+        return self
+
     def __del__(self):
         ctx = getattr(self, "_pinned_ctx", None)
         if ctx is not None and getattr(ctx, "handle", None):
