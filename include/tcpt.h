@@ -101,6 +101,7 @@ typedef struct {
     double sobol_prefix_ms;  /* device time of the last build of the ZSobol pixel-prefix table (once per resolution / spp; 0 when reused) */
     uint64_t sobol_prefix_bytes; /* size of that table in device memory */
     double reduce_ms;        /* device time of the film reduce of the last tcpt_render_sharded* (0 on one GPU) */
+    uint32_t trace_launches, shade_launches; /* launches of the traversal kernels / the shading kernels among kernel_launches */
 } tcpt_stats;
 
 /* ---- context.  tcpt_create returns TCPT_ERR_CUDA when no sm_100 device is usable; *out is then still a context on which only

@@ -6,6 +6,10 @@ use std::os::raw::{c_char, c_int, c_void};
 pub struct TcptCtx {
     _opaque: [u8; 0],
 }
+#[repr(C)]
+pub struct TcptGroup {
+    _opaque: [u8; 0],
+}
 
 pub const TCPT_OK: c_int = 0;
 pub const TCPT_ERR_INVALID: c_int = -1;
@@ -123,6 +127,9 @@ pub struct TcptStats {
     pub max_bvh_depth: u32,
     pub sobol_prefix_ms: f64,
     pub sobol_prefix_bytes: u64,
+    pub reduce_ms: f64,
+    pub trace_launches: u32,
+    pub shade_launches: u32,
 }
 
 unsafe extern "C" {
@@ -149,4 +156,24 @@ unsafe extern "C" {
     pub fn tcpt_finalize_device(ctx: *mut TcptCtx, dev_acc: *const c_void, width: u32, height: u32, spp: u32, dev_srgb: *mut c_void,
                                 stream: *mut c_void) -> c_int;
     pub fn tcpt_get_stats(ctx: *const TcptCtx, out: *mut TcptStats) -> c_int;
+
+    // multi-GPU: one context per GPU; the library owns the NCCL communicator (include/tcpt.h "multi-GPU")
+    pub fn tcpt_comm_get_unique_id(id128: *mut c_void) -> c_int;
+    pub fn tcpt_comm_init(ctx: *mut TcptCtx, nranks: c_int, rank: c_int, id128: *const c_void) -> c_int;
+    pub fn tcpt_comm_destroy(ctx: *mut TcptCtx) -> c_int;
+    pub fn tcpt_shard_params(job: *const TcptRenderParams, shard_mode: c_int, rank: c_int, nranks: c_int, out: *mut TcptRenderParams) -> c_int;
+    pub fn tcpt_render_sharded(ctx: *mut TcptCtx, job: *const TcptRenderParams, shard_mode: c_int, out_acc: *mut f32, out_srgb: *mut f32) -> c_int;
+    pub fn tcpt_render_sharded_device(ctx: *mut TcptCtx, job: *const TcptRenderParams, shard_mode: c_int, dev_acc: *mut c_void, stream: *mut c_void) -> c_int;
+    // one host process, N GPUs: what GpuRendererImage::render_multi binds
+    pub fn tcpt_group_create(device_ids: *const c_int, n: c_int, out: *mut *mut TcptGroup) -> c_int;
+    pub fn tcpt_group_destroy(g: *mut TcptGroup);
+    pub fn tcpt_group_size(g: *const TcptGroup) -> c_int;
+    pub fn tcpt_group_context(g: *mut TcptGroup, i: c_int) -> *mut TcptCtx;
+    pub fn tcpt_group_last_error(g: *const TcptGroup) -> *const c_char;
+    pub fn tcpt_group_set_tables(g: *mut TcptGroup, std_tables: *const c_void, std_len: usize, rgb2spec: *const f32, rgb2spec_floats: usize) -> c_int;
+    pub fn tcpt_group_build(g: *mut TcptGroup, cam_pos: *const f32) -> c_int;
+    pub fn tcpt_group_render(g: *mut TcptGroup, job: *const TcptRenderParams, shard_mode: c_int, out_acc: *mut f32, out_srgb: *mut f32) -> c_int;
 }
+pub const TCPT_SHARD_TILE: c_int = 0;
+pub const TCPT_SHARD_SPP: c_int = 1;
+pub const TCPT_COMM_ID_BYTES: usize = 128;

@@ -171,6 +171,25 @@ impl GpuRendererImage {
             panic!("tcpt_render: {}", last_error(self.ctx)); // the reference panics on errors too (main.rs:61,91,138,235)
         }
     }
+    /// One complete frame from every GPU of the communicator this context belongs to (`tcpt_comm_init`, one process per GPU): every
+    /// rank calls it with the same image; rank 0's `pixels` / `accumulators` receive the frame after ONE ncclReduce inside the library.
+    /// `TCPT_SHARD_TILE` reproduces the one-GPU film bit for bit, `TCPT_SHARD_SPP` balances best.
+    pub fn render_sharded<S: GpuSampler>(&mut self, shard_mode: i32) {
+        self.params.sampler = S::ID;
+        let rc = unsafe { tcpt_render_sharded(self.ctx, &self.params, shard_mode, self.accumulators.as_mut_ptr() as *mut f32, self.pixels.as_mut_ptr() as *mut f32) };
+        if rc != TCPT_OK {
+            panic!("tcpt_render_sharded: {}", last_error(self.ctx));
+        }
+    }
+    /// The same from ONE host process that owns all GPUs of the box (`tcpt_group_create`; the scene was built with `tcpt_group_build`).
+    pub fn render_group<S: GpuSampler>(&mut self, group: *mut TcptGroup, shard_mode: i32) {
+        self.params.sampler = S::ID;
+        let rc = unsafe { tcpt_group_render(group, &self.params, shard_mode, self.accumulators.as_mut_ptr() as *mut f32, self.pixels.as_mut_ptr() as *mut f32) };
+        if rc != TCPT_OK {
+            let msg = unsafe { std::ffi::CStr::from_ptr(tcpt_group_last_error(group)) }.to_string_lossy().into_owned();
+            panic!("tcpt_group_render: {}", msg);
+        }
+    }
     pub fn stats(&self) -> TcptStats {
         let mut s = TcptStats::default();
         unsafe { tcpt_get_stats(self.ctx, &mut s) };

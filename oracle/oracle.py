@@ -44,6 +44,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(LIB))
         _lib.orc_scene_new.restype = C.c_void_p
         _lib.orc_build.restype = C.c_double
+        _lib.orc_trace_mt.restype = C.c_double
         for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_add_single_triangle", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
                      "orc_add_env_light", "orc_add_delta_light", "orc_set_modes", "orc_set_optimised", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
                      "orc_sampler_stream", "orc_get_bvh", "orc_get_mesh_tangents"):
@@ -155,6 +156,14 @@ class OracleScene:
         nb, nt = C.c_uint64(0), C.c_uint64(0)
         self.l.orc_trace(_vp(self.h), _p(rays), len(rays), int(any_hit), _p(out, C.c_int32), C.byref(nb), C.byref(nt))
         return out, nb.value, nt.value
+
+    def trace_mt(self, rays: np.ndarray, any_hit=False, threads=0):
+        """orc_trace over all host threads; returns (hits, seconds, box tests, triangle tests)."""
+        rays = np.ascontiguousarray(rays, dtype=f32)
+        out = np.zeros((len(rays), 6), dtype=np.int32)
+        nb, nt = C.c_uint64(0), C.c_uint64(0)
+        sec = self.l.orc_trace_mt(_vp(self.h), _p(rays), len(rays), int(any_hit), _p(out, C.c_int32), int(threads), C.byref(nb), C.byref(nt))
+        return out, float(sec), nb.value, nt.value
 
     def sobol_probe(self, spp, w, h, seed, px, py, sample_index):
         vals = np.zeros(4, dtype=f32)

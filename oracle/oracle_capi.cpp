@@ -291,13 +291,11 @@ int orc_record_rays(void* h, const orc_render_params* p, float* closest_od, int 
 }
 
 // closest-hit / any-hit of explicit rays.  rays = n x {o[3], d[3], tmax}.  out_hit = n x {prim, tri, t bits, b0 bits, b1 bits, b2 bits} (prim = -1 on miss)
-int orc_trace(void* h, const float* rays, int n, int any_hit, int32_t* out_hit, uint64_t* box_tests, uint64_t* tri_tests) {
-    OrcScene* s = (OrcScene*)h;
-    RayStats st;
-    for (int i = 0; i < n; ++i) {
-        const float* r = rays + 7 * i;
+static void trace_range(OrcScene* s, const float* rays, int b, int e, int any_hit, int32_t* out_hit, RayStats& st) {
+    for (int i = b; i < e; ++i) {
+        const float* r = rays + 7 * (size_t)i;
         Ray ray{Vec3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5])};
-        int32_t* o = out_hit + 6 * i;
+        int32_t* o = out_hit + 6 * (size_t)i;
         if (any_hit) {
             o[0] = s->scene.intersect_p(ray, r[6], &st) ? 1 : 0;
             o[1] = o[2] = o[3] = o[4] = o[5] = 0;
@@ -309,9 +307,40 @@ int orc_trace(void* h, const float* rays, int n, int any_hit, int32_t* out_hit, 
             } else { o[0] = -1; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
         }
     }
+}
+int orc_trace(void* h, const float* rays, int n, int any_hit, int32_t* out_hit, uint64_t* box_tests, uint64_t* tri_tests) {
+    OrcScene* s = (OrcScene*)h;
+    RayStats st;
+    trace_range(s, rays, 0, n, any_hit, out_hit, st);
     if (box_tests) *box_tests = st.tc.box_tests;
     if (tri_tests) *tri_tests = st.tc.tri_tests;
     return 0;
+}
+// the same over `threads` host threads (0 = all cores), blocks of 4096 rays handed out dynamically; returns the wall-clock seconds of
+// the tracing alone (bench.py's CPU figure for the triangle-soup workloads)
+double orc_trace_mt(void* h, const float* rays, int n, int any_hit, int32_t* out_hit, int threads, uint64_t* box_tests, uint64_t* tri_tests) {
+    OrcScene* s = (OrcScene*)h;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    std::vector<RayStats> st(threads);
+    std::atomic<int> next{0};
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int t) {
+        for (;;) {
+            const int b = next.fetch_add(4096);
+            if (b >= n) break;
+            trace_range(s, rays, b, b + 4096 < n ? b + 4096 : n, any_hit, out_hit, st[t]);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+    for (auto& t : pool) t.join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t nb = 0, nt = 0;
+    for (auto& x : st) { nb += x.tc.box_tests; nt += x.tc.tri_tests; }
+    if (box_tests) *box_tests = nb;
+    if (tri_tests) *tri_tests = nt;
+    return sec;
 }
 
 // Sobol known-answer probe: start_pixel_sample(p, i); get_1d; get_2d; get_1d  -> 4 floats + the 3 sample indices

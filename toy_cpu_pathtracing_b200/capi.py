@@ -64,7 +64,7 @@ class Stats(C.Structure):
                 ("tri_tests", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
                 ("trace_closest_ms", C.c_double), ("trace_shadow_ms", C.c_double), ("shade_ms", C.c_double),
                 ("generate_ms", C.c_double), ("film_ms", C.c_double), ("passes", C.c_uint32), ("max_bvh_depth", C.c_uint32),
-                ("sobol_prefix_ms", C.c_double), ("sobol_prefix_bytes", C.c_uint64), ("reduce_ms", C.c_double)]
+                ("sobol_prefix_ms", C.c_double), ("sobol_prefix_bytes", C.c_uint64), ("reduce_ms", C.c_double), ("trace_launches", C.c_uint32), ("shade_launches", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -337,7 +337,7 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
         else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
         k_aov<<<g128, 128, 0, stream>>>(sc, R, st);
-        ctx->stats.kernel_launches += 2;
+        ctx->stats.kernel_launches += 2; ctx->stats.trace_launches++; ctx->stats.shade_launches++;
     } else {
     // option "fused_launches": bit 0 = k_trace_fused (shadow rays of the previous bounce + this bounce's extension rays in one
     // launch), bit 1 = k_shade_all (all shading buckets in one launch); 0 = one launch per queue and per bucket
@@ -359,13 +359,13 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
                 if (count) k_trace_closest<true><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
                 else k_trace_closest<false><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
             }
-            ctx->stats.kernel_launches++;
+            ctx->stats.kernel_launches++; ctx->stats.trace_launches++;
         }
         {
             StageTimer t(ctx, STAGE_SHADE, stream);
             if (fuse_shade) {
                 k_shade_all<<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                ctx->stats.kernel_launches++;
+                ctx->stats.kernel_launches++; ctx->stats.shade_launches++;
             } else {
                 if (stage == 0) {  // bounce 0 has its own instantiations (no previous-bounce half; the terminal bucket is empty)
                     k_shade<0, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
@@ -388,7 +388,7 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
                     k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                     k_shade<8><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                 }
-                ctx->stats.kernel_launches += 9;
+                ctx->stats.kernel_launches += 9; ctx->stats.shade_launches += 9;
             }
         }
         if (ctx->opt.debug_path_log && n_slots == 1) debug_dump(ctx, "after shade", stage, cur ^ 1, stream);
@@ -397,7 +397,7 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
             StageTimer t(ctx, STAGE_SHADOW, stream);
             if (count) k_trace_shadow<true><<<g128, 128, 0, stream>>>(sc, R, st);
             else k_trace_shadow<false><<<g128, 128, 0, stream>>>(sc, R, st);
-            ctx->stats.kernel_launches++;
+            ctx->stats.kernel_launches++; ctx->stats.trace_launches++;
         }
     }
     }

@@ -505,8 +505,10 @@ class SceneDescription:
 class Scene:
     """scene::Scene (scene/src/scene.rs:36-76) over libtcpt."""
 
-    def __init__(self, device: int = 0, context: Optional[capi.Context] = None, require_gpu: bool = True):
-        self.ctx = context or capi.Context(device, require_gpu=require_gpu)
+    def __init__(self, device: int = 0, context: Optional[capi.Context] = None, require_gpu: bool = True, describe_only: bool = False):
+        # describe_only: record the scene (self.desc) without creating a libtcpt context -- bench.py's reference arm replays the
+        # description into the CPU oracle and must not load the product library
+        self.ctx = None if describe_only else (context or capi.Context(device, require_gpu=require_gpu))
         self.desc = SceneDescription()
         self.built = False
 
