@@ -1,5 +1,5 @@
 # Profiling recipe of profiles/ (run under gpurun; one capture kind per call: the merged gpurun_out/ is limited to 64 MiB).
-# usage: prof.sh <tag> launches|trace|shade
+# usage: prof.sh <tag> launches|trace|shade|traffic
 #   launches : ncu launch list (duration, active lanes, DRAM bytes per launch) of the default bench command shortened to 2 steps,
 #              after the same command has run once WITHOUT ncu (its JSON line is the twin the kernel shares are checked against)
 #   trace    : ncu --set full of two k_trace_fused launches (bounce 0 and 1) of a 1-spp pass
@@ -18,6 +18,12 @@ case "$kind" in
   shade)
     $B1 > /dev/null 2>&1 || exit 1
     ncu --set full --clock-control none --import-source on -k regex:k_shade -c 18 -o gpurun_out/prof_shade_$tag -f $B1 > gpurun_out/ncu_s_$tag.log 2>&1 ;;
+  traffic)   # per-launch DRAM bytes, time, FP32 op counts and lanes of ONE default step -> tools/ncu_digest.py -> profiles/ncu_traffic.json
+    BT="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras"
+    $BT > gpurun_out/plain_$tag.json 2> gpurun_out/plain_$tag.err || exit 1
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,smsp__thread_inst_executed.sum,smsp__inst_executed.sum --clock-control none -k regex:k_ -c 260 --csv --log-file gpurun_out/traffic_$tag.csv $BT > gpurun_out/ncu_tr_$tag.log 2>&1
+    python tools/ncu_digest.py gpurun_out/traffic_$tag.csv gpurun_out/plain_$tag.json $tag > gpurun_out/digest_$tag.txt 2>&1
+    cp profiles/ncu_traffic.json gpurun_out/ncu_traffic_$tag.json; cp profiles/${tag}_step_launches.json gpurun_out/ ;;
   *) echo "usage: prof.sh <tag> launches|trace|shade"; exit 2 ;;
 esac
 ls -la gpurun_out/*$tag*
