@@ -143,6 +143,26 @@ int tcpt_scene_add_env_light(tcpt_ctx* ctx, float intensity, const float* rgb /*
 enum { TCPT_LIGHT_POINT = 3, TCPT_LIGHT_SPOT = 4, TCPT_LIGHT_DIRECTIONAL = 5 };   /* = tcpt_flat_primitive.kind */
 int tcpt_scene_add_delta_light(tcpt_ctx* ctx, int kind, float intensity, const tcpt_spectrum_param* spectrum, float angle_inner, float angle_outer,
                                const float local_to_world[16]);
+/* ---- asset ingestion.  Scene::load_obj (scene.rs:54-57) = TriangleMesh::load_obj (geometry/impls/triangle_mesh.rs:141-243): tobj 4.0.3
+ * load_obj with { single_index, triangulate, ignore_points, ignore_lines } and the reference's concatenation of the returned models
+ * (no vertex offset between models; see csrc/host_obj.h for the rules and the two quirks).  tcpt_obj_* hand the arrays to the caller
+ * (counts = {position vertices, normal vertices, texcoord vertices, triangles, models}; copy: any pointer may be NULL; tangent_tri[j] =
+ * the triangle whose load-time tangent triangle j receives, identity for one-model files).  tcpt_scene_load_obj adds the mesh to the
+ * scene and returns its geometry index; TCPT_ERR_INVALID when the file does not parse, lacks vn normals (the reference panics:
+ * triangle_mesh.rs:57-61) or carries texcoords for only some vertices. */
+typedef struct tcpt_obj tcpt_obj;
+int tcpt_obj_load(const char* path, tcpt_obj** out, char* err /*nullable*/, size_t err_len);
+int tcpt_obj_counts(const tcpt_obj* obj, uint32_t counts[5]);
+int tcpt_obj_copy(const tcpt_obj* obj, float* positions, float* normals, float* texcoords, uint32_t* indices, uint32_t* tangent_tri);
+void tcpt_obj_free(tcpt_obj* obj);
+int tcpt_scene_load_obj(tcpt_ctx* ctx, const char* path);
+/* triangle j of `geometry` takes the load-time tangent of triangle tri[j] (multi-model OBJ files, see above) */
+int tcpt_scene_set_tangent_source(tcpt_ctx* ctx, int geometry, const uint32_t* tri, int n_triangles);
+/* The `image` crate's (0.25.6) buffer conversions behind the texture loaders (texture/loader.rs:43-87: anything that is not Rgb8 / Rgb32F resp.
+ * Luma8 / LumaA8 goes through DynamicImage::to_rgb8 / to_luma8; environment_light.rs:36-37: to_rgb32f), for an already DECODED image
+ * (rules in csrc/host_image.h).  src = height*width*channels samples, channels 1 L | 2 LA | 3 RGB | 4 RGBA; sample_type 0 u8 | 1 u16 | 2 f32;
+ * dst_kind 0 = rgb8 (u8 x 3 per pixel), 1 = luma8 (u8), 2 = rgb32f (f32 x 3). */
+int tcpt_image_convert(const void* src, uint32_t width, uint32_t height, uint32_t channels, int sample_type, int dst_kind, void* dst);
 /* Scene::build(&camera): bakes world_to_render = translate(-cam_pos), builds BLAS/TLAS with the reference's exact SAH topology,
  * flattens to the device layout and uploads (scene.rs:64-76, bvh.rs:92-295). */
 int tcpt_scene_build(tcpt_ctx* ctx, const float cam_pos[3]);

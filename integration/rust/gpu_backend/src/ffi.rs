@@ -10,6 +10,10 @@ pub struct TcptCtx {
 pub struct TcptGroup {
     _opaque: [u8; 0],
 }
+#[repr(C)]
+pub struct TcptObj {
+    _opaque: [u8; 0],
+}
 
 pub const TCPT_OK: c_int = 0;
 pub const TCPT_ERR_INVALID: c_int = -1;
@@ -150,6 +154,15 @@ unsafe extern "C" {
     pub fn tcpt_scene_add_delta_light(ctx: *mut TcptCtx, kind: c_int, intensity: f32, spectrum: *const TcptSpectrumParam, angle_inner: f32,
                                       angle_outer: f32, local_to_world: *const f32) -> c_int;
     pub fn tcpt_scene_build(ctx: *mut TcptCtx, cam_pos: *const f32) -> c_int;
+
+    // asset ingestion: what Scene::load_obj / the texture loaders do with tobj and the image crate in the CPU build (include/tcpt.h)
+    pub fn tcpt_obj_load(path: *const c_char, out: *mut *mut TcptObj, err: *mut c_char, err_len: usize) -> c_int;
+    pub fn tcpt_obj_counts(obj: *const TcptObj, counts: *mut u32) -> c_int;
+    pub fn tcpt_obj_copy(obj: *const TcptObj, positions: *mut f32, normals: *mut f32, texcoords: *mut f32, indices: *mut u32, tangent_tri: *mut u32) -> c_int;
+    pub fn tcpt_obj_free(obj: *mut TcptObj);
+    pub fn tcpt_scene_load_obj(ctx: *mut TcptCtx, path: *const c_char) -> c_int;
+    pub fn tcpt_scene_set_tangent_source(ctx: *mut TcptCtx, geometry: c_int, tri: *const u32, n_triangles: c_int) -> c_int;
+    pub fn tcpt_image_convert(src: *const c_void, width: u32, height: u32, channels: u32, sample_type: c_int, dst_kind: c_int, dst: *mut c_void) -> c_int;
 
     pub fn tcpt_render(ctx: *mut TcptCtx, params: *const TcptRenderParams, out_acc: *mut f32, out_srgb: *mut f32) -> c_int;
     pub fn tcpt_render_device(ctx: *mut TcptCtx, params: *const TcptRenderParams, dev_acc: *mut c_void, stream: *mut c_void) -> c_int;

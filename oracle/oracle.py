@@ -45,7 +45,7 @@ def lib() -> C.CDLL:
         _lib.orc_scene_new.restype = C.c_void_p
         _lib.orc_build.restype = C.c_double
         _lib.orc_trace_mt.restype = C.c_double
-        for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_add_single_triangle", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
+        for name in ("orc_scene_free", "orc_set_tables", "orc_add_mesh", "orc_set_tangent_source", "orc_add_single_triangle", "orc_add_texture", "orc_add_material", "orc_rgb_to_coeffs", "orc_add_primitive",
                      "orc_add_env_light", "orc_add_delta_light", "orc_set_modes", "orc_set_optimised", "orc_build", "orc_render", "orc_path_samples", "orc_record_rays", "orc_trace", "orc_sobol_probe",
                      "orc_sampler_stream", "orc_get_bvh", "orc_get_mesh_tangents"):
             getattr(_lib, name).argtypes = None
@@ -86,6 +86,9 @@ class OracleScene:
     # --- replay protocol
     def add_mesh(self, pos, nrm, uv, idx):
         return self.l.orc_add_mesh(_vp(self.h), _p(pos), _p(nrm), _p(uv) if uv is not None else None, len(pos), _p(idx, C.c_uint32), len(idx))
+
+    def set_tangent_source(self, geometry, tri):
+        return self.l.orc_set_tangent_source(_vp(self.h), geometry, _p(tri, C.c_uint32), len(tri))
 
     def add_single_triangle(self, pos, nrm, uv):
         return self.l.orc_add_single_triangle(_vp(self.h), _p(pos), _p(nrm), _p(uv))

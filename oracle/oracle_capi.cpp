@@ -93,6 +93,18 @@ int orc_add_mesh(void* h, const float* pos, const float* nrm, const float* uv, i
     return (int)s->scene.meshes.size() - 1;
 }
 
+// multi-model OBJ files: the reference's tangent loop (triangle_mesh.rs:181-226) runs over every triangle gathered so far after each model
+// and pushes again, so tangents[j] of a later triangle j is the tangent of an earlier one: tri[j] names it (oracle/obj_oracle.py)
+int orc_set_tangent_source(void* h, int geometry, const uint32_t* tri, int n) {
+    OrcScene* s = (OrcScene*)h;
+    Mesh& m = s->scene.meshes[geometry];
+    if (m.tangents.empty()) return 0;
+    std::vector<Vec3> moved(n);
+    for (int t = 0; t < n; ++t) moved[t] = m.tangents[tri[t]];
+    m.tangents.swap(moved);
+    return 0;
+}
+
 // geometry of CreatePrimitiveDesc::SingleTrianglePrimitive (single_triangle.rs:24-41)
 int orc_add_single_triangle(void* h, const float pos[9], const float nrm[9], const float uv[6]) {
     OrcScene* s = (OrcScene*)h;

@@ -22,6 +22,7 @@ class MeshData:
     uvs: np.ndarray | None  # (V,2) f32 or None
     indices: np.ndarray    # (T,3) u32
     single: bool = False   # geometry of a SingleTrianglePrimitive (primitive/impls/single_triangle.rs): three inline vertices
+    tangent_tri: np.ndarray | None = None  # (T,) u32: triangle whose load-time tangent each triangle receives (multi-model OBJ files, csrc/host_obj.h); None = its own
 
     def __post_init__(self):
         self.positions = np.ascontiguousarray(self.positions, dtype=f32)
@@ -29,6 +30,8 @@ class MeshData:
         if self.uvs is not None:
             self.uvs = np.ascontiguousarray(self.uvs, dtype=f32)
         self.indices = np.ascontiguousarray(self.indices, dtype=np.uint32)
+        if self.tangent_tri is not None:
+            self.tangent_tri = np.ascontiguousarray(self.tangent_tri, dtype=np.uint32)
 
     @property
     def n_tris(self) -> int:

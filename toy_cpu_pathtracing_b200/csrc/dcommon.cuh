@@ -96,6 +96,9 @@ struct DEnv {
     const float* data; const float* marginal; const float* conditional;
     const uint32_t* marginal_guide; const uint32_t* conditional_guide; uint32_t guide_h, guide_w;
     float intensity, total_weight; uint32_t w, h; tcpt_flat_spectrum integrated; int32_t primitive;
+    // per texel {wi_render.xyz, pdf_dir}, {sigmoid coefficients, scale}: everything light sampling computes that only depends on WHICH texel
+    // was drawn (see env_nee_texel, kernels.cuh k_env_nee_table); null = compute per sample (option "env_nee_table" 0)
+    const float4* nee_table;
 };
 struct DScene {
     const float4* nodes;            // 8 x float4 per 4-wide record (include/tcpt_flat.h)
@@ -528,6 +531,18 @@ __device__ __forceinline__ float param_float(const DScene& sc, const tcpt_flat_f
     return p.gamma_corrected ? srgb_to_linear(v) : v;  // float_texture.rs:45-52
 }
 
+// two appends at once (extension ray and shadow ray of one vertex): lanes 0 and 1 issue the two atomics back to back, so the warp
+// pays ONE round trip to L2 instead of two dependent ones.  Every lane of the warp must call it.
+__device__ __forceinline__ void warp_push2(uint32_t* ca, bool pa, uint32_t* cb, bool pb, uint32_t* ia, uint32_t* ib) {
+    const uint32_t ma = __ballot_sync(0xffffffffu, pa), mb = __ballot_sync(0xffffffffu, pb);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0u) { if (ma) base = atomicAdd(ca, (uint32_t)__popc(ma)); }
+    else if (lane == 1u) { if (mb) base = atomicAdd(cb, (uint32_t)__popc(mb)); }
+    const uint32_t ba = __shfl_sync(0xffffffffu, base, 0), bb = __shfl_sync(0xffffffffu, base, 1);
+    const uint32_t below = (1u << lane) - 1u;
+    *ia = ba + (uint32_t)__popc(ma & below); *ib = bb + (uint32_t)__popc(mb & below);
+}
 // warp-aggregated queue append: every lane of the warp must call it (pred = false for lanes with nothing to push)
 __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool pred) {
     const uint32_t mask = __ballot_sync(0xffffffffu, pred);

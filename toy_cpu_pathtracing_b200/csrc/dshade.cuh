@@ -871,6 +871,33 @@ __device__ __noinline__ S4 env_radiance_spherical(const DScene& sc, const DEnv& 
     const float3 rgb = env_texel_bilinear(e, phi / (2.0f * TCPT_PI), theta / TCPT_PI);
     return spectrum_sample(sc, illuminant_from_rgb(sc, rgb), wl) * e.intensity;
 }
+// EnvironmentLight::sample_infinite_light (environment_light.rs:326-350) from the drawn texel (xx, yy) on: direction through the texel
+// centre, the pdf of that direction (:234-259) and the illuminant spectrum of the bilinear lookup there (:304-316).  A pure function of
+// the texel, so k_env_nee_table evaluates it once per texel with this very code and the shading kernels read the result (bit-identical:
+// same instructions, same inputs); env_nee_texel_call is the per-sample fallback when the table is switched off.
+struct EnvNee { float3 wi_r; float pdf_dir; DSpectrum spec; };
+__device__ __forceinline__ EnvNee env_nee_texel(const DScene& sc, const tcpt_flat_primitive& LP, const DEnv& e, uint32_t xx, uint32_t yy) {
+    EnvNee r;
+    const float eu = ((float)xx + 0.5f) / (float)e.w, ev = ((float)yy + 0.5f) / (float)e.h;
+    const float theta = ev * TCPT_PI, phi = eu * 2.0f * TCPT_PI;
+    const float3 wl_local = f3(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));
+    r.wi_r = xf_vector(LP.l2r, wl_local);
+    float th_l, ph_l;
+    direction_to_spherical(xf_vector(LP.r2l, r.wi_r), &th_l, &ph_l);
+    r.pdf_dir = env_pdf_spherical(e, th_l, ph_l);
+    r.spec = illuminant_from_rgb(sc, env_texel_bilinear(e, ph_l / (2.0f * TCPT_PI), th_l / TCPT_PI));
+    return r;
+}
+__device__ __noinline__ EnvNee env_nee_texel_call(const DScene& sc, const tcpt_flat_primitive& LP, const DEnv& e, uint32_t xx, uint32_t yy) { return env_nee_texel(sc, LP, e, xx, yy); }
+__device__ __forceinline__ EnvNee env_nee_lookup(const DScene& sc, const tcpt_flat_primitive& LP, const DEnv& e, uint32_t xx, uint32_t yy) {
+    if (e.nee_table == nullptr) return env_nee_texel_call(sc, LP, e, xx, yy);
+    const float4* row = e.nee_table + 2 * ((size_t)yy * e.w + xx);
+    const float4 a = __ldg(row), b = __ldg(row + 1);
+    EnvNee r;
+    r.wi_r = f3(a.x, a.y, a.z); r.pdf_dir = a.w;
+    r.spec.kind = 2; r.spec.table = 0; r.spec.c[0] = b.x; r.spec.c[1] = b.y; r.spec.c[2] = b.z; r.spec.scale = b.w;
+    return r;
+}
 // direction -> (theta, phi) is evaluated once per direction and shared by the pdf and radiance lookups (the reference
 // recomputes it inside each from the same direction: identical values)
 __device__ __forceinline__ float env_direction_pdf(const DScene& sc, const tcpt_flat_primitive& P, float3 dir) {
@@ -923,13 +950,15 @@ __device__ inline void scene_env_radiance_pdf(const DScene& sc, const LightTable
 // Rust slice::binary_search_by(partial_cmp) then clamp (environment_light.rs:218-223).  On a non-decreasing CDF the
 // reference's probing sequence ends at base = (#entries <= u) - 1 (or 0), so with k = #{i : cdf[i] <= u} the result is
 //   k == 0 -> 0 ;  cdf[k-1] == u -> k-1 ;  else min(k, n-1)
-// and k is found with the guide table (tcpt_flat_env) plus a scan of the one or two entries it leaves, instead of
+// and k is found with the guide table (tcpt_flat_env) plus a bisection / scan of the few entries it leaves, instead of
 // log2(n) dependent loads (profile: the 19 serial L2 round trips of the two searches were the top stall of bounce-0 shading).
 __device__ __noinline__ uint32_t sample_from_cdf(const float* cdf, uint32_t n, const uint32_t* guide, uint32_t G, float u) {
     const uint32_t j = min(f2u_sat(u * (float)G), G - 1u);   // u * 2^m is exact
     uint32_t k = __ldg(guide + j);
     const uint32_t hi = __ldg(guide + j + 1);
-    while (k < hi && __ldg(cdf + k) <= u) ++k;
+    uint32_t top = hi;
+    while (top - k > 2u) { const uint32_t mid = (k + top) >> 1; if (__ldg(cdf + mid) <= u) k = mid + 1u; else top = mid; }   // entries <= u are a prefix of [k, hi)
+    while (k < top && __ldg(cdf + k) <= u) ++k;
     if (k == 0u) return 0u;
     const float c = __ldg(cdf + k - 1u);
     if (c == u) return k - 1u;

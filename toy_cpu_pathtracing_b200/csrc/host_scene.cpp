@@ -69,6 +69,19 @@ int HostScene::add_mesh(const float* pos, const float* nrm, const float* uv, int
     return (int)meshes.size() - 1;
 }
 
+int HostScene::set_tangent_source(int mesh, const uint32_t* tri, int ntris) {
+    if (mesh < 0 || mesh >= (int)meshes.size() || !tri) { error = "set_tangent_source: bad geometry"; return TCPT_ERR_INVALID; }
+    HostMesh& m = meshes[mesh];
+    if ((size_t)ntris * 3 != m.indices.size()) { error = "set_tangent_source: triangle count mismatch"; return TCPT_ERR_INVALID; }
+    if (m.tangents.empty()) return TCPT_OK;   // no uvs: the reference holds no tangents either
+    for (int t = 0; t < ntris; ++t) if (tri[t] >= (uint32_t)ntris) { error = "set_tangent_source: triangle out of range"; return TCPT_ERR_INVALID; }
+    std::vector<V3> moved(ntris);
+    for (int t = 0; t < ntris; ++t) moved[t] = m.tangents[tri[t]];
+    m.tangents.swap(moved);
+    m.built = false;
+    return TCPT_OK;
+}
+
 int HostScene::add_single_triangle(const float pos[9], const float nrm[9], const float uv[6]) {
     if (!pos || !nrm || !uv) { error = "add_single_triangle: null argument"; return TCPT_ERR_INVALID; }
     const uint32_t idx[3] = {0, 1, 2};
@@ -247,7 +260,10 @@ int HostScene::add_env_light(float intensity, const float* rgb, uint32_t w, uint
             out[j] = k;
         }
     };
-    e.guide_h = pow2_at_least(h); e.guide_w = pow2_at_least(w);
+    // four guide cells per CDF entry while the conditional guides stay below 64 MB: a warp waits for its longest scan, and the scans are
+    // long exactly where the map is dark (many entries per cell); the search result does not depend on G
+    const uint32_t fine = (size_t)h * (4 * (size_t)pow2_at_least(w) + 1) * 4 <= ((size_t)64 << 20) ? 4u : 1u;
+    e.guide_h = fine * pow2_at_least(h); e.guide_w = fine * pow2_at_least(w);
     e.marginal_guide.resize(e.guide_h + 1);
     build_guide(e.marginal.data(), h, e.guide_h, e.marginal_guide.data());
     e.conditional_guide.resize((size_t)h * (e.guide_w + 1));

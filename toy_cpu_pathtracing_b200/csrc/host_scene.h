@@ -83,6 +83,7 @@ class HostScene {
 
     void clear();
     int add_mesh(const float* pos, const float* nrm, const float* uv, int nverts, const uint32_t* idx, int ntris);
+    int set_tangent_source(int mesh, const uint32_t* tri, int ntris);  // multi-model OBJ files: see host_obj.h
     int add_single_triangle(const float pos[9], const float nrm[9], const float uv[6]);
     int add_texture(const uint8_t* data, uint32_t w, uint32_t h, uint32_t channels);
     int add_material(const tcpt_material_desc& d);

@@ -66,6 +66,19 @@ __global__ void __launch_bounds__(256) k_sobol_pass(uint32_t* __restrict__ table
     }
 }
 
+// builds DEnv::nee_table (once per scene upload): one thread per texel runs env_nee_texel, the code the shading kernels would run per sample
+__global__ void __launch_bounds__(256) k_env_nee_table(const __grid_constant__ DScene sc, uint32_t env_index, float4* __restrict__ table) {
+    const DEnv& e = sc.envs[env_index];
+    const tcpt_flat_primitive& LP = sc.primitives[e.primitive];
+    const uint32_t n = e.w * e.h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t yy = i / e.w, xx = i - yy * e.w;
+        const EnvNee r = env_nee_texel(sc, LP, e, xx, yy);
+        table[2 * (size_t)i] = make_float4(r.wi_r.x, r.wi_r.y, r.wi_r.z, r.pdf_dir);
+        table[2 * (size_t)i + 1] = make_float4(r.spec.c[0], r.spec.c[1], r.spec.c[2], r.spec.scale);
+    }
+}
+
 // ---------------------------------------------------------------- K0 generate
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DCamera cam,
                                                    const __grid_constant__ DState st, const __grid_constant__ PathList L, uint32_t n_slots) {
@@ -417,14 +430,10 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
                 const DEnv& e = sc.envs[LP.env];
                 const uint32_t yy = sample_from_cdf(e.marginal, e.h, e.marginal_guide, e.guide_h, luv.x);
                 const uint32_t xx = sample_from_cdf(e.conditional + (size_t)yy * e.w, e.w, e.conditional_guide + (size_t)yy * (e.guide_w + 1u), e.guide_w, luv.y);
-                const float eu = ((float)xx + 0.5f) / (float)e.w, ev = ((float)yy + 0.5f) / (float)e.h;
-                const float theta = ev * TCPT_PI, phi = eu * 2.0f * TCPT_PI;
-                const float3 wl_local = f3(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));
-                const float3 wi_r = xf_vector(LP.l2r, wl_local);
-                float th_l, ph_l;
-                direction_to_spherical(xf_vector(LP.r2l, wi_r), &th_l, &ph_l);
-                const float pdf_dir = env_pdf_spherical(e, th_l, ph_l);
-                const S4 radiance = env_radiance_spherical(sc, e, th_l, ph_l, wl);
+                const EnvNee en = env_nee_lookup(sc, LP, e, xx, yy);
+                const float3 wi_r = en.wi_r;
+                const float pdf_dir = en.pdf_dir;
+                const S4 radiance = spectrum_sample(sc, en.spec, wl) * e.intensity;
                 const float3 wi = m3_vector(r2t, wi_r);
                 S4 f; float bpdf;
                 material_eval_pdf<MT>(mc, mat, nmf, wl, wo, wi, ng_t, hit.uv, with_mis, &f, &bpdf);
@@ -532,22 +541,33 @@ __device__ __forceinline__ void shade_position(const DScene& sc, const DRender& 
         shade_vertex<B, FIRST>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
     }
     if (B < 6) {  // emissive hits and misses end the path: nothing to push
-        const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
+        uint32_t pe, ps;
+        warp_push2(&st.counters[cur ^ 1], out.push_ext, &st.counters[sh], out.push_sh, &pe, &ps);
         if (out.push_ext) { st.ext_o[cur ^ 1][pe] = out.eo; st.ext_d[cur ^ 1][pe] = out.ed; }
-        const uint32_t ps = warp_push(&st.counters[sh], out.push_sh);
         if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
     }
 }
 
 // One instantiation per shading bucket; each walks only its own range of the bucketed order.
+#ifndef TCPT_SHADE_THREADS
+#define TCPT_SHADE_THREADS 512
+#endif
+#ifndef TCPT_SHADE_SYNC
+#define TCPT_SHADE_SYNC 1
+#endif
 template <int B, bool FIRST = false>
-__global__ void __launch_bounds__(128, (B >= 6 ? 8 : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS)) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
+__global__ void __launch_bounds__(TCPT_SHADE_THREADS, (B >= 6 ? 8 : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS) * 128 / TCPT_SHADE_THREADS) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
                                                                                      const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, int sh, uint32_t stage) {
     if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n = st.counters[4 + TCPT_BUCKET_STRIDE * cur + B];
-    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together (warp_push is warp-collective)
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n);
+    // whole warps iterate together (warp_push is warp-collective); with TCPT_SHADE_SYNC whole blocks do, and start every vertex together
+    const uint32_t unit = (TCPT_SHADE_SYNC && B < 6) ? (uint32_t)TCPT_SHADE_THREADS : 32u;
+    const uint32_t n_round = (n + unit - 1u) / unit * unit;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        if (TCPT_SHADE_SYNC && B < 6) __syncthreads();
+        shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n);
+    }
 }
 
 // shade_vertex<B> behind a call, so that the eight instantiations keep their own register allocation inside k_shade_all
@@ -589,9 +609,9 @@ __global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade_all(const 
             }
         }
         if (b < 6) {  // emissive hits and misses end the path: nothing to push (b is uniform over the block)
-            const uint32_t pe = warp_push(&st.counters[cur ^ 1], out.push_ext);
+            uint32_t pe, ps;
+            warp_push2(&st.counters[cur ^ 1], out.push_ext, &st.counters[sh], out.push_sh, &pe, &ps);
             if (out.push_ext) { st.ext_o[cur ^ 1][pe] = out.eo; st.ext_d[cur ^ 1][pe] = out.ed; }
-            const uint32_t ps = warp_push(&st.counters[sh], out.push_sh);
             if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
         }
     }

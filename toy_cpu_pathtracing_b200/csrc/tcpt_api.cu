@@ -2,8 +2,11 @@
 // Product code.  There is no CPU fallback: without a usable sm_100 device every computing entry point fails with TCPT_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include "host_image.h"
+#include "host_obj.h"
 #include <nccl.h>   // types only: the library is opened at run time by tcpt_comm_init (see NcclApi)
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -28,7 +31,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool valid = false;
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -333,6 +336,7 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         ctx->stats.kernel_launches++;
     }
     const int g128 = grid_for(ctx, n_slots, 128);
+    const int gsh = grid_for(ctx, n_slots, TCPT_SHADE_THREADS) < 1 ? 1 : (int)std::min<uint64_t>((uint64_t)grid_for(ctx, n_slots, TCPT_SHADE_THREADS), std::max<uint64_t>(1, (uint64_t)ctx->sm_count * ctx->opt.blocks_per_sm * 128 / TCPT_SHADE_THREADS));  // the shading kernels' own block size
     if (R.integrator >= TCPT_INTEGRATOR_ALBEDO) {  // AOV renderers: one camera ray per sample, no bounces
         if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
         else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
@@ -368,25 +372,25 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
                 ctx->stats.kernel_launches++; ctx->stats.shade_launches++;
             } else {
                 if (stage == 0) {  // bounce 0 has its own instantiations (no previous-bounce half; the terminal bucket is empty)
-                    k_shade<0, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<1, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<2, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<3, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<4, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<5, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<6, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<7, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<8, true><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<0, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<1, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<2, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<3, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<4, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<5, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<6, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<7, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<8, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                 } else {
-                    k_shade<0><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<1><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<2><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<3><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<4><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<5><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<6><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<7><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<8><<<g128, 128, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<0><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<1><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<2><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<3><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<4><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<5><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<6><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<7><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    k_shade<8><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
                 }
                 ctx->stats.kernel_launches += 9; ctx->stats.shade_launches += 9;
             }
@@ -562,6 +566,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
+    else if (n == "env_nee_table") ctx->opt.env_nee_table = value;       // takes effect at the next scene upload
     else if (n == "sobol_prefix_mb") ctx->opt.sobol_prefix_mb = value;
     else if (n == "sobol_pass") ctx->opt.sobol_pass = value;
     else if (n == "sobol_pass_dims") ctx->opt.sobol_pass_dims = value;
@@ -630,6 +635,63 @@ int tcpt_scene_add_mesh(tcpt_ctx* ctx, const float* positions, const float* norm
     int r = ctx->host.add_mesh(positions, normals, uvs, n_vertices, indices, n_triangles);
     if (r < 0) ctx->error = ctx->host.error;
     return r;
+}
+// ---- asset ingestion (csrc/host_obj.h)
+struct tcpt_obj { tcpt::ObjData d; };
+int tcpt_obj_load(const char* path, tcpt_obj** out, char* err, size_t err_len) {
+    if (!path || !out) return TCPT_ERR_INVALID;
+    *out = nullptr;
+    tcpt_obj* o = new tcpt_obj();
+    std::string e;
+    if (!tcpt::load_obj_file(path, o->d, e)) {
+        if (err && err_len) { std::strncpy(err, e.c_str(), err_len - 1); err[err_len - 1] = 0; }
+        delete o;
+        return TCPT_ERR_INVALID;
+    }
+    *out = o;
+    return TCPT_OK;
+}
+int tcpt_obj_counts(const tcpt_obj* o, uint32_t counts[5]) {
+    if (!o || !counts) return TCPT_ERR_INVALID;
+    counts[0] = (uint32_t)(o->d.positions.size() / 3); counts[1] = (uint32_t)(o->d.normals.size() / 3); counts[2] = (uint32_t)(o->d.texcoords.size() / 2);
+    counts[3] = (uint32_t)(o->d.indices.size() / 3); counts[4] = o->d.n_models;
+    return TCPT_OK;
+}
+int tcpt_obj_copy(const tcpt_obj* o, float* positions, float* normals, float* texcoords, uint32_t* indices, uint32_t* tangent_tri) {
+    if (!o) return TCPT_ERR_INVALID;
+    const tcpt::ObjData& d = o->d;
+    if (positions) std::memcpy(positions, d.positions.data(), d.positions.size() * sizeof(float));
+    if (normals) std::memcpy(normals, d.normals.data(), d.normals.size() * sizeof(float));
+    if (texcoords) std::memcpy(texcoords, d.texcoords.data(), d.texcoords.size() * sizeof(float));
+    if (indices) std::memcpy(indices, d.indices.data(), d.indices.size() * sizeof(uint32_t));
+    if (tangent_tri) for (size_t t = 0; t < d.indices.size() / 3; ++t) tangent_tri[t] = d.tangent_tri.empty() ? (uint32_t)t : d.tangent_tri[t];
+    return TCPT_OK;
+}
+void tcpt_obj_free(tcpt_obj* o) { delete o; }
+int tcpt_scene_load_obj(tcpt_ctx* ctx, const char* path) {
+    if (!ctx || !path) return TCPT_ERR_INVALID;
+    tcpt::ObjData d;
+    std::string e;
+    if (!tcpt::load_obj_file(path, d, e)) return fail(ctx, TCPT_ERR_INVALID, "load_obj: " + e);
+    const size_t nv = d.positions.size() / 3;
+    if (d.normals.size() != d.positions.size()) return fail(ctx, TCPT_ERR_INVALID, "load_obj: every face vertex must carry a vn normal (the reference panics without them)");
+    if (!d.texcoords.empty() && d.texcoords.size() / 2 != nv) return fail(ctx, TCPT_ERR_INVALID, "load_obj: texcoords on only some of the vertices (the reference would misindex them)");
+    const int g = ctx->host.add_mesh(d.positions.data(), d.normals.data(), d.texcoords.empty() ? nullptr : d.texcoords.data(), (int)nv, d.indices.data(), (int)(d.indices.size() / 3));
+    if (g < 0) { ctx->error = ctx->host.error; return g; }
+    if (!d.tangent_tri.empty()) {
+        const int rc = ctx->host.set_tangent_source(g, d.tangent_tri.data(), (int)d.tangent_tri.size());
+        if (rc < 0) { ctx->error = ctx->host.error; return rc; }
+    }
+    return g;
+}
+int tcpt_image_convert(const void* src, uint32_t width, uint32_t height, uint32_t channels, int sample_type, int dst_kind, void* dst) {
+    return tcpt::image_convert(src, width, height, channels, sample_type, dst_kind, dst) ? TCPT_OK : TCPT_ERR_INVALID;
+}
+int tcpt_scene_set_tangent_source(tcpt_ctx* ctx, int geometry, const uint32_t* tri, int n_triangles) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    const int rc = ctx->host.set_tangent_source(geometry, tri, n_triangles);
+    if (rc < 0) ctx->error = ctx->host.error;
+    return rc;
 }
 int tcpt_scene_add_texture(tcpt_ctx* ctx, const uint8_t* data, uint32_t width, uint32_t height, uint32_t channels) {
     if (!ctx) return TCPT_ERR_INVALID;
@@ -748,12 +810,30 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     for (uint32_t i = 0; i < s->n_envs; ++i) {
         const tcpt_flat_env& e = s->envs[i];
         de[i] = DEnv{envf + e.data_offset, envf + e.marginal_offset, envf + e.conditional_offset,
-                     envg + e.marginal_guide_offset, envg + e.conditional_guide_offset, e.guide_h, e.guide_w, e.intensity, e.total_weight, e.width, e.height, e.integrated, e.primitive};
+                     envg + e.marginal_guide_offset, envg + e.conditional_guide_offset, e.guide_h, e.guide_w, e.intensity, e.total_weight, e.width, e.height, e.integrated, e.primitive, nullptr};
     }
     UP(upload(ctx, db, de.data(), de.size(), &v.envs)); v.n_envs = s->n_envs;
 #undef UP
     v.cmf = ctx->d_cmf; v.z_nodes = ctx->d_rgb2spec; v.rgb2spec = ctx->d_rgb2spec + 64; v.presets = ctx->d_presets;
     std::memcpy(v.xyz_to_rgb, ctx->xyz_to_rgb, sizeof v.xyz_to_rgb);
+    // per-texel light-sampling table of every environment map (32 B per texel), filled on the device by the code it replaces
+    if (ctx->opt.env_nee_table) {
+        bool any = false;
+        for (uint32_t i = 0; i < s->n_envs; ++i) {
+            const size_t texels = (size_t)de[i].w * de[i].h;
+            if (texels == 0 || de[i].primitive < 0 || texels * 32 > ((size_t)1 << 31)) continue;
+            void* t = nullptr;
+            CU(cudaMalloc(&t, texels * 2 * sizeof(float4)));
+            db.allocs.push_back(t);
+            k_env_nee_table<<<grid_for(ctx, texels, 256), 256, 0, ctx->stream>>>(v, i, (float4*)t);
+            CU(cudaGetLastError());
+            de[i].nee_table = (const float4*)t; any = true;
+        }
+        if (any) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaMemcpy((void*)v.envs, de.data(), de.size() * sizeof(DEnv), cudaMemcpyHostToDevice));
+        }
+    }
     db.max_bvh_depth = s->max_bvh_depth;
     ctx->stats.max_bvh_depth = s->max_bvh_depth;
     db.valid = true;

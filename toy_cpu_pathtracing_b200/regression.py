@@ -68,6 +68,29 @@ def calculate_rmse(img1_u8: np.ndarray, img2_u8: np.ndarray) -> float:   # regre
     return float(np.sqrt(np.mean(d * d)))
 
 
+def open_rgb8(path):
+    """image::open(path).to_rgb8() of the harness (regression_test.rs:77-83): decode, then the image crate's conversion (libtcpt)."""
+    from .scene import convert_image, decode_image
+    return convert_image(decode_image(path), "rgb8")
+
+
+def run_render_and_compare(image, sampler, output_file, reference_file, max_rmse, **render_kw):
+    """run_render_and_compare (regression_test.rs:41-107) with the renderer in-process: render -> RendererImage.save (the truncating PNG
+    writer of renderer.rs:136-149) -> open both files -> calculate_rmse -> threshold.  Returns the RMSE; raises AssertionError like the
+    reference's assert!, and removes the rendered file afterwards (regression_test.rs:103-106)."""
+    image.render(sampler, **render_kw)
+    image.save(output_file)
+    try:
+        rmse = calculate_rmse(open_rgb8(output_file), open_rgb8(reference_file))
+    finally:
+        try:
+            os.remove(output_file)
+        except OSError:
+            pass
+    assert rmse <= max_rmse, f"RMSE {rmse:.6f} exceeds threshold {max_rmse:.6f} for {output_file} vs {reference_file}"
+    return rmse
+
+
 def reference_image(name: str):
     """The decoded RGB8 reference PNG, or None when its payload is not available (LFS pointer stub / no TCPT_REFERENCE_DIR)."""
     root = os.environ.get("TCPT_REFERENCE_DIR")

@@ -95,20 +95,46 @@ class NormalTexture:        # scene::NormalTexture::load(path, flip_y)
         return NormalTexture(_load_image(array_or_path, 3), flip_y)
 
 
-def _load_image(src, channels):
-    if isinstance(src, np.ndarray):
-        a = src
-    else:  # real asset ingestion: PNG via OpenCV when available
-        import cv2
-        a = cv2.imread(str(src), cv2.IMREAD_COLOR if channels == 3 else cv2.IMREAD_GRAYSCALE)
-        if a is None:
-            raise FileNotFoundError(src)
-        if channels == 3:
-            a = a[..., ::-1]
-    a = np.ascontiguousarray(a, dtype=np.uint8)
-    if channels == 1 and a.ndim == 3:
-        a = a[..., 0]
+def decode_image(path) -> np.ndarray:
+    """Decoder only (OpenCV): the file's own channels and sample depth, channel order L | LA | RGB | RGBA, dtype uint8 | uint16 | float32."""
+    import os
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    a = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+    if a is None:
+        raise FileNotFoundError(path)
+    if a.ndim == 3 and a.shape[2] >= 3:
+        a = a[..., [2, 1, 0] + ([3] if a.shape[2] == 4 else [])]        # BGR(A) -> RGB(A)
+    if a.dtype not in (np.uint8, np.uint16, np.float32):
+        a = a.astype(np.float32)
     return np.ascontiguousarray(a)
+
+
+IMG_KINDS = {"rgb8": (0, np.uint8, 3), "luma8": (1, np.uint8, 1), "rgb32f": (2, np.float32, 3)}
+
+
+def convert_image(a: np.ndarray, kind: str) -> np.ndarray:
+    """DynamicImage::to_rgb8 / to_luma8 / to_rgb32f of the `image` crate on a decoded array (libtcpt: csrc/host_image.h)."""
+    a = np.ascontiguousarray(a)
+    hgt, wid = a.shape[:2]
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    code, dtype, out_ch = IMG_KINDS[kind]
+    st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[a.dtype]
+    out = np.zeros((hgt, wid, out_ch) if out_ch == 3 else (hgt, wid), dtype=dtype)
+    rc = capi.load_library().tcpt_image_convert(a.ctypes.data_as(C.c_void_p), wid, hgt, ch, st, code, out.ctypes.data_as(C.c_void_p))
+    if rc != capi.TCPT_OK:
+        raise ValueError("tcpt_image_convert: unsupported image layout")
+    return out
+
+
+def _load_image(src, channels):
+    """texture/loader.rs:43-87: load_rgb_image (channels 3) keeps Rgb8 and converts everything else with to_rgb8; load_grayscale_image
+    (channels 1) keeps Luma8, drops the alpha of LumaA8 and converts everything else with to_luma8.  Arrays are taken as already loaded."""
+    if isinstance(src, np.ndarray):
+        a = np.ascontiguousarray(src, dtype=np.uint8)
+        return a[..., 0] if channels == 1 and a.ndim == 3 else a
+    a = decode_image(src)
+    return convert_image(a, "rgb8" if channels == 3 else "luma8")
 
 
 class SpectrumType:
@@ -361,37 +387,28 @@ class CreatePrimitiveDesc:
 
 
 def load_obj(path) -> MeshData:
-    """Minimal OBJ ingestion in the spirit of tobj's `single_index, triangulate` (geometry/impls/triangle_mesh.rs:141-160):
-    unique (v, vt, vn) triples become vertices in first-use order, polygons are fan-triangulated.  `vn` is required."""
-    vs, vts, vns, verts, index, tris = [], [], [], [], {}, []
-    for line in open(path):
-        t = line.split()
-        if not t:
-            continue
-        if t[0] == "v":
-            vs.append([float(x) for x in t[1:4]])
-        elif t[0] == "vt":
-            vts.append([float(x) for x in t[1:3]])
-        elif t[0] == "vn":
-            vns.append([float(x) for x in t[1:4]])
-        elif t[0] == "f":
-            ids = []
-            for tok in t[1:]:
-                parts = (tok.split("/") + ["", ""])[:3]
-                key = tuple(int(p) if p else 0 for p in parts)
-                key = tuple(k - 1 if k > 0 else (len(src) + k if k < 0 else -1) for k, src in zip(key, (vs, vts, vns)))
-                if key not in index:
-                    index[key] = len(verts)
-                    verts.append(key)
-                ids.append(index[key])
-            for k in range(1, len(ids) - 1):
-                tris.append([ids[0], ids[k], ids[k + 1]])
-    if not vns:
-        raise ValueError("OBJ files must carry vn normals (the reference panics without them, triangle_mesh.rs:57-61)")
-    pos = np.array([vs[a] for a, _, _ in verts], dtype=f32)
-    nrm = np.array([vns[c] for _, _, c in verts], dtype=f32)
-    uvs = np.array([vts[b] for _, b, _ in verts], dtype=f32) if vts and all(b >= 0 for _, b, _ in verts) else None
-    return MeshData(pos, nrm, uvs, np.array(tris, dtype=np.uint32))
+    """TriangleMesh::load_obj (geometry/impls/triangle_mesh.rs:141-243) through libtcpt's loader (csrc/host_obj.h: tobj 4.0.3's
+    `single_index + triangulate` rules and the reference's concatenation of the models, quirks included).  Host-side only: needs no GPU."""
+    lib = capi.load_library()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    if lib.tcpt_obj_load(str(path).encode(), C.byref(h), err, len(err)) != capi.TCPT_OK:
+        raise ValueError(f"load_obj({path}): {err.value.decode()}")
+    try:
+        counts = (C.c_uint32 * 5)()
+        lib.tcpt_obj_counts(h, counts)
+        nv, nn, nt, ntri, nmodels = (int(c) for c in counts)
+        pos, nrm, uvs = np.zeros((nv, 3), f32), np.zeros((nn, 3), f32), np.zeros((nt, 2), f32)
+        idx, ttri = np.zeros((ntri, 3), np.uint32), np.zeros(ntri, np.uint32)
+        lib.tcpt_obj_copy(h, capi.as_ptr(pos, C.c_float), capi.as_ptr(nrm, C.c_float), capi.as_ptr(uvs, C.c_float), capi.as_ptr(idx, C.c_uint32), capi.as_ptr(ttri, C.c_uint32))
+    finally:
+        lib.tcpt_obj_free(h)
+    if nn != nv:
+        raise ValueError("OBJ files must carry vn normals on every face vertex (the reference panics without them, triangle_mesh.rs:57-61)")
+    if nt not in (0, nv):
+        raise ValueError("texcoords on only some of the vertices (the reference would misindex them)")
+    identity = np.array_equal(ttri, np.arange(ntri, dtype=np.uint32))
+    return MeshData(pos, nrm, uvs if nt else None, idx, tangent_tri=None if identity else ttri)
 
 
 # ------------------------------------------------------------------ scene description
@@ -488,7 +505,9 @@ class SceneDescription:
             if mesh.single:
                 backend.add_single_triangle(mesh.positions, mesh.normals, mesh.uvs)
             else:
-                backend.add_mesh(mesh.positions, mesh.normals, mesh.uvs, mesh.indices)
+                g = backend.add_mesh(mesh.positions, mesh.normals, mesh.uvs, mesh.indices)
+                if mesh.tangent_tri is not None:
+                    backend.set_tangent_source(g, mesh.tangent_tri)
         for t in self.textures:
             backend.add_texture(t)
         for m in self.materials:
@@ -529,10 +548,7 @@ class Scene:
         elif isinstance(desc, EnvironmentLightPrimitive):
             tex = desc.texture
             if not isinstance(tex, np.ndarray):
-                import os
-                os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
-                import cv2
-                tex = cv2.imread(str(tex), cv2.IMREAD_UNCHANGED)[..., 2::-1]
+                tex = convert_image(decode_image(tex), "rgb32f")       # image::open(path).to_rgb32f() (environment_light.rs:36-37)
             d.primitives.append(("env", float(desc.intensity), np.ascontiguousarray(tex, dtype=f32), desc.transform.column_major()))
         elif isinstance(desc, SingleTrianglePrimitive):
             tri = MeshData(np.asarray(desc.positions, dtype=f32).reshape(3, 3), np.asarray(desc.normals, dtype=f32).reshape(3, 3),
@@ -563,6 +579,9 @@ class Scene:
         lib, h = self.ctx.lib, self.ctx.handle
         uvp = capi.as_ptr(uv, C.c_float) if uv is not None else None
         return self.ctx.check(lib.tcpt_scene_add_mesh(h, capi.as_ptr(pos, C.c_float), capi.as_ptr(nrm, C.c_float), uvp, len(pos), capi.as_ptr(idx, C.c_uint32), len(idx)))
+
+    def set_tangent_source(self, geometry, tri):
+        return self.ctx.check(self.ctx.lib.tcpt_scene_set_tangent_source(self.ctx.handle, geometry, capi.as_ptr(tri, C.c_uint32), len(tri)))
 
     def add_single_triangle(self, pos, nrm, uv):
         return self.ctx.check(self.ctx.lib.tcpt_scene_add_single_triangle(self.ctx.handle, capi.as_ptr(pos, C.c_float), capi.as_ptr(nrm, C.c_float), capi.as_ptr(uv, C.c_float)))

@@ -51,10 +51,8 @@ def _load_real(name: str, path):
     if str(path).endswith(".obj"):
         return load_obj(path)
     if str(path).endswith(".exr"):
-        import os
-        os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
-        import cv2
-        return np.ascontiguousarray(cv2.imread(str(path), cv2.IMREAD_UNCHANGED)[..., 2::-1], dtype=np.float32)
+        from .scene import convert_image, decode_image
+        return convert_image(decode_image(path), "rgb32f")
     return _load_image(path, 1 if name in _GRAY else 3)
 
 
