@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], help="developer knob: libtcpt option as name=value (tcpt_set_option), repeatable")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--soup-rays", type=int, default=4096, help="soup workloads: the primary-ray grid is N x N (4096 -> 16.8 M rays)")
+    ap.add_argument("--soup-builder", default="device", choices=["device", "host"], help="soup workloads: LBVH built on the device (csrc/lbvh.cuh) or the host binned-SAH builder")
     return ap.parse_args()
 
 
@@ -276,12 +277,12 @@ def main_gpu(args, wl):
     if "soup" in wl:
         return soup_gpu(args, wl, world, rank, local)
     tp, scene, cam = describe_scene(wl, device=local)
-    t0 = time.time(); scene.build(cam); build_s = time.time() - t0
     ctx = scene.ctx
-    init_comm(ctx, rank, world)          # tcpt_comm_init: the film reduce is libtcpt's own ncclReduce from here on
-    for kv in args.opt:
+    for kv in args.opt:                  # before the build: some options are decided when the scene is uploaded
         name, _, val = kv.partition("=")
         ctx.set_option(name, int(val))
+    t0 = time.time(); scene.build(cam); build_s = time.time() - t0
+    init_comm(ctx, rank, world)          # tcpt_comm_init: the film reduce is libtcpt's own ncclReduce from here on
     W, H, S = wl["width"], wl["height"], args.spp_per_step
     SPP, TILE = capi.SHARD_MODES["spp"], capi.SHARD_MODES["tile"]
     renderer = tp.RENDERERS[wl["integrator"]](tp.RendererArgs((W, H), wl["frame_spp"], scene, cam, seed=0))
@@ -596,15 +597,26 @@ def soup_gpu(args, wl, world, rank, local):
     for kv in args.opt:
         name, _, val = kv.partition("=")
         ctx.set_option(name, int(val))
-    t0 = time.time(); scene.build(cam); build_s = time.time() - t0
+    device_builder = args.soup_builder == "device"
+    t0 = time.time()
+    if device_builder:
+        # the BVH is built where the triangles are (csrc/lbvh.cuh); the scene is the soup alone, in world space (camera at (0, 0, 3))
+        mesh = scene.desc.meshes[0]
+        scene.build_soup(mesh.positions[mesh.indices.reshape(-1)].reshape(-1, 3, 3))
+        build_info = scene.soup_build_info()
+    else:
+        scene.build(cam)
+        build_info = {}
+    build_s = time.time() - t0
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
     FMAX = np.finfo(np.float32).max
+    shift = np.asarray(cam.position, dtype=np.float32) if device_builder else np.zeros(3, np.float32)    # Render space -> the space the scene was built in
 
     def pack(o, d):
         n = len(o)
         r = np.zeros((2 * n, 4), dtype=np.float32)
-        r[:n, :3], r[:n, 3], r[n:, :3] = o, FMAX, d
+        r[:n, :3], r[:n, 3], r[n:, :3] = o + shift, FMAX, d
         return torch.from_numpy(r).to(dev)
 
     def trace_dev(rays, n, any_hit, hits):
@@ -653,9 +665,10 @@ def soup_gpu(args, wl, world, rank, local):
     # e2e: the host-buffer entry point (rays in, hit records out)
     host_rays = np.concatenate([o2, d2, np.full((m, 1), FMAX, np.float32)], 1)
     e2e_n = min(m, 4_000_000)
-    scene.trace(host_rays[:e2e_n])
+    e2e_rays = host_rays[:e2e_n].copy(); e2e_rays[:, :3] += shift
+    scene.trace(e2e_rays)
     barrier(); t0 = time.perf_counter()
-    scene.trace(host_rays[:e2e_n])
+    scene.trace(e2e_rays)
     barrier(); e2e_s = time.perf_counter() - t0
     tt = torch.tensor([ms_i, float(m), e2e_s, float(e2e_n)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -699,7 +712,8 @@ def soup_gpu(args, wl, world, rank, local):
             "gpu_launches": args.steps, "clocks": clk.summary(),
             "roofline": {"kernel": "k_trace_closest (soup, incoherent)", "bound": "hbm", "achieved": ri["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": ri["frac"], "traffic": traffic,
                          "traffic_note": note, "definition": "48 + 32*B + 48*T bytes per ray (SURVEY.md 8d), B and T counted by the kernel"},
-            "incoherent_closest": ri, "coherent_closest": rc, "incoherent_anyhit": rs, "bvh_depth": depth, "scene_build_s": build_s, "kernel_source_sha": kernel_source_sha()}
+            "incoherent_closest": ri, "coherent_closest": rc, "incoherent_anyhit": rs, "bvh_depth": depth, "scene_build_s": build_s, "builder": args.soup_builder, "device_build": build_info,
+            "kernel_source_sha": kernel_source_sha()}
     if not args.no_cpu_baseline and world == 1 and wl["soup"] <= 10_000_000:
         try:
             line["cpu_baseline"] = soup_cpu(args, wl, scene.desc, cam, host_rays, np.concatenate([o, d, np.full((n, 1), FMAX, np.float32)], 1))

@@ -116,7 +116,8 @@ const char* tcpt_last_error(const tcpt_ctx* ctx);
  * sample digits shared by all samples of a pixel inside one pass, default; 0: off), "sobol_pass_dims" (dimensions it covers, default 11),
  * "fused_launches" (bit 0: shadow rays of one bounce and extension rays of the next in one launch, bit 1: all shading buckets in one
  * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "light_shortcut" (1: a scene whose
- * only light has strictly positive power skips the per-vertex light-power table, its selection probability being exactly 1), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
+ * only light has strictly positive power skips the per-vertex light-power table, its selection probability being exactly 1), "env_nee_table" (1, default: per-texel table of what environment-light sampling computes from the drawn texel alone -- direction, pdf, illuminant
+ * coefficients; 32 B per texel, built on the device at scene upload by the code it replaces, bit-transparent; 0: compute per sample), "pin_host_buffers" (1: tcpt_render page-locks the caller's output
  * buffers on first use and keeps them registered while the same pointers are passed; 0: releases them — set 0 before freeing) */
 int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value);
 /* std_tables = data/std_tables.bin (Sobol matrices 0-1: sampler/sobol_matrices.rs:7; CIE XYZ, D65 and the metal / glass presets:
@@ -212,6 +213,14 @@ int tcpt_group_set_tables(tcpt_group* g, const void* std_tables, size_t std_len,
 int tcpt_group_build(tcpt_group* g, const float cam_pos[3]);               /* Scene::build on context 0, replica on every other GPU */
 int tcpt_group_render(tcpt_group* g, const tcpt_render_params* job, int shard_mode, float* out_acc, float* out_srgb);
 
+/* ---- synthetic triangle soups (BASELINE.json configs[4], 1 M - 100 M triangles): a TRAVERSAL-ONLY scene whose BVH is built on the device
+ * (Morton order + radix tree, collapsed to the 4-wide records the traversal kernels read: csrc/lbvh.cuh; the reference's O(N^2) builder is
+ * a parity requirement for the config scenes only).  triangles = n_triangles x 9 floats on the host (world space = Render space, one
+ * primitive with the identity transform, primitive index 0, triangle index = position in the array).  Afterwards tcpt_trace /
+ * tcpt_trace_device work; tcpt_render* refuse.  tcpt_soup_build_info: device time of the build, 128-byte records, wide levels. */
+int tcpt_scene_build_soup(tcpt_ctx* ctx, const float* triangles, uint32_t n_triangles);
+int tcpt_soup_build_info(const tcpt_ctx* ctx, double* build_ms, uint64_t* n_records, uint32_t* levels);
+
 /* ---- single stages, exposed for parity tests and the traversal micro-benchmark */
 /* rays: n x {o[3], d[3], tmax}; out: n x {prim, tri, t bits, b0 bits, b1 bits, b2 bits} (prim -1 = miss; any_hit: out[0] = 0|1) */
 int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* out_hit);
@@ -220,6 +229,9 @@ int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* ou
 int tcpt_trace_device(tcpt_ctx* ctx, const void* dev_rays, int n, int any_hit, void* dev_hits, void* stream);
 int tcpt_sampler_stream(tcpt_ctx* ctx, int sampler, uint32_t spp, uint32_t width, uint32_t height, uint32_t seed, uint32_t px,
                         uint32_t py, uint32_t sample_index, const int32_t* kinds /*1 = get_1d, 2 = get_2d*/, int n, float* out);
+/* the CDF search of EnvironmentLight::sample_infinite_light (environment_light.rs:218-223: slice::binary_search_by + clamp) as the device runs it:
+ * cdf = n non-decreasing values, guide_cells = a power of two (the device's guide table is built for it), u = m numbers, out = m indices */
+int tcpt_cdf_search(tcpt_ctx* ctx, const float* cdf, uint32_t n, uint32_t guide_cells, const float* u, int m, uint32_t* out);
 /* RGB contribution of individual (pixel, sample) paths = what Sensor::add_sample adds for that sample */
 int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uint32_t* pixels_xy, const uint32_t* sample_indices,
                       int n, float* out_rgb);

@@ -162,6 +162,8 @@ unsafe extern "C" {
     pub fn tcpt_obj_free(obj: *mut TcptObj);
     pub fn tcpt_scene_load_obj(ctx: *mut TcptCtx, path: *const c_char) -> c_int;
     pub fn tcpt_scene_set_tangent_source(ctx: *mut TcptCtx, geometry: c_int, tri: *const u32, n_triangles: c_int) -> c_int;
+    pub fn tcpt_scene_build_soup(ctx: *mut TcptCtx, triangles: *const f32, n_triangles: u32) -> c_int;
+    pub fn tcpt_soup_build_info(ctx: *const TcptCtx, build_ms: *mut f64, n_records: *mut u64, levels: *mut u32) -> c_int;
     pub fn tcpt_image_convert(src: *const c_void, width: u32, height: u32, channels: u32, sample_type: c_int, dst_kind: c_int, dst: *mut c_void) -> c_int;
 
     pub fn tcpt_render(ctx: *mut TcptCtx, params: *const TcptRenderParams, out_acc: *mut f32, out_srgb: *mut f32) -> c_int;

@@ -206,6 +206,13 @@ class OracleScene:
         return out
 
 
+def cdf_search(cdf: np.ndarray, u: np.ndarray) -> np.ndarray:
+    cdf = np.ascontiguousarray(cdf, dtype=f32); u = np.ascontiguousarray(u, dtype=f32)
+    out = np.zeros(len(u), dtype=np.uint32)
+    lib().orc_cdf_search(_p(cdf), len(cdf), _p(u), len(u), _p(out, C.c_uint32))
+    return out
+
+
 def build_bvh_boxes(boxes: np.ndarray, literal: bool) -> np.ndarray:
     l = lib()
     b = np.ascontiguousarray(boxes, dtype=f32)

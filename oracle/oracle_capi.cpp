@@ -355,6 +355,12 @@ double orc_trace_mt(void* h, const float* rays, int n, int any_hit, int32_t* out
     return sec;
 }
 
+// the CDF search of EnvironmentLight::sample_infinite_light alone (environment_light.rs:218-223)
+int orc_cdf_search(const float* cdf, int n, const float* u, int m, uint32_t* out) {
+    for (int i = 0; i < m; ++i) out[i] = (uint32_t)Scene::sample_from_cdf(cdf, (size_t)n, u[i]);
+    return 0;
+}
+
 // Sobol known-answer probe: start_pixel_sample(p, i); get_1d; get_2d; get_1d  -> 4 floats + the 3 sample indices
 int orc_sobol_probe(void* h, uint32_t spp, uint32_t w, uint32_t hgt, uint32_t seed, uint32_t px, uint32_t py, uint32_t sample_index, float out_vals[4], uint64_t out_index[3], uint32_t* morton) {
     OrcScene* s = (OrcScene*)h;

@@ -80,7 +80,7 @@ def test_rust_binding_source_is_in_sync_with_the_header(built):
     fns = set(re.findall(r"pub fn (tcpt_[a-z0-9_]+)\(", text))
     declared = set(declared_symbols())
     assert fns <= declared, fns - declared
-    product = {s for s in declared if not re.search(r"trace|sampler_stream|path_samples|get_bvh|get_wide_bvh|build_bvh|rgb_to_coeffs|mesh_tangents|upload_flat", s)}
+    product = {s for s in declared if not re.search(r"trace|sampler_stream|path_samples|get_bvh|get_wide_bvh|build_bvh|rgb_to_coeffs|mesh_tangents|upload_flat|cdf_search", s)}
     assert product <= fns, f"ffi.rs misses {product - fns}"        # everything but the test / introspection probes is bound
 
     def rust_fields(name):

@@ -83,6 +83,24 @@ def test_single_light_shortcut_is_bit_transparent(bundle_factory, scene_id):
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
 
 
+@pytest.mark.parametrize("scene_id,integrator", [(19, "mis"), (19, "nee"), (17, "mis")])   # scenes lit by an environment map
+def test_environment_nee_table_is_bit_transparent(bundle_factory, scene_id, integrator):
+    """Light sampling draws a TEXEL of the environment map; the direction through its centre, the pdf of that direction and the
+    illuminant spectrum looked up there (environment_light.rs:326-350, :234-259, :304-316) only depend on the texel, so they are
+    evaluated once per texel when the scene is uploaded (k_env_nee_table, same device code) and read back per sample: not a bit may change."""
+    b = bundle_factory(scene_id, 200, 150)
+    ctx = b.scene.ctx
+    a = b.image(integrator, 16).render("sobol").accumulators.copy()
+    try:
+        ctx.set_option("env_nee_table", 0)
+        b.scene.build(b.camera)                      # the table is built when the scene is uploaded
+        c = b.image(integrator, 16).render("sobol").accumulators.copy()
+    finally:
+        ctx.set_option("env_nee_table", 1)
+        b.scene.build(b.camera)
+    assert a.any() and np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
 @pytest.mark.parametrize("scene_id,spp", [(3, 64), (19, 256), (10, 16)])
 def test_sobol_pass_table_is_bit_transparent(bundle_factory, scene_id, spp):
     """The per-pass table caches the permuted sample digits that all samples of a pixel share inside one pass (and the permutation row

@@ -22,7 +22,33 @@ def family(name):
     return None
 
 
+def soup(csv_path, plain_path, tag, workload):
+    """Launches of `bench.py --workload soup_* --steps 1 --warmup 0`: k_trace_rays #0 = the primaries that produce the hit points,
+    #1 = the timed incoherent closest-hit batch, #2 = coherent, #3 = any hit (then the counting launches)."""
+    rows = [r for r in csv.reader(open(csv_path, newline="")) if len(r) >= 15 and r[0].isdigit() and "k_trace_rays" in r[4]]
+    launches = collections.OrderedDict()
+    for r in rows:
+        launches.setdefault(int(r[0]), {})[r[12]] = float(r[14].replace(",", ""))
+    L = [launches[k] for k in sorted(launches)]
+    plain = json.loads([ln for ln in open(plain_path) if ln.startswith("{")][-1])
+    names = {1: "incoherent_closest", 2: "coherent_closest", 3: "incoherent_anyhit"}
+    out = {"captured": tag, "kernel_source_sha": bench.kernel_source_sha()}
+    for i, name in names.items():
+        rays = plain[name]["rays"]
+        db = L[i].get("dram__bytes_read.sum", 0.0) + L[i].get("dram__bytes_write.sum", 0.0)
+        out[name] = {"dram_bytes_per_ray": db / rays, "ncu_ms": L[i].get("gpu__time_duration.sum", 0.0) / 1e6, "rays": rays,
+                     "algorithmic_bytes_per_ray": plain[name]["bytes_per_ray"]}
+    out["incoherent_dram_bytes_per_ray"] = out["incoherent_closest"]["dram_bytes_per_ray"]
+    dst = ROOT / "profiles" / "ncu_traffic.json"
+    doc = json.loads(dst.read_text())
+    doc.setdefault("soups", {})[workload] = out
+    dst.write_text(json.dumps(doc, indent=1))
+    print(json.dumps(out, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--soup":
+        return soup(*sys.argv[2:6])
     csv_path, plain_path, tag = sys.argv[1], sys.argv[2], sys.argv[3]
     workload = sys.argv[4] if len(sys.argv) > 4 else "scene19_4k"
     rows = [r for r in csv.reader(open(csv_path, newline="")) if len(r) >= 15 and r[0].isdigit()]

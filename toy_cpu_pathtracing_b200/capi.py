@@ -80,7 +80,7 @@ EXPORTED_SYMBOLS = [
     "tcpt_comm_get_unique_id", "tcpt_comm_init", "tcpt_comm_destroy", "tcpt_shard_params", "tcpt_render_sharded", "tcpt_render_sharded_device",
     "tcpt_group_create", "tcpt_group_destroy", "tcpt_group_size", "tcpt_group_context", "tcpt_group_last_error", "tcpt_group_set_tables",
     "tcpt_group_build", "tcpt_group_render",
-    "tcpt_obj_load", "tcpt_obj_counts", "tcpt_obj_copy", "tcpt_obj_free", "tcpt_scene_load_obj", "tcpt_scene_set_tangent_source", "tcpt_image_convert",
+    "tcpt_obj_load", "tcpt_obj_counts", "tcpt_obj_copy", "tcpt_obj_free", "tcpt_scene_load_obj", "tcpt_scene_set_tangent_source", "tcpt_image_convert", "tcpt_cdf_search", "tcpt_scene_build_soup", "tcpt_soup_build_info",
 ]
 
 _lib = None
@@ -125,6 +125,8 @@ def load_library() -> C.CDLL:
         "tcpt_group_render": (I, [P, C.POINTER(RenderParams), I, fp, fp]),
         "tcpt_obj_load": (I, [C.c_char_p, C.POINTER(P), C.c_char_p, C.c_size_t]), "tcpt_obj_counts": (I, [P, up]),
         "tcpt_obj_copy": (I, [P, fp, fp, fp, up, up]), "tcpt_obj_free": (None, [P]),
+        "tcpt_scene_build_soup": (I, [P, fp, U]), "tcpt_soup_build_info": (I, [P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), up]),
+        "tcpt_cdf_search": (I, [P, fp, U, U, fp, I, up]),
         "tcpt_image_convert": (I, [C.c_void_p, U, U, U, I, I, C.c_void_p]),
         "tcpt_scene_load_obj": (I, [P, C.c_char_p]), "tcpt_scene_set_tangent_source": (I, [P, I, up, I]),
     }

@@ -69,6 +69,15 @@ int HostScene::add_mesh(const float* pos, const float* nrm, const float* uv, int
     return (int)meshes.size() - 1;
 }
 
+void build_cdf_guide(const float* cdf, uint32_t n, uint32_t G, uint32_t* out) {
+    uint32_t k = 0;
+    for (uint32_t j = 0; j <= G; ++j) {
+        const float edge = (float)j / (float)G;
+        while (k < n && cdf[k] <= edge) ++k;
+        out[j] = k;
+    }
+}
+
 int HostScene::set_tangent_source(int mesh, const uint32_t* tri, int ntris) {
     if (mesh < 0 || mesh >= (int)meshes.size() || !tri) { error = "set_tangent_source: bad geometry"; return TCPT_ERR_INVALID; }
     HostMesh& m = meshes[mesh];
@@ -179,6 +188,13 @@ int HostScene::add_material(const tcpt_material_desc& d) {
     if ((d.type == TCPT_MAT_METAL && (d.color.kind != TCPT_SPEC_PRESET || d.coat_tint.kind != TCPT_SPEC_PRESET)) || (d.type == TCPT_MAT_GLASS && d.color.kind != TCPT_SPEC_PRESET)) {
         error = "add_material: metal needs eta and k presets (color, coat_tint), glass an eta preset (color)"; return TCPT_ERR_INVALID;
     }
+    // RgbSigmoidPolynomial::from_rgb panics when a (linearised) component exceeds 1 (rgb_sigmoid_polynomial.rs:95-108): refuse the material
+    auto rgb_ok = [&](const tcpt_spectrum_param& p) {
+        if (p.kind != TCPT_SPEC_RGB_ALBEDO_SRGB && p.kind != TCPT_SPEC_RGB_ALBEDO_LINEAR) return true;
+        float cs[3];
+        return rgb_to_coeffs(p.value, p.kind == TCPT_SPEC_RGB_ALBEDO_SRGB, cs, nullptr);
+    };
+    if (!rgb_ok(d.color) || !rgb_ok(d.coat_tint)) { error = "add_material: an RGB albedo component exceeds 1 after linearisation (the reference panics: rgb_sigmoid_polynomial.rs:95-108)"; return TCPT_ERR_INVALID; }
     tcpt_flat_material m{};
     m.type = d.type;
     m.color = resolve_spectrum(d.color);
@@ -252,14 +268,7 @@ int HostScene::add_env_light(float intensity, const float* rgb, uint32_t w, uint
     for (uint32_t y = 0; y < h; ++y) { run += row_w[y]; e.marginal[y] = total > 0.0f ? run / total : (float)(y + 1) / (float)h; }
     // guide tables: guide[j] = #{i : cdf[i] <= j/G} for j = 0..G (cdf is non-decreasing, j/G is exact in f32)
     auto pow2_at_least = [](uint32_t n) { uint32_t g = 1; while (g < n) g <<= 1; return g; };
-    auto build_guide = [](const float* cdf, uint32_t n, uint32_t G, uint32_t* out) {
-        uint32_t k = 0;
-        for (uint32_t j = 0; j <= G; ++j) {
-            const float edge = (float)j / (float)G;
-            while (k < n && cdf[k] <= edge) ++k;
-            out[j] = k;
-        }
-    };
+    auto build_guide = build_cdf_guide;
     // four guide cells per CDF entry while the conditional guides stay below 64 MB: a warp waits for its longest scan, and the scans are
     // long exactly where the map is dark (many entries per cell); the search result does not depend on G
     const uint32_t fine = (size_t)h * (4 * (size_t)pow2_at_least(w) + 1) * 4 <= ((size_t)64 << 20) ? 4u : 1u;
@@ -280,6 +289,10 @@ int HostScene::add_delta_light(int kind, float intensity, const tcpt_spectrum_pa
     if (kind < TCPT_LIGHT_POINT || kind > TCPT_LIGHT_DIRECTIONAL) { error = "add_delta_light: unknown light kind"; return TCPT_ERR_INVALID; }
     if (spectrum.kind == TCPT_SPEC_TEXTURE_SRGB) { error = "add_delta_light: a light spectrum cannot be a texture"; return TCPT_ERR_INVALID; }
     if (spectrum.kind == TCPT_SPEC_PRESET && (spectrum.texture < 0 || (size_t)spectrum.texture * 470 >= tables.presets.size())) { error = "add_delta_light: spectrum preset id out of range"; return TCPT_ERR_INVALID; }
+    if (spectrum.kind == TCPT_SPEC_RGB_ALBEDO_SRGB || spectrum.kind == TCPT_SPEC_RGB_ALBEDO_LINEAR) {
+        float cs[3];
+        if (!rgb_to_coeffs(spectrum.value, spectrum.kind == TCPT_SPEC_RGB_ALBEDO_SRGB, cs, nullptr)) { error = "add_delta_light: an RGB component exceeds 1 after linearisation (the reference panics: rgb_sigmoid_polynomial.rs:95-108)"; return TCPT_ERR_INVALID; }
+    }
     HostPrimitive p; p.kind = kind; p.light_intensity = intensity; p.angle_inner = angle_inner; p.angle_outer = angle_outer;
     p.light_spectrum = resolve_spectrum(spectrum);
     std::memcpy(p.local_to_world.m, l2w, 64);

@@ -67,6 +67,9 @@ struct FlatStorage {
     tcpt_flat_scene view{};
 };
 
+// guide table of a CDF search (tcpt_flat_env): out[j] = #{i : cdf[i] <= j/G}, j = 0..G (G a power of two: j/G is exact in f32)
+void build_cdf_guide(const float* cdf, uint32_t n, uint32_t G, uint32_t* out);
+
 class HostScene {
    public:
     HostTables tables;

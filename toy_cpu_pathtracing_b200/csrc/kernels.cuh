@@ -699,6 +699,10 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ DSce
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)nb); atomicAdd(&stats[3], (unsigned long long)nt); }
 }
 
+__global__ void k_cdf_search(const float* __restrict__ cdf, uint32_t n, const uint32_t* __restrict__ guide, uint32_t G, const float* __restrict__ u, int m, uint32_t* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) out[i] = sample_from_cdf(cdf, n, guide, G, u[i]);
+}
+
 __global__ void k_sampler_stream(const __grid_constant__ DRender R, uint32_t px, uint32_t py, uint32_t si, const int32_t* kinds, int n, float* out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     DSampler smp = make_sampler(R, px, py, si);

@@ -19,6 +19,7 @@
 #include "../../include/tcpt_flat.h"
 #include "host_scene.h"
 #include "kernels.cuh"
+#include "lbvh.cuh"
 
 using namespace tcpt;
 
@@ -29,9 +30,10 @@ struct DeviceBuffers {  // one flattened scene on the device
     DScene view{};
     uint32_t max_bvh_depth = 0;
     bool valid = false;
+    bool traversal_only = false;   // built by tcpt_scene_build_soup: BVH and triangles only, nothing to shade with
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -102,6 +104,7 @@ struct tcpt_ctx {
     uint64_t default_slots = 0;  // path-slot budget of a pass when the caller gives none (see render_into)
     // multi-GPU: this context's rank in an NCCL communicator (tcpt_comm_init); the ctx owns the communicator
     ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;
+    double soup_build_ms = 0.0; uint64_t soup_records = 0; uint32_t soup_levels = 0;   // last tcpt_scene_build_soup
     cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
 };
 
@@ -130,6 +133,7 @@ void free_scene(DeviceBuffers& db) {
     for (void* p : db.allocs) cudaFree(p);
     db.allocs.clear();
     db.valid = false;
+    db.traversal_only = false;
 }
 
 // color/src/gamut.rs:29-69 with glam's Mat3 arithmetic (column major), evaluated on the host like the reference does
@@ -194,6 +198,7 @@ int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera&
     if (!p || p->width == 0 || p->height == 0 || p->spp == 0) return fail(ctx, TCPT_ERR_INVALID, "render: width, height and spp must be positive");
     if (p->integrator < 0 || p->integrator > TCPT_INTEGRATOR_NORMAL || p->sampler < 0 || p->sampler > 1) return fail(ctx, TCPT_ERR_INVALID, "render: unknown integrator or sampler");
     if (!ctx->dev.valid) return fail(ctx, TCPT_ERR_INVALID, "render: no scene uploaded (call tcpt_scene_build or tcpt_upload_flat_scene)");
+    if (ctx->dev.traversal_only) return fail(ctx, TCPT_ERR_INVALID, "render: the scene of tcpt_scene_build_soup holds traversal data only (tcpt_trace / tcpt_trace_device)");
     std::memset(&R, 0, sizeof R);
     R.width = p->width; R.height = p->height; R.spp = p->spp; R.seed = p->seed; R.max_depth = p->max_depth;
     R.integrator = p->integrator; R.sampler = p->sampler; R.exposure = p->exposure;
@@ -566,6 +571,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
+    else if (n == "soup_leaf") ctx->opt.soup_leaf = value;               // triangles per leaf of tcpt_scene_build_soup
     else if (n == "env_nee_table") ctx->opt.env_nee_table = value;       // takes effect at the next scene upload
     else if (n == "sobol_prefix_mb") ctx->opt.sobol_prefix_mb = value;
     else if (n == "sobol_pass") ctx->opt.sobol_pass = value;
@@ -837,6 +843,54 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     db.max_bvh_depth = s->max_bvh_depth;
     ctx->stats.max_bvh_depth = s->max_bvh_depth;
     db.valid = true;
+    return TCPT_OK;
+}
+
+// BASELINE.json configs[4]: a triangle soup as a traversal-only scene, BVH built on the device (csrc/lbvh.cuh)
+int tcpt_scene_build_soup(tcpt_ctx* ctx, const float* triangles, uint32_t n_triangles) {
+    if (!ctx || !triangles || n_triangles == 0) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    // the small tables of a one-primitive scene (identity transform, Render space = world space) go through the ordinary upload ...
+    tcpt_flat_scene f{};
+    tcpt_bvh_node dummy{};
+    const int32_t items[2] = {0, 0};
+    tcpt_flat_geometry g{}; g.node_base = 1; g.node_count = 1; g.slot_base = 0; g.tri_count = n_triangles;
+    tcpt_flat_primitive P{};
+    const float ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    std::memcpy(P.l2r, ident, sizeof ident); std::memcpy(P.r2l, ident, sizeof ident);
+    P.geometry = 0; P.material = 0; P.kind = 0; P.light_index = -1; P.identity = 1; P.env = -1;
+    tcpt_flat_material m{}; m.type = TCPT_MAT_LAMBERT; m.color.kind = 0; m.color.c[0] = 0.5f; m.color.texture = -1; m.coat_tint.texture = -1; m.normal_texture = -1; m.eta = 1.5f;
+    f.bvh_nodes = &dummy; f.n_bvh_nodes = 1; f.tlas_node_count = 1; f.tlas_items = items; f.n_tlas_items = 1;
+    f.geometries = &g; f.n_geometries = 1; f.primitives = &P; f.n_primitives = 1; f.materials = &m; f.n_materials = 1;
+    f.max_bvh_depth = 1;
+    int rc = tcpt_upload_flat_scene(ctx, &f);
+    if (rc != TCPT_OK) return rc;
+    ctx->dev.valid = false;
+    // ... the triangles and the BVH never exist on the host
+    float* d_tri = nullptr;
+    CU(cudaMalloc((void**)&d_tri, (size_t)n_triangles * 9 * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d_tri, triangles, (size_t)n_triangles * 9 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_tri); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    tcpt::lbvh::Built b;
+    std::string err;
+    const bool ok = tcpt::lbvh::build(d_tri, n_triangles, (uint32_t)ctx->opt.soup_leaf, ctx->sm_count, ctx->stream, b, err);
+    cudaFree(d_tri);
+    if (!ok) return fail(ctx, TCPT_ERR_CUDA, "build_soup: " + err);
+    ctx->dev.allocs.push_back(b.nodes); ctx->dev.allocs.push_back(b.tri_verts);
+    if (b.max_stack >= TCPT_TRAVERSAL_STACK) return fail(ctx, TCPT_ERR_LIMIT, "build_soup: BVH deeper than the traversal stack");
+    ctx->dev.view.nodes = b.nodes; ctx->dev.view.tri_verts = b.tri_verts;
+    ctx->dev.max_bvh_depth = b.max_stack; ctx->stats.max_bvh_depth = b.max_stack;
+    ctx->soup_build_ms = b.build_ms; ctx->soup_records = b.n_nodes; ctx->soup_levels = b.levels;
+    ctx->dev.traversal_only = true;
+    ctx->dev.valid = true;
+    return TCPT_OK;
+}
+int tcpt_soup_build_info(const tcpt_ctx* ctx, double* build_ms, uint64_t* n_records, uint32_t* levels) {
+    if (!ctx) return TCPT_ERR_INVALID;
+    if (build_ms) *build_ms = ctx->soup_build_ms;
+    if (n_records) *n_records = ctx->soup_records;
+    if (levels) *levels = ctx->soup_levels;
     return TCPT_OK;
 }
 
@@ -1165,6 +1219,26 @@ int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* ou
         else { o[0] = prim; o[1] = (int32_t)h1[2 * (size_t)i + 1]; std::memcpy(&o[2], &h0[4 * (size_t)i], 16); }
     }
     return fetch_stats(ctx);
+}
+
+// the CDF search of EnvironmentLight::sample_infinite_light (environment_light.rs:218-223) alone, as the device runs it (guide table + bisection)
+int tcpt_cdf_search(tcpt_ctx* ctx, const float* cdf, uint32_t n, uint32_t guide_cells, const float* u, int m, uint32_t* out) {
+    if (!ctx || !cdf || !u || !out || n == 0 || m <= 0 || guide_cells == 0 || (guide_cells & (guide_cells - 1)) != 0) return TCPT_ERR_INVALID;
+    if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> guide(guide_cells + 1);
+    build_cdf_guide(cdf, n, guide_cells, guide.data());
+    float *d_cdf = nullptr, *d_u = nullptr; uint32_t *d_g = nullptr, *d_o = nullptr;
+    CU(cudaMalloc((void**)&d_cdf, n * sizeof(float))); CU(cudaMalloc((void**)&d_u, (size_t)m * sizeof(float)));
+    CU(cudaMalloc((void**)&d_g, guide.size() * sizeof(uint32_t))); CU(cudaMalloc((void**)&d_o, (size_t)m * sizeof(uint32_t)));
+    CU(cudaMemcpy(d_cdf, cdf, n * sizeof(float), cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_u, u, (size_t)m * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_g, guide.data(), guide.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    k_cdf_search<<<grid_for(ctx, (uint64_t)m, 128), 128, 0, ctx->stream>>>(d_cdf, n, d_g, guide_cells, d_u, m, d_o);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, d_o, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    cudaFree(d_cdf); cudaFree(d_u); cudaFree(d_g); cudaFree(d_o);
+    return TCPT_OK;
 }
 
 int tcpt_sampler_stream(tcpt_ctx* ctx, int sampler, uint32_t spp, uint32_t width, uint32_t height, uint32_t seed, uint32_t px, uint32_t py,

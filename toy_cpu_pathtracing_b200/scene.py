@@ -574,6 +574,18 @@ class Scene:
         ctx.check(lib.tcpt_scene_build(h, capi.as_ptr(pos, C.c_float)), allow_no_gpu=True)
         self.built = True
 
+    # BASELINE.json configs[4]: a triangle soup as a traversal-only scene whose BVH is built on the device (tcpt_scene_build_soup, csrc/lbvh.cuh)
+    def build_soup(self, triangles) -> None:
+        """triangles: (n, 3, 3) f32 vertices in world space (= Render space: one primitive, identity transform, primitive index 0)."""
+        tri = np.ascontiguousarray(triangles, dtype=f32).reshape(-1, 9)
+        self.ctx.check(self.ctx.lib.tcpt_scene_build_soup(self.ctx.handle, capi.as_ptr(tri, C.c_float), len(tri)))
+        self.built = True
+
+    def soup_build_info(self) -> dict:
+        ms, rec, lev = C.c_double(0), C.c_uint64(0), C.c_uint32(0)
+        self.ctx.check(self.ctx.lib.tcpt_soup_build_info(self.ctx.handle, C.byref(ms), C.byref(rec), C.byref(lev)))
+        return {"build_ms": ms.value, "records": rec.value, "levels": lev.value}
+
     # --- backend protocol used by SceneDescription.replay
     def add_mesh(self, pos, nrm, uv, idx):
         lib, h = self.ctx.lib, self.ctx.handle
