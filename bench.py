@@ -526,6 +526,7 @@ def main_gpu(args, wl):
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only
         try:
             arm = CpuArm(wl, scene.desc, cam)
+            arm.sample(max(2.0, args.cpu_seconds / 4.0))      # warm-up: settles the paths-per-second estimate the real sample is sized with (the reference arm has warm-up steps too)
             info = arm.sample(args.cpu_seconds)
             line["cpu_baseline"] = {"value": info["mrays"], "unit": "Mrays/s", "cores": info["cores"], "kind": "port", "sample": info["sample"], "mpaths_per_s": info["mpaths"],
                                     "rays_per_path": info["rays_per_path"]}

@@ -552,17 +552,27 @@ __device__ __forceinline__ void shade_position(const DScene& sc, const DRender& 
 #ifndef TCPT_SHADE_THREADS
 #define TCPT_SHADE_THREADS 512
 #endif
+#ifndef TCPT_SHADE_THREADS_LAMBERT
+#define TCPT_SHADE_THREADS_LAMBERT TCPT_SHADE_THREADS
+#endif
 #ifndef TCPT_SHADE_SYNC
 #define TCPT_SHADE_SYNC 1
 #endif
+// block shape of k_shade<B>: the material buckets run ONE big block per SM whose warps start every vertex together (see the kernel);
+// the register budget follows from the block size (512 threads: 128 registers, 640: 96, 768: 80)
+template <int B> struct ShadeCfg {
+    static constexpr int threads = B == 5 ? TCPT_SHADE_THREADS_LAMBERT : TCPT_SHADE_THREADS;
+    static constexpr int per_sm_128 = B >= 6 ? 8 : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS;   // resident blocks if blocks were 128 threads
+    static constexpr int min_blocks = per_sm_128 * 128 / threads > 0 ? per_sm_128 * 128 / threads : 1;
+};
 template <int B, bool FIRST = false>
-__global__ void __launch_bounds__(TCPT_SHADE_THREADS, (B >= 6 ? 8 : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS) * 128 / TCPT_SHADE_THREADS) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
+__global__ void __launch_bounds__(ShadeCfg<B>::threads, ShadeCfg<B>::min_blocks) k_shade(const __grid_constant__ DScene sc, const __grid_constant__ DRender R,
                                                                                      const __grid_constant__ DState st, const __grid_constant__ PathList L, int cur, int sh, uint32_t stage) {
     if (B == 0 && blockIdx.x == 0 && threadIdx.x == 0) { st.counters[24] = 0; st.counters[25] = 0; }  // work counters of the next trace launch
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n = st.counters[4 + TCPT_BUCKET_STRIDE * cur + B];
     // whole warps iterate together (warp_push is warp-collective); with TCPT_SHADE_SYNC whole blocks do, and start every vertex together
-    const uint32_t unit = (TCPT_SHADE_SYNC && B < 6) ? (uint32_t)TCPT_SHADE_THREADS : 32u;
+    const uint32_t unit = (TCPT_SHADE_SYNC && B < 6) ? (uint32_t)ShadeCfg<B>::threads : 32u;
     const uint32_t n_round = (n + unit - 1u) / unit * unit;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
         if (TCPT_SHADE_SYNC && B < 6) __syncthreads();
@@ -697,6 +707,27 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ DSce
     if (any_hit) trace_queue<true, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, store);
     else trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, store);
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)nb); atomicAdd(&stats[3], (unsigned long long)nt); }
+}
+
+// tcpt_trace's host-facing layouts <-> the SoA queues: rays n x {o[3], d[3], tmax} -> n x {o, tmax} then n x {d, 0};
+// hit records n x {t, b0, b1, b2} then n x {prim, tri} -> n x {prim, tri, t bits, b0 bits, b1 bits, b2 bits} (any hit: {0|1, 0, 0, 0, 0, 0})
+__global__ void __launch_bounds__(256) k_pack_rays(const float* __restrict__ in, int n, float4* __restrict__ q) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* r = in + 7 * (size_t)i;
+        q[i] = make_float4(r[0], r[1], r[2], r[6]);
+        q[(size_t)n + i] = make_float4(r[3], r[4], r[5], 0.0f);
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_hits(const float4* __restrict__ h0, int n, int any_hit, int32_t* __restrict__ out) {
+    const uint2* h1 = (const uint2*)(h0 + n);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = h0[i]; const uint2 b = h1[i];
+        int32_t* o = out + 6 * (size_t)i;
+        const int32_t prim = (int32_t)b.x;
+        if (any_hit) { o[0] = prim >= 0 ? 1 : 0; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
+        else if (prim < 0) { o[0] = -1; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
+        else { o[0] = prim; o[1] = (int32_t)b.y; o[2] = __float_as_int(a.x); o[3] = __float_as_int(a.y); o[4] = __float_as_int(a.z); o[5] = __float_as_int(a.w); }
+    }
 }
 
 __global__ void k_cdf_search(const float* __restrict__ cdf, uint32_t n, const uint32_t* __restrict__ guide, uint32_t G, const float* __restrict__ u, int m, uint32_t* __restrict__ out) {

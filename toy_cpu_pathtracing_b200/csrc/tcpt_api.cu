@@ -162,13 +162,25 @@ void srgb_xyz_to_rgb(float out[9]) {
     std::memcpy(out, v, sizeof v);
 }
 
+// device memory of one path slot: 14 float4 records (path state, both extension queues, hit record, shadow queue), the uint2 half of the
+// hit record and one order entry per shading bucket (ensure_state below allocates exactly this list)
+constexpr uint64_t kBytesPerSlot = 14 * sizeof(float4) + sizeof(uint2) + sizeof(uint32_t) * TCPT_N_BUCKETS;
+static_assert(kBytesPerSlot == 268, "update the figure quoted in include/tcpt.h and DESIGN.md");
+
 int ensure_state(tcpt_ctx* ctx, uint32_t capacity) {
     if (ctx->st_capacity >= capacity) return TCPT_OK;
     for (void* p : ctx->st_allocs) cudaFree(p);
     ctx->st_allocs.clear();
     ctx->st_capacity = 0;
     auto alloc = [&](size_t bytes, void** out) -> int {
-        CU(cudaMalloc(out, bytes));
+        const cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) {   // give back what this attempt took: the caller may retry with a smaller pass
+            cudaGetLastError();
+            for (void* q : ctx->st_allocs) cudaFree(q);
+            ctx->st_allocs.clear();
+            ctx->error = std::string("cudaMalloc of the wavefront state: ") + cudaGetErrorString(e);
+            return TCPT_ERR_NOMEM;
+        }
         ctx->st_allocs.push_back(*out);
         return TCPT_OK;
     };
@@ -341,7 +353,10 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         ctx->stats.kernel_launches++;
     }
     const int g128 = grid_for(ctx, n_slots, 128);
-    const int gsh = grid_for(ctx, n_slots, TCPT_SHADE_THREADS) < 1 ? 1 : (int)std::min<uint64_t>((uint64_t)grid_for(ctx, n_slots, TCPT_SHADE_THREADS), std::max<uint64_t>(1, (uint64_t)ctx->sm_count * ctx->opt.blocks_per_sm * 128 / TCPT_SHADE_THREADS));  // the shading kernels' own block size
+    // the shading kernels' own block sizes (ShadeCfg<B>): as many blocks as the trace grid has threads for
+    auto shade_grid = [&](int threads) { return (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_slots + threads - 1) / threads, (uint64_t)ctx->sm_count * ctx->opt.blocks_per_sm * 128 / threads)); };
+#define TCPT_SHADE_LAUNCH(...) k_shade<__VA_ARGS__><<<shade_grid(ShadeCfg<TCPT_FIRST_ARG(__VA_ARGS__)>::threads), ShadeCfg<TCPT_FIRST_ARG(__VA_ARGS__)>::threads, 0, stream>>>(sc, R, st, L, cur, sh, stage)
+#define TCPT_FIRST_ARG(a, ...) a
     if (R.integrator >= TCPT_INTEGRATOR_ALBEDO) {  // AOV renderers: one camera ray per sample, no bounces
         if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
         else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3);
@@ -377,25 +392,25 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
                 ctx->stats.kernel_launches++; ctx->stats.shade_launches++;
             } else {
                 if (stage == 0) {  // bounce 0 has its own instantiations (no previous-bounce half; the terminal bucket is empty)
-                    k_shade<0, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<1, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<2, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<3, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<4, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<5, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<6, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<7, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<8, true><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    TCPT_SHADE_LAUNCH(0, true);
+                    TCPT_SHADE_LAUNCH(1, true);
+                    TCPT_SHADE_LAUNCH(2, true);
+                    TCPT_SHADE_LAUNCH(3, true);
+                    TCPT_SHADE_LAUNCH(4, true);
+                    TCPT_SHADE_LAUNCH(5, true);
+                    TCPT_SHADE_LAUNCH(6, true);
+                    TCPT_SHADE_LAUNCH(7, true);
+                    TCPT_SHADE_LAUNCH(8, true);
                 } else {
-                    k_shade<0><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<1><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<2><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<3><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<4><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<5><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<6><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<7><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
-                    k_shade<8><<<gsh, TCPT_SHADE_THREADS, 0, stream>>>(sc, R, st, L, cur, sh, stage);
+                    TCPT_SHADE_LAUNCH(0);
+                    TCPT_SHADE_LAUNCH(1);
+                    TCPT_SHADE_LAUNCH(2);
+                    TCPT_SHADE_LAUNCH(3);
+                    TCPT_SHADE_LAUNCH(4);
+                    TCPT_SHADE_LAUNCH(5);
+                    TCPT_SHADE_LAUNCH(6);
+                    TCPT_SHADE_LAUNCH(7);
+                    TCPT_SHADE_LAUNCH(8);
                 }
                 ctx->stats.kernel_launches += 9; ctx->stats.shade_launches += 9;
             }
@@ -449,25 +464,32 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     if (owned == 0 || s0 == s1) return TCPT_OK;
     // Path-slot budget of one pass.  Every pass pays a fixed latency (about 35 launches whose deep-bounce queues are nearly
     // empty: 4 to 8 ms on the 4K frame), so passes are made as large as memory comfortably allows: up to 128 Mi slots
-    // (264 B each: 34 GB of the 180 GB), never more than 45 % of the memory that is free.
+    // (268 B each: 36 GB of the 180 GB), never more than 45 % of the memory that is free.
     uint64_t budget = p->max_slots;
     if (budget == 0) {
         if (ctx->default_slots == 0) {  // asked once per context: cudaMemGetInfo was measured to stall a render by up to 80 ms
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)16 << 30; }
-            const uint64_t avail = (uint64_t)free_b + (uint64_t)ctx->st_capacity * 264u;
-            uint64_t b = (uint64_t)(0.45 * (double)avail) / 264u;
+            const uint64_t avail = (uint64_t)free_b + (uint64_t)ctx->st_capacity * kBytesPerSlot;
+            uint64_t b = (uint64_t)(0.45 * (double)avail) / kBytesPerSlot;
             if (b > (128ull << 20)) b = 128ull << 20;
             if (b < (1ull << 20)) b = 1ull << 20;
             ctx->default_slots = b;
         }
         budget = ctx->default_slots;
     }
-    const uint32_t np = (uint32_t)(owned < budget ? owned : budget);
-    uint32_t sc_per_pass = (uint32_t)(budget / np);
-    if (sc_per_pass < 1) sc_per_pass = 1;
-    if (sc_per_pass > s1 - s0) sc_per_pass = s1 - s0;
-    rc = ensure_state(ctx, (uint32_t)((uint64_t)np * sc_per_pass));
+    if (budget > 0xffffffffull) budget = 0xffffffffull;   // slots are indexed with 32 bits
+    uint32_t np, sc_per_pass;
+    for (;;) {
+        np = (uint32_t)(owned < budget ? owned : budget);
+        sc_per_pass = (uint32_t)(budget / np);
+        if (sc_per_pass < 1) sc_per_pass = 1;
+        if (sc_per_pass > s1 - s0) sc_per_pass = s1 - s0;
+        rc = ensure_state(ctx, (uint32_t)((uint64_t)np * sc_per_pass));
+        // the budget is a guess made once per context (other tenants, a Z-Sobol table that has grown since): shrink the pass instead of failing
+        if (rc == TCPT_ERR_NOMEM && p->max_slots == 0 && budget > (1ull << 20)) { budget >>= 1; ctx->default_slots = budget; continue; }
+        break;
+    }
     if (rc) return rc;
     PathList none{nullptr, nullptr};
     for (uint64_t pb = 0; pb < owned; pb += np) {
@@ -771,8 +793,69 @@ static bool one_light_always_on(const tcpt_flat_scene* s, const HostTables& T) {
     return false;  // spot lights: the cone factor can vanish
 }
 
+// Every cross-reference of a flattened scene, checked before anything is uploaded: this is the ABI a foreign flatten.rs calls, and an
+// index out of range would otherwise surface as a device fault instead of TCPT_ERR_INVALID.
+static bool validate_flat(const tcpt_flat_scene* s, std::string& why) {
+    auto bad = [&](const std::string& w) { why = "upload: " + w; return false; };
+    if (s->n_bvh_nodes == 0 || !s->bvh_nodes || s->tlas_node_count == 0 || s->tlas_node_count > s->n_bvh_nodes) return bad("no BVH nodes / bad tlas_node_count");
+    if (s->n_primitives == 0 || !s->primitives) return bad("no primitives");
+    if ((s->n_tlas_items && !s->tlas_items) || (s->n_tri_slots && !s->tri_verts) || (s->n_geometries && !s->geometries) || (s->n_materials && !s->materials) ||
+        (s->n_textures && !s->textures) || (s->n_lights && !s->light_list) || (s->n_envs && !s->envs)) return bad("a non-empty table has a null pointer");
+    for (uint32_t i = 0; i < s->n_tlas_items; ++i) {
+        const int32_t prim = s->tlas_items[2 * (size_t)i];
+        if (prim < 0 || (uint32_t)prim >= s->n_primitives) return bad("tlas_items names a primitive out of range");
+        if (s->primitives[prim].geometry < 0) return bad("tlas_items names a primitive without geometry");
+    }
+    for (uint32_t i = 0; i < s->n_geometries; ++i) {
+        const tcpt_flat_geometry& g = s->geometries[i];
+        if (!g.single && g.node_base >= s->n_bvh_nodes) return bad("geometry node_base out of range");
+        if ((uint64_t)g.slot_base + g.tri_count > s->n_tri_slots && s->n_tri_slots != 0) return bad("geometry triangle slots out of range");
+        if (s->n_triangles != 0 && (uint64_t)g.index_base + g.tri_count > s->n_triangles) return bad("geometry index range out of range");
+        if (s->n_vertices != 0 && g.vertex_base >= s->n_vertices) return bad("geometry vertex_base out of range");
+    }
+    for (uint32_t i = 0; i < s->n_materials; ++i) {
+        const tcpt_flat_material& m = s->materials[i];
+        auto tex_ok = [&](int32_t t) { return t < 0 || (uint32_t)t < s->n_textures; };
+        if (m.type < TCPT_MAT_LAMBERT || m.type > TCPT_MAT_GLASS) return bad("unknown material type");
+        if ((m.color.kind == 4 && (m.color.texture < 0 || !tex_ok(m.color.texture))) || (m.coat_tint.kind == 4 && (m.coat_tint.texture < 0 || !tex_ok(m.coat_tint.texture))) || !tex_ok(m.normal_texture))
+            return bad("material texture index out of range");
+        const tcpt_flat_float* fl[] = {&m.intensity, &m.roughness, &m.metallic, &m.ior, &m.coat_ior, &m.coat_roughness, &m.coat_thickness};
+        for (const tcpt_flat_float* f : fl) if (f->is_texture && (f->texture < 0 || (uint32_t)f->texture >= s->n_textures)) return bad("material float texture index out of range");
+    }
+    for (uint32_t i = 0; i < s->n_textures; ++i) {
+        const tcpt_flat_texture& t = s->textures[i];
+        if (t.channels != 1 && t.channels != 3) return bad("texture channels must be 1 or 3");
+        if (t.width == 0 || t.height == 0 || t.offset + (uint64_t)t.width * t.height * t.channels > s->n_texture_bytes) return bad("texture outside texture_bytes");
+    }
+    for (uint32_t i = 0; i < s->n_primitives; ++i) {
+        const tcpt_flat_primitive& P = s->primitives[i];
+        if (P.kind < 0 || P.kind > 5) return bad("unknown primitive kind");
+        if (P.kind <= 1) {
+            if (P.geometry < 0 || (uint32_t)P.geometry >= s->n_geometries) return bad("primitive geometry out of range");
+            if (P.material < 0 || (uint32_t)P.material >= s->n_materials) return bad("primitive material out of range");
+            if (P.kind == 1 && (uint64_t)P.area_base + s->geometries[P.geometry].tri_count > s->n_area) return bad("emissive primitive area table out of range");
+        }
+        if (P.kind == 2 && (P.env < 0 || (uint32_t)P.env >= s->n_envs)) return bad("environment primitive env index out of range");
+        if (P.light_index >= (int32_t)s->n_lights) return bad("primitive light_index out of range");
+    }
+    for (uint32_t i = 0; i < s->n_lights; ++i) {
+        const int32_t prim = s->light_list[i];
+        if (prim < 0 || (uint32_t)prim >= s->n_primitives || s->primitives[prim].kind == 0) return bad("light_list names a primitive that is not a light");
+    }
+    for (uint32_t i = 0; i < s->n_envs; ++i) {
+        const tcpt_flat_env& e = s->envs[i];
+        const uint64_t px = (uint64_t)e.width * e.height;
+        if (px == 0 || e.data_offset + 3 * px > s->n_env_floats || e.marginal_offset + e.height > s->n_env_floats || e.conditional_offset + px > s->n_env_floats) return bad("environment map outside env_floats");
+        if (e.guide_h == 0 || e.guide_w == 0 || (e.guide_h & (e.guide_h - 1)) || (e.guide_w & (e.guide_w - 1))) return bad("environment guide sizes must be powers of two");
+        if (e.marginal_guide_offset + e.guide_h + 1 > s->n_env_guides || e.conditional_guide_offset + (uint64_t)e.height * (e.guide_w + 1) > s->n_env_guides) return bad("environment guides outside env_guides");
+        if (e.primitive < 0 || (uint32_t)e.primitive >= s->n_primitives) return bad("environment map names a primitive out of range");
+    }
+    return true;
+}
+
 int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     if (!ctx || !s) return TCPT_ERR_INVALID;
+    { std::string why; if (!validate_flat(s, why)) return fail(ctx, TCPT_ERR_INVALID, why); }
     if (!ctx->stream) return fail(ctx, TCPT_ERR_CUDA, "no CUDA device");
     if (!ctx->d_cmf) return fail(ctx, TCPT_ERR_INVALID, "upload: call tcpt_set_tables first");
     if (s->n_lights > TCPT_MAX_LIGHTS) return fail(ctx, TCPT_ERR_LIMIT, "upload: too many lights");
@@ -1193,31 +1276,27 @@ int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* ou
     if (!ctx->dev.valid) return fail(ctx, TCPT_ERR_INVALID, "trace: no scene uploaded");
     if (n == 0) return TCPT_OK;
     CU(cudaSetDevice(ctx->device));
-    std::vector<float> packed((size_t)n * 8);
-    for (int i = 0; i < n; ++i) {
-        const float* r = rays + 7 * (size_t)i;
-        float* o = &packed[4 * (size_t)i]; float* d = &packed[4 * ((size_t)n + i)];
-        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[6]; d[0] = r[3]; d[1] = r[4]; d[2] = r[5]; d[3] = 0.0f;
-    }
-    void* d_rays = nullptr; void* d_hits = nullptr;
-    CU(cudaMalloc(&d_rays, packed.size() * 4));
-    cudaError_t e = cudaMalloc(&d_hits, (size_t)n * 24);
-    if (e != cudaSuccess) { cudaFree(d_rays); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    // the caller's AoS rays go up as they are and come back as AoS hit records: the SoA queues the kernels read are (un)packed on the
+    // device (a host loop over 16 M rays cost more than the traversal)
+    float* d_in = nullptr; void* d_rays = nullptr; void* d_hits = nullptr; int32_t* d_out = nullptr;
+    auto release = [&]() { cudaFree(d_in); cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_out); };
+    cudaError_t e = cudaMalloc((void**)&d_in, (size_t)n * 7 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_rays, (size_t)n * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&d_hits, (size_t)n * 24);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)n * 6 * sizeof(int32_t));
+    if (e != cudaSuccess) { release(); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
     reset_stats(ctx);
-    cudaMemcpyAsync(d_rays, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_in, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    k_pack_rays<<<grid_for(ctx, (uint64_t)n, 256), 256, 0, ctx->stream>>>(d_in, n, (float4*)d_rays);
     int rc = tcpt_trace_device(ctx, d_rays, n, any_hit, d_hits, nullptr);
-    std::vector<uint8_t> hits((size_t)n * 24);
-    if (rc == TCPT_OK) { e = cudaMemcpyAsync(hits.data(), d_hits, hits.size(), cudaMemcpyDeviceToHost, ctx->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
-    cudaFree(d_rays); cudaFree(d_hits);
-    if (rc) return rc;
-    const float* h0 = (const float*)hits.data(); const uint32_t* h1 = (const uint32_t*)(hits.data() + (size_t)n * 16);
-    for (int i = 0; i < n; ++i) {
-        int32_t* o = out_hit + 6 * (size_t)i;
-        const int32_t prim = (int32_t)h1[2 * (size_t)i];
-        if (any_hit) { o[0] = prim >= 0 ? 1 : 0; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
-        else if (prim < 0) { o[0] = -1; o[1] = o[2] = o[3] = o[4] = o[5] = 0; }
-        else { o[0] = prim; o[1] = (int32_t)h1[2 * (size_t)i + 1]; std::memcpy(&o[2], &h0[4 * (size_t)i], 16); }
+    if (rc == TCPT_OK) {
+        k_unpack_hits<<<grid_for(ctx, (uint64_t)n, 256), 256, 0, ctx->stream>>>((const float4*)d_hits, n, any_hit, d_out);
+        e = cudaMemcpyAsync(out_hit, d_out, (size_t)n * 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
     }
+    release();
+    if (rc) return rc;
     return fetch_stats(ctx);
 }
 
@@ -1273,6 +1352,10 @@ int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uin
     DRender R; DCamera cam;
     int rc = make_render(ctx, params, R, cam);
     if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        if (pixels_xy[2 * (size_t)i] >= params->width || pixels_xy[2 * (size_t)i + 1] >= params->height) return fail(ctx, TCPT_ERR_INVALID, "path_samples: pixel outside the frame");
+        if (sample_indices[i] >= params->spp) return fail(ctx, TCPT_ERR_INVALID, "path_samples: sample index >= spp");
+    }
     rc = ensure_state(ctx, (uint32_t)n);
     if (rc) return rc;
     uint32_t* d_xy = nullptr; uint32_t* d_s = nullptr;
