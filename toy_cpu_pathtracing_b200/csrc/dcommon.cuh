@@ -130,6 +130,9 @@ struct DRender {
     // pass geometry: slot = s_local * n_pix + p_local ; owned pixel index = pix_begin + p_local ;
     // owned pixel k -> x = k % width, y = row_offset + (k / width) * row_stride ; sample_index = s_begin + s_local
     uint32_t n_pix, pix_begin, s_begin, s_count, row_offset, row_stride;
+    // exact division of a 32-bit number by n_pix / by width as one 64 x 64 -> high multiply: magic = floor(2^64 / d) + 1 (0 = divisor 1);
+    // floor(n * magic / 2^64) == n / d for every n < 2^32 because n * (magic * d - 2^64) <= n * d < 2^64 (set by set_div_magics on the host)
+    uint64_t n_pix_magic, width_magic;
     // ZSobol pixel-prefix table (see DSampler::sample_index): prefix[dim * prefix_stride + y * width + x], dims < prefix_dims
     const uint32_t* sobol_prefix; uint32_t prefix_dims, prefix_stride;
     // ZSobol pass table (see DSampler::sample_index): rows prefix_dims .. prefix_dims + pass_dims of the same allocation, rebuilt for
@@ -164,6 +167,7 @@ __constant__ const uint32_t* c_sobol_dim1_bytes;
 // index); everything the frame fixes (seed, log2 spp, digit count, tables) is read from the kernel parameters at the call.  The heavy
 // work sits in two __noinline__ functions that take every input BY VALUE: as member functions they took `this`, which forced the
 // sampler into the caller's stack frame and turned every field read of every call into a local-memory load.
+__device__ __forceinline__ uint32_t div_magic(uint32_t n, uint64_t magic) { return magic ? (uint32_t)__umul64hi((uint64_t)n, magic) : n; }
 struct SobolFrame {  // the frame-constant inputs of a Sobol call, packed for the by-value call
     const uint32_t* prefix;   // DRender::sobol_prefix (nullptr: no tables)
     uint32_t prefix_stride, tables;  // tables = prefix_dims | pass_dims << 16 | n_varying_digits << 24
@@ -224,6 +228,27 @@ struct DSampler {
         f.tables = R.sobol_prefix ? (R.prefix_dims | (R.pass_info << 16)) : 0u;
         f.cfg = R.log2_spp | (R.n_base4_digits << 8); f.seed = R.seed;
         return f;
+    }
+
+    // The table entries the next draws of this vertex will load (sample_index: one entry of the prefix table and one of the pass table per
+    // sampler call, each on its own 33 MB row: a DRAM round trip in front of every random number).  Their addresses only depend on the
+    // pixel and the dimension counter, so a vertex asks for them as soon as it knows both, long before the values are needed.
+#ifndef TCPT_PREFETCH_DRAWS
+#define TCPT_PREFETCH_DRAWS 0
+#endif
+    __device__ __forceinline__ void prefetch_draws(const DRender& R, uint32_t offsets) const {   // offsets: bit k set = a sampler call at dimension dim + k
+#if TCPT_PREFETCH_DRAWS
+        if (R.sampler != TCPT_SAMPLER_SOBOL || R.sobol_prefix == nullptr) return;
+        const uint32_t n_prefix = R.prefix_dims, n_pass = R.pass_info & 0xffu;
+        const uint32_t* col = R.sobol_prefix + pix;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            if (!((offsets >> k) & 1u)) continue;
+            const uint32_t d = dim + k;
+            if (d < n_prefix) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (size_t)d * R.prefix_stride));
+            if (d < n_pass) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (size_t)(n_prefix + d) * R.prefix_stride));
+        }
+#endif
     }
 
     __device__ __forceinline__ static uint32_t perm_digit(uint32_t p, uint32_t digit) {

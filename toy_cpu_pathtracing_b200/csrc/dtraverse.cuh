@@ -32,8 +32,12 @@
 #ifndef TCPT_BOTH_PHASES
 #define TCPT_BOTH_PHASES 0       // 1: no phase vote, every iteration runs a triangle step for the lanes holding triangles and a walking step for the others
 #endif
+#ifndef TCPT_MIN_CHUNK
+#define TCPT_MIN_CHUNK 32         // smallest block of ray indices a warp reserves at a time
+#endif
+static_assert(TCPT_MIN_CHUNK >= 32, "a refill hands the idle lanes of a warp consecutive indices of ONE chunk: it must cover a whole warp");
 #ifndef TCPT_SMEM_STACK
-#define TCPT_SMEM_STACK 0         // traversal-stack entries kept in shared memory (the rest, or all of them when 0, live in local memory)
+#define TCPT_SMEM_STACK 8         // the SHORT stack: the first 8 traversal-stack entries live in shared memory (one word per thread and row), deeper ones spill to local memory (measured 0 / 8 / 16 entries: 29.87 / 29.76 / 30.2 ms of traversal per step)
 #endif
 
 namespace tcpt {
@@ -368,7 +372,7 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
     // The chunk shrinks with the queue so that short queues (deep bounces) still spread over the whole grid.
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     uint32_t chunk = n / (n_warps * 8u);
-    chunk = chunk < 32u ? 32u : (chunk > 512u ? 512u : chunk);
+    chunk = chunk < (uint32_t)TCPT_MIN_CHUNK ? (uint32_t)TCPT_MIN_CHUNK : (chunk > 512u ? 512u : chunk);
     uint32_t pool = 0, pool_end = 0;  // warp-uniform: indices [pool, pool_end) belong to this warp
     bool drained = false;             // the global counter has passed n
     for (;;) {

@@ -29,9 +29,9 @@ struct PathList { const uint32_t* xy; const uint32_t* sample; };  // explicit (p
 
 __device__ __forceinline__ void path_coords(const DRender& R, const PathList& L, uint32_t slot, uint32_t* px, uint32_t* py, uint32_t* si) {
     if (L.xy) { *px = __ldg(L.xy + 2 * (size_t)slot); *py = __ldg(L.xy + 2 * (size_t)slot + 1); *si = __ldg(L.sample + slot); return; }
-    const uint32_t s_local = slot / R.n_pix, p_local = slot - s_local * R.n_pix;
+    const uint32_t s_local = div_magic(slot, R.n_pix_magic), p_local = slot - s_local * R.n_pix;
     const uint32_t k = R.pix_begin + p_local;
-    const uint32_t row = k / R.width;
+    const uint32_t row = div_magic(k, R.width_magic);
     *px = k - row * R.width;
     *py = R.row_offset + row * R.row_stride;
     *si = R.s_begin + s_local;
@@ -239,11 +239,10 @@ template <int B> struct BucketInfo {
 // FIRST = compiled for bounce 0 only (k_shade<B, true>): no previous-bounce half, no state loads beyond the wavelength record
 template <int B, bool FIRST = false>
 __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R, const DState& st, const PathList& L, uint32_t stage_in,
-                                             float3 ray_d, uint32_t slot, const float4 h0, const uint2 h1, ShadeOut& out) {
+                                             float3 ray_d, uint32_t slot, const float4 h0, const uint2 h1, const float4 misc, ShadeOut& out) {
     constexpr int MT = BucketInfo<B>::mat;
     const uint32_t stage = FIRST ? 0u : stage_in;
     out.push_ext = false; out.push_sh = false;
-    const float4 misc = st.misc[slot];
     float pdf_prev = misc.x;
     const float lambda0 = misc.y;
     uint32_t flags = __float_as_uint(misc.w);
@@ -252,6 +251,10 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     path_coords(R, L, slot, &px, &py, &si);
     DSampler smp = make_sampler(R, px, py, si);
     smp.dim = __float_as_uint(misc.z);
+    // sampler calls of one bounce sit at dimension offsets 0 (lobe choice; Lambert and metal skip it), 1 (direction), 3 (light choice, skipped
+    // with one light), 4 (triangle of an area light), 5 (point on the light) and 7 (Russian roulette; 3 under pt, which draws nothing for lights)
+    if (!BucketInfo<B>::miss && !BucketInfo<B>::terminal && MT != TCPT_MAT_EMISSIVE)
+        smp.prefetch_draws(R, ((MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) ? 0u : 1u) | 2u | (R.integrator != TCPT_INTEGRATOR_PT ? 0xa0u : 0x08u));
     S4 thr = s4(1.0f), con = s4(0.0f);
     if (!FIRST && stage != 0u) { thr = s4(st.thr[slot]); con = s4(st.con[slot]); }
     const int integrator = R.integrator;
@@ -530,16 +533,25 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     }  // !miss
 }
 
+// What a vertex reads before it can start: its queue position (through the bucketed order), the ray it arrived on, the hit record and
+// the head of its path state.  Four DEPENDENT loads (order -> ray -> slot -> state), each a DRAM round trip at the benchmarked pass size.
+struct VertexIn { float4 d, h0, misc; uint2 h1; };
+template <int B>
+__device__ __forceinline__ VertexIn load_vertex(const DState& st, int cur, uint32_t p, uint32_t n) {
+    VertexIn v;
+    v.d = make_float4(0.0f, 0.0f, 0.0f, 0.0f); v.h0 = v.d; v.misc = v.d; v.h1 = make_uint2(0u, 0u);
+    if (p < n) {
+        const uint32_t i = st.order[(size_t)B * st.capacity + p];
+        v.d = st.ext_d[cur][i]; v.h0 = st.hit0[i]; v.h1 = st.hit1[i];
+        v.misc = st.misc[__float_as_uint(v.d.w) & 0x7fffffffu];
+    }
+    return v;
+}
 // Shades position p of bucket B's range of the bucketed order (p >= n: the lane only takes part in the warp-collective pushes).
 template <int B, bool FIRST = false>
-__device__ __forceinline__ void shade_position(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, int sh, uint32_t stage, uint32_t p, uint32_t n) {
-    const uint32_t* __restrict__ order = st.order + (size_t)B * st.capacity;
+__device__ __forceinline__ void shade_position(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, int sh, uint32_t stage, uint32_t p, uint32_t n, const VertexIn& v) {
     ShadeOut out; out.push_ext = false; out.push_sh = false;
-    if (p < n) {
-        const uint32_t i = order[p];
-        const float4 d = st.ext_d[cur][i];
-        shade_vertex<B, FIRST>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
-    }
+    if (p < n) shade_vertex<B, FIRST>(sc, R, st, L, stage, f3(v.d.x, v.d.y, v.d.z), __float_as_uint(v.d.w) & 0x7fffffffu, v.h0, v.h1, v.misc, out);
     if (B < 6) {  // emissive hits and misses end the path: nothing to push
         uint32_t pe, ps;
         warp_push2(&st.counters[cur ^ 1], out.push_ext, &st.counters[sh], out.push_sh, &pe, &ps);
@@ -558,6 +570,9 @@ __device__ __forceinline__ void shade_position(const DScene& sc, const DRender& 
 #ifndef TCPT_SHADE_SYNC
 #define TCPT_SHADE_SYNC 1
 #endif
+#ifndef TCPT_SHADE_PIPELINE
+#define TCPT_SHADE_PIPELINE 0   // 1: issue the loads of the NEXT vertex before shading this one.  Measured slower (34.3 vs 32.8 ms of shading per step): the 15 registers it holds across the vertex cost more than the four round trips it hides
+#endif
 // block shape of k_shade<B>: the material buckets run ONE big block per SM whose warps start every vertex together (see the kernel);
 // the register budget follows from the block size (512 threads: 128 registers, 640: 96, 768: 80)
 template <int B> struct ShadeCfg {
@@ -574,9 +589,21 @@ __global__ void __launch_bounds__(ShadeCfg<B>::threads, ShadeCfg<B>::min_blocks)
     // whole warps iterate together (warp_push is warp-collective); with TCPT_SHADE_SYNC whole blocks do, and start every vertex together
     const uint32_t unit = (TCPT_SHADE_SYNC && B < 6) ? (uint32_t)ShadeCfg<B>::threads : 32u;
     const uint32_t n_round = (n + unit - 1u) / unit * unit;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += stride) {
+    // software pipeline: the loads of the NEXT vertex are issued before this one is shaded, so their round trips overlap the shading
+    // instead of standing in front of it (ncu: 15 % of the Lambert kernel's stall samples sat on these four loads)
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    VertexIn v = load_vertex<B>(st, cur, p, p < n_round ? n : 0u);
+    for (; p < n_round; p += stride) {
+#if TCPT_SHADE_PIPELINE
+        const VertexIn next = load_vertex<B>(st, cur, p + stride, (p + stride < n_round && p + stride > p) ? n : 0u);
+#endif
         if (TCPT_SHADE_SYNC && B < 6) __syncthreads();
-        shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n);
+        shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n, v);
+#if TCPT_SHADE_PIPELINE
+        v = next;
+#else
+        v = load_vertex<B>(st, cur, p + stride, (p + stride < n_round && p + stride > p) ? n : 0u);
+#endif
     }
 }
 
@@ -584,7 +611,8 @@ __global__ void __launch_bounds__(ShadeCfg<B>::threads, ShadeCfg<B>::min_blocks)
 template <int B>
 __device__ __noinline__ void shade_vertex_call(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, uint32_t stage, uint32_t i, ShadeOut& out) {
     const float4 d = st.ext_d[cur][i];
-    shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), __float_as_uint(d.w) & 0x7fffffffu, st.hit0[i], st.hit1[i], out);
+    const uint32_t slot = __float_as_uint(d.w) & 0x7fffffffu;
+    shade_vertex<B>(sc, R, st, L, stage, f3(d.x, d.y, d.z), slot, st.hit0[i], st.hit1[i], st.misc[slot], out);
 }
 
 // All buckets in one launch: the launch is cut into chunks of 128 consecutive positions of ONE bucket, numbered bucket by bucket

@@ -206,6 +206,12 @@ int grid_for(const tcpt_ctx* ctx, uint64_t n, int block) {
 uint32_t log2_int(uint32_t v) { return v == 0 ? 0 : 31 - (uint32_t)__builtin_clz(v); }
 uint32_t round_up_pow2(uint32_t v) { return v <= 1 ? 1u : 1u << (32 - __builtin_clz(v - 1)); }
 
+// DRender::n_pix_magic / width_magic (see div_magic): call after n_pix and width are set
+void set_div_magics(DRender& R) {
+    auto magic = [](uint32_t d) -> uint64_t { return d <= 1u ? 0ull : (~0ull) / d + 1ull; };   // floor((2^64 - 1) / d) + 1 == floor(2^64 / d) + 1 unless d divides 2^64: then one more than that, still exact (n / 2^64 < 1 / d)
+    R.n_pix_magic = magic(R.n_pix); R.width_magic = magic(R.width);
+}
+
 int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera& cam) {
     if (!p || p->width == 0 || p->height == 0 || p->spp == 0) return fail(ctx, TCPT_ERR_INVALID, "render: width, height and spp must be positive");
     if (p->integrator < 0 || p->integrator > TCPT_INTEGRATOR_NORMAL || p->sampler < 0 || p->sampler > 1) return fail(ctx, TCPT_ERR_INVALID, "render: unknown integrator or sampler");
@@ -497,6 +503,7 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
         for (uint32_t sb = s0; sb < s1; sb += sc_per_pass) {
             DRender Rp = R;
             Rp.n_pix = n_pix; Rp.pix_begin = (uint32_t)pb; Rp.s_begin = sb; Rp.s_count = (s1 - sb) < sc_per_pass ? (s1 - sb) : sc_per_pass;
+            set_div_magics(Rp);
             build_sobol_pass(ctx, Rp, stream);
             rc = run_pass(ctx, Rp, cam, none, n_pix * Rp.s_count, dev_acc, stream);
             if (rc) return rc;
@@ -936,7 +943,7 @@ int tcpt_scene_build_soup(tcpt_ctx* ctx, const float* triangles, uint32_t n_tria
     CU(cudaSetDevice(ctx->device));
     // the small tables of a one-primitive scene (identity transform, Render space = world space) go through the ordinary upload ...
     tcpt_flat_scene f{};
-    tcpt_bvh_node dummy{};
+    tcpt_bvh_node dummy[2] = {};      // placeholders for the TLAS record and the BLAS root: the real records are built on the device below
     const int32_t items[2] = {0, 0};
     tcpt_flat_geometry g{}; g.node_base = 1; g.node_count = 1; g.slot_base = 0; g.tri_count = n_triangles;
     tcpt_flat_primitive P{};
@@ -944,7 +951,7 @@ int tcpt_scene_build_soup(tcpt_ctx* ctx, const float* triangles, uint32_t n_tria
     std::memcpy(P.l2r, ident, sizeof ident); std::memcpy(P.r2l, ident, sizeof ident);
     P.geometry = 0; P.material = 0; P.kind = 0; P.light_index = -1; P.identity = 1; P.env = -1;
     tcpt_flat_material m{}; m.type = TCPT_MAT_LAMBERT; m.color.kind = 0; m.color.c[0] = 0.5f; m.color.texture = -1; m.coat_tint.texture = -1; m.normal_texture = -1; m.eta = 1.5f;
-    f.bvh_nodes = &dummy; f.n_bvh_nodes = 1; f.tlas_node_count = 1; f.tlas_items = items; f.n_tlas_items = 1;
+    f.bvh_nodes = dummy; f.n_bvh_nodes = 2; f.tlas_node_count = 1; f.tlas_items = items; f.n_tlas_items = 1;
     f.geometries = &g; f.n_geometries = 1; f.primitives = &P; f.n_primitives = 1; f.materials = &m; f.n_materials = 1;
     f.max_bvh_depth = 1;
     int rc = tcpt_upload_flat_scene(ctx, &f);
@@ -1368,6 +1375,7 @@ int tcpt_path_samples(tcpt_ctx* ctx, const tcpt_render_params* params, const uin
     rc = ensure_sobol_prefix(ctx, R, ctx->stream);
     if (rc) { cudaFree(d_xy); cudaFree(d_s); return rc; }
     R.n_pix = (uint32_t)n; R.s_count = 1;
+    set_div_magics(R);
     PathList L{d_xy, d_s};
     rc = run_pass(ctx, R, cam, L, (uint32_t)n, nullptr, ctx->stream);
     std::vector<float> rgb((size_t)n * 4);
