@@ -165,14 +165,16 @@ def describe_scene(wl, **scene_kw):
 
 
 def cpu_sample(wl, want_paths):
-    """A strided subsample of the WHOLE frame: pixels (i*k, j*k), 4 sample indices each (more when the whole frame is too small to
-    fill the time), so that the CPU sees the same mix of floor / dragon / sky pixels -- the same rays per path -- as the GPU arm."""
+    """A strided subsample of the WHOLE frame: pixels (i*k, j*k), 64 consecutive sample indices each (more when the whole frame is too
+    small to fill the time), so that the CPU sees the same mix of floor / dragon / sky pixels -- the same rays per path -- as the GPU arm,
+    and the pixel-major order of the reference's loop (every sample of a pixel back to back, renderer.rs:120-134 -> base_renderer.rs:160):
+    its cache locality is part of the CPU's speed (measured on one box: 10.6 / 11.1 / 12.5 / 12.9 Mrays/s at 4 / 6 / 9 / 11 samples per pixel)."""
     W, H = wl["width"], wl["height"]
-    spp = 4
+    spp = int(min(64, wl["frame_spp"]))
     k = int(max(1, np.floor(np.sqrt(W * H * spp / max(1.0, want_paths)))))
     n_pix = ((W + k - 1) // k) * ((H + k - 1) // k)
     if k == 1 and n_pix * spp < 0.7 * want_paths:
-        spp = int(min(wl["frame_spp"], max(4, want_paths / n_pix)))
+        spp = int(min(wl["frame_spp"], max(spp, want_paths / n_pix)))
     return k, spp, n_pix
 
 
@@ -203,7 +205,7 @@ class CpuArm:
         ncores = self.threads if self.threads > 0 else (os.cpu_count() or 1)
         return {"mrays": rays / st["seconds"] / 1e6, "mpaths": st["paths"] / st["seconds"] / 1e6, "cores": ncores, "seconds": st["seconds"], "paths": st["paths"], "rays": rays,
                 "rays_per_path": rays / max(1, st["paths"]),
-                "sample": f"every {k}th pixel in x and y of the whole {wl['width']}x{wl['height']} frame, sample indices 0..{spp - 1}: {st['paths']} paths, "
+                "sample": f"every {k}-th pixel in x and y of the whole {wl['width']}x{wl['height']} frame, sample indices 0..{spp - 1}: {st['paths']} paths, "
                           f"{rays / max(1, st['paths']):.3f} rays/path, {st['seconds']:.2f} s"}
 
     def _render(self, want_paths):
@@ -221,7 +223,9 @@ def workload_config(args, wl, world, cpu_info=None):
     cfg = {"workload": f"scene{wl['scene']} {W}x{H} {wl['integrator']}+{wl['sampler']} max_depth 16, {wl['frame_spp']}-spp frame, "
                        f"{args.spp_per_step} sample indices of every pixel per GPU per step" + (" (BASELINE.json configs[3])" if wl["scene"] == 19 else "") + (" no-coat" if wl.get("kw") else ""),
            "paths_per_gpu_per_step": W * H * args.spp_per_step, "sharding": "spp-pass", "collective": "one ncclReduce of the film accumulators per step, issued inside libtcpt",
-           "cache": f"working set (path state + ray queues, {W * H * args.spp_per_step * 268 / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no explicit flush",
+           "cache": (f"working set (path state + ray queues, {W * H * args.spp_per_step * 268 / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no explicit flush"
+                     if W * H * args.spp_per_step * 268 > 4 * 126e6 else
+                     f"working set {W * H * args.spp_per_step * 268 / 1e6:.0f} MB per GPU does not exceed the 126 MB L2 by a wide margin and nothing is flushed: a test-size workload, not a bench line"),
            "assets": "procedural stand-ins (reference assets are LFS stubs)"}
     if cpu_info is not None:   # the reference arm: what one of ITS steps really covers
         cfg["reference_arm_paths_per_step"] = cpu_info["paths"]
@@ -345,7 +349,7 @@ def main_gpu(args, wl):
     ms = e0.elapsed_time(e1)
     ctx.set_option("stage_timing", 0)
     rays_mine = tot["closest_rays"] + tot["shadow_rays"]
-    mx, sm = over_ranks([ms, rays_mine, tot["paths"], tot["kernel_launches"] + (args.steps if world > 1 else 0)])
+    mx, sm = over_ranks([ms, rays_mine, tot["paths"], tot["kernel_launches"]])   # libtcpt's own kernels only: the ncclReduce kernel of a step is NCCL's
     ms_max, rays_all, paths_all, launches_all = mx[0], sm[1], sm[2], sm[3]
     value = rays_all / (ms_max * 1e-3) / 1e6
 
