@@ -223,9 +223,9 @@ def workload_config(args, wl, world, cpu_info=None):
     cfg = {"workload": f"scene{wl['scene']} {W}x{H} {wl['integrator']}+{wl['sampler']} max_depth 16, {wl['frame_spp']}-spp frame, "
                        f"{args.spp_per_step} sample indices of every pixel per GPU per step" + (" (BASELINE.json configs[3])" if wl["scene"] == 19 else "") + (" no-coat" if wl.get("kw") else ""),
            "paths_per_gpu_per_step": W * H * args.spp_per_step, "sharding": "spp-pass", "collective": "one ncclReduce of the film accumulators per step, issued inside libtcpt",
-           "cache": (f"working set (path state + ray queues, {W * H * args.spp_per_step * 268 / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no explicit flush"
-                     if W * H * args.spp_per_step * 268 > 4 * 126e6 else
-                     f"working set {W * H * args.spp_per_step * 268 / 1e6:.0f} MB per GPU does not exceed the 126 MB L2 by a wide margin and nothing is flushed: a test-size workload, not a bench line"),
+           "cache": (f"working set (path state + ray queues, {W * H * args.spp_per_step * 304 / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no explicit flush"
+                     if W * H * args.spp_per_step * 304 > 4 * 126e6 else
+                     f"working set {W * H * args.spp_per_step * 304 / 1e6:.0f} MB per GPU does not exceed the 126 MB L2 by a wide margin and nothing is flushed: a test-size workload, not a bench line"),
            "assets": "procedural stand-ins (reference assets are LFS stubs)"}
     if cpu_info is not None:   # the reference arm: what one of ITS steps really covers
         cfg["reference_arm_paths_per_step"] = cpu_info["paths"]

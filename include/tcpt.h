@@ -86,7 +86,7 @@ typedef struct {
      * (0,0 = all rows / all samples).  Tile(row) sharding keeps the per-pixel sample order => bitwise equal to one GPU. */
     uint32_t row_offset, row_stride;
     uint32_t spp_begin, spp_end;
-    uint32_t max_slots;                      /* wavefront size in paths (0 = default: up to 128 Mi, 268 B of device memory each, at most 45 % of free memory; halved and retried when the allocation fails) */
+    uint32_t max_slots;                      /* wavefront size in paths (0 = default: up to 128 Mi, 304 B of device memory each, at most 45 % of free memory; halved and retried when the allocation fails) */
 } tcpt_render_params;
 
 typedef struct {

@@ -289,21 +289,31 @@ struct DSampler {
         return sidx;
     }
     __device__ __forceinline__ static int first_pixel_digit(uint32_t log2_spp) { return (int)((log2_spp + 1u) >> 1); }
-    __device__ __forceinline__ static uint64_t sample_index(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
+    // the table entries a sampler call at `dim` reads (prefix row, pass row), split from the arithmetic so that a vertex can ask for the
+    // entries of several calls at once (sobol_draws3)
+    struct SobolLoads { uint32_t hi, e; };
+    __device__ __forceinline__ static SobolLoads sample_index_loads(uint32_t dim, uint32_t pix, const SobolFrame f) {
+        SobolLoads l; l.hi = 0u; l.e = 0u;
+        const uint32_t n_prefix = f.tables & 0xffffu, n_pass = (f.tables >> 16) & 0xffu;
+        const uint32_t* __restrict__ col = f.prefix + pix;   // this pixel's column of the tables
+        if (dim < n_prefix || dim < n_pass) l.hi = __ldg(col + (size_t)dim * f.prefix_stride);
+        if (dim < n_pass) l.e = __ldg(col + (size_t)(n_prefix + dim) * f.prefix_stride);
+        return l;
+    }
+    __device__ __forceinline__ static uint64_t sample_index_from(uint32_t morton, uint32_t dim, const SobolFrame f, const SobolLoads l) {
         const uint32_t log2_spp = f.cfg & 0xffu, nb4 = f.cfg >> 8;
         const bool pow2 = (log2_spp & 1u) == 1u;
         const int last_digit = pow2 ? 1 : 0;
         uint64_t sidx;
         const uint32_t n_prefix = f.tables & 0xffffu, n_pass = (f.tables >> 16) & 0xffu;
-        const uint32_t* __restrict__ col = f.prefix + pix;   // this pixel's column of the tables
         if (dim < n_pass) {
             // Pass table: the samples of one pass differ in their lowest `iv` base-4 digits only, so the permuted digits above those
             // (they are keyed by the digits above them: pixel and pass, not sample) and the permutation of digit iv - 1 (keyed by
             // everything above it) are the same for every sample of the pixel in this pass: computed once per (dimension, pixel,
             // pass) by k_sobol_pass instead of once per path vertex.  Left here: one table-driven digit and iv - 1 hashed ones.
             const uint32_t iv = f.tables >> 24;
-            const uint32_t hi = __ldg(col + (size_t)dim * f.prefix_stride);
-            const uint32_t e = __ldg(col + (size_t)(n_prefix + dim) * f.prefix_stride);
+            const uint32_t hi = l.hi;
+            const uint32_t e = l.e;
             sidx = ((uint64_t)hi << log2_spp) | ((uint64_t)(e & 0xffffu) << (2u * iv));
             if (iv >= 1u) {
                 const uint32_t sh = 2u * iv - 2u;
@@ -313,7 +323,7 @@ struct DSampler {
             return sidx;   // (the pass table is only built for even log2_spp: no trailing binary digit)
         }
         if (dim < n_prefix) {
-            const uint32_t hi = __ldg(col + (size_t)dim * f.prefix_stride);
+            const uint32_t hi = l.hi;
             sidx = ((uint64_t)hi << log2_spp) | permuted_digits(morton, dim, log2_spp, first_pixel_digit(log2_spp) - 1, last_digit);
         } else {
             sidx = permuted_digits(morton, dim, log2_spp, (int)nb4 - 1, last_digit);
@@ -325,6 +335,9 @@ struct DSampler {
             sidx |= digit ^ (mix_bits(((uint64_t)morton >> 1) ^ dk) & 1ull);
         }
         return sidx;
+    }
+    __device__ __forceinline__ static uint64_t sample_index(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
+        return sample_index_from(morton, dim, f, sample_index_loads(dim, pix, f));
     }
     // table entry of (pixel, dimension): the permuted pixel digits, shifted down by log2_spp
     __device__ __forceinline__ static uint32_t pixel_prefix(uint32_t morton, uint32_t dim, uint32_t log2_spp, uint32_t nb4) {
@@ -359,6 +372,32 @@ struct DSampler {
         float2 r;
         r.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
         r.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+        return r;
+    }
+    // Three sampler calls of one vertex at once (a 2-D call at dimension da, a 2-D call at db, a 1-D call at dc): the values are pure
+    // functions of (pixel, sample, dimension), so drawing them before they are needed changes nothing but WHEN their six table entries are
+    // asked for: together, one round trip instead of three in a row in front of the BSDF sample, the light sample and Russian roulette.
+    struct Draws3 { float2 a, b; float c; };
+    __device__ __noinline__ static Draws3 sobol_draws3(uint32_t morton, uint32_t da, uint32_t db, uint32_t dc, uint32_t pix, const SobolFrame f) {
+        const SobolLoads la = sample_index_loads(da, pix, f), lb = sample_index_loads(db, pix, f), lc = sample_index_loads(dc, pix, f);
+        Draws3 r;
+        {
+            const uint64_t a = sample_index_from(morton, da, f, la);
+            const uint64_t h = hash(da + 2u, f.seed);
+            r.a.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+            r.a.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+        }
+        {
+            const uint64_t a = sample_index_from(morton, db, f, lb);
+            const uint64_t h = hash(db + 2u, f.seed);
+            r.b.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+            r.b.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+        }
+        {
+            const uint64_t a = sample_index_from(morton, dc, f, lc);
+            const uint64_t h = hash(dc + 1u, f.seed);
+            r.c = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+        }
         return r;
     }
     // get_1d whose value the caller provably does not use: both samplers are pure functions of the dimension counter, so

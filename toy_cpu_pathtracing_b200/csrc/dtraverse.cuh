@@ -36,6 +36,9 @@
 #define TCPT_MIN_CHUNK 32         // smallest block of ray indices a warp reserves at a time
 #endif
 static_assert(TCPT_MIN_CHUNK >= 32, "a refill hands the idle lanes of a warp consecutive indices of ONE chunk: it must cover a whole warp");
+#ifndef TCPT_POP_CULL
+#define TCPT_POP_CULL 1           // closest hit: a stack entry carries the entry distance of its box and is dropped when it comes off the stack behind the best hit
+#endif
 #ifndef TCPT_SMEM_STACK
 #define TCPT_SMEM_STACK 8         // the SHORT stack: the first 8 traversal-stack entries live in shared memory (one word per thread and row), deeper ones spill to local memory (measured 0 / 8 / 16 entries: 29.87 / 29.76 / 30.2 ms of traversal per step)
 #endif
@@ -173,6 +176,9 @@ struct TraceShared {
     uint32_t w[TS_WORDS][128];
 #if TCPT_SMEM_STACK > 0
     uint32_t stack[TCPT_SMEM_STACK][128];
+#if TCPT_POP_CULL
+    float stack_t[TCPT_SMEM_STACK][128];
+#endif
 #endif
 };
 #define TS_F(row) __uint_as_float(S.w[row][tid])
@@ -206,26 +212,49 @@ struct Traversal {
     }
     __device__ __forceinline__ bool holds_triangles() const { return (cur & TCPT_ENTRY_LEAF) != 0u && blas_sp >= 0; }   // (cur is never NONE between steps)
 
-    __device__ __forceinline__ void push(TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t v) {
+    // A stack entry of a closest-hit walk carries the entry distance `te` of its box (TCPT_POP_CULL): see advance().
+    template <bool ANY>
+    __device__ __forceinline__ void push(TraceShared& S, uint32_t tid, uint32_t* stack, float* stack_t, uint32_t v, float te) {
 #if TCPT_SMEM_STACK > 0
-        if (sp < TCPT_SMEM_STACK) S.stack[sp][tid] = v; else stack[sp - TCPT_SMEM_STACK] = v;
+        if (sp < TCPT_SMEM_STACK) {
+            S.stack[sp][tid] = v;
+#if TCPT_POP_CULL
+            if (!ANY) S.stack_t[sp][tid] = te;
+#endif
+        } else {
+            stack[sp - TCPT_SMEM_STACK] = v;
+#if TCPT_POP_CULL
+            if (!ANY) stack_t[sp - TCPT_SMEM_STACK] = te;
+#endif
+        }
         ++sp;
 #else
-        stack[sp++] = v;
+        stack[sp] = v;
+#if TCPT_POP_CULL
+        if (!ANY) stack_t[sp] = te;
+#endif
+        ++sp;
 #endif
     }
-    __device__ __forceinline__ uint32_t pop(TraceShared& S, uint32_t tid, uint32_t* stack) {
-#if TCPT_SMEM_STACK > 0
+    template <bool ANY>
+    __device__ __forceinline__ uint32_t pop(TraceShared& S, uint32_t tid, uint32_t* stack, float* stack_t, float* te) {
         --sp;
+#if TCPT_SMEM_STACK > 0
+#if TCPT_POP_CULL
+        if (!ANY) *te = sp < TCPT_SMEM_STACK ? S.stack_t[sp][tid] : stack_t[sp - TCPT_SMEM_STACK];
+#endif
         return sp < TCPT_SMEM_STACK ? S.stack[sp][tid] : stack[sp - TCPT_SMEM_STACK];
 #else
-        return stack[--sp];
+#if TCPT_POP_CULL
+        if (!ANY) *te = stack_t[sp];
+#endif
+        return stack[sp];
 #endif
     }
 
     // Tests the first triangle of the pending leaf range.  ANY = Scene::intersect_p (scene.rs:93-103): returns true (ray finished) at the first accepted triangle.
     template <bool ANY, bool COUNT>
-    __device__ __forceinline__ bool tri_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t* n_tri) {
+    __device__ __forceinline__ bool tri_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, float* stack_t, uint32_t* n_tri) {
         const uint32_t bslot = entry_slot(cur);
         cur = entry_more(cur) != 0u ? cur + TCPT_ENTRY_ONE_ITEM : TCPT_ENTRY_NONE;
         const size_t s = 3 * (size_t)bslot;
@@ -254,17 +283,17 @@ struct Traversal {
                 limit = fminf(t_max, cull_limit(t));
             }
         }
-        return advance(S, tid, stack);
+        return advance<ANY>(S, tid, stack, stack_t);
     }
 
     // One walking step: open the instance of a TLAS item if that is what the lane holds, then visit a wide node (four slab tests; the
     // nearest hit child is looked at next, the others are pushed).  Returns true when the ray is finished.
-    template <bool COUNT>
-    __device__ __forceinline__ bool node_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, uint32_t* n_box) {
+    template <bool ANY, bool COUNT>
+    __device__ __forceinline__ bool node_step(const DScene& sc, TraceShared& S, uint32_t tid, uint32_t* stack, float* stack_t, uint32_t* n_box) {
         if (cur & TCPT_ENTRY_LEAF) {
             // TLAS leaf (a leaf inside a BLAS belongs to the triangle phase): open its first primitive, leave the others on the stack
             const uint32_t tslot = entry_slot(cur);
-            if (entry_more(cur) != 0u) push(S, tid, stack, cur + TCPT_ENTRY_ONE_ITEM);
+            if (entry_more(cur) != 0u) push<ANY>(S, tid, stack, stack_t, cur + TCPT_ENTRY_ONE_ITEM, 0.0f);   // (entry distance 0: the other items of the leaf are never dropped)
             const int2 item = __ldg(&sc.tlas_items[tslot]);
             TS_U(TS_CPRIM) = (uint32_t)item.x; TS_U(TS_CTLEAF) = (uint32_t)item.y; TS_U(TS_CTSLOT) = tslot;
             const tcpt_flat_primitive& P = sc.primitives[item.x];
@@ -320,28 +349,36 @@ struct Traversal {
         TCPT_CE(k1, e1, k3, e3) TCPT_CE(k1, e1, k2, e2)
 #endif
 #undef TCPT_CE
-        if (e3 != TCPT_ENTRY_NONE) push(S, tid, stack, e3);
-        if (e2 != TCPT_ENTRY_NONE) push(S, tid, stack, e2);
-        if (e1 != TCPT_ENTRY_NONE) push(S, tid, stack, e1);
+        if (e3 != TCPT_ENTRY_NONE) push<ANY>(S, tid, stack, stack_t, e3, k3);
+        if (e2 != TCPT_ENTRY_NONE) push<ANY>(S, tid, stack, stack_t, e2, k2);
+        if (e1 != TCPT_ENTRY_NONE) push<ANY>(S, tid, stack, stack_t, e1, k1);
         cur = e0;   // NONE when nothing was hit
-        return advance(S, tid, stack);
+        return advance<ANY>(S, tid, stack, stack_t);
     }
 
     // The cheap transitions, taken eagerly at the end of a step so that a lane enters the next iteration with a wide node, an instance
     // or a triangle at hand -- or is finished NOW: with nothing at hand, the ray is done when the stack is empty; a stack back at
     // its height of BLAS entry means this instance is exhausted (back to the Render-space ray); otherwise the next entry comes off.
     // (As separate walking steps these cost every ray one or two of its five or so iterations: rays here are short.)
-    __device__ __forceinline__ bool advance(TraceShared& S, uint32_t tid, uint32_t* stack) {
+    // Closest hit (TCPT_POP_CULL): an entry whose box is entered behind the culling bound is dropped as it comes off the stack.  The bound has
+    // shrunk since the entry was pushed; every box below it is entered at or behind its own entry distance (the slab test is monotone
+    // in the box, see the header), so the visit would have failed all of its slab tests: same candidates, one wide-node visit (or one
+    // instance transform plus the visit of the BLAS root) less.
+    template <bool ANY>
+    __device__ __forceinline__ bool advance(TraceShared& S, uint32_t tid, uint32_t* stack, float* stack_t) {
         if (cur != TCPT_ENTRY_NONE) return false;
-        if (sp == 0) return true;
-        if (sp == blas_sp) {
-            blas_sp = -1;
-            r.o = f3(TS_F(TS_OX), TS_F(TS_OY), TS_F(TS_OZ));
-            r.inv_d = f3(TS_F(TS_WIX), TS_F(TS_WIY), TS_F(TS_WIZ));
-            r.kz = (int)TS_U(TS_WKZ); r.sx = TS_F(TS_WSX); r.sy = TS_F(TS_WSY); r.sz = TS_F(TS_WSZ);
+        for (;;) {
+            if (sp == 0) return true;
+            if (sp == blas_sp) {
+                blas_sp = -1;
+                r.o = f3(TS_F(TS_OX), TS_F(TS_OY), TS_F(TS_OZ));
+                r.inv_d = f3(TS_F(TS_WIX), TS_F(TS_WIY), TS_F(TS_WIZ));
+                r.kz = (int)TS_U(TS_WKZ); r.sx = TS_F(TS_WSX); r.sy = TS_F(TS_WSY); r.sz = TS_F(TS_WSZ);
+            }
+            float te = 0.0f;
+            cur = pop<ANY>(S, tid, stack, stack_t, &te);
+            if (ANY || !TCPT_POP_CULL || !(te > limit)) return false;
         }
-        cur = pop(S, tid, stack);
-        return false;
     }
 };
 
@@ -364,6 +401,11 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
     const uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
     uint32_t stack[TCPT_LOCAL_STACK];
+#if TCPT_POP_CULL
+    float stack_t[ANY ? 1 : TCPT_LOCAL_STACK];
+#else
+    float stack_t[1];
+#endif
     Traversal T;
     T.cur = TCPT_ENTRY_NONE; T.blas_sp = -1;
     uint32_t ray = NONE, fin = NONE;
@@ -414,16 +456,16 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
 #if TCPT_BOTH_PHASES
             // no vote: the lanes holding triangles test one, then the walking lanes visit a node, every iteration
             bool finished = false;
-            if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, stack, n_tri);
-            if (walks) finished = T.template node_step<COUNT>(sc, S, tid, stack, n_box);
+            if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, stack, stack_t, n_tri);
+            if (walks) finished = T.template node_step<ANY, COUNT>(sc, S, tid, stack, stack_t, n_box);
 #else
             const uint32_t tri_mask = __ballot_sync(FULL, has_tri);
             const uint32_t node_mask = __ballot_sync(FULL, walks);
             bool finished = false;
             if (tri_mask != 0u && ((uint32_t)__popc(tri_mask) >= (uint32_t)TCPT_TRI_PHASE_LANES || node_mask == 0u)) {
-                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, stack, n_tri);
+                if (has_tri) finished = T.template tri_step<ANY, COUNT>(sc, S, tid, stack, stack_t, n_tri);
             } else {
-                if (walks) finished = T.template node_step<COUNT>(sc, S, tid, stack, n_box);
+                if (walks) finished = T.template node_step<ANY, COUNT>(sc, S, tid, stack, stack_t, n_box);
             }
 #endif
             if (finished) { fin = ray; ray = NONE; T.cur = TCPT_ENTRY_NONE; }

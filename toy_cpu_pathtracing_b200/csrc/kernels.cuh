@@ -22,8 +22,27 @@
 #define TCPT_TRACE_MIN_BLOCKS 8   // 64 registers + 13 KB of shared memory per block: 32 warps per SM (measured 6 / 7 / 8 blocks: 35.7 / 33.5 / 32.1 ms per step)
 #endif
 #define TCPT_BUCKET_STRIDE 10
+#ifndef TCPT_LAMBERT_DRAWS3
+#define TCPT_LAMBERT_DRAWS3 1
+#endif
+#ifndef TCPT_ORDER_SLOT
+#define TCPT_ORDER_SLOT 1    // an entry of the bucketed order is {queue position, path slot} (8 B) instead of the queue position alone
+#endif
+#ifndef TCPT_ORDER_AHEAD
+#define TCPT_ORDER_AHEAD 1   // the order entry of a thread's NEXT vertex is loaded before the current one is shaded
+#endif
 
 namespace tcpt {
+
+// TCPT_ORDER_SLOT: an order entry carries the path slot next to the queue position, so the head of the path state is asked for together
+// with the ray and the hit record instead of after the ray has arrived (one round trip less in front of every vertex).
+#if TCPT_ORDER_SLOT
+typedef uint2 OrderEntry;
+__device__ __forceinline__ OrderEntry make_order(uint32_t i, uint32_t slot) { return make_uint2(i, slot); }
+#else
+typedef uint32_t OrderEntry;
+__device__ __forceinline__ OrderEntry make_order(uint32_t i, uint32_t) { return i; }
+#endif
 
 struct PathList { const uint32_t* xy; const uint32_t* sample; };  // explicit (pixel, sample) lists for tcpt_path_samples
 
@@ -138,7 +157,8 @@ __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim, bool k
 __device__ __forceinline__ void commit_closest(const DScene& sc, const DState& st, const float4* __restrict__ q_d, float4* __restrict__ hit0, uint2* __restrict__ hit1, uint32_t* bcount, uint32_t i, const DHit& h) {
     hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
     hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
-    const bool killed = (__float_as_uint(q_d[i].w) & 0x80000000u) != 0u;  // ext_d.w = slot | killed << 31
+    const float dw = q_d[i].w;
+    const bool killed = (__float_as_uint(dw) & 0x80000000u) != 0u;  // ext_d.w = slot | killed << 31
     const uint32_t b = bucket_of(sc, h.prim, killed);
     const uint32_t peers = __match_any_sync(__activemask(), b);
     const uint32_t lane = threadIdx.x & 31u;
@@ -146,7 +166,7 @@ __device__ __forceinline__ void commit_closest(const DScene& sc, const DState& s
     uint32_t base = 0;
     if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
-    st.order[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+    ((OrderEntry*)st.order)[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = make_order(i, __float_as_uint(dw) & 0x7fffffffu);
 }
 // what a finished shadow ray does: add the pending NEE contribution if the light is visible (common.rs:134-170); hand a path that
 // ended at this vertex (failed BSDF sample) to the sensor
@@ -255,6 +275,15 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     // with one light), 4 (triangle of an area light), 5 (point on the light) and 7 (Russian roulette; 3 under pt, which draws nothing for lights)
     if (!BucketInfo<B>::miss && !BucketInfo<B>::terminal && MT != TCPT_MAT_EMISSIVE)
         smp.prefetch_draws(R, ((MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) ? 0u : 1u) | 2u | (R.integrator != TCPT_INTEGRATOR_PT ? 0xa0u : 0x08u));
+    // Lambert under nee / mis with the Sobol sampler: the direction, the point on the light and Russian roulette sit at dimension offsets 1, 5
+    // and 7 on the usual way through the vertex; all three are drawn here in one call (DSampler::sobol_draws3) and handed out below if the
+    // dimension counter is where it was expected to be (otherwise the ordinary call runs: same values either way)
+    constexpr bool PRE = TCPT_LAMBERT_DRAWS3 && MT == TCPT_MAT_LAMBERT && !BucketInfo<B>::miss && !BucketInfo<B>::terminal;
+    DSampler::Draws3 pre; bool have_pre = false; const uint32_t pre_d0 = smp.dim;
+    if (PRE && R.sampler == TCPT_SAMPLER_SOBOL && R.integrator != TCPT_INTEGRATOR_PT && (FIRST || stage < R.max_depth)) {
+        pre = DSampler::sobol_draws3(smp.morton, pre_d0 + 1u, pre_d0 + 5u, pre_d0 + 7u, smp.pix, DSampler::frame_of(R));
+        have_pre = true;
+    }
     S4 thr = s4(1.0f), con = s4(0.0f);
     if (!FIRST && stage != 0u) { thr = s4(st.thr[slot]); con = s4(st.con[slot]); }
     const int integrator = R.integrator;
@@ -365,7 +394,8 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     // `uc` only selects between lobes; LambertMaterial::sample and MetalMaterial::sample never read it (lambert_material.rs:42-97, metal_material.rs:124)
     float uc = 0.0f;
     if (MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) smp.skip_1d(); else uc = smp.get_1d(R);
-    const float2 uv = smp.get_2d(R);
+    float2 uv;
+    if (PRE && have_pre && smp.dim == pre_d0 + 1u) { uv = pre.a; smp.dim += 2; } else uv = smp.get_2d(R);
     const bool was_terminated = wl.terminated;
     NmFrame nmf;
     material_frame(sc, mat, hit.uv, nmf);
@@ -398,7 +428,8 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
             float s = 0.0f;
             if (LP.kind == 1) s = smp.get_1d(R); else smp.skip_1d();
             float2 luv = make_float2(0.0f, 0.0f);
-            if (LP.kind <= 2) luv = smp.get_2d(R); else { smp.skip_1d(); smp.skip_1d(); }
+            if (LP.kind <= 2) { if (PRE && have_pre && smp.dim == pre_d0 + 5u) { luv = pre.b; smp.dim += 2; } else luv = smp.get_2d(R); }
+            else { smp.skip_1d(); smp.skip_1d(); }
             float3 sh_dir; float sh_tmax; S4 pending; float sh_eps = 1e-4f;
             if (LP.kind == 3 || LP.kind == 4) {
                 // PointLight / SpotLight::calculate_intensity (point_light.rs:75-88, spot_light.rs:98-122) + evaluate_delta_point_light
@@ -518,7 +549,11 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     if (stage + 1 <= R.max_depth) {
         const S4 thr2 = thr * (ms.f * (1.0f / ms.pdf));
         const float p_rr = s4_max(thr2);
-        if (!(p_rr >= 1.0f)) killed = !(smp.get_1d(R) < p_rr);
+        if (!(p_rr >= 1.0f)) {
+            float u_rr;
+            if (PRE && have_pre && smp.dim == pre_d0 + 7u) { u_rr = pre.c; smp.dim += 1; } else u_rr = smp.get_1d(R);
+            killed = !(u_rr < p_rr);
+        }
     }
     out.push_ext = true;
     out.eo = make_float4(o2.x, o2.y, o2.z, TCPT_FLT_MAX);
@@ -534,16 +569,32 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
 }
 
 // What a vertex reads before it can start: its queue position (through the bucketed order), the ray it arrived on, the hit record and
-// the head of its path state.  Four DEPENDENT loads (order -> ray -> slot -> state), each a DRAM round trip at the benchmarked pass size.
+// the head of its path state: a chain of DEPENDENT loads (order -> ray -> slot -> state), each a DRAM round trip at the benchmarked pass
+// size.  The order entry of the NEXT vertex is asked for before this one is shaded (one or two registers across the vertex).
 struct VertexIn { float4 d, h0, misc; uint2 h1; };
 template <int B>
-__device__ __forceinline__ VertexIn load_vertex(const DState& st, int cur, uint32_t p, uint32_t n) {
+__device__ __forceinline__ OrderEntry load_order(const DState& st, uint32_t p, uint32_t n) {
+    OrderEntry o = make_order(0u, 0u);
+    if (p < n) o = ((const OrderEntry*)st.order)[(size_t)B * st.capacity + p];
+    return o;
+}
+template <int B>
+__device__ __forceinline__ VertexIn load_vertex(const DState& st, int cur, OrderEntry o, bool valid) {
     VertexIn v;
     v.d = make_float4(0.0f, 0.0f, 0.0f, 0.0f); v.h0 = v.d; v.misc = v.d; v.h1 = make_uint2(0u, 0u);
-    if (p < n) {
-        const uint32_t i = st.order[(size_t)B * st.capacity + p];
-        v.d = st.ext_d[cur][i]; v.h0 = st.hit0[i]; v.h1 = st.hit1[i];
+    if (valid) {
+#if TCPT_ORDER_SLOT
+        const uint32_t i = o.x;
+        v.misc = st.misc[o.y];
+        v.d = st.ext_d[cur][i];
+#else
+        const uint32_t i = o;
+        v.d = st.ext_d[cur][i];
+#endif
+        if (B < 7) { v.h0 = st.hit0[i]; v.h1 = st.hit1[i]; }   // an escaped ray and a path Russian roulette ended read nothing of the hit record: 24 B per vertex less
+#if !TCPT_ORDER_SLOT
         v.misc = st.misc[__float_as_uint(v.d.w) & 0x7fffffffu];
+#endif
     }
     return v;
 }
@@ -592,17 +643,24 @@ __global__ void __launch_bounds__(ShadeCfg<B>::threads, ShadeCfg<B>::min_blocks)
     // software pipeline: the loads of the NEXT vertex are issued before this one is shaded, so their round trips overlap the shading
     // instead of standing in front of it (ncu: 15 % of the Lambert kernel's stall samples sat on these four loads)
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    VertexIn v = load_vertex<B>(st, cur, p, p < n_round ? n : 0u);
+    VertexIn v = load_vertex<B>(st, cur, load_order<B>(st, p, n), p < n);
     for (; p < n_round; p += stride) {
+        const uint32_t pn = p + stride;
+        const bool more = pn < n && pn > p;
+#if TCPT_ORDER_AHEAD
+        const OrderEntry o_next = load_order<B>(st, pn, more ? n : 0u);
+#endif
 #if TCPT_SHADE_PIPELINE
-        const VertexIn next = load_vertex<B>(st, cur, p + stride, (p + stride < n_round && p + stride > p) ? n : 0u);
+        const VertexIn next = load_vertex<B>(st, cur, load_order<B>(st, pn, more ? n : 0u), more);
 #endif
         if (TCPT_SHADE_SYNC && B < 6) __syncthreads();
         shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n, v);
 #if TCPT_SHADE_PIPELINE
         v = next;
+#elif TCPT_ORDER_AHEAD
+        v = load_vertex<B>(st, cur, o_next, more);
 #else
-        v = load_vertex<B>(st, cur, p + stride, (p + stride < n_round && p + stride > p) ? n : 0u);
+        v = load_vertex<B>(st, cur, load_order<B>(st, pn, more ? n : 0u), more);
 #endif
     }
 }
@@ -633,7 +691,11 @@ __global__ void __launch_bounds__(128, TCPT_SHADE_MIN_BLOCKS) k_shade_all(const 
         const uint32_t p = c * 128u + threadIdx.x;
         ShadeOut out; out.push_ext = false; out.push_sh = false;
         if (p < n) {
+#if TCPT_ORDER_SLOT
+            const uint32_t i = ((const OrderEntry*)st.order)[(size_t)b * st.capacity + p].x;
+#else
             const uint32_t i = st.order[(size_t)b * st.capacity + p];
+#endif
             switch (b) {
                 case 0: shade_vertex_call<0>(sc, R, st, L, cur, stage, i, out); break;
                 case 1: shade_vertex_call<1>(sc, R, st, L, cur, stage, i, out); break;

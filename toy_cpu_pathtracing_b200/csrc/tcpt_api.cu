@@ -164,8 +164,8 @@ void srgb_xyz_to_rgb(float out[9]) {
 
 // device memory of one path slot: 14 float4 records (path state, both extension queues, hit record, shadow queue), the uint2 half of the
 // hit record and one order entry per shading bucket (ensure_state below allocates exactly this list)
-constexpr uint64_t kBytesPerSlot = 14 * sizeof(float4) + sizeof(uint2) + sizeof(uint32_t) * TCPT_N_BUCKETS;
-static_assert(kBytesPerSlot == 268, "update the figure quoted in include/tcpt.h and DESIGN.md");
+constexpr uint64_t kBytesPerSlot = 14 * sizeof(float4) + sizeof(uint2) + sizeof(tcpt::OrderEntry) * TCPT_N_BUCKETS;
+static_assert(kBytesPerSlot == (TCPT_ORDER_SLOT ? 304 : 268), "update the figure quoted in include/tcpt.h and DESIGN.md");
 
 int ensure_state(tcpt_ctx* ctx, uint32_t capacity) {
     if (ctx->st_capacity >= capacity) return TCPT_OK;
@@ -189,7 +189,7 @@ int ensure_state(tcpt_ctx* ctx, uint32_t capacity) {
     float4** f4s[] = {&s.thr, &s.con, &s.fprev, &s.misc, &s.ppos, &s.rgb, &s.ext_o[0], &s.ext_o[1], &s.ext_d[0], &s.ext_d[1], &s.hit0, &s.sh_o, &s.sh_d, &s.sh_c};
     for (float4** p : f4s) { int r = alloc(n * sizeof(float4), (void**)p); if (r) return r; }
     { int r = alloc(n * sizeof(uint2), (void**)&s.hit1); if (r) return r; }
-    { int r = alloc(n * sizeof(uint32_t) * TCPT_N_BUCKETS, (void**)&s.order); if (r) return r; }
+    { int r = alloc(n * sizeof(tcpt::OrderEntry) * TCPT_N_BUCKETS, (void**)&s.order); if (r) return r; }
     s.capacity = capacity;
     s.counters = ctx->d_counters;
     s.stats = ctx->d_stats;
@@ -470,7 +470,7 @@ int render_into(tcpt_ctx* ctx, const tcpt_render_params* p, float* dev_acc, cuda
     if (owned == 0 || s0 == s1) return TCPT_OK;
     // Path-slot budget of one pass.  Every pass pays a fixed latency (about 35 launches whose deep-bounce queues are nearly
     // empty: 4 to 8 ms on the 4K frame), so passes are made as large as memory comfortably allows: up to 128 Mi slots
-    // (268 B each: 36 GB of the 180 GB), never more than 45 % of the memory that is free.
+    // (304 B each: 40 GB of the 180 GB), never more than 45 % of the memory that is free.
     uint64_t budget = p->max_slots;
     if (budget == 0) {
         if (ctx->default_slots == 0) {  // asked once per context: cudaMemGetInfo was measured to stall a render by up to 80 ms
