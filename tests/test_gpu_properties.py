@@ -48,6 +48,23 @@ def test_sobol_prefix_table_is_bit_transparent(bundle_factory, spp):
         ctx.set_option("sobol_prefix_mb", 8192)
 
 
+def test_sobol_hash_table_is_bit_transparent(bundle_factory):
+    """The per-dimension Owen-scramble seeds hash(dimension, seed) come from a table built when the seed changes: table on, table off and a
+    change of seed in between must give the same films to the bit."""
+    b = bundle_factory(19, 200, 150)
+    ctx = b.scene.ctx
+    try:
+        on = [b.image("mis", 16, seed=s).render("sobol").accumulators.copy() for s in (0, 7, 0)]
+        ctx.set_option("sobol_hash", 0)
+        off = [b.image("mis", 16, seed=s).render("sobol").accumulators.copy() for s in (0, 7)]
+    finally:
+        ctx.set_option("sobol_hash", 1)
+    assert np.array_equal(on[0].view(np.uint32), off[0].view(np.uint32))
+    assert np.array_equal(on[1].view(np.uint32), off[1].view(np.uint32))
+    assert np.array_equal(on[0].view(np.uint32), on[2].view(np.uint32))
+    assert not np.array_equal(on[0].view(np.uint32), on[1].view(np.uint32))
+
+
 @pytest.mark.parametrize("scene_id,integrator", [(19, "mis"), (10, "nee"), (8, "pt")])
 def test_fused_launches_do_not_change_the_film(bundle_factory, scene_id, integrator):
     """Two launches per bounce (k_trace_fused, k_shade_all) against one launch per queue and per shading bucket: the same

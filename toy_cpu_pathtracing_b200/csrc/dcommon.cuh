@@ -138,7 +138,11 @@ struct DRender {
     // ZSobol pass table (see DSampler::sample_index): rows prefix_dims .. prefix_dims + pass_dims of the same allocation, rebuilt for
     // every pass by k_sobol_pass.  pass_info = pass_dims | n_varying_digits << 8 (0 = no pass table)
     uint32_t pass_info;
+    // hash(k, seed) of DSampler::hash for k < TCPT_SOBOL_HASH_N (the Owen-scramble seeds of sampler dimension k - 1 / k - 2): frame constants,
+    // built by k_sobol_hash when the seed changes (nullptr: computed per call)
+    const unsigned long long* sobol_hash;
 };
+#define TCPT_SOBOL_HASH_N 512
 
 // Wavefront buffers.  Path state is a structure of arrays of 16-byte records indexed by path slot; ray queues, hit records
 // and shadow queues are indexed by QUEUE POSITION so every stage reads and writes them fully coalesced.
@@ -173,6 +177,7 @@ struct SobolFrame {  // the frame-constant inputs of a Sobol call, packed for th
     uint32_t prefix_stride, tables;  // tables = prefix_dims | pass_dims << 16 | n_varying_digits << 24
     uint32_t cfg;             // log2_spp | n_base4_digits << 8
     uint32_t seed;
+    const unsigned long long* hash_table;   // DRender::sobol_hash
 };
 struct DSampler {
     uint32_t morton, dim, key, pix;
@@ -197,6 +202,11 @@ struct DSampler {
         h ^= k; h *= M;
         h ^= h >> 47; h *= M; h ^= h >> 47;
         return h;
+    }
+    // hash(k, f.seed) from the frame's table (three 64-bit multiplies of dependent latency less per sampler call)
+    __device__ __forceinline__ static uint64_t hash_of(uint32_t k, const SobolFrame& f) {
+        if (f.hash_table != nullptr && k < (uint32_t)TCPT_SOBOL_HASH_N) return __ldg(f.hash_table + k);
+        return hash(k, f.seed);
     }
     __device__ __forceinline__ static uint32_t owen(uint32_t v, uint32_t seed) {  // FastOwenScrambler (z_sobol_sampler.rs:3-29)
         v = __brev(v);
@@ -226,7 +236,7 @@ struct DSampler {
         SobolFrame f;
         f.prefix = R.sobol_prefix; f.prefix_stride = R.prefix_stride;
         f.tables = R.sobol_prefix ? (R.prefix_dims | (R.pass_info << 16)) : 0u;
-        f.cfg = R.log2_spp | (R.n_base4_digits << 8); f.seed = R.seed;
+        f.cfg = R.log2_spp | (R.n_base4_digits << 8); f.seed = R.seed; f.hash_table = R.sobol_hash;
         return f;
     }
 
@@ -363,12 +373,12 @@ struct DSampler {
     // increments it before hashing, :204-207,215-218)
     __device__ __noinline__ static float sobol_1d(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
         const uint64_t a = sample_index(morton, dim, pix, f);
-        const uint64_t h = hash(dim + 1u, f.seed);
+        const uint64_t h = hash_of(dim + 1u, f);
         return to_unit(owen(__brev((uint32_t)a), (uint32_t)h));  // Sobol matrix 0 = identity on reversed bits; rows >= 32 are zero
     }
     __device__ __noinline__ static float2 sobol_2d(uint32_t morton, uint32_t dim, uint32_t pix, const SobolFrame f) {
         const uint64_t a = sample_index(morton, dim, pix, f);
-        const uint64_t h = hash(dim + 2u, f.seed);
+        const uint64_t h = hash_of(dim + 2u, f);
         float2 r;
         r.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
         r.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
@@ -383,19 +393,19 @@ struct DSampler {
         Draws3 r;
         {
             const uint64_t a = sample_index_from(morton, da, f, la);
-            const uint64_t h = hash(da + 2u, f.seed);
+            const uint64_t h = hash_of(da + 2u, f);
             r.a.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
             r.a.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
         }
         {
             const uint64_t a = sample_index_from(morton, db, f, lb);
-            const uint64_t h = hash(db + 2u, f.seed);
+            const uint64_t h = hash_of(db + 2u, f);
             r.b.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
             r.b.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
         }
         {
             const uint64_t a = sample_index_from(morton, dc, f, lc);
-            const uint64_t h = hash(dc + 1u, f.seed);
+            const uint64_t h = hash_of(dc + 1u, f);
             r.c = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
         }
         return r;
@@ -606,6 +616,24 @@ __device__ __forceinline__ void warp_push2(uint32_t* ca, bool pa, uint32_t* cb, 
     const uint32_t ba = __shfl_sync(0xffffffffu, base, 0), bb = __shfl_sync(0xffffffffu, base, 1);
     const uint32_t below = (1u << lane) - 1u;
     *ia = ba + (uint32_t)__popc(ma & below); *ib = bb + (uint32_t)__popc(mb & below);
+}
+// the same in two halves: begin issues the two atomics and does not wait for them, end hands out the positions.  What the caller puts
+// between the two (the loads of its next vertex) overlaps the atomics' round trip.
+struct Push2 { uint32_t ma, mb, base; };
+__device__ __forceinline__ Push2 warp_push2_begin(uint32_t* ca, bool pa, uint32_t* cb, bool pb) {
+    Push2 t;
+    t.ma = __ballot_sync(0xffffffffu, pa); t.mb = __ballot_sync(0xffffffffu, pb);
+    const uint32_t lane = threadIdx.x & 31u;
+    t.base = 0;
+    if (lane == 0u) { if (t.ma) t.base = atomicAdd(ca, (uint32_t)__popc(t.ma)); }
+    else if (lane == 1u) { if (t.mb) t.base = atomicAdd(cb, (uint32_t)__popc(t.mb)); }
+    return t;
+}
+__device__ __forceinline__ void warp_push2_end(const Push2& t, uint32_t* ia, uint32_t* ib) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ba = __shfl_sync(0xffffffffu, t.base, 0), bb = __shfl_sync(0xffffffffu, t.base, 1);
+    const uint32_t below = (1u << lane) - 1u;
+    *ia = ba + (uint32_t)__popc(t.ma & below); *ib = bb + (uint32_t)__popc(t.mb & below);
 }
 // warp-aggregated queue append: every lane of the warp must call it (pred = false for lanes with nothing to push)
 __device__ __forceinline__ uint32_t warp_push(uint32_t* counter, bool pred) {

@@ -389,6 +389,20 @@ struct Traversal {
 #define TCPT_TRI_PHASE_LANES 8    // a warp runs a triangle iteration once this many lanes hold pending triangles (4 / 8 / 12: 31.4 / 30.4 / 30.9 ms; no vote at all, both phases every iteration: 31.2)
 #endif
 #define TCPT_LOCAL_STACK (TCPT_TRAVERSAL_STACK - TCPT_SMEM_STACK)
+#ifndef TCPT_SPLIT_COMMIT
+#define TCPT_SPLIT_COMMIT 1       // a commit is begun (its loads and its atomic issued) before the refill asks for the next rays and ended after: the round trips overlap (measured neutral: 29.68 vs 29.66 ms; the kernel is bound by instruction issue, not by these waits)
+#endif
+
+// What a finished ray leaves behind, in two halves around the refill's ray loads: begin() issues the loads / the atomic whose results
+// end() needs (ncu: the shuffle waiting for the bucket counter's atomic and the first use of the freshly loaded ray were the two top stall
+// sites of the camera-ray launch, one after the other).
+struct CommitToken { uint32_t a, b, c, d, e; };
+template <class F> struct CommitNow {   // a commit without a second half
+    F f;
+    __device__ __forceinline__ CommitToken begin(uint32_t i, const DHit& h) const { f(i, h); return CommitToken{0u, 0u, 0u, 0u, 0u}; }
+    __device__ __forceinline__ void end(const CommitToken&) const {}
+};
+template <class F> __device__ __forceinline__ CommitNow<F> commit_now(F f) { return CommitNow<F>{f}; }
 
 // Traces the rays of a queue with persistent warps.  `work` is a global counter zeroed before the launch.  A finished ray's
 // result stays in the lane's shared-memory rows until the warp's next refill point, where `commit(i, hit)` is called for all finished
@@ -424,7 +438,18 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
         const bool fetch = n_idle > left && !drained;
         uint32_t fetched = 0;
         if (fetch && lane == 0) fetched = atomicAdd(work, chunk);  // in flight while the finished rays are committed
-        if (fin != NONE) { DHit h; T.result(S, tid, h); commit(fin, h); fin = NONE; }
+        CommitToken tok{0u, 0u, 0u, 0u, 0u};
+        const bool committing = fin != NONE;
+        if (committing) {
+            DHit h; T.result(S, tid, h); tok = commit.begin(fin, h); fin = NONE;
+#if !TCPT_SPLIT_COMMIT
+            commit.end(tok);
+#endif
+        }
+#if TCPT_SPLIT_COMMIT
+        float4 new_o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), new_d = new_o;
+        uint32_t mine = NONE;
+#endif
         if (n_idle != 0u) {
             uint32_t base_b = 0;
             if (fetch) {
@@ -434,6 +459,11 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
             if (ray == NONE) {
                 // the first `left` idle lanes take what remains of the old chunk, the others start the new one
                 const uint32_t rk = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+#if TCPT_SPLIT_COMMIT
+                if (rk < left) mine = pool + rk;
+                else if (fetch) mine = base_b + (rk - left);
+                if (mine < n) { new_o = q_o[mine]; new_d = q_d[mine]; }
+#else
                 uint32_t mine = NONE;
                 if (rk < left) mine = pool + rk;
                 else if (fetch) mine = base_b + (rk - left);
@@ -442,10 +472,18 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
                     T.init(S, tid, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w);
                     ray = mine;
                 }
+#endif
             }
             if (fetch) { pool = base_b + (n_idle - left); pool_end = base_b + chunk; if (pool_end > n) pool_end = n; if (pool > pool_end) pool = pool_end; }
             else { pool += n_idle; if (pool > pool_end) pool = pool_end; }
         }
+#if TCPT_SPLIT_COMMIT
+        if (committing) commit.end(tok);
+        if (mine < n) {   // (mine == NONE for a lane that did not refill)
+            T.init(S, tid, f3(new_o.x, new_o.y, new_o.z), f3(new_d.x, new_d.y, new_d.z), new_o.w);
+            ray = mine;
+        }
+#endif
         const bool exhausted = drained && pool >= pool_end;
         if (__ballot_sync(FULL, ray != NONE) == 0u) break;  // nothing in flight and nothing left to fetch
         const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;

@@ -22,6 +22,9 @@
 #define TCPT_TRACE_MIN_BLOCKS 8   // 64 registers + 13 KB of shared memory per block: 32 warps per SM (measured 6 / 7 / 8 blocks: 35.7 / 33.5 / 32.1 ms per step)
 #endif
 #define TCPT_BUCKET_STRIDE 10
+#ifndef TCPT_SPLIT_PUSH
+#define TCPT_SPLIT_PUSH 0    // 1: the queue-append atomics of a vertex are issued, then the loads of the thread's next vertex, then the rays are stored.  Measured slower (31.73 vs 31.47 ms of shading per step): the 20 words of the pending rays stay live across the next vertex's loads
+#endif
 #ifndef TCPT_LAMBERT_DRAWS3
 #define TCPT_LAMBERT_DRAWS3 1
 #endif
@@ -70,6 +73,12 @@ __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ tab
         const uint32_t py = k / width, px = k - py * width;
         table[i] = DSampler::pixel_prefix(DSampler::morton_of(px, py, 0u, log2_spp), dim, log2_spp, nb4);
     }
+}
+
+// builds DRender::sobol_hash
+__global__ void k_sobol_hash(unsigned long long* __restrict__ table, uint32_t seed) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < (uint32_t)TCPT_SOBOL_HASH_N) table[k] = DSampler::hash(k, seed);
 }
 
 // builds the pass rows of DRender::sobol_prefix for the pixels and the sample block of ONE pass (see DSampler::sample_index):
@@ -154,39 +163,54 @@ __device__ __forceinline__ uint32_t bucket_of(const DScene& sc, int prim, bool k
 // work counters of the persistent trace kernels: counters[24] closest, counters[25] shadow.  Each is zeroed by an earlier kernel
 // of the same bounce (stream order): k_generate / k_shade zero [24] for the next k_trace_closest, k_trace_closest zeroes [25].
 // what a finished extension ray leaves behind: its hit record and its place in a shading bucket
-__device__ __forceinline__ void commit_closest(const DScene& sc, const DState& st, const float4* __restrict__ q_d, float4* __restrict__ hit0, uint2* __restrict__ hit1, uint32_t* bcount, uint32_t i, const DHit& h) {
-    hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
-    hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
-    const float dw = q_d[i].w;
-    const bool killed = (__float_as_uint(dw) & 0x80000000u) != 0u;  // ext_d.w = slot | killed << 31
-    const uint32_t b = bucket_of(sc, h.prim, killed);
-    const uint32_t peers = __match_any_sync(__activemask(), b);
-    const uint32_t lane = threadIdx.x & 31u;
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    ((OrderEntry*)st.order)[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = make_order(i, __float_as_uint(dw) & 0x7fffffffu);
-}
+struct CommitClosest {
+    const DScene& sc; const DState& st; const float4* __restrict__ q_d; float4* __restrict__ hit0; uint2* __restrict__ hit1; uint32_t* bcount;
+    // the hit record, the bucket, and the warp-aggregated atomic that reserves the bucket's next positions (its result is not waited for)
+    __device__ __forceinline__ CommitToken begin(uint32_t i, const DHit& h) const {
+        hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
+        hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
+        const float dw = q_d[i].w;
+        const bool killed = (__float_as_uint(dw) & 0x80000000u) != 0u;  // ext_d.w = slot | killed << 31
+        const uint32_t b = bucket_of(sc, h.prim, killed);
+        const uint32_t peers = __match_any_sync(__activemask(), b);
+        const uint32_t lane = threadIdx.x & 31u;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&bcount[b], (uint32_t)__popc(peers));
+        return CommitToken{base, peers, b, i, __float_as_uint(dw) & 0x7fffffffu};
+    }
+    __device__ __forceinline__ void end(const CommitToken& t) const {
+        const uint32_t lane = threadIdx.x & 31u, peers = t.b, b = t.c, i = t.d;
+        const uint32_t base = __shfl_sync(peers, t.a, __ffs(peers) - 1);
+        ((OrderEntry*)st.order)[(size_t)b * st.capacity + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = make_order(i, t.e);
+    }
+};
 // what a finished shadow ray does: add the pending NEE contribution if the light is visible (common.rs:134-170); hand a path that
 // ended at this vertex (failed BSDF sample) to the sensor
-__device__ __forceinline__ void commit_shadow(const DScene& sc, const DRender& R, const DState& st, uint32_t i, const DHit& h) {
-    const uint32_t tag = __float_as_uint(st.sh_d[i].w);
-    const uint32_t slot = tag & 0x7fffffffu;
-    const bool visible = h.prim < 0, last = (tag & 0x80000000u) != 0;
-    if (!visible && !last) return;
-    S4 con = s4(st.con[slot]);
-    if (visible) {
-        con = con + s4(st.sh_c[i]);
-        st.con[slot] = to_f4(con);
+struct CommitShadow {
+    const DScene& sc; const DRender& R; const DState& st;
+    __device__ __forceinline__ CommitToken begin(uint32_t i, const DHit& h) const {
+        const uint32_t tag = __float_as_uint(st.sh_d[i].w);
+        return CommitToken{tag, i, h.prim < 0 ? 1u : 0u, 0u, 0u};
     }
-    if (last) {
-        const float4 misc = st.misc[slot];
-        const DWavelengths wl = wavelengths_uniform(misc.y, (__float_as_uint(misc.w) & FLAG_LAMBDA_TERMINATED) != 0);
-        const float3 rgb = sensor_rgb(sc, wl.lambda[0], wl.terminated, con, R.exposure);
-        st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+    __device__ __forceinline__ void end(const CommitToken& t) const {
+        const uint32_t tag = t.a, i = t.b;
+        const uint32_t slot = tag & 0x7fffffffu;
+        const bool visible = t.c != 0u, last = (tag & 0x80000000u) != 0;
+        if (!visible && !last) return;
+        S4 con = s4(st.con[slot]);
+        if (visible) {
+            con = con + s4(st.sh_c[i]);
+            st.con[slot] = to_f4(con);
+        }
+        if (last) {
+            const float4 misc = st.misc[slot];
+            const DWavelengths wl = wavelengths_uniform(misc.y, (__float_as_uint(misc.w) & FLAG_LAMBDA_TERMINATED) != 0);
+            const float3 rgb = sensor_rgb(sc, wl.lambda[0], wl.terminated, con, R.exposure);
+            st.rgb[slot] = make_float4(rgb.x, rgb.y, rgb.z, 0.0f);
+        }
     }
-}
+};
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128, 6) k_trace_closest(const __grid_constant__ DScene sc, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
@@ -201,7 +225,7 @@ __global__ void __launch_bounds__(128, 6) k_trace_closest(const __grid_constant_
     }
     uint32_t nb = 0, nt = 0;
     __shared__ TraceShared ts;
-    trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, q_d, hit0, hit1, bcount, i, h); });
+    trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, &st.counters[24], &nb, &nt, CommitClosest{sc, st, q_d, hit0, hit1, bcount});
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -212,7 +236,7 @@ __global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&st.stats[1], (unsigned long long)n);
     uint32_t nb = 0, nt = 0;
     __shared__ TraceShared ts;
-    trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
+    trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n, &st.counters[25], &nb, &nt, CommitShadow{sc, R, st});
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -236,9 +260,9 @@ __global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(cons
     __shared__ TraceShared ts;
     // (shadow first: it is the shorter queue.  Letting half of the blocks start on the extension queue so that short queues are
     // walked side by side was measured slower: 16.6 vs 15.3 ms per 33 M paths.)
-    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_shadow(sc, R, st, i, h); });
+    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, CommitShadow{sc, R, st});
     float4* __restrict__ hit0 = st.hit0; uint2* __restrict__ hit1 = st.hit1;
-    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, [&](uint32_t i, const DHit& h) { commit_closest(sc, st, st.ext_d[cur], hit0, hit1, bcount, i, h); });
+    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, CommitClosest{sc, st, st.ext_d[cur], hit0, hit1, bcount});
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
@@ -598,14 +622,22 @@ __device__ __forceinline__ VertexIn load_vertex(const DState& st, int cur, Order
     }
     return v;
 }
-// Shades position p of bucket B's range of the bucketed order (p >= n: the lane only takes part in the warp-collective pushes).
+// Shades position p of bucket B's range of the bucketed order (p >= n: the lane only takes part in the warp-collective pushes).  In two
+// halves: shade_position_begin shades the vertex and ISSUES the two queue-append atomics, shade_position_end waits for them and stores the
+// rays; the kernel asks for its next vertex in between, so that the atomics' round trip and the next vertex's loads overlap.
+struct ShadePending { ShadeOut out; Push2 push; };
 template <int B, bool FIRST = false>
-__device__ __forceinline__ void shade_position(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, int sh, uint32_t stage, uint32_t p, uint32_t n, const VertexIn& v) {
-    ShadeOut out; out.push_ext = false; out.push_sh = false;
-    if (p < n) shade_vertex<B, FIRST>(sc, R, st, L, stage, f3(v.d.x, v.d.y, v.d.z), __float_as_uint(v.d.w) & 0x7fffffffu, v.h0, v.h1, v.misc, out);
-    if (B < 6) {  // emissive hits and misses end the path: nothing to push
+__device__ __forceinline__ void shade_position_begin(const DScene& sc, const DRender& R, const DState& st, const PathList& L, int cur, int sh, uint32_t stage, uint32_t p, uint32_t n, const VertexIn& v, ShadePending& pend) {
+    pend.out.push_ext = false; pend.out.push_sh = false;
+    if (p < n) shade_vertex<B, FIRST>(sc, R, st, L, stage, f3(v.d.x, v.d.y, v.d.z), __float_as_uint(v.d.w) & 0x7fffffffu, v.h0, v.h1, v.misc, pend.out);
+    if (B < 6) pend.push = warp_push2_begin(&st.counters[cur ^ 1], pend.out.push_ext, &st.counters[sh], pend.out.push_sh);   // emissive hits and misses end the path: nothing to push
+}
+template <int B>
+__device__ __forceinline__ void shade_position_end(const DState& st, int cur, const ShadePending& pend) {
+    if (B < 6) {
         uint32_t pe, ps;
-        warp_push2(&st.counters[cur ^ 1], out.push_ext, &st.counters[sh], out.push_sh, &pe, &ps);
+        warp_push2_end(pend.push, &pe, &ps);
+        const ShadeOut& out = pend.out;
         if (out.push_ext) { st.ext_o[cur ^ 1][pe] = out.eo; st.ext_d[cur ^ 1][pe] = out.ed; }
         if (out.push_sh) { st.sh_o[ps] = out.so; st.sh_d[ps] = out.sd; st.sh_c[ps] = out.sc; }
     }
@@ -654,13 +686,20 @@ __global__ void __launch_bounds__(ShadeCfg<B>::threads, ShadeCfg<B>::min_blocks)
         const VertexIn next = load_vertex<B>(st, cur, load_order<B>(st, pn, more ? n : 0u), more);
 #endif
         if (TCPT_SHADE_SYNC && B < 6) __syncthreads();
-        shade_position<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n, v);
+        ShadePending pend;
+        shade_position_begin<B, FIRST>(sc, R, st, L, cur, sh, stage, p, n, v, pend);
+#if !TCPT_SPLIT_PUSH
+        shade_position_end<B>(st, cur, pend);
+#endif
 #if TCPT_SHADE_PIPELINE
         v = next;
 #elif TCPT_ORDER_AHEAD
         v = load_vertex<B>(st, cur, o_next, more);
 #else
         v = load_vertex<B>(st, cur, load_order<B>(st, pn, more ? n : 0u), more);
+#endif
+#if TCPT_SPLIT_PUSH
+        shade_position_end<B>(st, cur, pend);
 #endif
     }
 }
@@ -794,8 +833,8 @@ __global__ void __launch_bounds__(128) k_trace_rays(const __grid_constant__ DSce
         hit0[i] = make_float4(h.t, h.b0, h.b1, h.b2);
         hit1[i] = make_uint2((uint32_t)h.prim, h.tri);
     };
-    if (any_hit) trace_queue<true, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, store);
-    else trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, store);
+    if (any_hit) trace_queue<true, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, commit_now(store));
+    else trace_queue<false, COUNT>(sc, ts, q_o, q_d, n, work, &nb, &nt, commit_now(store));
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)nb); atomicAdd(&stats[3], (unsigned long long)nt); }
 }
 

@@ -33,7 +33,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool traversal_only = false;   // built by tcpt_scene_build_soup: BVH and triangles only, nothing to shade with
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -99,6 +99,7 @@ struct tcpt_ctx {
     float* film_acc = nullptr; float* film_srgb = nullptr; size_t film_cap = 0;
     HostPin pins[2];
     // ZSobol pixel-prefix table (DSampler::sample_index), cached per (width, height, log2_spp); grows when more dimensions are asked for
+    unsigned long long* d_sobol_hash = nullptr; uint32_t sobol_hash_seed = 0; bool sobol_hash_valid = false;
     uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0, pass_rows = 0; size_t prefix_cap = 0;
     double prefix_build_ms = 0.0;
     uint64_t default_slots = 0;  // path-slot budget of a pass when the caller gives none (see render_into)
@@ -245,7 +246,19 @@ int make_render(tcpt_ctx* ctx, const tcpt_render_params* p, DRender& R, DCamera&
 // kept until the resolution or spp changes.  Dimensions covered: what a max_depth path can draw (3 + 8 per bounce), capped by
 // option "sobol_prefix_mb"; deeper dimensions are computed in full by the sampler.
 int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
-    R.sobol_prefix = nullptr; R.prefix_dims = 0; R.prefix_stride = 0; R.pass_info = 0;
+    R.sobol_prefix = nullptr; R.prefix_dims = 0; R.prefix_stride = 0; R.pass_info = 0; R.sobol_hash = nullptr;
+    if (R.sampler == TCPT_SAMPLER_SOBOL && ctx->opt.sobol_hash) {
+        // the 64-bit seeds of the per-dimension Owen scrambles only depend on (dimension, seed): one 4 KB table per context, rebuilt in
+        // stream order when the seed changes (a failed allocation just leaves the per-call hash in place)
+        if (!ctx->d_sobol_hash && cudaMalloc((void**)&ctx->d_sobol_hash, TCPT_SOBOL_HASH_N * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); ctx->d_sobol_hash = nullptr; }
+        if (ctx->d_sobol_hash) {
+            if (!ctx->sobol_hash_valid || ctx->sobol_hash_seed != R.seed) {
+                k_sobol_hash<<<(TCPT_SOBOL_HASH_N + 255) / 256, 256, 0, stream>>>(ctx->d_sobol_hash, R.seed);
+                ctx->sobol_hash_seed = R.seed; ctx->sobol_hash_valid = true;
+            }
+            R.sobol_hash = ctx->d_sobol_hash;
+        }
+    }
     if (R.sampler != TCPT_SAMPLER_SOBOL || !ctx->opt.sobol_prefix) return TCPT_OK;
     // Both tables assume that the bits of the Morton index at and above log2_spp belong to the pixel alone.  The reference takes any
     // spp (main.rs only warns) with log2_spp = floor(log2(spp)) and ORs the sample index in (z_sobol_sampler.rs:200), so for a spp that
@@ -578,6 +591,7 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->d_sobol_bytes) cudaFree(ctx->d_sobol_bytes);
     if (ctx->d_presets) cudaFree(ctx->d_presets);
     if (ctx->d_prefix) cudaFree(ctx->d_prefix);
+    if (ctx->d_sobol_hash) cudaFree(ctx->d_sobol_hash);
     if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -597,6 +611,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "stage_timing") ctx->opt.stage_timing = value;
     else if (n == "debug_path_log") ctx->opt.debug_path_log = value;
     else if (n == "sobol_prefix") ctx->opt.sobol_prefix = value;
+    else if (n == "sobol_hash") ctx->opt.sobol_hash = value;
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
