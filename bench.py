@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--clock-period", type=float, default=0.05, help="seconds between NVML clock samples during the timed region")
     ap.add_argument("--opt", action="append", default=[], help="developer knob: libtcpt option as name=value (tcpt_set_option), repeatable")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--max-depth", type=int, default=16, help="developer knob (what the deep bounces cost); the benchmarked configuration is 16, the reference's default")
     ap.add_argument("--soup-rays", type=int, default=4096, help="soup workloads: the primary-ray grid is N x N (4096 -> 16.8 M rays)")
     ap.add_argument("--soup-builder", default="device", choices=["device", "host"], help="soup workloads: LBVH built on the device (csrc/lbvh.cuh) or the host binned-SAH builder")
     return ap.parse_args()
@@ -220,7 +221,7 @@ class CpuArm:
 
 def workload_config(args, wl, world, cpu_info=None):
     W, H = wl["width"], wl["height"]
-    cfg = {"workload": f"scene{wl['scene']} {W}x{H} {wl['integrator']}+{wl['sampler']} max_depth 16, {wl['frame_spp']}-spp frame, "
+    cfg = {"workload": f"scene{wl['scene']} {W}x{H} {wl['integrator']}+{wl['sampler']} max_depth {args.max_depth}, {wl['frame_spp']}-spp frame, "
                        f"{args.spp_per_step} sample indices of every pixel per GPU per step" + (" (BASELINE.json configs[3])" if wl["scene"] == 19 else "") + (" no-coat" if wl.get("kw") else ""),
            "paths_per_gpu_per_step": W * H * args.spp_per_step, "sharding": "spp-pass", "collective": "one ncclReduce of the film accumulators per step, issued inside libtcpt",
            "cache": (f"working set (path state + ray queues, {W * H * args.spp_per_step * 304 / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no explicit flush"
@@ -289,7 +290,7 @@ def main_gpu(args, wl):
     init_comm(ctx, rank, world)          # tcpt_comm_init: the film reduce is libtcpt's own ncclReduce from here on
     W, H, S = wl["width"], wl["height"], args.spp_per_step
     SPP, TILE = capi.SHARD_MODES["spp"], capi.SHARD_MODES["tile"]
-    renderer = tp.RENDERERS[wl["integrator"]](tp.RendererArgs((W, H), wl["frame_spp"], scene, cam, seed=0))
+    renderer = tp.RENDERERS[wl["integrator"]](tp.RendererArgs((W, H), wl["frame_spp"], scene, cam, seed=0), max_depth=args.max_depth)
     image = tp.RendererImage(W, H, renderer)
     acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
     frame = torch.zeros_like(acc) if rank == 0 else None
