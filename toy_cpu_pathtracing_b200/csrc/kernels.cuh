@@ -650,6 +650,12 @@ __device__ __forceinline__ void shade_position_end(const DState& st, int cur, co
 #ifndef TCPT_SHADE_THREADS_LAMBERT
 #define TCPT_SHADE_THREADS_LAMBERT TCPT_SHADE_THREADS
 #endif
+#ifndef TCPT_SHADE_THREADS_MISS
+#define TCPT_SHADE_THREADS_MISS TCPT_SHADE_THREADS   // block size of the buckets that end the path (emissive, miss, terminal)
+#endif
+#ifndef TCPT_SHADE_MIN_BLOCKS_MISS
+#define TCPT_SHADE_MIN_BLOCKS_MISS 8                 // their resident 128-thread units per SM (8: 64 registers).  256-thread blocks x 3 (85 registers, no spills) / x 4, 128-thread blocks x 5: 31.5 / 31.4 / 32.4 ms of shading per step against 31.4 (profiles/r02l_ab_miss_bucket_configs.log)
+#endif
 #ifndef TCPT_SHADE_SYNC
 #define TCPT_SHADE_SYNC 1
 #endif
@@ -659,8 +665,8 @@ __device__ __forceinline__ void shade_position_end(const DState& st, int cur, co
 // block shape of k_shade<B>: the material buckets run ONE big block per SM whose warps start every vertex together (see the kernel);
 // the register budget follows from the block size (512 threads: 128 registers, 640: 96, 768: 80)
 template <int B> struct ShadeCfg {
-    static constexpr int threads = B == 5 ? TCPT_SHADE_THREADS_LAMBERT : TCPT_SHADE_THREADS;
-    static constexpr int per_sm_128 = B >= 6 ? 8 : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS;   // resident blocks if blocks were 128 threads
+    static constexpr int threads = B >= 6 ? TCPT_SHADE_THREADS_MISS : B == 5 ? TCPT_SHADE_THREADS_LAMBERT : TCPT_SHADE_THREADS;
+    static constexpr int per_sm_128 = B >= 6 ? TCPT_SHADE_MIN_BLOCKS_MISS : B == 5 ? TCPT_SHADE_MIN_BLOCKS_LAMBERT : TCPT_SHADE_MIN_BLOCKS;   // resident blocks if blocks were 128 threads
     static constexpr int min_blocks = per_sm_128 * 128 / threads > 0 ? per_sm_128 * 128 / threads : 1;
 };
 template <int B, bool FIRST = false>
