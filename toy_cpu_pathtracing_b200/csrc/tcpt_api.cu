@@ -99,6 +99,7 @@ struct tcpt_ctx {
     float* film_acc = nullptr; float* film_srgb = nullptr; size_t film_cap = 0;
     HostPin pins[2];
     // ZSobol pixel-prefix table (DSampler::sample_index), cached per (width, height, log2_spp); grows when more dimensions are asked for
+    void* trace_scratch = nullptr; size_t trace_scratch_cap = 0;   // device staging of tcpt_trace (rays in, hit records out), kept between calls
     unsigned long long* d_sobol_hash = nullptr; uint32_t sobol_hash_seed = 0; bool sobol_hash_valid = false;
     uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0, pass_rows = 0; size_t prefix_cap = 0;
     double prefix_build_ms = 0.0;
@@ -592,6 +593,7 @@ void tcpt_destroy(tcpt_ctx* ctx) {
     if (ctx->d_presets) cudaFree(ctx->d_presets);
     if (ctx->d_prefix) cudaFree(ctx->d_prefix);
     if (ctx->d_sobol_hash) cudaFree(ctx->d_sobol_hash);
+    if (ctx->trace_scratch) cudaFree(ctx->trace_scratch);
     if (ctx->d_rgb2spec) cudaFree(ctx->d_rgb2spec);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -1300,13 +1302,19 @@ int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* ou
     CU(cudaSetDevice(ctx->device));
     // the caller's AoS rays go up as they are and come back as AoS hit records: the SoA queues the kernels read are (un)packed on the
     // device (a host loop over 16 M rays cost more than the traversal)
-    float* d_in = nullptr; void* d_rays = nullptr; void* d_hits = nullptr; int32_t* d_out = nullptr;
-    auto release = [&]() { cudaFree(d_in); cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_out); };
-    cudaError_t e = cudaMalloc((void**)&d_in, (size_t)n * 7 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&d_rays, (size_t)n * 32);
-    if (e == cudaSuccess) e = cudaMalloc(&d_hits, (size_t)n * 24);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)n * 6 * sizeof(int32_t));
-    if (e != cudaSuccess) { release(); return fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e)); }
+    // One staging allocation per context, grown when a call needs more and kept between calls: a cudaMalloc / cudaFree pair per call cost
+    // more than the traversal (and a cudaFree lets the driver trim the kernels' local-memory pool, which the next launch rebuilds).
+    const size_t b_in = ((size_t)n * 7 * sizeof(float) + 255) & ~(size_t)255, b_rays = (size_t)n * 32, b_hits = ((size_t)n * 24 + 255) & ~(size_t)255, b_out = (size_t)n * 6 * sizeof(int32_t);
+    const size_t need = b_in + b_rays + b_hits + b_out;
+    if (need > ctx->trace_scratch_cap) {
+        if (ctx->trace_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->trace_scratch); ctx->trace_scratch = nullptr; ctx->trace_scratch_cap = 0; }
+        const cudaError_t e0 = cudaMalloc(&ctx->trace_scratch, need);
+        if (e0 != cudaSuccess) { cudaGetLastError(); ctx->trace_scratch = nullptr; return fail(ctx, TCPT_ERR_NOMEM, cudaGetErrorString(e0)); }
+        ctx->trace_scratch_cap = need;
+    }
+    char* base = (char*)ctx->trace_scratch;
+    float* d_in = (float*)base; void* d_rays = base + b_in; void* d_hits = base + b_in + b_rays; int32_t* d_out = (int32_t*)(base + b_in + b_rays + b_hits);
+    cudaError_t e = cudaSuccess;
     reset_stats(ctx);
     cudaMemcpyAsync(d_in, rays, (size_t)n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
     k_pack_rays<<<grid_for(ctx, (uint64_t)n, 256), 256, 0, ctx->stream>>>(d_in, n, (float4*)d_rays);
@@ -1317,7 +1325,6 @@ int tcpt_trace(tcpt_ctx* ctx, const float* rays, int n, int any_hit, int32_t* ou
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, TCPT_ERR_CUDA, cudaGetErrorString(e));
     }
-    release();
     if (rc) return rc;
     return fetch_stats(ctx);
 }
