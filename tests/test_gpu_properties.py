@@ -118,6 +118,34 @@ def test_environment_nee_table_is_bit_transparent(bundle_factory, scene_id, inte
     assert a.any() and np.array_equal(a.view(np.uint32), c.view(np.uint32))
 
 
+@pytest.mark.parametrize("integrator", ["mis", "pt"])
+def test_illuminant_half_shortcut_is_bit_transparent(bundle_factory, integrator):
+    """The colour of an RgbIlluminantSpectrum is divided by twice its largest component (rgb_illuminant_spectrum.rs:27-40), so that component
+    is exactly 0.5: its sRGB decoding and the z-node interval of every environment lookup are constants, evaluated once by the device code
+    the lookups run (k_illum_half).  With the shortcut, without it, and without the per-texel table (the shortcut then also serves light
+    sampling): the same film to the bit."""
+    b = bundle_factory(19, 200, 150)
+    ctx = b.scene.ctx
+    a = b.image(integrator, 16).render("sobol").accumulators.copy()
+    try:
+        ctx.set_option("illum_half", 0)
+        b.scene.build(b.camera)                      # the constants ride in the uploaded scene
+        c = b.image(integrator, 16).render("sobol").accumulators.copy()
+        ctx.set_option("env_nee_table", 0)
+        b.scene.build(b.camera)
+        d = b.image(integrator, 16).render("sobol").accumulators.copy()
+        ctx.set_option("illum_half", 1)
+        b.scene.build(b.camera)
+        e = b.image(integrator, 16).render("sobol").accumulators.copy()
+    finally:
+        ctx.set_option("illum_half", 1)
+        ctx.set_option("env_nee_table", 1)
+        b.scene.build(b.camera)
+    assert a.any()
+    for other in (c, d, e):
+        assert np.array_equal(a.view(np.uint32), other.view(np.uint32))
+
+
 @pytest.mark.parametrize("scene_id,spp", [(3, 64), (19, 256), (10, 16)])
 def test_sobol_pass_table_is_bit_transparent(bundle_factory, scene_id, spp):
     """The per-pass table caches the permuted sample digits that all samples of a pixel share inside one pass (and the permutation row

@@ -116,6 +116,10 @@ struct DScene {
     const DEnv* envs; uint32_t n_envs;
     const float4* cmf;              // 470 x {x_bar, y_bar, z_bar, d65}  (spectrum/src/presets.rs tables, densely resampled)
     const float* z_nodes; const float* rgb2spec;
+    // srgb_to_linear(0.5f) as THIS build's device code evaluates it, and its z-node interval (k_illum_half, once per table upload): the largest
+    // component of an RgbIlluminantSpectrum's colour is exactly 0.5 after the division by 2 * max (rgb_illuminant_spectrum.rs:27-40), so one of
+    // the three decodings and the node search of every environment lookup are constants.  half_zi < 0: not available, compute per call.
+    float half_lin; int32_t half_zi;
     const float* presets;           // dense metal / glass tables (spectrum/src/presets.rs), n x 470
     float xyz_to_rgb[9];            // column major (color/src/gamut.rs:43-69)
 };
@@ -472,12 +476,26 @@ __device__ __forceinline__ float4 cmf_at(const DScene& sc, float lambda) {  // D
     return i < 470u ? __ldg(&sc.cmf[i]) : make_float4(0, 0, 0, 0);
 }
 
+#ifndef TCPT_ILLUM_HALF
+#define TCPT_ILLUM_HALF 1
+#endif
 // RgbToSpectrumTable::get (rgb_sigmoid_polynomial.rs:87-155), sRGB-gamma typed colour
 // (returns by value: an out-array lived in local memory and cost a store -> load -> store -> load chain through L1 before the first
 // wavelength could be evaluated)
-__device__ __noinline__ float3 rgb_to_coeffs(const DScene& sc, float3 rgb_in) {
+// HALF: the caller guarantees nothing, but expects the largest component to be exactly 0.5 (illuminant_from_rgb): that component is not
+// decoded again and the node search is skipped when the largest linear value is the precomputed one.  Same values either way: the shortcut
+// replaces a pure function of a constant by its result (computed by the same device code) and a search by its (unique) answer.
+template <bool HALF>
+__device__ __noinline__ float3 rgb_to_coeffs_t(const DScene& sc, float3 rgb_in) {
     float cs[3];
-    float rgb[3] = {srgb_to_linear(rgb_in.x), srgb_to_linear(rgb_in.y), srgb_to_linear(rgb_in.z)};
+    float rgb[3];
+    const int h = !HALF || sc.half_zi < 0 ? -1 : (rgb_in.x == 0.5f ? 0 : (rgb_in.y == 0.5f ? 1 : (rgb_in.z == 0.5f ? 2 : -1)));
+    if (HALF && h >= 0) {
+        const float la = srgb_to_linear(h == 0 ? rgb_in.y : rgb_in.x), lb = srgb_to_linear(h == 2 ? rgb_in.y : rgb_in.z);   // the two other components, in order
+        rgb[0] = h == 0 ? sc.half_lin : la; rgb[1] = h == 1 ? sc.half_lin : (h == 0 ? la : lb); rgb[2] = h == 2 ? sc.half_lin : lb;
+    } else {
+        rgb[0] = srgb_to_linear(rgb_in.x); rgb[1] = srgb_to_linear(rgb_in.y); rgb[2] = srgb_to_linear(rgb_in.z);
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) rgb[k] = rgb[k] > 0.0f ? rgb[k] : 0.0f;
     // (component > 1 panics in the reference; u8/255 texels and half-scaled illuminant colours never exceed 1)
@@ -492,9 +510,13 @@ __device__ __noinline__ float3 rgb_to_coeffs(const DScene& sc, float3 rgb_in) {
     const uint32_t xi = min(f2u_sat(x), 62u), yi = min(f2u_sat(y), 62u);
     // zi = first i with z_nodes[i+1] > z, else 62 (rgb_sigmoid_polynomial.rs:124-126); the nodes are increasing, so a
     // binary search over the same predicate returns the same index
-    uint32_t lo = 0, hi = 62;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&sc.z_nodes[mid + 1]) > z) hi = mid; else lo = mid + 1; }
-    const uint32_t zi = lo;
+    uint32_t zi;
+    if (HALF && h >= 0 && z == sc.half_lin) zi = (uint32_t)sc.half_zi;
+    else {
+        uint32_t lo = 0, hi = 62;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&sc.z_nodes[mid + 1]) > z) hi = mid; else lo = mid + 1; }
+        zi = lo;
+    }
     const float z0 = __ldg(&sc.z_nodes[zi]), z1 = __ldg(&sc.z_nodes[zi + 1]);
     const float dx = x - (float)xi, dy = y - (float)yi, dz = (z - z0) / (z1 - z0);
     const float* base = sc.rgb2spec + ((((size_t)m * 64 + zi) * 64 + yi) * 64 + xi) * 3;
@@ -510,6 +532,7 @@ __device__ __noinline__ float3 rgb_to_coeffs(const DScene& sc, float3 rgb_in) {
     }
     return f3(cs[0], cs[1], cs[2]);
 }
+__device__ __forceinline__ float3 rgb_to_coeffs(const DScene& sc, float3 rgb_in) { return rgb_to_coeffs_t<false>(sc, rgb_in); }
 
 // a resolved Spectrum (SpectrumTrait object) on the device
 struct DSpectrum { int kind; float c[3]; float scale; int table; };  // 0 const 1 sigmoid 2 sigmoid*scale*D65 3 D65 5 dense preset table
@@ -552,7 +575,7 @@ __device__ __forceinline__ DSpectrum illuminant_from_rgb(const DScene& sc, float
     DSpectrum s; s.kind = 2; s.table = 0;
     const float mx = rmax(rgb.x, rmax(rgb.y, rgb.z));
     s.scale = 2.0f * mx;
-    const float3 c = rgb_to_coeffs(sc, rgb / s.scale);
+    const float3 c = rgb_to_coeffs_t<TCPT_ILLUM_HALF != 0>(sc, rgb / s.scale);
     s.c[0] = c.x; s.c[1] = c.y; s.c[2] = c.z;
     return s;
 }

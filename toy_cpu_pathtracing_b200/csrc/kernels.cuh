@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(256) k_sobol_prefix(uint32_t* __restrict__ tab
     }
 }
 
+// DScene::half_lin / half_zi: srgb_to_linear(0.5f) and its z-node interval, evaluated by the code the lookups run (out = {bits of the value, index})
+__global__ void k_illum_half(const float* __restrict__ z_nodes, uint32_t* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const volatile float half_in = 0.5f;   // (volatile: evaluated at run time by the device's powf, not folded by the compiler's)
+    const float z = srgb_to_linear(half_in);
+    uint32_t lo = 0, hi = 62;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (z_nodes[mid + 1] > z) hi = mid; else lo = mid + 1; }
+    out[0] = __float_as_uint(z); out[1] = lo;
+}
+
 // builds DRender::sobol_hash
 __global__ void k_sobol_hash(unsigned long long* __restrict__ table, uint32_t seed) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;

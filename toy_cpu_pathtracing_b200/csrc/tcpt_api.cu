@@ -33,7 +33,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool traversal_only = false;   // built by tcpt_scene_build_soup: BVH and triangles only, nothing to shade with
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -99,6 +99,7 @@ struct tcpt_ctx {
     float* film_acc = nullptr; float* film_srgb = nullptr; size_t film_cap = 0;
     HostPin pins[2];
     // ZSobol pixel-prefix table (DSampler::sample_index), cached per (width, height, log2_spp); grows when more dimensions are asked for
+    float half_lin = 0.0f; int32_t half_zi = -1;   // DScene::half_lin / half_zi (tcpt_set_tables)
     void* trace_scratch = nullptr; size_t trace_scratch_cap = 0;   // device staging of tcpt_trace (rays in, hit records out), kept between calls
     unsigned long long* d_sobol_hash = nullptr; uint32_t sobol_hash_seed = 0; bool sobol_hash_valid = false;
     uint32_t* d_prefix = nullptr; uint32_t prefix_w = 0, prefix_h = 0, prefix_log2spp = 0, prefix_dims = 0, pass_rows = 0; size_t prefix_cap = 0;
@@ -614,6 +615,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "debug_path_log") ctx->opt.debug_path_log = value;
     else if (n == "sobol_prefix") ctx->opt.sobol_prefix = value;
     else if (n == "sobol_hash") ctx->opt.sobol_hash = value;
+    else if (n == "illum_half") ctx->opt.illum_half = value;
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
@@ -678,6 +680,14 @@ int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const
     if (!T.presets.empty()) CU(cudaMemcpy(ctx->d_presets, T.presets.data(), T.presets.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (!ctx->d_rgb2spec) CU(cudaMalloc((void**)&ctx->d_rgb2spec, rgb2spec_floats * sizeof(float)));
     CU(cudaMemcpy(ctx->d_rgb2spec, rgb2spec, rgb2spec_floats * sizeof(float), cudaMemcpyHostToDevice));
+    {   // srgb_to_linear(0.5f) and its z-node interval as the device evaluates them (DScene::half_lin / half_zi)
+        uint32_t* d_out = ctx->d_counters + 28;   // two scratch words of the counter block
+        k_illum_half<<<1, 32, 0, ctx->stream>>>(ctx->d_rgb2spec, d_out);
+        uint32_t h[2] = {0u, 0u};
+        CU(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(&ctx->half_lin, &h[0], 4); ctx->half_zi = (int32_t)h[1];
+    }
     return TCPT_OK;
 }
 
@@ -928,6 +938,7 @@ int tcpt_upload_flat_scene(tcpt_ctx* ctx, const tcpt_flat_scene* s) {
     UP(upload(ctx, db, de.data(), de.size(), &v.envs)); v.n_envs = s->n_envs;
 #undef UP
     v.cmf = ctx->d_cmf; v.z_nodes = ctx->d_rgb2spec; v.rgb2spec = ctx->d_rgb2spec + 64; v.presets = ctx->d_presets;
+    v.half_lin = ctx->half_lin; v.half_zi = ctx->opt.illum_half ? ctx->half_zi : -1;
     std::memcpy(v.xyz_to_rgb, ctx->xyz_to_rgb, sizeof v.xyz_to_rgb);
     // per-texel light-sampling table of every environment map (32 B per texel), filled on the device by the code it replaces
     if (ctx->opt.env_nee_table) {
