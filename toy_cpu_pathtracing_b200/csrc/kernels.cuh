@@ -118,6 +118,29 @@ __global__ void __launch_bounds__(256) k_env_nee_table(const __grid_constant__ D
 }
 
 // ---------------------------------------------------------------- K0 generate
+// camera ray of one path from its two sampler values (BoxFilter::sample + Camera::sample_ray / generate_ray, filter.rs:24-30, camera.rs:51-81)
+__device__ __forceinline__ void generate_store(const DRender& R, const DCamera& cam, const DState& st, uint32_t slot, uint32_t px, uint32_t py, float u, float2 uv, uint32_t dim_after) {
+    // NormalRenderer draws the pixel sample first and no wavelength (normal_renderer.rs:33-40); the AOV renderers do not push the ray forward
+    const bool aov = R.integrator >= TCPT_INTEGRATOR_ALBEDO;
+    const float lambda0 = 360.0f + u * (830.0f - 360.0f);  // SampledWavelengths::new_uniform (sampled_spectrum.rs:318-336)
+    const float fx = uv.x * 1.0f - 1.0f * 0.5f, fy = uv.y * 1.0f - 1.0f * 0.5f;
+    const float x = (float)px + fx + 0.5f, y = (float)py + fy + 0.5f;
+    const float dir_x = (2.0f * x / (float)R.width - 1.0f) * cam.aspect * cam.scale;
+    const float dir_y = (1.0f - 2.0f * y / (float)R.height) * cam.scale;
+    const float3 rd = normalize(f3(dir_x, dir_y, -1.0f));
+    const float3 d = normalize((cam.s * rd.x + cam.u * rd.y) + cam.nf * rd.z);
+    const float3 o = aov ? f3(0.0f, 0.0f, 0.0f) : f3(0.0f, 0.0f, 0.0f) + d * 1e-5f;  // move_forward(1e-5) (base_renderer.rs:177)
+    st.ext_o[0][slot] = make_float4(o.x, o.y, o.z, TCPT_FLT_MAX);
+    st.ext_d[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
+    // throughput = 1 and contribution = 0 are implied at bounce 0 (shade_vertex does not load them there): 32 B per path less each way
+    st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(dim_after), __uint_as_float(0u));
+}
+__device__ __forceinline__ void generate_reset(const DState& st, uint32_t n_slots) {
+    st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0;
+    for (int b = 0; b < 2 * TCPT_BUCKET_STRIDE; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
+    st.counters[24] = 0; st.counters[25] = 0;             // work counters of the persistent trace kernels
+    atomicAdd(&st.stats[4], (unsigned long long)n_slots);
+}
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DCamera cam,
                                                    const __grid_constant__ DState st, const __grid_constant__ PathList L, uint32_t n_slots) {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -125,31 +148,42 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DScene
         uint32_t px, py, si;
         path_coords(R, L, slot, &px, &py, &si);
         DSampler smp = make_sampler(R, px, py, si);
-        // NormalRenderer draws the pixel sample first and no wavelength (normal_renderer.rs:33-40); the AOV renderers do not push the ray forward
-        const bool aov = R.integrator >= TCPT_INTEGRATOR_ALBEDO;
         float u = 0.0f;
         if (R.integrator != TCPT_INTEGRATOR_NORMAL) u = smp.get_1d(R);
-        const float lambda0 = 360.0f + u * (830.0f - 360.0f);  // SampledWavelengths::new_uniform (sampled_spectrum.rs:318-336)
         const float2 uv = smp.get_2d(R);
-        // BoxFilter::sample + Camera::sample_ray / generate_ray (filter.rs:24-30, camera.rs:51-81)
-        const float fx = uv.x * 1.0f - 1.0f * 0.5f, fy = uv.y * 1.0f - 1.0f * 0.5f;
-        const float x = (float)px + fx + 0.5f, y = (float)py + fy + 0.5f;
-        const float dir_x = (2.0f * x / (float)R.width - 1.0f) * cam.aspect * cam.scale;
-        const float dir_y = (1.0f - 2.0f * y / (float)R.height) * cam.scale;
-        const float3 rd = normalize(f3(dir_x, dir_y, -1.0f));
-        const float3 d = normalize((cam.s * rd.x + cam.u * rd.y) + cam.nf * rd.z);
-        const float3 o = aov ? f3(0.0f, 0.0f, 0.0f) : f3(0.0f, 0.0f, 0.0f) + d * 1e-5f;  // move_forward(1e-5) (base_renderer.rs:177)
-        st.ext_o[0][slot] = make_float4(o.x, o.y, o.z, TCPT_FLT_MAX);
-        st.ext_d[0][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(slot));
-        // throughput = 1 and contribution = 0 are implied at bounce 0 (shade_vertex does not load them there): 32 B per path less each way
-        st.misc[slot] = make_float4(0.0f, lambda0, __uint_as_float(smp.dim), __uint_as_float(0u));
+        generate_store(R, cam, st, slot, px, py, u, uv, smp.dim);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        st.counters[0] = n_slots; st.counters[1] = 0; st.counters[2] = 0; st.counters[3] = 0;
-        for (int b = 0; b < 2 * TCPT_BUCKET_STRIDE; ++b) st.counters[4 + b] = 0;  // both sets of bucket sizes
-        st.counters[24] = 0; st.counters[25] = 0;             // work counters of the persistent trace kernels
-        atomicAdd(&st.stats[4], (unsigned long long)n_slots);
+    if (blockIdx.x == 0 && threadIdx.x == 0) generate_reset(st, n_slots);
+}
+// The same for a pass of the Z-Sobol sampler, one thread per PIXEL looping over the pass's sample indices (slot = sample * n_pix + pixel:
+// the stores of a warp stay contiguous): what a sampler call derives from the pixel alone -- its coordinates, the Morton prefix, the four
+// table entries, the two Owen-scramble seeds -- is fetched once per pixel instead of once per path.  Same functions, same values.
+__global__ void __launch_bounds__(256) k_generate_pixels(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DCamera cam,
+                                                          const __grid_constant__ DState st, uint32_t n_slots) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const SobolFrame f = DSampler::frame_of(R);
+    const bool with_lambda = R.integrator != TCPT_INTEGRATOR_NORMAL;
+    const uint32_t d_uv = with_lambda ? 1u : 0u;
+    const uint64_t h_u = DSampler::hash_of(1u, f), h_uv = DSampler::hash_of(d_uv + 2u, f);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < R.n_pix; p += stride) {
+        const uint32_t k = R.pix_begin + p;
+        const uint32_t row = div_magic(k, R.width_magic);
+        const uint32_t px = k - row * R.width, py = R.row_offset + row * R.row_stride;
+        const uint32_t pix = py * R.width + px;
+        const uint32_t pixel_morton = DSampler::morton_of(px, py, 0u, R.log2_spp);
+        const DSampler::SobolLoads l_u = DSampler::sample_index_loads(0u, pix, f), l_uv = DSampler::sample_index_loads(d_uv, pix, f);
+        for (uint32_t s = 0; s < R.s_count; ++s) {
+            const uint32_t morton = pixel_morton | (R.s_begin + s);
+            float u = 0.0f;
+            if (with_lambda) u = DSampler::to_unit(DSampler::owen(__brev((uint32_t)DSampler::sample_index_from(morton, 0u, f, l_u)), (uint32_t)h_u));
+            const uint64_t a = DSampler::sample_index_from(morton, d_uv, f, l_uv);
+            float2 uv;
+            uv.x = DSampler::to_unit(DSampler::owen(__brev((uint32_t)a), (uint32_t)h_uv));
+            uv.y = DSampler::to_unit(DSampler::owen(DSampler::sobol_dim1(a), (uint32_t)(h_uv >> 32)));
+            generate_store(R, cam, st, s * R.n_pix + p, px, py, u, uv, d_uv + 2u);
+        }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) generate_reset(st, n_slots);
 }
 
 // ---------------------------------------------------------------- K1 closest hit

@@ -33,7 +33,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool traversal_only = false;   // built by tcpt_scene_build_soup: BVH and triangles only, nothing to shade with
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, generate_pixels = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -370,7 +370,11 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
     const bool count = ctx->opt.count_tests != 0;
     {
         StageTimer t(ctx, STAGE_GENERATE, stream);
-        k_generate<<<grid_for(ctx, n_slots, 256), 256, 0, stream>>>(sc, R, cam, st, L, n_slots);
+        // a Z-Sobol pass over whole pixels: one thread per pixel (what the sampler derives from the pixel is fetched once); else one thread per path
+        if (ctx->opt.generate_pixels && L.xy == nullptr && R.sampler == TCPT_SAMPLER_SOBOL && R.s_count >= 2u && (uint64_t)R.n_pix * R.s_count == n_slots)
+            k_generate_pixels<<<grid_for(ctx, R.n_pix, 256), 256, 0, stream>>>(sc, R, cam, st, n_slots);
+        else
+            k_generate<<<grid_for(ctx, n_slots, 256), 256, 0, stream>>>(sc, R, cam, st, L, n_slots);
         ctx->stats.kernel_launches++;
     }
     const int g128 = grid_for(ctx, n_slots, 128);
@@ -616,6 +620,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "sobol_prefix") ctx->opt.sobol_prefix = value;
     else if (n == "sobol_hash") ctx->opt.sobol_hash = value;
     else if (n == "illum_half") ctx->opt.illum_half = value;
+    else if (n == "generate_pixels") ctx->opt.generate_pixels = value;
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
