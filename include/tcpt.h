@@ -117,7 +117,9 @@ const char* tcpt_last_error(const tcpt_ctx* ctx);
  * "sobol_hash" (1, default: the 64-bit Owen-scramble seeds of the sampler dimensions, a function of (dimension, seed) alone, are read from a
  * 4 KB table built when the seed changes; 0: hashed per sampler call), "illum_half" (1, default: the largest component of an illuminant colour is
  * exactly 0.5 after its normalisation, so its sRGB decoding and z-node interval are constants evaluated once on the device; 0: per lookup;
- * takes effect at the next scene upload),
+ * takes effect at the next scene upload), "generate_pixels" (1, default: camera rays of a Z-Sobol pass by one thread per pixel looping over the
+ * pass's samples; 0: one thread per path), "sobol_pass_cache" (1, default: the per-pass table is built incrementally from the permutation rows
+ * the previous pass left behind; 0: every row recomputed),
  * "fused_launches" (bit 0: shadow rays of one bounce and extension rays of the next in one launch, bit 1: all shading buckets in one
  * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "light_shortcut" (1: a scene whose
  * only light has strictly positive power skips the per-vertex light-power table, its selection probability being exactly 1), "env_nee_table" (1, default: per-texel table of what environment-light sampling computes from the drawn texel alone -- direction, pdf, illuminant

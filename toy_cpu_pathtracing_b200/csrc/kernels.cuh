@@ -104,6 +104,40 @@ __global__ void __launch_bounds__(256) k_sobol_pass(uint32_t* __restrict__ table
     }
 }
 
+// The same rows, built INCREMENTALLY.  The permutation row of digit i is keyed by the digits above i and the dimension; from one pass to the
+// next only the low sample digits of the table change, so most rows are the ones the previous pass computed.  Per (dimension, pixel) a cache
+// word keeps the rows of the digits iv .. top (5 bits each, at most four), the sample digits they were computed for (the tag) and iv; an
+// entry recomputes the rows below the highest digit that changed (all of them when the word is invalid) and always the row of digit iv - 1.
+// On consecutive 16-sample passes of a 4096-spp frame that is 1.33 hashes per entry instead of 5.  Same values: rows are pure functions of
+// their keys.  cache word: bit 31 valid | iv << 28 | tag << 20 | rows.
+__global__ void __launch_bounds__(256) k_sobol_pass_cached(uint32_t* __restrict__ table, const __grid_constant__ DRender R, uint32_t dims, uint32_t iv, uint32_t cache_row0) {
+    const size_t total = (size_t)R.n_pix * dims;
+    const uint32_t top = (R.log2_spp >> 1) - 1u, levels = top - iv + 1u;
+    const uint32_t tag_new = (R.s_begin >> (2u * iv)) & ((1u << (2u * levels)) - 1u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t dim = (uint32_t)(i / R.n_pix), p_local = (uint32_t)(i - (size_t)dim * R.n_pix);
+        const uint32_t k = R.pix_begin + p_local, row = k / R.width;
+        const uint32_t px = k - row * R.width, py = R.row_offset + row * R.row_stride;
+        const size_t col = (size_t)py * R.width + px;
+        const uint32_t morton = DSampler::morton_of(px, py, R.s_begin, R.log2_spp);
+        uint32_t* cache = table + (size_t)(cache_row0 + dim) * R.prefix_stride + col;
+        const uint32_t cw = *cache;
+        uint32_t stale = levels;   // rows of the digits iv .. iv + stale - 1 have to be recomputed
+        if ((cw >> 31) != 0u && ((cw >> 28) & 7u) == iv) { const uint32_t diff = ((cw >> 20) & 0xffu) ^ tag_new; stale = diff ? (31u - (uint32_t)__clz(diff)) >> 1 : 0u; }
+        uint32_t rows = cw & 0xfffffu;
+        const uint64_t dk = 0x55555555ull * (uint64_t)dim;
+        uint32_t c = 0u;
+        for (uint32_t j = 0; j < levels; ++j) {
+            const uint32_t sh = 2u * (iv + j);
+            if (j < stale) rows = (rows & ~(31u << (5u * j))) | (DSampler::perm_index(DSampler::mix_bits(((uint64_t)morton >> (sh + 2u)) ^ dk)) << (5u * j));
+            c |= DSampler::perm_digit((rows >> (5u * j)) & 31u, (morton >> sh) & 3u) << (2u * j);
+        }
+        const uint32_t p = DSampler::perm_index(DSampler::mix_bits(((uint64_t)morton >> (2u * iv)) ^ dk));
+        table[(size_t)(R.prefix_dims + dim) * R.prefix_stride + col] = c | (p << 16);
+        *cache = 0x80000000u | (iv << 28) | (tag_new << 20) | rows;
+    }
+}
+
 // builds DEnv::nee_table (once per scene upload): one thread per texel runs env_nee_texel, the code the shading kernels would run per sample
 __global__ void __launch_bounds__(256) k_env_nee_table(const __grid_constant__ DScene sc, uint32_t env_index, float4* __restrict__ table) {
     const DEnv& e = sc.envs[env_index];

@@ -33,7 +33,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool traversal_only = false;   // built by tcpt_scene_build_soup: BVH and triangles only, nothing to shade with
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, generate_pixels = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, generate_pixels = 1, sobol_pass_cache = 1, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -279,7 +279,7 @@ int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
     if (pass_rows > 255) pass_rows = 255;
     const bool same = ctx->d_prefix && ctx->prefix_w == R.width && ctx->prefix_h == R.height && ctx->prefix_log2spp == R.log2_spp && ctx->pass_rows == pass_rows;
     if (!same || ctx->prefix_dims < dims) {
-        const size_t need = n_pix * (dims + pass_rows);
+        const size_t need = n_pix * (dims + 2 * pass_rows);   // prefix rows, pass rows, cache rows of the incremental pass build
         if (need > ctx->prefix_cap) {
             if (ctx->d_prefix) { cudaStreamSynchronize(stream); cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr; ctx->prefix_cap = 0; }
             if (cudaMalloc((void**)&ctx->d_prefix, need * 4) != cudaSuccess) { cudaGetLastError(); ctx->prefix_dims = 0; return TCPT_OK; }  // no table: full loop
@@ -295,6 +295,7 @@ int ensure_sobol_prefix(tcpt_ctx* ctx, DRender& R, cudaStream_t stream) {
         float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); ctx->prefix_build_ms = ms; ctx->stats.sobol_prefix_ms = ms;
         cudaEventDestroy(a); cudaEventDestroy(b);
         CU(cudaGetLastError());
+        if (pass_rows) CU(cudaMemsetAsync(ctx->d_prefix + n_pix * (dims + pass_rows), 0, n_pix * pass_rows * 4, stream));   // cache words: invalid
         ctx->prefix_w = R.width; ctx->prefix_h = R.height; ctx->prefix_log2spp = R.log2_spp; ctx->prefix_dims = (uint32_t)dims; ctx->pass_rows = (uint32_t)pass_rows;
     }
     R.sobol_prefix = ctx->d_prefix; R.prefix_dims = ctx->prefix_dims; R.prefix_stride = (uint32_t)n_pix;
@@ -332,7 +333,12 @@ void build_sobol_pass(tcpt_ctx* ctx, DRender& Rp, cudaStream_t stream) {
     const size_t total = (size_t)Rp.n_pix * ctx->pass_rows;
     const int grid = (int)((total + 255) / 256 < (size_t)ctx->sm_count * 64 ? (total + 255) / 256 : (size_t)ctx->sm_count * 64);
     StageTimer t(ctx, STAGE_GENERATE, stream);
-    k_sobol_pass<<<grid, 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv);
+    // digits iv .. log2_spp / 2 - 1 of the sample index sit in the table: with one to four of them the rows are built incrementally
+    const uint32_t half = Rp.log2_spp >> 1;
+    if (ctx->opt.sobol_pass_cache && iv >= 1u && iv <= 7u && half >= iv + 1u && half - iv <= 4u)
+        k_sobol_pass_cached<<<grid, 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv, ctx->prefix_dims + ctx->pass_rows);
+    else
+        k_sobol_pass<<<grid, 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv);
     ctx->stats.kernel_launches++;
     Rp.pass_info = ctx->pass_rows | (iv << 8);
 }
@@ -621,6 +627,7 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "sobol_hash") ctx->opt.sobol_hash = value;
     else if (n == "illum_half") ctx->opt.illum_half = value;
     else if (n == "generate_pixels") ctx->opt.generate_pixels = value;
+    else if (n == "sobol_pass_cache") ctx->opt.sobol_pass_cache = value;
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
