@@ -414,6 +414,33 @@ struct DSampler {
         }
         return r;
     }
+    // the same with the lobe choice in front (a 1-D call at dimension d0): what the other material buckets draw on their usual way through a vertex
+    struct Draws4 { float2 a, b; float c, u0; };
+    __device__ __noinline__ static Draws4 sobol_draws4(uint32_t morton, uint32_t d0, uint32_t da, uint32_t db, uint32_t dc, uint32_t pix, const SobolFrame f) {
+        const SobolLoads l0 = sample_index_loads(d0, pix, f), la = sample_index_loads(da, pix, f), lb = sample_index_loads(db, pix, f), lc = sample_index_loads(dc, pix, f);
+        Draws4 r;
+        {
+            const uint64_t a = sample_index_from(morton, d0, f, l0);
+            r.u0 = to_unit(owen(__brev((uint32_t)a), (uint32_t)hash_of(d0 + 1u, f)));
+        }
+        {
+            const uint64_t a = sample_index_from(morton, da, f, la);
+            const uint64_t h = hash_of(da + 2u, f);
+            r.a.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+            r.a.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+        }
+        {
+            const uint64_t a = sample_index_from(morton, db, f, lb);
+            const uint64_t h = hash_of(db + 2u, f);
+            r.b.x = to_unit(owen(__brev((uint32_t)a), (uint32_t)h));
+            r.b.y = to_unit(owen(sobol_dim1(a), (uint32_t)(h >> 32)));
+        }
+        {
+            const uint64_t a = sample_index_from(morton, dc, f, lc);
+            r.c = to_unit(owen(__brev((uint32_t)a), (uint32_t)hash_of(dc + 1u, f)));
+        }
+        return r;
+    }
     // get_1d whose value the caller provably does not use: both samplers are pure functions of the dimension counter, so
     // advancing the counter is all that has to happen (the reference computes and discards the value)
     __device__ __forceinline__ void skip_1d() { dim += 1; }

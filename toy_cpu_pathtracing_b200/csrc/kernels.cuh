@@ -25,6 +25,9 @@
 #ifndef TCPT_SPLIT_PUSH
 #define TCPT_SPLIT_PUSH 0    // 1: the queue-append atomics of a vertex are issued, then the loads of the thread's next vertex, then the rays are stored.  Measured slower (31.73 vs 31.47 ms of shading per step): the 20 words of the pending rays stay live across the next vertex's loads
 #endif
+#ifndef TCPT_PBR_DRAWS4
+#define TCPT_PBR_DRAWS4 0    // 1: the other material buckets draw their four sampler calls at once (sobol_draws4).  Measured slower on scene 19 (31.52 vs 30.98 ms of shading per step: six more live values in kernels that already spill), neutral on scene 17
+#endif
 #ifndef TCPT_LAMBERT_DRAWS3
 #define TCPT_LAMBERT_DRAWS3 1
 #endif
@@ -380,10 +383,14 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     // Lambert under nee / mis with the Sobol sampler: the direction, the point on the light and Russian roulette sit at dimension offsets 1, 5
     // and 7 on the usual way through the vertex; all three are drawn here in one call (DSampler::sobol_draws3) and handed out below if the
     // dimension counter is where it was expected to be (otherwise the ordinary call runs: same values either way)
-    constexpr bool PRE = TCPT_LAMBERT_DRAWS3 && MT == TCPT_MAT_LAMBERT && !BucketInfo<B>::miss && !BucketInfo<B>::terminal;
-    DSampler::Draws3 pre; bool have_pre = false; const uint32_t pre_d0 = smp.dim;
+    constexpr bool NO_LOBE = MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL;   // these never read the lobe-choice number
+    constexpr bool PRE = !BucketInfo<B>::miss && !BucketInfo<B>::terminal && MT != TCPT_MAT_EMISSIVE && (MT == TCPT_MAT_LAMBERT ? TCPT_LAMBERT_DRAWS3 != 0 : TCPT_PBR_DRAWS4 != 0);
+    DSampler::Draws4 pre; bool have_pre = false; const uint32_t pre_d0 = smp.dim;
     if (PRE && R.sampler == TCPT_SAMPLER_SOBOL && R.integrator != TCPT_INTEGRATOR_PT && (FIRST || stage < R.max_depth)) {
-        pre = DSampler::sobol_draws3(smp.morton, pre_d0 + 1u, pre_d0 + 5u, pre_d0 + 7u, smp.pix, DSampler::frame_of(R));
+        if (NO_LOBE) {
+            const DSampler::Draws3 t = DSampler::sobol_draws3(smp.morton, pre_d0 + 1u, pre_d0 + 5u, pre_d0 + 7u, smp.pix, DSampler::frame_of(R));
+            pre.a = t.a; pre.b = t.b; pre.c = t.c; pre.u0 = 0.0f;
+        } else pre = DSampler::sobol_draws4(smp.morton, pre_d0, pre_d0 + 1u, pre_d0 + 5u, pre_d0 + 7u, smp.pix, DSampler::frame_of(R));
         have_pre = true;
     }
     S4 thr = s4(1.0f), con = s4(0.0f);
@@ -495,7 +502,9 @@ __device__ __forceinline__ void shade_vertex(const DScene& sc, const DRender& R,
     MatCtx mc; mc.sc = &sc; mc.path_key = smp.key; mc.depth = stage + 1;
     // `uc` only selects between lobes; LambertMaterial::sample and MetalMaterial::sample never read it (lambert_material.rs:42-97, metal_material.rs:124)
     float uc = 0.0f;
-    if (MT == TCPT_MAT_LAMBERT || MT == TCPT_MAT_METAL) smp.skip_1d(); else uc = smp.get_1d(R);
+    if (NO_LOBE) smp.skip_1d();
+    else if (PRE && have_pre && smp.dim == pre_d0) { uc = pre.u0; smp.dim += 1; }
+    else uc = smp.get_1d(R);
     float2 uv;
     if (PRE && have_pre && smp.dim == pre_d0 + 1u) { uv = pre.a; smp.dim += 2; } else uv = smp.get_2d(R);
     const bool was_terminated = wl.terminated;
