@@ -119,7 +119,9 @@ const char* tcpt_last_error(const tcpt_ctx* ctx);
  * exactly 0.5 after its normalisation, so its sRGB decoding and z-node interval are constants evaluated once on the device; 0: per lookup;
  * takes effect at the next scene upload), "generate_pixels" (1, default: camera rays of a Z-Sobol pass by one thread per pixel looping over the
  * pass's samples; 0: one thread per path), "sobol_pass_cache" (1, default: the per-pass table is built incrementally from the permutation rows
- * the previous pass left behind; 0: every row recomputed),
+ * the previous pass left behind; 0: every row recomputed), "refill_b0" / "refill" (1..32: idle lanes at which a warp of the persistent
+ * traversal kernel fetches new rays, for the camera-ray launch / the later ones; default 32 / 16: camera rays are coherent, a warp that
+ * traces 32 of them to the end also files them into the shading buckets in pixel order),
  * "fused_launches" (bit 0: shadow rays of one bounce and extension rays of the next in one launch, bit 1: all shading buckets in one
  * launch from bounce "fused_shade_from" on; default 3 / 3; 0 = one launch per queue and per bucket), "light_shortcut" (1: a scene whose
  * only light has strictly positive power skips the per-vertex light-power table, its selection probability being exactly 1), "env_nee_table" (1, default: per-texel table of what environment-light sampling computes from the drawn texel alone -- direction, pdf, illuminant

@@ -383,7 +383,9 @@ struct Traversal {
 };
 
 #ifndef TCPT_REFILL_IDLE_LANES
-#define TCPT_REFILL_IDLE_LANES 16  // a warp fetches new rays once this many of its lanes are idle (4-wide tree, eager advance: 8 / 12 / 16 / 20 give 31.8 / 30.4 / 29.9 / 30.0 ms of tracing per step)
+#define TCPT_REFILL_IDLE_LANES 16  // a warp fetches new rays once this many of its lanes are idle (4-wide tree, eager advance: 8 / 12 / 16 / 20 give 31.8 / 30.4 / 29.9 / 30.0 ms of tracing per step).
+                                   // The threshold is a kernel argument (options "refill_b0", "refill"): the camera-ray launch runs with 32, i.e. a warp traces 32 consecutive rays to the end
+                                   // (12 / 16 / 20 / 24 / 32 there: 29.80 / 29.68 / 29.48 / 29.32 / 29.39 ms of tracing, and with 32 the bounce-0 shading reads its vertices in pixel order: 31.0 -> 30.65 ms)
 #endif
 #ifndef TCPT_TRI_PHASE_LANES
 #define TCPT_TRI_PHASE_LANES 8    // a warp runs a triangle iteration once this many lanes hold pending triangles (4 / 8 / 12: 31.4 / 30.4 / 30.9 ms; no vote at all, both phases every iteration: 31.2)
@@ -411,7 +413,7 @@ template <class F> __device__ __forceinline__ CommitNow<F> commit_now(F f) { ret
 // Every warp of the grid must call this with all 32 lanes; blocks are 128 threads (TraceShared).
 template <bool ANY, bool COUNT, class Commit>
 __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
-                                            uint32_t* work, uint32_t* n_box, uint32_t* n_tri, Commit&& commit) {
+                                            uint32_t* work, uint32_t* n_box, uint32_t* n_tri, Commit&& commit, uint32_t refill_lanes = (uint32_t)TCPT_REFILL_IDLE_LANES) {
     const uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
     uint32_t stack[TCPT_LOCAL_STACK];
@@ -486,7 +488,7 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
 #endif
         const bool exhausted = drained && pool >= pool_end;
         if (__ballot_sync(FULL, ray != NONE) == 0u) break;  // nothing in flight and nothing left to fetch
-        const uint32_t stop_at = exhausted ? 32u : (uint32_t)TCPT_REFILL_IDLE_LANES;
+        const uint32_t stop_at = exhausted ? 32u : refill_lanes;
         uint32_t n_idle_now;
         do {
             const bool has_tri = ray != NONE && T.holds_triangles();

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__
 // `cur` = parity of the extension queue to trace, `sh` = index (2 or 3) of the shadow-queue size to read; the sizes the next
 // k_shade appends to (counters[cur ^ 1], counters[sh ^ 1]) were last read one launch ago and are reset here.
 template <bool COUNT>
-__global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh) {
+__global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh, uint32_t refill_lanes) {
     const uint32_t n_sh = st.counters[sh], n = st.counters[cur];
     uint32_t* bcount = st.counters + 4 + TCPT_BUCKET_STRIDE * cur;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -341,9 +341,9 @@ __global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(cons
     __shared__ TraceShared ts;
     // (shadow first: it is the shorter queue.  Letting half of the blocks start on the extension queue so that short queues are
     // walked side by side was measured slower: 16.6 vs 15.3 ms per 33 M paths.)
-    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, CommitShadow{sc, R, st});
+    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, CommitShadow{sc, R, st}, refill_lanes);
     float4* __restrict__ hit0 = st.hit0; uint2* __restrict__ hit1 = st.hit1;
-    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, CommitClosest{sc, st, st.ext_d[cur], hit0, hit1, bcount});
+    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, CommitClosest{sc, st, st.ext_d[cur], hit0, hit1, bcount}, refill_lanes);
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 
