@@ -36,6 +36,9 @@
 #define TCPT_MIN_CHUNK 32         // smallest block of ray indices a warp reserves at a time
 #endif
 static_assert(TCPT_MIN_CHUNK >= 32, "a refill hands the idle lanes of a warp consecutive indices of ONE chunk: it must cover a whole warp");
+#ifndef TCPT_ANYHIT_UNSORTED
+#define TCPT_ANYHIT_UNSORTED 1
+#endif
 #ifndef TCPT_POP_CULL
 #define TCPT_POP_CULL 1           // closest hit: a stack entry carries the entry distance of its box and is dropped when it comes off the stack behind the best hit
 #endif
@@ -344,10 +347,14 @@ struct Traversal {
         float k0 = h0 ? te0 : TCPT_INF, k1 = h1 ? te1 : TCPT_INF, k2 = h2 ? te2 : TCPT_INF, k3 = h3 ? te3 : TCPT_INF;
         uint32_t e0 = h0 ? ent.x : TCPT_ENTRY_NONE, e1 = h1 ? ent.y : TCPT_ENTRY_NONE, e2 = h2 ? ent.z : TCPT_ENTRY_NONE, e3 = h3 ? ent.w : TCPT_ENTRY_NONE;
 #define TCPT_CE(ka, ea, kb, eb) { const bool sw = kb < ka; const float kt = sw ? kb : ka; kb = sw ? ka : kb; ka = kt; const uint32_t et = sw ? eb : ea; eb = sw ? ea : eb; ea = et; }
-        TCPT_CE(k0, e0, k1, e1) TCPT_CE(k2, e2, k3, e3) TCPT_CE(k0, e0, k2, e2)
+        // (any hit: the answer does not depend on the order of the walk, and a ray that reaches its light -- most do -- visits every box it
+        // passes whatever the order: no ordering network)
+        if (!ANY || !TCPT_ANYHIT_UNSORTED) {
+            TCPT_CE(k0, e0, k1, e1) TCPT_CE(k2, e2, k3, e3) TCPT_CE(k0, e0, k2, e2)
 #if TCPT_SORT_FULL
-        TCPT_CE(k1, e1, k3, e3) TCPT_CE(k1, e1, k2, e2)
+            TCPT_CE(k1, e1, k3, e3) TCPT_CE(k1, e1, k2, e2)
 #endif
+        }
 #undef TCPT_CE
         if (e3 != TCPT_ENTRY_NONE) push<ANY>(S, tid, stack, stack_t, e3, k3);
         if (e2 != TCPT_ENTRY_NONE) push<ANY>(S, tid, stack, stack_t, e2, k2);
