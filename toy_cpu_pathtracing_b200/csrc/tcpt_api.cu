@@ -701,6 +701,8 @@ int tcpt_set_tables(tcpt_ctx* ctx, const void* std_tables, size_t std_len, const
         CU(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         std::memcpy(&ctx->half_lin, &h[0], 4); ctx->half_zi = (int32_t)h[1];
+        // a scene uploaded before the tables were replaced keeps reading the table allocations in place: its constants follow
+        if (ctx->dev.valid) { ctx->dev.view.half_lin = ctx->half_lin; ctx->dev.view.half_zi = ctx->opt.illum_half ? ctx->half_zi : -1; }
     }
     return TCPT_OK;
 }
