@@ -420,7 +420,7 @@ template <class F> __device__ __forceinline__ CommitNow<F> commit_now(F f) { ret
 // Every warp of the grid must call this with all 32 lanes; blocks are 128 threads (TraceShared).
 template <bool ANY, bool COUNT, class Commit>
 __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, uint32_t n,
-                                            uint32_t* work, uint32_t* n_box, uint32_t* n_tri, Commit&& commit, uint32_t refill_lanes = (uint32_t)TCPT_REFILL_IDLE_LANES) {
+                                            uint32_t* work, uint32_t* n_box, uint32_t* n_tri, Commit&& commit, uint32_t refill_lanes = (uint32_t)TCPT_REFILL_IDLE_LANES, uint32_t max_chunk = 512u) {
     const uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
     uint32_t stack[TCPT_LOCAL_STACK];
@@ -437,7 +437,7 @@ __device__ __forceinline__ void trace_queue(const DScene& sc, TraceShared& S, co
     // The chunk shrinks with the queue so that short queues (deep bounces) still spread over the whole grid.
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     uint32_t chunk = n / (n_warps * 8u);
-    chunk = chunk < (uint32_t)TCPT_MIN_CHUNK ? (uint32_t)TCPT_MIN_CHUNK : (chunk > 512u ? 512u : chunk);
+    chunk = chunk < (uint32_t)TCPT_MIN_CHUNK ? (uint32_t)TCPT_MIN_CHUNK : (chunk > max_chunk ? max_chunk : chunk);
     uint32_t pool = 0, pool_end = 0;  // warp-uniform: indices [pool, pool_end) belong to this warp
     bool drained = false;             // the global counter has passed n
     for (;;) {

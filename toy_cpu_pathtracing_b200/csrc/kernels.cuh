@@ -114,30 +114,31 @@ __global__ void __launch_bounds__(256) k_sobol_pass(uint32_t* __restrict__ table
 // On consecutive 16-sample passes of a 4096-spp frame that is 1.33 hashes per entry instead of 5.  Same values: rows are pure functions of
 // their keys.  cache word: bit 31 valid | iv << 28 | tag << 20 | rows.
 __global__ void __launch_bounds__(256) k_sobol_pass_cached(uint32_t* __restrict__ table, const __grid_constant__ DRender R, uint32_t dims, uint32_t iv, uint32_t cache_row0) {
-    const size_t total = (size_t)R.n_pix * dims;
     const uint32_t top = (R.log2_spp >> 1) - 1u, levels = top - iv + 1u;
     const uint32_t tag_new = (R.s_begin >> (2u * iv)) & ((1u << (2u * levels)) - 1u);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t dim = (uint32_t)(i / R.n_pix), p_local = (uint32_t)(i - (size_t)dim * R.n_pix);
-        const uint32_t k = R.pix_begin + p_local, row = k / R.width;
+    // one thread per PIXEL, looping over the dimensions: coordinates and Morton code once per pixel; a warp's accesses to a row stay contiguous
+    for (uint32_t p_local = blockIdx.x * blockDim.x + threadIdx.x; p_local < R.n_pix; p_local += gridDim.x * blockDim.x) {
+        const uint32_t k = R.pix_begin + p_local, row = div_magic(k, R.width_magic);
         const uint32_t px = k - row * R.width, py = R.row_offset + row * R.row_stride;
         const size_t col = (size_t)py * R.width + px;
         const uint32_t morton = DSampler::morton_of(px, py, R.s_begin, R.log2_spp);
-        uint32_t* cache = table + (size_t)(cache_row0 + dim) * R.prefix_stride + col;
-        const uint32_t cw = *cache;
-        uint32_t stale = levels;   // rows of the digits iv .. iv + stale - 1 have to be recomputed
-        if ((cw >> 31) != 0u && ((cw >> 28) & 7u) == iv) { const uint32_t diff = ((cw >> 20) & 0xffu) ^ tag_new; stale = diff ? (31u - (uint32_t)__clz(diff)) >> 1 : 0u; }
-        uint32_t rows = cw & 0xfffffu;
-        const uint64_t dk = 0x55555555ull * (uint64_t)dim;
-        uint32_t c = 0u;
-        for (uint32_t j = 0; j < levels; ++j) {
-            const uint32_t sh = 2u * (iv + j);
-            if (j < stale) rows = (rows & ~(31u << (5u * j))) | (DSampler::perm_index(DSampler::mix_bits(((uint64_t)morton >> (sh + 2u)) ^ dk)) << (5u * j));
-            c |= DSampler::perm_digit((rows >> (5u * j)) & 31u, (morton >> sh) & 3u) << (2u * j);
+        for (uint32_t dim = 0; dim < dims; ++dim) {
+            uint32_t* cache = table + (size_t)(cache_row0 + dim) * R.prefix_stride + col;
+            const uint32_t cw = *cache;
+            uint32_t stale = levels;   // rows of the digits iv .. iv + stale - 1 have to be recomputed
+            if ((cw >> 31) != 0u && ((cw >> 28) & 7u) == iv) { const uint32_t diff = ((cw >> 20) & 0xffu) ^ tag_new; stale = diff ? (31u - (uint32_t)__clz(diff)) >> 1 : 0u; }
+            uint32_t rows = cw & 0xfffffu;
+            const uint64_t dk = 0x55555555ull * (uint64_t)dim;
+            uint32_t c = 0u;
+            for (uint32_t j = 0; j < levels; ++j) {
+                const uint32_t sh = 2u * (iv + j);
+                if (j < stale) rows = (rows & ~(31u << (5u * j))) | (DSampler::perm_index(DSampler::mix_bits(((uint64_t)morton >> (sh + 2u)) ^ dk)) << (5u * j));
+                c |= DSampler::perm_digit((rows >> (5u * j)) & 31u, (morton >> sh) & 3u) << (2u * j);
+            }
+            const uint32_t p = DSampler::perm_index(DSampler::mix_bits(((uint64_t)morton >> (2u * iv)) ^ dk));
+            table[(size_t)(R.prefix_dims + dim) * R.prefix_stride + col] = c | (p << 16);
+            *cache = 0x80000000u | (iv << 28) | (tag_new << 20) | rows;
         }
-        const uint32_t p = DSampler::perm_index(DSampler::mix_bits(((uint64_t)morton >> (2u * iv)) ^ dk));
-        table[(size_t)(R.prefix_dims + dim) * R.prefix_stride + col] = c | (p << 16);
-        *cache = 0x80000000u | (iv << 28) | (tag_new << 20) | rows;
     }
 }
 
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(128, 6) k_trace_shadow(const __grid_constant__
 // `cur` = parity of the extension queue to trace, `sh` = index (2 or 3) of the shadow-queue size to read; the sizes the next
 // k_shade appends to (counters[cur ^ 1], counters[sh ^ 1]) were last read one launch ago and are reset here.
 template <bool COUNT>
-__global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh, uint32_t refill_lanes) {
+__global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(const __grid_constant__ DScene sc, const __grid_constant__ DRender R, const __grid_constant__ DState st, int cur, int sh, uint32_t refill_lanes, uint32_t max_chunk) {
     const uint32_t n_sh = st.counters[sh], n = st.counters[cur];
     uint32_t* bcount = st.counters + 4 + TCPT_BUCKET_STRIDE * cur;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -341,9 +342,9 @@ __global__ void __launch_bounds__(128, TCPT_TRACE_MIN_BLOCKS) k_trace_fused(cons
     __shared__ TraceShared ts;
     // (shadow first: it is the shorter queue.  Letting half of the blocks start on the extension queue so that short queues are
     // walked side by side was measured slower: 16.6 vs 15.3 ms per 33 M paths.)
-    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, CommitShadow{sc, R, st}, refill_lanes);
+    if (n_sh) trace_queue<true, COUNT>(sc, ts, st.sh_o, st.sh_d, n_sh, &st.counters[25], &nb, &nt, CommitShadow{sc, R, st}, refill_lanes, max_chunk);
     float4* __restrict__ hit0 = st.hit0; uint2* __restrict__ hit1 = st.hit1;
-    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, CommitClosest{sc, st, st.ext_d[cur], hit0, hit1, bcount}, refill_lanes);
+    if (n) trace_queue<false, COUNT>(sc, ts, st.ext_o[cur], st.ext_d[cur], n, &st.counters[24], &nb, &nt, CommitClosest{sc, st, st.ext_d[cur], hit0, hit1, bcount}, refill_lanes, max_chunk);
     if (COUNT) { atomicAdd(&st.stats[2], (unsigned long long)nb); atomicAdd(&st.stats[3], (unsigned long long)nt); }
 }
 

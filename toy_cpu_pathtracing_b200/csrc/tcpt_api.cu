@@ -33,7 +33,7 @@ struct DeviceBuffers {  // one flattened scene on the device
     bool traversal_only = false;   // built by tcpt_scene_build_soup: BVH and triangles only, nothing to shade with
 };
 
-struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, generate_pixels = 1, sobol_pass_cache = 1, refill_b0 = 32, refill = TCPT_REFILL_IDLE_LANES, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
+struct Options { int count_tests = 0, stage_timing = 0, blocks_per_sm = 8, pin_host_buffers = 0, debug_path_log = 0, sobol_prefix = 1, sobol_prefix_mb = 8192, sobol_pass = 1, sobol_pass_dims = 11, sobol_hash = 1, illum_half = 1, generate_pixels = 1, sobol_pass_cache = 1, refill_b0 = 32, refill = TCPT_REFILL_IDLE_LANES, chunk_b0 = 512, chunk = 512, fused_launches = 3, fused_shade_from = 3, light_shortcut = 1, env_nee_table = 1, soup_leaf = 1; };
 struct HostPin { void* ptr = nullptr; size_t bytes = 0; };
 
 }  // namespace
@@ -336,7 +336,7 @@ void build_sobol_pass(tcpt_ctx* ctx, DRender& Rp, cudaStream_t stream) {
     // digits iv .. log2_spp / 2 - 1 of the sample index sit in the table: with one to four of them the rows are built incrementally
     const uint32_t half = Rp.log2_spp >> 1;
     if (ctx->opt.sobol_pass_cache && iv >= 1u && iv <= 7u && half >= iv + 1u && half - iv <= 4u)
-        k_sobol_pass_cached<<<grid, 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv, ctx->prefix_dims + ctx->pass_rows);
+        k_sobol_pass_cached<<<grid_for(ctx, Rp.n_pix, 256), 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv, ctx->prefix_dims + ctx->pass_rows);
     else
         k_sobol_pass<<<grid, 256, 0, stream>>>(ctx->d_prefix, Rp, ctx->pass_rows, iv);
     ctx->stats.kernel_launches++;
@@ -389,8 +389,8 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
 #define TCPT_SHADE_LAUNCH(...) k_shade<__VA_ARGS__><<<shade_grid(ShadeCfg<TCPT_FIRST_ARG(__VA_ARGS__)>::threads), ShadeCfg<TCPT_FIRST_ARG(__VA_ARGS__)>::threads, 0, stream>>>(sc, R, st, L, cur, sh, stage)
 #define TCPT_FIRST_ARG(a, ...) a
     if (R.integrator >= TCPT_INTEGRATOR_ALBEDO) {  // AOV renderers: one camera ray per sample, no bounces
-        if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3, (uint32_t)ctx->opt.refill_b0);
-        else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3, (uint32_t)ctx->opt.refill_b0);
+        if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3, (uint32_t)ctx->opt.refill_b0, (uint32_t)ctx->opt.chunk_b0);
+        else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, 0, 3, (uint32_t)ctx->opt.refill_b0, (uint32_t)ctx->opt.chunk_b0);
         k_aov<<<g128, 128, 0, stream>>>(sc, R, st);
         ctx->stats.kernel_launches += 2; ctx->stats.trace_launches++; ctx->stats.shade_launches++;
     } else {
@@ -408,8 +408,8 @@ int run_pass(tcpt_ctx* ctx, const DRender& R, const DCamera& cam, const PathList
         {
             StageTimer t(ctx, STAGE_CLOSEST, stream);
             if (fuse_trace) {
-                if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, cur, sh_prev, (uint32_t)(stage == 0 ? ctx->opt.refill_b0 : ctx->opt.refill));
-                else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, cur, sh_prev, (uint32_t)(stage == 0 ? ctx->opt.refill_b0 : ctx->opt.refill));
+                if (count) k_trace_fused<true><<<g128, 128, 0, stream>>>(sc, R, st, cur, sh_prev, (uint32_t)(stage == 0 ? ctx->opt.refill_b0 : ctx->opt.refill), (uint32_t)(stage == 0 ? ctx->opt.chunk_b0 : ctx->opt.chunk));
+                else k_trace_fused<false><<<g128, 128, 0, stream>>>(sc, R, st, cur, sh_prev, (uint32_t)(stage == 0 ? ctx->opt.refill_b0 : ctx->opt.refill), (uint32_t)(stage == 0 ? ctx->opt.chunk_b0 : ctx->opt.chunk));
             } else {
                 if (count) k_trace_closest<true><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
                 else k_trace_closest<false><<<g128, 128, 0, stream>>>(sc, st.ext_o[cur], st.ext_d[cur], st.hit0, st.hit1, st, cur);
@@ -630,6 +630,8 @@ int tcpt_set_option(tcpt_ctx* ctx, const char* name, int value) {
     else if (n == "sobol_pass_cache") ctx->opt.sobol_pass_cache = value;
     else if (n == "refill_b0") ctx->opt.refill_b0 = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (n == "refill") ctx->opt.refill = value < 1 ? 1 : (value > 32 ? 32 : value);
+    else if (n == "chunk_b0") ctx->opt.chunk_b0 = value < 32 ? 32 : value;
+    else if (n == "chunk") ctx->opt.chunk = value < 32 ? 32 : value;
     else if (n == "fused_launches") ctx->opt.fused_launches = value;
     else if (n == "fused_shade_from") ctx->opt.fused_shade_from = value;
     else if (n == "light_shortcut") ctx->opt.light_shortcut = value;   // takes effect at the next scene upload
