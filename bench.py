@@ -214,7 +214,7 @@ class CpuArm:
         k, spp, _ = cpu_sample(wl, max(2000.0, want_paths))
         # the oracle's frame loop runs p.spp samples per pixel with the sampler sized for p.spp; throughput does not depend on which
         # low-discrepancy points are drawn, so the sample renders `spp` samples with the sampler sized for them
-        p = self.osc.params(wl["width"], wl["height"], spp, wl["integrator"], wl["sampler"], self.cam, threads=self.threads, stride=k)
+        p = self.osc.params(wl["width"], wl["height"], spp, wl["integrator"], wl["sampler"], self.cam, threads=self.threads, stride=k, max_depth=wl.get("max_depth", 16))
         _, _, st = self.osc.render(p)
         return st, k, spp
 
@@ -792,7 +792,7 @@ def soup_reference(args, wl):
 
 def main():
     args = parse()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload], max_depth=args.max_depth)
     if args.impl == "reference":
         return main_reference(args, wl)
     return main_gpu(args, wl)
